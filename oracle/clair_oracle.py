@@ -1,0 +1,394 @@
+"""CPU oracle (numpy) for the per-pixel radiometric hot path of samivout/clair-torch.
+
+TEST INFRASTRUCTURE ONLY.  This module is a closed-form CPU restatement of the
+reference's algorithm; it exists to check the CUDA path.  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s CPU-baseline legs may import it.
+The product package (`clair_torch_b200`) never imports anything from `oracle/`.
+
+Parity status: PINNED.  `tests/test_oracle_golden.py` checks every function
+here against fixtures under `tests/golden/` that were produced by running the
+unmodified reference (see `tests/golden/make_golden.py`), including the
+known-answer vectors of the reference's own unit tests.
+
+The reference evaluates everything through chains of ATen ops plus
+`torch.autograd`; here the same quantities are written in closed form (no
+autograd).  Where a result decides an integer (LUT index, validity mask) the
+arithmetic is done in float32 in the reference's op order so that it is
+bit-exact; everything else is float64, which the reference's own mixed
+fp32/fp64 results agree with to ~5e-6.
+
+All `file:line` citations are relative to the reference repository root.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+F32 = np.float32
+F64 = np.float64
+
+HDR_WEIGHT_SCALE = 30.0   # training/losses.py:193 default, used by inference/hdr_merge.py:95
+PAIR_WEIGHT_SCALE = 10.0  # training/losses.py:212 default
+
+
+# ----------------------------------------------------------------------------------------------
+# ICRF evaluation
+# ----------------------------------------------------------------------------------------------
+def curve_rows(shape, flat_offset=0):
+    """Row of the (C, L) table each element of a contiguous (..., C, H, W) batch reads in LINEAR mode.
+
+    models/base.py:173-176 pairs the NCHW-flattened indices with `arange(C).repeat(N*H*W)`, so the
+    element with flat index k uses row `k mod C` rather than its own channel.
+    `flat_offset` is the flat index of this array's first element inside the full batch tensor
+    (non-zero only for a spatial shard of a larger image).
+    """
+    n_elem = int(np.prod(shape))
+    c = shape[-3]
+    return ((np.arange(n_elem, dtype=np.int64) + int(flat_offset)) % c).reshape(shape)
+
+
+def icrf_linear(x, theta, flat_offset=0, rows=None):
+    """LINEAR-mode ICRF, models/base.py:160-182, and its autograd derivative d f / d x.
+
+    Returns (f, fprime, x0, rows): f and fprime float32 (bit-exact with the reference), x0 the lower
+    LUT index (int64), rows the table row used per element.
+    """
+    x = np.ascontiguousarray(x, dtype=F32)
+    theta = np.asarray(theta, dtype=F32)
+    n_rows, l = theta.shape
+    lm1 = F32(l - 1)
+    xs_raw = x * lm1                                     # :167 (fp32 multiply)
+    xs = np.minimum(np.maximum(xs_raw, F32(0)), lm1)     # :167 clamp_
+    x0 = np.floor(xs).astype(np.int64)                   # :169
+    x1 = np.minimum(x0 + 1, l - 1)                       # :170
+    w = xs - x0.astype(F32)                              # :171
+    if rows is None:
+        rows = curve_rows(x.shape, flat_offset)
+    g0 = theta[rows, x0]
+    g1 = theta[rows, x1]
+    f = g0 * (F32(1.0) - w) + g1 * w                     # :182, separate fp32 roundings
+    inside = (xs_raw >= F32(0)) & (xs_raw <= lm1)        # clamp backward passes grad on the closed range
+    fprime = np.where(inside, (g1 - g0) * lm1, F32(0)).astype(F32)
+    return f.astype(F32), fprime, x0, rows
+
+
+def icrf_lookup(x, theta):
+    """LOOKUP-mode ICRF, models/base.py:138-158: round-half-even index, true channel row."""
+    x = np.ascontiguousarray(x, dtype=F32)
+    theta = np.asarray(theta, dtype=F32)
+    l = theta.shape[1]
+    idx = np.clip(np.rint(x * F32(l - 1)), 0, l - 1).astype(np.int64)   # :145
+    c = x.shape[-3]
+    chan = np.arange(c).reshape((c, 1, 1))
+    chan = np.broadcast_to(chan, x.shape)
+    return theta[chan, idx], idx
+
+
+def gaussian_value_weights(x, scale=HDR_WEIGHT_SCALE):
+    """training/losses.py:193-205 in float32."""
+    x = np.asarray(x, dtype=F32)
+    d = x - F32(0.5)
+    return np.exp(F32(-scale) * (d * d)).astype(F32)
+
+
+# ----------------------------------------------------------------------------------------------
+# HDR merge with first-order uncertainty
+# ----------------------------------------------------------------------------------------------
+class HdrState:
+    """Running state of the merge: WBOMean's (mean, sum_of_weights) plus the running variance.
+
+    common/statistics.py:27-29 starts both at the python float 0.0; inference/hdr_merge.py:55
+    starts the variance at None.
+    """
+
+    def __init__(self):
+        self.mean = None     # float64 (C,H,W)
+        self.wsum = None     # float64 here; float32 in the reference
+        self.var = None      # float64 here; float32 in the reference
+
+
+def hdr_merge_update(state, val, std, exposure, theta=None, gaussian=True, flat_offset=0):
+    """One DataLoader batch of compute_hdr_image (inference/hdr_merge.py:95-128).
+
+    val, std: (N,C,H,W) float32 (std may be None); exposure: (N,) float64 seconds; theta (C,L) or None
+    (`icrf_model=None` => identity, :99-100).  `gaussian` mirrors `weight_fn is not None` (:95).
+
+    Closed form of the autograd pass at :107-115:
+      w_n = exp(-30 (x_n-.5)^2) | 1,   v_n = f(x_n)/t_n,   W_B = sum w_n,   mean_B = sum w_n v_n / (W_B+1e-6)
+      W = W_A + W_B,   mean = mean_A + (W_B/W)(mean_B - mean_A)                    (statistics.py:74-109)
+      g_n = d mean / d x_n = (W_B/W) [w_n f'_n/t_n + w'_n (v_n-mean_B)]/(W_B+1e-6) + w'_n (W_A/W^2)(mean_B-mean_A)
+      var += sum_n (g_n s_n)^2                                                        (hdr_merge.py:114-115)
+    """
+    val = np.ascontiguousarray(val, dtype=F32)
+    n = val.shape[0]
+    t = np.asarray(exposure, dtype=F64).reshape(n, 1, 1, 1)
+    if theta is not None:
+        f32, fp32_, _, _ = icrf_linear(val, theta, flat_offset)
+        f = f32.astype(F64)
+        fp = fp32_.astype(F64)
+    else:
+        f = val.astype(F64)
+        fp = np.ones_like(f)
+    x = val.astype(F64)
+    if gaussian:
+        w = gaussian_value_weights(val, HDR_WEIGHT_SCALE).astype(F64)
+        wp = -2.0 * HDR_WEIGHT_SCALE * (x - 0.5) * w
+    else:
+        w = np.ones_like(f)
+        wp = np.zeros_like(f)
+    v = f / t
+    w_b = w.sum(axis=0)
+    mean_b = (w * v).sum(axis=0) / (w_b + 1e-6)
+    if state.mean is None:
+        w_a = np.zeros_like(w_b)
+        mean_a = np.zeros_like(mean_b)
+    else:
+        w_a, mean_a = state.wsum, state.mean
+    w_tot = w_a + w_b
+    frac = w_b / w_tot
+    mean_new = mean_a + frac * (mean_b - mean_a)
+    if std is not None:
+        s = np.asarray(std, dtype=F32).astype(F64)
+        dmean_b = (w * fp / t + wp * (v - mean_b)) / (w_b + 1e-6)
+        g = frac * dmean_b + wp * (w_a / (w_tot * w_tot)) * (mean_b - mean_a)
+        upd = ((g * s) ** 2).sum(axis=0)
+        state.var = upd if state.var is None else state.var + upd
+    state.mean, state.wsum = mean_new, w_tot
+    return state
+
+
+def hdr_merge(val, std, exposure, theta=None, gaussian=True, batch_size=None, flat_offset=0):
+    """compute_hdr_image (inference/hdr_merge.py:19-155) without flat/dark-field branches.
+
+    The stack is assumed sorted by ascending exposure inside each batch (datasets/collate.py:23).
+    Returns (radiance float64 (C,H,W), sigma float64 or None).
+    """
+    n = val.shape[0]
+    bs = n if batch_size is None else int(batch_size)
+    st = HdrState()
+    for a in range(0, n, bs):
+        sl = slice(a, min(a + bs, n))
+        hdr_merge_update(st, val[sl], None if std is None else std[sl], np.asarray(exposure)[sl], theta,
+                         gaussian, flat_offset)
+    sigma = None if st.var is None else np.sqrt(st.var)
+    return st.mean, sigma
+
+
+def linearize(val, std, theta, flat_offset=0):
+    """linearize_dataset_generator core for one (1,C,H,W) image (inference/linearization.py:94-106,132).
+
+    Returns (f float32, sigma float32) with sigma = sqrt((f'(x) s)^2); zeros when std is None (:97).
+    """
+    f, fp, _, _ = icrf_linear(val, theta, flat_offset)
+    if std is None:
+        return f, np.zeros_like(f)
+    g = fp * np.asarray(std, dtype=F32)
+    return f, np.sqrt(g * g).astype(F32)
+
+
+# ----------------------------------------------------------------------------------------------
+# Exposure pairs, validity mask, pair loss statistics
+# ----------------------------------------------------------------------------------------------
+def exposure_pairs(exposure, threshold=None):
+    """get_valid_exposure_pairs, common/general_functions.py:242-272 (row-major upper triangle)."""
+    t = np.asarray(exposure)
+    n = t.shape[0]
+    i_idx, j_idx = np.triu_indices(n, k=1)
+    ratio = t[i_idx] / t[j_idx]
+    if threshold is not None:
+        keep = ratio >= threshold
+        i_idx, j_idx, ratio = i_idx[keep], j_idx[keep], ratio[keep]
+    return i_idx.astype(np.int64), j_idx.astype(np.int64), ratio
+
+
+def frame_valid(val, lo, hi):
+    """Per-frame half of get_pairwise_valid_pixel_mask (general_functions.py:303-305).
+
+    The python-float thresholds are compared in the tensor's dtype, i.e. after rounding to float32.
+    """
+    val = np.asarray(val, dtype=F32)
+    return (val >= F32(lo)) & (val <= F32(hi))
+
+
+def pair_valid_mask(val, i_idx, j_idx, lo, hi):
+    fv = frame_valid(val, lo, hi)
+    return fv[i_idx] & fv[j_idx]
+
+
+def _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weighting, flat_offset):
+    """Everything per pair-element that losses.py:13-67,70-108 and general_functions.py:118-178 form.
+
+    Returns a dict of float64 (P,C,H,W) arrays plus the per-frame ICRF pieces.
+    """
+    val = np.ascontiguousarray(val, dtype=F32)
+    if theta is not None:
+        f32, fp32_, x0, rows = icrf_linear(val, theta, flat_offset)
+    else:
+        f32, fp32_, x0, rows = val, np.ones_like(val), None, None
+    f = f32.astype(F64)
+    have_std = std is not None
+    if have_std:
+        sig32 = np.abs(fp32_ * np.asarray(std, dtype=F32))            # icrf_training.py:124 (fp32)
+        sig = sig32.astype(F64)
+    r = np.asarray(ratio, dtype=F64).reshape(-1, 1, 1, 1)
+    a, b = f[i_idx], f[j_idx]
+    e = b * r                                                         # losses.py:40 (promotes to fp64)
+    d = a - e
+    out = {"f32": f32, "fp32": fp32_, "x0": x0, "rows": rows, "a": a, "b": b, "r": r}
+    if relative:
+        es = e + 1e-6                                                 # :45
+        q = d / es
+        out["es"] = es
+    else:
+        q = d
+    ell = np.abs(q)
+    out["sgn"] = np.sign(q)
+    err = None
+    if have_std:
+        sa, sb = sig[i_idx], sig[j_idx]
+        if relative:
+            bs = np.maximum(f32[j_idx], F32(1e-6)).astype(F64)        # :55 clamp in fp32
+            num = (f32[i_idx] * sig32[j_idx]).astype(F64)             # :58 fp32 product
+            term = (sa / es) ** 2 + (num / (es * bs)) ** 2 + 1e-6
+            err = np.sqrt(term)
+            out.update(bs=bs, sa=sa, sb=sb)
+        else:
+            err = np.sqrt((sig32[i_idx] ** 2).astype(F64) + (r * sb) ** 2)   # :62
+    gw = (gaussian_value_weights(val, PAIR_WEIGHT_SCALE)[i_idx]
+          + gaussian_value_weights(val, PAIR_WEIGHT_SCALE)[j_idx]).astype(F64)   # losses.py:229-234 (fp32 add)
+    wt = gw.copy()
+    if err is not None and unc_weighting:
+        wt = wt + 1.0 / (err + 1e-6)                                  # losses.py:97
+    m = pair_valid_mask(val, i_idx, j_idx, lo, hi).astype(F64)
+    out.update(ell=ell, err=err, wt=wt, mask=m)
+    return out
+
+
+def linearity_stats(val, std, exposure, theta=None, threshold=0.2, lo=1 / 255, hi=254 / 255, relative=True,
+                    unc_weighting=True, flat_offset=0, pairs=None):
+    """measure_linearity (inference/measure_linearity.py:41-74).
+
+    Returns (ratio (P,), mean (P,C), stddev (P,C), errmean (P,C) or None), float64.
+    """
+    i_idx, j_idx, ratio = exposure_pairs(exposure, threshold) if pairs is None else pairs
+    tm = _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weighting, flat_offset)
+    m, wt, ell = tm["mask"], tm["wt"], tm["ell"]
+    mw = m * wt
+    dsum = np.maximum(mw.sum(axis=(2, 3)), 1e-8)                      # general_functions.py:156
+    mean = (mw * ell).sum(axis=(2, 3)) / dsum
+    dev = (ell * m - mean[:, :, None, None]) ** 2                     # values were masked at :149
+    stddev = np.sqrt((dev * mw).sum(axis=(2, 3)) / dsum)
+    errmean = None
+    if tm["err"] is not None:
+        errmean = (tm["err"] * m).sum(axis=(2, 3)) / np.maximum(m.sum(axis=(2, 3)), 1e-8)
+    return np.asarray(ratio, dtype=F64), mean, stddev, errmean
+
+
+# ----------------------------------------------------------------------------------------------
+# ICRF training step
+# ----------------------------------------------------------------------------------------------
+def curve_penalties(theta):
+    """The four per-channel penalties of training/losses.py:111-190 and their gradients wrt theta (C,L)."""
+    th = np.asarray(theta, dtype=F64)
+    df = th[:, 1:] - th[:, :-1]
+    neg = (df <= 0).astype(F64)
+    mono = (neg * df * df).sum(axis=1)
+    g_mono = np.zeros_like(th)
+    g_mono[:, 1:] += 2 * neg * df
+    g_mono[:, :-1] -= 2 * neg * df
+    sd = th[:, :-2] - 2 * th[:, 1:-1] + th[:, 2:]
+    smooth = (sd * sd).sum(axis=1)
+    g_smooth = np.zeros_like(th)
+    g_smooth[:, :-2] += 2 * sd
+    g_smooth[:, 1:-1] -= 4 * sd
+    g_smooth[:, 2:] += 2 * sd
+    rng = (np.maximum(-th, 0) + np.maximum(th - 1, 0)).sum(axis=1)
+    g_rng = -(th < 0).astype(F64) + (th > 1).astype(F64)
+    endp = th[:, 0] ** 2 + (th[:, -1] - 1) ** 2
+    g_end = np.zeros_like(th)
+    g_end[:, 0] = 2 * th[:, 0]
+    g_end[:, -1] = 2 * (th[:, -1] - 1)
+    return (mono, rng, endp, smooth), (g_mono, g_rng, g_end, g_smooth)
+
+
+def train_loss_and_grad(val, std, exposure, theta, threshold=0.1, lo=1 / 255, hi=254 / 255, relative=True,
+                        unc_weighting=True, coeffs=(1.0, 1.0, 1.0, 1.0), flat_offset=0):
+    """Loss and d(sum_c Loss_c)/d theta of one train_icrf step (training/icrf_training.py:105-149).
+
+    Returns dict(loss (C,), linloss (C,), spatial (P,C), grad (C,L) float64, grad_lin (C,L)).
+    Closed form of the C `backward` calls.
+    """
+    theta = np.asarray(theta, dtype=F32)
+    n_rows, l = theta.shape
+    i_idx, j_idx, ratio = exposure_pairs(exposure, threshold)
+    tm = _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weighting, flat_offset)
+    m, wt, ell, sgn, r = tm["mask"], tm["wt"], tm["ell"], tm["sgn"], tm["r"]
+    a, b = tm["a"], tm["b"]
+    mw = m * wt
+    wsum = mw.sum(axis=(2, 3))
+    clamped = wsum < 1e-8
+    dsum = np.maximum(wsum, 1e-8)
+    spatial = (mw * ell).sum(axis=(2, 3)) / dsum                      # (P,C)
+    linloss = np.sqrt((spatial ** 2).sum(axis=0))                     # icrf_training.py:136
+    with np.errstate(divide="ignore", invalid="ignore"):
+        up = np.where(linloss[None, :] > 0, spatial / linloss[None, :], 0.0) / dsum     # U_{p,c}
+    up = up[:, :, None, None]
+    if relative:
+        es = tm["es"]
+        dl_da = sgn / es
+        dl_db = -sgn * r * (a + 1e-6) / (es * es)
+    else:
+        dl_da = sgn * np.ones_like(a)
+        dl_db = -sgn * r
+    g_a = mw * dl_da * up
+    g_b = mw * dl_db * up
+    if relative and unc_weighting and tm["err"] is not None:
+        # weights depend on a and b through err (losses.py:55-60 are inside the graph)
+        err, bs, sa, sb = tm["err"], tm["bs"], tm["sa"], tm["sb"]
+        dm_dwt = m * (ell - np.where(clamped, 0.0, spatial)[:, :, None, None]) * up
+        dm_dwt = np.where(clamped[:, :, None, None], 0.0, dm_dwt)
+        dwt_dt = -1.0 / (err + 1e-6) ** 2 / (2.0 * err)               # dWt/derr * derr/dT
+        dt_da = 2 * a * sb * sb / (es * bs) ** 2
+        dt_des = -2 * sa * sa / es ** 3 - 2 * a * a * sb * sb / (es ** 3 * bs ** 2)
+        dt_dbs = -2 * a * a * sb * sb / (es ** 2 * bs ** 3)
+        dbs_db = (tm["f32"][j_idx] >= F32(1e-6)).astype(F64)
+        g_a = g_a + dm_dwt * dwt_dt * dt_da
+        g_b = g_b + dm_dwt * dwt_dt * (dt_des * r + dt_dbs * dbs_db)
+    # gather per-frame upstream, then scatter to the two taps of each element (models/base.py:173-182)
+    g_frame = np.zeros(tm["f32"].shape, dtype=F64)
+    np.add.at(g_frame, i_idx, g_a)
+    np.add.at(g_frame, j_idx, g_b)
+    x0, rows = tm["x0"], tm["rows"]
+    x1 = np.minimum(x0 + 1, l - 1)
+    xs = np.minimum(np.maximum(np.asarray(val, dtype=F32) * F32(l - 1), F32(0)), F32(l - 1))
+    w = (xs - x0.astype(F32)).astype(F64)
+    grad_lin = np.zeros((n_rows, l), dtype=F64)
+    np.add.at(grad_lin, (rows.ravel(), x0.ravel()), (g_frame * (1.0 - w)).ravel())
+    np.add.at(grad_lin, (rows.ravel(), x1.ravel()), (g_frame * w).ravel())
+    pens, gpens = curve_penalties(theta)
+    loss = linloss.copy()
+    grad = grad_lin.copy()
+    for k, (p, g) in zip(coeffs, zip(pens, gpens)):
+        loss = loss + k * p
+        grad = grad + k * g
+    return {"loss": loss, "linloss": linloss, "spatial": spatial, "grad": grad, "grad_lin": grad_lin,
+            "pairs": (i_idx, j_idx, ratio)}
+
+
+class Adam:
+    """torch.optim.Adam(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, amsgrad=False) on one float32 array."""
+
+    def __init__(self, shape, lr=1e-3, b1=0.9, b2=0.999, eps=1e-8):
+        self.m = np.zeros(shape, dtype=F32)
+        self.v = np.zeros(shape, dtype=F32)
+        self.t = 0
+        self.lr, self.b1, self.b2, self.eps = lr, b1, b2, eps
+
+    def step(self, param, grad):
+        g = np.asarray(grad, dtype=F32)
+        self.t += 1
+        self.m = (self.m + (g - self.m) * F32(1 - self.b1)).astype(F32)       # lerp_
+        self.v = (self.v * F32(self.b2) + F32(1 - self.b2) * g * g).astype(F32)
+        bc1 = 1 - self.b1 ** self.t
+        bc2 = 1 - self.b2 ** self.t
+        denom = (np.sqrt(self.v) / F32(np.sqrt(bc2)) + F32(self.eps)).astype(F32)
+        return (np.asarray(param, dtype=F32) - F32(self.lr / bc1) * (self.m / denom)).astype(F32)

@@ -1,0 +1,158 @@
+"""Pins the CPU oracle (oracle/clair_oracle.py) to the reference.
+
+Every fixture under tests/golden/ was written by tests/golden/make_golden.py from the UNMODIFIED
+reference; this file checks the oracle's closed forms against them.  Bit-exact where the result is an
+index, a mask or a pure fp32 table evaluation; 1e-5 relative (the north-star tolerance) elsewhere, with
+the tighter bound the oracle actually meets asserted next to it.
+"""
+import numpy as np
+import pytest
+
+from _helpers import golden, golden_names, max_abs_over_max, max_rel
+from oracle import clair_oracle as orc
+
+TOL = 1e-5   # BASELINE.json north_star: radiance, uncertainty and loss within 1e-5 relative
+
+
+def _opt(z, k):
+    return z[k] if k in z else None
+
+
+# ---- known-answer vectors held by the reference's own unit tests ------------------------------
+def test_known_exposure_pairs():
+    z = golden("known_answers")
+    i, j, r = orc.exposure_pairs(z["pairs_exposure"])
+    assert np.array_equal(i, z["pairs_i"]) and np.array_equal(j, z["pairs_j"])
+    assert np.array_equal(r.astype(np.float32), z["pairs_r"])
+    assert np.array_equal(i, [0, 0, 1]) and np.array_equal(j, [1, 2, 2])          # test_general_functions.py:298-300
+    i, j, r = orc.exposure_pairs(z["pairs_exposure"], float(z["pairs_thr"]))
+    assert np.array_equal(i, z["pairs_thr_i"]) and np.array_equal(j, z["pairs_thr_j"])
+    assert np.array_equal(i, [0, 1]) and np.array_equal(j, [1, 2])                # :313-315
+    i, j, r = orc.exposure_pairs(z["pairs6_exposure"], float(z["pairs6_thr"]))
+    assert np.array_equal(i, z["pairs6_i"]) and np.array_equal(j, z["pairs6_j"]) and np.array_equal(r, z["pairs6_r"])
+
+
+def test_known_valid_masks():
+    z = golden("known_answers")
+    m = orc.pair_valid_mask(z["mask_stack"], z["mask_i"], z["mask_j"], float(z["mask_lo"]), float(z["mask_hi"]))
+    assert np.array_equal(m, z["mask_expected"])
+    k16 = (np.arange(65536, dtype=np.float32) / np.float32(65535.0))
+    v16 = orc.frame_valid(k16, 1 / 255, 254 / 255)
+    assert np.array_equal(v16, z["valid16"])
+    assert v16[257] and not v16[256] and v16[65278] and not v16[65279]
+    k8 = (np.arange(256, dtype=np.float32) / np.float32(255.0))
+    assert np.array_equal(orc.frame_valid(k8, 1 / 255, 254 / 255), z["valid8"])
+
+
+def test_known_gaussian_weights():
+    z = golden("known_answers")
+    assert max_rel(orc.gaussian_value_weights(z["gw_x"], 30.0), z["gw_30"]) < 5e-7
+    assert max_rel(orc.gaussian_value_weights(z["gw_x"], 10.0), z["gw_10"]) < 5e-7
+    assert orc.gaussian_value_weights(np.float32(0.5)) == 1.0                      # test_losses.py: peak at 0.5
+
+
+def test_known_running_weighted_mean():
+    """WBOMean (common/statistics.py) equals the direct weighted mean; HdrState uses the same merge."""
+    z = golden("known_answers")
+    v, w = z["wbo_values"], z["wbo_weights"]
+    mean, wsum = 0.0, 0.0
+    for a in range(0, 12, 5):
+        wb = w[a:a + 5].sum(0)
+        mb = (w[a:a + 5] * v[a:a + 5]).sum(0) / (wb + 1e-6)
+        tot = wsum + wb
+        mean = mean + (wb / tot) * (mb - mean)
+        wsum = tot
+    assert max_rel(mean, z["wbo_mean"][0]) < 1e-12
+    assert max_rel(wsum, z["wbo_wsum"][0]) < 1e-12
+
+
+# ---- ICRF evaluation ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("forward_linear"))
+def test_forward_linear_bit_exact(name):
+    z = golden(name)
+    f, fp, x0, rows = orc.icrf_linear(z["x"], z["theta"])
+    assert np.array_equal(f, z["y"])
+    assert np.array_equal(fp, z["dydx"])
+
+
+@pytest.mark.parametrize("name", golden_names("forward_lookup"))
+def test_forward_lookup_bit_exact(name):
+    z = golden(name)
+    y, _ = orc.icrf_lookup(z["x"], z["theta"])
+    assert np.array_equal(y, z["y"])
+
+
+@pytest.mark.parametrize("name", golden_names("forward_codes"))
+def test_forward_all_codes(name):
+    z = golden(name)
+    f, _, x0, _ = orc.icrf_linear(z["x"], z["theta"])
+    y, idx = orc.icrf_lookup(z["x"], z["theta"])
+    assert np.array_equal(f, z["y_linear"]) and np.array_equal(y, z["y_lookup"])
+    if name.endswith("u8"):   # fl32(k/255)*255 == k exactly, so x0 == k
+        assert np.array_equal(x0[0, 0, 0], np.arange(256))
+
+
+# ---- HDR merge ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("hdr_"))
+def test_hdr_merge(name):
+    z = golden(name)
+    rad, sig = orc.hdr_merge(z["val"], _opt(z, "std"), z["exposure"], _opt(z, "theta"), bool(z["gaussian"]),
+                             int(z["batch_size"]))
+    assert max_rel(rad.reshape(z["radiance"].shape), z["radiance"]) < 5e-7
+    if "sigma" in z:
+        # the reference's own fp32 autograd carries ~5e-6 of cancellation noise at bright codes
+        assert max_rel(sig.reshape(z["sigma"].shape), z["sigma"]) < TOL
+    else:
+        assert sig is None
+
+
+@pytest.mark.parametrize("name", golden_names("linearize_"))
+def test_linearize_bit_exact(name):
+    z = golden(name)
+    for n in range(z["val"].shape[0]):
+        std = None if "std" not in z else z["std"][n:n + 1]
+        f, s = orc.linearize(z["val"][n:n + 1], std, z["theta"])
+        assert np.array_equal(f[0], z["linearized"][n])
+        assert np.array_equal(s[0], z["sigma"][n])
+
+
+# ---- linearity measurement ---------------------------------------------------------------------
+def _linearity_flags(name):
+    if name == "linearity_u16_w11":
+        return True, True
+    return "rel1" in name, "unc1" in name
+
+
+@pytest.mark.parametrize("name", golden_names("linearity_"))
+def test_linearity_stats(name):
+    z = golden(name)
+    rel, unc = _linearity_flags(name)
+    ratio, m, sd, em = orc.linearity_stats(z["val"], _opt(z, "std"), z["exposure"], _opt(z, "theta"), 0.2,
+                                           relative=rel, unc_weighting=unc)
+    assert np.array_equal(ratio, z["ratio"])
+    assert max_rel(m, z["mean"]) < 1e-7
+    assert max_rel(sd, z["stddev"]) < 1e-7
+    if "errmean" in z:
+        assert max_rel(em, z["errmean"]) < 1e-12
+    else:
+        assert em is None
+
+
+# ---- training step -----------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("trainstep_"))
+def test_train_step(name):
+    z = golden(name)
+    c = z["theta0"].shape[0]
+    adams = [orc.Adam(z["theta0"][k].shape) for k in range(c)]
+    for step in range(int(z["n_steps"])):
+        theta = z["theta0"] if step == 0 else z[f"theta_after_{step - 1}"]
+        out = orc.train_loss_and_grad(z["val"], _opt(z, "std"), z["exposure"], theta, float(z["thr"]),
+                                      relative=bool(z["rel"]), unc_weighting=bool(z["unc"]),
+                                      coeffs=tuple(z["coeffs"]))
+        assert max_rel(out["loss"], z[f"loss_{step}"]) < 1e-6
+        assert max_rel(out["linloss"], z[f"linloss_{step}"]) < 1e-6
+        assert max_rel(out["spatial"], z[f"spatial_{step}"]) < 1e-6
+        assert max_abs_over_max(out["grad"], z[f"grad_theta_{step}"]) < TOL
+        # Adam on the reference's own gradient reproduces the reference's next table
+        nxt = np.stack([adams[k].step(theta[k], z[f"grad_theta_{step}"][k]) for k in range(c)])
+        assert np.max(np.abs(nxt - z[f"theta_after_{step}"])) < 2e-7
