@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Benchmark of the headline metric: HDR-merge throughput in Mpixel*frames/s (BASELINE.json).
+
+Workload: a 5-frame 8-bit RGB 1920x1080 synthetic exposure stack handed over as
+fp32 value + fp32 std images, fixed 256-entry ICRF with distinct rows (LINEAR), Gaussian weights, whole stack in
+one batch, radiance + uncertainty written as fp32.  One "step" = one merge of one stack.
+
+  value     kernel-only: stacks resident in HBM, K back-to-back launches through the C ABI, CUDA events.
+            Four distinct stacks (995 MB) are rotated so no step finds its inputs in the 126 MB L2.
+  e2e       the same merge through the public API (compute_hdr_image) from PINNED HOST buffers, with the
+            host->device copy of the stack and the device->host read of radiance + uncertainty inside the
+            timed region.
+  roofline  algorithmic bytes (28.8 B per pixel*frame) / measured kernel time vs the measured HBM copy peak.
+  cpu_baseline  the CPU oracle port of the reference algorithm timed on this box's host cores on a row-cropped
+            sample of the same stack (rank 0, N=1 only).
+
+`--impl reference` times the CPU implementation of the path (the oracle port: the reference is pure Python/torch
+and cannot travel to the GPU box) with all host threads on the same config and prints the same JSON line.
+Multi-GPU (torchrun): stacks shard by stack across ranks (weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_FRAMES, CHANNELS, HEIGHT, WIDTH, BITS, LUT = 5, 3, 1080, 1920, 8, 256
+ALGO_BYTES_PER_PIXEL_FRAME = CHANNELS * (4 * 2 + 8 / N_FRAMES)      # C*(b_in(1+sigma) + 8/N) = 28.8
+METRIC = "hdr_merge_mpixel_frames_per_s"
+WORKLOAD = ("c1: HDR merge, 5x 8-bit RGB 1920x1080 synthetic exposure stack as fp32 val+std, 256-entry LINEAR ICRF "
+            "(distinct rows), gaussian weights, first-order uncertainty, fp32 radiance+sigma")
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[2:6]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(rows, threads):
+    """Mpixel*frames/s of the CPU oracle port on a row-cropped sample of the c1 stack."""
+    import numpy as np
+    import torch
+    torch.set_num_threads(max(1, threads))
+    import clair_torch_b200.synthetic as syn
+    from oracle import clair_oracle as orc
+    val, std, t = syn.make_stack(N_FRAMES, CHANNELS, rows, WIDTH, bits=BITS, seed=1234)
+    theta = syn.reference_curve(CHANNELS, LUT).numpy()
+    v, s = val.numpy(), std.numpy()
+    orc.hdr_merge(v[:, :, :8], s[:, :, :8], t, theta, True)          # warm-up
+    t0 = time.perf_counter()
+    orc.hdr_merge(v, s, t, theta, True)
+    dt = time.perf_counter() - t0
+    return N_FRAMES * rows * WIDTH / dt / 1e6, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    rows = 270
+    vals = []
+    for _ in range(args.warmup):
+        cpu_oracle_rate(rows, cores)
+    t_total = 0.0
+    for _ in range(args.steps):
+        rate, dt = cpu_oracle_rate(rows, cores)
+        vals.append(rate)
+        t_total += dt
+    value = sum(vals) / len(vals)
+    sample = f"rows 0..{rows} of 1080 (1/{1080 // rows} of one stack) per step, numpy closed-form oracle port"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel*frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "Mpixel*frames/s", "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from torch.utils.data import DataLoader
+
+    import clair_torch_b200 as ct
+    from clair_torch_b200 import kernels
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = ct._native.load()
+
+    # ---- device-resident stacks: each rank owns its own stacks (sharding by stack, no data-path collective) ----
+    n_sets = 4
+    theta = ct.synthetic.reference_curve(CHANNELS, LUT).to(dev)
+    stacks = []
+    for k in range(n_sets):
+        val, std, t = ct.synthetic.make_stack(N_FRAMES, CHANNELS, HEIGHT, WIDTH, bits=BITS, seed=1234 + 97 * rank + k,
+                                              device=dev)
+        stacks.append((val, std))
+    radiance = torch.empty((CHANNELS, HEIGHT, WIDTH), dtype=torch.float32, device=dev)
+    sigma = torch.empty_like(radiance)
+    t_host = np.ascontiguousarray(t)
+    import ctypes
+    stream = torch.cuda.current_stream(dev)
+
+    def launch(k):
+        val, std = stacks[k % n_sets]
+        rc = lib.clair_hdr_merge_update(val.data_ptr(), std.data_ptr(), t_host.ctypes.data_as(ctypes.c_void_p), N_FRAMES,
+                                        theta.data_ptr(), CHANNELS, LUT, HEIGHT * WIDTH, None, 1, None, None, None, 1, 1,
+                                        radiance.data_ptr(), 0, sigma.data_ptr(), stream.cuda_stream)
+        ct._native.check(rc, "clair_hdr_merge_update")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for k in range(args.warmup):
+        launch(k)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches_before = ct._native.launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record(stream)
+    for k in range(args.steps):
+        launch(k)
+    stop.record(stream)
+    barrier()
+    kernel_ms = start.elapsed_time(stop)
+    launches = ct._native.launch_count() - launches_before
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        kernel_ms = float(tt.item())
+    ms_per_step = kernel_ms / args.steps
+    units_per_step = N_FRAMES * HEIGHT * WIDTH / 1e6                        # Mpixel*frames per stack
+    value = world * units_per_step / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API from pinned host memory ----
+    val_h = stacks[0][0].cpu().pin_memory()
+    std_h = stacks[0][1].cpu().pin_memory()
+    rad_h = torch.empty((CHANNELS, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
+    sig_h = torch.empty_like(rad_h).pin_memory()
+    batch = (torch.arange(N_FRAMES), val_h, std_h, {"exposure_time": torch.from_numpy(t_host)})
+
+    class OneBatch(torch.utils.data.Dataset):
+        def __len__(self):
+            return 1
+
+        def __getitem__(self, i):
+            return batch
+
+    loader = DataLoader(OneBatch(), batch_size=None, shuffle=False)
+    model = ct.ICRFModelDirect(icrf=theta.clone()).to(dev)
+
+    def e2e_step():
+        rad, sig = ct.compute_hdr_image(loader, dev, model, max, radiance_dtype=torch.float32)
+        rad_h.copy_(rad, non_blocking=True)
+        sig_h.copy_(sig, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms) / args.e2e_steps
+    if world > 1:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+    e2e_value = world * units_per_step / (e2e_ms * 1e-3)
+    h2d = val_h.numel() * 4 + std_h.numel() * 4
+    d2h = rad_h.numel() * 4 + sig_h.numel() * 4
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        algo_bytes = ALGO_BYTES_PER_PIXEL_FRAME * N_FRAMES * HEIGHT * WIDTH          # per launch = per stack
+        achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rows = 270
+            rate, dt = cpu_oracle_rate(rows, os.cpu_count() or 1)
+            cpu = {"value": rate, "unit": "Mpixel*frames/s", "cores": 1, "kind": "port",
+                   "sample": f"rows 0..{rows} of 1080 of one c1 stack, numpy closed-form oracle port, {dt:.2f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "Mpixel*frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "stacks_per_rank_rotated": n_sets,
+                       "l2": "4 distinct stacks (995 MB) rotated per step, each far larger than the 126 MB L2",
+                       "sharding": "by stack, one rank per GPU, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                         "kernel": "clair::hdr_merge_kernel<4,true>"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "api": "clair_torch_b200.compute_hdr_image from pinned host batch"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""ctypes binding of libclair_b200.so (the C ABI declared in include/clair_b200.h).
+
+PyTorch is used for device memory and streams only; every arithmetic step of the hot path happens inside
+the hand-written sm_100a kernels behind this binding.  There is NO fallback: if the shared library is
+missing, or no CUDA device is present, the ops raise instead of silently computing something else.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "lib", "libclair_b200.so")
+CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
+
+ABI_VERSION = 1
+MAX_FRAMES = 64
+MAX_CHANNELS = 8
+MAX_LUT = 1024
+MAX_PAIRS = 2016
+INTERP_LOOKUP = 1
+INTERP_LINEAR = 2
+
+# every symbol include/clair_b200.h declares, with its ctypes prototype
+_c = ctypes
+_PROTOTYPES = {
+    "clair_abi_version": (_c.c_int, []),
+    "clair_last_error": (_c.c_char_p, []),
+    "clair_launch_count": (_c.c_uint64, []),
+    "clair_grad_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int]),
+    "clair_icrf_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
+                                      _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "clair_icrf_backward_theta": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
+                                             _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "clair_linearize": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
+                                   _c.c_int, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "clair_hdr_merge_update": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int,
+                                          _c.c_int, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                          _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
+                                          _c.c_void_p]),
+    "clair_pair_stats": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p,
+                                    _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
+                                    _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "clair_pair_grad": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p,
+                                   _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
+                                   _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                   _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+}
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeLibraryError(RuntimeError):
+    """libclair_b200.so is missing or does not match the header."""
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into clair_torch_b200/lib/libclair_b200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC_DIR, "-j4"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise NativeLibraryError(f"building libclair_b200.so failed (exit {res.returncode})")
+    return LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library and attach prototypes.  Raises NativeLibraryError when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"or `make -C {CSRC_DIR}`.  clair_torch_b200 has no CPU or eager fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _PROTOTYPES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as exc:
+                raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from exc
+            fn.restype = restype
+            fn.argtypes = argtypes
+        if lib.clair_abi_version() != ABI_VERSION:
+            raise NativeLibraryError(f"ABI mismatch: library {lib.clair_abi_version()}, binding {ABI_VERSION}")
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    """Turn a non-zero return code into the exception type the reference would raise for the same mistake."""
+    if rc == 0:
+        return
+    msg = load().clair_last_error().decode("utf-8", "replace")
+    if rc < 0:
+        raise ValueError(f"{what}: {msg} (code {rc})")
+    raise RuntimeError(f"{what}: {msg} (cudaError {rc})")
+
+
+def launch_count() -> int:
+    return int(load().clair_launch_count())

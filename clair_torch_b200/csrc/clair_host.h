@@ -1,0 +1,26 @@
+// Host-side helpers shared by the C-ABI entry points (argument checks, error reporting, launch accounting).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <initializer_list>
+
+#include "../../include/clair_b200.h"
+#include "clair_common.cuh"
+
+namespace clair {
+
+// records `msg` as the calling thread's last error and returns `code`
+int fail(int code, const char *msg);
+int fail_cuda(cudaError_t e, const char *what);
+// checks cudaGetLastError() after a launch and bumps the launch counter
+int launched(const char *kernel_name);
+
+int check_geometry(const char *fn, int n_frames, int n_channels, int64_t plane, int lut_size, bool limit_frames);
+
+// curve_row_base_host == NULL: whole image, row of element (c, p) is (c*plane + p) mod C
+void fill_rows(CurveRows &rows, const int32_t *curve_row_base_host, int n_channels, int64_t plane);
+
+}  // namespace clair

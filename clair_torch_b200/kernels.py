@@ -1,0 +1,244 @@
+"""Tensor-level launchers for the sm_100a kernels (thin: argument checks, output allocation, ctypes call).
+
+Everything here takes CUDA tensors; torch supplies memory and the current stream, nothing else.  The
+functions mirror the C ABI of include/clair_b200.h one to one.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _native
+
+_F32 = torch.float32
+_F64 = torch.float64
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _stack(t: torch.Tensor, name: str) -> torch.Tensor:
+    """An (N, C, H, W) fp32 CUDA stack, made contiguous (MissingStdMode.CONSTANT hands over stride-0 views)."""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t)}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must live on a CUDA device: clair_torch_b200 has no CPU path")
+    if t.dtype != _F32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    if t.dim() != 4:
+        raise ValueError(f"{name} must have shape (N, C, H, W), got {tuple(t.shape)}")
+    return t.detach().contiguous()
+
+
+def _table(theta: Optional[torch.Tensor], device, channels: int) -> Optional[torch.Tensor]:
+    if theta is None:
+        return None
+    th = theta.detach().to(device=device, dtype=_F32).contiguous()
+    if th.dim() != 2 or th.shape[0] != channels:
+        raise ValueError(f"ICRF table must have shape (C={channels}, L), got {tuple(th.shape)}")
+    return th
+
+
+def _rows(row_base: Optional[Sequence[int]], channels: int):
+    if row_base is None:
+        return None, None
+    arr = np.ascontiguousarray(np.asarray(row_base, dtype=np.int32))
+    if arr.shape != (channels,):
+        raise ValueError(f"curve_row_base must have {channels} entries")
+    return arr, arr.ctypes.data_as(ctypes.c_void_p)
+
+
+def shard_row_base(channels: int, full_height: int, width: int, first_row: int) -> np.ndarray:
+    """curve_row_base for a row band [first_row, ...) of a full (C, full_height, width) frame."""
+    c = np.arange(channels, dtype=np.int64)
+    return ((c * full_height * width + first_row * width) % channels).astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def icrf_forward(x: torch.Tensor, theta: torch.Tensor, interp_mode: int = _native.INTERP_LINEAR,
+                 want_derivative: bool = False, row_base=None):
+    """f(x) [and autograd's df/dx] for an (N, C, H, W) stack.  models/base.py:135-182."""
+    lib = _native.load()
+    x = _stack(x, "image")
+    n, c, h, w = x.shape
+    th = _table(theta, x.device, c)
+    y = torch.empty_like(x)
+    dydx = torch.empty_like(x) if want_derivative else None
+    keep, rows = _rows(row_base, c)
+    with torch.cuda.device(x.device):
+        rc = lib.clair_icrf_forward(_ptr(x), _ptr(th), _ptr(y), _ptr(dydx), n, c, h * w, th.shape[1], interp_mode,
+                                    rows, _stream(x.device))
+    _native.check(rc, "clair_icrf_forward")
+    return (y, dydx) if want_derivative else y
+
+
+def _workspace(device, channels: int, lut: int) -> torch.Tensor:
+    nbytes = _native.load().clair_grad_workspace_bytes(channels, lut)
+    return torch.empty(nbytes // 4, dtype=_F32, device=device)
+
+
+def icrf_backward_theta(x: torch.Tensor, grad_y: torch.Tensor, channels: int, lut: int, row_base=None) -> torch.Tensor:
+    """(C, L) float64 gradient of sum(grad_y * f(x)) with respect to the table.  models/base.py:173-182 backward."""
+    lib = _native.load()
+    x = _stack(x, "image")
+    gy = _stack(grad_y, "grad_output")
+    n, c, h, w = x.shape
+    grad = torch.zeros((channels, lut), dtype=_F64, device=x.device)
+    ws = _workspace(x.device, channels, lut)
+    keep, rows = _rows(row_base, c)
+    with torch.cuda.device(x.device):
+        rc = lib.clair_icrf_backward_theta(_ptr(x), _ptr(gy), _ptr(grad), n, c, h * w, lut, rows, _ptr(ws),
+                                           ws.numel() * 4, _stream(x.device))
+    _native.check(rc, "clair_icrf_backward_theta")
+    return grad
+
+
+def linearize(val: torch.Tensor, std: Optional[torch.Tensor], theta: torch.Tensor, row_base=None):
+    """(f(x), sqrt((f'(x) std)^2)) per image of an (N, C, H, W) stack.  inference/linearization.py:94-106."""
+    lib = _native.load()
+    val = _stack(val, "val_batch")
+    std = None if std is None else _stack(std, "std_batch")
+    n, c, h, w = val.shape
+    th = _table(theta, val.device, c)
+    lin = torch.empty_like(val)
+    sigma = torch.empty_like(val)
+    keep, rows = _rows(row_base, c)
+    with torch.cuda.device(val.device):
+        rc = lib.clair_linearize(_ptr(val), _ptr(std), _ptr(th), _ptr(lin), _ptr(sigma), n, c, h * w, th.shape[1],
+                                 rows, _stream(val.device))
+    _native.check(rc, "clair_linearize")
+    return lin, sigma
+
+
+class HdrMergeState:
+    """Running (mean, sum of weights, variance) of the merge — WBOMean's state (common/statistics.py:27-29)
+    plus hdr_merge.py's running_variance, kept as device buffers between DataLoader batches."""
+
+    def __init__(self):
+        self.mean: Optional[torch.Tensor] = None     # (C, H, W) float64
+        self.wsum: Optional[torch.Tensor] = None     # (C, H, W) float32
+        self.var: Optional[torch.Tensor] = None      # (C, H, W) float32
+        self.batches = 0
+
+    def _ensure(self, like: torch.Tensor, with_var: bool):
+        shape = tuple(like.shape[1:])
+        if self.mean is None:
+            self.mean = torch.empty(shape, dtype=_F64, device=like.device)
+            self.wsum = torch.empty(shape, dtype=_F32, device=like.device)
+        if with_var and self.var is None:
+            self.var = torch.empty(shape, dtype=_F32, device=like.device)
+
+
+def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std: Optional[torch.Tensor], exposure,
+                     theta: Optional[torch.Tensor], gaussian_weights: bool, is_final: bool,
+                     radiance_dtype: torch.dtype = _F64, row_base=None):
+    """One batch of compute_hdr_image (inference/hdr_merge.py:95-128).  Returns (radiance, sigma) when
+    `is_final`, else None.  `exposure` is the collated float64 'exposure_time' (host tensor, array or list)."""
+    lib = _native.load()
+    val = _stack(val, "val_batch")
+    std = None if std is None else _stack(std, "std_batch")
+    if std is not None and std.shape != val.shape:
+        raise ValueError("std_batch must have the same shape as val_batch")
+    n, c, h, w = val.shape
+    if torch.is_tensor(exposure):
+        exposure = exposure.detach().cpu().numpy()
+    t = np.ascontiguousarray(np.asarray(exposure, dtype=np.float64).reshape(-1))
+    if t.shape[0] != n:
+        raise ValueError(f"{n} frames but {t.shape[0]} exposure times")
+    th = _table(theta, val.device, c)
+    lut = 0 if th is None else th.shape[1]
+    is_first = state.batches == 0
+    if std is not None and not is_first and state.var is None:
+        raise ValueError("std images appeared after a batch without them")
+    if not (is_first and is_final):
+        state._ensure(val, std is not None)
+    radiance = sigma = None
+    if is_final:
+        if radiance_dtype not in (_F32, _F64):
+            raise TypeError("radiance_dtype must be torch.float32 or torch.float64")
+        radiance = torch.empty((c, h, w), dtype=radiance_dtype, device=val.device)
+        if std is not None:
+            sigma = torch.empty((c, h, w), dtype=_F32, device=val.device)
+    keep, rows = _rows(row_base, c)
+    with torch.cuda.device(val.device):
+        rc = lib.clair_hdr_merge_update(
+            _ptr(val), _ptr(std), t.ctypes.data_as(ctypes.c_void_p), n, _ptr(th), c, lut, h * w, rows,
+            int(bool(gaussian_weights)), _ptr(state.mean), _ptr(state.wsum), _ptr(state.var), int(is_first),
+            int(is_final), _ptr(radiance), int(radiance_dtype == _F64), _ptr(sigma), _stream(val.device))
+    _native.check(rc, "clair_hdr_merge_update")
+    state.batches += 1
+    return (radiance, sigma) if is_final else None
+
+
+# ----------------------------------------------------------------------------------------------------------
+def _pair_arrays(i_idx, j_idx, ratio):
+    def host(a, dt):
+        if torch.is_tensor(a):
+            a = a.detach().cpu().numpy()
+        return np.ascontiguousarray(np.asarray(a).reshape(-1).astype(dt))
+    pi, pj, pr = host(i_idx, np.int32), host(j_idx, np.int32), host(ratio, np.float64)
+    if not (pi.shape == pj.shape == pr.shape):
+        raise ValueError("i_idx, j_idx and ratio_pairs must have the same length")
+    return pi, pj, pr
+
+
+def pair_stats(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, ratio,
+               theta: Optional[torch.Tensor], valid_lo: float, valid_hi: float, relative: bool,
+               unc_weighting: bool, row_base=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(P, C, 5) float64 sums [sum MWt, sum MWt l, sum MWt l^2, sum M err, sum M] for one batch.
+    training/losses.py:13-108, common/general_functions.py:118-178,276-312."""
+    lib = _native.load()
+    val = _stack(val, "val_batch")
+    std = None if std is None else _stack(std, "std_batch")
+    n, c, h, w = val.shape
+    pi, pj, pr = _pair_arrays(i_idx, j_idx, ratio)
+    p = pi.shape[0]
+    th = _table(theta, val.device, c)
+    lut = 0 if th is None else th.shape[1]
+    sums = torch.zeros((p, c, 5), dtype=_F64, device=val.device) if out is None else out
+    keep, rows = _rows(row_base, c)
+    with torch.cuda.device(val.device):
+        rc = lib.clair_pair_stats(
+            _ptr(val), _ptr(std), n, c, h * w, pi.ctypes.data_as(ctypes.c_void_p),
+            pj.ctypes.data_as(ctypes.c_void_p), pr.ctypes.data_as(ctypes.c_void_p), p, _ptr(th), lut, rows,
+            float(np.float32(valid_lo)), float(np.float32(valid_hi)), int(bool(relative)), int(bool(unc_weighting)),
+            _ptr(sums), _stream(val.device))
+    _native.check(rc, "clair_pair_stats")
+    return sums
+
+
+def pair_grad(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, ratio, theta: torch.Tensor,
+              valid_lo: float, valid_hi: float, relative: bool, unc_weighting: bool, upstream: torch.Tensor,
+              mean: torch.Tensor, row_base=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(C, L) float64 gradient of the linearity loss with respect to the table."""
+    lib = _native.load()
+    val = _stack(val, "val_batch")
+    std = None if std is None else _stack(std, "std_batch")
+    n, c, h, w = val.shape
+    pi, pj, pr = _pair_arrays(i_idx, j_idx, ratio)
+    p = pi.shape[0]
+    th = _table(theta, val.device, c)
+    lut = th.shape[1]
+    up = upstream.detach().to(device=val.device, dtype=_F64).contiguous()
+    mn = mean.detach().to(device=val.device, dtype=_F64).contiguous()
+    if tuple(up.shape) != (p, c) or tuple(mn.shape) != (p, c):
+        raise ValueError("upstream and mean must have shape (P, C)")
+    grad = torch.zeros((c, lut), dtype=_F64, device=val.device) if out is None else out
+    ws = _workspace(val.device, c, lut)
+    keep, rows = _rows(row_base, c)
+    with torch.cuda.device(val.device):
+        rc = lib.clair_pair_grad(
+            _ptr(val), _ptr(std), n, c, h * w, pi.ctypes.data_as(ctypes.c_void_p),
+            pj.ctypes.data_as(ctypes.c_void_p), pr.ctypes.data_as(ctypes.c_void_p), p, _ptr(th), lut, rows,
+            float(np.float32(valid_lo)), float(np.float32(valid_hi)), int(bool(relative)), int(bool(unc_weighting)),
+            _ptr(up), _ptr(mn), _ptr(grad), _ptr(ws), ws.numel() * 4, _stream(val.device))
+    _native.check(rc, "clair_pair_grad")
+    return grad

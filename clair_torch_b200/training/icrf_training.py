@@ -1,0 +1,151 @@
+"""ICRF training — call-compatible with clair_torch/training/icrf_training.py:18-186.
+
+One optimisation step = two fused kernel passes over the device-resident exposure stack:
+  1. clair_pair_stats: per (pair, channel) spatial sums -> weighted means m[p, c] (icrf_training.py:105-133)
+  2. clair_pair_grad : d(sum_c sqrt(sum_p m[p,c]^2)) / d table, in closed form     (icrf_training.py:136,148-149)
+The (P, C)-sized algebra between them, the four curve penalties (768 numbers), Adam and update_icrf stay in torch.
+"""
+from typing import Optional
+
+import torch
+from torch.optim import Optimizer
+from torch.utils.data import DataLoader
+
+from .. import kernels
+from ..common.general_functions import get_valid_exposure_pairs
+from ..models.base import ICRFModelBase
+from ..inference._common import as_device, stage_batch
+from ..common.enums import InterpMode
+from .losses import (compute_endpoint_penalty, compute_monotonicity_penalty, compute_range_penalty,
+                     compute_smoothness_penalty)
+
+
+def linearity_loss_and_table_grad(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
+                                  upper_valid_threshold, use_relative_linearity_loss, use_uncertainty_weighting,
+                                  want_grad=True, row_base=None, reduce_fn=None):
+    """Linearity loss per channel (C,) float64, spatial means (P, C), and d(sum_c loss_c)/d table (C, L) float64.
+
+    `reduce_fn`, if given, is applied in place to the (P, C, 5) sums and to the (C, L) gradient: the data-parallel
+    trainer passes an NCCL all-reduce here (spatial shards of one image add their sums).
+    """
+    sums = kernels.pair_stats(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
+                              upper_valid_threshold, use_relative_linearity_loss, use_uncertainty_weighting,
+                              row_base=row_base)
+    if reduce_fn is not None:
+        reduce_fn(sums)
+    s0, s1 = sums[..., 0], sums[..., 1]
+    denom = s0.clamp(min=1e-8)
+    spatial = s1 / denom                                          # general_functions.py:156-160
+    linearity_loss = torch.sqrt((spatial ** 2).sum(dim=0))        # icrf_training.py:136
+    grad = None
+    if want_grad:
+        safe = torch.where(linearity_loss > 0, linearity_loss, torch.ones_like(linearity_loss))
+        upstream = torch.where(linearity_loss > 0, spatial / safe, torch.zeros_like(spatial)) / denom
+        mean_for_grad = torch.where(s0 < 1e-8, torch.zeros_like(spatial), spatial)   # clamped denominators carry no d/dWt
+        grad = kernels.pair_grad(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
+                                 upper_valid_threshold, use_relative_linearity_loss, use_uncertainty_weighting,
+                                 upstream, mean_for_grad, row_base=row_base)
+        if reduce_fn is not None:
+            reduce_fn(grad)
+    return linearity_loss, spatial, grad
+
+
+def train_icrf_step(icrf_model: ICRFModelBase, optimizers: list[Optimizer], images: torch.Tensor,
+                    stds: Optional[torch.Tensor], exposures: torch.Tensor, *, use_relative_linearity_loss=True,
+                    use_uncertainty_weighting=True, alpha=1.0, beta=1.0, gamma=1.0, delta=1.0,
+                    lower_valid_threshold=1 / 255, upper_valid_threshold=254 / 255, exposure_ratio_threshold=0.1,
+                    row_base=None, reduce_fn=None):
+    """Body of the batch loop, icrf_training.py:105-156, for one device-resident batch.  Returns the detached
+    per-channel loss (C,) (a 0-dim sum when a single optimiser is used, :145-146)."""
+    if icrf_model.interpolation_mode is not InterpMode.LINEAR:
+        raise NotImplementedError("train_icrf on B200 supports InterpMode.LINEAR (the reference default)")
+    i_idx, j_idx, ratio_pairs = get_valid_exposure_pairs(exposures, exposure_ratio_threshold)
+    for optimizer in optimizers:
+        optimizer.zero_grad()
+    curve = icrf_model.icrf                                        # (C, L); a function of the parameters after update_icrf
+    table = curve.detach()
+    connected = curve.requires_grad                                # False on the very first step
+    linearity_loss, _, grad = linearity_loss_and_table_grad(
+        images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold, upper_valid_threshold,
+        use_relative_linearity_loss, use_uncertainty_weighting, want_grad=connected, row_base=row_base,
+        reduce_fn=reduce_fn)
+    penalties = (alpha * compute_monotonicity_penalty(curve, per_channel=True)
+                 + beta * compute_range_penalty(curve, per_channel=True)
+                 + gamma * compute_endpoint_penalty(curve, per_channel=True)
+                 + delta * compute_smoothness_penalty(curve, per_channel=True))
+    loss = linearity_loss + penalties.detach()
+    if connected:
+        # sum_c loss_c back-propagated once: the C backward() calls of :148-149 accumulate exactly this
+        torch.autograd.backward([penalties.sum(), curve], [None, grad.to(curve.dtype)])
+    for optimizer in optimizers:
+        optimizer.step()
+    icrf_model.update_icrf()
+    if len(optimizers) == 1:
+        loss = torch.sum(loss)
+    return loss.detach()
+
+
+def train_icrf(dataloader: DataLoader, batch_size: int, device, icrf_model: ICRFModelBase,
+               optimizers: Optional[list[Optimizer]] = None, schedulers: Optional[list] = None,
+               use_relative_linearity_loss: bool = True, use_uncertainty_weighting: bool = True, epochs: int = 150,
+               patience: int = 300, alpha: float = 1.0, beta: float = 1.0, gamma: float = 1.0, delta: float = 1.0,
+               lower_valid_threshold: float = 1 / 255, upper_valid_threshold: float = 254 / 255,
+               exposure_ratio_threshold: float = 0.1, *, verbose: bool = True) -> ICRFModelBase:
+    """Training loop with the reference's signature, defaults, early stopping and scheduler handling."""
+    if not isinstance(dataloader, DataLoader):
+        raise TypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
+    if not isinstance(icrf_model, ICRFModelBase):
+        raise TypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
+    if not isinstance(batch_size, int):
+        raise TypeError("batch_size must be an int")
+    dev = as_device(device)
+    channels = icrf_model.channels
+    if batch_size == 1:
+        raise ValueError("Batch size must be larger than 1.")
+    if optimizers is None:
+        optimizers = [torch.optim.Adam(icrf_model.channel_params(c), lr=1e-3, amsgrad=False) for c in range(channels)]
+    previous_lrs = [pg["lr"] for opt in optimizers for pg in opt.param_groups]
+    if schedulers is None:
+        schedulers = [None] * len(optimizers)
+    if len(schedulers) != len(optimizers):
+        raise ValueError(f"Mismatched number of optimizers: {len(optimizers)} and schedulers: {len(schedulers)}.")
+    best_losses = [float("inf")] * channels
+    epochs_without_improvement = [0] * channels
+    icrf_model.train()
+    icrf_model.plot_icrf()
+    for epoch in range(epochs):
+        running_loss = torch.zeros(channels if len(optimizers) > 1 else (), dtype=torch.float64, device=dev)
+        for _, val_batch, std_batch, meta_batch in dataloader:
+            images, stds = stage_batch(val_batch, std_batch, dev)
+            if images.shape[0] < 2:
+                if verbose:
+                    print("Skipped batch due to single image.")
+                continue
+            running_loss += train_icrf_step(
+                icrf_model, optimizers, images, stds, meta_batch["exposure_time"],
+                use_relative_linearity_loss=use_relative_linearity_loss,
+                use_uncertainty_weighting=use_uncertainty_weighting, alpha=alpha, beta=beta, gamma=gamma, delta=delta,
+                lower_valid_threshold=lower_valid_threshold, upper_valid_threshold=upper_valid_threshold,
+                exposure_ratio_threshold=exposure_ratio_threshold)
+        avg_loss = (running_loss / len(dataloader)).cpu().numpy().reshape(-1)
+        if verbose:
+            print(f"Epoch {epoch + 1} Loss: {avg_loss}")
+        for c in range(min(channels, len(avg_loss))):
+            if avg_loss[c] < best_losses[c]:
+                best_losses[c] = avg_loss[c]
+                epochs_without_improvement[c] = 0
+            else:
+                epochs_without_improvement[c] += 1
+        if all(epochs_without_improvement[c] >= patience for c in range(min(channels, len(avg_loss)))):
+            if verbose:
+                print(f"Early stopping triggered for all channels (patience = {patience} epochs).")
+            break
+        for c, scheduler in enumerate(schedulers):
+            if scheduler is not None:
+                scheduler.step(avg_loss[min(c, len(avg_loss) - 1)])
+        for i, optimizer in enumerate(optimizers):
+            current_lr = optimizer.param_groups[0]["lr"]
+            if current_lr != previous_lrs[i] and verbose:
+                print(f"Optimizer {i} learning rate changed to: {current_lr}")
+            previous_lrs[i] = current_lr
+    return icrf_model

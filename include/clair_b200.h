@@ -1,0 +1,161 @@
+/*
+ * clair_b200.h — C ABI of the B200-native radiometric hot path (libclair_b200.so).
+ *
+ * The reference (samivout/clair-torch) is pure Python/torch and has no FFI layer; the boundary it
+ * exposes for this path is its Python API.  Each entry point below replaces the
+ * per-pixel arithmetic of one reference function and is what a reference-side binding (ctypes, see
+ * INTEGRATION.md) would call.  Citations are file:line in the reference repository.
+ *
+ * Conventions
+ *   - every pointer named *_dev is DEVICE memory (fp32 unless stated), contiguous; image stacks are
+ *     (N, C, H, W) with W fastest, exactly as `datasets/collate.py:8-43` hands them over;
+ *   - every pointer named *_host is HOST memory read synchronously during the call;
+ *   - `plane` = H*W of the tensor handed over; `stream` is a cudaStream_t (NULL = default stream);
+ *   - all launches are asynchronous and stream-ordered; no call synchronises the device;
+ *   - return value: 0 on success, a negative CLAIR_E_* code for a rejected argument, a positive
+ *     cudaError_t if the CUDA runtime reported an error.  Nothing throws.  `clair_last_error()` returns
+ *     a thread-local description of the last non-zero return.
+ *   - `curve_row_base_host[c]`: the reference's LINEAR mode reads row `k mod C` of the (C, L) table for
+ *     the element with flat NCHW index k (models/base.py:173-176).  For a whole image the
+ *     row of element (c, p) is `(c*plane + p) mod C`; for a spatial shard the caller passes
+ *     `curve_row_base_host[c] = (flat index of the shard's element (c, 0) in the full frame) mod C`.
+ *     NULL means "whole image" (`(c*plane) mod C`).
+ */
+#ifndef CLAIR_B200_H
+#define CLAIR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CLAIR_API __attribute__((visibility("default")))
+#else
+#define CLAIR_API
+#endif
+
+#define CLAIR_ABI_VERSION 1
+#define CLAIR_MAX_FRAMES 64     /* exposure frames per batch (exposure times travel as kernel arguments) */
+#define CLAIR_MAX_CHANNELS 8
+#define CLAIR_MAX_LUT 1024      /* ICRF samples per channel (reference default 256) */
+#define CLAIR_MAX_PAIRS 2016    /* exposure pairs per batch = 64*63/2 */
+
+#define CLAIR_E_ARG (-1)        /* null pointer / non-positive size / misaligned buffer */
+#define CLAIR_E_LIMIT (-2)      /* a CLAIR_MAX_* limit exceeded */
+#define CLAIR_E_MODE (-3)       /* unknown interpolation mode or flag combination */
+
+/* interpolation modes, values of clair_torch.common.enums.InterpMode (common/enums.py:10-17) */
+#define CLAIR_INTERP_LOOKUP 1
+#define CLAIR_INTERP_LINEAR 2
+
+CLAIR_API int clair_abi_version(void);
+CLAIR_API const char *clair_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+CLAIR_API uint64_t clair_launch_count(void);
+
+/*
+ * ICRF evaluation — replaces ICRFModelBase.forward (models/base.py:135-182): LINEAR (:160-182, rows per
+ * Q1) or LOOKUP (:138-158, round-half-even, true channel).  x_dev is (n_frames, C, plane).
+ *   y_dev      f(x)                                        (required)
+ *   dydx_dev   autograd's d f / d x, LINEAR only           (optional, may be NULL)
+ */
+CLAIR_API int clair_icrf_forward(const float *x_dev, const float *theta_dev, float *y_dev, float *dydx_dev,
+                       int n_frames, int n_channels, int64_t plane, int lut_size, int interp_mode,
+                       const int32_t *curve_row_base_host, void *stream);
+
+/*
+ * Back-propagation of clair_icrf_forward to the table: grad_theta[u, x0] += g*(1-w), grad_theta[u, x1] += g*w
+ * (the index_put of models/base.py:176 under autograd).  grad_theta_dev is (C, L) float64 and is ACCUMULATED
+ * into (zero it first).  LINEAR only.
+ */
+CLAIR_API int clair_icrf_backward_theta(const float *x_dev, const float *grad_y_dev, double *grad_theta_dev,
+                              int n_frames, int n_channels, int64_t plane, int lut_size,
+                              const int32_t *curve_row_base_host, void *workspace_dev, size_t workspace_bytes,
+                              void *stream);
+
+/* Bytes of device scratch the two table-gradient entry points need (replicated fp32 tables the per-element
+ * reductions are spread over); the buffer must be 16-byte aligned and is zeroed by the call itself. */
+CLAIR_API size_t clair_grad_workspace_bytes(int n_channels, int lut_size);
+
+/*
+ * Linearisation of single images with uncertainty — replaces the core of linearize_dataset_generator
+ * (inference/linearization.py:94-106,132): lin = f(x), sigma = sqrt((f'(x) * std)^2); sigma = 0 when
+ * std_dev is NULL (:97).  Inputs are (n_frames, C, plane); each frame is an independent image.
+ */
+CLAIR_API int clair_linearize(const float *val_dev, const float *std_dev, const float *theta_dev, float *lin_dev,
+                    float *sigma_dev, int n_frames, int n_channels, int64_t plane, int lut_size,
+                    const int32_t *curve_row_base_host, void *stream);
+
+/*
+ * One DataLoader batch of the exposure-weighted HDR merge with first-order uncertainty — replaces the
+ * loop body of compute_hdr_image (inference/hdr_merge.py:95-128) including WBOMean.update_values
+ * (common/statistics.py:64-109) and the autograd pass at :107-115, in closed form.
+ *
+ *   val_dev, std_dev      (n_frames, C, plane) fp32, frames sorted by ascending exposure; std_dev may be NULL
+ *                         (then no variance is produced)
+ *   exposure_host         n_frames exposure times in seconds (float64, the collated 'exposure_time')
+ *   theta_dev             (C, lut_size) ICRF table, LINEAR mode; NULL = identity (icrf_model=None, :99-100)
+ *   gaussian_weights      1: w = exp(-30 (x-0.5)^2) (:95 with weight_fn != None); 0: w = 1
+ *   mean_state_dev        (C, plane) float64   running weighted mean      } read unless is_first,
+ *   wsum_state_dev        (C, plane) float32   running sum of weights     } written unless is_final;
+ *   var_state_dev         (C, plane) float32   running variance           } may be NULL if is_first && is_final
+ *   is_first / is_final   first / last batch of the stack
+ *   radiance_dev          written when is_final: (C, plane), float64 if radiance_f64 else float32
+ *                         (the reference returns float64 by type promotion)
+ *   sigma_dev             written when is_final and std_dev != NULL: sqrt(variance), (C, plane) float32
+ */
+CLAIR_API int clair_hdr_merge_update(const float *val_dev, const float *std_dev, const double *exposure_host,
+                           int n_frames, const float *theta_dev, int n_channels, int lut_size, int64_t plane,
+                           const int32_t *curve_row_base_host, int gaussian_weights,
+                           double *mean_state_dev, float *wsum_state_dev, float *var_state_dev,
+                           int is_first, int is_final, void *radiance_dev, int radiance_f64,
+                           float *sigma_dev, void *stream);
+
+/*
+ * Pairwise exposure-ratio statistics — replaces, for one batch, get_pairwise_valid_pixel_mask
+ * (common/general_functions.py:276-312), combined_gaussian_pair_weights (training/losses.py:208-235),
+ * pixelwise_linearity_loss (:13-67) and the reductions of compute_spatial_linearity_loss (:70-108) /
+ * weighted_mean_and_std (common/general_functions.py:118-178), as used by measure_linearity
+ * (inference/measure_linearity.py:41-74) and the forward half of a train_icrf step
+ * (training/icrf_training.py:105-136).
+ *
+ *   pair_i_host, pair_j_host, pair_ratio_host   P pairs from get_valid_exposure_pairs (int32, int32, float64)
+ *   theta_dev            (C, L) table or NULL (identity linearisation, measure_linearity.py:53)
+ *   valid_lo, valid_hi   inclusive validity range, compared in fp32 (training default 1/255, 254/255)
+ *   relative             use_relative_linearity_loss
+ *   unc_weighting        use_uncertainty_weighting (only has an effect when std_dev != NULL)
+ *   sums_dev             (P, C, 5) float64, ACCUMULATED into (zero it first; shards of one image may add
+ *                        into the same buffer, or be all-reduced):
+ *                          [0] sum M*Wt   [1] sum M*Wt*l   [2] sum M*Wt*l^2   [3] sum M*err   [4] sum M
+ *                        from which  mean = s1/max(s0,1e-8),  std = sqrt(max(s2 - 2 mean s1 + mean^2 s0, 0)/max(s0,1e-8)),
+ *                        errmean = s3/max(s4,1e-8).
+ */
+CLAIR_API int clair_pair_stats(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
+                     const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
+                     int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
+                     float valid_lo, float valid_hi, int relative, int unc_weighting, double *sums_dev,
+                     void *stream);
+
+/*
+ * Gradient of the linearity loss of one train_icrf step with respect to the ICRF table — replaces the C
+ * `loss[c].backward(retain_graph=True)` passes (training/icrf_training.py:148-149) for the linearity term,
+ * in closed form.  Arguments as clair_pair_stats, plus
+ *   upstream_dev    (P, C) float64: U[p,c] = dLoss_c/dmean[p,c] / max(s0[p,c],1e-8)
+ *   mean_dev        (P, C) float64: the spatial means (needed when the weights depend on the curve)
+ *   grad_theta_dev  (C, L) float64, ACCUMULATED into (zero it first).
+ *   workspace_dev   clair_grad_workspace_bytes(C, L) bytes of scratch
+ */
+CLAIR_API int clair_pair_grad(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
+                    const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
+                    int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
+                    float valid_lo, float valid_hi, int relative, int unc_weighting,
+                    const double *upstream_dev, const double *mean_dev, double *grad_theta_dev,
+                    void *workspace_dev, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLAIR_B200_H */

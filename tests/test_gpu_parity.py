@@ -1,0 +1,284 @@
+"""GPU parity tests: the sm_100a kernels, called through the public API / C ABI, against
+(a) the fixtures written by the unmodified reference (tests/golden/) and (b) the pinned CPU oracle on larger
+seeded inputs.  Bars (BASELINE.json north_star): indices, masks and pure table look-ups bit-exact;
+radiance, uncertainty, loss statistics within 1e-5 relative; table gradient within 1e-5 of max|grad|.
+"""
+import numpy as np
+import pytest
+import torch
+from torch.utils.data import DataLoader
+
+from _helpers import golden, golden_names, max_abs_over_max, max_rel
+from oracle import clair_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ct():
+    import clair_torch_b200 as pkg
+    pkg._native.load()          # fail loudly if the extension is missing
+    return pkg
+
+
+def _opt(z, k):
+    return z[k] if k in z else None
+
+
+def _loader(ct, z, batch_size):
+    from clair_torch_b200.datasets import ExposureStackDataset, custom_collate
+    vals = [torch.from_numpy(v) for v in z["val"]]
+    stds = None if "std" not in z else [torch.from_numpy(s) for s in z["std"]]
+    ds = ExposureStackDataset(vals, stds, list(z["exposure"]))
+    return DataLoader(ds, batch_size=batch_size, shuffle=False, collate_fn=custom_collate)
+
+
+def _model(ct, theta, mode=None):
+    from clair_torch_b200 import ICRFModelDirect, InterpMode
+    return ICRFModelDirect(icrf=torch.from_numpy(theta).clone(), interpolation_mode=mode or InterpMode.LINEAR).to(DEV)
+
+
+# ---- ICRF evaluation ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("forward_linear"))
+def test_forward_linear_bit_exact(ct, name):
+    z = golden(name)
+    model = _model(ct, z["theta"])
+    x = torch.from_numpy(z["x"]).to(DEV).requires_grad_(True)
+    y = model(x)
+    (dydx,) = torch.autograd.grad(y, x, torch.ones_like(y))
+    assert np.array_equal(y.detach().cpu().numpy(), z["y"])
+    assert np.array_equal(dydx.cpu().numpy(), z["dydx"])
+
+
+@pytest.mark.parametrize("name", golden_names("forward_lookup"))
+def test_forward_lookup_bit_exact(ct, name):
+    z = golden(name)
+    model = _model(ct, z["theta"], ct.InterpMode.LOOKUP)
+    y = model(torch.from_numpy(z["x"]).to(DEV))
+    assert np.array_equal(y.cpu().numpy(), z["y"])
+
+
+@pytest.mark.parametrize("name", golden_names("forward_codes"))
+def test_forward_every_code(ct, name):
+    z = golden(name)
+    x = torch.from_numpy(z["x"]).to(DEV)
+    assert np.array_equal(_model(ct, z["theta"])(x).cpu().numpy(), z["y_linear"])
+    assert np.array_equal(_model(ct, z["theta"], ct.InterpMode.LOOKUP)(x).cpu().numpy(), z["y_lookup"])
+
+
+def test_forward_table_gradient_matches_scatter(ct):
+    """d/d table of sum(g * f(x)) equals the two-tap scatter of the oracle (index_put of models/base.py:176)."""
+    rng = np.random.default_rng(5)
+    x = rng.uniform(-0.05, 1.05, size=(3, 3, 37, 53)).astype(np.float32)
+    g = rng.normal(size=x.shape).astype(np.float32)
+    theta = ct.synthetic.reference_curve(3).numpy()
+    model = _model(ct, theta)
+    model.update_icrf()   # connect the table to the parameters
+    with torch.no_grad():
+        for c, p in enumerate(model.direct_params):
+            p.copy_(torch.from_numpy(theta[c]))
+    model.update_icrf()
+    y = model(torch.from_numpy(x).to(DEV))
+    y.backward(torch.from_numpy(g).to(DEV))
+    got = torch.stack([p.grad for p in model.direct_params]).cpu().numpy().astype(np.float64)
+    _, _, x0, rows = orc.icrf_linear(x, theta)
+    xs = np.clip(x * np.float32(255), 0, 255).astype(np.float32)
+    w = (xs - x0.astype(np.float32)).astype(np.float64)
+    want = np.zeros((3, 256))
+    np.add.at(want, (rows.ravel(), x0.ravel()), (g * (1 - w)).ravel())
+    np.add.at(want, (rows.ravel(), np.minimum(x0 + 1, 255).ravel()), (g * w).ravel())
+    assert max_abs_over_max(got, want) < TOL
+
+
+# ---- HDR merge ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("hdr_"))
+def test_hdr_merge_golden(ct, name):
+    z = golden(name)
+    model = _model(ct, z["theta"]) if "theta" in z else None
+    weight_fn = (lambda img: img) if int(z["gaussian"]) else None
+    rad, sig = ct.compute_hdr_image(_loader(ct, z, int(z["batch_size"])), DEV, model, weight_fn)
+    assert rad.dtype == torch.float64 and tuple(rad.shape) == z["radiance"].shape
+    assert max_rel(rad.cpu().numpy(), z["radiance"]) < TOL
+    if "sigma" in z:
+        assert sig.dtype == torch.float32
+        assert max_rel(sig.cpu().numpy(), z["sigma"]) < TOL
+    else:
+        assert sig is None
+
+
+@pytest.mark.parametrize("bits,batch", [(8, None), (16, None), (8, 2), (16, 4)])
+def test_hdr_merge_vs_oracle_larger(ct, bits, batch):
+    val, std, t = ct.synthetic.make_stack(5 if bits == 8 else 6, 3, 135, 240, bits=bits, seed=99 + bits)
+    theta = ct.synthetic.reference_curve(3)
+    z = {"val": val.numpy(), "std": std.numpy(), "exposure": t}
+    rad, sig = ct.compute_hdr_image(_loader(ct, z, batch or len(t)), DEV, _model(ct, theta.numpy()), max)
+    o_rad, o_sig = orc.hdr_merge(z["val"], z["std"], t, theta.numpy(), True, batch)
+    assert max_rel(rad.cpu().numpy(), o_rad) < 2e-6
+    assert max_rel(sig.cpu().numpy(), o_sig) < 5e-6
+
+
+def test_hdr_merge_fp32_radiance_and_flags(ct):
+    val, std, t = ct.synthetic.make_stack(4, 3, 32, 48, seed=3)
+    z = {"val": val.numpy(), "std": std.numpy(), "exposure": t}
+    theta = ct.synthetic.reference_curve(3)
+    for gaussian in (True, False):
+        for with_model in (True, False):
+            model = _model(ct, theta.numpy()) if with_model else None
+            rad, sig = ct.compute_hdr_image(_loader(ct, z, 4), DEV, model, (max if gaussian else None),
+                                            radiance_dtype=torch.float32)
+            assert rad.dtype == torch.float32
+            o_rad, o_sig = orc.hdr_merge(z["val"], z["std"], t, theta.numpy() if with_model else None, gaussian)
+            assert max_rel(rad.cpu().numpy(), o_rad) < 2e-6
+            assert max_rel(sig.cpu().numpy(), o_sig) < 5e-6
+
+
+def test_hdr_merge_odd_sizes_use_scalar_path(ct):
+    """H*W not divisible by 4 or 2 exercises the VEC=2 / VEC=1 kernels and the k-mod-C row arithmetic."""
+    theta = ct.synthetic.reference_curve(3)
+    for h, w in ((7, 13), (6, 9), (5, 5)):
+        val, std, t = ct.synthetic.make_stack(3, 3, h, w, seed=h * w)
+        z = {"val": val.numpy(), "std": std.numpy(), "exposure": t}
+        rad, sig = ct.compute_hdr_image(_loader(ct, z, 3), DEV, _model(ct, theta.numpy()), max)
+        o_rad, o_sig = orc.hdr_merge(z["val"], z["std"], t, theta.numpy(), True)
+        assert max_rel(rad.cpu().numpy(), o_rad) < 2e-6
+        assert max_rel(sig.cpu().numpy(), o_sig) < 5e-6
+
+
+def test_hdr_merge_row_band_shards_equal_whole_image(ct):
+    """Spatial shards with the right curve_row_base reproduce the whole-image result bit for bit."""
+    from clair_torch_b200 import kernels
+    val, std, t = ct.synthetic.make_stack(4, 3, 40, 50, seed=8)
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    full = kernels.hdr_merge_update(kernels.HdrMergeState(), val.to(DEV), std.to(DEV), t, theta, True, True)
+    for r0, r1 in ((0, 13), (13, 27), (27, 40)):
+        rb = kernels.shard_row_base(3, 40, 50, r0)
+        part = kernels.hdr_merge_update(kernels.HdrMergeState(), val[:, :, r0:r1].contiguous().to(DEV),
+                                        std[:, :, r0:r1].contiguous().to(DEV), t, theta, True, True, row_base=rb)
+        assert torch.equal(part[0], full[0][:, r0:r1])
+        assert torch.equal(part[1], full[1][:, r0:r1])
+
+
+# ---- linearisation -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("linearize_"))
+def test_linearize_bit_exact(ct, name):
+    z = golden(name)
+    model = _model(ct, z["theta"])
+    outs = list(ct.linearize_dataset_generator(_loader(ct, z, 1), DEV, model))
+    assert len(outs) == z["val"].shape[0]
+    for n, (lin, sig, meta) in enumerate(outs):
+        assert lin.device.type == "cpu" and sig.device.type == "cpu"
+        assert np.array_equal(lin.numpy(), z["linearized"][n])
+        assert np.array_equal(sig.numpy(), z["sigma"][n])
+        assert float(meta["exposure_time"][0]) == float(z["exposure"][n])
+
+
+# ---- linearity measurement ---------------------------------------------------------------------------
+def _linearity_flags(name):
+    if name == "linearity_u16_w11":
+        return True, True
+    return "rel1" in name, "unc1" in name
+
+
+@pytest.mark.parametrize("name", golden_names("linearity_"))
+def test_measure_linearity_golden(ct, name):
+    z = golden(name)
+    rel, unc = _linearity_flags(name)
+    model = _model(ct, z["theta"]) if "theta" in z else None
+    ratio, mean, std, err = ct.measure_linearity(_loader(ct, z, len(z["exposure"])), DEV, unc, rel, model)
+    assert np.array_equal(ratio.cpu().numpy(), z["ratio"])
+    assert max_rel(mean.cpu().numpy(), z["mean"]) < TOL
+    assert max_rel(std.cpu().numpy(), z["stddev"]) < TOL
+    if "errmean" in z:
+        assert max_rel(err.cpu().numpy(), z["errmean"]) < TOL
+    else:
+        assert err is None
+
+
+@pytest.mark.parametrize("bits,n,relative,unc", [(8, 7, True, True), (16, 8, True, True), (16, 6, False, True),
+                                                  (8, 10, True, False)])
+def test_pair_stats_vs_oracle_larger(ct, bits, n, relative, unc):
+    from clair_torch_b200 import kernels
+    val, std, t = ct.synthetic.make_stack(n, 3, 96, 130, bits=bits, seed=7 * n)
+    theta = ct.synthetic.reference_curve(3)
+    i_idx, j_idx, ratio = orc.exposure_pairs(t, 0.1)
+    sums = kernels.pair_stats(val.to(DEV), std.to(DEV), i_idx, j_idx, ratio, theta.to(DEV), 1 / 255, 254 / 255,
+                              relative, unc).cpu().numpy()
+    # validity mask: bit-exact through its per-(pair, channel) population count
+    mask = orc.pair_valid_mask(val.numpy(), i_idx, j_idx, 1 / 255, 254 / 255)
+    assert np.array_equal(sums[..., 4], mask.sum(axis=(2, 3)).astype(np.float64))
+    _, o_mean, o_std, o_err = orc.linearity_stats(val.numpy(), std.numpy(), t, theta.numpy(), 0.1, relative=relative,
+                                                  unc_weighting=unc)
+    from clair_torch_b200.inference.measure_linearity import spatial_statistics
+    mean, sd, err = spatial_statistics(torch.from_numpy(sums), True)
+    assert max_rel(mean.numpy(), o_mean) < 2e-6
+    assert max_rel(sd.numpy(), o_std) < 2e-6
+    assert max_rel(err.numpy(), o_err) < 2e-6
+
+
+def test_pair_stats_degenerate_spread(ct):
+    """Identity linearisation of gamma-encoded 16-bit data: the relative loss is almost the same number at every
+    pixel (std << mean), the case a one-pass sum-of-squares loses without float64 accumulation."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.inference.measure_linearity import spatial_statistics
+    val, std, t = ct.synthetic.make_stack(5, 3, 64, 64, bits=16, seed=12)
+    i_idx, j_idx, ratio = orc.exposure_pairs(t, 0.2)
+    sums = kernels.pair_stats(val.to(DEV), std.to(DEV), i_idx, j_idx, ratio, None, 1 / 255, 254 / 255, True, True)
+    mean, sd, err = spatial_statistics(sums.cpu(), True)
+    _, o_mean, o_std, o_err = orc.linearity_stats(val.numpy(), std.numpy(), t, None, 0.2)
+    assert max_rel(mean.numpy(), o_mean) < 2e-6
+    assert max_rel(sd.numpy(), o_std) < TOL
+
+
+# ---- training step -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("trainstep_"))
+def test_train_step_golden(ct, name):
+    """Loss, spatial means, table gradient and the Adam-updated table of every recorded step, each step started
+    from the reference's own table (teacher forcing: a sign-like first Adam step amplifies 1e-8-sized gradient
+    differences into +-lr, so free-running trajectories are not comparable bin by bin)."""
+    from clair_torch_b200.training import linearity_loss_and_table_grad
+    z = golden(name)
+    val = torch.from_numpy(z["val"]).to(DEV)
+    std = torch.from_numpy(z["std"]).to(DEV) if "std" in z else None
+    exposure = torch.from_numpy(z["exposure"])
+    i_idx, j_idx, ratio = ct.common.get_valid_exposure_pairs(exposure, float(z["thr"]))
+    coeffs = tuple(z["coeffs"])
+    for step in range(int(z["n_steps"])):
+        theta = z["theta0"] if step == 0 else z[f"theta_after_{step - 1}"]
+        lin, spatial, grad = linearity_loss_and_table_grad(val, std, i_idx, j_idx, ratio, torch.from_numpy(theta).to(DEV),
+                                                           1 / 255, 254 / 255, bool(z["rel"]), bool(z["unc"]))
+        assert max_rel(lin.cpu().numpy(), z[f"linloss_{step}"]) < TOL
+        assert max_rel(spatial.cpu().numpy(), z[f"spatial_{step}"]) < TOL
+        pens, gpens = orc.curve_penalties(theta)
+        total = grad.cpu().numpy() + sum(k * g for k, g in zip(coeffs, gpens))
+        assert max_abs_over_max(total, z[f"grad_theta_{step}"]) < TOL
+
+
+def test_train_icrf_step_updates_like_reference(ct):
+    """train_icrf_step through the model / optimiser objects: first step moves nothing, afterwards
+    the table follows Adam on the reference's gradient."""
+    z = golden("trainstep_script")
+    from clair_torch_b200 import ICRFModelDirect, train_icrf_step
+    model = ICRFModelDirect(256, 3, initial_power=2.5).to(DEV)
+    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3) for c in range(3)]
+    val, std = torch.from_numpy(z["val"]).to(DEV), torch.from_numpy(z["std"]).to(DEV)
+    exposure = torch.from_numpy(z["exposure"])
+    before = model.icrf.detach().clone()
+    kw = dict(use_relative_linearity_loss=True, use_uncertainty_weighting=False, alpha=10.0, beta=1.0, gamma=1.0,
+              delta=1.0, exposure_ratio_threshold=0.25)
+    loss0 = train_icrf_step(model, opts, val, std, exposure, **kw)
+    assert torch.equal(model.icrf.detach(), before) and model.icrf.requires_grad
+    # now reproduce the recorded first connected step: load the recorded start table into the parameters
+    with torch.no_grad():
+        for c, p in enumerate(model.direct_params):
+            p.copy_(torch.from_numpy(z["theta0"][c]))
+    model.update_icrf()
+    loss1 = train_icrf_step(model, opts, val, std, exposure, **kw)
+    assert max_rel(loss1.cpu().numpy(), z["loss_0"]) < TOL
+    # Adam's first step is lr * g / (|g| + 1e-8): compare only bins whose gradient is far above the 1e-8 knee
+    g = z["grad_theta_0"]
+    strong = np.abs(g) > 1e-4
+    diff = np.abs(model.icrf.detach().cpu().numpy() - z["theta_after_0"])
+    assert diff[strong].max() < 5e-7
+    assert loss0.shape == (3,)
