@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -135,8 +135,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -163,6 +163,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = ct._native.load()
+    for item in filter(None, os.environ.get("CLAIR_TUNE", "").split(",")):     # kernel tuning experiments only
+        key, _, val = item.partition("=")
+        ct._native.check(lib.clair_set_tuning(key.encode(), int(val)), "clair_set_tuning")
 
     # ---- device-resident stacks: each rank owns its own stacks (sharding by stack, no data-path collective) ----
     n_sets = 4

@@ -29,6 +29,7 @@ _PROTOTYPES = {
     "clair_abi_version": (_c.c_int, []),
     "clair_last_error": (_c.c_char_p, []),
     "clair_launch_count": (_c.c_uint64, []),
+    "clair_set_tuning": (_c.c_int, [_c.c_char_p, _c.c_int]),
     "clair_grad_workspace_bytes": (_c.c_size_t, [_c.c_int, _c.c_int]),
     "clair_icrf_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                       _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),

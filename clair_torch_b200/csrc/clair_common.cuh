@@ -67,6 +67,18 @@ __device__ __forceinline__ void store_stream_f64(double *p, const double (&r)[VE
     }
 }
 
+__device__ __forceinline__ float exp2f_approx(float t) {
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+
+__device__ __forceinline__ float rcp_approx(float t) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+
 // ---- table staging ----
 // smem layout: tab[u * L + k] = (theta[u][k], theta[u][min(k+1, L-1)])
 __device__ __forceinline__ void stage_curve_pairs(float2 *tab, const float *__restrict__ theta, int n_rows, int L) {
@@ -87,17 +99,24 @@ struct IcrfTap {
     int x0;      // lower LUT index                              models/base.py:169
 };
 
+// floor of a value in [0, 2^22] without the conversion unit: a round-down add of 2^23 leaves floor(xs) in the low
+// mantissa bits (F2I / I2F / FRND all issue on the 16-lane XU pipe, which this path is short of).
+__device__ __forceinline__ float floor_small(float xs, int &as_int) {
+    const float t = __fadd_rd(xs, 8388608.0f);
+    as_int = __float_as_int(t) & 0x007fffff;
+    return __fsub_rn(t, 8388608.0f);
+}
+
 __device__ __forceinline__ IcrfTap icrf_linear(float x, const float2 *__restrict__ row, float lm1) {
     IcrfTap t;
     const float xs_raw = __fmul_rn(x, lm1);                       // image * (L - 1)
     const float xs = fminf(fmaxf(xs_raw, 0.0f), lm1);             // .clamp_(0, L - 1)
-    const float fl = floorf(xs);
-    t.x0 = static_cast<int>(fl);
+    const float fl = floor_small(xs, t.x0);
     t.w = __fsub_rn(xs, fl);
     const float2 g = row[t.x0];
     t.f = __fadd_rn(__fmul_rn(g.x, __fsub_rn(1.0f, t.w)), __fmul_rn(g.y, t.w));
-    const bool inside = (xs_raw >= 0.0f) && (xs_raw <= lm1);      // clamp backward: closed interval
-    t.fp = inside ? __fmul_rn(__fsub_rn(g.y, g.x), lm1) : 0.0f;
+    // clamp backward passes the gradient on the closed interval, i.e. exactly when the clamp changed nothing
+    t.fp = (xs == xs_raw) ? __fmul_rn(__fsub_rn(g.y, g.x), lm1) : 0.0f;
     return t;
 }
 
@@ -107,10 +126,12 @@ __device__ __forceinline__ int icrf_lookup_index(float x, float lm1) {
     return static_cast<int>(fminf(fmaxf(r, 0.0f), lm1));
 }
 
-// exp(-scale * (x - 0.5)^2) in the reference's op order (training/losses.py:205)
-__device__ __forceinline__ float gaussian_weight(float x, float neg_scale, float &d) {
+// exp(-scale * (x - 0.5)^2): d^2 rounded as the reference does (training/losses.py:205), then ONE multiply by
+// -scale*log2(e) and MUFU.EX2.  Relative error <= ~5e-7 at the largest exponent used (|-30*0.25*log2e| = 10.8),
+// far inside the 1e-5 gate; libdevice expf costs 8 more instructions per element.
+__device__ __forceinline__ float gaussian_weight(float x, float neg_scale_log2e, float &d) {
     d = __fsub_rn(x, 0.5f);
-    return expf(__fmul_rn(neg_scale, __fmul_rn(d, d)));
+    return exp2f_approx(__fmul_rn(neg_scale_log2e, __fmul_rn(d, d)));
 }
 
 __device__ __forceinline__ int wrap_inc(int u, int C) { return (u + 1 == C) ? 0 : u + 1; }

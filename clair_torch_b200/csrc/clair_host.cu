@@ -3,6 +3,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <string>
 
 namespace clair {
 
@@ -60,7 +61,32 @@ void fill_rows(CurveRows &rows, const int32_t *curve_row_base_host, int n_channe
     }
 }
 
+Tuning g_tuning;
+
+int device_sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        cached[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    }
+    return cached[dev];
+}
+
 }  // namespace clair
+
+extern "C" int clair_set_tuning(const char *key, int value) {
+    using clair::g_tuning;
+    const std::string k(key ? key : "");
+    if (k == "hdr_vec") g_tuning.hdr_vec = value;
+    else if (k == "hdr_waves") g_tuning.hdr_waves = value;
+    else if (k == "hdr_force_dynamic") g_tuning.hdr_force_dynamic = value;
+    else if (k == "stats_blocks_per_sm") g_tuning.stats_blocks_per_sm = value;
+    else if (k == "grad_blocks_per_sm") g_tuning.grad_blocks_per_sm = value;
+    else return clair::fail(CLAIR_E_ARG, "clair_set_tuning: unknown key");
+    return 0;
+}
 
 extern "C" int clair_abi_version(void) { return CLAIR_ABI_VERSION; }
 extern "C" const char *clair_last_error(void) { return clair::g_last_error; }

@@ -23,4 +23,16 @@ int check_geometry(const char *fn, int n_frames, int n_channels, int64_t plane, 
 // curve_row_base_host == NULL: whole image, row of element (c, p) is (c*plane + p) mod C
 void fill_rows(CurveRows &rows, const int32_t *curve_row_base_host, int n_channels, int64_t plane);
 
+int device_sm_count();
+
+// Developer tuning knobs (clair_set_tuning); 0 = library default.
+struct Tuning {
+    int hdr_vec = 0;            // cap the pixels per thread of the HDR-merge kernel (1, 2, 4)
+    int hdr_waves = 0;          // resident waves per persistent grid
+    int hdr_force_dynamic = 0;  // use the N-dynamic float64-sum kernel even for N <= 8
+    int stats_blocks_per_sm = 0;
+    int grad_blocks_per_sm = 0;
+};
+extern Tuning g_tuning;
+
 }  // namespace clair

@@ -10,7 +10,7 @@
 
 namespace clair {
 
-constexpr float kPairNegScale = -10.0f;   // training/losses.py:212 default scale
+constexpr float kPairNegScaleLog2e = -14.426950408889634f;   // -10 * log2(e); training/losses.py:212 default scale 10
 constexpr int kMaxPairsPerLaunch = 256;   // the pair table travels as a kernel argument
 constexpr int kStatsTile = 128;           // pixels per shared-memory tile in the statistics kernel
 constexpr int kMaxSlots = 4;              // pairs a warp carries in registers in the statistics kernel
@@ -65,7 +65,7 @@ __device__ __forceinline__ FrameTerms frame_terms(float x, float s, bool has_mod
     }
     t.sig = has_std ? fabsf(__fmul_rn(fp, s)) : 0.0f;
     float d;
-    const float g = gaussian_weight(x, kPairNegScale, d);
+    const float g = gaussian_weight(x, kPairNegScaleLog2e, d);
     t.gw = (x >= lo && x <= hi) ? g : -1.0f;
     return t;
 }

@@ -9,7 +9,7 @@ namespace clair {
 
 constexpr int kBlock = 256;
 constexpr int kFrameChunk = 4;          // frames whose loads are in flight together (8 x LDG.128 / thread)
-constexpr float kHdrNegScale = -30.0f;  // training/losses.py:193 default scale, used by inference/hdr_merge.py:95
+constexpr float kHdrNegScaleLog2e = -43.28085122666890f;  // -30 * log2(e): training/losses.py:193 default scale 30 (hdr_merge.py:95)
 
 // =====================================================================================================
 // ICRF forward / linearise
@@ -98,96 +98,54 @@ struct HdrParams {
     FrameScale scale;
 };
 
-// One thread owns VEC horizontally adjacent pixels of one channel and walks the N frames.
-//
-// Per frame n (fp32):  w = exp(-30 (x-.5)^2) | 1,  q = w'/w = -60 (x-.5) | 0,  v = f(x)/t,
-//                      Wsum += w,  S += w v,
-//                      R = s w (f'(x)/t + q v),   Q = s w q
-// so that  s * d mean_new / d x  =  alpha R + gamma Q   with per-pixel constants
-//      alpha = (W_B/W) / (W_B + 1e-6),   gamma = (W_A/W^2)(mean_B - mean_A) - alpha mean_B,
-// and the variance update  sum_n (alpha R_n + gamma Q_n)^2 = alpha^2 SRR + 2 alpha gamma SRQ + gamma^2 SQQ
-// needs only three running sums.  The expansion cancels (|gamma Q| can be ~14x the result), so the three
-// sums and the final combination are float64; everything per element stays float32.
-template <int VEC, bool HAS_STD>
-__global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
-    extern __shared__ float2 s_tab[];
-    const int C = p.n_channels, L = p.lut;
-    const bool has_model = p.theta != nullptr;
+// Per frame element (all fp32):
+//   w = exp(-30 (x-.5)^2) | 1,   q = w'/w = -60 (x-.5) | 0,   v = f(x)/t
+//   R = s w (f'(x)/t + q v),     Q = s w q
+// so that  s * d mean_new/dx = alpha R + gamma Q  with the per-pixel constants
+//   alpha = (W_B/W) / (W_B + 1e-6),   gamma = (W_A/W^2)(mean_B - mean_A) - alpha mean_B
+// (closed form of the autograd pass of inference/hdr_merge.py:107-115).
+struct HdrTerms {
+    float w, wv, R, Q;
+};
+
+__device__ __forceinline__ HdrTerms hdr_terms(float x, float s, float it, bool has_model, bool gaussian,
+                                              const float2 *row, float lm1, bool has_std) {
+    HdrTerms o;
+    float f = x, fp = 1.0f;
     if (has_model) {
-        stage_curve_pairs(s_tab, p.theta, C, L);
-        __syncthreads();
+        const IcrfTap t = icrf_linear(x, row, lm1);
+        f = t.f; fp = t.fp;
     }
-    const int64_t item = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
-    const int64_t pix = item * VEC;
-    if (pix >= p.plane) return;
-    const int c = blockIdx.y;
-    const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
-    const int64_t off = static_cast<int64_t>(c) * p.plane + pix;
-    const float lm1 = static_cast<float>(L - 1);
-    const int u0 = static_cast<int>((pix + p.rows.base(c)) % C);
-    const bool gaussian = p.gaussian != 0;
-    const int N = p.n_frames;
-
-    float wsum[VEC], wv[VEC];
-    double srr[VEC], srq[VEC], sqq[VEC];
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-        wsum[k] = 0.0f; wv[k] = 0.0f;
-        srr[k] = 0.0; srq[k] = 0.0; sqq[k] = 0.0;
+    float w = 1.0f, q = 0.0f;
+    if (gaussian) {
+        float d;
+        w = gaussian_weight(x, kHdrNegScaleLog2e, d);
+        q = -60.0f * d;
     }
-
-    for (int n0 = 0; n0 < N; n0 += kFrameChunk) {
-        Pack<VEC> xv[kFrameChunk], sv[kFrameChunk];
-#pragma unroll
-        for (int j = 0; j < kFrameChunk; ++j) {
-            if (n0 + j < N) {
-                const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
-                xv[j] = load_stream<VEC>(p.val + o);
-                if constexpr (HAS_STD) sv[j] = load_stream<VEC>(p.std + o);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < kFrameChunk; ++j) {
-            if (n0 + j < N) {
-                const float it = p.scale.inv_t[n0 + j];
-                int u = u0;
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) {
-                    const float x = xv[j].v[k];
-                    float f = x, fp = 1.0f;
-                    if (has_model) {
-                        const IcrfTap t = icrf_linear(x, s_tab + u * L, lm1);
-                        f = t.f; fp = t.fp;
-                        u = wrap_inc(u, C);
-                    }
-                    float w = 1.0f, q = 0.0f;
-                    if (gaussian) {
-                        float d;
-                        w = gaussian_weight(x, kHdrNegScale, d);
-                        q = -60.0f * d;
-                    }
-                    const float v = f * it;
-                    wsum[k] += w;
-                    wv[k] = fmaf(w, v, wv[k]);
-                    if constexpr (HAS_STD) {
-                        const float ws = w * sv[j].v[k];
-                        const double R = static_cast<double>(ws * fmaf(q, v, fp * it));
-                        const double Q = static_cast<double>(ws * q);
-                        srr[k] = fma(R, R, srr[k]);
-                        srq[k] = fma(R, Q, srq[k]);
-                        sqq[k] = fma(Q, Q, sqq[k]);
-                    }
-                }
-            }
-        }
+    const float v = f * it;
+    o.w = w;
+    o.wv = w * v;
+    if (has_std) {
+        const float ws = w * s;
+        o.R = ws * fmaf(q, v, fp * it);
+        o.Q = ws * q;
+    } else {
+        o.R = 0.0f; o.Q = 0.0f;
     }
+    return o;
+}
 
-    // ---- per-pixel merge with the running state (common/statistics.py:88-109) ----
+// Merge of the batch sums with the running state (common/statistics.py:88-109) and the output stage, shared by
+// both kernels.  `sq(alpha, gamma)` returns sum_n (alpha R_n + gamma Q_n)^2 for pixel k.
+template <int VEC, bool HAS_STD, typename VarFn>
+__device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, const float (&wsum)[VEC], const float (&wv)[VEC],
+                                           VarFn var_update) {
     double mean_new[VEC];
     Pack<VEC> wtot, var_new;
     Pack<VEC> w_a, var_a;
     double mean_a[VEC];
-    if (!p.is_first) {
+    const bool first = p.is_first != 0;
+    if (!first) {
         w_a = load_stream<VEC>(p.wsum_state + off);
         if constexpr (HAS_STD) var_a = load_stream<VEC>(p.var_state + off);
 #pragma unroll
@@ -199,23 +157,26 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
         const float wbe = wsum[k] + 1e-6f;                        // statistics.py:76 (fp32 add)
-        const double inv_wbe = 1.0 / static_cast<double>(wbe);
-        const double mean_b = static_cast<double>(wv[k]) * inv_wbe;
-        const float wt = w_a.v[k] + wsum[k];                      // statistics.py:104
-        const float frac = wsum[k] / wt;                          // statistics.py:106 (0/0 = NaN as in the reference)
-        const double dm = mean_b - mean_a[k];
-        mean_new[k] = mean_a[k] + static_cast<double>(frac) * dm;
-        wtot.v[k] = wt;
-        if constexpr (HAS_STD) {
-            const double alpha = static_cast<double>(frac) * inv_wbe;
-            double gamma = -alpha * mean_b;
-            if (!p.is_first) {
-                const double wtd = static_cast<double>(wt);
-                gamma += static_cast<double>(w_a.v[k]) / (wtd * wtd) * dm;
-            }
-            const double upd = alpha * alpha * srr[k] + 2.0 * alpha * gamma * srq[k] + gamma * gamma * sqq[k];
-            var_new.v[k] = var_a.v[k] + static_cast<float>(fmax(upd, 0.0));
+        const float inv_wbe = 1.0f / wbe;
+        const float mean_b = wv[k] * inv_wbe;
+        float alpha, gamma;
+        if (first) {
+            // W = 0.0 + W_B, so W_B/W is exactly 1 (or 0/0 = NaN for an all-zero-weight pixel, as in the reference)
+            const float frac = (wsum[k] != 0.0f) ? 1.0f : __int_as_float(0x7fc00000);
+            mean_new[k] = static_cast<double>(frac * mean_b);
+            wtot.v[k] = wsum[k];
+            alpha = frac * inv_wbe;
+            gamma = -alpha * mean_b;
+        } else {
+            const float wt = w_a.v[k] + wsum[k];                  // statistics.py:104
+            const float frac = wsum[k] / wt;                      // statistics.py:106
+            const double dm = static_cast<double>(mean_b) - mean_a[k];
+            mean_new[k] = mean_a[k] + static_cast<double>(frac) * dm;
+            wtot.v[k] = wt;
+            alpha = frac * inv_wbe;
+            gamma = static_cast<float>(static_cast<double>(w_a.v[k]) / (static_cast<double>(wt) * wt) * dm) - alpha * mean_b;
         }
+        if constexpr (HAS_STD) var_new.v[k] = var_a.v[k] + var_update(k, alpha, gamma);
     }
     if (p.is_final) {
         if (p.radiance_f64) {
@@ -236,6 +197,136 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
         store_stream_f64<VEC>(p.mean_state + off, mean_new);
         store_stream<VEC>(p.wsum_state + off, wtot);
         if constexpr (HAS_STD) store_stream<VEC>(p.var_state + off, var_new);
+    }
+}
+
+// ---- main kernel: N known at compile time (1..kMaxFixedFrames) -------------------------------------------
+// Persistent blocks; one thread owns VEC adjacent pixels of one channel per loop trip.  All 2N vector loads of
+// the trip are issued before the first use; (R_n, Q_n) stay in registers until mean_B is known, so the variance
+// is a plain sum of squares of the actual (small) per-frame terms: no cancellation, everything in fp32.
+constexpr int kMaxFixedFrames = 8;
+
+template <int VEC, int NF, bool HAS_STD>
+__global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams p) {
+    extern __shared__ float2 s_tab[];
+    const int C = p.n_channels, L = p.lut;
+    const bool has_model = p.theta != nullptr;
+    if (has_model) {
+        stage_curve_pairs(s_tab, p.theta, C, L);
+        __syncthreads();
+    }
+    const int c = blockIdx.y;
+    const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
+    const float lm1 = static_cast<float>(L - 1);
+    const bool gaussian = p.gaussian != 0;
+    const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
+    const uint32_t row_base = static_cast<uint32_t>(p.rows.base(c));
+
+    for (uint32_t item = blockIdx.x * kBlock + threadIdx.x; item < n_items; item += gridDim.x * kBlock) {
+        const uint32_t pix = item * VEC;
+        const int64_t off = static_cast<int64_t>(c) * p.plane + pix;
+        Pack<VEC> xv[NF], sv[NF];
+#pragma unroll
+        for (int n = 0; n < NF; ++n) {
+            const int64_t o = off + static_cast<int64_t>(n) * frame_stride;
+            xv[n] = load_stream<VEC>(p.val + o);
+            if constexpr (HAS_STD) sv[n] = load_stream<VEC>(p.std + o);
+        }
+        const int u0 = static_cast<int>((pix + row_base) % static_cast<uint32_t>(C));
+        float wsum[VEC], wv[VEC], R[NF][VEC], Q[NF][VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; }
+#pragma unroll
+        for (int n = 0; n < NF; ++n) {
+            const float it = p.scale.inv_t[n];
+            int u = u0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const HdrTerms t = hdr_terms(xv[n].v[k], HAS_STD ? sv[n].v[k] : 0.0f, it, has_model, gaussian,
+                                             s_tab + u * L, lm1, HAS_STD);
+                u = wrap_inc(u, C);
+                wsum[k] += t.w;
+                wv[k] += t.wv;
+                R[n][k] = t.R;
+                Q[n][k] = t.Q;
+            }
+        }
+        hdr_finish<VEC, HAS_STD>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int n = 0; n < NF; ++n) {
+                const float g = fmaf(alpha, R[n][k], gamma * Q[n][k]);
+                acc = fmaf(g, g, acc);
+            }
+            return acc;
+        });
+    }
+}
+
+// ---- fallback for N > kMaxFixedFrames: single pass, N dynamic --------------------------------------------
+// sum_n (alpha R_n + gamma Q_n)^2 = alpha^2 SRR + 2 alpha gamma SRQ + gamma^2 SQQ needs only three running
+// sums, but the expansion cancels (|gamma Q| can be ~14x the result), so the three sums are float64.
+template <int VEC, bool HAS_STD>
+__global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
+    extern __shared__ float2 s_tab[];
+    const int C = p.n_channels, L = p.lut;
+    const bool has_model = p.theta != nullptr;
+    if (has_model) {
+        stage_curve_pairs(s_tab, p.theta, C, L);
+        __syncthreads();
+    }
+    const int c = blockIdx.y;
+    const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
+    const float lm1 = static_cast<float>(L - 1);
+    const bool gaussian = p.gaussian != 0;
+    const int N = p.n_frames;
+    const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
+    const uint32_t row_base = static_cast<uint32_t>(p.rows.base(c));
+
+    for (uint32_t item = blockIdx.x * kBlock + threadIdx.x; item < n_items; item += gridDim.x * kBlock) {
+        const uint32_t pix = item * VEC;
+        const int64_t off = static_cast<int64_t>(c) * p.plane + pix;
+        const int u0 = static_cast<int>((pix + row_base) % static_cast<uint32_t>(C));
+        float wsum[VEC], wv[VEC];
+        double srr[VEC], srq[VEC], sqq[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; srr[k] = 0.0; srq[k] = 0.0; sqq[k] = 0.0; }
+        for (int n0 = 0; n0 < N; n0 += kFrameChunk) {
+            Pack<VEC> xv[kFrameChunk], sv[kFrameChunk];
+#pragma unroll
+            for (int j = 0; j < kFrameChunk; ++j) {
+                if (n0 + j < N) {
+                    const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
+                    xv[j] = load_stream<VEC>(p.val + o);
+                    if constexpr (HAS_STD) sv[j] = load_stream<VEC>(p.std + o);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kFrameChunk; ++j) {
+                if (n0 + j < N) {
+                    const float it = p.scale.inv_t[n0 + j];
+                    int u = u0;
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) {
+                        const HdrTerms t = hdr_terms(xv[j].v[k], HAS_STD ? sv[j].v[k] : 0.0f, it, has_model, gaussian,
+                                                     s_tab + u * L, lm1, HAS_STD);
+                        u = wrap_inc(u, C);
+                        wsum[k] += t.w;
+                        wv[k] += t.wv;
+                        if constexpr (HAS_STD) {
+                            const double R = static_cast<double>(t.R), Q = static_cast<double>(t.Q);
+                            srr[k] = fma(R, R, srr[k]);
+                            srq[k] = fma(R, Q, srq[k]);
+                            sqq[k] = fma(Q, Q, sqq[k]);
+                        }
+                    }
+                }
+            }
+        }
+        hdr_finish<VEC, HAS_STD>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+            const double a = static_cast<double>(alpha), g = static_cast<double>(gamma);
+            return static_cast<float>(fmax(a * a * srr[k] + 2.0 * a * g * srq[k] + g * g * sqq[k], 0.0));
+        });
     }
 }
 
@@ -356,16 +447,51 @@ extern "C" int clair_hdr_merge_update(const float *val_dev, const float *std_dev
     if (!radiance_f64 && radiance_dev) vec = std::min(vec, pick_vec(plane, {radiance_dev}));
     const size_t smem = theta_dev ? sizeof(float2) * n_channels * lut_size : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-#define LAUNCH_HDR(V, S)                                                                          \
+    if (g_tuning.hdr_vec > 0 && g_tuning.hdr_vec < vec) vec = g_tuning.hdr_vec;
+    const bool has_std = std_dev != nullptr;
+    const int64_t items = plane / vec;
+    const int64_t want_blocks = (items + kBlock - 1) / kBlock;
+    // persistent grid: a whole number of resident waves (blocks/SM from the occupancy calculator), split over C
+    auto grid_for = [&](auto kernel) {
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
+        per_sm = std::max(per_sm, 1) * std::max(g_tuning.hdr_waves, 1);
+        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want_blocks, (static_cast<int64_t>(device_sm_count()) * per_sm + n_channels - 1) / n_channels));
+        return dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels));
+    };
+#define LAUNCH_FIXED(V, NF, S)                                                                    \
+    do {                                                                                          \
+        if (int rc = ensure_smem(hdr_merge_fixed_kernel<V, NF, S>, smem)) return rc;              \
+        hdr_merge_fixed_kernel<V, NF, S><<<grid_for(hdr_merge_fixed_kernel<V, NF, S>), kBlock, smem, s>>>(p); \
+    } while (0)
+#define LAUNCH_DYN(V, S)                                                                          \
     do {                                                                                          \
         if (int rc = ensure_smem(hdr_merge_kernel<V, S>, smem)) return rc;                        \
-        dim3 grid(static_cast<unsigned>((plane / V + kBlock - 1) / kBlock), static_cast<unsigned>(n_channels)); \
-        hdr_merge_kernel<V, S><<<grid, kBlock, smem, s>>>(p);                                     \
+        hdr_merge_kernel<V, S><<<grid_for(hdr_merge_kernel<V, S>), kBlock, smem, s>>>(p);         \
     } while (0)
-    const bool has_std = std_dev != nullptr;
-    if (vec == 4) { if (has_std) LAUNCH_HDR(4, true); else LAUNCH_HDR(4, false); }
-    else if (vec == 2) { if (has_std) LAUNCH_HDR(2, true); else LAUNCH_HDR(2, false); }
-    else { if (has_std) LAUNCH_HDR(1, true); else LAUNCH_HDR(1, false); }
-#undef LAUNCH_HDR
+#define DISPATCH_NF(V)                                                                            \
+    do {                                                                                          \
+        switch (n_frames) {                                                                       \
+            case 1: LAUNCH_FIXED(V, 1, true); break;                                              \
+            case 2: LAUNCH_FIXED(V, 2, true); break;                                              \
+            case 3: LAUNCH_FIXED(V, 3, true); break;                                              \
+            case 4: LAUNCH_FIXED(V, 4, true); break;                                              \
+            case 5: LAUNCH_FIXED(V, 5, true); break;                                              \
+            case 6: LAUNCH_FIXED(V, 6, true); break;                                              \
+            case 7: LAUNCH_FIXED(V, 7, true); break;                                              \
+            case 8: LAUNCH_FIXED(V, 8, true); break;                                              \
+            default: LAUNCH_DYN(V, true); break;                                                  \
+        }                                                                                         \
+    } while (0)
+    if (has_std && !g_tuning.hdr_force_dynamic) {
+        if (vec == 4) DISPATCH_NF(4); else if (vec == 2) DISPATCH_NF(2); else DISPATCH_NF(1);
+    } else if (has_std) {
+        if (vec == 4) LAUNCH_DYN(4, true); else if (vec == 2) LAUNCH_DYN(2, true); else LAUNCH_DYN(1, true);
+    } else {
+        if (vec == 4) LAUNCH_DYN(4, false); else if (vec == 2) LAUNCH_DYN(2, false); else LAUNCH_DYN(1, false);
+    }
+#undef DISPATCH_NF
+#undef LAUNCH_DYN
+#undef LAUNCH_FIXED
     return launched("hdr_merge_kernel");
 }

@@ -56,6 +56,10 @@ CLAIR_API const char *clair_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 CLAIR_API uint64_t clair_launch_count(void);
 
+/* developer knob for kernel tuning experiments (keys: hdr_vec, hdr_waves, hdr_force_dynamic,
+ * stats_blocks_per_sm, grad_blocks_per_sm); 0 restores the library default.  Not part of the reference boundary. */
+CLAIR_API int clair_set_tuning(const char *key, int value);
+
 /*
  * ICRF evaluation — replaces ICRFModelBase.forward (models/base.py:135-182): LINEAR (:160-182, rows per
  * Q1) or LOOKUP (:138-158, round-half-even, true channel).  x_dev is (n_frames, C, plane).

@@ -228,7 +228,9 @@ def test_pair_stats_degenerate_spread(ct):
     mean, sd, err = spatial_statistics(sums.cpu(), True)
     _, o_mean, o_std, o_err = orc.linearity_stats(val.numpy(), std.numpy(), t, None, 0.2)
     assert max_rel(mean.numpy(), o_mean) < 2e-6
-    assert max_rel(sd.numpy(), o_std) < TOL
+    # here std/mean ~ 3e-4: the fp32 rounding of each per-pixel loss (~3e-8 absolute at l ~ 0.46) shows up in the
+    # spread, so the bound is stated relative to the mean the rounding scales with
+    assert np.max(np.abs(sd.numpy() - o_std) / (o_std + 2e-4 * o_mean)) < TOL
 
 
 # ---- training step -----------------------------------------------------------------------------------
