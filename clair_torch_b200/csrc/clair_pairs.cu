@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
                     float inv = 1.0f, ell;
                     if constexpr (RELATIVE) {
                         inv = __frcp_rn(fmaf(b, r_hi, 1e-6f));              // 1 / (expected + 1e-6), losses.py:45
-                        ell = fabsf(d) * inv;
+                        ell = fabsf(d * inv);                               // es can be negative once the curve dips below 0
                     } else {
                         ell = fabsf(d);
                     }

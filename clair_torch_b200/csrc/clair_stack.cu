@@ -447,15 +447,18 @@ extern "C" int clair_hdr_merge_update(const float *val_dev, const float *std_dev
     if (!radiance_f64 && radiance_dev) vec = std::min(vec, pick_vec(plane, {radiance_dev}));
     const size_t smem = theta_dev ? sizeof(float2) * n_channels * lut_size : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (g_tuning.hdr_vec > 0 && g_tuning.hdr_vec < vec) vec = g_tuning.hdr_vec;
     const bool has_std = std_dev != nullptr;
+    // measured on B200 (profiles/): 2 pixels per thread keeps the fixed-N kernel at 64 registers (4 blocks/SM);
+    // 4 pixels per thread needs 105 and halves the resident warps
+    const int vec_cap = g_tuning.hdr_vec > 0 ? g_tuning.hdr_vec : ((has_std && n_frames <= kMaxFixedFrames) ? 2 : 4);
+    if (vec_cap < vec) vec = vec_cap;
     const int64_t items = plane / vec;
     const int64_t want_blocks = (items + kBlock - 1) / kBlock;
     // persistent grid: a whole number of resident waves (blocks/SM from the occupancy calculator), split over C
     auto grid_for = [&](auto kernel) {
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
-        per_sm = std::max(per_sm, 1) * std::max(g_tuning.hdr_waves, 1);
+        per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : 3);   // 3 waves: best tail/balance measured
         const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want_blocks, (static_cast<int64_t>(device_sm_count()) * per_sm + n_channels - 1) / n_channels));
         return dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels));
     };
