@@ -120,6 +120,31 @@ __device__ __forceinline__ IcrfTap icrf_linear(float x, const float2 *__restrict
     return t;
 }
 
+// Same evaluation with the table row given as a pre-biased 32-bit shared-memory address:
+//   row_bias = shared_addr(row) - 8 * 0x4B000000   (mod 2^32)
+// The round-down add of 2^23 leaves the bit pattern 0x4B000000 | x0, so `bits * 8 + row_bias` is the byte address
+// of the (g0, g1) pair: one shift-add instead of mask + multiply-add + shift-add per element.
+__device__ __forceinline__ uint32_t curve_row_bias(const float2 *row) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(row)) - 8u * 0x4B000000u;
+}
+
+__device__ __forceinline__ void icrf_linear_biased(float x, uint32_t row_bias, float lm1, float &f, float &fp) {
+    const float xs_raw = __fmul_rn(x, lm1);
+    const float xs = fminf(fmaxf(xs_raw, 0.0f), lm1);
+    const float t = __fadd_rd(xs, 8388608.0f);
+    const float w = __fsub_rn(xs, __fsub_rn(t, 8388608.0f));
+    float g0, g1;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g0), "=f"(g1) : "r"(static_cast<uint32_t>(__float_as_int(t)) * 8u + row_bias));
+    f = __fadd_rn(__fmul_rn(g0, __fsub_rn(1.0f, w)), __fmul_rn(g1, w));
+    fp = (xs == xs_raw) ? __fmul_rn(__fsub_rn(g1, g0), lm1) : 0.0f;
+}
+
+__device__ __forceinline__ float sqrt_approx(float t) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+
 // LOOKUP mode index: round-half-even, then clamp (models/base.py:145)
 __device__ __forceinline__ int icrf_lookup_index(float x, float lm1) {
     const float r = rintf(__fmul_rn(x, lm1));

@@ -109,13 +109,10 @@ struct HdrTerms {
 };
 
 __device__ __forceinline__ HdrTerms hdr_terms(float x, float s, float it, bool has_model, bool gaussian,
-                                              const float2 *row, float lm1, bool has_std) {
+                                              uint32_t row_bias, float lm1, bool has_std) {
     HdrTerms o;
     float f = x, fp = 1.0f;
-    if (has_model) {
-        const IcrfTap t = icrf_linear(x, row, lm1);
-        f = t.f; fp = t.fp;
-    }
+    if (has_model) icrf_linear_biased(x, row_bias, lm1, f, fp);
     float w = 1.0f, q = 0.0f;
     if (gaussian) {
         float d;
@@ -136,10 +133,38 @@ __device__ __forceinline__ HdrTerms hdr_terms(float x, float s, float it, bool h
 }
 
 // Merge of the batch sums with the running state (common/statistics.py:88-109) and the output stage, shared by
-// both kernels.  `sq(alpha, gamma)` returns sum_n (alpha R_n + gamma Q_n)^2 for pixel k.
-template <int VEC, bool HAS_STD, typename VarFn>
+// both kernels.  `var_update(k, alpha, gamma)` returns sum_n (alpha R_n + gamma Q_n)^2 for pixel k.
+// SINGLE = the whole stack is this one batch (is_first && is_final): no state traffic, no float64.
+template <int VEC, bool HAS_STD, bool SINGLE, typename VarFn>
 __device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, const float (&wsum)[VEC], const float (&wv)[VEC],
                                            VarFn var_update) {
+    if constexpr (SINGLE) {
+        Pack<VEC> rad, sg;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float wbe = wsum[k] + 1e-6f;                    // statistics.py:76 (fp32 add)
+            float inv = rcp_approx(wbe);
+            inv = fmaf(fmaf(-wbe, inv, 1.0f), inv, inv);          // one Newton step: <= 1 ulp
+            const float mean_b = wv[k] * inv;
+            // W = 0.0 + W_B so W_B/W is exactly 1; an all-zero-weight pixel gives 0/0 = NaN as in the reference
+            const float frac = (wsum[k] != 0.0f) ? 1.0f : __int_as_float(0x7fc00000);
+            rad.v[k] = frac * mean_b;
+            if constexpr (HAS_STD) {
+                const float alpha = frac * inv;
+                sg.v[k] = sqrt_approx(var_update(k, alpha, -alpha * mean_b));
+            }
+        }
+        if (p.radiance_f64) {
+            double r64[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) r64[k] = static_cast<double>(rad.v[k]);
+            store_stream_f64<VEC>(static_cast<double *>(p.radiance) + off, r64);
+        } else {
+            store_stream<VEC>(static_cast<float *>(p.radiance) + off, rad);
+        }
+        if constexpr (HAS_STD) store_stream<VEC>(p.sigma + off, sg);
+        return;
+    }
     double mean_new[VEC];
     Pack<VEC> wtot, var_new;
     Pack<VEC> w_a, var_a;
@@ -156,16 +181,16 @@ __device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, cons
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-        const float wbe = wsum[k] + 1e-6f;                        // statistics.py:76 (fp32 add)
-        const float inv_wbe = 1.0f / wbe;
-        const float mean_b = wv[k] * inv_wbe;
+        const float wbe = wsum[k] + 1e-6f;
+        float inv = rcp_approx(wbe);
+        inv = fmaf(fmaf(-wbe, inv, 1.0f), inv, inv);
+        const float mean_b = wv[k] * inv;
         float alpha, gamma;
         if (first) {
-            // W = 0.0 + W_B, so W_B/W is exactly 1 (or 0/0 = NaN for an all-zero-weight pixel, as in the reference)
             const float frac = (wsum[k] != 0.0f) ? 1.0f : __int_as_float(0x7fc00000);
             mean_new[k] = static_cast<double>(frac * mean_b);
             wtot.v[k] = wsum[k];
-            alpha = frac * inv_wbe;
+            alpha = frac * inv;
             gamma = -alpha * mean_b;
         } else {
             const float wt = w_a.v[k] + wsum[k];                  // statistics.py:104
@@ -173,7 +198,7 @@ __device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, cons
             const double dm = static_cast<double>(mean_b) - mean_a[k];
             mean_new[k] = mean_a[k] + static_cast<double>(frac) * dm;
             wtot.v[k] = wt;
-            alpha = frac * inv_wbe;
+            alpha = frac * inv;
             gamma = static_cast<float>(static_cast<double>(w_a.v[k]) / (static_cast<double>(wt) * wt) * dm) - alpha * mean_b;
         }
         if constexpr (HAS_STD) var_new.v[k] = var_a.v[k] + var_update(k, alpha, gamma);
@@ -190,7 +215,7 @@ __device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, cons
         if constexpr (HAS_STD) {
             Pack<VEC> sg;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) sg.v[k] = sqrtf(var_new.v[k]);
+            for (int k = 0; k < VEC; ++k) sg.v[k] = sqrt_approx(var_new.v[k]);
             store_stream<VEC>(p.sigma + off, sg);
         }
     } else {
@@ -200,13 +225,23 @@ __device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, cons
     }
 }
 
+// Table-row bookkeeping of a persistent thread: element (c, pix) reads row (pix + base(c)) mod C, so the VEC
+// row addresses rotate by (stride mod C) per trip; one modulo per thread instead of one per trip.
+template <int VEC>
+struct RowCursor {
+    uint32_t u0, du, C;
+    __device__ __forceinline__ RowCursor(uint32_t first_pix, uint32_t pix_stride, uint32_t row_base, uint32_t channels)
+        : u0((first_pix + row_base) % channels), du(pix_stride % channels), C(channels) {}
+    __device__ __forceinline__ void advance() { u0 += du; u0 = (u0 >= C) ? u0 - C : u0; }
+};
+
 // ---- main kernel: N known at compile time (1..kMaxFixedFrames) -------------------------------------------
 // Persistent blocks; one thread owns VEC adjacent pixels of one channel per loop trip.  All 2N vector loads of
 // the trip are issued before the first use; (R_n, Q_n) stay in registers until mean_B is known, so the variance
 // is a plain sum of squares of the actual (small) per-frame terms: no cancellation, everything in fp32.
 constexpr int kMaxFixedFrames = 8;
 
-template <int VEC, int NF, bool HAS_STD>
+template <int VEC, int NF, bool HAS_STD, bool SINGLE>
 __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams p) {
     extern __shared__ float2 s_tab[];
     const int C = p.n_channels, L = p.lut;
@@ -220,9 +255,13 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
     const float lm1 = static_cast<float>(L - 1);
     const bool gaussian = p.gaussian != 0;
     const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
-    const uint32_t row_base = static_cast<uint32_t>(p.rows.base(c));
+    const uint32_t item_stride = gridDim.x * kBlock;
+    const uint32_t first_item = blockIdx.x * kBlock + threadIdx.x;
+    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
+    const uint32_t tab_bias = curve_row_bias(s_tab);
+    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
 
-    for (uint32_t item = blockIdx.x * kBlock + threadIdx.x; item < n_items; item += gridDim.x * kBlock) {
+    for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
         const uint32_t pix = item * VEC;
         const int64_t off = static_cast<int64_t>(c) * p.plane + pix;
         Pack<VEC> xv[NF], sv[NF];
@@ -232,26 +271,32 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
             xv[n] = load_stream<VEC>(p.val + o);
             if constexpr (HAS_STD) sv[n] = load_stream<VEC>(p.std + o);
         }
-        const int u0 = static_cast<int>((pix + row_base) % static_cast<uint32_t>(C));
+        uint32_t bias[VEC];
+        {
+            uint32_t u = cur.u0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                bias[k] = tab_bias + u * row_bytes;
+                u = (u + 1 == cur.C) ? 0u : u + 1;
+            }
+        }
         float wsum[VEC], wv[VEC], R[NF][VEC], Q[NF][VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; }
 #pragma unroll
         for (int n = 0; n < NF; ++n) {
             const float it = p.scale.inv_t[n];
-            int u = u0;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                const HdrTerms t = hdr_terms(xv[n].v[k], HAS_STD ? sv[n].v[k] : 0.0f, it, has_model, gaussian,
-                                             s_tab + u * L, lm1, HAS_STD);
-                u = wrap_inc(u, C);
+                const HdrTerms t = hdr_terms(xv[n].v[k], HAS_STD ? sv[n].v[k] : 0.0f, it, has_model, gaussian, bias[k], lm1,
+                                             HAS_STD);
                 wsum[k] += t.w;
                 wv[k] += t.wv;
                 R[n][k] = t.R;
                 Q[n][k] = t.Q;
             }
         }
-        hdr_finish<VEC, HAS_STD>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+        hdr_finish<VEC, HAS_STD, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
             float acc = 0.0f;
 #pragma unroll
             for (int n = 0; n < NF; ++n) {
@@ -281,12 +326,24 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
     const bool gaussian = p.gaussian != 0;
     const int N = p.n_frames;
     const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
-    const uint32_t row_base = static_cast<uint32_t>(p.rows.base(c));
+    const uint32_t item_stride = gridDim.x * kBlock;
+    const uint32_t first_item = blockIdx.x * kBlock + threadIdx.x;
+    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
+    const uint32_t tab_bias = curve_row_bias(s_tab);
+    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
 
-    for (uint32_t item = blockIdx.x * kBlock + threadIdx.x; item < n_items; item += gridDim.x * kBlock) {
+    for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
         const uint32_t pix = item * VEC;
         const int64_t off = static_cast<int64_t>(c) * p.plane + pix;
-        const int u0 = static_cast<int>((pix + row_base) % static_cast<uint32_t>(C));
+        uint32_t bias[VEC];
+        {
+            uint32_t u = cur.u0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                bias[k] = tab_bias + u * row_bytes;
+                u = (u + 1 == cur.C) ? 0u : u + 1;
+            }
+        }
         float wsum[VEC], wv[VEC];
         double srr[VEC], srq[VEC], sqq[VEC];
 #pragma unroll
@@ -305,12 +362,10 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
             for (int j = 0; j < kFrameChunk; ++j) {
                 if (n0 + j < N) {
                     const float it = p.scale.inv_t[n0 + j];
-                    int u = u0;
 #pragma unroll
                     for (int k = 0; k < VEC; ++k) {
                         const HdrTerms t = hdr_terms(xv[j].v[k], HAS_STD ? sv[j].v[k] : 0.0f, it, has_model, gaussian,
-                                                     s_tab + u * L, lm1, HAS_STD);
-                        u = wrap_inc(u, C);
+                                                     bias[k], lm1, HAS_STD);
                         wsum[k] += t.w;
                         wv[k] += t.wv;
                         if constexpr (HAS_STD) {
@@ -323,7 +378,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
                 }
             }
         }
-        hdr_finish<VEC, HAS_STD>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+        hdr_finish<VEC, HAS_STD, false>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
             const double a = static_cast<double>(alpha), g = static_cast<double>(gamma);
             return static_cast<float>(fmax(a * a * srr[k] + 2.0 * a * g * srq[k] + g * g * sqq[k], 0.0));
         });
@@ -448,6 +503,7 @@ extern "C" int clair_hdr_merge_update(const float *val_dev, const float *std_dev
     const size_t smem = theta_dev ? sizeof(float2) * n_channels * lut_size : 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool has_std = std_dev != nullptr;
+    const bool single = is_first && is_final;
     // measured on B200 (profiles/): 2 pixels per thread keeps the fixed-N kernel at 64 registers (4 blocks/SM);
     // 4 pixels per thread needs 105 and halves the resident warps
     const int vec_cap = g_tuning.hdr_vec > 0 ? g_tuning.hdr_vec : ((has_std && n_frames <= kMaxFixedFrames) ? 2 : 4);
@@ -458,14 +514,19 @@ extern "C" int clair_hdr_merge_update(const float *val_dev, const float *std_dev
     auto grid_for = [&](auto kernel) {
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
-        per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : 3);   // 3 waves: best tail/balance measured
+        per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : 2);   // 2 waves: best tail/balance measured (profiles/)
         const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want_blocks, (static_cast<int64_t>(device_sm_count()) * per_sm + n_channels - 1) / n_channels));
         return dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels));
     };
 #define LAUNCH_FIXED(V, NF, S)                                                                    \
     do {                                                                                          \
-        if (int rc = ensure_smem(hdr_merge_fixed_kernel<V, NF, S>, smem)) return rc;              \
-        hdr_merge_fixed_kernel<V, NF, S><<<grid_for(hdr_merge_fixed_kernel<V, NF, S>), kBlock, smem, s>>>(p); \
+        if (single) {                                                                             \
+            if (int rc = ensure_smem(hdr_merge_fixed_kernel<V, NF, S, true>, smem)) return rc;    \
+            hdr_merge_fixed_kernel<V, NF, S, true><<<grid_for(hdr_merge_fixed_kernel<V, NF, S, true>), kBlock, smem, s>>>(p); \
+        } else {                                                                                  \
+            if (int rc = ensure_smem(hdr_merge_fixed_kernel<V, NF, S, false>, smem)) return rc;   \
+            hdr_merge_fixed_kernel<V, NF, S, false><<<grid_for(hdr_merge_fixed_kernel<V, NF, S, false>), kBlock, smem, s>>>(p); \
+        }                                                                                         \
     } while (0)
 #define LAUNCH_DYN(V, S)                                                                          \
     do {                                                                                          \

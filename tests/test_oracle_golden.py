@@ -156,3 +156,62 @@ def test_train_step(name):
         # Adam on the reference's own gradient reproduces the reference's next table
         nxt = np.stack([adams[k].step(theta[k], z[f"grad_theta_{step}"][k]) for k in range(c)])
         assert np.max(np.abs(nxt - z[f"theta_after_{step}"])) < 2e-7
+
+
+# ---- the C (OpenMP) twin of the oracle: same fixtures, same bars ---------------------------------------
+from oracle import c_oracle as corc  # noqa: E402
+
+
+@pytest.mark.parametrize("name", golden_names("forward_linear") + golden_names("forward_lookup"))
+def test_c_forward_bit_exact(name):
+    z = golden(name)
+    if "lookup" in name:
+        y, _ = corc.icrf_lookup(z["x"], z["theta"])
+        assert np.array_equal(y, z["y"])
+    else:
+        f, fp, x0 = corc.icrf_linear(z["x"], z["theta"])
+        assert np.array_equal(f, z["y"]) and np.array_equal(fp, z["dydx"])
+        assert np.array_equal(x0, orc.icrf_linear(z["x"], z["theta"])[2])
+
+
+@pytest.mark.parametrize("name", golden_names("hdr_"))
+def test_c_hdr_merge(name):
+    z = golden(name)
+    rad, sig = corc.hdr_merge(z["val"], _opt(z, "std"), z["exposure"], _opt(z, "theta"), bool(z["gaussian"]),
+                              int(z["batch_size"]))
+    assert max_rel(rad.reshape(z["radiance"].shape), z["radiance"]) < 5e-7
+    if "sigma" in z:
+        assert max_rel(sig.reshape(z["sigma"].shape), z["sigma"]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names("linearize_"))
+def test_c_linearize_bit_exact(name):
+    z = golden(name)
+    lin, sig = corc.linearize(z["val"], _opt(z, "std"), z["theta"])
+    assert np.array_equal(lin, z["linearized"]) and np.array_equal(sig, z["sigma"])
+
+
+@pytest.mark.parametrize("name", golden_names("linearity_"))
+def test_c_linearity_stats(name):
+    z = golden(name)
+    rel, unc = _linearity_flags(name)
+    i, j, r = orc.exposure_pairs(z["exposure"], 0.2)
+    m, sd, em = corc.pair_stats(z["val"], _opt(z, "std"), i, j, r, _opt(z, "theta"), relative=rel, unc_weighting=unc)
+    assert max_rel(m, z["mean"]) < 1e-7 and max_rel(sd, z["stddev"]) < 1e-7
+    if "errmean" in z:
+        assert max_rel(em, z["errmean"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", golden_names("trainstep_"))
+def test_c_train_grad(name):
+    z = golden(name)
+    i, j, r = orc.exposure_pairs(z["exposure"], float(z["thr"]))
+    for step in range(int(z["n_steps"])):
+        theta = z["theta0"] if step == 0 else z[f"theta_after_{step - 1}"]
+        lin, mean, grad = corc.train_grad(z["val"], _opt(z, "std"), i, j, r, theta, relative=bool(z["rel"]),
+                                          unc_weighting=bool(z["unc"]))
+        assert max_rel(lin, z[f"linloss_{step}"]) < 1e-6
+        assert max_rel(mean, z[f"spatial_{step}"]) < 1e-6
+        _, gpens = orc.curve_penalties(theta)
+        total = grad + sum(k * g for k, g in zip(tuple(z["coeffs"]), gpens))
+        assert max_abs_over_max(total, z[f"grad_theta_{step}"]) < TOL
