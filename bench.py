@@ -90,46 +90,112 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(rows, threads):
-    """Mpixel*frames/s of the CPU oracle port on a row-cropped sample of the c1 stack."""
-    import numpy as np
-    import torch
-    torch.set_num_threads(max(1, threads))
+def cpu_oracle_rate(rows, repeats=1):
+    """Mpixel*frames/s of the CPU oracle (C + OpenMP port of the reference algorithm, all host threads) on the
+    first `rows` rows of the c1 stack.  Returns (rate, seconds per merge, threads)."""
     import clair_torch_b200.synthetic as syn
-    from oracle import clair_oracle as orc
+    from oracle import c_oracle as corc
     val, std, t = syn.make_stack(N_FRAMES, CHANNELS, rows, WIDTH, bits=BITS, seed=1234)
     theta = syn.reference_curve(CHANNELS, LUT).numpy()
     v, s = val.numpy(), std.numpy()
-    orc.hdr_merge(v[:, :, :8], s[:, :, :8], t, theta, True)          # warm-up
+    corc.hdr_merge(v[:, :, :8], s[:, :, :8], t, theta, True)          # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
-    orc.hdr_merge(v, s, t, theta, True)
-    dt = time.perf_counter() - t0
-    return N_FRAMES * rows * WIDTH / dt / 1e6, dt
+    for _ in range(repeats):
+        corc.hdr_merge(v, s, t, theta, True)
+    dt = (time.perf_counter() - t0) / repeats
+    return N_FRAMES * rows * WIDTH / dt / 1e6, dt, corc.max_threads()
+
+
+REFERENCE_NOTE = ("the reference itself is pure Python/torch and cannot travel to the GPU box; its own CPU path measured in "
+                  "the build container was 5.8 Mpixel*frames/s on 8 cores (BASELINE.md section 2)")
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the CPU implementation of the path (oracle port, all host threads), K timed steps."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    rows = 270
-    vals = []
+    import clair_torch_b200.synthetic as syn
+    from oracle import c_oracle as corc
+    # size the per-step sample so that K steps stay within ~2 minutes: calibrate on 135 rows
+    _, dt135, threads = cpu_oracle_rate(135)
+    budget_s = 100.0
+    rows = int(max(8, min(HEIGHT, 135 * budget_s / max(dt135 * max(args.steps + args.warmup, 1), 1e-9))))
+    val, std, t = syn.make_stack(N_FRAMES, CHANNELS, rows, WIDTH, bits=BITS, seed=1234)
+    theta = syn.reference_curve(CHANNELS, LUT).numpy()
+    v, s = val.numpy(), std.numpy()
     for _ in range(args.warmup):
-        cpu_oracle_rate(rows, cores)
-    t_total = 0.0
+        corc.hdr_merge(v, s, t, theta, True)
+    t0 = time.perf_counter()
     for _ in range(args.steps):
-        rate, dt = cpu_oracle_rate(rows, cores)
-        vals.append(rate)
-        t_total += dt
-    value = sum(vals) / len(vals)
-    sample = f"rows 0..{rows} of 1080 (1/{1080 // rows} of one stack) per step, numpy closed-form oracle port"
+        corc.hdr_merge(v, s, t, theta, True)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    value = N_FRAMES * rows * WIDTH / dt / 1e6
+    sample = (f"rows 0..{rows} of {HEIGHT} of one c1 stack per step ({rows / HEIGHT:.3f} of the workload), C/OpenMP oracle "
+              f"port of the reference algorithm; {REFERENCE_NOTE}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel*frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "Mpixel*frames/s", "cores": 1, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "Mpixel*frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def secondary_metrics(dev):
+    """BASELINE.json's other single-GPU configs, device-resident, CUDA-event timed: c2 ICRF train steps/s and
+    c3 linearity measurement.  Reported under "extra"; the headline metric stays the HDR merge."""
+    import torch
+    import clair_torch_b200 as ct
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.inference.measure_linearity import spatial_statistics
+    out = {}
+    stream = torch.cuda.current_stream(dev)
+
+    def timed(fn, warm, reps):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    # c2: ICRF training, 10 exposures of 1080p 8-bit, 256-bin curve, script settings (SURVEY.md 8(d))
+    val, std, t = ct.synthetic.make_stack(10, CHANNELS, HEIGHT, WIDTH, bits=8, seed=2345, device=dev)
+    exposures = torch.from_numpy(t)
+    model = ct.ICRFModelDirect(256, CHANNELS, ct.InterpMode.LINEAR, 2.5).to(dev)
+    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3) for c in range(CHANNELS)]
+    kw = dict(use_relative_linearity_loss=True, use_uncertainty_weighting=False, alpha=10.0, beta=1.0, gamma=1.0,
+              delta=1.0, exposure_ratio_threshold=0.25)
+    ms = timed(lambda: ct.train_icrf_step(model, opts, val, std, exposures, **kw), 3, 20)
+    kw2 = dict(kw, use_uncertainty_weighting=True, exposure_ratio_threshold=0.1)
+    ms2 = timed(lambda: ct.train_icrf_step(model, opts, val, std, exposures, **kw2), 2, 10)
+    elems = 10 * CHANNELS * HEIGHT * WIDTH
+    out["icrf_train_c2"] = {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "pairs": 17,
+                            "config": "10x3x1080x1920 8-bit, L=256, thr 0.25, relative, no uncertainty weighting, Adam x3",
+                            "hbm_frac_one_pass": elems * 8 / (ms * 1e-3) / 1e9 / peaks()[0],
+                            "defaults_variant": {"steps_per_s": 1e3 / ms2, "ms_per_step": ms2, "pairs": 24,
+                                                 "config": "thr 0.1, uncertainty weighting on"}}
+    del val, std, model, opts
+    # c3: linearity measurement, 16 exposures of 4K 16-bit
+    val, std, t = ct.synthetic.make_stack(16, CHANNELS, 2160, 3840, bits=16, seed=3456, device=dev)
+    theta = ct.synthetic.reference_curve(CHANNELS, LUT).to(dev)
+    i_idx, j_idx, ratio = ct.common.get_valid_exposure_pairs(torch.from_numpy(t), 0.2)
+
+    def lin():
+        sums = kernels.pair_stats(val, std, i_idx, j_idx, ratio, theta, 1 / 255, 254 / 255, True, True)
+        return spatial_statistics(sums, True)
+
+    ms3 = timed(lin, 2, 10)
+    elems3 = 16 * CHANNELS * 2160 * 3840
+    out["linearity_c3"] = {"ms": ms3, "pairs": int(len(i_idx)), "config": "16x3x2160x3840 16-bit, thr 0.2, relative, unc. weighting",
+                           "pair_elements_per_s": len(i_idx) * CHANNELS * 2160 * 3840 / (ms3 * 1e-3),
+                           "hbm_frac": elems3 * 8 / (ms3 * 1e-3) / 1e9 / peaks()[0]}
+    return out
 
 
 def main():
@@ -140,6 +206,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c2 training / c3 linearity secondary timings")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -266,10 +333,16 @@ def main():
         achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rows = 270
-            rate, dt = cpu_oracle_rate(rows, os.cpu_count() or 1)
-            cpu = {"value": rate, "unit": "Mpixel*frames/s", "cores": 1, "kind": "port",
-                   "sample": f"rows 0..{rows} of 1080 of one c1 stack, numpy closed-form oracle port, {dt:.2f} s"}
+            rows = HEIGHT
+            rate, dt, threads = cpu_oracle_rate(rows, repeats=20)
+            cpu = {"value": rate, "unit": "Mpixel*frames/s", "cores": threads, "kind": "port",
+                   "sample": f"20 merges of the full c1 stack ({rows} rows), C/OpenMP oracle port, {dt:.3f} s per merge; "
+                             + REFERENCE_NOTE}
+        extra = None
+        if world == 1 and not args.no_extras:
+            del stacks
+            torch.cuda.empty_cache()
+            extra = secondary_metrics(dev)
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixel*frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -279,11 +352,11 @@ def main():
                        "sharding": "by stack, one rank per GPU, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                         "kernel": "clair::hdr_merge_kernel<4,true>"},
+                         "kernel": "clair::hdr_merge_fixed_kernel<2,5,true,true> (2 px/thread, N=5 in registers, single batch)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms, "api": "clair_torch_b200.compute_hdr_image from pinned host batch"},
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:

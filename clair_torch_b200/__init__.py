@@ -6,7 +6,7 @@ The sub-packages mirror the reference's public surface for this path
 (`clair_torch.models`, `clair_torch.inference`, `clair_torch.training`); the arithmetic runs in hand-written
 CUDA kernels behind the C ABI of `include/clair_b200.h`.  There is no CPU or eager fallback.
 """
-from . import _native, common, datasets, kernels, synthetic  # noqa: F401
+from . import _native, common, datasets, distributed, kernels, synthetic  # noqa: F401
 from .common.enums import InterpMode
 from .inference import compute_hdr_image, linearize_dataset_generator, measure_linearity
 from .models import ICRFModelBase, ICRFModelDirect
