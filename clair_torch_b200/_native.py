@@ -44,6 +44,13 @@ _PROTOTYPES = {
     "clair_pair_stats": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p,
                                     _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
                                     _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "clair_pair_means": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p,
+                                    _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
+                                    _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "clair_pair_upstream": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                       _c.c_void_p, _c.c_void_p]),
+    "clair_curve_penalties": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _c.c_float,
+                                         _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "clair_pair_grad": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p,
                                    _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
                                    _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,

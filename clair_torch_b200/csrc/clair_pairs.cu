@@ -1,8 +1,10 @@
-// Pairwise exposure-ratio kernels: linearity statistics (forward) and the ICRF-table gradient (backward).
+// Pairwise exposure-ratio kernels: linearity statistics (forward) and the ICRF-table gradient (backward),
+// plus the two tiny kernels that close a training step on the device (upstream factors, curve penalties).
 //
-// Both are FP32-issue-bound once there are more than a handful of exposure pairs (P grows as N^2/2), not
-// HBM-bound: every frame element is read from HBM once per launch and then reused from shared memory for
-// all pairs it takes part in.  See DESIGN.md §4-§5.
+// Both big kernels are FP32-issue-bound once there are more than a handful of exposure pairs (P grows as N^2/2),
+// not HBM-bound: every frame element is read from HBM once per launch, its per-frame terms (ICRF value, sigma,
+// Gaussian weight, validity) are evaluated once, and all pairs it takes part in reuse them from shared memory.
+// See DESIGN.md §3.3-§3.5.
 #include "clair_common.cuh"
 #include "clair_host.h"
 
@@ -12,7 +14,7 @@ namespace clair {
 
 constexpr float kPairNegScaleLog2e = -14.426950408889634f;   // -10 * log2(e); training/losses.py:212 default scale 10
 constexpr int kMaxPairsPerLaunch = 256;   // the pair table travels as a kernel argument
-constexpr int kStatsTile = 128;           // pixels per shared-memory tile in the statistics kernel
+constexpr int kStatsTile = 128;           // pixels per shared-memory tile in the statistics kernel (power of two)
 constexpr int kMaxSlots = 4;              // pairs a warp carries in registers in the statistics kernel
 constexpr int kGradCopies = 64;           // replicated gradient tables the REDs are spread over
 
@@ -25,7 +27,7 @@ struct PairTable {
 
 struct PairParams {
     const float *val;
-    const float *std;
+    const float *std;            // nullptr when no per-pair error term is needed
     const float *theta;          // nullptr = identity
     double *sums;                // statistics: (P, C, 5), already offset to this launch's first pair
     const double *upstream;      // gradient: (P, C)
@@ -38,32 +40,37 @@ struct PairParams {
     int n_pairs;                 // pairs in this launch
     int unc_weighting;
     float valid_lo, valid_hi;
+    uint32_t mod_magic;          // ceil(2^16 / C): x mod C for x < 2^13 without a divide
     CurveRows rows;
     PairTable pairs;
 };
+
+__device__ __forceinline__ uint32_t mod_small(uint32_t x, uint32_t C, uint32_t magic) {
+    return x - C * ((x * magic) >> 16);
+}
 
 // Per-frame quantities shared by all pairs a frame element takes part in.
 //   f     linearised value                                     (models/base.py:182)
 //   sig   |f'(x) * std|                                         (training/icrf_training.py:124)
 //   gw    exp(-10 (x-.5)^2) of the RAW value, or -1 when the raw value is outside [valid_lo, valid_hi]
 //         (training/losses.py:229-234 and common/general_functions.py:305 folded into one number)
+//   xs    clamped scaled value x*(L-1): floor = lower LUT index, fraction = interpolation weight
 struct FrameTerms {
     float f, sig, gw, xs;
 };
 
-__device__ __forceinline__ FrameTerms frame_terms(float x, float s, bool has_model, const float2 *row, float lm1,
-                                                  float lo, float hi, bool has_std) {
+template <bool HAS_STD>
+__device__ __forceinline__ FrameTerms frame_terms(float x, float s, bool has_model, uint32_t row_bias, float lm1, float lo,
+                                                  float hi) {
     FrameTerms t;
     float fp = 1.0f;
     t.f = x;
     t.xs = 0.0f;
     if (has_model) {
-        const IcrfTap tap = icrf_linear(x, row, lm1);
-        t.f = tap.f;
-        fp = tap.fp;
-        t.xs = static_cast<float>(tap.x0) + tap.w;     // exact: x0 + w reproduces the clamped scaled value
+        icrf_linear_biased(x, row_bias, lm1, t.f, fp);
+        t.xs = fminf(fmaxf(__fmul_rn(x, lm1), 0.0f), lm1);
     }
-    t.sig = has_std ? fabsf(__fmul_rn(fp, s)) : 0.0f;
+    t.sig = HAS_STD ? fabsf(__fmul_rn(fp, s)) : 0.0f;
     float d;
     const float g = gaussian_weight(x, kPairNegScaleLog2e, d);
     t.gw = (x >= lo && x <= hi) ? g : -1.0f;
@@ -76,13 +83,31 @@ __device__ __forceinline__ float ratio_residual(float a, float b, float r_hi, fl
     return fmaf(-b, r_lo, fmaf(-b, r_hi, a));
 }
 
+__device__ __forceinline__ float rcp_fast(float x) {     // MUFU.RCP + one Newton step: <= 1 ulp
+    const float r = rcp_approx(x);
+    return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
+
+__device__ __forceinline__ float rsqrt_approx(float t) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+    return r;
+}
+
 // =====================================================================================================
 // Statistics kernel.  Block = W warps; a tile of kStatsTile pixels x N frames of one channel is staged in
-// shared memory once (ICRF, sigma, Gaussian weight, validity evaluated once per frame element), then warp w
-// owns pairs w, w+W, ... (at most SLOTS of them) and keeps their five running sums in registers across all
-// tiles of the persistent loop.  One warp reduction and 5 fp64 atomics per (block, pair) at the very end.
+// shared memory once, then warp w owns pairs w, w+W, ... (at most SLOTS of them) and keeps their running sums in
+// registers across all tiles of the persistent loop.
+//   FULL  = measure_linearity: sum w, sum w l, sum w l^2, sum err, count.  Per tile the three weighted sums are
+//           accumulated in fp32 AROUND A PIVOT k (the first valid loss the thread saw): sum w(l-k), sum w(l-k)^2.
+//           Their conversion to pivot 0 happens once per thread in float64, so the variance never sees the
+//           k^2 sum(w) cancellation in fp32 and no per-element float64 / conversion instruction is needed.
+//   !FULL = training: only sum w and sum w l.
+//   ERR   = the per-pair uncertainty term is needed (std images present and either FULL or uncertainty weights).
+// Per tile the fp32 partials are flushed into float64 running sums; one warp reduction and <= 5 fp64 atomics per
+// (block, pair) at the very end.
 // =====================================================================================================
-template <int SLOTS, bool HAS_STD, bool RELATIVE>
+template <int SLOTS, bool ERR, bool RELATIVE, bool FULL>
 __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int C = p.n_channels, L = p.lut, N = p.n_frames;
@@ -90,8 +115,8 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
     float2 *s_tab = reinterpret_cast<float2 *>(s_raw);
     float *s_f = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
     float *s_gw = s_f + N * kStatsTile;
-    float *s_sig = s_gw + N * kStatsTile;               // HAS_STD only
-    float *s_sb = s_sig + N * kStatsTile;               // HAS_STD && RELATIVE only: sig / max(f, 1e-6)
+    float *s_sig = s_gw + N * kStatsTile;               // ERR only
+    float *s_sb = s_sig + N * kStatsTile;               // ERR && RELATIVE only: sig / max(f, 1e-6)
     if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
 
     const int c = blockIdx.y;
@@ -99,38 +124,49 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
     const int n_warps = blockDim.x >> 5;
     const float lm1 = static_cast<float>(L - 1);
     const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
-    const int64_t chan_off = static_cast<int64_t>(c) * p.plane;
-    const int row_base = p.rows.base(c);
+    const float *val_c = p.val + static_cast<int64_t>(c) * p.plane;
+    const float *std_c = ERR ? p.std + static_cast<int64_t>(c) * p.plane : nullptr;
     const bool unc = p.unc_weighting != 0;
+    const uint32_t tab_bias = curve_row_bias(s_tab);
+    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
+    const uint32_t uC = static_cast<uint32_t>(C);
+    const uint32_t plane = static_cast<uint32_t>(p.plane);
 
-    double s0[SLOTS], s1[SLOTS], s2[SLOTS], s3[SLOTS];
-    unsigned int s4[SLOTS];
+    double d0[SLOTS], d1[SLOTS], d2[SLOTS], d3[SLOTS];
+    float pivot[SLOTS];
+    unsigned int cnt[SLOTS];
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) { s0[s] = 0.0; s1[s] = 0.0; s2[s] = 0.0; s3[s] = 0.0; s4[s] = 0u; }
+    for (int s = 0; s < SLOTS; ++s) { d0[s] = 0.0; d1[s] = 0.0; d2[s] = 0.0; d3[s] = 0.0; pivot[s] = 0.0f; cnt[s] = 0u; }
 
-    const int64_t n_tiles = (p.plane + kStatsTile - 1) / kStatsTile;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
+    // table row of the tile's first pixel, advanced incrementally (no divide in the loop)
+    uint32_t u_tile = (blockIdx.x * kStatsTile + static_cast<uint32_t>(p.rows.base(c))) % uC;
+    const uint32_t du_tile = (gridDim.x * kStatsTile) % uC;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();   // previous tile fully consumed (also orders the table staging on the first pass)
-        const int64_t pix0 = tile * kStatsTile;
+        const uint32_t pix0 = tile * kStatsTile;
         for (int e = threadIdx.x; e < N * kStatsTile; e += blockDim.x) {
-            const int n = e / kStatsTile, q = e - n * kStatsTile;
-            const int64_t pix = pix0 + q;
+            const int n = e >> 7;
+            const uint32_t q = static_cast<uint32_t>(e) & (kStatsTile - 1);
+            const uint32_t pix = pix0 + q;
             FrameTerms t;
             t.f = 1.0f; t.sig = 0.0f; t.gw = -1.0f;
-            if (pix < p.plane) {
-                const int64_t o = static_cast<int64_t>(n) * frame_stride + chan_off + pix;
-                const float x = __ldcs(p.val + o);
-                const float s = HAS_STD ? __ldcs(p.std + o) : 0.0f;
-                const int u = static_cast<int>((pix + row_base) % C);
-                t = frame_terms(x, s, has_model, s_tab + u * L, lm1, p.valid_lo, p.valid_hi, HAS_STD);
+            if (pix < plane) {
+                const int64_t o = static_cast<int64_t>(n) * frame_stride + pix;
+                const float x = __ldcs(val_c + o);
+                const float s = ERR ? __ldcs(std_c + o) : 0.0f;
+                const uint32_t u = mod_small(u_tile + q, uC, p.mod_magic);
+                t = frame_terms<ERR>(x, s, has_model, tab_bias + u * row_bytes, lm1, p.valid_lo, p.valid_hi);
             }
             s_f[e] = t.f;
             s_gw[e] = t.gw;
-            if constexpr (HAS_STD) {
+            if constexpr (ERR) {
                 s_sig[e] = t.sig;
-                if constexpr (RELATIVE) s_sb[e] = t.sig / fmaxf(t.f, 1e-6f);   // losses.py:55,58
+                if constexpr (RELATIVE) s_sb[e] = t.sig * rcp_fast(fmaxf(t.f, 1e-6f));   // losses.py:55,58
             }
         }
+        u_tile += du_tile;
+        u_tile = (u_tile >= uC) ? u_tile - uC : u_tile;
         __syncthreads();
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
@@ -138,7 +174,9 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
             if (pr < p.n_pairs) {
                 const int fi = p.pairs.i[pr] * kStatsTile, fj = p.pairs.j[pr] * kStatsTile;
                 const float r_hi = p.pairs.r_hi[pr], r_lo = p.pairs.r_lo[pr];
-                float t3 = 0.0f;
+                float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+                float k = pivot[s];
+                unsigned int n_valid = cnt[s];
 #pragma unroll
                 for (int it = 0; it < kStatsTile / 32; ++it) {
                     const int q = lane + 32 * it;
@@ -148,36 +186,48 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
                     const float d = ratio_residual(a, b, r_hi, r_lo);
                     float inv = 1.0f, ell;
                     if constexpr (RELATIVE) {
-                        inv = __frcp_rn(fmaf(b, r_hi, 1e-6f));              // 1 / (expected + 1e-6), losses.py:45
-                        ell = fabsf(d * inv);                               // es can be negative once the curve dips below 0
+                        inv = rcp_fast(fmaf(b, r_hi, 1e-6f));                 // 1 / (expected + 1e-6), losses.py:45
+                        ell = fabsf(d * inv);                                 // es can be negative once the curve dips below 0
                     } else {
                         ell = fabsf(d);
                     }
                     float wt = gi + gj;
                     float err = 0.0f;
-                    if constexpr (HAS_STD) {
+                    if constexpr (ERR) {
                         const float sa = s_sig[fi + q];
                         if constexpr (RELATIVE) {
-                            const float t1 = sa * inv;
-                            const float t2 = a * s_sb[fj + q] * inv;
-                            err = sqrtf(fmaf(t1, t1, fmaf(t2, t2, 1e-6f)));   // losses.py:57-60
+                            const float e1 = sa * inv;
+                            const float e2 = a * s_sb[fj + q] * inv;
+                            err = sqrt_approx(fmaf(e1, e1, fmaf(e2, e2, 1e-6f)));   // losses.py:57-60
                         } else {
                             const float rs = r_hi * s_sig[fj + q];
-                            err = sqrtf(fmaf(sa, sa, rs * rs));               // losses.py:62
+                            err = sqrt_approx(fmaf(sa, sa, rs * rs));               // losses.py:62
                         }
-                        if (unc) wt += __frcp_rn(err + 1e-6f);                // losses.py:97
+                        if (unc) wt += rcp_fast(err + 1e-6f);                       // losses.py:97
                     }
-                    if (valid) {
-                        const double W = static_cast<double>(wt), Ld = static_cast<double>(ell);
-                        const double WL = W * Ld;
-                        s0[s] += W;
-                        s1[s] += WL;
-                        s2[s] = fma(WL, Ld, s2[s]);
-                        t3 += err;
-                        s4[s] += 1u;
+                    const float w = valid ? wt : 0.0f;
+                    if constexpr (FULL) {
+                        k = (valid && n_valid == 0u) ? ell : k;
+                        n_valid += valid ? 1u : 0u;
+                        const float dl = valid ? ell - k : 0.0f;
+                        const float wdl = w * dl;
+                        t0 += w;
+                        t1 += wdl;
+                        t2 = fmaf(wdl, dl, t2);
+                        if constexpr (ERR) t3 += valid ? err : 0.0f;
+                    } else {
+                        t0 += w;
+                        t1 = fmaf(w, ell, t1);
                     }
                 }
-                if constexpr (HAS_STD) s3[s] += static_cast<double>(t3);
+                d0[s] += static_cast<double>(t0);
+                d1[s] += static_cast<double>(t1);
+                if constexpr (FULL) {
+                    d2[s] += static_cast<double>(t2);
+                    if constexpr (ERR) d3[s] += static_cast<double>(t3);
+                    pivot[s] = k;
+                    cnt[s] = n_valid;
+                }
             }
         }
     }
@@ -186,23 +236,32 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
     for (int s = 0; s < SLOTS; ++s) {
         const int pr = warp + s * n_warps;
         if (pr < p.n_pairs) {     // warp-uniform
-            double v0 = s0[s], v1 = s1[s], v2 = s2[s], v3 = s3[s];
-            unsigned int v4 = s4[s];
+            // back to pivot 0 in float64:  sum w l = B + k W,  sum w l^2 = A + 2 k B + k^2 W
+            const double kd = static_cast<double>(pivot[s]);
+            double v0 = d0[s];
+            double v1 = FULL ? d1[s] + kd * d0[s] : d1[s];
+            double v2 = FULL ? d2[s] + 2.0 * kd * d1[s] + kd * kd * d0[s] : 0.0;
+            double v3 = d3[s];
+            unsigned int v4 = cnt[s];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 v0 += __shfl_xor_sync(0xffffffffu, v0, o);
                 v1 += __shfl_xor_sync(0xffffffffu, v1, o);
-                v2 += __shfl_xor_sync(0xffffffffu, v2, o);
-                v3 += __shfl_xor_sync(0xffffffffu, v3, o);
-                v4 += __shfl_xor_sync(0xffffffffu, v4, o);
+                if constexpr (FULL) {
+                    v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+                    if constexpr (ERR) v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+                    v4 += __shfl_xor_sync(0xffffffffu, v4, o);
+                }
             }
             if (lane == 0) {
                 double *out = p.sums + (static_cast<int64_t>(pr) * C + c) * 5;
                 atomicAdd(out + 0, v0);
                 atomicAdd(out + 1, v1);
-                atomicAdd(out + 2, v2);
-                if constexpr (HAS_STD) atomicAdd(out + 3, v3);
-                atomicAdd(out + 4, static_cast<double>(v4));
+                if constexpr (FULL) {
+                    atomicAdd(out + 2, v2);
+                    if constexpr (ERR) atomicAdd(out + 3, v3);
+                    atomicAdd(out + 4, static_cast<double>(v4));
+                }
             }
         }
     }
@@ -211,8 +270,10 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
 // =====================================================================================================
 // Gradient kernel.  Each warp owns 32 pixels of one channel at a time: the per-frame terms of those pixels
 // go to the warp's private shared-memory slice, every pair is visited by the same lane that owns the pixel
-// (so the per-frame upstream G[n] accumulates without atomics), and each frame element ends with ONE
-// vectorised reduction  red.global.add.v2.f32 {G(1-w), G w}  into one of kGradCopies replicated tables.
+// (so the per-frame upstream G[n] accumulates without atomics; runs of pairs with the same first frame keep
+// that frame's sum in a register), and each frame element ends with ONE vectorised reduction
+// red.global.add.v2.f32 {G(1-w), G w} into one of kGradCopies replicated tables.
+// ERR = the weights contain the inverse-uncertainty term (std images present and uncertainty weighting on).
 // =====================================================================================================
 __device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
@@ -222,122 +283,148 @@ __device__ __forceinline__ void red_add_v2(float *addr, float a, float b) {
 // A[u][x0], A[u][x0+1]; one with odd x0 adds them at B[u][x0+1], B[u][x0+2] (8-byte aligned in both cases).
 // grad[u][k] = A[u][k] + B[u][k+1].
 __device__ __forceinline__ void scatter_taps(float *copy, int C, int L, int u, float xs, float g) {
-    const float fl = floorf(xs);
-    const int x0 = static_cast<int>(fl);
+    int x0;
+    const float fl = floor_small(xs, x0);
     const float w = xs - fl;
     const int lp = L + 2;
     float *base = copy + ((x0 & 1) ? (C * lp + u * lp + x0 + 1) : (u * lp + x0));
     red_add_v2(base, g * (1.0f - w), g * w);
 }
 
-template <bool HAS_STD, bool RELATIVE>
+template <bool ERR, bool RELATIVE>
 __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    const int C = p.n_channels, L = p.lut, N = p.n_frames;
+    const int C = p.n_channels, L = p.lut, N = p.n_frames, P = p.n_pairs;
+    const int c = blockIdx.y;
     float2 *s_tab = reinterpret_cast<float2 *>(s_raw);
+    float *s_up = reinterpret_cast<float *>(s_tab + C * L);      // U[p, c] and mean[p, c] of this channel
+    float *s_mean = s_up + P;
     stage_curve_pairs(s_tab, p.theta, C, L);
+    for (int k = threadIdx.x; k < P; k += blockDim.x) {
+        s_up[k] = static_cast<float>(p.upstream[static_cast<int64_t>(k) * C + c]);
+        s_mean[k] = static_cast<float>(p.mean[static_cast<int64_t>(k) * C + c]);
+    }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_warps = blockDim.x >> 5;
-    constexpr int kArrays = 6;
-    float *slice = reinterpret_cast<float *>(s_tab + C * L) + warp * (kArrays * N * 32);
+    constexpr int kArrays = ERR ? 6 : 4;
+    float *slice = s_mean + P + warp * (kArrays * N * 32);
     float *s_f = slice, *s_gw = slice + N * 32, *s_xs = slice + 2 * N * 32, *s_g = slice + 3 * N * 32;
-    float *s_sig = slice + 4 * N * 32, *s_ib = slice + 5 * N * 32;   // HAS_STD: sigma, 1 / max(f, 1e-6)
+    float *s_sig = slice + 4 * N * 32, *s_ib = slice + 5 * N * 32;   // ERR: sigma, 1 / max(f, 1e-6)
 
-    const int c = blockIdx.y;
     const float lm1 = static_cast<float>(L - 1);
     const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
-    const int64_t chan_off = static_cast<int64_t>(c) * p.plane;
-    const int row_base = p.rows.base(c);
-    const bool unc = p.unc_weighting != 0;
+    const float *val_c = p.val + static_cast<int64_t>(c) * p.plane;
+    const float *std_c = ERR ? p.std + static_cast<int64_t>(c) * p.plane : nullptr;
     const int lp = L + 2;
     float *copy = p.hist + static_cast<int64_t>((blockIdx.x * n_warps + warp) % kGradCopies) * (2 * C * lp);
+    const uint32_t tab_bias = curve_row_bias(s_tab);
+    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
+    const uint32_t uC = static_cast<uint32_t>(C);
+    const uint32_t plane = static_cast<uint32_t>(p.plane);
 
-    const int64_t n_groups = (p.plane + 31) / 32;
-    for (int64_t grp = static_cast<int64_t>(blockIdx.x) * n_warps + warp; grp < n_groups;
-         grp += static_cast<int64_t>(gridDim.x) * n_warps) {
-        const int64_t pix = grp * 32 + lane;
-        const bool live = pix < p.plane;
-        const int u = static_cast<int>((pix + row_base) % C);
+    const uint32_t n_groups = (plane + 31) / 32;
+    const uint32_t grp_stride = gridDim.x * n_warps;
+    uint32_t grp = blockIdx.x * n_warps + warp;
+    uint32_t u = (grp * 32 + lane + static_cast<uint32_t>(p.rows.base(c))) % uC;
+    const uint32_t du = (grp_stride * 32) % uC;
+    for (; grp < n_groups; grp += grp_stride) {
+        const uint32_t pix = grp * 32 + lane;
+        const bool live = pix < plane;
         __syncwarp();
-        for (int n = 0; n < N; ++n) {
-            FrameTerms t;
-            t.f = 1.0f; t.sig = 0.0f; t.gw = -1.0f; t.xs = 0.0f;
-            if (live) {
-                const int64_t o = static_cast<int64_t>(n) * frame_stride + chan_off + pix;
-                const float x = __ldcs(p.val + o);
-                const float s = HAS_STD ? __ldcs(p.std + o) : 0.0f;
-                t = frame_terms(x, s, true, s_tab + u * L, lm1, p.valid_lo, p.valid_hi, HAS_STD);
+        // loads of four frames in flight together, then their arithmetic
+        for (int n0 = 0; n0 < N; n0 += 4) {
+            float xv[4], sv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                xv[k] = 0.0f; sv[k] = 0.0f;
+                if (n0 + k < N && live) {
+                    const int64_t o = static_cast<int64_t>(n0 + k) * frame_stride + pix;
+                    xv[k] = __ldcs(val_c + o);
+                    if constexpr (ERR) sv[k] = __ldcs(std_c + o);
+                }
             }
-            const int e = n * 32 + lane;
-            s_f[e] = t.f; s_gw[e] = t.gw; s_xs[e] = t.xs; s_g[e] = 0.0f;
-            if constexpr (HAS_STD) {
-                s_sig[e] = t.sig;
-                s_ib[e] = __frcp_rn(fmaxf(t.f, 1e-6f));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (n0 + k < N) {
+                    FrameTerms t = frame_terms<ERR>(xv[k], sv[k], true, tab_bias + u * row_bytes, lm1, p.valid_lo, p.valid_hi);
+                    if (!live) t.gw = -1.0f;
+                    const int e = (n0 + k) * 32 + lane;
+                    s_f[e] = t.f; s_gw[e] = t.gw; s_xs[e] = t.xs; s_g[e] = 0.0f;
+                    if constexpr (ERR) {
+                        s_sig[e] = t.sig;
+                        s_ib[e] = rcp_fast(fmaxf(t.f, 1e-6f));
+                    }
+                }
             }
         }
         __syncwarp();
-        for (int pr = 0; pr < p.n_pairs; ++pr) {
-            const int ei = p.pairs.i[pr] * 32 + lane, ej = p.pairs.j[pr] * 32 + lane;
+        int cur_i = -1;
+        float acc_i = 0.0f;
+        for (int pr = 0; pr < P; ++pr) {
+            const int pi = p.pairs.i[pr];
+            if (pi != cur_i) {                                   // uniform across the warp
+                if (cur_i >= 0) s_g[cur_i * 32 + lane] += acc_i;
+                cur_i = pi;
+                acc_i = 0.0f;
+            }
+            const int ei = pi * 32 + lane, ej = p.pairs.j[pr] * 32 + lane;
             const float gi = s_gw[ei], gj = s_gw[ej];
-            if (!((gi >= 0.0f) && (gj >= 0.0f))) continue;      // masked pair elements carry no gradient
+            const bool valid = (gi >= 0.0f) && (gj >= 0.0f);     // masked pair elements carry no gradient
             const float r_hi = p.pairs.r_hi[pr], r_lo = p.pairs.r_lo[pr];
-            const float up = static_cast<float>(__ldg(p.upstream + static_cast<int64_t>(pr) * C + c));
+            const float up = valid ? s_up[pr] : 0.0f;
             const float a = s_f[ei], b = s_f[ej];
             const float d = ratio_residual(a, b, r_hi, r_lo);
             float wt = gi + gj;
             float ga, gb;
             if constexpr (RELATIVE) {
-                const float inv = __frcp_rn(fmaf(b, r_hi, 1e-6f));
+                const float inv = rcp_fast(fmaf(b, r_hi, 1e-6f));
                 const float q = d * inv;
                 const float sgn = (q > 0.0f) ? 1.0f : ((q < 0.0f) ? -1.0f : 0.0f);
                 float extra_a = 0.0f, extra_b = 0.0f;
-                if constexpr (HAS_STD) {
-                    if (unc) {
-                        // the inverse-uncertainty weight depends on the curve through a, es and max(b, 1e-6)
-                        const float sa = s_sig[ei], sb = s_sig[ej], ib = s_ib[ej];
-                        const float t1 = sa * inv;
-                        const float c2 = sb * ib * inv;
-                        const float t2 = a * c2;
-                        const float T = fmaf(t1, t1, fmaf(t2, t2, 1e-6f));
-                        const float err = sqrtf(T);
-                        const float rw = __frcp_rn(err + 1e-6f);
-                        wt += rw;
-                        const float ell = fabsf(q);
-                        const float m = static_cast<float>(__ldg(p.mean + static_cast<int64_t>(pr) * C + c));
-                        // dm/dWt * dWt/derr * derr/dT = (l - m) U * (-rw^2) * 1/(2 err)
-                        const float k = (ell - m) * up * (-0.5f * rw * rw) * __frcp_rn(err);
-                        const float dT_da = 2.0f * t2 * c2;
-                        const float dT_des = -2.0f * inv * (t1 * t1 + t2 * t2);
-                        const float dT_dbs = (b >= 1e-6f) ? (-2.0f * t2 * t2 * ib) : 0.0f;
-                        extra_a = k * dT_da;
-                        extra_b = k * (dT_des * r_hi + dT_dbs);
-                    }
+                if constexpr (ERR) {
+                    // the inverse-uncertainty weight depends on the curve through a, es and max(b, 1e-6)
+                    const float sa = s_sig[ei], sb = s_sig[ej], ib = s_ib[ej];
+                    const float e1 = sa * inv;
+                    const float c2 = sb * ib * inv;
+                    const float e2 = a * c2;
+                    const float T = fmaf(e1, e1, fmaf(e2, e2, 1e-6f));
+                    const float rerr = rsqrt_approx(T);                    // 1 / err
+                    const float rw = rcp_fast(fmaf(T, rerr, 1e-6f));       // 1 / (err + 1e-6)
+                    wt += rw;
+                    // dm/dWt * dWt/derr * derr/dT = (l - m) U * (-rw^2) * 1/(2 err)
+                    const float kk = (fabsf(q) - s_mean[pr]) * up * (-0.5f * rw * rw) * rerr;
+                    const float dT_da = 2.0f * e2 * c2;
+                    const float dT_des = -2.0f * inv * (e1 * e1 + e2 * e2);
+                    const float dT_dbs = (b >= 1e-6f) ? (-2.0f * e2 * e2 * ib) : 0.0f;
+                    extra_a = kk * dT_da;
+                    extra_b = kk * fmaf(dT_des, r_hi, dT_dbs);
                 }
                 const float base = wt * up * sgn * inv;
                 ga = base + extra_a;                                   // dl/da = sgn / es
-                gb = -base * r_hi * (a + 1e-6f) * inv + extra_b;       // dl/db = -sgn r (a + 1e-6) / es^2
+                gb = fmaf(-base * r_hi, (a + 1e-6f) * inv, extra_b);   // dl/db = -sgn r (a + 1e-6) / es^2
             } else {
                 const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
-                if constexpr (HAS_STD) {
-                    if (unc) {
-                        const float sa = s_sig[ei], rs = r_hi * s_sig[ej];
-                        wt += __frcp_rn(sqrtf(fmaf(sa, sa, rs * rs)) + 1e-6f);   // constant wrt the curve
-                    }
+                if constexpr (ERR) {
+                    const float sa = s_sig[ei], rs = r_hi * s_sig[ej];
+                    wt += rcp_fast(sqrt_approx(fmaf(sa, sa, rs * rs)) + 1e-6f);   // constant wrt the curve
                 }
                 const float base = wt * up * sgn;
                 ga = base;
                 gb = -base * r_hi;
             }
-            s_g[ei] += ga;
+            acc_i += ga;
             s_g[ej] += gb;
         }
+        if (cur_i >= 0) s_g[cur_i * 32 + lane] += acc_i;
         __syncwarp();
         for (int n = 0; n < N; ++n) {
             const float g = s_g[n * 32 + lane];
-            if (g != 0.0f) scatter_taps(copy, C, L, u, s_xs[n * 32 + lane], g);
+            if (g != 0.0f) scatter_taps(copy, C, L, static_cast<int>(u), s_xs[n * 32 + lane], g);
         }
+        u += du;
+        u = (u >= uC) ? u - uC : u;
     }
 }
 
@@ -357,18 +444,102 @@ __global__ void __launch_bounds__(256) icrf_backward_theta_kernel(const float *_
     scatter_taps(copy, C, L, u, xs, g);
 }
 
-// grad[u][k] += sum over copies of A[u][k] + B[u][k+1], in float64
-__global__ void grad_finalize_kernel(const float *__restrict__ hist, double *grad, int C, int L) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// grad[u][k] += sum over copies of A[u][k] + B[u][k+1], in float64; one warp per table entry
+__global__ void __launch_bounds__(256) grad_finalize_kernel(const float *__restrict__ hist, double *grad, int C, int L) {
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= C * L) return;
     const int u = i / L, k = i - u * L;
     const int lp = L + 2;
     double acc = 0.0;
-    for (int r = 0; r < kGradCopies; ++r) {
+    for (int r = lane; r < kGradCopies; r += 32) {
         const float *copy = hist + static_cast<int64_t>(r) * (2 * C * lp);
         acc += static_cast<double>(copy[u * lp + k]) + static_cast<double>(copy[C * lp + u * lp + k + 1]);
     }
-    grad[i] += acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) grad[i] += acc;
+}
+
+// =====================================================================================================
+// Closing a training step on the device (training/icrf_training.py:133-146): (P, C)-sized
+// algebra and the four curve penalties with their gradients.  One block each; they exist because the same
+// arithmetic as ~100 separate 3-microsecond ATen launches dominated the step time.
+// =====================================================================================================
+// mean[p,c] = s1/max(s0,1e-8); linloss[c] = sqrt(sum_p mean^2); upstream[p,c] = mean/linloss/max(s0,1e-8) (0 if linloss = 0);
+// mean_for_grad = mean, or 0 where the denominator was clamped (no d/dWt through a clamped denominator)
+__global__ void __launch_bounds__(256) pair_upstream_kernel(const double *__restrict__ sums, int P, int C, double *linloss,
+                                                            double *mean, double *upstream, double *mean_for_grad) {
+    __shared__ double s_lin[CLAIR_MAX_CHANNELS];
+    const int total = P * C;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const double s0 = sums[e * 5 + 0], s1 = sums[e * 5 + 1];
+        mean[e] = s1 / fmax(s0, 1e-8);                            // common/general_functions.py:156-160
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        double acc = 0.0;
+        for (int k = 0; k < P; ++k) {
+            const double m = mean[k * C + threadIdx.x];
+            acc += m * m;
+        }
+        const double l = sqrt(acc);                               // training/icrf_training.py:136
+        s_lin[threadIdx.x] = l;
+        linloss[threadIdx.x] = l;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const double s0 = sums[e * 5 + 0];
+        const double l = s_lin[e % C];
+        const double m = mean[e];
+        upstream[e] = (l > 0.0) ? m / l / fmax(s0, 1e-8) : 0.0;
+        mean_for_grad[e] = (s0 < 1e-8) ? 0.0 : m;
+    }
+}
+
+// pen[c] = alpha*monotonicity + beta*range + gamma*endpoints + delta*smoothness (training/losses.py:111-190, per channel)
+// and grad[c][k] += d pen[c] / d theta[c][k].  One block per channel, fp32 arithmetic like the reference's.
+__global__ void __launch_bounds__(256) curve_penalty_kernel(const float *__restrict__ theta, int C, int L, float alpha, float beta,
+                                                            float gamma, float delta, double *pen, double *grad) {
+    __shared__ float s_red[256];
+    const int c = blockIdx.x;
+    const float *th = theta + static_cast<int64_t>(c) * L;
+    float local = 0.0f;
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+        const float t = th[k];
+        float g = 0.0f;
+        // monotonicity: sum [df <= 0] df^2 over df = th[k+1] - th[k]
+        if (k + 1 < L) {
+            const float df = th[k + 1] - t;
+            if (df <= 0.0f) { local += alpha * df * df; g -= alpha * 2.0f * df; }
+        }
+        if (k >= 1) {
+            const float df = t - th[k - 1];
+            if (df <= 0.0f) g += alpha * 2.0f * df;
+        }
+        // range: relu(-t) + relu(t - 1)
+        local += beta * (fmaxf(-t, 0.0f) + fmaxf(t - 1.0f, 0.0f));
+        g += beta * ((t > 1.0f ? 1.0f : 0.0f) - (t < 0.0f ? 1.0f : 0.0f));
+        // endpoints: th[0]^2 + (th[L-1] - 1)^2
+        if (k == 0) { local += gamma * t * t; g += gamma * 2.0f * t; }
+        if (k == L - 1) { local += gamma * (t - 1.0f) * (t - 1.0f); g += gamma * 2.0f * (t - 1.0f); }
+        // smoothness: sum (th[k] - 2 th[k+1] + th[k+2])^2; entry k is the left, middle and right tap of three terms
+        if (k + 2 < L) {
+            const float sd = t - 2.0f * th[k + 1] + th[k + 2];
+            local += delta * sd * sd;
+            g += delta * 2.0f * sd;
+        }
+        if (k >= 1 && k + 1 < L) g -= delta * 4.0f * (th[k - 1] - 2.0f * t + th[k + 1]);
+        if (k >= 2) g += delta * 2.0f * (th[k - 2] - 2.0f * th[k - 1] + t);
+        grad[static_cast<int64_t>(c) * L + k] += static_cast<double>(g);
+    }
+    s_red[threadIdx.x] = local;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pen[c] = static_cast<double>(s_red[0]);
 }
 
 }  // namespace clair
@@ -379,19 +550,6 @@ __global__ void grad_finalize_kernel(const float *__restrict__ hist, double *gra
 using namespace clair;
 
 namespace {
-
-int sm_count() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            cached = n;
-        else
-            cached = 148;
-    }
-    return cached;
-}
 
 int fill_pairs(const char *fn, PairTable &t, const int32_t *pi, const int32_t *pj, const double *pr, int first, int count,
                int n_frames) {
@@ -434,64 +592,101 @@ void pick_stats_shape(int count, int &warps, int &slots) {
     warps = best_w; slots = best_s;
 }
 
+void common_params(PairParams &p, const float *val, const float *std, const float *theta, int n_frames, int n_channels,
+                   int64_t plane, int lut, const int32_t *row_base_host, float lo, float hi, int unc) {
+    p.val = val; p.std = std; p.theta = theta;
+    p.plane = plane; p.n_frames = n_frames; p.n_channels = n_channels; p.lut = lut;
+    p.unc_weighting = unc; p.valid_lo = lo; p.valid_hi = hi;
+    p.mod_magic = (65536u + n_channels - 1) / n_channels;
+    fill_rows(p.rows, row_base_host, n_channels, plane);
+}
+
 }  // namespace
+
+static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
+                           const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host, int n_pairs,
+                           const float *theta_dev, int lut_size, const int32_t *curve_row_base_host, float valid_lo,
+                           float valid_hi, int relative, int unc_weighting, int full, double *sums_dev, void *stream) {
+    const char *fn = full ? "clair_pair_stats" : "clair_pair_means";
+    if (!val_dev || !sums_dev) return fail(CLAIR_E_ARG, "clair_pair_stats: null buffer");
+    if (n_pairs < 0 || (n_pairs > 0 && (!pair_i_host || !pair_j_host || !pair_ratio_host)))
+        return fail(CLAIR_E_ARG, "clair_pair_stats: pair table missing");
+    if (theta_dev == nullptr && lut_size <= 0) lut_size = 2;
+    if (int rc = check_geometry(fn, n_frames, n_channels, plane, lut_size, true)) return rc;
+    if (n_pairs > CLAIR_MAX_PAIRS) return fail(CLAIR_E_LIMIT, "clair_pair_stats: more than CLAIR_MAX_PAIRS pairs");
+    if (n_pairs == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // the uncertainty term is only evaluated (and the std images only read) when something uses it
+    const bool err = std_dev != nullptr && (full || unc_weighting);
+    const int arrays = 2 + (err ? (relative ? 2 : 1) : 0);
+    const size_t smem = (theta_dev ? sizeof(float2) * n_channels * lut_size : 0) + sizeof(float) * arrays * n_frames * kStatsTile;
+    const int per_launch = 16 * kMaxSlots;   // 64 pairs: 16 warps x 4 register slots
+    const int n_launches = (n_pairs + per_launch - 1) / per_launch;
+    int first = 0;
+    for (int l = 0; l < n_launches; ++l) {
+        const int count = (n_pairs - first + (n_launches - l) - 1) / (n_launches - l);   // balanced chunks
+        PairParams p{};
+        common_params(p, val_dev, err ? std_dev : nullptr, theta_dev, n_frames, n_channels, plane, lut_size, curve_row_base_host,
+                      valid_lo, valid_hi, unc_weighting);
+        p.sums = sums_dev + static_cast<int64_t>(first) * n_channels * 5;
+        p.n_pairs = count;
+        if (int rc = fill_pairs(fn, p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
+        int warps, slots;
+        pick_stats_shape(count, warps, slots);
+        const int64_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
+        auto launch = [&](auto kernel) -> int {
+            if (int rc = set_smem(kernel, smem)) return rc;
+            int per_sm = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
+            per_sm = g_tuning.stats_blocks_per_sm > 0 ? g_tuning.stats_blocks_per_sm : std::max(per_sm, 1);
+            const int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, (static_cast<int64_t>(device_sm_count()) * per_sm + n_channels - 1) / n_channels));
+            kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), warps * 32, smem, s>>>(p);
+            return 0;
+        };
+        int rc = 0;
+#define STATS_CASE(S)                                                                                   \
+    case S:                                                                                             \
+        if (err) {                                                                                      \
+            if (relative) rc = full ? launch(pair_stats_kernel<S, true, true, true>) : launch(pair_stats_kernel<S, true, true, false>);   \
+            else rc = full ? launch(pair_stats_kernel<S, true, false, true>) : launch(pair_stats_kernel<S, true, false, false>);         \
+        } else {                                                                                        \
+            if (relative) rc = full ? launch(pair_stats_kernel<S, false, true, true>) : launch(pair_stats_kernel<S, false, true, false>); \
+            else rc = full ? launch(pair_stats_kernel<S, false, false, true>) : launch(pair_stats_kernel<S, false, false, false>);       \
+        }                                                                                               \
+        break;
+        switch (slots) {
+            STATS_CASE(1)
+            STATS_CASE(2)
+            STATS_CASE(3)
+            default:
+            STATS_CASE(4)
+        }
+#undef STATS_CASE
+        if (rc) return rc;
+        if (int rc2 = launched("pair_stats_kernel")) return rc2;
+        first += count;
+    }
+    return 0;
+}
 
 extern "C" int clair_pair_stats(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
                                 const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
                                 int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
                                 float valid_lo, float valid_hi, int relative, int unc_weighting, double *sums_dev,
                                 void *stream) {
-    if (!val_dev || !sums_dev) return fail(CLAIR_E_ARG, "clair_pair_stats: null buffer");
-    if (n_pairs < 0 || (n_pairs > 0 && (!pair_i_host || !pair_j_host || !pair_ratio_host)))
-        return fail(CLAIR_E_ARG, "clair_pair_stats: pair table missing");
-    if (theta_dev == nullptr && lut_size <= 0) lut_size = 2;
-    if (int rc = check_geometry("clair_pair_stats", n_frames, n_channels, plane, lut_size, true)) return rc;
-    if (n_pairs > CLAIR_MAX_PAIRS) return fail(CLAIR_E_LIMIT, "clair_pair_stats: more than CLAIR_MAX_PAIRS pairs");
-    if (n_pairs == 0) return 0;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool has_std = std_dev != nullptr;
-    const int arrays = 2 + (has_std ? (relative ? 2 : 1) : 0);
-    const size_t smem = (theta_dev ? sizeof(float2) * n_channels * lut_size : 0) + sizeof(float) * arrays * n_frames * kStatsTile;
-    const int per_launch = 16 * kMaxSlots < kMaxPairsPerLaunch ? 16 * kMaxSlots : kMaxPairsPerLaunch;   // 64
-    const int n_launches = (n_pairs + per_launch - 1) / per_launch;
-    int first = 0;
-    for (int l = 0; l < n_launches; ++l) {
-        const int count = (n_pairs - first + (n_launches - l) - 1) / (n_launches - l);   // balanced chunks
-        PairParams p{};
-        p.val = val_dev; p.std = std_dev; p.theta = theta_dev;
-        p.sums = sums_dev + static_cast<int64_t>(first) * n_channels * 5;
-        p.plane = plane; p.n_frames = n_frames; p.n_channels = n_channels; p.lut = lut_size;
-        p.n_pairs = count; p.unc_weighting = unc_weighting; p.valid_lo = valid_lo; p.valid_hi = valid_hi;
-        fill_rows(p.rows, curve_row_base_host, n_channels, plane);
-        if (int rc = fill_pairs("clair_pair_stats", p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
-        int warps, slots;
-        pick_stats_shape(count, warps, slots);
-        const int64_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
-        const int blocks_per_sm = std::max(1, std::min<int>(2048 / (warps * 32), static_cast<int>((200 * 1024) / std::max<size_t>(smem, 1))));
-        const int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, static_cast<int64_t>(sm_count()) * blocks_per_sm / n_channels));
-        dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels));
-#define LAUNCH_STATS(S, HS, RL)                                                             \
-    do {                                                                                    \
-        if (int rc = set_smem(pair_stats_kernel<S, HS, RL>, smem)) return rc;               \
-        pair_stats_kernel<S, HS, RL><<<grid, warps * 32, smem, s>>>(p);                     \
-    } while (0)
-#define DISPATCH_STATS(S)                                                                   \
-    do {                                                                                    \
-        if (has_std) { if (relative) LAUNCH_STATS(S, true, true); else LAUNCH_STATS(S, true, false); } \
-        else { if (relative) LAUNCH_STATS(S, false, true); else LAUNCH_STATS(S, false, false); }       \
-    } while (0)
-        switch (slots) {
-            case 1: DISPATCH_STATS(1); break;
-            case 2: DISPATCH_STATS(2); break;
-            case 3: DISPATCH_STATS(3); break;
-            default: DISPATCH_STATS(4); break;
-        }
-#undef DISPATCH_STATS
-#undef LAUNCH_STATS
-        if (int rc = launched("pair_stats_kernel")) return rc;
-        first += count;
-    }
-    return 0;
+    return pair_stats_impl(val_dev, std_dev, n_frames, n_channels, plane, pair_i_host, pair_j_host, pair_ratio_host, n_pairs,
+                           theta_dev, lut_size, curve_row_base_host, valid_lo, valid_hi, relative, unc_weighting, 1, sums_dev,
+                           stream);
+}
+
+extern "C" int clair_pair_means(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
+                                const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
+                                int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
+                                float valid_lo, float valid_hi, int relative, int unc_weighting, double *sums_dev,
+                                void *stream) {
+    return pair_stats_impl(val_dev, std_dev, n_frames, n_channels, plane, pair_i_host, pair_j_host, pair_ratio_host, n_pairs,
+                           theta_dev, lut_size, curve_row_base_host, valid_lo, valid_hi, relative, unc_weighting, 0, sums_dev,
+                           stream);
 }
 
 extern "C" size_t clair_grad_workspace_bytes(int n_channels, int lut_size) {
@@ -502,7 +697,7 @@ extern "C" size_t clair_grad_workspace_bytes(int n_channels, int lut_size) {
 namespace {
 int finalize_grad(const float *hist, double *grad, int C, int L, cudaStream_t s) {
     const int n = C * L;
-    grad_finalize_kernel<<<(n + 255) / 256, 256, 0, s>>>(hist, grad, C, L);
+    grad_finalize_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(hist, grad, C, L);
     return launched("grad_finalize_kernel");
 }
 }  // namespace
@@ -513,11 +708,12 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
                                float valid_lo, float valid_hi, int relative, int unc_weighting,
                                const double *upstream_dev, const double *mean_dev, double *grad_theta_dev,
                                void *workspace_dev, size_t workspace_bytes, void *stream) {
+    const char *fn = "clair_pair_grad";
     if (!val_dev || !theta_dev || !upstream_dev || !mean_dev || !grad_theta_dev || !workspace_dev)
         return fail(CLAIR_E_ARG, "clair_pair_grad: null buffer");
     if (n_pairs < 0 || (n_pairs > 0 && (!pair_i_host || !pair_j_host || !pair_ratio_host)))
         return fail(CLAIR_E_ARG, "clair_pair_grad: pair table missing");
-    if (int rc = check_geometry("clair_pair_grad", n_frames, n_channels, plane, lut_size, true)) return rc;
+    if (int rc = check_geometry(fn, n_frames, n_channels, plane, lut_size, true)) return rc;
     if (n_pairs > CLAIR_MAX_PAIRS) return fail(CLAIR_E_LIMIT, "clair_pair_grad: more than CLAIR_MAX_PAIRS pairs");
     const size_t need = clair_grad_workspace_bytes(n_channels, lut_size);
     if (workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace_dev) % 16 != 0)
@@ -525,37 +721,39 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
     if (n_pairs == 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (cudaError_t e = cudaMemsetAsync(workspace_dev, 0, need, s); e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(workspace)");
-    const bool has_std = std_dev != nullptr;
-    const size_t tab_bytes = sizeof(float2) * n_channels * lut_size;
-    const size_t per_warp = sizeof(float) * 6 * n_frames * 32;
-    const int warps = static_cast<int>(std::max<size_t>(1, std::min<size_t>(8, (200 * 1024 - tab_bytes) / per_warp)));
-    const size_t smem = tab_bytes + per_warp * warps;
-    const int64_t n_groups = (plane + 31) / 32;
-    const int blocks_per_sm = std::max(1, std::min<int>(8, static_cast<int>((200 * 1024) / smem)));
+    const bool err = std_dev != nullptr && unc_weighting;
     int first = 0;
     while (first < n_pairs) {
         const int count = std::min(kMaxPairsPerLaunch, n_pairs - first);
+        const size_t fixed_bytes = sizeof(float2) * n_channels * lut_size + sizeof(float) * 2 * count;
+        const size_t per_warp = sizeof(float) * (err ? 6 : 4) * n_frames * 32;
+        // 4 warps per block: more, smaller blocks balance better across the SMs than 8-warp blocks
+        const int warps = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (200 * 1024 - fixed_bytes) / per_warp)));
+        const size_t smem = fixed_bytes + per_warp * warps;
         PairParams p{};
-        p.val = val_dev; p.std = std_dev; p.theta = theta_dev;
+        common_params(p, val_dev, err ? std_dev : nullptr, theta_dev, n_frames, n_channels, plane, lut_size, curve_row_base_host,
+                      valid_lo, valid_hi, unc_weighting);
         p.upstream = upstream_dev + static_cast<int64_t>(first) * n_channels;
         p.mean = mean_dev + static_cast<int64_t>(first) * n_channels;
         p.hist = static_cast<float *>(workspace_dev);
-        p.plane = plane; p.n_frames = n_frames; p.n_channels = n_channels; p.lut = lut_size;
-        p.n_pairs = count; p.unc_weighting = unc_weighting; p.valid_lo = valid_lo; p.valid_hi = valid_hi;
-        fill_rows(p.rows, curve_row_base_host, n_channels, plane);
-        if (int rc = fill_pairs("clair_pair_grad", p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
-        const int64_t gx = std::min<int64_t>((n_groups + warps - 1) / warps,
-                                             std::max<int64_t>(1, static_cast<int64_t>(sm_count()) * blocks_per_sm / n_channels));
-        dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels));
-#define LAUNCH_GRAD(HS, RL)                                                                 \
-    do {                                                                                    \
-        if (int rc = set_smem(pair_grad_kernel<HS, RL>, smem)) return rc;                   \
-        pair_grad_kernel<HS, RL><<<grid, warps * 32, smem, s>>>(p);                         \
-    } while (0)
-        if (has_std) { if (relative) LAUNCH_GRAD(true, true); else LAUNCH_GRAD(true, false); }
-        else { if (relative) LAUNCH_GRAD(false, true); else LAUNCH_GRAD(false, false); }
-#undef LAUNCH_GRAD
-        if (int rc = launched("pair_grad_kernel")) return rc;
+        p.n_pairs = count;
+        if (int rc = fill_pairs(fn, p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
+        const int64_t n_groups = (plane + 31) / 32;
+        auto launch = [&](auto kernel) -> int {
+            if (int rc = set_smem(kernel, smem)) return rc;
+            int per_sm = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
+            per_sm = g_tuning.grad_blocks_per_sm > 0 ? g_tuning.grad_blocks_per_sm : std::max(per_sm, 1);
+            const int64_t gx = std::min<int64_t>((n_groups + warps - 1) / warps,
+                                                 std::max<int64_t>(1, (static_cast<int64_t>(device_sm_count()) * per_sm + n_channels - 1) / n_channels));
+            kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), warps * 32, smem, s>>>(p);
+            return 0;
+        };
+        int rc;
+        if (err) rc = relative ? launch(pair_grad_kernel<true, true>) : launch(pair_grad_kernel<true, false>);
+        else rc = relative ? launch(pair_grad_kernel<false, true>) : launch(pair_grad_kernel<false, false>);
+        if (rc) return rc;
+        if (int rc2 = launched("pair_grad_kernel")) return rc2;
         first += count;
     }
     return finalize_grad(static_cast<const float *>(workspace_dev), grad_theta_dev, n_channels, lut_size, s);
@@ -581,4 +779,25 @@ extern "C" int clair_icrf_backward_theta(const float *x_dev, const float *grad_y
                                                     lut_size, rows);
     if (int rc = launched("icrf_backward_theta_kernel")) return rc;
     return finalize_grad(static_cast<const float *>(workspace_dev), grad_theta_dev, n_channels, lut_size, s);
+}
+
+extern "C" int clair_pair_upstream(const double *sums_dev, int n_pairs, int n_channels, double *linloss_dev, double *mean_dev,
+                                   double *upstream_dev, double *mean_for_grad_dev, void *stream) {
+    if (!sums_dev || !linloss_dev || !mean_dev || !upstream_dev || !mean_for_grad_dev)
+        return fail(CLAIR_E_ARG, "clair_pair_upstream: null buffer");
+    if (n_pairs <= 0 || n_channels <= 0 || n_channels > CLAIR_MAX_CHANNELS || n_pairs > CLAIR_MAX_PAIRS)
+        return fail(CLAIR_E_LIMIT, "clair_pair_upstream: bad pair / channel count");
+    pair_upstream_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(sums_dev, n_pairs, n_channels, linloss_dev, mean_dev,
+                                                                           upstream_dev, mean_for_grad_dev);
+    return launched("pair_upstream_kernel");
+}
+
+extern "C" int clair_curve_penalties(const float *theta_dev, int n_channels, int lut_size, float alpha, float beta, float gamma,
+                                     float delta, double *penalty_dev, double *grad_theta_dev, void *stream) {
+    if (!theta_dev || !penalty_dev || !grad_theta_dev) return fail(CLAIR_E_ARG, "clair_curve_penalties: null buffer");
+    if (n_channels <= 0 || n_channels > CLAIR_MAX_CHANNELS || lut_size < 3)
+        return fail(CLAIR_E_LIMIT, "clair_curve_penalties: bad table shape");
+    curve_penalty_kernel<<<n_channels, 256, 0, static_cast<cudaStream_t>(stream)>>>(theta_dev, n_channels, lut_size, alpha, beta,
+                                                                                    gamma, delta, penalty_dev, grad_theta_dev);
+    return launched("curve_penalty_kernel");
 }

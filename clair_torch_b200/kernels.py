@@ -192,8 +192,10 @@ def _pair_arrays(i_idx, j_idx, ratio):
 
 def pair_stats(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, ratio,
                theta: Optional[torch.Tensor], valid_lo: float, valid_hi: float, relative: bool,
-               unc_weighting: bool, row_base=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(P, C, 5) float64 sums [sum MWt, sum MWt l, sum MWt l^2, sum M err, sum M] for one batch.
+               unc_weighting: bool, row_base=None, out: Optional[torch.Tensor] = None,
+               means_only: bool = False) -> torch.Tensor:
+    """(P, C, 5) float64 sums [sum MWt, sum MWt l, sum MWt l^2, sum M err, sum M] for one batch
+    (only the first two when `means_only`, the training-step variant).
     training/losses.py:13-108, common/general_functions.py:118-178,276-312."""
     lib = _native.load()
     val = _stack(val, "val_batch")
@@ -206,7 +208,8 @@ def pair_stats(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, rat
     sums = torch.zeros((p, c, 5), dtype=_F64, device=val.device) if out is None else out
     keep, rows = _rows(row_base, c)
     with torch.cuda.device(val.device):
-        rc = lib.clair_pair_stats(
+        entry = lib.clair_pair_means if means_only else lib.clair_pair_stats
+        rc = entry(
             _ptr(val), _ptr(std), n, c, h * w, pi.ctypes.data_as(ctypes.c_void_p),
             pj.ctypes.data_as(ctypes.c_void_p), pr.ctypes.data_as(ctypes.c_void_p), p, _ptr(th), lut, rows,
             float(np.float32(valid_lo)), float(np.float32(valid_hi)), int(bool(relative)), int(bool(unc_weighting)),
@@ -242,3 +245,34 @@ def pair_grad(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, rati
             _ptr(up), _ptr(mn), _ptr(grad), _ptr(ws), ws.numel() * 4, _stream(val.device))
     _native.check(rc, "clair_pair_grad")
     return grad
+
+
+def pair_upstream(sums: torch.Tensor):
+    """(linloss (C,), mean (P,C), upstream (P,C), mean_for_grad (P,C)) float64 from the (P,C,5) sums, on the device."""
+    lib = _native.load()
+    p, c, _ = sums.shape
+    dev = sums.device
+    linloss = torch.empty((c,), dtype=_F64, device=dev)
+    mean = torch.empty((p, c), dtype=_F64, device=dev)
+    upstream = torch.empty((p, c), dtype=_F64, device=dev)
+    mean_for_grad = torch.empty((p, c), dtype=_F64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.clair_pair_upstream(_ptr(sums), p, c, _ptr(linloss), _ptr(mean), _ptr(upstream), _ptr(mean_for_grad),
+                                     _stream(dev))
+    _native.check(rc, "clair_pair_upstream")
+    return linloss, mean, upstream, mean_for_grad
+
+
+def curve_penalties(theta: torch.Tensor, alpha: float, beta: float, gamma: float, delta: float, grad: torch.Tensor):
+    """Per-channel weighted sum of the four curve penalties (C,) float64; their gradient is ADDED to `grad` (C,L) float64."""
+    lib = _native.load()
+    th = theta.detach().to(dtype=_F32).contiguous()
+    if not th.is_cuda:
+        raise RuntimeError("the ICRF table must live on a CUDA device")
+    c, lut = th.shape
+    pen = torch.empty((c,), dtype=_F64, device=th.device)
+    with torch.cuda.device(th.device):
+        rc = lib.clair_curve_penalties(_ptr(th), c, lut, float(alpha), float(beta), float(gamma), float(delta), _ptr(pen),
+                                       _ptr(grad), _stream(th.device))
+    _native.check(rc, "clair_curve_penalties")
+    return pen

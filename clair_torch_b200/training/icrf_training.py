@@ -16,8 +16,6 @@ from ..common.general_functions import get_valid_exposure_pairs
 from ..models.base import ICRFModelBase
 from ..inference._common import as_device, stage_batch
 from ..common.enums import InterpMode
-from .losses import (compute_endpoint_penalty, compute_monotonicity_penalty, compute_range_penalty,
-                     compute_smoothness_penalty)
 
 
 def linearity_loss_and_table_grad(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
@@ -30,18 +28,12 @@ def linearity_loss_and_table_grad(images, stds, i_idx, j_idx, ratio_pairs, table
     """
     sums = kernels.pair_stats(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
                               upper_valid_threshold, use_relative_linearity_loss, use_uncertainty_weighting,
-                              row_base=row_base)
+                              row_base=row_base, means_only=True)
     if reduce_fn is not None:
         reduce_fn(sums)
-    s0, s1 = sums[..., 0], sums[..., 1]
-    denom = s0.clamp(min=1e-8)
-    spatial = s1 / denom                                          # general_functions.py:156-160
-    linearity_loss = torch.sqrt((spatial ** 2).sum(dim=0))        # icrf_training.py:136
+    linearity_loss, spatial, upstream, mean_for_grad = kernels.pair_upstream(sums)
     grad = None
     if want_grad:
-        safe = torch.where(linearity_loss > 0, linearity_loss, torch.ones_like(linearity_loss))
-        upstream = torch.where(linearity_loss > 0, spatial / safe, torch.zeros_like(spatial)) / denom
-        mean_for_grad = torch.where(s0 < 1e-8, torch.zeros_like(spatial), spatial)   # clamped denominators carry no d/dWt
         grad = kernels.pair_grad(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
                                  upper_valid_threshold, use_relative_linearity_loss, use_uncertainty_weighting,
                                  upstream, mean_for_grad, row_base=row_base)
@@ -56,7 +48,11 @@ def train_icrf_step(icrf_model: ICRFModelBase, optimizers: list[Optimizer], imag
                     lower_valid_threshold=1 / 255, upper_valid_threshold=254 / 255, exposure_ratio_threshold=0.1,
                     row_base=None, reduce_fn=None):
     """Body of the batch loop, icrf_training.py:105-156, for one device-resident batch.  Returns the detached
-    per-channel loss (C,) (a 0-dim sum when a single optimiser is used, :145-146)."""
+    per-channel loss (C,) (a 0-dim sum when a single optimiser is used, :145-146).
+
+    Launch sequence: pair means -> upstream factors -> table gradient (+ finalize) -> curve penalties (value and
+    gradient) -> one autograd edge from the table to the model parameters -> optimisers -> update_icrf.
+    """
     if icrf_model.interpolation_mode is not InterpMode.LINEAR:
         raise NotImplementedError("train_icrf on B200 supports InterpMode.LINEAR (the reference default)")
     i_idx, j_idx, ratio_pairs = get_valid_exposure_pairs(exposures, exposure_ratio_threshold)
@@ -69,14 +65,13 @@ def train_icrf_step(icrf_model: ICRFModelBase, optimizers: list[Optimizer], imag
         images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold, upper_valid_threshold,
         use_relative_linearity_loss, use_uncertainty_weighting, want_grad=connected, row_base=row_base,
         reduce_fn=reduce_fn)
-    penalties = (alpha * compute_monotonicity_penalty(curve, per_channel=True)
-                 + beta * compute_range_penalty(curve, per_channel=True)
-                 + gamma * compute_endpoint_penalty(curve, per_channel=True)
-                 + delta * compute_smoothness_penalty(curve, per_channel=True))
-    loss = linearity_loss + penalties.detach()
+    if grad is None:
+        grad = torch.zeros(tuple(table.shape), dtype=torch.float64, device=table.device)
+    penalties = kernels.curve_penalties(table, alpha, beta, gamma, delta, grad)     # adds d penalties / d table to grad
+    loss = linearity_loss + penalties
     if connected:
         # sum_c loss_c back-propagated once: the C backward() calls of :148-149 accumulate exactly this
-        torch.autograd.backward([penalties.sum(), curve], [None, grad.to(curve.dtype)])
+        curve.backward(grad.to(curve.dtype))
     for optimizer in optimizers:
         optimizer.step()
     icrf_model.update_icrf()

@@ -144,6 +144,35 @@ CLAIR_API int clair_pair_stats(const float *val_dev, const float *std_dev, int n
                      void *stream);
 
 /*
+ * Training-step variant of clair_pair_stats: same arguments, but only sums [0] (sum M*Wt) and [1] (sum M*Wt*l) are
+ * produced — all a train_icrf step needs (training/icrf_training.py:133-136) — and the std images are only read when
+ * the uncertainty weights need them.
+ */
+CLAIR_API int clair_pair_means(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
+                     const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
+                     int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
+                     float valid_lo, float valid_hi, int relative, int unc_weighting, double *sums_dev,
+                     void *stream);
+
+/*
+ * (P, C)-sized algebra between the two passes of a training step (training/icrf_training.py:133-136 and the head of
+ * the closed-form backward), on the device so the step never synchronises:
+ *   mean[p,c] = s1/max(s0,1e-8);  linloss[c] = sqrt(sum_p mean[p,c]^2);
+ *   upstream[p,c] = mean/linloss/max(s0,1e-8) (0 where linloss = 0);  mean_for_grad = mean (0 where s0 < 1e-8).
+ * All buffers float64: sums (P,C,5) in; linloss (C), mean / upstream / mean_for_grad (P,C) out.
+ */
+CLAIR_API int clair_pair_upstream(const double *sums_dev, int n_pairs, int n_channels, double *linloss_dev, double *mean_dev,
+                        double *upstream_dev, double *mean_for_grad_dev, void *stream);
+
+/*
+ * The four curve penalties of training/losses.py:111-190 per channel, weighted as in training/icrf_training.py:143,
+ *   penalty[c] = alpha*monotonicity + beta*range + gamma*endpoints + delta*smoothness     (float64 (C), overwritten)
+ * and their gradient ADDED to grad_theta_dev (C, L) float64.  fp32 arithmetic like the reference.
+ */
+CLAIR_API int clair_curve_penalties(const float *theta_dev, int n_channels, int lut_size, float alpha, float beta, float gamma,
+                          float delta, double *penalty_dev, double *grad_theta_dev, void *stream);
+
+/*
  * Gradient of the linearity loss of one train_icrf step with respect to the ICRF table — replaces the C
  * `loss[c].backward(retain_graph=True)` passes (training/icrf_training.py:148-149) for the linearity term,
  * in closed form.  Arguments as clair_pair_stats, plus
