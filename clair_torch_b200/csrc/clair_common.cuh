@@ -55,6 +55,33 @@ __device__ __forceinline__ void store_stream(float *p, const Pack<VEC> &r) {
     }
 }
 
+// shared-memory packs (the pointers are VEC*4-byte aligned by construction)
+template <int VEC>
+__device__ __forceinline__ void store_shared(float *p, const Pack<VEC> &r) {
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    } else if constexpr (VEC == 2) {
+        *reinterpret_cast<float2 *>(p) = make_float2(r.v[0], r.v[1]);
+    } else {
+        *p = r.v[0];
+    }
+}
+
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> load_shared(const float *p) {
+    Pack<VEC> r;
+    if constexpr (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else if constexpr (VEC == 2) {
+        const float2 t = *reinterpret_cast<const float2 *>(p);
+        r.v[0] = t.x; r.v[1] = t.y;
+    } else {
+        r.v[0] = *p;
+    }
+    return r;
+}
+
 template <int VEC>
 __device__ __forceinline__ void store_stream_f64(double *p, const double (&r)[VEC]) {
     if constexpr (VEC == 4) {

@@ -17,6 +17,7 @@ constexpr int kMaxPairsPerLaunch = 256;   // the pair table travels as a kernel 
 constexpr int kStatsTile = 128;           // pixels per shared-memory tile in the statistics kernel (power of two)
 constexpr int kMaxSlots = 4;              // pairs a warp carries in registers in the statistics kernel
 constexpr int kGradCopies = 64;           // replicated gradient tables the REDs are spread over
+constexpr int kFlushTiles = 8;            // tiles between flushes of the fp32 partial sums into float64 (32 terms per lane)
 
 struct PairTable {
     float r_hi[kMaxPairsPerLaunch];       // exposure ratio t_i/t_j split into two floats (r = hi + lo to ~48 bits)
@@ -107,16 +108,17 @@ __device__ __forceinline__ float rsqrt_approx(float t) {
 // Per tile the fp32 partials are flushed into float64 running sums; one warp reduction and <= 5 fp64 atomics per
 // (block, pair) at the very end.
 // =====================================================================================================
-template <int SLOTS, bool ERR, bool RELATIVE, bool FULL>
+template <int SLOTS, bool ERR, bool RELATIVE, bool FULL, int VA>
 __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int C = p.n_channels, L = p.lut, N = p.n_frames;
     const bool has_model = p.theta != nullptr;
     float2 *s_tab = reinterpret_cast<float2 *>(s_raw);
-    float *s_f = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
-    float *s_gw = s_f + N * kStatsTile;
-    float *s_sig = s_gw + N * kStatsTile;               // ERR only
-    float *s_sb = s_sig + N * kStatsTile;               // ERR && RELATIVE only: sig / max(f, 1e-6)
+    // tile layout [frame][array][pixel]: one base address per frame, the arrays at constant offsets
+    //   array 0: f   1: gw   2: sig (ERR)   3: sig / max(f, 1e-6) (ERR && RELATIVE)
+    constexpr int kArr = 2 + (ERR ? (RELATIVE ? 2 : 1) : 0);
+    constexpr int kFrameFloats = kArr * kStatsTile;
+    float *s_tile = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
     if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
 
     const int c = blockIdx.y;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
     const float lm1 = static_cast<float>(L - 1);
     const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
     const float *val_c = p.val + static_cast<int64_t>(c) * p.plane;
-    const float *std_c = ERR ? p.std + static_cast<int64_t>(c) * p.plane : nullptr;
+    const int64_t std_minus_val = ERR ? (p.std - p.val) : 0;      // std element = val element + this many floats
     const bool unc = p.unc_weighting != 0;
     const uint32_t tab_bias = curve_row_bias(s_tab);
     const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
@@ -133,10 +135,27 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
     const uint32_t plane = static_cast<uint32_t>(p.plane);
 
     double d0[SLOTS], d1[SLOTS], d2[SLOTS], d3[SLOTS];
+    float t0[SLOTS], t1[SLOTS], t2[SLOTS], t3[SLOTS];   // fp32 partials of the last <= kFlushTiles tiles
     float pivot[SLOTS];
     unsigned int cnt[SLOTS];
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) { d0[s] = 0.0; d1[s] = 0.0; d2[s] = 0.0; d3[s] = 0.0; pivot[s] = 0.0f; cnt[s] = 0u; }
+    for (int s = 0; s < SLOTS; ++s) {
+        d0[s] = 0.0; d1[s] = 0.0; d2[s] = 0.0; d3[s] = 0.0;
+        t0[s] = 0.0f; t1[s] = 0.0f; t2[s] = 0.0f; t3[s] = 0.0f;
+        pivot[s] = 0.0f; cnt[s] = 0u;
+    }
+    auto flush = [&]() {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            d0[s] += static_cast<double>(t0[s]); t0[s] = 0.0f;
+            d1[s] += static_cast<double>(t1[s]); t1[s] = 0.0f;
+            if constexpr (FULL) {
+                d2[s] += static_cast<double>(t2[s]); t2[s] = 0.0f;
+                if constexpr (ERR) { d3[s] += static_cast<double>(t3[s]); t3[s] = 0.0f; }
+            }
+        }
+    };
+    int since_flush = 0;
 
     const uint32_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
     // table row of the tile's first pixel, advanced incrementally (no divide in the loop)
@@ -145,24 +164,42 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         __syncthreads();   // previous tile fully consumed (also orders the table staging on the first pass)
         const uint32_t pix0 = tile * kStatsTile;
-        for (int e = threadIdx.x; e < N * kStatsTile; e += blockDim.x) {
-            const int n = e >> 7;
-            const uint32_t q = static_cast<uint32_t>(e) & (kStatsTile - 1);
+        // phase A: one item = VA adjacent pixels of one frame (one 128-bit load per input when VA = 4)
+        constexpr int kItemsPerFrame = kStatsTile / VA;
+        constexpr int kItemShift = (VA == 4) ? 5 : 7;
+        for (int item = threadIdx.x; item < N * kItemsPerFrame; item += blockDim.x) {
+            const int n = item >> kItemShift;
+            const uint32_t q = (static_cast<uint32_t>(item) & (kItemsPerFrame - 1)) * VA;
             const uint32_t pix = pix0 + q;
-            FrameTerms t;
-            t.f = 1.0f; t.sig = 0.0f; t.gw = -1.0f;
-            if (pix < plane) {
-                const int64_t o = static_cast<int64_t>(n) * frame_stride + pix;
-                const float x = __ldcs(val_c + o);
-                const float s = ERR ? __ldcs(std_c + o) : 0.0f;
-                const uint32_t u = mod_small(u_tile + q, uC, p.mod_magic);
-                t = frame_terms<ERR>(x, s, has_model, tab_bias + u * row_bytes, lm1, p.valid_lo, p.valid_hi);
+            const bool live = pix < plane;                     // plane % VA == 0: the whole item is in or out
+            Pack<VA> xv, sv;
+#pragma unroll
+            for (int k = 0; k < VA; ++k) { xv.v[k] = 0.0f; sv.v[k] = 0.0f; }
+            if (live) {
+                const float *src = val_c + static_cast<int64_t>(n) * frame_stride + pix;
+                xv = load_stream<VA>(src);
+                if constexpr (ERR) sv = load_stream<VA>(src + std_minus_val);
             }
-            s_f[e] = t.f;
-            s_gw[e] = t.gw;
+            uint32_t u = mod_small(u_tile + q, uC, p.mod_magic);
+            Pack<VA> of, og, os, ob;
+#pragma unroll
+            for (int k = 0; k < VA; ++k) {
+                const FrameTerms t = frame_terms<ERR>(xv.v[k], sv.v[k], has_model, tab_bias + u * row_bytes, lm1, p.valid_lo,
+                                                      p.valid_hi);
+                u = (u + 1 == uC) ? 0u : u + 1;
+                of.v[k] = t.f;
+                og.v[k] = live ? t.gw : -1.0f;
+                if constexpr (ERR) {
+                    os.v[k] = t.sig;
+                    if constexpr (RELATIVE) ob.v[k] = t.sig * rcp_fast(fmaxf(t.f, 1e-6f));   // losses.py:55,58
+                }
+            }
+            float *dst = s_tile + n * kFrameFloats + q;
+            store_shared<VA>(dst, of);
+            store_shared<VA>(dst + kStatsTile, og);
             if constexpr (ERR) {
-                s_sig[e] = t.sig;
-                if constexpr (RELATIVE) s_sb[e] = t.sig * rcp_fast(fmaxf(t.f, 1e-6f));   // losses.py:55,58
+                store_shared<VA>(dst + 2 * kStatsTile, os);
+                if constexpr (RELATIVE) store_shared<VA>(dst + 3 * kStatsTile, ob);
             }
         }
         u_tile += du_tile;
@@ -172,16 +209,17 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
         for (int s = 0; s < SLOTS; ++s) {
             const int pr = warp + s * n_warps;
             if (pr < p.n_pairs) {
-                const int fi = p.pairs.i[pr] * kStatsTile, fj = p.pairs.j[pr] * kStatsTile;
+                const float *fi = s_tile + p.pairs.i[pr] * kFrameFloats + lane;
+                const float *fj = s_tile + p.pairs.j[pr] * kFrameFloats + lane;
                 const float r_hi = p.pairs.r_hi[pr], r_lo = p.pairs.r_lo[pr];
-                float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+                float a0 = t0[s], a1 = t1[s], a2 = t2[s], a3 = t3[s];
                 float k = pivot[s];
                 unsigned int n_valid = cnt[s];
 #pragma unroll
                 for (int it = 0; it < kStatsTile / 32; ++it) {
-                    const int q = lane + 32 * it;
-                    const float a = s_f[fi + q], b = s_f[fj + q];
-                    const float gi = s_gw[fi + q], gj = s_gw[fj + q];
+                    const int q = 32 * it;
+                    const float a = fi[q], b = fj[q];
+                    const float gi = fi[kStatsTile + q], gj = fj[kStatsTile + q];
                     const bool valid = (gi >= 0.0f) && (gj >= 0.0f);
                     const float d = ratio_residual(a, b, r_hi, r_lo);
                     float inv = 1.0f, ell;
@@ -194,13 +232,13 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
                     float wt = gi + gj;
                     float err = 0.0f;
                     if constexpr (ERR) {
-                        const float sa = s_sig[fi + q];
+                        const float sa = fi[2 * kStatsTile + q];
                         if constexpr (RELATIVE) {
                             const float e1 = sa * inv;
-                            const float e2 = a * s_sb[fj + q] * inv;
+                            const float e2 = a * fj[3 * kStatsTile + q] * inv;
                             err = sqrt_approx(fmaf(e1, e1, fmaf(e2, e2, 1e-6f)));   // losses.py:57-60
                         } else {
-                            const float rs = r_hi * s_sig[fj + q];
+                            const float rs = r_hi * fj[2 * kStatsTile + q];
                             err = sqrt_approx(fmaf(sa, sa, rs * rs));               // losses.py:62
                         }
                         if (unc) wt += rcp_fast(err + 1e-6f);                       // losses.py:97
@@ -211,26 +249,27 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
                         n_valid += valid ? 1u : 0u;
                         const float dl = valid ? ell - k : 0.0f;
                         const float wdl = w * dl;
-                        t0 += w;
-                        t1 += wdl;
-                        t2 = fmaf(wdl, dl, t2);
-                        if constexpr (ERR) t3 += valid ? err : 0.0f;
+                        a0 += w;
+                        a1 += wdl;
+                        a2 = fmaf(wdl, dl, a2);
+                        if constexpr (ERR) a3 += valid ? err : 0.0f;
                     } else {
-                        t0 += w;
-                        t1 = fmaf(w, ell, t1);
+                        a0 += w;
+                        a1 = fmaf(w, ell, a1);
                     }
                 }
-                d0[s] += static_cast<double>(t0);
-                d1[s] += static_cast<double>(t1);
+                t0[s] = a0; t1[s] = a1;
                 if constexpr (FULL) {
-                    d2[s] += static_cast<double>(t2);
-                    if constexpr (ERR) d3[s] += static_cast<double>(t3);
+                    t2[s] = a2;
+                    if constexpr (ERR) t3[s] = a3;
                     pivot[s] = k;
                     cnt[s] = n_valid;
                 }
             }
         }
+        if (++since_flush == kFlushTiles) { flush(); since_flush = 0; }
     }
+    flush();
 
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
@@ -291,7 +330,7 @@ __device__ __forceinline__ void scatter_taps(float *copy, int C, int L, int u, f
     red_add_v2(base, g * (1.0f - w), g * w);
 }
 
-template <bool ERR, bool RELATIVE>
+template <bool ERR, bool RELATIVE, int PIX>
 __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int C = p.n_channels, L = p.lut, N = p.n_frames, P = p.n_pairs;
@@ -308,15 +347,18 @@ __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_warps = blockDim.x >> 5;
+    // warp-private slice, layout [frame][array][lane][PIX]: one base address per frame, arrays at constant offsets
+    //   0: f   1: gw   2: xs   3: G (per-frame upstream)   4: sigma (ERR)   5: 1 / max(f, 1e-6) (ERR)
     constexpr int kArrays = ERR ? 6 : 4;
-    float *slice = s_mean + P + warp * (kArrays * N * 32);
-    float *s_f = slice, *s_gw = slice + N * 32, *s_xs = slice + 2 * N * 32, *s_g = slice + 3 * N * 32;
-    float *s_sig = slice + 4 * N * 32, *s_ib = slice + 5 * N * 32;   // ERR: sigma, 1 / max(f, 1e-6)
+    constexpr int kArr = 32 * PIX;                       // floats per array
+    constexpr int kFrameFloats = kArrays * kArr;
+    // s_up and s_mean hold 2P floats after the float2 table, so the slices stay 8-byte aligned for paired accesses
+    float *slice = s_mean + P + warp * (N * kFrameFloats) + lane * PIX;
 
     const float lm1 = static_cast<float>(L - 1);
     const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
     const float *val_c = p.val + static_cast<int64_t>(c) * p.plane;
-    const float *std_c = ERR ? p.std + static_cast<int64_t>(c) * p.plane : nullptr;
+    const int64_t std_minus_val = ERR ? (p.std - p.val) : 0;
     const int lp = L + 2;
     float *copy = p.hist + static_cast<int64_t>((blockIdx.x * n_warps + warp) % kGradCopies) * (2 * C * lp);
     const uint32_t tab_bias = curve_row_bias(s_tab);
@@ -324,107 +366,152 @@ __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
     const uint32_t uC = static_cast<uint32_t>(C);
     const uint32_t plane = static_cast<uint32_t>(p.plane);
 
-    const uint32_t n_groups = (plane + 31) / 32;
+    constexpr uint32_t kGroup = 32 * PIX;                // pixels per warp trip
+    const uint32_t n_groups = (plane + kGroup - 1) / kGroup;
     const uint32_t grp_stride = gridDim.x * n_warps;
     uint32_t grp = blockIdx.x * n_warps + warp;
-    uint32_t u = (grp * 32 + lane + static_cast<uint32_t>(p.rows.base(c))) % uC;
-    const uint32_t du = (grp_stride * 32) % uC;
+    uint32_t u0 = (grp * kGroup + lane * PIX + static_cast<uint32_t>(p.rows.base(c))) % uC;
+    const uint32_t du = (grp_stride * kGroup) % uC;
     for (; grp < n_groups; grp += grp_stride) {
-        const uint32_t pix = grp * 32 + lane;
-        const bool live = pix < plane;
+        const uint32_t pix = grp * kGroup + lane * PIX;
+        const bool live = pix < plane;                   // plane % PIX == 0
+        uint32_t bias[PIX];
+        {
+            uint32_t u = u0;
+#pragma unroll
+            for (int k = 0; k < PIX; ++k) { bias[k] = tab_bias + u * row_bytes; u = (u + 1 == uC) ? 0u : u + 1; }
+        }
         __syncwarp();
         // loads of four frames in flight together, then their arithmetic
         for (int n0 = 0; n0 < N; n0 += 4) {
-            float xv[4], sv[4];
+            Pack<PIX> xv[4], sv[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                xv[k] = 0.0f; sv[k] = 0.0f;
-                if (n0 + k < N && live) {
-                    const int64_t o = static_cast<int64_t>(n0 + k) * frame_stride + pix;
-                    xv[k] = __ldcs(val_c + o);
-                    if constexpr (ERR) sv[k] = __ldcs(std_c + o);
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int k = 0; k < PIX; ++k) { xv[j].v[k] = 0.0f; sv[j].v[k] = 0.0f; }
+                if (n0 + j < N && live) {
+                    const float *src = val_c + static_cast<int64_t>(n0 + j) * frame_stride + pix;
+                    xv[j] = load_stream<PIX>(src);
+                    if constexpr (ERR) sv[j] = load_stream<PIX>(src + std_minus_val);
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (n0 + k < N) {
-                    FrameTerms t = frame_terms<ERR>(xv[k], sv[k], true, tab_bias + u * row_bytes, lm1, p.valid_lo, p.valid_hi);
-                    if (!live) t.gw = -1.0f;
-                    const int e = (n0 + k) * 32 + lane;
-                    s_f[e] = t.f; s_gw[e] = t.gw; s_xs[e] = t.xs; s_g[e] = 0.0f;
+            for (int j = 0; j < 4; ++j) {
+                if (n0 + j < N) {
+                    Pack<PIX> of, og, ox, oz, os, oi;
+#pragma unroll
+                    for (int k = 0; k < PIX; ++k) {
+                        const FrameTerms t = frame_terms<ERR>(xv[j].v[k], sv[j].v[k], true, bias[k], lm1, p.valid_lo, p.valid_hi);
+                        of.v[k] = t.f; og.v[k] = live ? t.gw : -1.0f; ox.v[k] = t.xs; oz.v[k] = 0.0f;
+                        if constexpr (ERR) { os.v[k] = t.sig; oi.v[k] = rcp_approx(fmaxf(t.f, 1e-6f)); }
+                    }
+                    float *dst = slice + (n0 + j) * kFrameFloats;
+                    store_shared<PIX>(dst, of);
+                    store_shared<PIX>(dst + kArr, og);
+                    store_shared<PIX>(dst + 2 * kArr, ox);
+                    store_shared<PIX>(dst + 3 * kArr, oz);
                     if constexpr (ERR) {
-                        s_sig[e] = t.sig;
-                        s_ib[e] = rcp_fast(fmaxf(t.f, 1e-6f));
+                        store_shared<PIX>(dst + 4 * kArr, os);
+                        store_shared<PIX>(dst + 5 * kArr, oi);
                     }
                 }
             }
         }
         __syncwarp();
         int cur_i = -1;
-        float acc_i = 0.0f;
+        Pack<PIX> acc_i;
+#pragma unroll
+        for (int k = 0; k < PIX; ++k) acc_i.v[k] = 0.0f;
+        auto flush_i = [&]() {
+            float *gi_ptr = slice + cur_i * kFrameFloats + 3 * kArr;
+            Pack<PIX> g = load_shared<PIX>(gi_ptr);
+#pragma unroll
+            for (int k = 0; k < PIX; ++k) { g.v[k] += acc_i.v[k]; acc_i.v[k] = 0.0f; }
+            store_shared<PIX>(gi_ptr, g);
+        };
         for (int pr = 0; pr < P; ++pr) {
             const int pi = p.pairs.i[pr];
             if (pi != cur_i) {                                   // uniform across the warp
-                if (cur_i >= 0) s_g[cur_i * 32 + lane] += acc_i;
+                if (cur_i >= 0) flush_i();
                 cur_i = pi;
-                acc_i = 0.0f;
             }
-            const int ei = pi * 32 + lane, ej = p.pairs.j[pr] * 32 + lane;
-            const float gi = s_gw[ei], gj = s_gw[ej];
-            const bool valid = (gi >= 0.0f) && (gj >= 0.0f);     // masked pair elements carry no gradient
+            const float *fi = slice + pi * kFrameFloats;
+            float *fj = slice + p.pairs.j[pr] * kFrameFloats;
             const float r_hi = p.pairs.r_hi[pr], r_lo = p.pairs.r_lo[pr];
-            const float up = valid ? s_up[pr] : 0.0f;
-            const float a = s_f[ei], b = s_f[ej];
-            const float d = ratio_residual(a, b, r_hi, r_lo);
-            float wt = gi + gj;
-            float ga, gb;
-            if constexpr (RELATIVE) {
-                const float inv = rcp_fast(fmaf(b, r_hi, 1e-6f));
-                const float q = d * inv;
-                const float sgn = (q > 0.0f) ? 1.0f : ((q < 0.0f) ? -1.0f : 0.0f);
-                float extra_a = 0.0f, extra_b = 0.0f;
-                if constexpr (ERR) {
-                    // the inverse-uncertainty weight depends on the curve through a, es and max(b, 1e-6)
-                    const float sa = s_sig[ei], sb = s_sig[ej], ib = s_ib[ej];
-                    const float e1 = sa * inv;
-                    const float c2 = sb * ib * inv;
-                    const float e2 = a * c2;
-                    const float T = fmaf(e1, e1, fmaf(e2, e2, 1e-6f));
-                    const float rerr = rsqrt_approx(T);                    // 1 / err
-                    const float rw = rcp_fast(fmaf(T, rerr, 1e-6f));       // 1 / (err + 1e-6)
-                    wt += rw;
-                    // dm/dWt * dWt/derr * derr/dT = (l - m) U * (-rw^2) * 1/(2 err)
-                    const float kk = (fabsf(q) - s_mean[pr]) * up * (-0.5f * rw * rw) * rerr;
-                    const float dT_da = 2.0f * e2 * c2;
-                    const float dT_des = -2.0f * inv * (e1 * e1 + e2 * e2);
-                    const float dT_dbs = (b >= 1e-6f) ? (-2.0f * e2 * e2 * ib) : 0.0f;
-                    extra_a = kk * dT_da;
-                    extra_b = kk * fmaf(dT_des, r_hi, dT_dbs);
-                }
-                const float base = wt * up * sgn * inv;
-                ga = base + extra_a;                                   // dl/da = sgn / es
-                gb = fmaf(-base * r_hi, (a + 1e-6f) * inv, extra_b);   // dl/db = -sgn r (a + 1e-6) / es^2
-            } else {
-                const float sgn = (d > 0.0f) ? 1.0f : ((d < 0.0f) ? -1.0f : 0.0f);
-                if constexpr (ERR) {
-                    const float sa = s_sig[ei], rs = r_hi * s_sig[ej];
-                    wt += rcp_fast(sqrt_approx(fmaf(sa, sa, rs * rs)) + 1e-6f);   // constant wrt the curve
-                }
-                const float base = wt * up * sgn;
-                ga = base;
-                gb = -base * r_hi;
+            const float up_pr = s_up[pr];
+            const Pack<PIX> gi = load_shared<PIX>(fi + kArr), gj = load_shared<PIX>(fj + kArr);
+            const Pack<PIX> av = load_shared<PIX>(fi), bv = load_shared<PIX>(fj);
+            Pack<PIX> gjacc = load_shared<PIX>(fj + 3 * kArr);
+            Pack<PIX> sav, sbv, ibv;
+            if constexpr (ERR) {
+                sav = load_shared<PIX>(fi + 4 * kArr);
+                sbv = load_shared<PIX>(fj + 4 * kArr);
+                if constexpr (RELATIVE) ibv = load_shared<PIX>(fj + 5 * kArr);
             }
-            acc_i += ga;
-            s_g[ej] += gb;
+#pragma unroll
+            for (int k = 0; k < PIX; ++k) {
+                const bool valid = (gi.v[k] >= 0.0f) && (gj.v[k] >= 0.0f);     // masked pair elements carry no gradient
+                const float up = valid ? up_pr : 0.0f;
+                const float a = av.v[k], b = bv.v[k];
+                const float d = ratio_residual(a, b, r_hi, r_lo);
+                float wt = gi.v[k] + gj.v[k];
+                float ga, gb;
+                if constexpr (RELATIVE) {
+                    // MUFU.RCP alone (~1 ulp): the gate on the gradient is 1e-5 of its maximum
+                    const float inv = rcp_approx(fmaf(b, r_hi, 1e-6f));
+                    const float q = d * inv;
+                    float extra_a = 0.0f, extra_b = 0.0f;
+                    if constexpr (ERR) {
+                        // the inverse-uncertainty weight depends on the curve through a, es and max(b, 1e-6)
+                        const float e1 = sav.v[k] * inv;
+                        const float c2 = sbv.v[k] * ibv.v[k] * inv;
+                        const float e2 = a * c2;
+                        const float T = fmaf(e1, e1, fmaf(e2, e2, 1e-6f));
+                        const float rerr = rsqrt_approx(T);                    // 1 / err
+                        const float rw = rcp_approx(fmaf(T, rerr, 1e-6f));     // 1 / (err + 1e-6)
+                        wt += rw;
+                        // dm/dWt * dWt/derr * derr/dT = (l - m) U * (-rw^2) * 1/(2 err)
+                        const float kk = (fabsf(q) - s_mean[pr]) * up * (-0.5f * rw * rw) * rerr;
+                        const float dT_da = 2.0f * e2 * c2;
+                        const float dT_des = -2.0f * inv * (e1 * e1 + e2 * e2);
+                        const float dT_dbs = (b >= 1e-6f) ? (-2.0f * e2 * e2 * ibv.v[k]) : 0.0f;
+                        extra_a = kk * dT_da;
+                        extra_b = kk * fmaf(dT_des, r_hi, dT_dbs);
+                    }
+                    // sign(q) * (wt U / es) with sign(0) = 0, as torch.abs' backward has it
+                    const float mag = (q != 0.0f) ? wt * up * inv : 0.0f;
+                    const float base = __int_as_float((__float_as_int(mag) ^ (__float_as_int(q) & 0x80000000)));
+                    ga = base + extra_a;                                   // dl/da = sgn / es
+                    gb = fmaf(-base * r_hi, (a + 1e-6f) * inv, extra_b);   // dl/db = -sgn r (a + 1e-6) / es^2
+                } else {
+                    if constexpr (ERR) {
+                        const float rs = r_hi * sbv.v[k];
+                        wt += rcp_approx(sqrt_approx(fmaf(sav.v[k], sav.v[k], rs * rs)) + 1e-6f);   // constant wrt the curve
+                    }
+                    const float mag = (d != 0.0f) ? wt * up : 0.0f;
+                    const float base = __int_as_float((__float_as_int(mag) ^ (__float_as_int(d) & 0x80000000)));
+                    ga = base;
+                    gb = -base * r_hi;
+                }
+                acc_i.v[k] += ga;
+                gjacc.v[k] += gb;
+            }
+            store_shared<PIX>(fj + 3 * kArr, gjacc);
         }
-        if (cur_i >= 0) s_g[cur_i * 32 + lane] += acc_i;
+        if (cur_i >= 0) flush_i();
         __syncwarp();
         for (int n = 0; n < N; ++n) {
-            const float g = s_g[n * 32 + lane];
-            if (g != 0.0f) scatter_taps(copy, C, L, static_cast<int>(u), s_xs[n * 32 + lane], g);
+            const Pack<PIX> g = load_shared<PIX>(slice + n * kFrameFloats + 3 * kArr);
+            const Pack<PIX> xs = load_shared<PIX>(slice + n * kFrameFloats + 2 * kArr);
+            uint32_t u = u0;
+#pragma unroll
+            for (int k = 0; k < PIX; ++k) {
+                if (g.v[k] != 0.0f) scatter_taps(copy, C, L, static_cast<int>(u), xs.v[k], g.v[k]);
+                u = (u + 1 == uC) ? 0u : u + 1;
+            }
         }
-        u += du;
-        u = (u >= uC) ? u - uC : u;
+        u0 += du;
+        u0 = (u0 >= uC) ? u0 - uC : u0;
     }
 }
 
@@ -579,17 +666,23 @@ int set_smem(K kernel, size_t bytes) {
     return 0;
 }
 
-// choose warps per block W (4..16) and register slots S (1..kMaxSlots) with W*S >= count and the least idle slots
-void pick_stats_shape(int count, int &warps, int &slots) {
-    int best_w = 8, best_s = kMaxSlots, best_waste = 1 << 30;
+// Choose warps per block W and register slots S (W*S >= pairs in the launch) from an instruction-count model of one
+// tile: every warp stages ceil(N*items/ (32 W)) items of VA pixels (cost_item each) and then walks S pair slots of
+// kStatsTile/32 pixels each (cost_pair per pixel).  Block time per tile ~ that sum; SM throughput ~ 1 / (W * sum).
+void pick_stats_shape(int count, int n_frames, int va, bool err, bool full, int &warps, int &slots) {
+    const int cost_item = va * (err ? 50 : 40) + 12;
+    const int cost_pair = (kStatsTile / 32) * ((full ? 30 : 21) + (err ? 16 : 0));
+    const int items = n_frames * (kStatsTile / va);
+    long best = -1;
+    warps = 8; slots = kMaxSlots;
     for (int s = 1; s <= kMaxSlots; ++s) {
-        for (int w = 4; w <= 16; ++w) {
+        for (int w = 2; w <= 16; ++w) {
             if (w * s < count) continue;
-            const int waste = (w * s - count) * 1000 / (w * s) * 8 + s;   // idle fraction first, then fewer registers
-            if (waste < best_waste) { best_waste = waste; best_w = w; best_s = s; }
+            const int trips = (items + 32 * w - 1) / (32 * w);
+            const long cost = static_cast<long>(w) * (static_cast<long>(trips) * cost_item + static_cast<long>(s) * cost_pair);
+            if (best < 0 || cost < best) { best = cost; warps = w; slots = s; }
         }
     }
-    warps = best_w; slots = best_s;
 }
 
 void common_params(PairParams &p, const float *val, const float *std, const float *theta, int n_frames, int n_channels,
@@ -621,6 +714,11 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
     const int arrays = 2 + (err ? (relative ? 2 : 1) : 0);
     const size_t smem = (theta_dev ? sizeof(float2) * n_channels * lut_size : 0) + sizeof(float) * arrays * n_frames * kStatsTile;
     const int per_launch = 16 * kMaxSlots;   // 64 pairs: 16 warps x 4 register slots
+    // 128-bit staging loads need H*W % 4 == 0 and 16-byte aligned stacks (every frame / channel slab then is, too)
+    const bool vec_ok = plane % 4 == 0 && reinterpret_cast<uintptr_t>(val_dev) % 16 == 0 &&
+                        (!err || reinterpret_cast<uintptr_t>(std_dev) % 16 == 0) &&
+                        (theta_dev == nullptr || (n_channels * lut_size) % 2 == 0);   // tile starts 16-byte aligned after the table
+    const int va = vec_ok ? 4 : 1;
     const int n_launches = (n_pairs + per_launch - 1) / per_launch;
     int first = 0;
     for (int l = 0; l < n_launches; ++l) {
@@ -632,7 +730,7 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
         p.n_pairs = count;
         if (int rc = fill_pairs(fn, p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
         int warps, slots;
-        pick_stats_shape(count, warps, slots);
+        pick_stats_shape(count, n_frames, va, err, full != 0, warps, slots);
         const int64_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
         auto launch = [&](auto kernel) -> int {
             if (int rc = set_smem(kernel, smem)) return rc;
@@ -644,14 +742,15 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
             return 0;
         };
         int rc = 0;
+#define STATS_FLAGS(S, E, R, F) (va == 4 ? launch(pair_stats_kernel<S, E, R, F, 4>) : launch(pair_stats_kernel<S, E, R, F, 1>))
 #define STATS_CASE(S)                                                                                   \
     case S:                                                                                             \
         if (err) {                                                                                      \
-            if (relative) rc = full ? launch(pair_stats_kernel<S, true, true, true>) : launch(pair_stats_kernel<S, true, true, false>);   \
-            else rc = full ? launch(pair_stats_kernel<S, true, false, true>) : launch(pair_stats_kernel<S, true, false, false>);         \
+            if (relative) rc = full ? STATS_FLAGS(S, true, true, true) : STATS_FLAGS(S, true, true, false);     \
+            else rc = full ? STATS_FLAGS(S, true, false, true) : STATS_FLAGS(S, true, false, false);            \
         } else {                                                                                        \
-            if (relative) rc = full ? launch(pair_stats_kernel<S, false, true, true>) : launch(pair_stats_kernel<S, false, true, false>); \
-            else rc = full ? launch(pair_stats_kernel<S, false, false, true>) : launch(pair_stats_kernel<S, false, false, false>);       \
+            if (relative) rc = full ? STATS_FLAGS(S, false, true, true) : STATS_FLAGS(S, false, true, false);   \
+            else rc = full ? STATS_FLAGS(S, false, false, true) : STATS_FLAGS(S, false, false, false);          \
         }                                                                                               \
         break;
         switch (slots) {
@@ -661,6 +760,7 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
             default:
             STATS_CASE(4)
         }
+#undef STATS_FLAGS
 #undef STATS_CASE
         if (rc) return rc;
         if (int rc2 = launched("pair_stats_kernel")) return rc2;
@@ -725,8 +825,11 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
     int first = 0;
     while (first < n_pairs) {
         const int count = std::min(kMaxPairsPerLaunch, n_pairs - first);
-        const size_t fixed_bytes = sizeof(float2) * n_channels * lut_size + sizeof(float) * 2 * count;
-        const size_t per_warp = sizeof(float) * (err ? 6 : 4) * n_frames * 32;
+        const bool pair_ok = plane % 2 == 0 && reinterpret_cast<uintptr_t>(val_dev) % 8 == 0 &&
+                             (!err || reinterpret_cast<uintptr_t>(std_dev) % 8 == 0);
+        const int pixn = pair_ok ? 2 : 1;                         // pixels per lane
+        const size_t fixed_bytes = sizeof(float2) * n_channels * lut_size + sizeof(float) * (2 * count + 2);
+        const size_t per_warp = sizeof(float) * (err ? 6 : 4) * n_frames * 32 * pixn;
         // 4 warps per block: more, smaller blocks balance better across the SMs than 8-warp blocks
         const int warps = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (200 * 1024 - fixed_bytes) / per_warp)));
         const size_t smem = fixed_bytes + per_warp * warps;
@@ -738,7 +841,7 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
         p.hist = static_cast<float *>(workspace_dev);
         p.n_pairs = count;
         if (int rc = fill_pairs(fn, p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
-        const int64_t n_groups = (plane + 31) / 32;
+        const int64_t n_groups = (plane + 32 * pixn - 1) / (32 * pixn);
         auto launch = [&](auto kernel) -> int {
             if (int rc = set_smem(kernel, smem)) return rc;
             int per_sm = 1;
@@ -750,8 +853,10 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
             return 0;
         };
         int rc;
-        if (err) rc = relative ? launch(pair_grad_kernel<true, true>) : launch(pair_grad_kernel<true, false>);
-        else rc = relative ? launch(pair_grad_kernel<false, true>) : launch(pair_grad_kernel<false, false>);
+#define GRAD_FLAGS(E, R) (pixn == 2 ? launch(pair_grad_kernel<E, R, 2>) : launch(pair_grad_kernel<E, R, 1>))
+        if (err) rc = relative ? GRAD_FLAGS(true, true) : GRAD_FLAGS(true, false);
+        else rc = relative ? GRAD_FLAGS(false, true) : GRAD_FLAGS(false, false);
+#undef GRAD_FLAGS
         if (rc) return rc;
         if (int rc2 = launched("pair_grad_kernel")) return rc2;
         first += count;

@@ -153,8 +153,8 @@ def test_row_band_statistics_add_up(ct):
         kernels.pair_stats(val[:, :, r0:r1].contiguous(), std[:, :, r0:r1].contiguous(), i, j, r, theta, 1 / 255, 254 / 255,
                            True, True, row_base=rb, out=acc)
     assert torch.equal(acc[..., 4], whole[..., 4])
-    assert max_rel(acc.cpu().numpy()[..., :3], whole.cpu().numpy()[..., :3], 1e-300) < 1e-12     # float64 sums
-    assert max_rel(acc.cpu().numpy()[..., 3], whole.cpu().numpy()[..., 3], 1e-300) < 1e-7        # fp32 per-tile partials
+    # fp32 partial sums of <= 32 terms per lane, merged in float64: tilings differ by a few 1e-9 relative
+    assert max_rel(acc.cpu().numpy()[..., :4], whole.cpu().numpy()[..., :4], 1e-300) < 1e-7
 
 
 def test_lookup_and_forward_full_frame(ct):
