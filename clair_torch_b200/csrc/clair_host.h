@@ -32,6 +32,8 @@ struct Tuning {
     int hdr_force_dynamic = 0;  // use the N-dynamic float64-sum kernel even for N <= 8
     int stats_blocks_per_sm = 0;
     int grad_blocks_per_sm = 0;
+    int grad_pix = 0;           // 1 forces one pixel per lane in the gradient kernel
+    int grad_warps = 0;         // warps per block of the gradient kernel
 };
 extern Tuning g_tuning;
 

@@ -827,11 +827,12 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
         const int count = std::min(kMaxPairsPerLaunch, n_pairs - first);
         const bool pair_ok = plane % 2 == 0 && reinterpret_cast<uintptr_t>(val_dev) % 8 == 0 &&
                              (!err || reinterpret_cast<uintptr_t>(std_dev) % 8 == 0);
-        const int pixn = pair_ok ? 2 : 1;                         // pixels per lane
+        const int pixn = (pair_ok && g_tuning.grad_pix != 1) ? 2 : 1;   // pixels per lane
         const size_t fixed_bytes = sizeof(float2) * n_channels * lut_size + sizeof(float) * (2 * count + 2);
         const size_t per_warp = sizeof(float) * (err ? 6 : 4) * n_frames * 32 * pixn;
         // 4 warps per block: more, smaller blocks balance better across the SMs than 8-warp blocks
-        const int warps = static_cast<int>(std::max<size_t>(1, std::min<size_t>(4, (200 * 1024 - fixed_bytes) / per_warp)));
+        const size_t want_warps = g_tuning.grad_warps > 0 ? static_cast<size_t>(g_tuning.grad_warps) : 4;
+        const int warps = static_cast<int>(std::max<size_t>(1, std::min<size_t>(want_warps, (200 * 1024 - fixed_bytes) / per_warp)));
         const size_t smem = fixed_bytes + per_warp * warps;
         PairParams p{};
         common_params(p, val_dev, err ? std_dev : nullptr, theta_dev, n_frames, n_channels, plane, lut_size, curve_row_base_host,
