@@ -303,9 +303,9 @@ def main():
     model = ct.ICRFModelDirect(icrf=theta.clone()).to(dev)
 
     def e2e_step():
-        rad, sig = ct.compute_hdr_image(loader, dev, model, max, radiance_dtype=torch.float32)
-        rad_h.copy_(rad, non_blocking=True)
-        sig_h.copy_(sig, non_blocking=True)
+        # pinned host batch in, pinned host results out: the kernel reads the stack over PCIe and writes radiance and
+        # sigma back over PCIe (zero-copy; the bytes below cross the bus inside the timed region)
+        ct.compute_hdr_image(loader, dev, model, max, radiance_dtype=torch.float32, host_out=(rad_h, sig_h))
 
     for _ in range(3):
         e2e_step()
@@ -355,7 +355,7 @@ def main():
                          "kernel": "clair::hdr_merge_fixed_kernel<2,5,true,true> (2 px/thread, N=5 in registers, single batch)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "api": "clair_torch_b200.compute_hdr_image from pinned host batch"},
+                    "ms_per_step": e2e_ms, "api": "clair_torch_b200.compute_hdr_image(pinned host batch, host_out=pinned buffers): zero-copy kernel over PCIe"},
             "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line))

@@ -11,7 +11,7 @@ from ._common import as_device, linear_table, normalise_transforms, reject_artef
 
 def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFModelBase] = None,
                       weight_fn: Optional[Callable] = None, flat_field_dataset=None, gpu_transforms=None,
-                      dark_field_dataset=None, *, radiance_dtype: Optional[torch.dtype] = None):
+                      dark_field_dataset=None, *, radiance_dtype: Optional[torch.dtype] = None, host_out=None):
     """Exposure-weighted HDR merge of a stationary exposure stack with first-order uncertainty.
 
     Each DataLoader batch goes through ONE fused kernel (ICRF evaluation, Gaussian weights, weighted running mean
@@ -21,6 +21,11 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
     Returns (radiance (C,H,W) squeezed, sigma (C,H,W) squeezed or None when the batches carry no std images).
     `radiance_dtype` defaults to the dtype the reference returns (float64, because the collated exposure times
     are float64 — SURVEY.md Q6); pass torch.float32 to halve the output traffic.
+
+    Host batches that are page-locked (DataLoader(pin_memory=True) or pre-pinned tensors) are read by the kernel
+    directly over PCIe — each input element is needed exactly once, so no staging copy is made; pageable batches
+    are copied to the device first like the reference does.  `host_out=(radiance, sigma)`, two pinned (C,H,W) host
+    tensors, makes the kernel write the results straight to host memory (they are then what is returned).
     """
     if not isinstance(dataloader, DataLoader):
         raise TypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
@@ -38,13 +43,19 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
     while current is not None:
         upcoming = next(batches, None)                   # look one batch ahead to know which one is the last
         _, val_batch, std_batch, meta_batch = current
-        images, stds = stage_batch(val_batch, std_batch, dev, transforms)
+        zero_copy = (not transforms and not val_batch.is_cuda and val_batch.is_pinned() and val_batch.is_contiguous()
+                     and (std_batch is None or (std_batch.is_pinned() and std_batch.is_contiguous())))
+        if zero_copy:
+            images, stds = val_batch, std_batch
+        else:
+            images, stds = stage_batch(val_batch, std_batch, dev, transforms)
         exposures = meta_batch["exposure_time"]
         out_dtype = radiance_dtype
         if out_dtype is None:
             out_dtype = torch.promote_types(images.dtype, exposures.dtype if torch.is_tensor(exposures) else torch.float64)
         result = kernels.hdr_merge_update(state, images, stds, exposures, table, weight_fn is not None,
-                                          is_final=upcoming is None, radiance_dtype=out_dtype)
+                                          is_final=upcoming is None, radiance_dtype=out_dtype, device=dev,
+                                          host_out=host_out if upcoming is None else None)
         current = upcoming
     if result is None:
         raise ValueError("the dataloader yielded no batches")

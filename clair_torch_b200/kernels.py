@@ -25,11 +25,15 @@ def _stream(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def _stack(t: torch.Tensor, name: str) -> torch.Tensor:
-    """An (N, C, H, W) fp32 CUDA stack, made contiguous (MissingStdMode.CONSTANT hands over stride-0 views)."""
+def _stack(t: torch.Tensor, name: str, allow_pinned: bool = False) -> torch.Tensor:
+    """An (N, C, H, W) fp32 CUDA stack, made contiguous (MissingStdMode.CONSTANT hands over stride-0 views).
+    With `allow_pinned`, a contiguous page-locked HOST tensor is accepted as well: the kernel then reads it over PCIe
+    directly (every input element is read exactly once, so staging it in HBM first only adds a copy)."""
     if not isinstance(t, torch.Tensor):
         raise TypeError(f"{name} must be a torch.Tensor, got {type(t)}")
     if not t.is_cuda:
+        if allow_pinned and t.is_pinned() and t.is_contiguous() and t.dtype == _F32 and t.dim() == 4:
+            return t.detach()
         raise RuntimeError(f"{name} must live on a CUDA device: clair_torch_b200 has no CPU path")
     if t.dtype != _F32:
         raise TypeError(f"{name} must be float32, got {t.dtype}")
@@ -128,23 +132,28 @@ class HdrMergeState:
         self.var: Optional[torch.Tensor] = None      # (C, H, W) float32
         self.batches = 0
 
-    def _ensure(self, like: torch.Tensor, with_var: bool):
-        shape = tuple(like.shape[1:])
+    def _ensure(self, shape, device, with_var: bool):
         if self.mean is None:
-            self.mean = torch.empty(shape, dtype=_F64, device=like.device)
-            self.wsum = torch.empty(shape, dtype=_F32, device=like.device)
+            self.mean = torch.empty(shape, dtype=_F64, device=device)
+            self.wsum = torch.empty(shape, dtype=_F32, device=device)
         if with_var and self.var is None:
-            self.var = torch.empty(shape, dtype=_F32, device=like.device)
+            self.var = torch.empty(shape, dtype=_F32, device=device)
 
 
 def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std: Optional[torch.Tensor], exposure,
                      theta: Optional[torch.Tensor], gaussian_weights: bool, is_final: bool,
-                     radiance_dtype: torch.dtype = _F64, row_base=None):
+                     radiance_dtype: torch.dtype = _F64, row_base=None, device=None, host_out=None):
     """One batch of compute_hdr_image (inference/hdr_merge.py:95-128).  Returns (radiance, sigma) when
-    `is_final`, else None.  `exposure` is the collated float64 'exposure_time' (host tensor, array or list)."""
+    `is_final`, else None.  `exposure` is the collated float64 'exposure_time' (host tensor, array or list).
+
+    `val` / `std` may be pinned host tensors (zero-copy: `device` then names the GPU that runs the kernel), and
+    `host_out=(radiance, sigma)` pinned host buffers make the kernel write its results straight to host memory."""
     lib = _native.load()
-    val = _stack(val, "val_batch")
-    std = None if std is None else _stack(std, "std_batch")
+    val = _stack(val, "val_batch", allow_pinned=device is not None)
+    std = None if std is None else _stack(std, "std_batch", allow_pinned=device is not None)
+    dev = torch.device(device) if device is not None else val.device
+    if val.is_cuda and val.device != dev:
+        raise ValueError("val_batch lives on a different device than the one requested")
     if std is not None and std.shape != val.shape:
         raise ValueError("std_batch must have the same shape as val_batch")
     n, c, h, w = val.shape
@@ -153,26 +162,38 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std: Optional[torc
     t = np.ascontiguousarray(np.asarray(exposure, dtype=np.float64).reshape(-1))
     if t.shape[0] != n:
         raise ValueError(f"{n} frames but {t.shape[0]} exposure times")
-    th = _table(theta, val.device, c)
+    th = _table(theta, dev, c)
     lut = 0 if th is None else th.shape[1]
     is_first = state.batches == 0
     if std is not None and not is_first and state.var is None:
         raise ValueError("std images appeared after a batch without them")
     if not (is_first and is_final):
-        state._ensure(val, std is not None)
+        state._ensure((c, h, w), dev, std is not None)
     radiance = sigma = None
     if is_final:
         if radiance_dtype not in (_F32, _F64):
             raise TypeError("radiance_dtype must be torch.float32 or torch.float64")
-        radiance = torch.empty((c, h, w), dtype=radiance_dtype, device=val.device)
-        if std is not None:
-            sigma = torch.empty((c, h, w), dtype=_F32, device=val.device)
+        if host_out is not None:
+            radiance, sigma = host_out
+            ok = (radiance.is_pinned() and radiance.is_contiguous() and tuple(radiance.shape) == (c, h, w)
+                  and radiance.dtype == radiance_dtype)
+            if std is not None:
+                ok = ok and sigma is not None and sigma.is_pinned() and sigma.is_contiguous() and sigma.dtype == _F32 \
+                    and tuple(sigma.shape) == (c, h, w)
+            if not ok:
+                raise ValueError("host_out must be pinned, contiguous (C, H, W) tensors of the output dtypes")
+            if std is None:
+                sigma = None
+        else:
+            radiance = torch.empty((c, h, w), dtype=radiance_dtype, device=dev)
+            if std is not None:
+                sigma = torch.empty((c, h, w), dtype=_F32, device=dev)
     keep, rows = _rows(row_base, c)
-    with torch.cuda.device(val.device):
+    with torch.cuda.device(dev):
         rc = lib.clair_hdr_merge_update(
             _ptr(val), _ptr(std), t.ctypes.data_as(ctypes.c_void_p), n, _ptr(th), c, lut, h * w, rows,
             int(bool(gaussian_weights)), _ptr(state.mean), _ptr(state.wsum), _ptr(state.var), int(is_first),
-            int(is_final), _ptr(radiance), int(radiance_dtype == _F64), _ptr(sigma), _stream(val.device))
+            int(is_final), _ptr(radiance), int(radiance_dtype == _F64), _ptr(sigma), _stream(dev))
     _native.check(rc, "clair_hdr_merge_update")
     state.batches += 1
     return (radiance, sigma) if is_final else None

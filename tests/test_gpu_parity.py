@@ -284,3 +284,30 @@ def test_train_icrf_step_updates_like_reference(ct):
     diff = np.abs(model.icrf.detach().cpu().numpy() - z["theta_after_0"])
     assert diff[strong].max() < 5e-7
     assert loss0.shape == (3,)
+
+
+def test_hdr_merge_zero_copy_pinned_host(ct):
+    """Pinned host batches are read by the kernel over PCIe and results can be written straight to pinned host
+    buffers: bit-identical to the staged path, for one batch and for several."""
+    from clair_torch_b200.datasets import ExposureStackDataset, custom_collate
+    val, std, t = ct.synthetic.make_stack(5, 3, 90, 160, seed=17)
+    theta = ct.synthetic.reference_curve(3)
+    model = _model(ct, theta.numpy())
+    z = {"val": val.numpy(), "std": std.numpy(), "exposure": t}
+    ref_rad, ref_sig = ct.compute_hdr_image(_loader(ct, z, 5), DEV, model, max, radiance_dtype=torch.float32)
+    ds = ExposureStackDataset(list(val), list(std), list(t))
+    for bs in (5, 2):
+        loader = DataLoader(ds, batch_size=bs, shuffle=False, collate_fn=custom_collate, pin_memory=True)
+        rad_h = torch.empty((3, 90, 160), dtype=torch.float32).pin_memory()
+        sig_h = torch.empty((3, 90, 160), dtype=torch.float32).pin_memory()
+        rad, sig = ct.compute_hdr_image(loader, DEV, model, max, radiance_dtype=torch.float32, host_out=(rad_h, sig_h))
+        torch.cuda.synchronize()
+        assert rad.data_ptr() == rad_h.data_ptr() and not rad.is_cuda
+        if bs == 5:
+            assert torch.equal(rad, ref_rad.cpu()) and torch.equal(sig, ref_sig.cpu())
+        else:
+            o_rad, o_sig = orc.hdr_merge(z["val"], z["std"], t, theta.numpy(), True, bs)
+            assert max_rel(rad.numpy(), o_rad) < 2e-6 and max_rel(sig.numpy(), o_sig) < 5e-6
+    with pytest.raises(ValueError):
+        ct.compute_hdr_image(loader, DEV, model, max, radiance_dtype=torch.float32,
+                             host_out=(torch.empty((3, 90, 160)), torch.empty((3, 90, 160))))
