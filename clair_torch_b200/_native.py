@@ -41,6 +41,10 @@ _PROTOTYPES = {
                                           _c.c_int, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,
                                           _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
                                           _c.c_void_p]),
+    "clair_hdr_merge_codes": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_float, _c.c_void_p, _c.c_int, _c.c_float, _c.c_void_p,
+                                         _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_int,
+                                         _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int,
+                                         _c.c_void_p, _c.c_void_p]),
     "clair_pair_stats": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p,
                                     _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
                                     _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),

@@ -5,6 +5,8 @@
 #include "clair_common.cuh"
 #include "clair_host.h"
 
+#include <cstdio>
+
 namespace clair {
 
 constexpr int kBlock = 256;
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(kBlock) icrf_forward_kernel(const ForwardParam
 // HDR merge + uncertainty
 // =====================================================================================================
 struct HdrParams {
-    const float *val;
+    const void *val;          // fp32 values, or uint8 / uint16 codes (integer ingest)
     const float *std;
     const float *theta;       // nullptr = identity
     double *mean_state;
@@ -94,9 +96,53 @@ struct HdrParams {
     int is_first;
     int is_final;
     int radiance_f64;
+    int std_mode;             // kStdNone / kStdTensor / kStdMultiplier / kStdConstant
+    float std_value;          // multiplier or constant
+    float code_max;           // integer ingest: x = fl32(code) / fl32(code_max)   (CastTo + Normalize)
     CurveRows rows;
     FrameScale scale;
 };
+
+constexpr int kStdNone = 0, kStdTensor = 1, kStdMultiplier = 2, kStdConstant = 3;
+constexpr int kSrcF32 = 0, kSrcU8 = 1, kSrcU16 = 2;
+
+// One frame's VEC pixel values.  SRC = kSrcF32: the fp32 stack the reference hands over.  kSrcU8 / kSrcU16: the raw
+// integer codes, normalised in-register exactly like the reference's CPU transforms do it (CastTo(float32) then
+// Normalize(max_val, min_val=0): an IEEE fp32 division, clair_torch/common/general_functions.py:378) — 8-bit codes
+// go through a 256-entry table of those quotients, 16-bit codes through __fdiv_rn.
+template <int SRC, int VEC>
+__device__ __forceinline__ Pack<VEC> load_pixels(const void *base, int64_t o, float code_max, const float *s_x) {
+    if constexpr (SRC == kSrcF32) {
+        return load_stream<VEC>(static_cast<const float *>(base) + o);
+    } else if constexpr (SRC == kSrcU8) {
+        static_assert(VEC == 4, "integer ingest is 4 pixels per thread");
+        const uint32_t w = __ldcs(reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(base) + o));
+        Pack<VEC> r;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r.v[k] = s_x[(w >> (8 * k)) & 0xffu];
+        return r;
+    } else {
+        static_assert(VEC == 4, "integer ingest is 4 pixels per thread");
+        const uint2 w = __ldcs(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(base) + o));
+        Pack<VEC> r;
+        r.v[0] = __fdiv_rn(static_cast<float>(w.x & 0xffffu), code_max);
+        r.v[1] = __fdiv_rn(static_cast<float>(w.x >> 16), code_max);
+        r.v[2] = __fdiv_rn(static_cast<float>(w.y & 0xffffu), code_max);
+        r.v[3] = __fdiv_rn(static_cast<float>(w.y >> 16), code_max);
+        return r;
+    }
+}
+
+// The std of one frame's VEC pixels: a tensor, or synthesised the way MultiFileMapDataset does for missing std
+// images (clair_torch/datasets/base.py:128-133): value * multiplier, or a constant.
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> load_std(const HdrParams &p, int64_t o, const Pack<VEC> &x) {
+    if (p.std_mode == kStdTensor) return load_stream<VEC>(p.std + o);
+    Pack<VEC> r;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) r.v[k] = (p.std_mode == kStdMultiplier) ? __fmul_rn(x.v[k], p.std_value) : p.std_value;
+    return r;
+}
 
 // Per frame element (all fp32):
 //   w = exp(-30 (x-.5)^2) | 1,   q = w'/w = -60 (x-.5) | 0,   v = f(x)/t
@@ -241,15 +287,17 @@ struct RowCursor {
 // is a plain sum of squares of the actual (small) per-frame terms: no cancellation, everything in fp32.
 constexpr int kMaxFixedFrames = 8;
 
-template <int VEC, int NF, bool HAS_STD, bool SINGLE>
+template <int VEC, int NF, bool HAS_STD, bool SINGLE, int SRC>
 __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams p) {
     extern __shared__ float2 s_tab[];
     const int C = p.n_channels, L = p.lut;
     const bool has_model = p.theta != nullptr;
-    if (has_model) {
-        stage_curve_pairs(s_tab, p.theta, C, L);
-        __syncthreads();
+    float *s_x = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));     // kSrcU8: code -> fl32(code)/code_max
+    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
+    if constexpr (SRC == kSrcU8) {
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
     }
+    __syncthreads();
     const int c = blockIdx.y;
     const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
     const float lm1 = static_cast<float>(L - 1);
@@ -268,8 +316,8 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
 #pragma unroll
         for (int n = 0; n < NF; ++n) {
             const int64_t o = off + static_cast<int64_t>(n) * frame_stride;
-            xv[n] = load_stream<VEC>(p.val + o);
-            if constexpr (HAS_STD) sv[n] = load_stream<VEC>(p.std + o);
+            xv[n] = load_pixels<SRC, VEC>(p.val, o, p.code_max, s_x);
+            if constexpr (HAS_STD) sv[n] = load_std<VEC>(p, o, xv[n]);
         }
         uint32_t bias[VEC];
         {
@@ -311,15 +359,17 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
 // ---- fallback for N > kMaxFixedFrames: single pass, N dynamic --------------------------------------------
 // sum_n (alpha R_n + gamma Q_n)^2 = alpha^2 SRR + 2 alpha gamma SRQ + gamma^2 SQQ needs only three running
 // sums, but the expansion cancels (|gamma Q| can be ~14x the result), so the three sums are float64.
-template <int VEC, bool HAS_STD>
+template <int VEC, bool HAS_STD, int SRC>
 __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
     extern __shared__ float2 s_tab[];
     const int C = p.n_channels, L = p.lut;
     const bool has_model = p.theta != nullptr;
-    if (has_model) {
-        stage_curve_pairs(s_tab, p.theta, C, L);
-        __syncthreads();
+    float *s_x = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
+    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
+    if constexpr (SRC == kSrcU8) {
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
     }
+    __syncthreads();
     const int c = blockIdx.y;
     const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
     const float lm1 = static_cast<float>(L - 1);
@@ -354,8 +404,8 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
             for (int j = 0; j < kFrameChunk; ++j) {
                 if (n0 + j < N) {
                     const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
-                    xv[j] = load_stream<VEC>(p.val + o);
-                    if constexpr (HAS_STD) sv[j] = load_stream<VEC>(p.std + o);
+                    xv[j] = load_pixels<SRC, VEC>(p.val, o, p.code_max, s_x);
+                    if constexpr (HAS_STD) sv[j] = load_std<VEC>(p, o, xv[j]);
                 }
             }
 #pragma unroll
@@ -472,90 +522,128 @@ extern "C" int clair_linearize(const float *val_dev, const float *std_dev, const
     return launched("icrf_forward_kernel<linearize>");
 }
 
-extern "C" int clair_hdr_merge_update(const float *val_dev, const float *std_dev, const double *exposure_host,
-                                      int n_frames, const float *theta_dev, int n_channels, int lut_size,
-                                      int64_t plane, const int32_t *curve_row_base_host, int gaussian_weights,
-                                      double *mean_state_dev, float *wsum_state_dev, float *var_state_dev,
-                                      int is_first, int is_final, void *radiance_dev, int radiance_f64,
-                                      float *sigma_dev, void *stream) {
-    if (!val_dev || !exposure_host) return fail(CLAIR_E_ARG, "clair_hdr_merge_update: null val/exposure");
+namespace {
+
+// Shared implementation of clair_hdr_merge_update (src = kSrcF32) and clair_hdr_merge_codes (kSrcU8 / kSrcU16).
+int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max, const float *std_dev, int std_mode,
+                   float std_value, const double *exposure_host, int n_frames, const float *theta_dev, int n_channels,
+                   int lut_size, int64_t plane, const int32_t *curve_row_base_host, int gaussian_weights,
+                   double *mean_state_dev, float *wsum_state_dev, float *var_state_dev, int is_first, int is_final,
+                   void *radiance_dev, int radiance_f64, float *sigma_dev, void *stream) {
+    char msg[200];
+    auto bad = [&](int code, const char *what) {
+        std::snprintf(msg, sizeof(msg), "%s: %s", fn, what);
+        return fail(code, msg);
+    };
+    if (!val_dev || !exposure_host) return bad(CLAIR_E_ARG, "null val/exposure");
     if (theta_dev == nullptr && lut_size <= 0) lut_size = 2;   // unused without a model
-    if (int rc = check_geometry("clair_hdr_merge_update", n_frames, n_channels, plane, lut_size, true)) return rc;
+    if (int rc = check_geometry(fn, n_frames, n_channels, plane, lut_size, true)) return rc;
+    if (std_mode < kStdNone || std_mode > kStdConstant) return bad(CLAIR_E_MODE, "unknown std_mode");
+    if (std_mode == kStdTensor && !std_dev) return bad(CLAIR_E_ARG, "std_mode = tensor needs std_dev");
+    const bool has_std = std_mode != kStdNone;
     const bool need_state = !(is_first && is_final);
-    if (need_state && (!mean_state_dev || !wsum_state_dev || (std_dev && !var_state_dev)))
-        return fail(CLAIR_E_ARG, "clair_hdr_merge_update: running-state buffers required unless is_first && is_final");
-    if (is_final && (!radiance_dev || (std_dev && !sigma_dev)))
-        return fail(CLAIR_E_ARG, "clair_hdr_merge_update: output buffers required when is_final");
+    if (need_state && (!mean_state_dev || !wsum_state_dev || (has_std && !var_state_dev)))
+        return bad(CLAIR_E_ARG, "running-state buffers required unless is_first && is_final");
+    if (is_final && (!radiance_dev || (has_std && !sigma_dev))) return bad(CLAIR_E_ARG, "output buffers required when is_final");
     HdrParams p{};
     p.val = val_dev; p.std = std_dev; p.theta = theta_dev;
     p.mean_state = mean_state_dev; p.wsum_state = wsum_state_dev; p.var_state = var_state_dev;
     p.radiance = radiance_dev; p.sigma = sigma_dev;
     p.plane = plane; p.n_frames = n_frames; p.n_channels = n_channels; p.lut = lut_size;
     p.gaussian = gaussian_weights; p.is_first = is_first; p.is_final = is_final; p.radiance_f64 = radiance_f64;
+    p.std_mode = std_mode; p.std_value = std_value; p.code_max = code_max;
     fill_rows(p.rows, curve_row_base_host, n_channels, plane);
     for (int n = 0; n < n_frames; ++n) p.scale.inv_t[n] = static_cast<float>(1.0 / exposure_host[n]);
-    int vec = pick_vec(plane, {val_dev, std_dev, wsum_state_dev, var_state_dev, sigma_dev});
+    int vec = pick_vec(plane, {src == kSrcF32 ? val_dev : nullptr, std_dev, wsum_state_dev, var_state_dev, sigma_dev});
     // float64 buffers need twice the alignment for the paired 128-bit stores
     for (const void *q : {static_cast<const void *>(mean_state_dev), static_cast<const void *>(radiance_f64 ? radiance_dev : nullptr)}) {
         if (q && reinterpret_cast<uintptr_t>(q) % 16 != 0) vec = 1;
     }
     if (!radiance_f64 && radiance_dev) vec = std::min(vec, pick_vec(plane, {radiance_dev}));
-    const size_t smem = theta_dev ? sizeof(float2) * n_channels * lut_size : 0;
+    if (src != kSrcF32) {
+        // four codes per 32- / 64-bit load
+        const size_t code_bytes = src == kSrcU8 ? 1 : 2;
+        if (vec != 4 || reinterpret_cast<uintptr_t>(val_dev) % (4 * code_bytes) != 0)
+            return bad(CLAIR_E_ARG, "integer ingest needs H*W % 4 == 0 and 16-byte aligned output / std / state buffers");
+    }
+    const size_t smem = (theta_dev ? sizeof(float2) * n_channels * lut_size : 0) + (src == kSrcU8 ? 256 * sizeof(float) : 0);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const bool has_std = std_dev != nullptr;
     const bool single = is_first && is_final;
-    // measured on B200 (profiles/): 2 pixels per thread keeps the fixed-N kernel at 64 registers (4 blocks/SM);
-    // 4 pixels per thread needs 105 and halves the resident warps
-    const int vec_cap = g_tuning.hdr_vec > 0 ? g_tuning.hdr_vec : ((has_std && n_frames <= kMaxFixedFrames) ? 2 : 4);
-    if (vec_cap < vec) vec = vec_cap;
+    const bool fixed = has_std && n_frames <= kMaxFixedFrames && !g_tuning.hdr_force_dynamic;
+    // measured on B200 (profiles/): with fp32 input 2 pixels per thread keep the fixed-N kernel at 40 registers
+    // (6 blocks/SM); 4 pixels per thread need 64.  Integer ingest always takes 4 codes per load.
+    if (src == kSrcF32) {
+        const int vec_cap = g_tuning.hdr_vec > 0 ? g_tuning.hdr_vec : (fixed ? 2 : 4);
+        if (vec_cap < vec) vec = vec_cap;
+    }
     const int64_t items = plane / vec;
     const int64_t want_blocks = (items + kBlock - 1) / kBlock;
     // persistent grid: a whole number of resident waves (blocks/SM from the occupancy calculator), split over C
-    auto grid_for = [&](auto kernel) {
+    auto launch = [&](auto kernel) -> int {
+        if (int rc = ensure_smem(kernel, smem)) return rc;
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
-        per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : 2);   // 2 waves: best tail/balance measured (profiles/)
+        per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : 2);   // 2 waves: best tail/balance measured
         const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want_blocks, (static_cast<int64_t>(device_sm_count()) * per_sm + n_channels - 1) / n_channels));
-        return dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels));
+        kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p);
+        return 0;
     };
-#define LAUNCH_FIXED(V, NF, S)                                                                    \
-    do {                                                                                          \
-        if (single) {                                                                             \
-            if (int rc = ensure_smem(hdr_merge_fixed_kernel<V, NF, S, true>, smem)) return rc;    \
-            hdr_merge_fixed_kernel<V, NF, S, true><<<grid_for(hdr_merge_fixed_kernel<V, NF, S, true>), kBlock, smem, s>>>(p); \
-        } else {                                                                                  \
-            if (int rc = ensure_smem(hdr_merge_fixed_kernel<V, NF, S, false>, smem)) return rc;   \
-            hdr_merge_fixed_kernel<V, NF, S, false><<<grid_for(hdr_merge_fixed_kernel<V, NF, S, false>), kBlock, smem, s>>>(p); \
-        }                                                                                         \
-    } while (0)
-#define LAUNCH_DYN(V, S)                                                                          \
-    do {                                                                                          \
-        if (int rc = ensure_smem(hdr_merge_kernel<V, S>, smem)) return rc;                        \
-        hdr_merge_kernel<V, S><<<grid_for(hdr_merge_kernel<V, S>), kBlock, smem, s>>>(p);         \
-    } while (0)
-#define DISPATCH_NF(V)                                                                            \
-    do {                                                                                          \
-        switch (n_frames) {                                                                       \
-            case 1: LAUNCH_FIXED(V, 1, true); break;                                              \
-            case 2: LAUNCH_FIXED(V, 2, true); break;                                              \
-            case 3: LAUNCH_FIXED(V, 3, true); break;                                              \
-            case 4: LAUNCH_FIXED(V, 4, true); break;                                              \
-            case 5: LAUNCH_FIXED(V, 5, true); break;                                              \
-            case 6: LAUNCH_FIXED(V, 6, true); break;                                              \
-            case 7: LAUNCH_FIXED(V, 7, true); break;                                              \
-            case 8: LAUNCH_FIXED(V, 8, true); break;                                              \
-            default: LAUNCH_DYN(V, true); break;                                                  \
-        }                                                                                         \
-    } while (0)
-    if (has_std && !g_tuning.hdr_force_dynamic) {
-        if (vec == 4) DISPATCH_NF(4); else if (vec == 2) DISPATCH_NF(2); else DISPATCH_NF(1);
-    } else if (has_std) {
-        if (vec == 4) LAUNCH_DYN(4, true); else if (vec == 2) LAUNCH_DYN(2, true); else LAUNCH_DYN(1, true);
-    } else {
-        if (vec == 4) LAUNCH_DYN(4, false); else if (vec == 2) LAUNCH_DYN(2, false); else LAUNCH_DYN(1, false);
+    int rc = 0;
+#define FIXED_NF(V, NF, SRC) (single ? launch(hdr_merge_fixed_kernel<V, NF, true, true, SRC>) : launch(hdr_merge_fixed_kernel<V, NF, true, false, SRC>))
+#define FIXED(V, SRC)                                   \
+    switch (n_frames) {                                 \
+        case 1: rc = FIXED_NF(V, 1, SRC); break;        \
+        case 2: rc = FIXED_NF(V, 2, SRC); break;        \
+        case 3: rc = FIXED_NF(V, 3, SRC); break;        \
+        case 4: rc = FIXED_NF(V, 4, SRC); break;        \
+        case 5: rc = FIXED_NF(V, 5, SRC); break;        \
+        case 6: rc = FIXED_NF(V, 6, SRC); break;        \
+        case 7: rc = FIXED_NF(V, 7, SRC); break;        \
+        default: rc = FIXED_NF(V, 8, SRC); break;       \
     }
-#undef DISPATCH_NF
-#undef LAUNCH_DYN
-#undef LAUNCH_FIXED
+#define DYN(V, SRC) rc = has_std ? launch(hdr_merge_kernel<V, true, SRC>) : launch(hdr_merge_kernel<V, false, SRC>)
+    if (src == kSrcU8) {
+        if (fixed) { FIXED(4, kSrcU8) } else { DYN(4, kSrcU8); }
+    } else if (src == kSrcU16) {
+        if (fixed) { FIXED(4, kSrcU16) } else { DYN(4, kSrcU16); }
+    } else if (vec == 4) {
+        if (fixed) { FIXED(4, kSrcF32) } else { DYN(4, kSrcF32); }
+    } else if (vec == 2) {
+        if (fixed) { FIXED(2, kSrcF32) } else { DYN(2, kSrcF32); }
+    } else {
+        if (fixed) { FIXED(1, kSrcF32) } else { DYN(1, kSrcF32); }
+    }
+#undef DYN
+#undef FIXED
+#undef FIXED_NF
+    if (rc) return rc;
     return launched("hdr_merge_kernel");
+}
+
+}  // namespace
+
+extern "C" int clair_hdr_merge_update(const float *val_dev, const float *std_dev, const double *exposure_host,
+                                      int n_frames, const float *theta_dev, int n_channels, int lut_size,
+                                      int64_t plane, const int32_t *curve_row_base_host, int gaussian_weights,
+                                      double *mean_state_dev, float *wsum_state_dev, float *var_state_dev,
+                                      int is_first, int is_final, void *radiance_dev, int radiance_f64,
+                                      float *sigma_dev, void *stream) {
+    return hdr_merge_impl("clair_hdr_merge_update", val_dev, kSrcF32, 1.0f, std_dev, std_dev ? kStdTensor : kStdNone, 0.0f,
+                          exposure_host, n_frames, theta_dev, n_channels, lut_size, plane, curve_row_base_host, gaussian_weights,
+                          mean_state_dev, wsum_state_dev, var_state_dev, is_first, is_final, radiance_dev, radiance_f64,
+                          sigma_dev, stream);
+}
+
+extern "C" int clair_hdr_merge_codes(const void *codes_dev, int code_bytes, float code_max, const float *std_dev, int std_mode,
+                                     float std_value, const double *exposure_host, int n_frames, const float *theta_dev,
+                                     int n_channels, int lut_size, int64_t plane, const int32_t *curve_row_base_host,
+                                     int gaussian_weights, double *mean_state_dev, float *wsum_state_dev,
+                                     float *var_state_dev, int is_first, int is_final, void *radiance_dev, int radiance_f64,
+                                     float *sigma_dev, void *stream) {
+    if (code_bytes != 1 && code_bytes != 2) return fail(CLAIR_E_MODE, "clair_hdr_merge_codes: code_bytes must be 1 (uint8) or 2 (uint16)");
+    if (!(code_max > 0.0f)) return fail(CLAIR_E_ARG, "clair_hdr_merge_codes: code_max must be positive");
+    return hdr_merge_impl("clair_hdr_merge_codes", codes_dev, code_bytes == 1 ? kSrcU8 : kSrcU16, code_max, std_dev, std_mode,
+                          std_value, exposure_host, n_frames, theta_dev, n_channels, lut_size, plane, curve_row_base_host,
+                          gaussian_weights, mean_state_dev, wsum_state_dev, var_state_dev, is_first, is_final, radiance_dev,
+                          radiance_f64, sigma_dev, stream);
 }

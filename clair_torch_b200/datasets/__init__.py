@@ -1,4 +1,4 @@
 from .collate import custom_collate
-from .stack_dataset import ExposureStackDataset
+from .stack_dataset import ExposureStackDataset, StdSpec
 
-__all__ = ["custom_collate", "ExposureStackDataset"]
+__all__ = ["custom_collate", "ExposureStackDataset", "StdSpec"]

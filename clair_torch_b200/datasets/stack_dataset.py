@@ -4,16 +4,35 @@ The reference's file-backed datasets (clair_torch/datasets/base.py:20-172) are o
 yields `(index, val (C,H,W) fp32, std (C,H,W) fp32 | None, {'exposure_time': float})` works with the driver
 loops here, including the reference's own ImageMapDataset when clair_torch is installed.
 """
+from dataclasses import dataclass
 from typing import Optional, Sequence
 
 import torch
 from torch.utils.data import Dataset
 
 
+@dataclass(frozen=True)
+class StdSpec:
+    """A std image that is a function of the value image, evaluated inside the kernel instead of being materialised:
+    the two ways MultiFileMapDataset fills in a missing std image (clair_torch/datasets/base.py:128-133).
+      mode "multiplier": std = value * `value`     (MissingStdMode.MULTIPLIER; value after normalisation)
+      mode "constant"  : std = `value`             (MissingStdMode.CONSTANT)
+    """
+    mode: str
+    value: float
+
+    def __post_init__(self):
+        if self.mode not in ("multiplier", "constant"):
+            raise ValueError(f"StdSpec mode must be 'multiplier' or 'constant', got {self.mode!r}")
+
+
 class ExposureStackDataset(Dataset):
-    def __init__(self, vals: Sequence[torch.Tensor] | torch.Tensor, stds: Optional[Sequence[torch.Tensor] | torch.Tensor],
-                 exposures: Sequence[float], copy: bool = False):
-        if len(vals) != len(exposures) or (stds is not None and len(stds) != len(vals)):
+    def __init__(self, vals: Sequence[torch.Tensor] | torch.Tensor,
+                 stds: Optional[Sequence[torch.Tensor] | torch.Tensor | StdSpec], exposures: Sequence[float],
+                 copy: bool = False):
+        """`vals` may be fp32 (already normalised, the reference's hand-over) or raw uint8 / uint16 codes (integer
+        ingest); `stds` a matching sequence of fp32 images, None, or a StdSpec."""
+        if len(vals) != len(exposures) or (stds is not None and not isinstance(stds, StdSpec) and len(stds) != len(vals)):
             raise ValueError("vals, stds and exposures must have the same length")
         self.vals, self.stds, self.exposures, self.copy = vals, stds, [float(e) for e in exposures], copy
         self.files = tuple(range(len(vals)))
@@ -23,8 +42,11 @@ class ExposureStackDataset(Dataset):
 
     def __getitem__(self, idx: int):
         val = self.vals[idx]
-        std = None if self.stds is None else self.stds[idx]
+        if self.stds is None or isinstance(self.stds, StdSpec):
+            std = self.stds
+        else:
+            std = self.stds[idx]
         if self.copy:
             val = val.clone()
-            std = None if std is None else std.clone()
+            std = std.clone() if torch.is_tensor(std) else std
         return idx, val, std, {"exposure_time": self.exposures[idx]}

@@ -11,7 +11,8 @@ from ._common import as_device, linear_table, normalise_transforms, reject_artef
 
 def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFModelBase] = None,
                       weight_fn: Optional[Callable] = None, flat_field_dataset=None, gpu_transforms=None,
-                      dark_field_dataset=None, *, radiance_dtype: Optional[torch.dtype] = None, host_out=None):
+                      dark_field_dataset=None, *, radiance_dtype: Optional[torch.dtype] = None, host_out=None,
+                      code_max: Optional[float] = None):
     """Exposure-weighted HDR merge of a stationary exposure stack with first-order uncertainty.
 
     Each DataLoader batch goes through ONE fused kernel (ICRF evaluation, Gaussian weights, weighted running mean
@@ -26,6 +27,12 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
     directly over PCIe — each input element is needed exactly once, so no staging copy is made; pageable batches
     are copied to the device first like the reference does.  `host_out=(radiance, sigma)`, two pinned (C,H,W) host
     tensors, makes the kernel write the results straight to host memory (they are then what is returned).
+
+    Integer ingest: batches may carry the raw uint8 / uint16 camera codes instead of
+    normalised fp32 images; the kernel then performs the reference's CastTo(float32) + Normalize(max_val=code_max,
+    min_val=0) on load (code_max defaults to 255 / 65535), and the std batch may be a `datasets.StdSpec`
+    (MissingStdMode.MULTIPLIER / CONSTANT evaluated in-register).  Results are bit-identical to feeding the
+    CPU-transformed fp32 images; 4-8x fewer bytes cross PCIe and HBM.
     """
     if not isinstance(dataloader, DataLoader):
         raise TypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
@@ -43,19 +50,22 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
     while current is not None:
         upcoming = next(batches, None)                   # look one batch ahead to know which one is the last
         _, val_batch, std_batch, meta_batch = current
+        std_is_tensor = torch.is_tensor(std_batch)
         zero_copy = (not transforms and not val_batch.is_cuda and val_batch.is_pinned() and val_batch.is_contiguous()
-                     and (std_batch is None or (std_batch.is_pinned() and std_batch.is_contiguous())))
+                     and (not std_is_tensor or (std_batch.is_pinned() and std_batch.is_contiguous())))
         if zero_copy:
             images, stds = val_batch, std_batch
         else:
-            images, stds = stage_batch(val_batch, std_batch, dev, transforms)
+            images, stds = stage_batch(val_batch, std_batch if std_is_tensor else None, dev, transforms)
+            stds = stds if std_is_tensor else std_batch
         exposures = meta_batch["exposure_time"]
         out_dtype = radiance_dtype
         if out_dtype is None:
-            out_dtype = torch.promote_types(images.dtype, exposures.dtype if torch.is_tensor(exposures) else torch.float64)
+            value_dtype = torch.float32 if not images.dtype.is_floating_point else images.dtype
+            out_dtype = torch.promote_types(value_dtype, exposures.dtype if torch.is_tensor(exposures) else torch.float64)
         result = kernels.hdr_merge_update(state, images, stds, exposures, table, weight_fn is not None,
                                           is_final=upcoming is None, radiance_dtype=out_dtype, device=dev,
-                                          host_out=host_out if upcoming is None else None)
+                                          host_out=host_out if upcoming is None else None, code_max=code_max)
         current = upcoming
     if result is None:
         raise ValueError("the dataloader yielded no batches")

@@ -140,22 +140,56 @@ class HdrMergeState:
             self.var = torch.empty(shape, dtype=_F32, device=device)
 
 
-def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std: Optional[torch.Tensor], exposure,
+_CODE_DTYPES = {torch.uint8: (1, 255.0), torch.uint16: (2, 65535.0)}
+_STD_MODES = {"multiplier": 2, "constant": 3}
+
+
+def _code_stack(t: torch.Tensor, allow_pinned: bool) -> torch.Tensor:
+    if t.dim() != 4:
+        raise ValueError(f"val_batch must have shape (N, C, H, W), got {tuple(t.shape)}")
+    if not t.is_cuda and not (allow_pinned and t.is_pinned() and t.is_contiguous()):
+        raise RuntimeError("val_batch must live on a CUDA device (or be pinned host memory): clair_torch_b200 has no CPU path")
+    return t.detach().contiguous()
+
+
+def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
                      theta: Optional[torch.Tensor], gaussian_weights: bool, is_final: bool,
-                     radiance_dtype: torch.dtype = _F64, row_base=None, device=None, host_out=None):
+                     radiance_dtype: torch.dtype = _F64, row_base=None, device=None, host_out=None, code_max=None):
     """One batch of compute_hdr_image (inference/hdr_merge.py:95-128).  Returns (radiance, sigma) when
     `is_final`, else None.  `exposure` is the collated float64 'exposure_time' (host tensor, array or list).
 
     `val` / `std` may be pinned host tensors (zero-copy: `device` then names the GPU that runs the kernel), and
-    `host_out=(radiance, sigma)` pinned host buffers make the kernel write its results straight to host memory."""
+    `host_out=(radiance, sigma)` pinned host buffers make the kernel write its results straight to host memory.
+
+    Integer ingest: `val` may hold raw uint8 / uint16 codes; the kernel then applies the reference's
+    CastTo(float32) + Normalize(max_val=code_max, min_val=0) itself (code_max defaults to 255 / 65535), and `std` may be
+    a `datasets.StdSpec` (std = value * m, or a constant) instead of a tensor."""
     lib = _native.load()
-    val = _stack(val, "val_batch", allow_pinned=device is not None)
-    std = None if std is None else _stack(std, "std_batch", allow_pinned=device is not None)
+    if not isinstance(val, torch.Tensor):
+        raise TypeError(f"val_batch must be a torch.Tensor, got {type(val)}")
+    codes = val.dtype in _CODE_DTYPES
+    if codes:
+        val = _code_stack(val, device is not None)
+    else:
+        val = _stack(val, "val_batch", allow_pinned=device is not None)
+    std_mode, std_value = 0, 0.0
+    if std is not None and not torch.is_tensor(std):
+        if not hasattr(std, "mode") or std.mode not in _STD_MODES:
+            raise TypeError(f"std_batch must be a tensor, None or a StdSpec, got {type(std)}")
+        std_mode, std_value, std = _STD_MODES[std.mode], float(np.float32(std.value)), None
+        if not codes:
+            raise ValueError("a StdSpec is evaluated by the integer-ingest kernel: pass uint8 / uint16 value codes with it")
+    elif std is not None:
+        std = _stack(std, "std_batch", allow_pinned=device is not None)
+        std_mode = 1
+    has_std = std_mode != 0
     dev = torch.device(device) if device is not None else val.device
     if val.is_cuda and val.device != dev:
         raise ValueError("val_batch lives on a different device than the one requested")
     if std is not None and std.shape != val.shape:
         raise ValueError("std_batch must have the same shape as val_batch")
+    if code_max is not None and not codes:
+        raise ValueError("code_max only applies to uint8 / uint16 value codes")
     n, c, h, w = val.shape
     if torch.is_tensor(exposure):
         exposure = exposure.detach().cpu().numpy()
@@ -165,10 +199,10 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std: Optional[torc
     th = _table(theta, dev, c)
     lut = 0 if th is None else th.shape[1]
     is_first = state.batches == 0
-    if std is not None and not is_first and state.var is None:
+    if has_std and not is_first and state.var is None:
         raise ValueError("std images appeared after a batch without them")
     if not (is_first and is_final):
-        state._ensure((c, h, w), dev, std is not None)
+        state._ensure((c, h, w), dev, has_std)
     radiance = sigma = None
     if is_final:
         if radiance_dtype not in (_F32, _F64):
@@ -177,24 +211,29 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std: Optional[torc
             radiance, sigma = host_out
             ok = (radiance.is_pinned() and radiance.is_contiguous() and tuple(radiance.shape) == (c, h, w)
                   and radiance.dtype == radiance_dtype)
-            if std is not None:
+            if has_std:
                 ok = ok and sigma is not None and sigma.is_pinned() and sigma.is_contiguous() and sigma.dtype == _F32 \
                     and tuple(sigma.shape) == (c, h, w)
             if not ok:
                 raise ValueError("host_out must be pinned, contiguous (C, H, W) tensors of the output dtypes")
-            if std is None:
+            if not has_std:
                 sigma = None
         else:
             radiance = torch.empty((c, h, w), dtype=radiance_dtype, device=dev)
-            if std is not None:
+            if has_std:
                 sigma = torch.empty((c, h, w), dtype=_F32, device=dev)
     keep, rows = _rows(row_base, c)
+    tail = (t.ctypes.data_as(ctypes.c_void_p), n, _ptr(th), c, lut, h * w, rows, int(bool(gaussian_weights)),
+            _ptr(state.mean), _ptr(state.wsum), _ptr(state.var), int(is_first), int(is_final), _ptr(radiance),
+            int(radiance_dtype == _F64), _ptr(sigma), _stream(dev))
     with torch.cuda.device(dev):
-        rc = lib.clair_hdr_merge_update(
-            _ptr(val), _ptr(std), t.ctypes.data_as(ctypes.c_void_p), n, _ptr(th), c, lut, h * w, rows,
-            int(bool(gaussian_weights)), _ptr(state.mean), _ptr(state.wsum), _ptr(state.var), int(is_first),
-            int(is_final), _ptr(radiance), int(radiance_dtype == _F64), _ptr(sigma), _stream(dev))
-    _native.check(rc, "clair_hdr_merge_update")
+        if codes:
+            code_bytes, default_max = _CODE_DTYPES[val.dtype]
+            rc = lib.clair_hdr_merge_codes(_ptr(val), code_bytes, float(default_max if code_max is None else code_max),
+                                           _ptr(std), std_mode, std_value, *tail)
+        else:
+            rc = lib.clair_hdr_merge_update(_ptr(val), _ptr(std), *tail)
+    _native.check(rc, "clair_hdr_merge_codes" if codes else "clair_hdr_merge_update")
     state.batches += 1
     return (radiance, sigma) if is_final else None
 

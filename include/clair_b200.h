@@ -119,6 +119,29 @@ CLAIR_API int clair_hdr_merge_update(const float *val_dev, const float *std_dev,
                            float *sigma_dev, void *stream);
 
 /*
+ * Integer-ingest form of clair_hdr_merge_update — SURVEY.md §8(f) rank 2: the reference's CastTo(float32) +
+ * Normalize(max_val=code_max, min_val=0) transforms (clair_torch/common/transforms.py:107-190,
+ * clair_torch/common/general_functions.py:359-388) and its synthesis of missing std images
+ * (clair_torch/datasets/base.py:128-133) are fused into the kernel's load, so the raw camera codes cross PCIe / HBM
+ * (1 or 2 bytes per sample instead of 4 + 4).
+ *   codes_dev        (n_frames, C, plane) uint8 (code_bytes = 1) or uint16 (code_bytes = 2); H*W must be a multiple of 4
+ *   code_max         x = fl32(code) / fl32(code_max), an IEEE fp32 division exactly as the CPU transform computes it
+ *   std_mode         0 none | 1 fp32 tensor std_dev | 2 std = x * std_value (MissingStdMode.MULTIPLIER) |
+ *                    3 std = std_value (MissingStdMode.CONSTANT)
+ * All other arguments as clair_hdr_merge_update.
+ */
+#define CLAIR_STD_NONE 0
+#define CLAIR_STD_TENSOR 1
+#define CLAIR_STD_MULTIPLIER 2
+#define CLAIR_STD_CONSTANT 3
+CLAIR_API int clair_hdr_merge_codes(const void *codes_dev, int code_bytes, float code_max, const float *std_dev, int std_mode,
+                          float std_value, const double *exposure_host, int n_frames, const float *theta_dev,
+                          int n_channels, int lut_size, int64_t plane, const int32_t *curve_row_base_host,
+                          int gaussian_weights, double *mean_state_dev, float *wsum_state_dev, float *var_state_dev,
+                          int is_first, int is_final, void *radiance_dev, int radiance_f64, float *sigma_dev,
+                          void *stream);
+
+/*
  * Pairwise exposure-ratio statistics — replaces, for one batch, get_pairwise_valid_pixel_mask
  * (common/general_functions.py:276-312), combined_gaussian_pair_weights (training/losses.py:208-235),
  * pixelwise_linearity_loss (:13-67) and the reductions of compute_spatial_linearity_loss (:70-108) /

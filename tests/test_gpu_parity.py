@@ -311,3 +311,52 @@ def test_hdr_merge_zero_copy_pinned_host(ct):
     with pytest.raises(ValueError):
         ct.compute_hdr_image(loader, DEV, model, max, radiance_dtype=torch.float32,
                              host_out=(torch.empty((3, 90, 160)), torch.empty((3, 90, 160))))
+
+
+@pytest.mark.parametrize("bits", [8, 16])
+def test_hdr_merge_integer_ingest_is_bit_identical(ct, bits):
+    """Raw uint8 / uint16 codes + in-kernel CastTo/Normalize/std synthesis give exactly what the CPU-transformed fp32
+    images give (fl32(code)/fl32(max) with an IEEE division), for every std mode, one batch and two."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.datasets import StdSpec
+    n = 5 if bits == 8 else 9          # 9 frames exercises the N > 8 kernel
+    val, _, t = ct.synthetic.make_stack(n, 3, 48, 64, bits=bits, seed=bits)
+    maxval = float(2 ** bits - 1)
+    codes = torch.round(val * maxval).to(torch.uint8 if bits == 8 else torch.uint16)
+    assert torch.equal(codes.to(torch.float32) / maxval, val)
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    mult = torch.tensor(0.05)
+    cases = [("multiplier", StdSpec("multiplier", 0.05), val * mult), ("constant", StdSpec("constant", 0.01), torch.full_like(val, 0.01)),
+             ("tensor", (val * 0.03 + 0.001), (val * 0.03 + 0.001)), ("none", None, None)]
+    for name, std_codes, std_f32 in cases:
+        for split in (None, 3):
+            def run(v, s, **kw):
+                st = kernels.HdrMergeState()
+                bounds = [(0, n)] if split is None else [(0, split), (split, n)]
+                out = None
+                for a, b in bounds:
+                    sb = s[a:b].contiguous().to(DEV) if torch.is_tensor(s) else s
+                    out = kernels.hdr_merge_update(st, v[a:b].contiguous().to(DEV), sb, t[a:b], theta, True, b == n,
+                                                   radiance_dtype=torch.float32, **kw)
+                return out
+            got = run(codes, std_codes)
+            want = run(val, std_f32)
+            assert torch.equal(got[0], want[0]), (name, split)
+            if want[1] is None:
+                assert got[1] is None
+            else:
+                assert torch.equal(got[1], want[1]), (name, split)
+
+
+def test_hdr_merge_integer_ingest_against_reference_fixture(ct):
+    """The 16-bit reference fixture fed as uint16 codes through the public API (DataLoader + StdSpec)."""
+    from clair_torch_b200.datasets import ExposureStackDataset, StdSpec, custom_collate
+    z = golden("hdr_u16")
+    codes = torch.round(torch.from_numpy(z["val"]) * 65535.0).to(torch.uint16)
+    assert np.array_equal((codes.to(torch.float32) / 65535.0).numpy(), z["val"])
+    ds = ExposureStackDataset(list(codes), StdSpec("multiplier", 0.05), list(z["exposure"]))
+    loader = DataLoader(ds, batch_size=len(codes), collate_fn=custom_collate)
+    rad, sig = ct.compute_hdr_image(loader, DEV, _model(ct, z["theta"]), max)
+    assert rad.dtype == torch.float64
+    assert max_rel(rad.cpu().numpy(), z["radiance"]) < TOL
+    assert max_rel(sig.cpu().numpy(), z["sigma"]) < TOL
