@@ -135,13 +135,18 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const void *base, int64_t o, fl
 
 // The std of one frame's VEC pixels: a tensor, or synthesised the way MultiFileMapDataset does for missing std
 // images (clair_torch/datasets/base.py:128-133): value * multiplier, or a constant.
-template <int VEC>
+// STD: 1 = tensor, 2 = synthesised (compile-time, so the tensor loads of the fp32 path stay unconditional and are
+// hoisted with the value loads)
+template <int VEC, int STD>
 __device__ __forceinline__ Pack<VEC> load_std(const HdrParams &p, int64_t o, const Pack<VEC> &x) {
-    if (p.std_mode == kStdTensor) return load_stream<VEC>(p.std + o);
-    Pack<VEC> r;
+    if constexpr (STD == 1) {
+        return load_stream<VEC>(p.std + o);
+    } else {
+        Pack<VEC> r;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) r.v[k] = (p.std_mode == kStdMultiplier) ? __fmul_rn(x.v[k], p.std_value) : p.std_value;
-    return r;
+        for (int k = 0; k < VEC; ++k) r.v[k] = (p.std_mode == kStdMultiplier) ? __fmul_rn(x.v[k], p.std_value) : p.std_value;
+        return r;
+    }
 }
 
 // Per frame element (all fp32):
@@ -287,8 +292,9 @@ struct RowCursor {
 // is a plain sum of squares of the actual (small) per-frame terms: no cancellation, everything in fp32.
 constexpr int kMaxFixedFrames = 8;
 
-template <int VEC, int NF, bool HAS_STD, bool SINGLE, int SRC>
+template <int VEC, int NF, int STD, bool SINGLE, int SRC>
 __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams p) {
+    constexpr bool HAS_STD = STD != 0;
     extern __shared__ float2 s_tab[];
     const int C = p.n_channels, L = p.lut;
     const bool has_model = p.theta != nullptr;
@@ -317,7 +323,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
         for (int n = 0; n < NF; ++n) {
             const int64_t o = off + static_cast<int64_t>(n) * frame_stride;
             xv[n] = load_pixels<SRC, VEC>(p.val, o, p.code_max, s_x);
-            if constexpr (HAS_STD) sv[n] = load_std<VEC>(p, o, xv[n]);
+            if constexpr (HAS_STD) sv[n] = load_std<VEC, STD>(p, o, xv[n]);
         }
         uint32_t bias[VEC];
         {
@@ -359,8 +365,9 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
 // ---- fallback for N > kMaxFixedFrames: single pass, N dynamic --------------------------------------------
 // sum_n (alpha R_n + gamma Q_n)^2 = alpha^2 SRR + 2 alpha gamma SRQ + gamma^2 SQQ needs only three running
 // sums, but the expansion cancels (|gamma Q| can be ~14x the result), so the three sums are float64.
-template <int VEC, bool HAS_STD, int SRC>
+template <int VEC, int STD, int SRC>
 __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
+    constexpr bool HAS_STD = STD != 0;
     extern __shared__ float2 s_tab[];
     const int C = p.n_channels, L = p.lut;
     const bool has_model = p.theta != nullptr;
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
                 if (n0 + j < N) {
                     const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
                     xv[j] = load_pixels<SRC, VEC>(p.val, o, p.code_max, s_x);
-                    if constexpr (HAS_STD) sv[j] = load_std<VEC>(p, o, xv[j]);
+                    if constexpr (HAS_STD) sv[j] = load_std<VEC, STD>(p, o, xv[j]);
                 }
             }
 #pragma unroll
@@ -589,30 +596,37 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         return 0;
     };
     int rc = 0;
-#define FIXED_NF(V, NF, SRC) (single ? launch(hdr_merge_fixed_kernel<V, NF, true, true, SRC>) : launch(hdr_merge_fixed_kernel<V, NF, true, false, SRC>))
-#define FIXED(V, SRC)                                   \
-    switch (n_frames) {                                 \
-        case 1: rc = FIXED_NF(V, 1, SRC); break;        \
-        case 2: rc = FIXED_NF(V, 2, SRC); break;        \
-        case 3: rc = FIXED_NF(V, 3, SRC); break;        \
-        case 4: rc = FIXED_NF(V, 4, SRC); break;        \
-        case 5: rc = FIXED_NF(V, 5, SRC); break;        \
-        case 6: rc = FIXED_NF(V, 6, SRC); break;        \
-        case 7: rc = FIXED_NF(V, 7, SRC); break;        \
-        default: rc = FIXED_NF(V, 8, SRC); break;       \
+#define FIXED_NF(V, NF, ST, SRC) (single ? launch(hdr_merge_fixed_kernel<V, NF, ST, true, SRC>) : launch(hdr_merge_fixed_kernel<V, NF, ST, false, SRC>))
+#define FIXED(V, ST, SRC)                                   \
+    switch (n_frames) {                                     \
+        case 1: rc = FIXED_NF(V, 1, ST, SRC); break;        \
+        case 2: rc = FIXED_NF(V, 2, ST, SRC); break;        \
+        case 3: rc = FIXED_NF(V, 3, ST, SRC); break;        \
+        case 4: rc = FIXED_NF(V, 4, ST, SRC); break;        \
+        case 5: rc = FIXED_NF(V, 5, ST, SRC); break;        \
+        case 6: rc = FIXED_NF(V, 6, ST, SRC); break;        \
+        case 7: rc = FIXED_NF(V, 7, ST, SRC); break;        \
+        default: rc = FIXED_NF(V, 8, ST, SRC); break;       \
     }
-#define DYN(V, SRC) rc = has_std ? launch(hdr_merge_kernel<V, true, SRC>) : launch(hdr_merge_kernel<V, false, SRC>)
-    if (src == kSrcU8) {
-        if (fixed) { FIXED(4, kSrcU8) } else { DYN(4, kSrcU8); }
-    } else if (src == kSrcU16) {
-        if (fixed) { FIXED(4, kSrcU16) } else { DYN(4, kSrcU16); }
+#define DYN(V, ST, SRC) rc = launch(hdr_merge_kernel<V, ST, SRC>)
+#define BY_STD(V, SRC)                                                          \
+    if (std_mode == kStdNone) { DYN(V, 0, SRC); }                               \
+    else if (std_mode == kStdTensor) { if (fixed) { FIXED(V, 1, SRC) } else { DYN(V, 1, SRC); } } \
+    else { if (fixed) { FIXED(V, 2, SRC) } else { DYN(V, 2, SRC); } }
+    if (src == kSrcU8) { BY_STD(4, kSrcU8) }
+    else if (src == kSrcU16) { BY_STD(4, kSrcU16) }
+    else if (std_mode == kStdNone) {
+        if (vec == 4) DYN(4, 0, kSrcF32); else if (vec == 2) DYN(2, 0, kSrcF32); else DYN(1, 0, kSrcF32);
+    } else if (std_mode != kStdTensor) {
+        return bad(CLAIR_E_MODE, "synthesised std needs integer codes");
     } else if (vec == 4) {
-        if (fixed) { FIXED(4, kSrcF32) } else { DYN(4, kSrcF32); }
+        if (fixed) { FIXED(4, 1, kSrcF32) } else { DYN(4, 1, kSrcF32); }
     } else if (vec == 2) {
-        if (fixed) { FIXED(2, kSrcF32) } else { DYN(2, kSrcF32); }
+        if (fixed) { FIXED(2, 1, kSrcF32) } else { DYN(2, 1, kSrcF32); }
     } else {
-        if (fixed) { FIXED(1, kSrcF32) } else { DYN(1, kSrcF32); }
+        if (fixed) { FIXED(1, 1, kSrcF32) } else { DYN(1, 1, kSrcF32); }
     }
+#undef BY_STD
 #undef DYN
 #undef FIXED
 #undef FIXED_NF
