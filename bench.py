@@ -37,6 +37,16 @@ WORKLOAD = ("c1: HDR merge, 5x 8-bit RGB 1920x1080 synthetic exposure stack as f
             "(distinct rows), gaussian weights, first-order uncertainty, fp32 radiance+sigma")
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the headline kernel from the committed ncu --set full capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r1_hdr_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        d = json.load(fh)
+    return d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"]
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -420,7 +430,7 @@ def main():
                        "l2": "4 distinct stacks (995 MB) rotated per step, each far larger than the 126 MB L2",
                        "sharding": "by stack, one rank per GPU, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                          "kernel": "clair::hdr_merge_fixed_kernel<2,5,true,true> (2 px/thread, N=5 in registers, single batch)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
