@@ -8,10 +8,11 @@ CUDA kernels behind the C ABI of `include/clair_b200.h`.  There is no CPU or eag
 """
 from . import _native, common, datasets, distributed, kernels, synthetic  # noqa: F401
 from .common.enums import InterpMode
-from .inference import compute_hdr_image, linearize_dataset_generator, measure_linearity
-from .models import ICRFModelBase, ICRFModelDirect
+from .inference import (compute_hdr_image, compute_video_mean_and_std, linearize_dataset_generator,
+                        measure_linearity)
+from .models import ICRFModelBase, ICRFModelDirect, ICRFModelPCA
 from .training import train_icrf, train_icrf_step
 
 __version__ = "0.1.0"
-__all__ = ["InterpMode", "ICRFModelBase", "ICRFModelDirect", "compute_hdr_image", "linearize_dataset_generator",
-           "measure_linearity", "train_icrf", "train_icrf_step"]
+__all__ = ["InterpMode", "ICRFModelBase", "ICRFModelDirect", "ICRFModelPCA", "compute_hdr_image", "linearize_dataset_generator",
+           "measure_linearity", "compute_video_mean_and_std", "train_icrf", "train_icrf_step"]

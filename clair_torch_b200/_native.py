@@ -22,6 +22,7 @@ MAX_LUT = 1024
 MAX_PAIRS = 2016
 INTERP_LOOKUP = 1
 INTERP_LINEAR = 2
+INTERP_CATMULL = 3
 
 # every symbol include/clair_b200.h declares, with its ctypes prototype
 _c = ctypes
@@ -34,7 +35,7 @@ _PROTOTYPES = {
     "clair_icrf_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                       _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "clair_icrf_backward_theta": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
-                                             _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+                                             _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "clair_linearize": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                    _c.c_int, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "clair_hdr_merge_update": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int,
@@ -45,6 +46,9 @@ _PROTOTYPES = {
                                          _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_int,
                                          _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int,
                                          _c.c_void_p, _c.c_void_p]),
+    "clair_frame_stats_update": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int,
+                                            _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
+                                            _c.c_void_p]),
     "clair_pair_stats": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p,
                                     _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
                                     _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),

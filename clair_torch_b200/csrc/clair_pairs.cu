@@ -531,6 +531,29 @@ __global__ void __launch_bounds__(256) icrf_backward_theta_kernel(const float *_
     scatter_taps(copy, C, L, u, xs, g);
 }
 
+// CATMULL table gradient: four taps per element, plain fp32 reductions into the A half of the replicated tables
+__global__ void __launch_bounds__(256) icrf_catmull_backward_kernel(const float *__restrict__ x, const float *__restrict__ gy,
+                                                                    float *hist, int64_t plane, int C, int L, CurveRows rows) {
+    const int64_t pix = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= plane) return;
+    const int slab = blockIdx.y, c = slab % C;
+    const int64_t o = static_cast<int64_t>(slab) * plane + pix;
+    const float g = __ldcs(gy + o);
+    if (g == 0.0f) return;
+    const float lm1 = static_cast<float>(L - 1);
+    const float xs = fminf(fmaxf(__fmul_rn(__ldcs(x + o), lm1), 0.0f), lm1);
+    int x0;
+    const float fl = floor_small(xs, x0);
+    const float t = fminf(fmaxf(xs - fl, 0.0f), 1.0f);
+    const float t2 = t * t, t3 = t2 * t;
+    const float w[4] = {-0.5f * t3 + t2 - 0.5f * t, 1.5f * t3 - 2.5f * t2 + 1.0f, -1.5f * t3 + 2.0f * t2 + 0.5f * t,
+                        0.5f * t3 - 0.5f * t2};
+    const int u = static_cast<int>((pix + rows.base(c)) % C);
+    float *copy = hist + static_cast<int64_t>((blockIdx.x + blockIdx.y) % kGradCopies) * (2 * C * (L + 2)) + u * (L + 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) atomicAdd(copy + min(max(x0 + k - 1, 0), L - 1), g * w[k]);
+}
+
 // grad[u][k] += sum over copies of A[u][k] + B[u][k+1], in float64; one warp per table entry
 __global__ void __launch_bounds__(256) grad_finalize_kernel(const float *__restrict__ hist, double *grad, int C, int L) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -866,10 +889,12 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
 }
 
 extern "C" int clair_icrf_backward_theta(const float *x_dev, const float *grad_y_dev, double *grad_theta_dev,
-                                         int n_frames, int n_channels, int64_t plane, int lut_size,
+                                         int n_frames, int n_channels, int64_t plane, int lut_size, int interp_mode,
                                          const int32_t *curve_row_base_host, void *workspace_dev, size_t workspace_bytes,
                                          void *stream) {
     if (!x_dev || !grad_y_dev || !grad_theta_dev || !workspace_dev) return fail(CLAIR_E_ARG, "clair_icrf_backward_theta: null buffer");
+    if (interp_mode != CLAIR_INTERP_LINEAR && interp_mode != CLAIR_INTERP_CATMULL)
+        return fail(CLAIR_E_MODE, "clair_icrf_backward_theta: interp_mode must be CLAIR_INTERP_LINEAR or CLAIR_INTERP_CATMULL");
     if (int rc = check_geometry("clair_icrf_backward_theta", n_frames, n_channels, plane, lut_size, false)) return rc;
     const size_t need = clair_grad_workspace_bytes(n_channels, lut_size);
     if (workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace_dev) % 16 != 0)
@@ -881,8 +906,12 @@ extern "C" int clair_icrf_backward_theta(const float *x_dev, const float *grad_y
     CurveRows rows;
     fill_rows(rows, curve_row_base_host, n_channels, plane);
     dim3 grid(static_cast<unsigned>((plane + 255) / 256), static_cast<unsigned>(slabs));
-    icrf_backward_theta_kernel<<<grid, 256, 0, s>>>(x_dev, grad_y_dev, static_cast<float *>(workspace_dev), plane, n_channels,
-                                                    lut_size, rows);
+    if (interp_mode == CLAIR_INTERP_CATMULL)
+        icrf_catmull_backward_kernel<<<grid, 256, 0, s>>>(x_dev, grad_y_dev, static_cast<float *>(workspace_dev), plane,
+                                                          n_channels, lut_size, rows);
+    else
+        icrf_backward_theta_kernel<<<grid, 256, 0, s>>>(x_dev, grad_y_dev, static_cast<float *>(workspace_dev), plane, n_channels,
+                                                        lut_size, rows);
     if (int rc = launched("icrf_backward_theta_kernel")) return rc;
     return finalize_grad(static_cast<const float *>(workspace_dev), grad_theta_dev, n_channels, lut_size, s);
 }

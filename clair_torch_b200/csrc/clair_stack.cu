@@ -76,6 +76,60 @@ __global__ void __launch_bounds__(kBlock) icrf_forward_kernel(const ForwardParam
     if constexpr (MODE == 2) store_stream<VEC>(p.sigma + off, gv);
 }
 
+// CATMULL mode (models/base.py:184-226): four taps x0-1 .. x0+2 (clamped), Catmull-Rom weights of t = xs - x0 in the
+// reference's left-to-right fp32 op order (so the value is bit-exact), rows per the same k-mod-C rule as LINEAR.
+// The derivative is the closed form sum_i w_i'(t) g_i (L-1) (the reference's autograd result differs from it by its own
+// fp32 rounding, ~3e-5 of the maximum).
+struct CatmullTaps {
+    int idx[4];
+    float w[4];
+    float dw[4];
+};
+
+__device__ __forceinline__ CatmullTaps catmull_taps(float x, int L) {
+    CatmullTaps c;
+    const float lm1 = static_cast<float>(L - 1);
+    const float xs_raw = __fmul_rn(x, lm1);
+    const float xs = fminf(fmaxf(xs_raw, 0.0f), lm1);
+    int x0;
+    const float fl = floor_small(xs, x0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c.idx[k] = min(max(x0 + k - 1, 0), L - 1);
+    const float t = fminf(fmaxf(__fsub_rn(xs, fl), 0.0f), 1.0f);
+    const float t2 = __fmul_rn(t, t), t3 = __fmul_rn(t2, t);
+    c.w[0] = __fsub_rn(__fadd_rn(__fmul_rn(-0.5f, t3), t2), __fmul_rn(0.5f, t));
+    c.w[1] = __fadd_rn(__fsub_rn(__fmul_rn(1.5f, t3), __fmul_rn(2.5f, t2)), 1.0f);
+    c.w[2] = __fadd_rn(__fadd_rn(__fmul_rn(-1.5f, t3), __fmul_rn(2.0f, t2)), __fmul_rn(0.5f, t));
+    c.w[3] = __fsub_rn(__fmul_rn(0.5f, t3), __fmul_rn(0.5f, t2));
+    const float inside = (xs == xs_raw) ? lm1 : 0.0f;
+    c.dw[0] = inside * (-1.5f * t2 + 2.0f * t - 0.5f);
+    c.dw[1] = inside * (4.5f * t2 - 5.0f * t);
+    c.dw[2] = inside * (-4.5f * t2 + 4.0f * t + 0.5f);
+    c.dw[3] = inside * (1.5f * t2 - t);
+    return c;
+}
+
+// grid: (ceil(plane / kBlock), n_frames * C); one element per thread (CATMULL is off the hot path)
+__global__ void __launch_bounds__(kBlock) icrf_catmull_kernel(const ForwardParams p) {
+    extern __shared__ float2 s_tab[];
+    const int C = p.n_channels, L = p.lut;
+    stage_curve_pairs(s_tab, p.theta, C, L);
+    __syncthreads();
+    const int64_t pix = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
+    if (pix >= p.plane) return;
+    const int slab = blockIdx.y, c = slab % C;
+    const int64_t off = static_cast<int64_t>(slab) * p.plane + pix;
+    const int u = static_cast<int>((pix + p.rows.base(c)) % C);
+    const CatmullTaps t = catmull_taps(__ldcs(p.x + off), L);
+    const float2 *row = s_tab + u * L;
+    const float g0 = row[t.idx[0]].x, g1 = row[t.idx[1]].x, g2 = row[t.idx[2]].x, g3 = row[t.idx[3]].x;
+    // stack([w_i g_i]).sum(dim=0): ((w0 g0 + w1 g1) + w2 g2) + w3 g3
+    const float y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t.w[0], g0), __fmul_rn(t.w[1], g1)), __fmul_rn(t.w[2], g2)),
+                              __fmul_rn(t.w[3], g3));
+    __stcs(p.y + off, y);
+    if (p.dydx != nullptr) __stcs(p.dydx + off, t.dw[0] * g0 + t.dw[1] * g1 + t.dw[2] * g2 + t.dw[3] * g3);
+}
+
 // =====================================================================================================
 // HDR merge + uncertainty
 // =====================================================================================================
@@ -478,8 +532,8 @@ extern "C" int clair_icrf_forward(const float *x_dev, const float *theta_dev, fl
                                   const int32_t *curve_row_base_host, void *stream) {
     if (!x_dev || !theta_dev || !y_dev) return fail(CLAIR_E_ARG, "clair_icrf_forward: null buffer");
     if (int rc = check_geometry("clair_icrf_forward", n_frames, n_channels, plane, lut_size, /*limit_frames=*/false)) return rc;
-    if (interp_mode != CLAIR_INTERP_LINEAR && interp_mode != CLAIR_INTERP_LOOKUP)
-        return fail(CLAIR_E_MODE, "clair_icrf_forward: interp_mode must be CLAIR_INTERP_LINEAR or CLAIR_INTERP_LOOKUP");
+    if (interp_mode != CLAIR_INTERP_LINEAR && interp_mode != CLAIR_INTERP_LOOKUP && interp_mode != CLAIR_INTERP_CATMULL)
+        return fail(CLAIR_E_MODE, "clair_icrf_forward: interp_mode must be CLAIR_INTERP_LOOKUP, _LINEAR or _CATMULL");
     if (interp_mode == CLAIR_INTERP_LOOKUP && dydx_dev) return fail(CLAIR_E_MODE, "clair_icrf_forward: LOOKUP has no derivative");
     ForwardParams p{};
     p.x = x_dev; p.theta = theta_dev; p.y = y_dev; p.dydx = dydx_dev;
@@ -490,6 +544,12 @@ extern "C" int clair_icrf_forward(const float *x_dev, const float *theta_dev, fl
     const int64_t slabs = static_cast<int64_t>(n_frames) * n_channels;
     if (slabs > 65535) return fail(CLAIR_E_LIMIT, "clair_icrf_forward: n_frames*n_channels exceeds 65535");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (interp_mode == CLAIR_INTERP_CATMULL) {
+        if (int rc = ensure_smem(icrf_catmull_kernel, smem)) return rc;
+        dim3 grid(static_cast<unsigned>((plane + kBlock - 1) / kBlock), static_cast<unsigned>(slabs));
+        icrf_catmull_kernel<<<grid, kBlock, smem, s>>>(p);
+        return launched("icrf_catmull_kernel");
+    }
 #define LAUNCH_FWD(V, M)                                                                          \
     do {                                                                                          \
         if (int rc = ensure_smem(icrf_forward_kernel<V, M>, smem)) return rc;                     \
@@ -660,4 +720,149 @@ extern "C" int clair_hdr_merge_codes(const void *codes_dev, int code_bytes, floa
                           std_value, exposure_host, n_frames, theta_dev, n_channels, lut_size, plane, curve_row_base_host,
                           gaussian_weights, mean_state_dev, wsum_state_dev, var_state_dev, is_first, is_final, radiance_dev,
                           radiance_f64, sigma_dev, stream);
+}
+
+// =====================================================================================================
+// Streaming weighted mean / variance over frames — WBOMeanVar.update_values + _update_internal_values
+// (clair_torch/common/statistics.py:209-259), as used by compute_video_mean_and_std
+// (clair_torch/inference/inferential_statistics.py:19-49).  SURVEY.md §8(f) rank 3.
+//   batch:  W_B = sum w,  W2_B = sum w^2,  mean_B = sum w v / (W_B + 1e-6)   [weights]   |   mean(v), W_B = W2_B = N   [none]
+//           M_B = sum w (v - mean_B)^2
+//   merge:  W = W_A + W_B,  M = M_A + M_B + (W_A W_B / W)(mean_B - mean_A)^2,  mean = mean_A + (W_B/W)(mean_B - mean_A)
+// One pass over the N frames: the second moment is accumulated around a pivot (the first frame's value), so
+// sum w (v - mean_B)^2 = S2 - 2 (mean_B - k) S1 + (mean_B - k)^2 W_B never cancels in fp32.
+// =====================================================================================================
+namespace clair {
+
+struct FrameStatsParams {
+    const float *val;
+    const float *weights;     // nullptr = unweighted
+    const float *theta;       // nullptr = no linearisation
+    float *mean, *m2, *wsum, *wsq;
+    int64_t plane;
+    int n_frames, n_channels, lut, is_first;
+    CurveRows rows;
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kBlock) frame_stats_kernel(const FrameStatsParams p) {
+    extern __shared__ float2 s_tab[];
+    const int C = p.n_channels, L = p.lut;
+    const bool has_model = p.theta != nullptr;
+    if (has_model) {
+        stage_curve_pairs(s_tab, p.theta, C, L);
+        __syncthreads();
+    }
+    const int c = blockIdx.y;
+    const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
+    const float lm1 = static_cast<float>(L - 1);
+    const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
+    const uint32_t item_stride = gridDim.x * kBlock;
+    const uint32_t first_item = blockIdx.x * kBlock + threadIdx.x;
+    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
+    const uint32_t tab_bias = curve_row_bias(s_tab);
+    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
+    const bool weighted = p.weights != nullptr;
+    const int N = p.n_frames;
+
+    for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
+        const uint32_t pix = item * VEC;
+        const int64_t off = static_cast<int64_t>(c) * p.plane + pix;
+        uint32_t bias[VEC];
+        {
+            uint32_t u = cur.u0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { bias[k] = tab_bias + u * row_bytes; u = (u + 1 == cur.C) ? 0u : u + 1; }
+        }
+        float w0[VEC], w2[VEC], s1[VEC], s2[VEC], pivot[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { w0[k] = 0.0f; w2[k] = 0.0f; s1[k] = 0.0f; s2[k] = 0.0f; pivot[k] = 0.0f; }
+        for (int n0 = 0; n0 < N; n0 += kFrameChunk) {
+            Pack<VEC> xv[kFrameChunk], wv[kFrameChunk];
+#pragma unroll
+            for (int j = 0; j < kFrameChunk; ++j) {
+                if (n0 + j < N) {
+                    const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
+                    xv[j] = load_stream<VEC>(p.val + o);
+                    if (weighted) wv[j] = load_stream<VEC>(p.weights + o);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kFrameChunk; ++j) {
+                if (n0 + j < N) {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) {
+                        float v = xv[j].v[k];
+                        if (has_model) { float fp; icrf_linear_biased(v, bias[k], lm1, v, fp); }
+                        const float w = weighted ? wv[j].v[k] : 1.0f;
+                        if (n0 + j == 0) pivot[k] = v;
+                        const float d = v - pivot[k];
+                        w0[k] += w;
+                        w2[k] = fmaf(w, w, w2[k]);
+                        s1[k] = fmaf(w, d, s1[k]);
+                        s2[k] = fmaf(w * d, d, s2[k]);
+                    }
+                }
+            }
+        }
+        Pack<VEC> o_mean, o_m2, o_w, o_wsq, a_mean, a_m2, a_w, a_wsq;
+        if (!p.is_first) {
+            a_mean = load_stream<VEC>(p.mean + off); a_m2 = load_stream<VEC>(p.m2 + off);
+            a_w = load_stream<VEC>(p.wsum + off); a_wsq = load_stream<VEC>(p.wsq + off);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float wb = weighted ? w0[k] : static_cast<float>(N);
+            // weighted: sum w v / (W_B + 1e-6) (statistics.py:223-224); unweighted: plain mean (:227)
+            const float db = weighted ? s1[k] / (w0[k] + 1e-6f) - pivot[k] * (1e-6f / (w0[k] + 1e-6f)) : s1[k] / wb;   // mean_B - pivot
+            const float mean_b = pivot[k] + db;
+            const float m2_b = fmaxf(s2[k] - 2.0f * db * s1[k] + db * db * w0[k], 0.0f);
+            const float wsq_b = weighted ? w2[k] : wb;
+            if (p.is_first) {
+                // W_A = 0, mean_A = 0, M_A = 0 (python floats in the reference)
+                o_w.v[k] = wb; o_mean.v[k] = (wb / wb) * mean_b; o_m2.v[k] = m2_b; o_wsq.v[k] = wsq_b;
+            } else {
+                const float wt = a_w.v[k] + wb;
+                const float dm = mean_b - a_mean.v[k];
+                o_m2.v[k] = a_m2.v[k] + m2_b + (a_w.v[k] * wb / wt) * dm * dm;
+                o_mean.v[k] = a_mean.v[k] + (wb / wt) * dm;
+                o_w.v[k] = wt;
+                o_wsq.v[k] = a_wsq.v[k] + wsq_b;
+            }
+        }
+        store_stream<VEC>(p.mean + off, o_mean); store_stream<VEC>(p.m2 + off, o_m2);
+        store_stream<VEC>(p.wsum + off, o_w); store_stream<VEC>(p.wsq + off, o_wsq);
+    }
+}
+
+}  // namespace clair
+
+extern "C" int clair_frame_stats_update(const float *val_dev, const float *weights_dev, const float *theta_dev, int n_frames,
+                                        int n_channels, int64_t plane, int lut_size, const int32_t *curve_row_base_host,
+                                        float *mean_state_dev, float *m2_state_dev, float *wsum_state_dev,
+                                        float *wsq_state_dev, int is_first, void *stream) {
+    if (!val_dev || !mean_state_dev || !m2_state_dev || !wsum_state_dev || !wsq_state_dev)
+        return fail(CLAIR_E_ARG, "clair_frame_stats_update: null buffer");
+    if (theta_dev == nullptr && lut_size <= 0) lut_size = 2;
+    if (int rc = check_geometry("clair_frame_stats_update", n_frames, n_channels, plane, lut_size, false)) return rc;
+    FrameStatsParams p{};
+    p.val = val_dev; p.weights = weights_dev; p.theta = theta_dev;
+    p.mean = mean_state_dev; p.m2 = m2_state_dev; p.wsum = wsum_state_dev; p.wsq = wsq_state_dev;
+    p.plane = plane; p.n_frames = n_frames; p.n_channels = n_channels; p.lut = lut_size; p.is_first = is_first;
+    fill_rows(p.rows, curve_row_base_host, n_channels, plane);
+    const int vec = pick_vec(plane, {val_dev, weights_dev, mean_state_dev, m2_state_dev, wsum_state_dev, wsq_state_dev});
+    const size_t smem = theta_dev ? sizeof(float2) * n_channels * lut_size : 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    auto launch = [&](auto kernel) -> int {
+        if (int rc = ensure_smem(kernel, smem)) return rc;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
+        const int64_t want = (plane / vec + kBlock - 1) / kBlock;
+        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want, (static_cast<int64_t>(device_sm_count()) * std::max(per_sm, 1) * 2 + n_channels - 1) / n_channels));
+        kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p);
+        return 0;
+    };
+    int rc = vec == 4 ? launch(frame_stats_kernel<4>) : vec == 2 ? launch(frame_stats_kernel<2>) : launch(frame_stats_kernel<1>);
+    if (rc) return rc;
+    return launched("frame_stats_kernel");
 }

@@ -89,7 +89,8 @@ def _workspace(device, channels: int, lut: int) -> torch.Tensor:
     return torch.empty(nbytes // 4, dtype=_F32, device=device)
 
 
-def icrf_backward_theta(x: torch.Tensor, grad_y: torch.Tensor, channels: int, lut: int, row_base=None) -> torch.Tensor:
+def icrf_backward_theta(x: torch.Tensor, grad_y: torch.Tensor, channels: int, lut: int, row_base=None,
+                        interp_mode: int = _native.INTERP_LINEAR) -> torch.Tensor:
     """(C, L) float64 gradient of sum(grad_y * f(x)) with respect to the table.  models/base.py:173-182 backward."""
     lib = _native.load()
     x = _stack(x, "image")
@@ -99,7 +100,7 @@ def icrf_backward_theta(x: torch.Tensor, grad_y: torch.Tensor, channels: int, lu
     ws = _workspace(x.device, channels, lut)
     keep, rows = _rows(row_base, c)
     with torch.cuda.device(x.device):
-        rc = lib.clair_icrf_backward_theta(_ptr(x), _ptr(gy), _ptr(grad), n, c, h * w, lut, rows, _ptr(ws),
+        rc = lib.clair_icrf_backward_theta(_ptr(x), _ptr(gy), _ptr(grad), n, c, h * w, lut, interp_mode, rows, _ptr(ws),
                                            ws.numel() * 4, _stream(x.device))
     _native.check(rc, "clair_icrf_backward_theta")
     return grad

@@ -1,4 +1,4 @@
 from .base import ICRFModelBase
-from .icrf_model import ICRFModelDirect
+from .icrf_model import ICRFModelDirect, ICRFModelPCA
 
-__all__ = ["ICRFModelBase", "ICRFModelDirect"]
+__all__ = ["ICRFModelBase", "ICRFModelDirect", "ICRFModelPCA"]

@@ -10,16 +10,17 @@ from .. import _native, kernels
 from ..common.enums import InterpMode
 
 
-class _LinearTableFn(torch.autograd.Function):
-    """f = table interpolation (models/base.py:160-182) with both of its autograd edges:
-    d/d image = f'(x) (elementwise) and d/d table = two-tap scatter (the index_put of :176)."""
+class _TableFn(torch.autograd.Function):
+    """f = table interpolation (LINEAR models/base.py:160-182, CATMULL :184-226) with both of its autograd edges:
+    d/d image = f'(x) (elementwise) and d/d table = tap scatter (the index_put of :176 / :219)."""
 
     @staticmethod
-    def forward(ctx, image, table):
-        y, dydx = kernels.icrf_forward(image, table, _native.INTERP_LINEAR, want_derivative=True)
+    def forward(ctx, image, table, interp_mode):
+        y, dydx = kernels.icrf_forward(image, table, interp_mode, want_derivative=True)
         ctx.save_for_backward(image.detach(), dydx)
         ctx.table_shape = tuple(table.shape)
         ctx.table_dtype = table.dtype
+        ctx.interp_mode = interp_mode
         return y
 
     @staticmethod
@@ -30,8 +31,9 @@ class _LinearTableFn(torch.autograd.Function):
             g_image = grad_out * dydx
         if ctx.needs_input_grad[1]:
             c, lut = ctx.table_shape
-            g_table = kernels.icrf_backward_theta(image, grad_out.to(torch.float32), c, lut).to(ctx.table_dtype)
-        return g_image, g_table
+            g_table = kernels.icrf_backward_theta(image, grad_out.to(torch.float32), c, lut,
+                                                  interp_mode=ctx.interp_mode).to(ctx.table_dtype)
+        return g_image, g_table, None
 
 
 class ICRFModelBase(nn.Module, ABC):
@@ -79,11 +81,11 @@ class ICRFModelBase(nn.Module, ABC):
     def forward(self, image: torch.Tensor) -> torch.Tensor:
         """(N, C, H, W) fp32 image stack on a CUDA device -> linearised stack of the same shape."""
         if self.interpolation_mode is InterpMode.LINEAR:
-            return _LinearTableFn.apply(image, self._icrf)
+            return _TableFn.apply(image, self._icrf, _native.INTERP_LINEAR)
         if self.interpolation_mode is InterpMode.LOOKUP:
             return kernels.icrf_forward(image, self._icrf, _native.INTERP_LOOKUP)
-        raise NotImplementedError("InterpMode.CATMULL is not part of the B200 hot path yet (SURVEY.md §8(f) rank 4); "
-                                  "note the reference's own CATMULL forward fails on CUDA (models/base.py:218)")
+        # the reference's own CATMULL forward only runs on the CPU (models/base.py:218 builds arange without a device)
+        return _TableFn.apply(image, self._icrf, _native.INTERP_CATMULL)
 
     def plot_icrf(self) -> None:
         """Live plotting lives in the reference's visualization package and is out of scope here (no-op)."""

@@ -50,6 +50,7 @@ extern "C" {
 /* interpolation modes, values of clair_torch.common.enums.InterpMode (common/enums.py:10-17) */
 #define CLAIR_INTERP_LOOKUP 1
 #define CLAIR_INTERP_LINEAR 2
+#define CLAIR_INTERP_CATMULL 3
 
 CLAIR_API int clair_abi_version(void);
 CLAIR_API const char *clair_last_error(void);
@@ -61,10 +62,11 @@ CLAIR_API uint64_t clair_launch_count(void);
 CLAIR_API int clair_set_tuning(const char *key, int value);
 
 /*
- * ICRF evaluation — replaces ICRFModelBase.forward (models/base.py:135-182): LINEAR (:160-182, rows per
- * Q1) or LOOKUP (:138-158, round-half-even, true channel).  x_dev is (n_frames, C, plane).
+ * ICRF evaluation — replaces ICRFModelBase.forward (models/base.py:135-226): LINEAR (:160-182, rows per
+ * Q1), LOOKUP (:138-158, round-half-even, true channel) or CATMULL (:184-226, four taps, rows per Q1).
+ * x_dev is (n_frames, C, plane).
  *   y_dev      f(x)                                        (required)
- *   dydx_dev   autograd's d f / d x, LINEAR only           (optional, may be NULL)
+ *   dydx_dev   autograd's d f / d x, LINEAR / CATMULL      (optional, may be NULL)
  */
 CLAIR_API int clair_icrf_forward(const float *x_dev, const float *theta_dev, float *y_dev, float *dydx_dev,
                        int n_frames, int n_channels, int64_t plane, int lut_size, int interp_mode,
@@ -72,11 +74,11 @@ CLAIR_API int clair_icrf_forward(const float *x_dev, const float *theta_dev, flo
 
 /*
  * Back-propagation of clair_icrf_forward to the table: grad_theta[u, x0] += g*(1-w), grad_theta[u, x1] += g*w
- * (the index_put of models/base.py:176 under autograd).  grad_theta_dev is (C, L) float64 and is ACCUMULATED
- * into (zero it first).  LINEAR only.
+ * (the index_put of models/base.py:176 under autograd; four taps at :219 for CATMULL).  grad_theta_dev is (C, L)
+ * float64 and is ACCUMULATED into (zero it first).  interp_mode: CLAIR_INTERP_LINEAR or CLAIR_INTERP_CATMULL.
  */
 CLAIR_API int clair_icrf_backward_theta(const float *x_dev, const float *grad_y_dev, double *grad_theta_dev,
-                              int n_frames, int n_channels, int64_t plane, int lut_size,
+                              int n_frames, int n_channels, int64_t plane, int lut_size, int interp_mode,
                               const int32_t *curve_row_base_host, void *workspace_dev, size_t workspace_bytes,
                               void *stream);
 
@@ -140,6 +142,21 @@ CLAIR_API int clair_hdr_merge_codes(const void *codes_dev, int code_bytes, float
                           int gaussian_weights, double *mean_state_dev, float *wsum_state_dev, float *var_state_dev,
                           int is_first, int is_final, void *radiance_dev, int radiance_f64, float *sigma_dev,
                           void *stream);
+
+/*
+ * Streaming weighted mean / second moment over frames — replaces WBOMeanVar.update_values + _update_internal_values
+ * (clair_torch/common/statistics.py:209-259) as used by compute_video_mean_and_std
+ * (clair_torch/inference/inferential_statistics.py:19-49); SURVEY.md §8(f) rank 3.
+ *   val_dev       (n_frames, C, plane) fp32 batch of frames (any n_frames)
+ *   weights_dev   same shape, or NULL (then W_B = n_frames, as statistics.py:226-229)
+ *   theta_dev     (C, L) table to linearise the frames first (LINEAR), or NULL
+ *   mean / m2 / wsum / wsq state   (C, plane) fp32 each: running mean, M2, sum of weights, sum of squared weights;
+ *                 overwritten when is_first, merged (Chan / West) otherwise
+ */
+CLAIR_API int clair_frame_stats_update(const float *val_dev, const float *weights_dev, const float *theta_dev, int n_frames,
+                             int n_channels, int64_t plane, int lut_size, const int32_t *curve_row_base_host,
+                             float *mean_state_dev, float *m2_state_dev, float *wsum_state_dev, float *wsq_state_dev,
+                             int is_first, void *stream);
 
 /*
  * Pairwise exposure-ratio statistics — replaces, for one batch, get_pairwise_valid_pixel_mask

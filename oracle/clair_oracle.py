@@ -71,6 +71,38 @@ def icrf_linear(x, theta, flat_offset=0, rows=None):
     return f.astype(F32), fprime, x0, rows
 
 
+def icrf_catmull(x, theta, flat_offset=0, rows=None):
+    """CATMULL-mode ICRF, models/base.py:184-226 (four-tap Catmull-Rom, rows per the same k-mod-C rule as LINEAR).
+
+    Returns (f float32 — same op order as the reference, fprime float64 closed form, taps (4 index arrays), weights
+    (4 float32 arrays), rows).
+    """
+    x = np.ascontiguousarray(x, dtype=F32)
+    theta = np.asarray(theta, dtype=F32)
+    l = theta.shape[1]
+    lm1 = F32(l - 1)
+    xs_raw = x * lm1
+    xs = np.minimum(np.maximum(xs_raw, F32(0)), lm1)                       # :190
+    x0 = np.floor(xs).astype(np.int64)                                     # :193
+    taps = [np.clip(x0 + d, 0, l - 1) for d in (-1, 0, 1, 2)]              # :194-199
+    t = np.minimum(np.maximum(xs - x0.astype(F32), F32(0)), F32(1))        # :202
+    t2 = t * t
+    t3 = t2 * t
+    w = [F32(-0.5) * t3 + t2 - F32(0.5) * t,                               # :208-211, left-to-right fp32
+         F32(1.5) * t3 - F32(2.5) * t2 + F32(1.0),
+         F32(-1.5) * t3 + F32(2.0) * t2 + F32(0.5) * t,
+         F32(0.5) * t3 - F32(0.5) * t2]
+    if rows is None:
+        rows = curve_rows(x.shape, flat_offset)
+    g = [theta[rows, ix] for ix in taps]
+    f = ((w[0] * g[0] + w[1] * g[1]) + w[2] * g[2]) + w[3] * g[3]          # stack(...).sum(dim=0), :224
+    td = t.astype(F64)
+    dw = [-1.5 * td * td + 2 * td - 0.5, 4.5 * td * td - 5 * td, -4.5 * td * td + 4 * td + 0.5, 1.5 * td * td - td]
+    inside = (xs_raw >= F32(0)) & (xs_raw <= lm1)
+    fprime = np.where(inside, sum(d * gi.astype(F64) for d, gi in zip(dw, g)) * float(l - 1), 0.0)
+    return f.astype(F32), fprime, taps, w, rows
+
+
 def icrf_lookup(x, theta):
     """LOOKUP-mode ICRF, models/base.py:138-158: round-half-even index, true channel row."""
     x = np.ascontiguousarray(x, dtype=F32)
@@ -392,3 +424,36 @@ class Adam:
         bc2 = 1 - self.b2 ** self.t
         denom = (np.sqrt(self.v) / F32(np.sqrt(bc2)) + F32(self.eps)).astype(F32)
         return (np.asarray(param, dtype=F32) - F32(self.lr / bc1) * (self.m / denom)).astype(F32)
+
+
+# ----------------------------------------------------------------------------------------------
+# Streaming weighted mean / second moment over frames
+# ----------------------------------------------------------------------------------------------
+def frame_stats(val, weights=None, bounds=None, theta=None):
+    """WBOMeanVar over dim 0 of an (N,C,H,W) stack fed in the batches [bounds[k], bounds[k+1])
+    (common/statistics.py:209-259), frames optionally linearised first
+    (inference/inferential_statistics.py:43-46).  Returns float64 (mean, m2, wsum, wsq)."""
+    val = np.asarray(val, dtype=F32)
+    n = val.shape[0]
+    bounds = [0, n] if bounds is None else list(bounds)
+    v_all = icrf_linear(val, theta)[0].astype(F64) if theta is not None else val.astype(F64)
+    mean = m2 = wsum = wsq = 0.0
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        v = v_all[a:b]
+        if weights is not None:
+            w = np.asarray(weights, dtype=F32)[a:b].astype(F64)
+            w_b = w.sum(0)
+            wsq_b = (w * w).sum(0)
+            mean_b = (w * v).sum(0) / (w_b + 1e-6)
+            m2_b = (w * (v - mean_b) ** 2).sum(0)
+        else:
+            mean_b = v.mean(0)
+            w_b = np.full_like(mean_b, float(b - a))
+            wsq_b = w_b
+            m2_b = ((v - mean_b) ** 2).sum(0)
+        w_tot = wsum + w_b
+        m2 = m2 + m2_b + (wsum * w_b / w_tot) * (mean_b - mean) ** 2
+        mean = mean + (w_b / w_tot) * (mean_b - mean)
+        wsum = w_tot
+        wsq = wsq + wsq_b
+    return mean, m2, wsum, wsq

@@ -164,6 +164,60 @@ def gen_forward():
         save(f"forward_codes_{tag}", x=xs, theta=theta, y_linear=yl, y_lookup=yn)
 
 
+def gen_catmull():
+    """CATMULL mode (models/base.py:184-226) on the CPU (the reference's CUDA path fails at :218): value, autograd
+    derivative wrt the image, and the table gradient for a fixed upstream."""
+    g = torch.Generator().manual_seed(17)
+    for c, h, w in ((3, 5, 7), (3, 4, 6), (1, 3, 5), (4, 3, 5)):
+        x = torch.rand((2, c, h, w), generator=g) * 1.2 - 0.1
+        flat = x.view(-1)
+        specials = torch.tensor([0.0, 1.0, 0.5, 1.0 / 255, 254.0 / 255, 1.5 / 255, 2.5 / 255, 0.5 / 255, 253.5 / 255])
+        flat[: len(specials)] = specials
+        up = torch.randn(x.shape, generator=g)
+        model = ICRFModelDirect(n_points=256, channels=c, interpolation_mode=InterpMode.CATMULL)
+        with torch.no_grad():
+            for k, p in enumerate(model.direct_params):
+                p.copy_(curve(c)[k])
+        model.update_icrf()
+        xi = x.clone().requires_grad_(True)
+        y = model(xi)
+        (dydx,) = torch.autograd.grad(y, xi, torch.ones_like(y), retain_graph=True)
+        (y * up).sum().backward()
+        gtheta = torch.stack([p.grad for p in model.direct_params])
+        save(f"forward_catmull_c{c}_w{w}", x=x, theta=curve(c), y=y, dydx=dydx, upstream=up, grad_theta=gtheta)
+
+
+def gen_frame_stats():
+    """WBOMeanVar (common/statistics.py:112-259) in fp32, weighted and unweighted, 3 batches; and
+    compute_video_mean_and_std (inference/inferential_statistics.py:19-49) with and without a model."""
+    from clair_torch.common.enums import VarianceMode
+    from clair_torch.common.statistics import WBOMeanVar
+    from clair_torch.inference.inferential_statistics import compute_video_mean_and_std
+    g = torch.Generator().manual_seed(5)
+    vals = torch.rand((11, 3, 6, 8), generator=g)
+    wts = torch.rand((11, 3, 6, 8), generator=g) * 2.0
+    out = dict(val=vals, weights=wts, bounds=np.array([0, 4, 9, 11]))
+    for weighted in (True, False):
+        h = WBOMeanVar(dim=0, variance_mode=VarianceMode.RELIABILITY_WEIGHTS)
+        for a, b in ((0, 4), (4, 9), (9, 11)):
+            h.update_values(vals[a:b], wts[a:b] if weighted else None)
+        tag = "w" if weighted else "u"
+        out[f"mean_{tag}"] = h.mean
+        out[f"m2_{tag}"] = h.m2
+        out[f"wsum_{tag}"] = h.sum_of_weights
+        out[f"wsq_{tag}"] = h.sum_of_squared_weights
+        out[f"var_rel_{tag}"] = h.variance()
+    save("framestats_wbomeanvar", **out)
+    vals2, _, t = make_stack(seed=61, n=9, c=3, h=8, w=12, bits=8, std_mult=None)
+    tv = [torch.from_numpy(v) for v in vals2]
+    theta = curve(3)
+    for with_model in (False, True):
+        model = ICRFModelDirect(icrf=theta.clone()) if with_model else None
+        mean, sem = compute_video_mean_and_std(loader(tv, None, t, 4), "cpu", model)
+        save(f"framestats_video_model{int(with_model)}", val=vals2, exposure=t, theta=theta if with_model else None,
+             batch_size=4, mean=mean, sem=sem)
+
+
 def gen_hdr():
     cases = [
         # name, stack kwargs, batch_size, with model, weight_fn, with std
@@ -373,6 +427,8 @@ def gen_known_answers():
 if __name__ == "__main__":
     gen_known_answers()
     gen_forward()
+    gen_catmull()
+    gen_frame_stats()
     gen_hdr()
     gen_linearize()
     gen_linearity()

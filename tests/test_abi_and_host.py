@@ -35,7 +35,8 @@ def test_header_symbols_are_exported(native):
     assert lib.clair_abi_version() == native.ABI_VERSION
     for macro, value in (("CLAIR_MAX_FRAMES", native.MAX_FRAMES), ("CLAIR_MAX_CHANNELS", native.MAX_CHANNELS),
                          ("CLAIR_MAX_LUT", native.MAX_LUT), ("CLAIR_MAX_PAIRS", native.MAX_PAIRS),
-                         ("CLAIR_INTERP_LOOKUP", native.INTERP_LOOKUP), ("CLAIR_INTERP_LINEAR", native.INTERP_LINEAR)):
+                         ("CLAIR_INTERP_LOOKUP", native.INTERP_LOOKUP), ("CLAIR_INTERP_LINEAR", native.INTERP_LINEAR),
+                         ("CLAIR_INTERP_CATMULL", native.INTERP_CATMULL)):
         assert int(re.search(rf"#define {macro} (\d+)", header).group(1)) == value
 
 

@@ -68,6 +68,46 @@ def test_forward_every_code(ct, name):
     assert np.array_equal(_model(ct, z["theta"], ct.InterpMode.LOOKUP)(x).cpu().numpy(), z["y_lookup"])
 
 
+@pytest.mark.parametrize("name", golden_names("forward_catmull"))
+def test_forward_catmull_golden(ct, name):
+    """CATMULL mode: value bit-exact, derivative and table gradient against the reference's CPU autograd."""
+    z = golden(name)
+    c = z["theta"].shape[0]
+    model = ct.ICRFModelDirect(256, c, ct.InterpMode.CATMULL).to(DEV)
+    with torch.no_grad():
+        for k, p in enumerate(model.direct_params):
+            p.copy_(torch.from_numpy(z["theta"][k]))
+    model.update_icrf()
+    x = torch.from_numpy(z["x"]).to(DEV).requires_grad_(True)
+    y = model(x)
+    (dydx,) = torch.autograd.grad(y, x, torch.ones_like(y), retain_graph=True)
+    (y * torch.from_numpy(z["upstream"]).to(DEV)).sum().backward()
+    gtheta = torch.stack([p.grad for p in model.direct_params]).cpu().numpy()
+    assert np.array_equal(y.detach().cpu().numpy(), z["y"])
+    assert max_abs_over_max(dydx.cpu().numpy(), z["dydx"]) < 1e-4
+    assert max_abs_over_max(gtheta, z["grad_theta"]) < TOL
+
+
+def test_pca_model_table_and_training_step(ct):
+    """ICRFModelPCA builds a (C, L) table from exponents + PCA coefficients and trains through the fused step."""
+    from clair_torch_b200 import ICRFModelPCA, train_icrf_step
+    L, K, C = 256, 3, 3
+    x = torch.linspace(0, 1, L)
+    basis = torch.stack([torch.sin((k + 1) * torch.pi * x) for k in range(K)], dim=1).unsqueeze(-1).repeat(1, 1, C) * 0.01
+    model = ICRFModelPCA(basis).to(DEV)
+    model.update_icrf()
+    assert tuple(model.icrf.shape) == (C, L)
+    want = x.clamp(min=1e-6).pow(2.0)
+    assert torch.allclose(model.icrf[0].cpu(), want, atol=1e-6)
+    val, std, t = ct.synthetic.make_stack(5, 3, 48, 64, seed=3)
+    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-2) for c in range(C)]
+    before = [p.detach().clone() for p in model.parameters()]
+    for _ in range(3):
+        loss = train_icrf_step(model, opts, val.to(DEV), std.to(DEV), torch.from_numpy(t))
+    assert loss.shape == (3,) and torch.isfinite(loss).all()
+    assert any(not torch.equal(a, b.detach()) for a, b in zip(before, model.parameters()))
+
+
 def test_forward_table_gradient_matches_scatter(ct):
     """d/d table of sum(g * f(x)) equals the two-tap scatter of the oracle (index_put of models/base.py:176)."""
     rng = np.random.default_rng(5)
@@ -360,3 +400,48 @@ def test_hdr_merge_integer_ingest_against_reference_fixture(ct):
     assert rad.dtype == torch.float64
     assert max_rel(rad.cpu().numpy(), z["radiance"]) < TOL
     assert max_rel(sig.cpu().numpy(), z["sigma"]) < TOL
+
+
+# ---- streaming frame statistics -------------------------------------------------
+def test_wbomeanvar_golden(ct):
+    from clair_torch_b200.common.statistics import WBOMeanVar
+    from clair_torch_b200.common.enums import VarianceMode
+    z = golden("framestats_wbomeanvar")
+    val, wts = torch.from_numpy(z["val"]).to(DEV), torch.from_numpy(z["weights"]).to(DEV)
+    b = z["bounds"]
+    for tag, weighted in (("w", True), ("u", False)):
+        h = WBOMeanVar(dim=0, variance_mode=VarianceMode.RELIABILITY_WEIGHTS)
+        for a, e in zip(b[:-1], b[1:]):
+            mean, m2 = h.update_values(val[a:e].contiguous(), wts[a:e].contiguous() if weighted else None)
+        assert tuple(mean.shape) == z[f"mean_{tag}"].shape
+        assert max_rel(mean.cpu().numpy(), z[f"mean_{tag}"]) < TOL
+        assert max_rel(m2.cpu().numpy(), z[f"m2_{tag}"]) < 3e-5        # the reference's own fp32 two-pass sum
+        assert max_rel(h.variance().cpu().numpy(), z[f"var_rel_{tag}"]) < 3e-5
+        o_mean, o_m2, _, _ = orc.frame_stats(z["val"], z["weights"] if weighted else None, b)
+        assert max_rel(mean.cpu().numpy()[0], o_mean) < 2e-6 and max_rel(m2.cpu().numpy()[0], o_m2) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names("framestats_video"))
+def test_compute_video_mean_and_std_golden(ct, name):
+    z = golden(name)
+    model = _model(ct, z["theta"]) if "theta" in z else None
+    loader = _loader(ct, z, int(z["batch_size"]))
+    mean, sem = ct.compute_video_mean_and_std(loader, DEV, model)
+    assert max_rel(mean.cpu().numpy(), z["mean"]) < TOL
+    assert max_rel(sem.cpu().numpy(), z["sem"]) < 3e-5
+
+
+def test_frame_stats_large_vs_oracle(ct):
+    """64 frames of 540p in four uneven batches, linearised in the same pass."""
+    from clair_torch_b200.common.statistics import WBOMeanVar
+    g = torch.Generator().manual_seed(1)
+    val = torch.rand((64, 3, 135, 240), generator=g)
+    theta = ct.synthetic.reference_curve(3)
+    h = WBOMeanVar(dim=0)
+    bounds = [0, 7, 30, 31, 64]
+    for a, e in zip(bounds[:-1], bounds[1:]):
+        h.update_values(val[a:e].contiguous().to(DEV), None, table=theta.to(DEV))
+    o_mean, o_m2, o_w, _ = orc.frame_stats(val.numpy(), None, bounds, theta.numpy())
+    assert max_rel(h.mean.cpu().numpy()[0], o_mean) < 2e-6
+    assert max_rel(h.m2.cpu().numpy()[0], o_m2) < TOL
+    assert torch.equal(h.sum_of_weights.cpu(), torch.full((1, 3, 135, 240), 64.0))

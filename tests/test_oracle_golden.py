@@ -75,6 +75,18 @@ def test_forward_linear_bit_exact(name):
     assert np.array_equal(fp, z["dydx"])
 
 
+@pytest.mark.parametrize("name", golden_names("forward_catmull"))
+def test_forward_catmull(name):
+    z = golden(name)
+    f, fp, taps, w, rows = orc.icrf_catmull(z["x"], z["theta"])
+    assert np.array_equal(f, z["y"])
+    assert max_abs_over_max(fp, z["dydx"]) < 1e-4      # the reference's fp32 autograd vs the closed form
+    gt = np.zeros(z["theta"].shape)
+    for ix, wi in zip(taps, w):
+        np.add.at(gt, (rows.ravel(), ix.ravel()), (z["upstream"] * wi).ravel().astype(np.float64))
+    assert max_abs_over_max(gt, z["grad_theta"]) < 1e-6
+
+
 @pytest.mark.parametrize("name", golden_names("forward_lookup"))
 def test_forward_lookup_bit_exact(name):
     z = golden(name)
@@ -215,3 +227,24 @@ def test_c_train_grad(name):
         _, gpens = orc.curve_penalties(theta)
         total = grad + sum(k * g for k, g in zip(tuple(z["coeffs"]), gpens))
         assert max_abs_over_max(total, z[f"grad_theta_{step}"]) < TOL
+
+
+# ---- streaming frame statistics -------------------------------------------------
+def test_frame_stats_wbomeanvar():
+    z = golden("framestats_wbomeanvar")
+    for tag, w in (("w", z["weights"]), ("u", None)):
+        mean, m2, wsum, wsq = orc.frame_stats(z["val"], w, z["bounds"])
+        assert max_rel(mean, z[f"mean_{tag}"][0]) < 1e-6 and max_rel(m2, z[f"m2_{tag}"][0]) < 2e-5
+        assert max_rel(wsum, z[f"wsum_{tag}"][0]) < 1e-6 and max_rel(wsq, z[f"wsq_{tag}"][0]) < 1e-6
+        assert max_rel(m2 / (wsum - wsq / wsum), z[f"var_rel_{tag}"][0]) < 2e-5
+
+
+@pytest.mark.parametrize("name", golden_names("framestats_video"))
+def test_frame_stats_video(name):
+    z = golden(name)
+    n = z["val"].shape[0]
+    order = np.argsort(z["exposure"], kind="stable")
+    bounds = list(range(0, n, int(z["batch_size"]))) + [n]
+    mean, m2, wsum, _ = orc.frame_stats(z["val"][order], None, bounds, _opt(z, "theta"))
+    assert max_rel(mean, z["mean"]) < 1e-6
+    assert max_rel(np.sqrt(m2 / (wsum - 1)) / np.sqrt(n), z["sem"]) < 2e-5
