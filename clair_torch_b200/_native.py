@@ -46,6 +46,10 @@ _PROTOTYPES = {
                                          _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_int,
                                          _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int,
                                          _c.c_void_p, _c.c_void_p]),
+    "clair_dark_field_mix": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
+                                        _c.c_int, _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    "clair_flat_field_correct": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
+                                            _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "clair_frame_stats_update": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int,
                                             _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                             _c.c_void_p]),

@@ -50,3 +50,26 @@ class ExposureStackDataset(Dataset):
             val = val.clone()
             std = std.clone() if torch.is_tensor(std) else std
         return idx, val, std, {"exposure_time": self.exposures[idx]}
+
+
+class InMemoryArtefactDataset:
+    """Flat-field / dark-field calibration frames held in memory.  The reference matches artefact files to frames by
+    filename metadata (clair_torch/datasets/base.py:175-296, host bookkeeping that is out of scope); here frame `i` of
+    the main dataset matches artefact `i mod len`, and the return value has the reference's collated structure."""
+
+    def __init__(self, vals: Sequence[torch.Tensor], stds: Optional[Sequence[torch.Tensor]], exposures: Optional[Sequence[float]] = None):
+        self.vals, self.stds = vals, stds
+        self.exposures = [float(e) for e in exposures] if exposures is not None else None
+
+    def __len__(self) -> int:
+        return len(self.vals)
+
+    def get_matching_artefact_images(self, reference_frame_settings_list):
+        from .collate import custom_collate
+        items = []
+        for pos, ref in enumerate(reference_frame_settings_list):
+            i = int(ref) % len(self.vals)
+            # custom_collate sorts by exposure time; without exposures the request order is kept
+            key = self.exposures[i] if self.exposures is not None else float(pos)
+            items.append((i, self.vals[i], None if self.stds is None else self.stds[i], {"exposure_time": key}))
+        return custom_collate(items)

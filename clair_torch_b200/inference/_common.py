@@ -46,8 +46,18 @@ def linear_table(icrf_model: Optional[ICRFModelBase], device) -> Optional[torch.
     return icrf_model.icrf.detach().to(device=device, dtype=torch.float32)
 
 
-def reject_artefacts(**datasets):
-    for name, ds in datasets.items():
-        if ds is not None:
-            raise NotImplementedError(f"{name}: flat-field / dark-field corrections are the next row of the scope table "
-                                      "(SURVEY.md §8(f) rank 1) and are not fused into the B200 kernels yet")
+def check_artefact_dataset(name, ds):
+    """Artefact datasets are duck-typed: the reference's Flat/DarkFieldArtefactMapDataset (file matching is host
+    bookkeeping, out of scope) or datasets.InMemoryArtefactDataset — anything with get_matching_artefact_images."""
+    if ds is not None and not hasattr(ds, "get_matching_artefact_images"):
+        raise TypeError(f"{name} must provide get_matching_artefact_images(frame_settings_list)")
+
+
+def matching_dark_frames(main_dataset, dark_field_dataset, index_batch, device):
+    """inference/hdr_merge.py:77-86: the dark frames matching the batch (None when nothing matches and the dataset
+    is in skip mode)."""
+    refs = [main_dataset.files[int(i)] for i in index_batch]
+    _, dark_val, dark_std, _ = dark_field_dataset.get_matching_artefact_images(refs)
+    if dark_val is None:
+        return None, None
+    return dark_val.to(device=device), (None if dark_std is None else dark_std.to(device=device))

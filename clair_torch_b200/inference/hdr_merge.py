@@ -6,7 +6,8 @@ from torch.utils.data import DataLoader
 
 from .. import kernels
 from ..models.base import ICRFModelBase
-from ._common import as_device, linear_table, normalise_transforms, reject_artefacts, stage_batch
+from ._common import (as_device, check_artefact_dataset, linear_table, matching_dark_frames, normalise_transforms,
+                      stage_batch)
 
 
 def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFModelBase] = None,
@@ -39,7 +40,9 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
     if weight_fn is not None and not callable(weight_fn):
         raise TypeError("weight_fn must be callable or None")
     dev = as_device(device)
-    reject_artefacts(flat_field_dataset=flat_field_dataset, dark_field_dataset=dark_field_dataset)
+    check_artefact_dataset("flat_field_dataset", flat_field_dataset)
+    check_artefact_dataset("dark_field_dataset", dark_field_dataset)
+    main_dataset = dataloader.dataset
     transforms = normalise_transforms(gpu_transforms)
     table = linear_table(icrf_model, dev)
 
@@ -51,13 +54,23 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
         upcoming = next(batches, None)                   # look one batch ahead to know which one is the last
         _, val_batch, std_batch, meta_batch = current
         std_is_tensor = torch.is_tensor(std_batch)
-        zero_copy = (not transforms and not val_batch.is_cuda and val_batch.is_pinned() and val_batch.is_contiguous()
+        index_batch = current[0]
+        zero_copy = (not transforms and dark_field_dataset is None and not val_batch.is_cuda and val_batch.is_pinned()
+                     and val_batch.is_contiguous()
                      and (not std_is_tensor or (std_batch.is_pinned() and std_batch.is_contiguous())))
         if zero_copy:
             images, stds = val_batch, std_batch
         else:
             images, stds = stage_batch(val_batch, std_batch if std_is_tensor else None, dev, transforms)
             stds = stds if std_is_tensor else std_batch
+        if dark_field_dataset is not None:
+            # hot pixels of the matching dark frames select a blurred copy; image-std and dark-std variance terms fold
+            # into one effective std (hdr_merge.py:76-92,107-126)
+            if images.dtype != torch.float32:
+                raise NotImplementedError("dark-field correction takes normalised fp32 images (not raw integer codes)")
+            dark_val, dark_std = matching_dark_frames(main_dataset, dark_field_dataset, index_batch, dev)
+            if dark_val is not None:
+                images, stds = kernels.dark_field_mix(images, stds if torch.is_tensor(stds) else None, dark_val, dark_std)
         exposures = meta_batch["exposure_time"]
         out_dtype = radiance_dtype
         if out_dtype is None:
@@ -65,9 +78,19 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
             out_dtype = torch.promote_types(value_dtype, exposures.dtype if torch.is_tensor(exposures) else torch.float64)
         result = kernels.hdr_merge_update(state, images, stds, exposures, table, weight_fn is not None,
                                           is_final=upcoming is None, radiance_dtype=out_dtype, device=dev,
-                                          host_out=host_out if upcoming is None else None, code_max=code_max)
+                                          host_out=host_out if (upcoming is None and flat_field_dataset is None) else None,
+                                          code_max=code_max)
         current = upcoming
     if result is None:
         raise ValueError("the dataloader yielded no batches")
     radiance, sigma = result
+    if flat_field_dataset is not None:
+        # hdr_merge.py:131-153: the whole-image mean of the flat field is inside the autograd graph there
+        _, flat_val, flat_std, _ = flat_field_dataset.get_matching_artefact_images([main_dataset.files[0]])
+        kernels.flat_field_correct_(radiance, sigma, flat_val, flat_std if sigma is not None else None, mean_in_graph=True)
+        if host_out is not None:
+            host_out[0].copy_(radiance, non_blocking=True)
+            if sigma is not None:
+                host_out[1].copy_(sigma, non_blocking=True)
+            radiance, sigma = host_out[0], (host_out[1] if sigma is not None else None)
     return radiance.squeeze(), (sigma.squeeze() if sigma is not None else None)

@@ -6,7 +6,8 @@ from torch.utils.data import DataLoader
 
 from .. import kernels
 from ..models.base import ICRFModelBase
-from ._common import as_device, linear_table, normalise_transforms, reject_artefacts, stage_batch
+from ._common import (as_device, check_artefact_dataset, linear_table, matching_dark_frames, normalise_transforms,
+                      stage_batch)
 
 
 def linearize_dataset_generator(dataloader: DataLoader, device, icrf_model: ICRFModelBase, flatfield_dataset=None,
@@ -24,10 +25,21 @@ def linearize_dataset_generator(dataloader: DataLoader, device, icrf_model: ICRF
     dev = as_device(device)
     if not dataloader.batch_size == 1:
         raise ValueError("For linearization only batch_size of 1 is allowed.")
-    reject_artefacts(flatfield_dataset=flatfield_dataset, dark_field_dataset=dark_field_dataset)
+    check_artefact_dataset("flatfield_dataset", flatfield_dataset)
+    check_artefact_dataset("dark_field_dataset", dark_field_dataset)
+    main_dataset = dataloader.dataset
     transforms = normalise_transforms(gpu_transforms)
     table = linear_table(icrf_model, dev)
-    for _, val_batch, std_batch, meta_batch in dataloader:
+    flat_val = flat_std = None
+    if flatfield_dataset is not None:                     # linearization.py:50-57: one flat field for the whole run
+        _, flat_val, flat_std, _ = flatfield_dataset.get_matching_artefact_images([main_dataset.files[0]])
+    for index_batch, val_batch, std_batch, meta_batch in dataloader:
         images, stds = stage_batch(val_batch, std_batch, dev, transforms)
+        if dark_field_dataset is not None:                # linearization.py:73-91,108-116
+            dark_val, dark_std = matching_dark_frames(main_dataset, dark_field_dataset, index_batch, dev)
+            if dark_val is not None:
+                images, stds = kernels.dark_field_mix(images, stds, dark_val, dark_std)
         lin, sigma = kernels.linearize(images, stds, table)
+        if flat_val is not None:                          # linearization.py:118-130: the mean is a constant here
+            kernels.flat_field_correct_(lin, sigma, flat_val, flat_std, mean_in_graph=False)
         yield lin.squeeze().cpu(), sigma.squeeze().cpu(), meta_batch

@@ -337,3 +337,58 @@ def curve_penalties(theta: torch.Tensor, alpha: float, beta: float, gamma: float
                                        _ptr(grad), _stream(th.device))
     _native.check(rc, "clair_curve_penalties")
     return pen
+
+
+DARK_THRESHOLD, DARK_ALPHA = 0.05, 50.0     # inference/hdr_merge.py:90, common/general_functions.py:442
+
+
+def dark_field_mix(val: torch.Tensor, std: Optional[torch.Tensor], dark: torch.Tensor, dark_std: Optional[torch.Tensor],
+                   threshold: float = DARK_THRESHOLD, alpha: float = DARK_ALPHA):
+    """(mixed images, effective std) of the dark-field correction: conditional_gaussian_blur plus the collapse of the
+    image-std and dark-std variance terms into one per-element std (see clair_dark_field_mix in the header)."""
+    lib = _native.load()
+    val = _stack(val, "val_batch")
+    dark = _stack(dark, "dark_field_val")
+    n, c, h, w = val.shape
+    if dark.shape[0] == 1 and n > 1:
+        dark = dark.expand(n, -1, -1, -1).contiguous()
+    if dark.shape != val.shape:
+        raise ValueError(f"mask_map batch dimension must be 1 or {n}, got {dark.shape[0]}")
+    want_std = std is not None
+    if want_std:
+        if dark_std is None:
+            raise ValueError("dark-field std images are required when the value images carry std images")
+        std = _stack(std, "std_batch")
+        dark_std = _stack(dark_std, "dark_field_std")
+        if dark_std.shape[0] == 1 and n > 1:
+            dark_std = dark_std.expand(n, -1, -1, -1).contiguous()
+    out_val = torch.empty_like(val)
+    out_std = torch.empty_like(val) if want_std else None
+    with torch.cuda.device(val.device):
+        rc = lib.clair_dark_field_mix(_ptr(val), _ptr(std) if want_std else None, _ptr(dark), _ptr(dark_std) if want_std else None,
+                                      n, c, h, w, float(threshold), float(alpha), _ptr(out_val), _ptr(out_std),
+                                      _stream(val.device))
+    _native.check(rc, "clair_dark_field_mix")
+    return out_val, out_std
+
+
+def flat_field_correct_(value: torch.Tensor, sigma: Optional[torch.Tensor], flat: torch.Tensor,
+                        flat_std: Optional[torch.Tensor], mean_in_graph: bool):
+    """In-place flat-field correction of `value` ((C,H,W) or (N,C,H,W), fp32 or fp64) and of its std `sigma` (fp32)."""
+    lib = _native.load()
+    if not value.is_cuda or not value.is_contiguous():
+        raise RuntimeError("flat-field correction works in place on contiguous CUDA tensors")
+    shape = value.shape if value.dim() == 4 else (1,) + tuple(value.shape)
+    n, c, h, w = shape
+    f = flat.detach().to(device=value.device, dtype=_F32).reshape(-1, h, w).contiguous()
+    if f.shape[0] != c:
+        raise ValueError(f"flat field must have shape (C={c}, H, W) (or (1, C, H, W)), got {tuple(flat.shape)}")
+    fs = None if flat_std is None else flat_std.detach().to(device=value.device, dtype=_F32).reshape(-1, h, w).contiguous()
+    if sigma is not None and (not sigma.is_cuda or sigma.dtype != _F32 or not sigma.is_contiguous() or sigma.numel() != value.numel()):
+        raise ValueError("sigma must be a contiguous fp32 CUDA tensor of the shape of value")
+    scratch = torch.empty(2 * c, dtype=_F64, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = lib.clair_flat_field_correct(_ptr(value), int(value.dtype == _F64), _ptr(sigma), _ptr(f), _ptr(fs), n, c, h * w,
+                                          int(bool(mean_in_graph)), _ptr(scratch), _stream(value.device))
+    _native.check(rc, "clair_flat_field_correct")
+    return value, sigma

@@ -144,6 +144,34 @@ CLAIR_API int clair_hdr_merge_codes(const void *codes_dev, int code_bytes, float
                           void *stream);
 
 /*
+ * Dark-field correction pre-pass — SURVEY.md §8(f) rank 1.  Replaces conditional_gaussian_blur(images, dark, 0.05, 3,
+ * differentiable=True) (clair_torch/common/general_functions.py:440-486) as called at clair_torch/inference/hdr_merge.py:
+ * 89-92 and clair_torch/inference/linearization.py:88-91, together with BOTH variance terms the drivers form afterwards
+ * (hdr_merge.py:107-126, linearization.py:98-116): the drivers differentiate with respect to the mixed image, so
+ *     val_out = m B(x) + (1 - m) x,    m = sigmoid(alpha (dark - threshold)),   B = 3x3 Gaussian blur, reflect padding
+ *     std_out = sqrt(std^2 + ((B(x) - x) alpha m (1 - m) dark_std)^2)
+ * and running the merge / linearise kernels on (val_out, std_out) reproduces mean, image-std and dark-std terms.
+ * All stacks (n_frames, C, H, W) fp32; std_out_dev may be NULL (then std_dev / dark_std_dev are not read).
+ */
+CLAIR_API int clair_dark_field_mix(const float *val_dev, const float *std_dev, const float *dark_dev, const float *dark_std_dev,
+                         int n_frames, int n_channels, int height, int width, float threshold, float alpha,
+                         float *val_out_dev, float *std_out_dev, void *stream);
+
+/*
+ * Flat-field correction in place — replaces flat_field_mean(F, 1.0) + flatfield_correction
+ * (clair_torch/common/general_functions.py:182-238) and the variance term of clair_torch/inference/hdr_merge.py:131-153
+ * (mean_in_graph = 1: the whole-image mean of F is differentiated through) or clair_torch/inference/linearization.py:
+ * 118-130 (mean_in_graph = 0: the mean is a constant) — SURVEY.md Q11.
+ *   value_dev   (n_images, C, plane) fp32 or fp64 (value_f64), overwritten with v / (F + 1e-6) * mean(F)
+ *   sigma_dev   (n_images, C, plane) fp32 std, overwritten with sqrt(sigma^2 + (dy/dF flat_std)^2); may be NULL
+ *   flat_dev, flat_std_dev   (C, plane) fp32; flat_std_dev may be NULL (value only)
+ *   scratch_dev 2*C doubles
+ */
+CLAIR_API int clair_flat_field_correct(void *value_dev, int value_f64, float *sigma_dev, const float *flat_dev,
+                             const float *flat_std_dev, int n_images, int n_channels, int64_t plane, int mean_in_graph,
+                             double *scratch_dev, void *stream);
+
+/*
  * Streaming weighted mean / second moment over frames — replaces WBOMeanVar.update_values + _update_internal_values
  * (clair_torch/common/statistics.py:209-259) as used by compute_video_mean_and_std
  * (clair_torch/inference/inferential_statistics.py:19-49); SURVEY.md §8(f) rank 3.

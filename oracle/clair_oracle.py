@@ -457,3 +457,55 @@ def frame_stats(val, weights=None, bounds=None, theta=None):
         wsum = w_tot
         wsq = wsq + wsq_b
     return mean, m2, wsum, wsq
+
+
+# ----------------------------------------------------------------------------------------------
+# Dark-field and flat-field corrections
+# ----------------------------------------------------------------------------------------------
+def gaussian_blur3(x):
+    """torchvision GaussianBlur(kernel_size=3, sigma=1.0) on (..., H, W): reflect padding, taps
+    exp(-0.5 d^2) / sum (common/general_functions.py:462-463)."""
+    k1 = np.exp(-0.5 * np.array([-1.0, 0.0, 1.0]) ** 2)
+    k1 = (k1 / k1.sum()).astype(F32).astype(F64)
+    x = np.asarray(x, dtype=F64)
+    p = np.pad(x, [(0, 0)] * (x.ndim - 2) + [(1, 1), (1, 1)], mode="reflect")
+    h, w = x.shape[-2:]
+    out = np.zeros_like(x)
+    for dy in range(3):
+        for dx in range(3):
+            out += k1[dy] * k1[dx] * p[..., dy:dy + h, dx:dx + w]
+    return out
+
+
+def dark_field_mix(val, std, dark, dark_std, threshold=0.05, alpha=50.0):
+    """conditional_gaussian_blur(images, dark, 0.05, 3, differentiable=True) (common/general_functions.py:440-486) as
+    used at inference/hdr_merge.py:89-92, plus the effective per-pixel std that carries BOTH variance terms of the
+    drivers: the gradient is taken wrt the MIXED image (hdr_merge.py:107-113 re-uses the reassigned `images`), so
+      var = sum (g' std)^2 + sum (g' dx'/dD dark_std)^2 = sum (g' std_eff)^2,   std_eff = sqrt(std^2 + (dx'/dD dark_std)^2),
+      dx'/dD = (blur(x) - x) * alpha * m (1 - m),   m = sigmoid(alpha (D - threshold)).
+    Returns (mixed float64, std_eff float64)."""
+    x = np.asarray(val, dtype=F32).astype(F64)
+    d = np.asarray(dark, dtype=F32).astype(F64)
+    m = 1.0 / (1.0 + np.exp(-(d - threshold) * alpha))
+    b = gaussian_blur3(x)
+    mixed = m * b + (1.0 - m) * x
+    dmix = (b - x) * alpha * m * (1.0 - m)
+    s = np.asarray(std, dtype=F32).astype(F64)
+    ds = np.asarray(dark_std, dtype=F32).astype(F64)
+    return mixed, np.sqrt(s * s + (dmix * ds) ** 2)
+
+
+def flat_field_correct(value, var, flat, flat_std, mean_in_graph=True):
+    """flatfield_correction with the whole-image mean (flat_field_mean(F, 1.0)) and its variance term
+    (common/general_functions.py:182-238; inference/hdr_merge.py:131-153 with the mean inside the autograd graph,
+    inference/linearization.py:50-57,118-130 with the mean a constant — SURVEY.md Q11).  The existing variance is not
+    rescaled by the gain.  value/var: (..., C, H, W); flat, flat_std: (C, H, W)."""
+    value = np.asarray(value, dtype=F64)
+    f = np.asarray(flat, dtype=F32).astype(F64)
+    mu = f.mean(axis=(-1, -2), keepdims=True)
+    corrected = value / (f + 1e-6) * mu
+    g = -value * mu / (f + 1e-6) ** 2
+    if mean_in_graph:
+        g = g + (value / (f + 1e-6)).sum(axis=(-1, -2), keepdims=True) / (f.shape[-1] * f.shape[-2])
+    fs = np.asarray(flat_std, dtype=F32).astype(F64)
+    return corrected, np.asarray(var, dtype=F64) + (g * fs) ** 2

@@ -218,6 +218,58 @@ def gen_frame_stats():
              batch_size=4, mean=mean, sem=sem)
 
 
+def _artefact_stub(base_cls, vals, stds, exposures):
+    """In-memory stand-in for the file-matching artefact datasets: frame i of the main dataset matches artefact i."""
+    class Stub(base_cls):
+        def __init__(self):
+            self.vals, self.stds, self.exposures = vals, stds, exposures
+
+        def get_matching_artefact_images(self, reference_frame_settings_list):
+            items = []
+            for ref in reference_frame_settings_list:
+                i = int(ref) % len(self.vals)
+                items.append((i, self.vals[i].clone(), None if self.stds is None else self.stds[i].clone(),
+                              {"exposure_time": float(self.exposures[i])}))
+            return custom_collate(items)
+    return Stub()
+
+
+def gen_artefacts():
+    """Dark-field (conditional blur of hot pixels) and flat-field corrections with their variance terms:
+    inference/hdr_merge.py:76-92,117-126,131-153 and inference/linearization.py:50-57,73-91,108-130."""
+    from clair_torch.datasets.image_dataset import DarkFieldArtefactMapDataset, FlatFieldArtefactMapDataset
+    rng = np.random.default_rng(71)
+    for name, kw, bs, use_dark, use_flat in (("dark", dict(seed=71, n=4, c=3, h=9, w=12, bits=8), 4, True, False),
+                                             ("flat", dict(seed=72, n=4, c=3, h=9, w=12, bits=8), 4, False, True),
+                                             ("both_2batches", dict(seed=73, n=5, c=3, h=8, w=11, bits=16), 3, True, True)):
+        vals, stds, t = make_stack(**kw)
+        n, c, h, w = vals.shape
+        theta = curve(c)
+        # dark frames: mostly ~0.01, a few hot pixels well above the 0.05 threshold, some near it
+        dark = rng.uniform(0.0, 0.02, size=vals.shape).astype(np.float32)
+        hot = rng.random(vals.shape) < 0.08
+        dark[hot] = rng.uniform(0.03, 0.3, size=int(hot.sum())).astype(np.float32)
+        dark_std = (0.1 * dark + 0.001).astype(np.float32)
+        flat = rng.uniform(0.6, 1.0, size=(1, c, h, w)).astype(np.float32)
+        flat_std = (0.02 * flat).astype(np.float32)
+        tv = [torch.from_numpy(v) for v in vals]
+        ts = [torch.from_numpy(x) for x in stds]
+        dark_ds = _artefact_stub(DarkFieldArtefactMapDataset, [torch.from_numpy(d) for d in dark],
+                                 [torch.from_numpy(d) for d in dark_std], t) if use_dark else None
+        flat_ds = _artefact_stub(FlatFieldArtefactMapDataset, [torch.from_numpy(flat[0])], [torch.from_numpy(flat_std[0])],
+                                 [1.0]) if use_flat else None
+        model = ICRFModelDirect(icrf=theta.clone())
+        rad, sig = compute_hdr_image(loader(tv, ts, t, bs), "cpu", model, gaussian_value_weights, flat_ds, None, dark_ds)
+        lin, lsig = [], []
+        for a, b, _ in linearize_dataset_generator(loader(tv, ts, t, 1), "cpu", model, flat_ds, None, dark_ds):
+            lin.append(a.numpy())
+            lsig.append(b.numpy())
+        save(f"artefact_{name}", val=vals, std=stds, exposure=t, theta=theta, batch_size=bs,
+             dark=dark if use_dark else None, dark_std=dark_std if use_dark else None,
+             flat=flat if use_flat else None, flat_std=flat_std if use_flat else None,
+             radiance=rad, sigma=sig, linearized=np.stack(lin), lin_sigma=np.stack(lsig))
+
+
 def gen_hdr():
     cases = [
         # name, stack kwargs, batch_size, with model, weight_fn, with std
@@ -429,6 +481,7 @@ if __name__ == "__main__":
     gen_forward()
     gen_catmull()
     gen_frame_stats()
+    gen_artefacts()
     gen_hdr()
     gen_linearize()
     gen_linearity()

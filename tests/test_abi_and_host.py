@@ -166,7 +166,7 @@ def test_error_conventions_match_reference():
         ct.compute_hdr_image("not a loader", "cuda")
     with pytest.raises(TypeError):
         ct.ICRFModelDirect(interpolation_mode="LINEAR")
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(TypeError):
         ct.compute_hdr_image(DataLoader(ds, batch_size=3, collate_fn=custom_collate), "cuda", model, None, object())
     m = ct.ICRFModelDirect(icrf=torch.zeros(2, 17))
     assert m.channels == 2 and m.n_points == 17 and m.icrf.shape == (2, 17)

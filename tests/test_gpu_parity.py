@@ -445,3 +445,53 @@ def test_frame_stats_large_vs_oracle(ct):
     assert max_rel(h.mean.cpu().numpy()[0], o_mean) < 2e-6
     assert max_rel(h.m2.cpu().numpy()[0], o_m2) < TOL
     assert torch.equal(h.sum_of_weights.cpu(), torch.full((1, 3, 135, 240), 64.0))
+
+
+# ---- dark-field / flat-field corrections -----------------------------------------
+def _artefact_datasets(z):
+    from clair_torch_b200.datasets import InMemoryArtefactDataset
+    dark = flat = None
+    if "dark" in z:
+        dark = InMemoryArtefactDataset([torch.from_numpy(d) for d in z["dark"]], [torch.from_numpy(d) for d in z["dark_std"]],
+                                       list(z["exposure"]))
+    if "flat" in z:
+        flat = InMemoryArtefactDataset([torch.from_numpy(z["flat"][0])], [torch.from_numpy(z["flat_std"][0])])
+    return dark, flat
+
+
+@pytest.mark.parametrize("name", golden_names("artefact_"))
+def test_artefact_corrections_golden(ct, name):
+    z = golden(name)
+    dark, flat = _artefact_datasets(z)
+    model = _model(ct, z["theta"])
+    rad, sig = ct.compute_hdr_image(_loader(ct, z, int(z["batch_size"])), DEV, model, max, flat, None, dark)
+    assert rad.dtype == torch.float64
+    assert max_rel(rad.cpu().numpy(), z["radiance"]) < TOL
+    assert max_rel(sig.cpu().numpy(), z["sigma"]) < TOL
+    outs = list(ct.linearize_dataset_generator(_loader(ct, z, 1), DEV, model, flat, None, dark))
+    for n, (lin, lsig, _) in enumerate(outs):
+        assert max_rel(lin.numpy(), z["linearized"][n]) < TOL
+        assert max_rel(lsig.numpy(), z["lin_sigma"][n]) < TOL
+
+
+def test_dark_mix_and_flat_field_vs_oracle_larger(ct):
+    from clair_torch_b200 import kernels
+    rng = np.random.default_rng(9)
+    val, std, t = ct.synthetic.make_stack(4, 3, 97, 131, bits=16, seed=5)
+    dark = rng.uniform(0, 0.02, size=val.shape).astype(np.float32)
+    hot = rng.random(val.shape) < 0.05
+    dark[hot] = rng.uniform(0.03, 0.4, size=int(hot.sum())).astype(np.float32)
+    dark_std = (0.1 * dark + 1e-3).astype(np.float32)
+    mixed, seff = kernels.dark_field_mix(val.to(DEV), std.to(DEV), torch.from_numpy(dark).to(DEV), torch.from_numpy(dark_std).to(DEV))
+    o_mixed, o_seff = orc.dark_field_mix(val.numpy(), std.numpy(), dark, dark_std)
+    assert max_rel(mixed.cpu().numpy(), o_mixed, 1e-12) < 2e-6
+    assert max_rel(seff.cpu().numpy(), o_seff, 1e-12) < 5e-6
+    flat = rng.uniform(0.5, 1.0, size=(3, 97, 131)).astype(np.float32)
+    flat_std = (0.02 * flat).astype(np.float32)
+    for dtype, in_graph in ((torch.float64, True), (torch.float32, False)):
+        value = torch.from_numpy(rng.uniform(0.1, 5.0, size=(3, 97, 131))).to(dtype).to(DEV)
+        sigma = torch.from_numpy(rng.uniform(0.01, 0.1, size=(3, 97, 131)).astype(np.float32)).to(DEV)
+        want_v, want_var = orc.flat_field_correct(value.cpu().numpy(), sigma.cpu().numpy().astype(np.float64) ** 2, flat, flat_std, in_graph)
+        kernels.flat_field_correct_(value, sigma, torch.from_numpy(flat), torch.from_numpy(flat_std), in_graph)
+        assert max_rel(value.cpu().numpy(), want_v) < (1e-12 if dtype == torch.float64 else 2e-7)
+        assert max_rel(sigma.cpu().numpy(), np.sqrt(want_var)) < 2e-7

@@ -248,3 +248,30 @@ def test_frame_stats_video(name):
     mean, m2, wsum, _ = orc.frame_stats(z["val"][order], None, bounds, _opt(z, "theta"))
     assert max_rel(mean, z["mean"]) < 1e-6
     assert max_rel(np.sqrt(m2 / (wsum - 1)) / np.sqrt(n), z["sem"]) < 2e-5
+
+
+# ---- dark-field / flat-field corrections -----------------------------------------
+@pytest.mark.parametrize("name", golden_names("artefact_"))
+def test_artefact_corrections(name):
+    """Closed forms of the dark-field mix (gradient taken wrt the mixed image, both variance terms folded into one
+    effective std) and of the flat-field correction (mean inside / outside the graph) against the reference."""
+    z = golden(name)
+    val, std = z["val"], z["std"]
+    if "dark" in z:
+        mixed, seff = orc.dark_field_mix(val, std, z["dark"], z["dark_std"])
+        mixed, seff = mixed.astype(np.float32), seff.astype(np.float32)
+    else:
+        mixed, seff = val, std
+    rad, sig = orc.hdr_merge(mixed, seff, z["exposure"], z["theta"], True, int(z["batch_size"]))
+    var = sig ** 2
+    if "flat" in z:
+        rad, var = orc.flat_field_correct(rad, var, z["flat"][0], z["flat_std"][0], True)
+    assert max_rel(rad, z["radiance"]) < 2e-6
+    assert max_rel(np.sqrt(var), z["sigma"]) < TOL
+    for i in range(val.shape[0]):
+        f, s = orc.linearize(mixed[i:i + 1], seff[i:i + 1], z["theta"])
+        lin, v = f.astype(np.float64), s.astype(np.float64) ** 2
+        if "flat" in z:
+            lin, v = orc.flat_field_correct(lin, v, z["flat"][0], z["flat_std"][0], False)
+        assert max_rel(lin[0], z["linearized"][i]) < 2e-6
+        assert max_rel(np.sqrt(v[0]), z["lin_sigma"][i]) < TOL
