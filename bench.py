@@ -269,6 +269,47 @@ def secondary_metrics(dev):
         return spatial_statistics(sums, True)
 
     ms3 = timed(lin, 2, 10)
+    del val, std
+    torch.cuda.empty_cache()
+    peak = peaks()[0]
+    # c4: one stack of 9 frames x 24 MP 16-bit (fp32 val + std): merge, then per-frame linearisation
+    val, std, t = ct.synthetic.make_stack(9, CHANNELS, 4000, 6000, bits=16, seed=4567, device=dev)
+    rad = torch.empty((CHANNELS, 4000, 6000), dtype=torch.float32, device=dev)
+    st = kernels.HdrMergeState
+
+    def merge9():
+        return kernels.hdr_merge_update(st(), val, std, t, theta, True, True, radiance_dtype=torch.float32)
+
+    ms4 = timed(merge9, 2, 10)
+    e4 = 9 * CHANNELS * 4000 * 6000
+    out["hdr_merge_c4_stack"] = {"ms": ms4, "config": "1 stack: 9x3x4000x6000 16-bit as fp32 val+std",
+                                 "mpixel_frames_per_s": 9 * 24.0 / (ms4 * 1e-3),
+                                 "hbm_frac": (e4 * 8 + CHANNELS * 24e6 * 8) / (ms4 * 1e-3) / 1e9 / peak}
+    one_val, one_std = val[:3].contiguous(), std[:3].contiguous()
+    ms5 = timed(lambda: kernels.linearize(one_val, one_std, theta), 2, 10)
+    out["linearize_c4_frames"] = {"ms_per_frame": ms5 / 3, "config": "3 frames of 3x4000x6000, f(x) and sigma",
+                                  "mpixel_per_s": 3 * 24.0 / (ms5 * 1e-3),
+                                  "hbm_frac": 3 * CHANNELS * 24e6 * 16 / (ms5 * 1e-3) / 1e9 / peak}
+    del val, std, one_val, one_std, rad
+    torch.cuda.empty_cache()
+    # 8(f) rows at c1 size: dark-field mix pre-pass, flat-field correction, streaming frame statistics
+    val, std, t = ct.synthetic.make_stack(N_FRAMES, CHANNELS, HEIGHT, WIDTH, bits=8, seed=99, device=dev)
+    dark = torch.rand_like(val) * 0.06
+    dark_std = dark * 0.1 + 1e-3
+    ms6 = timed(lambda: kernels.dark_field_mix(val, std, dark, dark_std), 2, 20)
+    radiance, sigma = kernels.hdr_merge_update(st(), val, std, t, theta, True, True, radiance_dtype=torch.float32)
+    flat = torch.rand_like(radiance) * 0.4 + 0.6
+    flat_std = flat * 0.02
+    ms7 = timed(lambda: kernels.flat_field_correct_(radiance, sigma, flat, flat_std, True), 2, 20)
+    from clair_torch_b200.common.statistics import WBOMeanVar
+    handler = WBOMeanVar(dim=0)
+    ms8 = timed(lambda: handler.update_values(val, None, table=theta), 2, 20)
+    ec1 = N_FRAMES * CHANNELS * HEIGHT * WIDTH
+    out["artefacts_c1"] = {"dark_mix_ms": ms6, "dark_mix_hbm_frac": ec1 * 24 / (ms6 * 1e-3) / 1e9 / peak,
+                           "flat_field_ms": ms7, "flat_field_hbm_frac": CHANNELS * HEIGHT * WIDTH * 24 / (ms7 * 1e-3) / 1e9 / peak,
+                           "note": "dark mix: 4 input + 2 output fp32 stacks; flat field: value, sigma, flat, flat_std, in place"}
+    out["frame_stats_c1"] = {"ms": ms8, "config": "5x3x1080x1920 batch, ICRF + running mean/M2 merge",
+                             "hbm_frac": (ec1 * 4 + CHANNELS * HEIGHT * WIDTH * 32) / (ms8 * 1e-3) / 1e9 / peak}
     elems3 = 16 * CHANNELS * 2160 * 3840
     out["linearity_c3"] = {"ms": ms3, "pairs": int(len(i_idx)), "config": "16x3x2160x3840 16-bit, thr 0.2, relative, unc. weighting",
                            "pair_elements_per_s": len(i_idx) * CHANNELS * 2160 * 3840 / (ms3 * 1e-3),

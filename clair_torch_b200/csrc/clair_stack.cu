@@ -372,13 +372,6 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
     for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
         const uint32_t pix = item * VEC;
         const int64_t off = static_cast<int64_t>(c) * p.plane + pix;
-        Pack<VEC> xv[NF], sv[NF];
-#pragma unroll
-        for (int n = 0; n < NF; ++n) {
-            const int64_t o = off + static_cast<int64_t>(n) * frame_stride;
-            xv[n] = load_pixels<SRC, VEC>(p.val, o, p.code_max, s_x);
-            if constexpr (HAS_STD) sv[n] = load_std<VEC, STD>(p, o, xv[n]);
-        }
         uint32_t bias[VEC];
         {
             uint32_t u = cur.u0;
@@ -391,17 +384,26 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
         float wsum[VEC], wv[VEC], R[NF][VEC], Q[NF][VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; }
+        {
+            Pack<VEC> xv[NF], sv[NF];
 #pragma unroll
-        for (int n = 0; n < NF; ++n) {
-            const float it = p.scale.inv_t[n];
+            for (int n = 0; n < NF; ++n) {
+                const int64_t o = off + static_cast<int64_t>(n) * frame_stride;
+                xv[n] = load_pixels<SRC, VEC>(p.val, o, p.code_max, s_x);
+                if constexpr (HAS_STD) sv[n] = load_std<VEC, STD>(p, o, xv[n]);
+            }
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                const HdrTerms t = hdr_terms(xv[n].v[k], HAS_STD ? sv[n].v[k] : 0.0f, it, has_model, gaussian, bias[k], lm1,
-                                             HAS_STD);
-                wsum[k] += t.w;
-                wv[k] += t.wv;
-                R[n][k] = t.R;
-                Q[n][k] = t.Q;
+            for (int n = 0; n < NF; ++n) {
+                const float it = p.scale.inv_t[n];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const HdrTerms t = hdr_terms(xv[n].v[k], HAS_STD ? sv[n].v[k] : 0.0f, it, has_model, gaussian, bias[k], lm1,
+                                                 HAS_STD);
+                    wsum[k] += t.w;
+                    wv[k] += t.wv;
+                    R[n][k] = t.R;
+                    Q[n][k] = t.Q;
+                }
             }
         }
         hdr_finish<VEC, HAS_STD, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
@@ -409,6 +411,86 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
 #pragma unroll
             for (int n = 0; n < NF; ++n) {
                 const float g = fmaf(alpha, R[n][k], gamma * Q[n][k]);
+                acc = fmaf(g, g, acc);
+            }
+            return acc;
+        });
+    }
+}
+
+// ---- 9 <= N <= ~40: the same two-step evaluation with (R_n, Q_n) parked in shared memory ---------------------
+// N is a runtime value; frames are loaded in chunks of four.  Each thread owns a private, conflict-free column
+// rq[(n*2 + which)*VEC + k][tid], so registers stay low (occupancy is bounded by shared memory instead: 4 KB x N per
+// 256-thread block at 2 px/thread) and the variance is again a plain fp32 sum of squares.
+template <int VEC, int STD, bool SINGLE, int SRC>
+__global__ void __launch_bounds__(kBlock) hdr_merge_smem_kernel(const HdrParams p) {
+    constexpr bool HAS_STD = STD != 0;
+    static_assert(HAS_STD, "without std images there is no second step");
+    extern __shared__ float2 s_tab[];
+    const int C = p.n_channels, L = p.lut;
+    const bool has_model = p.theta != nullptr;
+    float *s_x = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
+    float *s_rq = s_x + (SRC == kSrcU8 ? 256 : 0) + threadIdx.x;
+    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
+    if constexpr (SRC == kSrcU8) {
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
+    }
+    __syncthreads();
+    const int c = blockIdx.y;
+    const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
+    const float lm1 = static_cast<float>(L - 1);
+    const bool gaussian = p.gaussian != 0;
+    const int N = p.n_frames;
+    const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
+    const uint32_t item_stride = gridDim.x * kBlock;
+    const uint32_t first_item = blockIdx.x * kBlock + threadIdx.x;
+    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
+    const uint32_t tab_bias = curve_row_bias(s_tab);
+    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
+
+    for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
+        const uint32_t pix = item * VEC;
+        const int64_t off = static_cast<int64_t>(c) * p.plane + pix;
+        uint32_t bias[VEC];
+        {
+            uint32_t u = cur.u0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) { bias[k] = tab_bias + u * row_bytes; u = (u + 1 == cur.C) ? 0u : u + 1; }
+        }
+        float wsum[VEC], wv[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; }
+        for (int n0 = 0; n0 < N; n0 += kFrameChunk) {
+            Pack<VEC> xv[kFrameChunk], sv[kFrameChunk];
+#pragma unroll
+            for (int j = 0; j < kFrameChunk; ++j) {
+                if (n0 + j < N) {
+                    const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
+                    xv[j] = load_pixels<SRC, VEC>(p.val, o, p.code_max, s_x);
+                    sv[j] = load_std<VEC, STD>(p, o, xv[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kFrameChunk; ++j) {
+                if (n0 + j < N) {
+                    const float it = p.scale.inv_t[n0 + j];
+                    float *col = s_rq + (n0 + j) * (2 * VEC * kBlock);
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) {
+                        const HdrTerms t = hdr_terms(xv[j].v[k], sv[j].v[k], it, has_model, gaussian, bias[k], lm1, true);
+                        wsum[k] += t.w;
+                        wv[k] += t.wv;
+                        col[k * kBlock] = t.R;
+                        col[(VEC + k) * kBlock] = t.Q;
+                    }
+                }
+            }
+        }
+        hdr_finish<VEC, true, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+            float acc = 0.0f;
+            for (int n = 0; n < N; ++n) {
+                const float *col = s_rq + n * (2 * VEC * kBlock);
+                const float g = fmaf(alpha, col[k * kBlock], gamma * col[(VEC + k) * kBlock]);
                 acc = fmaf(g, g, acc);
             }
             return acc;
@@ -633,15 +715,27 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         if (vec != 4 || reinterpret_cast<uintptr_t>(val_dev) % (4 * code_bytes) != 0)
             return bad(CLAIR_E_ARG, "integer ingest needs H*W % 4 == 0 and 16-byte aligned output / std / state buffers");
     }
-    const size_t smem = (theta_dev ? sizeof(float2) * n_channels * lut_size : 0) + (src == kSrcU8 ? 256 * sizeof(float) : 0);
+    size_t smem = (theta_dev ? sizeof(float2) * n_channels * lut_size : 0) + (src == kSrcU8 ? 256 * sizeof(float) : 0);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const bool single = is_first && is_final;
-    const bool fixed = has_std && n_frames <= kMaxFixedFrames && !g_tuning.hdr_force_dynamic;
+    // integer ingest takes 4 codes per load, which leaves no registers for more than 8 frames of (R_n, Q_n)
+    const bool fixed = has_std && n_frames <= (src == kSrcF32 ? kMaxFixedFrames : 8) && !g_tuning.hdr_force_dynamic;
     // measured on B200 (profiles/): with fp32 input 2 pixels per thread keep the fixed-N kernel at 40 registers
     // (6 blocks/SM); 4 pixels per thread need 64.  Integer ingest always takes 4 codes per load.
+    // 9 .. ~40 frames: (R_n, Q_n) parked in shared memory, 2 pixels per thread (1 when H*W is odd)
+    bool parked = false;
+    if (src != kSrcF32) {
+        const size_t park_bytes = sizeof(float) * 2 * 4 * kBlock * static_cast<size_t>(n_frames);
+        parked = has_std && !fixed && !g_tuning.hdr_force_dynamic && smem + park_bytes <= 110 * 1024;
+        if (parked) smem += park_bytes;
+    }
     if (src == kSrcF32) {
-        const int vec_cap = g_tuning.hdr_vec > 0 ? g_tuning.hdr_vec : (fixed ? 2 : 4);
+        const int park_vec = std::min(vec, 2);
+        const size_t park_bytes = sizeof(float) * 2 * park_vec * kBlock * static_cast<size_t>(n_frames);
+        parked = has_std && !fixed && !g_tuning.hdr_force_dynamic && smem + park_bytes <= 110 * 1024;   // >= 2 blocks per SM
+        const int vec_cap = g_tuning.hdr_vec > 0 ? g_tuning.hdr_vec : ((fixed || parked) ? 2 : 4);
         if (vec_cap < vec) vec = vec_cap;
+        if (parked) smem += sizeof(float) * 2 * vec * kBlock * static_cast<size_t>(n_frames);
     }
     const int64_t items = plane / vec;
     const int64_t want_blocks = (items + kBlock - 1) / kBlock;
@@ -650,7 +744,8 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         if (int rc = ensure_smem(kernel, smem)) return rc;
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
-        per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : 2);   // 2 waves: best tail/balance measured
+        // resident waves per persistent grid: 2 for the register kernel, 3 for the shared-memory-parked one (measured)
+        per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : (parked ? 3 : 2));
         const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want_blocks, (static_cast<int64_t>(device_sm_count()) * per_sm + n_channels - 1) / n_channels));
         kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p);
         return 0;
@@ -669,16 +764,20 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         default: rc = FIXED_NF(V, 8, ST, SRC); break;       \
     }
 #define DYN(V, ST, SRC) rc = launch(hdr_merge_kernel<V, ST, SRC>)
+#define PARKED(V, ST, SRC) rc = single ? launch(hdr_merge_smem_kernel<V, ST, true, SRC>) : launch(hdr_merge_smem_kernel<V, ST, false, SRC>)
 #define BY_STD(V, SRC)                                                          \
     if (std_mode == kStdNone) { DYN(V, 0, SRC); }                               \
-    else if (std_mode == kStdTensor) { if (fixed) { FIXED(V, 1, SRC) } else { DYN(V, 1, SRC); } } \
-    else { if (fixed) { FIXED(V, 2, SRC) } else { DYN(V, 2, SRC); } }
+    else if (std_mode == kStdTensor) { if (fixed) { FIXED(V, 1, SRC) } else if (parked) { PARKED(V, 1, SRC); } else { DYN(V, 1, SRC); } } \
+    else { if (fixed) { FIXED(V, 2, SRC) } else if (parked) { PARKED(V, 2, SRC); } else { DYN(V, 2, SRC); } }
     if (src == kSrcU8) { BY_STD(4, kSrcU8) }
     else if (src == kSrcU16) { BY_STD(4, kSrcU16) }
     else if (std_mode == kStdNone) {
         if (vec == 4) DYN(4, 0, kSrcF32); else if (vec == 2) DYN(2, 0, kSrcF32); else DYN(1, 0, kSrcF32);
     } else if (std_mode != kStdTensor) {
         return bad(CLAIR_E_MODE, "synthesised std needs integer codes");
+    } else if (parked) {
+        if (vec == 2) rc = single ? launch(hdr_merge_smem_kernel<2, 1, true, kSrcF32>) : launch(hdr_merge_smem_kernel<2, 1, false, kSrcF32>);
+        else rc = single ? launch(hdr_merge_smem_kernel<1, 1, true, kSrcF32>) : launch(hdr_merge_smem_kernel<1, 1, false, kSrcF32>);
     } else if (vec == 4) {
         if (fixed) { FIXED(4, 1, kSrcF32) } else { DYN(4, 1, kSrcF32); }
     } else if (vec == 2) {
@@ -687,6 +786,7 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         if (fixed) { FIXED(1, 1, kSrcF32) } else { DYN(1, 1, kSrcF32); }
     }
 #undef BY_STD
+#undef PARKED
 #undef DYN
 #undef FIXED
 #undef FIXED_NF
