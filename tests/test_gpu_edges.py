@@ -1,0 +1,152 @@
+"""Edge cases on the GPU: channel counts 1..4, table sizes, frame counts from 1 to the 64-frame limit (register,
+shared-memory-parked and float64-sum kernels), odd image sizes, degenerate pixels, limits and error paths, and the
+train_icrf driver loop end to end."""
+import numpy as np
+import pytest
+import torch
+from torch.utils.data import DataLoader
+
+from _helpers import max_abs_over_max, max_rel
+from oracle import c_oracle as corc
+from oracle import clair_oracle as orc
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ct():
+    import clair_torch_b200 as pkg
+    pkg._native.load()
+    return pkg
+
+
+def _merge(ct, val, std, t, theta, gaussian=True, **kw):
+    from clair_torch_b200 import kernels
+    return kernels.hdr_merge_update(kernels.HdrMergeState(), val.to(DEV), None if std is None else std.to(DEV), t,
+                                    None if theta is None else theta.to(DEV), gaussian, True, radiance_dtype=torch.float32, **kw)
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("lut", [16, 256, 1024])
+def test_merge_channel_counts_and_table_sizes(ct, channels, lut):
+    val, std, t = ct.synthetic.make_stack(4, channels, 33, 52, bits=16, seed=channels * 7 + lut)
+    theta = ct.synthetic.reference_curve(channels, lut)
+    rad, sig = _merge(ct, val, std, t, theta)
+    o_rad, o_sig = corc.hdr_merge(val.numpy(), std.numpy(), t, theta.numpy(), True)
+    assert max_rel(rad.cpu().numpy(), o_rad) < 2e-6 and max_rel(sig.cpu().numpy(), o_sig) < 5e-6
+
+
+@pytest.mark.parametrize("n_frames", [1, 2, 8, 9, 13, 27, 40, 41, 64])
+def test_merge_frame_counts(ct, n_frames):
+    """1..8 register kernel, 9..40 shared-memory-parked kernel, 41..64 float64-sum kernel."""
+    val, std, _ = ct.synthetic.make_stack(n_frames, 3, 24, 40, bits=16, seed=n_frames)
+    t = 1e-3 * 1.19 ** np.arange(n_frames)
+    theta = ct.synthetic.reference_curve(3)
+    rad, sig = _merge(ct, val, std, t, theta)
+    o_rad, o_sig = corc.hdr_merge(val.numpy(), std.numpy(), t, theta.numpy(), True)
+    assert max_rel(rad.cpu().numpy(), o_rad) < 2e-6 and max_rel(sig.cpu().numpy(), o_sig) < 5e-6
+
+
+def test_limits_and_bad_arguments(ct):
+    from clair_torch_b200 import kernels
+    val, std, t = ct.synthetic.make_stack(3, 3, 8, 8)
+    theta = ct.synthetic.reference_curve(3)
+    big = torch.zeros((65, 1, 4, 4))
+    with pytest.raises(ValueError, match="limit"):
+        _merge(ct, big, big, np.ones(65), None)
+    with pytest.raises(ValueError, match="limit"):
+        _merge(ct, torch.zeros((2, 9, 4, 4)), torch.zeros((2, 9, 4, 4)), np.ones(2), None)
+    with pytest.raises(ValueError):
+        _merge(ct, val, std, t[:2], theta)                               # exposure count mismatch
+    with pytest.raises(ValueError):
+        _merge(ct, val, std[:, :, :4], t, theta)                         # std shape mismatch
+    with pytest.raises(ValueError):
+        _merge(ct, val, std, t, ct.synthetic.reference_curve(2))          # table rows != channels
+    with pytest.raises(TypeError):
+        _merge(ct, val.double(), std, t, theta)
+    with pytest.raises(ValueError):
+        kernels.pair_stats(val.to(DEV), std.to(DEV), [0, 7], [1, 2], [0.5, 0.5], theta.to(DEV), 0.0, 1.0, True, True)
+
+
+def test_degenerate_pixels(ct):
+    """All-saturated, all-black and out-of-range pixels: finite results that match the oracle; a pixel whose Gaussian
+    weights all underflow gives NaN like the reference's 0/0."""
+    val = torch.tensor([0.0, 1.0, 0.5, -0.2, 1.3, 1e-9, 254.5 / 255]).view(1, 1, 1, 7).repeat(3, 3, 2, 1).contiguous()
+    val[1] = val[1] * 0.5 + 0.25
+    std = torch.full_like(val, 0.01)
+    t = np.array([1e-3, 2e-3, 4e-3])
+    theta = ct.synthetic.reference_curve(3)
+    rad, sig = _merge(ct, val, std, t, theta)
+    o_rad, o_sig = orc.hdr_merge(val.numpy(), std.numpy(), t, theta.numpy(), True)
+    assert torch.isfinite(rad).all() and torch.isfinite(sig).all()
+    assert max_rel(rad.cpu().numpy(), o_rad, 1e-12) < 2e-6 and max_rel(sig.cpu().numpy(), o_sig, 1e-12) < 5e-6
+    far = torch.full((2, 1, 1, 4), 5.0)                                  # exp(-30 * 4.5^2) underflows to 0
+    rad, sig = _merge(ct, far, torch.ones_like(far), np.array([1.0, 2.0]), None)
+    assert torch.isnan(rad).all()
+
+
+def test_pair_kernels_many_pairs_and_odd_sizes(ct):
+    """More pairs than one launch carries (78 > 64), H*W not a multiple of 4 (scalar staging), C = 1 and 4."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.inference.measure_linearity import spatial_statistics
+    from clair_torch_b200.training import linearity_loss_and_table_grad
+    for channels, n, h, w in ((1, 13, 9, 11), (4, 5, 10, 13), (3, 13, 16, 16)):
+        val, std, _ = ct.synthetic.make_stack(n, channels, h, w, bits=16, seed=n + channels)
+        t = 1e-3 * 1.3 ** np.arange(n)
+        theta = ct.synthetic.reference_curve(channels)
+        i, j, r = orc.exposure_pairs(t, 0.0)
+        sums = kernels.pair_stats(val.to(DEV), std.to(DEV), i, j, r, theta.to(DEV), 1 / 255, 254 / 255, True, True)
+        mean, sd, err = spatial_statistics(sums.cpu(), True)
+        o_mean, o_sd, o_err = corc.pair_stats(val.numpy(), std.numpy(), i, j, r, theta.numpy())
+        assert max_rel(mean.numpy(), o_mean) < 2e-6 and max_rel(err.numpy(), o_err) < 2e-6
+        # pairs with a tiny exposure ratio have an almost constant loss (std << mean): the fp32 rounding of each loss
+        # shows in the spread, so the bound is relative to the scale the rounding has (see test_pair_stats_degenerate_spread)
+        assert np.all(np.abs(sd.numpy() - o_sd) <= 1e-5 * o_sd + 2e-8 * o_mean)
+        lin, spatial, grad = linearity_loss_and_table_grad(val.to(DEV), std.to(DEV), i, j, r, theta.to(DEV), 1 / 255, 254 / 255,
+                                                           True, True)
+        o_lin, o_m, o_grad = corc.train_grad(val.numpy(), std.numpy(), i, j, r, theta.numpy())
+        assert max_rel(lin.cpu().numpy(), o_lin) < 2e-6
+        assert max_abs_over_max(grad.cpu().numpy(), o_grad) < 1e-5
+
+
+def test_all_pairs_masked_gives_zero_loss_and_gradient(ct):
+    from clair_torch_b200.training import linearity_loss_and_table_grad
+    val = torch.zeros((3, 3, 8, 8))                                      # every pixel below the validity threshold
+    std = torch.zeros_like(val)
+    t = torch.tensor([1e-3, 2e-3, 4e-3], dtype=torch.float64)
+    i, j, r = ct.common.get_valid_exposure_pairs(t, 0.1)
+    lin, spatial, grad = linearity_loss_and_table_grad(val.to(DEV), std.to(DEV), i, j, r, ct.synthetic.reference_curve(3).to(DEV),
+                                                       1 / 255, 254 / 255, True, True)
+    assert torch.equal(lin, torch.zeros_like(lin)) and torch.equal(spatial, torch.zeros_like(spatial))
+    assert torch.equal(grad, torch.zeros_like(grad))
+
+
+def test_train_icrf_driver_loop(ct):
+    """train_icrf end to end: default per-channel Adam, early stopping bookkeeping, a ReduceLROnPlateau scheduler; the
+    loss goes down on a stack whose true response is a 2.2 gamma when starting from a 2.5 power curve."""
+    from clair_torch_b200.datasets import ExposureStackDataset, custom_collate
+    val, std, t = ct.synthetic.make_stack(6, 3, 64, 96, bits=8, seed=2)
+    loader = DataLoader(ExposureStackDataset(list(val), list(std), list(t)), batch_size=6, collate_fn=custom_collate)
+    from clair_torch_b200.training import linearity_loss_and_table_grad
+    model = ct.ICRFModelDirect(256, 3, initial_power=2.5).to(DEV)
+    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3) for c in range(3)]
+    i, j, r = ct.common.get_valid_exposure_pairs(torch.from_numpy(t), 0.25)
+
+    def objective():
+        return linearity_loss_and_table_grad(val.to(DEV), std.to(DEV), i, j, r, model.icrf.detach(), 1 / 255, 254 / 255, True,
+                                             False, want_grad=False)[0].sum().item()
+
+    before = objective()
+    out = ct.train_icrf(loader, 6, DEV, model, opts, None, use_uncertainty_weighting=False, epochs=40, patience=50,
+                        alpha=10.0, exposure_ratio_threshold=0.25, verbose=False)
+    assert out is model
+    assert objective() < 0.8 * before
+    # schedulers are stepped with the per-channel epoch loss (icrf_training.py:174-176); early stopping ends the run
+    scheds = [torch.optim.lr_scheduler.ReduceLROnPlateau(o, patience=0) for o in opts]
+    ct.train_icrf(loader, 6, DEV, model, opts, scheds, use_uncertainty_weighting=False, epochs=6, patience=2, verbose=False)
+    assert all(o.param_groups[0]["lr"] <= 1e-3 for o in opts)
+    # defaults: optimisers created inside, one epoch
+    ct.train_icrf(loader, 6, DEV, ct.ICRFModelDirect().to(DEV), epochs=2, verbose=False)
+    with pytest.raises(ValueError, match="Mismatched"):
+        ct.train_icrf(loader, 6, DEV, model, opts, [None], epochs=1, verbose=False)
