@@ -12,7 +12,7 @@ import subprocess
 import threading
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "lib", "libclair_b200.so")
+LIB_PATH = os.environ.get("CLAIR_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libclair_b200.so")   # env: kernel experiments
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 ABI_VERSION = 1
