@@ -290,7 +290,26 @@ def secondary_metrics(dev):
     out["linearize_c4_frames"] = {"ms_per_frame": ms5 / 3, "config": "3 frames of 3x4000x6000, f(x) and sigma",
                                   "mpixel_per_s": 3 * 24.0 / (ms5 * 1e-3),
                                   "hbm_frac": 3 * CHANNELS * 24e6 * 16 / (ms5 * 1e-3) / 1e9 / peak}
-    del val, std, one_val, one_std, rad
+    # the same through linearize_dataset_generator from pinned host frames to pinned host results
+    from torch.utils.data import DataLoader
+    from clair_torch_b200.datasets import ExposureStackDataset
+    hv, hs = one_val.cpu().pin_memory(), one_std.cpu().pin_memory()
+    ds = ExposureStackDataset(list(hv), list(hs), list(t[:3]))
+    view_collate = lambda b: (torch.tensor([b[0][0]]), b[0][1].unsqueeze(0), b[0][2].unsqueeze(0),
+                              {"exposure_time": torch.tensor([b[0][3]["exposure_time"]], dtype=torch.float64)})
+    lin_loader = DataLoader(ds, batch_size=1, shuffle=False, collate_fn=view_collate)
+    lin_model = ct.ICRFModelDirect(icrf=theta.clone()).to(dev)
+    for _ in ct.linearize_dataset_generator(lin_loader, dev, lin_model):
+        pass
+    t0 = time.perf_counter()
+    for _ in range(3):
+        for _ in ct.linearize_dataset_generator(lin_loader, dev, lin_model):
+            pass
+    e2e_lin = (time.perf_counter() - t0) / 9 * 1e3
+    out["linearize_c4_frames"]["e2e_ms_per_frame"] = e2e_lin
+    out["linearize_c4_frames"]["e2e_mpixel_per_s"] = 24.0 / (e2e_lin * 1e-3)
+    out["linearize_c4_frames"]["e2e_note"] = "pinned host frame (val+std, 576 MB) in, pinned host lin+sigma (576 MB) out, zero-copy"
+    del val, std, one_val, one_std, rad, hv, hs
     torch.cuda.empty_cache()
     # 8(f) rows at c1 size: dark-field mix pre-pass, flat-field correction, streaming frame statistics
     val, std, t = ct.synthetic.make_stack(N_FRAMES, CHANNELS, HEIGHT, WIDTH, bits=8, seed=99, device=dev)

@@ -34,11 +34,23 @@ def linearize_dataset_generator(dataloader: DataLoader, device, icrf_model: ICRF
     if flatfield_dataset is not None:                     # linearization.py:50-57: one flat field for the whole run
         _, flat_val, flat_std, _ = flatfield_dataset.get_matching_artefact_images([main_dataset.files[0]])
     for index_batch, val_batch, std_batch, meta_batch in dataloader:
-        images, stds = stage_batch(val_batch, std_batch, dev, transforms)
+        plain = dark_field_dataset is None and flat_val is None and not transforms
+        zero_copy = (plain and not val_batch.is_cuda and val_batch.is_pinned() and val_batch.is_contiguous()
+                     and (std_batch is None or (std_batch.is_pinned() and std_batch.is_contiguous())))
+        if zero_copy:
+            images, stds = val_batch, std_batch          # read over PCIe by the kernel itself
+        else:
+            images, stds = stage_batch(val_batch, std_batch, dev, transforms)
         if dark_field_dataset is not None:                # linearization.py:73-91,108-116
             dark_val, dark_std = matching_dark_frames(main_dataset, dark_field_dataset, index_batch, dev)
             if dark_val is not None:
                 images, stds = kernels.dark_field_mix(images, stds, dark_val, dark_std)
+        if plain:
+            # results go straight to page-locked host memory (the reference ends with .cpu(), :132)
+            lin, sigma = kernels.linearize(images, stds, table, device=dev, pinned_out=True)
+            torch.cuda.current_stream(dev).synchronize()
+            yield lin.squeeze(), sigma.squeeze(), meta_batch
+            continue
         lin, sigma = kernels.linearize(images, stds, table)
         if flat_val is not None:                          # linearization.py:118-130: the mean is a constant here
             kernels.flat_field_correct_(lin, sigma, flat_val, flat_std, mean_in_graph=False)

@@ -106,19 +106,29 @@ def icrf_backward_theta(x: torch.Tensor, grad_y: torch.Tensor, channels: int, lu
     return grad
 
 
-def linearize(val: torch.Tensor, std: Optional[torch.Tensor], theta: torch.Tensor, row_base=None):
-    """(f(x), sqrt((f'(x) std)^2)) per image of an (N, C, H, W) stack.  inference/linearization.py:94-106."""
+def linearize(val: torch.Tensor, std: Optional[torch.Tensor], theta: torch.Tensor, row_base=None, device=None,
+              pinned_out: bool = False):
+    """(f(x), sqrt((f'(x) std)^2)) per image of an (N, C, H, W) stack.  inference/linearization.py:94-106.
+
+    With `device`, `val` / `std` may be pinned host tensors (read over PCIe by the kernel); with `pinned_out` the two
+    results are written straight into page-locked host tensors (torch's caching host allocator), which is what
+    linearize_dataset_generator hands to its consumer."""
     lib = _native.load()
-    val = _stack(val, "val_batch")
-    std = None if std is None else _stack(std, "std_batch")
+    val = _stack(val, "val_batch", allow_pinned=device is not None)
+    std = None if std is None else _stack(std, "std_batch", allow_pinned=device is not None)
+    dev = torch.device(device) if device is not None else val.device
     n, c, h, w = val.shape
-    th = _table(theta, val.device, c)
-    lin = torch.empty_like(val)
-    sigma = torch.empty_like(val)
+    th = _table(theta, dev, c)
+    if pinned_out:
+        lin = torch.empty(tuple(val.shape), dtype=_F32, pin_memory=True)
+        sigma = torch.empty(tuple(val.shape), dtype=_F32, pin_memory=True)
+    else:
+        lin = torch.empty(tuple(val.shape), dtype=_F32, device=dev)
+        sigma = torch.empty(tuple(val.shape), dtype=_F32, device=dev)
     keep, rows = _rows(row_base, c)
-    with torch.cuda.device(val.device):
+    with torch.cuda.device(dev):
         rc = lib.clair_linearize(_ptr(val), _ptr(std), _ptr(th), _ptr(lin), _ptr(sigma), n, c, h * w, th.shape[1],
-                                 rows, _stream(val.device))
+                                 rows, _stream(dev))
     _native.check(rc, "clair_linearize")
     return lin, sigma
 
