@@ -220,6 +220,23 @@ def native_ingest_metrics(dev, lib, theta, t_host):
             "e2e_d2h_bytes": 2 * rad_h.numel() * 4}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads (and hence its first-touch pinned buffers) to the CPUs NVML reports as local to
+    the GPU: the end-to-end path streams the stack over PCIe straight from host memory."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def secondary_metrics(dev):
     """BASELINE.json's other single-GPU configs, device-resident, CUDA-event timed: c2 ICRF train steps/s and
     c3 linearity measurement.  Reported under "extra"; the headline metric stays the HDR merge."""
@@ -363,6 +380,7 @@ def main():
     import clair_torch_b200 as ct
     from clair_torch_b200 import kernels
 
+    local_cpus = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -494,7 +512,7 @@ def main():
                          "kernel": "clair::hdr_merge_fixed_kernel<2,5,true,true> (2 px/thread, N=5 in registers, single batch)"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "api": "clair_torch_b200.compute_hdr_image(pinned host batch, host_out=pinned buffers): zero-copy kernel over PCIe"},
+                    "ms_per_step": e2e_ms, "host_cpus_bound": local_cpus, "api": "clair_torch_b200.compute_hdr_image(pinned host batch, host_out=pinned buffers): zero-copy kernel over PCIe"},
             "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line))
