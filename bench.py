@@ -237,6 +237,44 @@ def bind_to_gpu_numa_node(index):
         return 0
 
 
+def dp_training_metrics(dev, rank, world):
+    """c5: data-parallel ICRF training on a 100 MP 16-bit exposure pair, row bands across the ranks, one NCCL sum
+    all-reduce of the (P,C,5) sums and one of the (C,L) gradient per step (strong scaling: the image is fixed)."""
+    import torch
+    import torch.distributed as dist
+    import clair_torch_b200 as ct
+    from clair_torch_b200 import distributed as cd
+    height, width, n_frames = 8192, 12288, 2
+    r0, r1 = cd.row_band(height, rank, world)
+    # every rank synthesises only its own band (seeded per band) — the kernels never see the other rows
+    val, std, _ = ct.synthetic.make_stack(n_frames, CHANNELS, r1 - r0, width, bits=16, seed=5678 + rank, device=dev)
+    exposures = torch.tensor([0.01, 0.02], dtype=torch.float64)
+    rb = cd.band_row_base(CHANNELS, height, width, r0)
+    model = ct.ICRFModelDirect(256, CHANNELS, ct.InterpMode.LINEAR, 2.5).to(dev)
+    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3) for c in range(CHANNELS)]
+    kw = dict(use_relative_linearity_loss=True, use_uncertainty_weighting=False, alpha=10.0, beta=1.0, gamma=1.0, delta=1.0,
+              exposure_ratio_threshold=0.25)
+    step = lambda: cd.train_icrf_step_data_parallel(model, opts, val, std, exposures, rb, **kw)
+    for _ in range(3):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    a.record()
+    for _ in range(reps):
+        step()
+    b.record()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    return {"config": "100.7 MP (8192x12288) 16-bit RGB exposure pair, row bands, NCCL all-reduce of sums and gradient",
+            "ms_per_step": ms, "steps_per_s": 1e3 / ms, "scaling": "strong", "n_gpus": world}
+
+
 def secondary_metrics(dev):
     """BASELINE.json's other single-GPU configs, device-resident, CUDA-event timed: c2 ICRF train steps/s and
     c3 linearity measurement.  Reported under "extra"; the headline metric stays the HDR merge."""
@@ -483,6 +521,11 @@ def main():
     h2d = val_h.numel() * 4 + std_h.numel() * 4
     d2h = rad_h.numel() * 4 + sig_h.numel() * 4
 
+    dp = None
+    if world > 1 and not args.no_extras:
+        del stacks
+        torch.cuda.empty_cache()
+        dp = dp_training_metrics(dev, rank, world)       # collective: every rank takes part
     if rank == 0:
         peak, peak_src = peaks()
         algo_bytes = ALGO_BYTES_PER_PIXEL_FRAME * N_FRAMES * HEIGHT * WIDTH          # per launch = per stack
@@ -495,11 +538,14 @@ def main():
                    "sample": f"20 merges of the full c1 stack ({rows} rows), C/OpenMP oracle port, {dt:.3f} s per merge; "
                              + REFERENCE_NOTE}
         extra = None
+        if world > 1 and dp is not None:
+            extra = {"dp_train_c5": dp}
         if world == 1 and not args.no_extras:
-            del stacks
+            stacks = None
             torch.cuda.empty_cache()
             extra = secondary_metrics(dev)
             extra["native_ingest_c1"] = native_ingest_metrics(dev, lib, theta, t_host)
+            extra["dp_train_c5"] = dp_training_metrics(dev, 0, 1)
         line = {
             "metric": METRIC, "value": value, "unit": "Mpixel*frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -487,13 +487,27 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_smem_kernel(const HdrParams 
             }
         }
         hdr_finish<VEC, true, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
-            float acc = 0.0f;
-            for (int n = 0; n < N; ++n) {
-                const float *col = s_rq + n * (2 * VEC * kBlock);
-                const float g = fmaf(alpha, col[k * kBlock], gamma * col[(VEC + k) * kBlock]);
-                acc = fmaf(g, g, acc);
+            float acc0 = 0.0f, acc1 = 0.0f;
+            const float *col = s_rq + k * kBlock;
+            int n = 0;
+            for (; n + 4 <= N; n += 4) {                      // four frames per trip: eight independent LDS in flight
+                float r[4], q[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    r[j] = col[(n + j) * (2 * VEC * kBlock)];
+                    q[j] = col[(n + j) * (2 * VEC * kBlock) + VEC * kBlock];
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float g = fmaf(alpha, r[j], gamma * q[j]);
+                    if (j & 1) acc1 = fmaf(g, g, acc1); else acc0 = fmaf(g, g, acc0);
+                }
             }
-            return acc;
+            for (; n < N; ++n) {
+                const float g = fmaf(alpha, col[n * (2 * VEC * kBlock)], gamma * col[n * (2 * VEC * kBlock) + VEC * kBlock]);
+                acc0 = fmaf(g, g, acc0);
+            }
+            return acc0 + acc1;
         });
     }
 }
