@@ -20,7 +20,7 @@ for n, h, w in ((5, 17, 23), (3, 16, 20), (9, 9, 14), (41, 6, 8)):
     if (h * w) % 4 == 0:
         codes = torch.round(val * 65535).to(torch.uint16).to(dev)
         kernels.hdr_merge_update(kernels.HdrMergeState(), codes, StdSpec("multiplier", 0.05), t, theta, True, True)
-        kernels.hdr_merge_update(kernels.HdrMergeState(), (codes >> 8).to(torch.uint8), s, t, theta, True, True)
+        kernels.hdr_merge_update(kernels.HdrMergeState(), torch.round(val * 255).to(torch.uint8).to(dev), s, t, theta, True, True)
     kernels.linearize(v, s, theta)
     kernels.icrf_forward(v, theta, ct._native.INTERP_LOOKUP)
     y, d = kernels.icrf_forward(v, theta, ct._native.INTERP_CATMULL, want_derivative=True)

@@ -150,3 +150,57 @@ def test_train_icrf_driver_loop(ct):
     ct.train_icrf(loader, 6, DEV, ct.ICRFModelDirect().to(DEV), epochs=2, verbose=False)
     with pytest.raises(ValueError, match="Mismatched"):
         ct.train_icrf(loader, 6, DEV, model, opts, [None], epochs=1, verbose=False)
+
+
+def test_kernels_do_not_write_outside_their_outputs(ct):
+    """compute-sanitizer is closed on this pool, so out-of-bounds WRITES are looked for with guard bands: every output
+    of the C ABI is carved out of the middle of a sentinel-filled buffer and the guards must survive, on image sizes
+    that exercise the scalar, 2-wide and 4-wide kernels and partially filled tiles."""
+    import ctypes
+    lib = ct._native.load()
+    guard = 4096
+    sentinel = -12345.0
+
+    def carve(numel, dtype=torch.float32):
+        buf = torch.full((numel + 2 * guard,), sentinel, dtype=dtype, device=DEV)
+        return buf, buf[guard:guard + numel]
+
+    def intact(buf, numel):
+        return bool((buf[:guard] == sentinel).all()) and bool((buf[guard + numel:] == sentinel).all())
+
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    stream = torch.cuda.current_stream().cuda_stream
+    for n, h, w in ((5, 17, 23), (3, 16, 20), (9, 9, 14), (4, 33, 2)):
+        val, std, _ = ct.synthetic.make_stack(n, 3, h, w, bits=16, seed=n)
+        v, s = val.to(DEV), std.to(DEV)
+        t = np.ascontiguousarray(1e-3 * 1.2 ** np.arange(n))
+        plane, numel = h * w, 3 * h * w
+        rb, rad = carve(numel)
+        sb, sig = carve(numel)
+        rc = lib.clair_hdr_merge_update(v.data_ptr(), s.data_ptr(), t.ctypes.data_as(ctypes.c_void_p), n, theta.data_ptr(), 3, 256,
+                                        plane, None, 1, None, None, None, 1, 1, rad.data_ptr(), 0, sig.data_ptr(), stream)
+        assert rc == 0
+        lb, lin = carve(n * numel)
+        gb, lsig = carve(n * numel)
+        assert lib.clair_linearize(v.data_ptr(), s.data_ptr(), theta.data_ptr(), lin.data_ptr(), lsig.data_ptr(), n, 3, plane, 256,
+                                   None, stream) == 0
+        mb, mixed = carve(n * numel)
+        eb, seff = carve(n * numel)
+        dark = torch.rand_like(v) * 0.1
+        assert lib.clair_dark_field_mix(v.data_ptr(), s.data_ptr(), dark.data_ptr(), dark.data_ptr(), n, 3, h, w, 0.05, 50.0,
+                                        mixed.data_ptr(), seff.data_ptr(), stream) == 0
+        states = [carve(numel) for _ in range(4)]
+        assert lib.clair_frame_stats_update(v.data_ptr(), None, theta.data_ptr(), n, 3, plane, 256, None, states[0][1].data_ptr(),
+                                            states[1][1].data_ptr(), states[2][1].data_ptr(), states[3][1].data_ptr(), 1, stream) == 0
+        i, j, r = orc.exposure_pairs(t, 0.0)
+        i32, j32 = np.ascontiguousarray(i, dtype=np.int32), np.ascontiguousarray(j, dtype=np.int32)
+        p = len(i)
+        sums_b, sums = carve(p * 3 * 5, torch.float64)
+        if n <= 16:
+            assert lib.clair_pair_stats(v.data_ptr(), s.data_ptr(), n, 3, plane, i32.ctypes.data_as(ctypes.c_void_p),
+                                        j32.ctypes.data_as(ctypes.c_void_p), r.ctypes.data_as(ctypes.c_void_p), p, theta.data_ptr(), 256,
+                                        None, 1 / 255, 254 / 255, 1, 1, sums.data_ptr(), stream) == 0
+        torch.cuda.synchronize()
+        assert intact(rb, numel) and intact(sb, numel) and intact(lb, n * numel) and intact(gb, n * numel)
+        assert intact(mb, n * numel) and intact(eb, n * numel) and all(intact(b, numel) for b, _ in states)
+        assert intact(sums_b, p * 3 * 5)
