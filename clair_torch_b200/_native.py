@@ -15,7 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CLAIR_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libclair_b200.so")   # env: kernel experiments
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_FRAMES = 64
 MAX_CHANNELS = 8
 MAX_LUT = 1024
@@ -24,8 +24,21 @@ INTERP_LOOKUP = 1
 INTERP_LINEAR = 2
 INTERP_CATMULL = 3
 
-# every symbol include/clair_b200.h declares, with its ctypes prototype
 _c = ctypes
+
+
+class MergeDesc(ctypes.Structure):
+    """clair_merge_desc of include/clair_b200.h (field order and types must match the header)."""
+    _fields_ = [("struct_bytes", _c.c_uint32), ("code_bytes", _c.c_int32), ("val_dev", _c.c_void_p), ("std_dev", _c.c_void_p),
+                ("std_mode", _c.c_int32), ("std_value", _c.c_float), ("code_max", _c.c_float), ("n_frames", _c.c_int32),
+                ("exposure_host", _c.c_void_p), ("theta_dev", _c.c_void_p), ("n_channels", _c.c_int32), ("lut_size", _c.c_int32),
+                ("interp_mode", _c.c_int32), ("gaussian_weights", _c.c_int32), ("plane", _c.c_int64), ("plane_stride", _c.c_int64),
+                ("curve_row_base_host", _c.c_void_p), ("mean_state_dev", _c.c_void_p), ("wsum_state_dev", _c.c_void_p),
+                ("var_state_dev", _c.c_void_p), ("is_first", _c.c_int32), ("is_final", _c.c_int32), ("radiance_f64", _c.c_int32),
+                ("reserved", _c.c_int32), ("radiance_dev", _c.c_void_p), ("sigma_dev", _c.c_void_p)]
+
+
+# every symbol include/clair_b200.h declares, with its ctypes prototype
 _PROTOTYPES = {
     "clair_abi_version": (_c.c_int, []),
     "clair_last_error": (_c.c_char_p, []),
@@ -37,7 +50,7 @@ _PROTOTYPES = {
     "clair_icrf_backward_theta": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64,
                                              _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "clair_linearize": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
-                                   _c.c_int, _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p]),
+                                   _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "clair_hdr_merge_update": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int,
                                           _c.c_int, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,
                                           _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
@@ -46,6 +59,8 @@ _PROTOTYPES = {
                                          _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_int,
                                          _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_int,
                                          _c.c_void_p, _c.c_void_p]),
+    "clair_hdr_merge": (_c.c_int, [_c.POINTER(MergeDesc), _c.c_void_p]),
+    "clair_hdr_merge_staged": (_c.c_int, [_c.POINTER(MergeDesc), _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "clair_dark_field_mix": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
                                         _c.c_int, _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "clair_flat_field_correct": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,

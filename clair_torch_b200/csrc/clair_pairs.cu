@@ -554,6 +554,19 @@ __global__ void __launch_bounds__(256) icrf_catmull_backward_kernel(const float 
     for (int k = 0; k < 4; ++k) atomicAdd(copy + min(max(x0 + k - 1, 0), L - 1), g * w[k]);
 }
 
+// LOOKUP table gradient (models/base.py:145-158 under autograd: an index gather): one tap, the true channel row
+__global__ void __launch_bounds__(256) icrf_lookup_backward_kernel(const float *__restrict__ x, const float *__restrict__ gy,
+                                                                   float *hist, int64_t plane, int C, int L) {
+    const int64_t pix = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (pix >= plane) return;
+    const int slab = blockIdx.y, c = slab % C;
+    const int64_t o = static_cast<int64_t>(slab) * plane + pix;
+    const float g = __ldcs(gy + o);
+    if (g == 0.0f) return;
+    float *copy = hist + static_cast<int64_t>((blockIdx.x + blockIdx.y) % kGradCopies) * (2 * C * (L + 2)) + c * (L + 2);
+    atomicAdd(copy + icrf_lookup_index(__ldcs(x + o), static_cast<float>(L - 1)), g);
+}
+
 // grad[u][k] += sum over copies of A[u][k] + B[u][k+1], in float64; one warp per table entry
 __global__ void __launch_bounds__(256) grad_finalize_kernel(const float *__restrict__ hist, double *grad, int C, int L) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -893,8 +906,8 @@ extern "C" int clair_icrf_backward_theta(const float *x_dev, const float *grad_y
                                          const int32_t *curve_row_base_host, void *workspace_dev, size_t workspace_bytes,
                                          void *stream) {
     if (!x_dev || !grad_y_dev || !grad_theta_dev || !workspace_dev) return fail(CLAIR_E_ARG, "clair_icrf_backward_theta: null buffer");
-    if (interp_mode != CLAIR_INTERP_LINEAR && interp_mode != CLAIR_INTERP_CATMULL)
-        return fail(CLAIR_E_MODE, "clair_icrf_backward_theta: interp_mode must be CLAIR_INTERP_LINEAR or CLAIR_INTERP_CATMULL");
+    if (interp_mode != CLAIR_INTERP_LINEAR && interp_mode != CLAIR_INTERP_CATMULL && interp_mode != CLAIR_INTERP_LOOKUP)
+        return fail(CLAIR_E_MODE, "clair_icrf_backward_theta: interp_mode must be CLAIR_INTERP_LOOKUP, _LINEAR or _CATMULL");
     if (int rc = check_geometry("clair_icrf_backward_theta", n_frames, n_channels, plane, lut_size, false)) return rc;
     const size_t need = clair_grad_workspace_bytes(n_channels, lut_size);
     if (workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace_dev) % 16 != 0)
@@ -909,6 +922,9 @@ extern "C" int clair_icrf_backward_theta(const float *x_dev, const float *grad_y
     if (interp_mode == CLAIR_INTERP_CATMULL)
         icrf_catmull_backward_kernel<<<grid, 256, 0, s>>>(x_dev, grad_y_dev, static_cast<float *>(workspace_dev), plane,
                                                           n_channels, lut_size, rows);
+    else if (interp_mode == CLAIR_INTERP_LOOKUP)
+        icrf_lookup_backward_kernel<<<grid, 256, 0, s>>>(x_dev, grad_y_dev, static_cast<float *>(workspace_dev), plane,
+                                                         n_channels, lut_size);
     else
         icrf_backward_theta_kernel<<<grid, 256, 0, s>>>(x_dev, grad_y_dev, static_cast<float *>(workspace_dev), plane, n_channels,
                                                         lut_size, rows);

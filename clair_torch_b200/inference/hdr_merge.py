@@ -6,14 +6,14 @@ from torch.utils.data import DataLoader
 
 from .. import kernels
 from ..models.base import ICRFModelBase
-from ._common import (as_device, check_artefact_dataset, linear_table, matching_dark_frames, normalise_transforms,
+from ._common import (as_device, check_artefact_dataset, matching_dark_frames, model_table, normalise_transforms,
                       stage_batch)
 
 
 def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFModelBase] = None,
                       weight_fn: Optional[Callable] = None, flat_field_dataset=None, gpu_transforms=None,
                       dark_field_dataset=None, *, radiance_dtype: Optional[torch.dtype] = None, host_out=None,
-                      code_max: Optional[float] = None):
+                      code_max: Optional[float] = None, staged: Optional[bool] = None):
     """Exposure-weighted HDR merge of a stationary exposure stack with first-order uncertainty.
 
     Each DataLoader batch goes through ONE fused kernel (ICRF evaluation, Gaussian weights, weighted running mean
@@ -24,10 +24,16 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
     `radiance_dtype` defaults to the dtype the reference returns (float64, because the collated exposure times
     are float64 — SURVEY.md Q6); pass torch.float32 to halve the output traffic.
 
-    Host batches that are page-locked (DataLoader(pin_memory=True) or pre-pinned tensors) are read by the kernel
-    directly over PCIe — each input element is needed exactly once, so no staging copy is made; pageable batches
-    are copied to the device first like the reference does.  `host_out=(radiance, sigma)`, two pinned (C,H,W) host
-    tensors, makes the kernel write the results straight to host memory (they are then what is returned).
+    Host batches that are page-locked (DataLoader(pin_memory=True) or pre-pinned tensors) are streamed band by band:
+    the copy engine moves the next band of every frame to the device while the kernel merges the current one
+    (`staged=False`: the kernel reads the host memory itself over PCIe instead); pageable batches are copied to the
+    device first like the reference does.  `host_out=(radiance, sigma)`, two pinned (C,H,W) host tensors, makes the
+    kernel write the results straight to host memory (they are then what is returned).
+
+    Models in any InterpMode are accepted: LINEAR (the reference default) runs the fused fast kernels, LOOKUP and
+    CATMULL an all-modes kernel.  As in the reference, a LOOKUP model has no derivative with respect to the image, so
+    with std images its uncertainty comes from the weights alone, and without `weight_fn` there is nothing to
+    differentiate: the reference's autograd call raises there and so does this function (RuntimeError).
 
     Integer ingest: batches may carry the raw uint8 / uint16 camera codes instead of
     normalised fp32 images; the kernel then performs the reference's CastTo(float32) + Normalize(max_val=code_max,
@@ -44,7 +50,7 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
     check_artefact_dataset("dark_field_dataset", dark_field_dataset)
     main_dataset = dataloader.dataset
     transforms = normalise_transforms(gpu_transforms)
-    table = linear_table(icrf_model, dev)
+    table, interp_mode = model_table(icrf_model, dev)
 
     state = kernels.HdrMergeState()
     result = None
@@ -71,6 +77,10 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
             dark_val, dark_std = matching_dark_frames(main_dataset, dark_field_dataset, index_batch, dev)
             if dark_val is not None:
                 images, stds = kernels.dark_field_mix(images, stds if torch.is_tensor(stds) else None, dark_val, dark_std)
+        if table is not None and interp_mode == 1 and stds is not None and weight_fn is None:
+            # hdr_merge.py:107-112: autograd.grad of a mean that does not depend on the images
+            raise RuntimeError("a LOOKUP model without weight_fn leaves the merged image independent of the input images: "
+                               "there is no gradient to propagate the std images through (the reference raises here too)")
         exposures = meta_batch["exposure_time"]
         out_dtype = radiance_dtype
         if out_dtype is None:
@@ -79,7 +89,8 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
         result = kernels.hdr_merge_update(state, images, stds, exposures, table, weight_fn is not None,
                                           is_final=upcoming is None, radiance_dtype=out_dtype, device=dev,
                                           host_out=host_out if (upcoming is None and flat_field_dataset is None) else None,
-                                          code_max=code_max)
+                                          code_max=code_max, interp_mode=interp_mode,
+                                          staged=staged if not images.is_cuda else None)
         current = upcoming
     if result is None:
         raise ValueError("the dataloader yielded no batches")

@@ -6,7 +6,7 @@ from torch.utils.data import DataLoader
 
 from .. import kernels
 from ..models.base import ICRFModelBase
-from ._common import (as_device, check_artefact_dataset, linear_table, matching_dark_frames, normalise_transforms,
+from ._common import (as_device, check_artefact_dataset, matching_dark_frames, model_table, normalise_transforms,
                       stage_batch)
 
 
@@ -29,7 +29,7 @@ def linearize_dataset_generator(dataloader: DataLoader, device, icrf_model: ICRF
     check_artefact_dataset("dark_field_dataset", dark_field_dataset)
     main_dataset = dataloader.dataset
     transforms = normalise_transforms(gpu_transforms)
-    table = linear_table(icrf_model, dev)
+    table, interp_mode = model_table(icrf_model, dev)
     flat_val = flat_std = None
     if flatfield_dataset is not None:                     # linearization.py:50-57: one flat field for the whole run
         _, flat_val, flat_std, _ = flatfield_dataset.get_matching_artefact_images([main_dataset.files[0]])
@@ -47,11 +47,11 @@ def linearize_dataset_generator(dataloader: DataLoader, device, icrf_model: ICRF
                 images, stds = kernels.dark_field_mix(images, stds, dark_val, dark_std)
         if plain:
             # results go straight to page-locked host memory (the reference ends with .cpu(), :132)
-            lin, sigma = kernels.linearize(images, stds, table, device=dev, pinned_out=True)
+            lin, sigma = kernels.linearize(images, stds, table, device=dev, pinned_out=True, interp_mode=interp_mode)
             torch.cuda.current_stream(dev).synchronize()
             yield lin.squeeze(), sigma.squeeze(), meta_batch
             continue
-        lin, sigma = kernels.linearize(images, stds, table)
+        lin, sigma = kernels.linearize(images, stds, table, interp_mode=interp_mode)
         if flat_val is not None:                          # linearization.py:118-130: the mean is a constant here
             kernels.flat_field_correct_(lin, sigma, flat_val, flat_std, mean_in_graph=False)
         yield lin.squeeze().cpu(), sigma.squeeze().cpu(), meta_batch

@@ -25,6 +25,18 @@ def _stream(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+_copy_streams: dict = {}
+
+
+def _copy_stream(device: torch.device) -> int:
+    """A per-device side stream for the host-to-device legs of the staged (copy / compute overlapped) entry points."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _copy_streams.get(key)
+    if st is None:
+        st = _copy_streams[key] = torch.cuda.Stream(device=device)
+    return st.cuda_stream
+
+
 def _stack(t: torch.Tensor, name: str, allow_pinned: bool = False) -> torch.Tensor:
     """An (N, C, H, W) fp32 CUDA stack, made contiguous (MissingStdMode.CONSTANT hands over stride-0 views).
     With `allow_pinned`, a contiguous page-locked HOST tensor is accepted as well: the kernel then reads it over PCIe
@@ -107,13 +119,17 @@ def icrf_backward_theta(x: torch.Tensor, grad_y: torch.Tensor, channels: int, lu
 
 
 def linearize(val: torch.Tensor, std: Optional[torch.Tensor], theta: torch.Tensor, row_base=None, device=None,
-              pinned_out: bool = False):
+              pinned_out: bool = False, interp_mode: int = _native.INTERP_LINEAR):
     """(f(x), sqrt((f'(x) std)^2)) per image of an (N, C, H, W) stack.  inference/linearization.py:94-106.
 
     With `device`, `val` / `std` may be pinned host tensors (read over PCIe by the kernel); with `pinned_out` the two
     results are written straight into page-locked host tensors (torch's caching host allocator), which is what
     linearize_dataset_generator hands to its consumer."""
     lib = _native.load()
+    if interp_mode == _native.INTERP_LOOKUP and std is not None:
+        # linearization.py:100-105: autograd.grad of an output that does not depend on the image
+        raise RuntimeError("a LOOKUP model has no derivative with respect to the image: std images cannot be propagated "
+                           "(the reference raises here too)")
     val = _stack(val, "val_batch", allow_pinned=device is not None)
     std = None if std is None else _stack(std, "std_batch", allow_pinned=device is not None)
     dev = torch.device(device) if device is not None else val.device
@@ -128,7 +144,7 @@ def linearize(val: torch.Tensor, std: Optional[torch.Tensor], theta: torch.Tenso
     keep, rows = _rows(row_base, c)
     with torch.cuda.device(dev):
         rc = lib.clair_linearize(_ptr(val), _ptr(std), _ptr(th), _ptr(lin), _ptr(sigma), n, c, h * w, th.shape[1],
-                                 rows, _stream(dev))
+                                 int(interp_mode), rows, _stream(dev))
     _native.check(rc, "clair_linearize")
     return lin, sigma
 
@@ -165,12 +181,17 @@ def _code_stack(t: torch.Tensor, allow_pinned: bool) -> torch.Tensor:
 
 def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
                      theta: Optional[torch.Tensor], gaussian_weights: bool, is_final: bool,
-                     radiance_dtype: torch.dtype = _F64, row_base=None, device=None, host_out=None, code_max=None):
+                     radiance_dtype: torch.dtype = _F64, row_base=None, device=None, host_out=None, code_max=None,
+                     interp_mode: int = _native.INTERP_LINEAR, staged: Optional[bool] = None, bands: int = 16):
     """One batch of compute_hdr_image (inference/hdr_merge.py:95-128).  Returns (radiance, sigma) when
     `is_final`, else None.  `exposure` is the collated float64 'exposure_time' (host tensor, array or list).
 
-    `val` / `std` may be pinned host tensors (zero-copy: `device` then names the GPU that runs the kernel), and
+    `val` / `std` may be pinned host tensors (`device` then names the GPU that runs the kernel), and
     `host_out=(radiance, sigma)` pinned host buffers make the kernel write its results straight to host memory.
+    Host stacks are `staged` by default: the copy engine streams bands of the planes into device buffers while the kernel
+    merges the previous band (clair_hdr_merge_staged); `staged=False` lets the kernel read the host memory itself (zero-copy).
+
+    `interp_mode`: the model's InterpMode (LINEAR: fused fast kernels; LOOKUP / CATMULL: the all-modes kernel).
 
     Integer ingest: `val` may hold raw uint8 / uint16 codes; the kernel then applies the reference's
     CastTo(float32) + Normalize(max_val=code_max, min_val=0) itself (code_max defaults to 255 / 65535), and `std` may be
@@ -234,17 +255,38 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
             if has_std:
                 sigma = torch.empty((c, h, w), dtype=_F32, device=dev)
     keep, rows = _rows(row_base, c)
-    tail = (t.ctypes.data_as(ctypes.c_void_p), n, _ptr(th), c, lut, h * w, rows, int(bool(gaussian_weights)),
-            _ptr(state.mean), _ptr(state.wsum), _ptr(state.var), int(is_first), int(is_final), _ptr(radiance),
-            int(radiance_dtype == _F64), _ptr(sigma), _stream(dev))
+    desc = _native.MergeDesc()
+    desc.struct_bytes = ctypes.sizeof(_native.MergeDesc)
+    desc.code_bytes, desc.code_max = 0, 1.0
+    if codes:
+        desc.code_bytes, default_max = _CODE_DTYPES[val.dtype]
+        desc.code_max = float(default_max if code_max is None else code_max)
+    desc.std_mode, desc.std_value = std_mode, std_value
+    desc.n_frames, desc.exposure_host = n, t.ctypes.data
+    desc.theta_dev, desc.n_channels, desc.lut_size, desc.interp_mode = _ptr(th), c, lut, int(interp_mode)
+    desc.gaussian_weights, desc.plane, desc.plane_stride = int(bool(gaussian_weights)), h * w, 0
+    desc.curve_row_base_host = keep.ctypes.data if keep is not None else None
+    desc.mean_state_dev, desc.wsum_state_dev, desc.var_state_dev = _ptr(state.mean), _ptr(state.wsum), _ptr(state.var)
+    desc.is_first, desc.is_final, desc.radiance_f64 = int(is_first), int(is_final), int(radiance_dtype == _F64)
+    desc.radiance_dev, desc.sigma_dev = _ptr(radiance), _ptr(sigma)
+    on_host = not val.is_cuda
+    if staged is None:
+        staged = on_host
+    if staged and not on_host:
+        raise ValueError("staged=True is for pinned host stacks")
     with torch.cuda.device(dev):
-        if codes:
-            code_bytes, default_max = _CODE_DTYPES[val.dtype]
-            rc = lib.clair_hdr_merge_codes(_ptr(val), code_bytes, float(default_max if code_max is None else code_max),
-                                           _ptr(std), std_mode, std_value, *tail)
+        if staged:
+            stage_val = torch.empty(val.shape, dtype=val.dtype, device=dev)
+            stage_std = torch.empty(std.shape, dtype=_F32, device=dev) if std is not None else None
+            desc.val_dev, desc.std_dev = _ptr(stage_val), _ptr(stage_std)
+            rc = lib.clair_hdr_merge_staged(ctypes.byref(desc), _ptr(val), _ptr(std), int(bands), _copy_stream(dev),
+                                            _stream(dev))
+            what = "clair_hdr_merge_staged"
         else:
-            rc = lib.clair_hdr_merge_update(_ptr(val), _ptr(std), *tail)
-    _native.check(rc, "clair_hdr_merge_codes" if codes else "clair_hdr_merge_update")
+            desc.val_dev, desc.std_dev = _ptr(val), _ptr(std)
+            rc = lib.clair_hdr_merge(ctypes.byref(desc), _stream(dev))
+            what = "clair_hdr_merge"
+    _native.check(rc, what)
     state.batches += 1
     return (radiance, sigma) if is_final else None
 

@@ -12,11 +12,15 @@ from ..common.enums import InterpMode
 
 class _TableFn(torch.autograd.Function):
     """f = table interpolation (LINEAR models/base.py:160-182, CATMULL :184-226) with both of its autograd edges:
-    d/d image = f'(x) (elementwise) and d/d table = tap scatter (the index_put of :176 / :219)."""
+    d/d image = f'(x) (elementwise) and d/d table = tap scatter (the index_put of :176 / :219).  LOOKUP (:138-158) is a
+    gather: it has the table edge only (callers hand it a detached image)."""
 
     @staticmethod
     def forward(ctx, image, table, interp_mode):
-        y, dydx = kernels.icrf_forward(image, table, interp_mode, want_derivative=True)
+        if interp_mode == _native.INTERP_LOOKUP:
+            y, dydx = kernels.icrf_forward(image, table, interp_mode), None
+        else:
+            y, dydx = kernels.icrf_forward(image, table, interp_mode, want_derivative=True)
         ctx.save_for_backward(image.detach(), dydx)
         ctx.table_shape = tuple(table.shape)
         ctx.table_dtype = table.dtype
@@ -27,7 +31,7 @@ class _TableFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         image, dydx = ctx.saved_tensors
         g_image = g_table = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and dydx is not None:
             g_image = grad_out * dydx
         if ctx.needs_input_grad[1]:
             c, lut = ctx.table_shape
@@ -83,7 +87,7 @@ class ICRFModelBase(nn.Module, ABC):
         if self.interpolation_mode is InterpMode.LINEAR:
             return _TableFn.apply(image, self._icrf, _native.INTERP_LINEAR)
         if self.interpolation_mode is InterpMode.LOOKUP:
-            return kernels.icrf_forward(image, self._icrf, _native.INTERP_LOOKUP)
+            return _TableFn.apply(image.detach(), self._icrf, _native.INTERP_LOOKUP)
         # the reference's own CATMULL forward only runs on the CPU (models/base.py:218 builds arange without a device)
         return _TableFn.apply(image, self._icrf, _native.INTERP_CATMULL)
 

@@ -42,6 +42,33 @@ def linearity_loss_and_table_grad(images, stds, i_idx, j_idx, ratio_pairs, table
     return linearity_loss, spatial, grad
 
 
+def _composed_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, relative, unc_weighting, alpha, beta,
+                         gamma, delta, lo, hi):
+    """LOOKUP / CATMULL models: the reference's step (icrf_training.py:105-156) through autograd, with the model's
+    forward, derivative and table-gradient kernels underneath and the pair algebra as torch ops (see
+    inference.measure_linearity.composed_linearity_terms).  Off the measured path: the reference default is LINEAR."""
+    from ..inference.measure_linearity import composed_linearity_terms
+    from .losses import (compute_endpoint_penalty, compute_monotonicity_penalty, compute_range_penalty,
+                         compute_smoothness_penalty)
+    curve = icrf_model.icrf
+    with torch.enable_grad():
+        spatial, _, _ = composed_linearity_terms(icrf_model, images, stds, i_idx, j_idx, ratio_pairs, lo, hi, relative,
+                                                 unc_weighting, create_graph=True)
+        linearity_loss = torch.sqrt((spatial ** 2).sum(dim=0))
+        loss = (linearity_loss + alpha * compute_monotonicity_penalty(curve, per_channel=True)
+                + beta * compute_range_penalty(curve, per_channel=True)
+                + gamma * compute_endpoint_penalty(curve, per_channel=True)
+                + delta * compute_smoothness_penalty(curve, per_channel=True))
+        if curve.requires_grad:
+            loss.sum().backward()            # the C backward() calls of :148-149 accumulate exactly this
+    for optimizer in optimizers:
+        optimizer.step()
+    icrf_model.update_icrf()
+    if len(optimizers) == 1:
+        loss = torch.sum(loss)
+    return loss.detach()
+
+
 def train_icrf_step(icrf_model: ICRFModelBase, optimizers: list[Optimizer], images: torch.Tensor,
                     stds: Optional[torch.Tensor], exposures: torch.Tensor, *, use_relative_linearity_loss=True,
                     use_uncertainty_weighting=True, alpha=1.0, beta=1.0, gamma=1.0, delta=1.0,
@@ -53,11 +80,15 @@ def train_icrf_step(icrf_model: ICRFModelBase, optimizers: list[Optimizer], imag
     Launch sequence: pair means -> upstream factors -> table gradient (+ finalize) -> curve penalties (value and
     gradient) -> one autograd edge from the table to the model parameters -> optimisers -> update_icrf.
     """
-    if icrf_model.interpolation_mode is not InterpMode.LINEAR:
-        raise NotImplementedError("train_icrf on B200 supports InterpMode.LINEAR (the reference default)")
     i_idx, j_idx, ratio_pairs = get_valid_exposure_pairs(exposures, exposure_ratio_threshold)
     for optimizer in optimizers:
         optimizer.zero_grad()
+    if icrf_model.interpolation_mode is not InterpMode.LINEAR:
+        if row_base is not None or reduce_fn is not None:
+            raise NotImplementedError("row-band sharded training uses the fused kernels: InterpMode.LINEAR only")
+        return _composed_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs,
+                                    use_relative_linearity_loss, use_uncertainty_weighting, alpha, beta, gamma, delta,
+                                    lower_valid_threshold, upper_valid_threshold)
     curve = icrf_model.icrf                                        # (C, L); a function of the parameters after update_icrf
     table = curve.detach()
     connected = curve.requires_grad                                # False on the very first step (SURVEY.md Q5)

@@ -37,7 +37,7 @@ extern "C" {
 #define CLAIR_API
 #endif
 
-#define CLAIR_ABI_VERSION 1
+#define CLAIR_ABI_VERSION 2
 #define CLAIR_MAX_FRAMES 64     /* exposure frames per batch (exposure times travel as kernel arguments) */
 #define CLAIR_MAX_CHANNELS 8
 #define CLAIR_MAX_LUT 1024      /* ICRF samples per channel (reference default 256) */
@@ -75,7 +75,8 @@ CLAIR_API int clair_icrf_forward(const float *x_dev, const float *theta_dev, flo
 /*
  * Back-propagation of clair_icrf_forward to the table: grad_theta[u, x0] += g*(1-w), grad_theta[u, x1] += g*w
  * (the index_put of models/base.py:176 under autograd; four taps at :219 for CATMULL).  grad_theta_dev is (C, L)
- * float64 and is ACCUMULATED into (zero it first).  interp_mode: CLAIR_INTERP_LINEAR or CLAIR_INTERP_CATMULL.
+ * float64 and is ACCUMULATED into (zero it first).  interp_mode: CLAIR_INTERP_LINEAR, CLAIR_INTERP_CATMULL or
+ * CLAIR_INTERP_LOOKUP (one tap with weight 1 in the true channel row: the gather of models/base.py:158).
  */
 CLAIR_API int clair_icrf_backward_theta(const float *x_dev, const float *grad_y_dev, double *grad_theta_dev,
                               int n_frames, int n_channels, int64_t plane, int lut_size, int interp_mode,
@@ -89,10 +90,12 @@ CLAIR_API size_t clair_grad_workspace_bytes(int n_channels, int lut_size);
 /*
  * Linearisation of single images with uncertainty — replaces the core of linearize_dataset_generator
  * (inference/linearization.py:94-106,132): lin = f(x), sigma = sqrt((f'(x) * std)^2); sigma = 0 when
- * std_dev is NULL (:97).  Inputs are (n_frames, C, plane); each frame is an independent image.
+ * std_dev is NULL (:97).  Inputs are (n_frames, C, plane); each frame is an independent image.  interp_mode is the
+ * model's InterpMode; CLAIR_INTERP_LOOKUP has no derivative, so std_dev must be NULL with it (the reference's
+ * autograd call raises in that combination).
  */
 CLAIR_API int clair_linearize(const float *val_dev, const float *std_dev, const float *theta_dev, float *lin_dev,
-                    float *sigma_dev, int n_frames, int n_channels, int64_t plane, int lut_size,
+                    float *sigma_dev, int n_frames, int n_channels, int64_t plane, int lut_size, int interp_mode,
                     const int32_t *curve_row_base_host, void *stream);
 
 /*
@@ -103,7 +106,8 @@ CLAIR_API int clair_linearize(const float *val_dev, const float *std_dev, const 
  *   val_dev, std_dev      (n_frames, C, plane) fp32, frames sorted by ascending exposure; std_dev may be NULL
  *                         (then no variance is produced)
  *   exposure_host         n_frames exposure times in seconds (float64, the collated 'exposure_time')
- *   theta_dev             (C, lut_size) ICRF table, LINEAR mode; NULL = identity (icrf_model=None, :99-100)
+ *   theta_dev             (C, lut_size) ICRF table, evaluated in LINEAR mode (other modes: clair_hdr_merge below);
+ *                         NULL = identity (icrf_model=None, :99-100)
  *   gaussian_weights      1: w = exp(-30 (x-0.5)^2) (:95 with weight_fn != None); 0: w = 1
  *   mean_state_dev        (C, plane) float64   running weighted mean      } read unless is_first,
  *   wsum_state_dev        (C, plane) float32   running sum of weights     } written unless is_final;
@@ -142,6 +146,62 @@ CLAIR_API int clair_hdr_merge_codes(const void *codes_dev, int code_bytes, float
                           int gaussian_weights, double *mean_state_dev, float *wsum_state_dev, float *var_state_dev,
                           int is_first, int is_final, void *radiance_dev, int radiance_f64, float *sigma_dev,
                           void *stream);
+
+/*
+ * Descriptor form of the two entry points above, with the two options they do not carry:
+ *   interp_mode    CLAIR_INTERP_LINEAR (fused fast kernels), CLAIR_INTERP_LOOKUP (models/base.py:138-158: nearest sample of
+ *                  the true channel row, no derivative: the uncertainty is the weight-derivative term only) or
+ *                  CLAIR_INTERP_CATMULL (models/base.py:184-226) — ICRFModelBase.interpolation_mode of the model
+ *                  compute_hdr_image was given (inference/hdr_merge.py:99-100)
+ *   plane_stride   elements between consecutive channel planes in EVERY buffer (inputs, state, outputs); 0 = plane.
+ *                  With plane_stride > plane the call processes `plane` pixels of larger planes (a band of rows of a
+ *                  frame): all pointers address the band's first pixel and curve_row_base_host[c] must be
+ *                  (c * plane_stride + first_pixel) mod C.
+ *   code_bytes     0: val_dev is fp32 and std_dev (may be NULL) its std, std_mode ignored;
+ *                  1 / 2: val_dev holds uint8 / uint16 codes, see clair_hdr_merge_codes
+ * struct_bytes must be sizeof(clair_merge_desc); all other fields as the arguments of clair_hdr_merge_update.
+ */
+typedef struct clair_merge_desc {
+    uint32_t struct_bytes;
+    int32_t code_bytes;
+    const void *val_dev;
+    const float *std_dev;
+    int32_t std_mode;
+    float std_value;
+    float code_max;
+    int32_t n_frames;
+    const double *exposure_host;
+    const float *theta_dev;
+    int32_t n_channels;
+    int32_t lut_size;
+    int32_t interp_mode;
+    int32_t gaussian_weights;
+    int64_t plane;
+    int64_t plane_stride;
+    const int32_t *curve_row_base_host;
+    double *mean_state_dev;
+    float *wsum_state_dev;
+    float *var_state_dev;
+    int32_t is_first;
+    int32_t is_final;
+    int32_t radiance_f64;
+    int32_t reserved;
+    void *radiance_dev;
+    float *sigma_dev;
+} clair_merge_desc;
+
+CLAIR_API int clair_hdr_merge(const clair_merge_desc *desc, void *stream);
+
+/*
+ * The same merge for a stack that lives in page-locked HOST memory (the collated DataLoader batch of
+ * inference/hdr_merge.py:61-66 before its `.to(device)`): val_host / std_host are (n_frames, C, plane) like the device
+ * form; desc->val_dev / desc->std_dev name device STAGING buffers of the same size.  The planes are cut into n_bands
+ * bands of pixels; the copy engine moves band b+1 (cudaMemcpy2DAsync on copy_stream) while the kernel merges band b on
+ * `stream`, so the call costs the PCIe transfer plus one band's kernel.  Outputs and running state (desc->radiance_dev,
+ * sigma_dev, *_state_dev) may be device or page-locked host memory.  copy_stream must be a different stream.
+ */
+CLAIR_API int clair_hdr_merge_staged(const clair_merge_desc *desc, const void *val_host, const float *std_host, int n_bands,
+                           void *copy_stream, void *stream);
 
 /*
  * Dark-field correction pre-pass — SURVEY.md §8(f) rank 1.  Replaces conditional_gaussian_blur(images, dark, 0.05, 3,

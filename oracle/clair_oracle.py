@@ -115,6 +115,31 @@ def icrf_lookup(x, theta):
     return theta[chan, idx], idx
 
 
+def icrf_eval(x, theta, mode="linear", flat_offset=0):
+    """ICRFModelBase.forward in any of the three modes plus the derivative autograd hands back for d f / d x.
+
+    Returns dict(f32, fp (float64), taps [index arrays], weights [float64 arrays], rows): `taps` / `weights` are what the
+    backward pass scatters the upstream gradient to (two for LINEAR, four for CATMULL, one with weight 1 for LOOKUP,
+    whose image edge does not exist: fp = 0).
+    """
+    if mode == "linear":
+        f32, fp, x0, rows = icrf_linear(x, theta, flat_offset)
+        l = np.asarray(theta).shape[1]
+        xs = np.minimum(np.maximum(np.asarray(x, dtype=F32) * F32(l - 1), F32(0)), F32(l - 1))
+        w = (xs - x0.astype(F32)).astype(F64)
+        return {"f32": f32, "fp": fp.astype(F64), "taps": [x0, np.minimum(x0 + 1, l - 1)], "weights": [1.0 - w, w], "rows": rows}
+    if mode == "catmull":
+        f32, fp, taps, w, rows = icrf_catmull(x, theta, flat_offset)
+        return {"f32": f32, "fp": np.asarray(fp, dtype=F64), "taps": taps, "weights": [wi.astype(F64) for wi in w], "rows": rows}
+    if mode == "lookup":
+        f32, idx = icrf_lookup(x, theta)
+        c = np.asarray(x).shape[-3]
+        rows = np.broadcast_to(np.arange(c).reshape((c, 1, 1)), np.asarray(x).shape)
+        return {"f32": f32.astype(F32), "fp": np.zeros(np.asarray(x).shape, dtype=F64), "taps": [idx],
+                "weights": [np.ones(np.asarray(x).shape, dtype=F64)], "rows": rows}
+    raise ValueError(f"unknown mode {mode!r}")
+
+
 def gaussian_value_weights(x, scale=HDR_WEIGHT_SCALE):
     """training/losses.py:193-205 in float32."""
     x = np.asarray(x, dtype=F32)
@@ -138,7 +163,7 @@ class HdrState:
         self.var = None      # float64 here; float32 in the reference
 
 
-def hdr_merge_update(state, val, std, exposure, theta=None, gaussian=True, flat_offset=0):
+def hdr_merge_update(state, val, std, exposure, theta=None, gaussian=True, flat_offset=0, mode="linear"):
     """One DataLoader batch of compute_hdr_image (inference/hdr_merge.py:95-128).
 
     val, std: (N,C,H,W) float32 (std may be None); exposure: (N,) float64 seconds; theta (C,L) or None
@@ -154,9 +179,9 @@ def hdr_merge_update(state, val, std, exposure, theta=None, gaussian=True, flat_
     n = val.shape[0]
     t = np.asarray(exposure, dtype=F64).reshape(n, 1, 1, 1)
     if theta is not None:
-        f32, fp32_, _, _ = icrf_linear(val, theta, flat_offset)
-        f = f32.astype(F64)
-        fp = fp32_.astype(F64)
+        ev = icrf_eval(val, theta, mode, flat_offset)
+        f = ev["f32"].astype(F64)
+        fp = ev["fp"]
     else:
         f = val.astype(F64)
         fp = np.ones_like(f)
@@ -168,8 +193,12 @@ def hdr_merge_update(state, val, std, exposure, theta=None, gaussian=True, flat_
         w = np.ones_like(f)
         wp = np.zeros_like(f)
     v = f / t
+    # statistics.py:75-77.  The reference sums its float32 weights in float32; here W_B is float64: the difference (6e-8
+    # relative) only matters for a LOOKUP model, whose whole uncertainty is the cancelling term w'(v_n - mean_B) below and
+    # therefore inherits the rounding of W_B amplified by mean_B / (v_n - mean_B) (SIGMA_TOL in tests/_helpers.py).
     w_b = w.sum(axis=0)
-    mean_b = (w * v).sum(axis=0) / (w_b + 1e-6)
+    w_be = w_b + 1e-6
+    mean_b = (w * v).sum(axis=0) / w_be
     if state.mean is None:
         w_a = np.zeros_like(w_b)
         mean_a = np.zeros_like(mean_b)
@@ -180,7 +209,7 @@ def hdr_merge_update(state, val, std, exposure, theta=None, gaussian=True, flat_
     mean_new = mean_a + frac * (mean_b - mean_a)
     if std is not None:
         s = np.asarray(std, dtype=F32).astype(F64)
-        dmean_b = (w * fp / t + wp * (v - mean_b)) / (w_b + 1e-6)
+        dmean_b = (w * fp / t + wp * (v - mean_b)) / w_be
         g = frac * dmean_b + wp * (w_a / (w_tot * w_tot)) * (mean_b - mean_a)
         upd = ((g * s) ** 2).sum(axis=0)
         state.var = upd if state.var is None else state.var + upd
@@ -188,7 +217,7 @@ def hdr_merge_update(state, val, std, exposure, theta=None, gaussian=True, flat_
     return state
 
 
-def hdr_merge(val, std, exposure, theta=None, gaussian=True, batch_size=None, flat_offset=0):
+def hdr_merge(val, std, exposure, theta=None, gaussian=True, batch_size=None, flat_offset=0, mode="linear"):
     """compute_hdr_image (inference/hdr_merge.py:19-155) without flat/dark-field branches.
 
     The stack is assumed sorted by ascending exposure inside each batch (datasets/collate.py:23).
@@ -200,16 +229,23 @@ def hdr_merge(val, std, exposure, theta=None, gaussian=True, batch_size=None, fl
     for a in range(0, n, bs):
         sl = slice(a, min(a + bs, n))
         hdr_merge_update(st, val[sl], None if std is None else std[sl], np.asarray(exposure)[sl], theta,
-                         gaussian, flat_offset)
+                         gaussian, flat_offset, mode)
     sigma = None if st.var is None else np.sqrt(st.var)
     return st.mean, sigma
 
 
-def linearize(val, std, theta, flat_offset=0):
+def linearize(val, std, theta, flat_offset=0, mode="linear"):
     """linearize_dataset_generator core for one (1,C,H,W) image (inference/linearization.py:94-106,132).
 
     Returns (f float32, sigma float32) with sigma = sqrt((f'(x) s)^2); zeros when std is None (:97).
     """
+    if mode != "linear":
+        ev = icrf_eval(val, theta, mode, flat_offset)
+        f = ev["f32"]
+        if std is None:
+            return f, np.zeros_like(f)
+        g = ev["fp"].astype(F32) * np.asarray(std, dtype=F32)
+        return f, np.sqrt(g * g).astype(F32)
     f, fp, _, _ = icrf_linear(val, theta, flat_offset)
     if std is None:
         return f, np.zeros_like(f)
@@ -246,16 +282,18 @@ def pair_valid_mask(val, i_idx, j_idx, lo, hi):
     return fv[i_idx] & fv[j_idx]
 
 
-def _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weighting, flat_offset):
+def _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weighting, flat_offset, mode="linear"):
     """Everything per pair-element that losses.py:13-67,70-108 and general_functions.py:118-178 form.
 
     Returns a dict of float64 (P,C,H,W) arrays plus the per-frame ICRF pieces.
     """
     val = np.ascontiguousarray(val, dtype=F32)
+    ev = None
     if theta is not None:
-        f32, fp32_, x0, rows = icrf_linear(val, theta, flat_offset)
+        ev = icrf_eval(val, theta, mode, flat_offset)
+        f32, fp32_ = ev["f32"], ev["fp"].astype(F32)
     else:
-        f32, fp32_, x0, rows = val, np.ones_like(val), None, None
+        f32, fp32_ = val, np.ones_like(val)
     f = f32.astype(F64)
     have_std = std is not None
     if have_std:
@@ -265,7 +303,7 @@ def _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weig
     a, b = f[i_idx], f[j_idx]
     e = b * r                                                         # losses.py:40 (promotes to fp64)
     d = a - e
-    out = {"f32": f32, "fp32": fp32_, "x0": x0, "rows": rows, "a": a, "b": b, "r": r}
+    out = {"f32": f32, "fp32": fp32_, "ev": ev, "a": a, "b": b, "r": r}
     if relative:
         es = e + 1e-6                                                 # :45
         q = d / es
@@ -296,13 +334,13 @@ def _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weig
 
 
 def linearity_stats(val, std, exposure, theta=None, threshold=0.2, lo=1 / 255, hi=254 / 255, relative=True,
-                    unc_weighting=True, flat_offset=0, pairs=None):
+                    unc_weighting=True, flat_offset=0, pairs=None, mode="linear"):
     """measure_linearity (inference/measure_linearity.py:41-74).
 
     Returns (ratio (P,), mean (P,C), stddev (P,C), errmean (P,C) or None), float64.
     """
     i_idx, j_idx, ratio = exposure_pairs(exposure, threshold) if pairs is None else pairs
-    tm = _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weighting, flat_offset)
+    tm = _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weighting, flat_offset, mode)
     m, wt, ell = tm["mask"], tm["wt"], tm["ell"]
     mw = m * wt
     dsum = np.maximum(mw.sum(axis=(2, 3)), 1e-8)                      # general_functions.py:156
@@ -343,7 +381,7 @@ def curve_penalties(theta):
 
 
 def train_loss_and_grad(val, std, exposure, theta, threshold=0.1, lo=1 / 255, hi=254 / 255, relative=True,
-                        unc_weighting=True, coeffs=(1.0, 1.0, 1.0, 1.0), flat_offset=0):
+                        unc_weighting=True, coeffs=(1.0, 1.0, 1.0, 1.0), flat_offset=0, mode="linear"):
     """Loss and d(sum_c Loss_c)/d theta of one train_icrf step (training/icrf_training.py:105-149).
 
     Returns dict(loss (C,), linloss (C,), spatial (P,C), grad (C,L) float64, grad_lin (C,L)).
@@ -352,7 +390,7 @@ def train_loss_and_grad(val, std, exposure, theta, threshold=0.1, lo=1 / 255, hi
     theta = np.asarray(theta, dtype=F32)
     n_rows, l = theta.shape
     i_idx, j_idx, ratio = exposure_pairs(exposure, threshold)
-    tm = _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weighting, flat_offset)
+    tm = _pair_terms(val, std, i_idx, j_idx, ratio, theta, lo, hi, relative, unc_weighting, flat_offset, mode)
     m, wt, ell, sgn, r = tm["mask"], tm["wt"], tm["ell"], tm["sgn"], tm["r"]
     a, b = tm["a"], tm["b"]
     mw = m * wt
@@ -385,17 +423,14 @@ def train_loss_and_grad(val, std, exposure, theta, threshold=0.1, lo=1 / 255, hi
         dbs_db = (tm["f32"][j_idx] >= F32(1e-6)).astype(F64)
         g_a = g_a + dm_dwt * dwt_dt * dt_da
         g_b = g_b + dm_dwt * dwt_dt * (dt_des * r + dt_dbs * dbs_db)
-    # gather per-frame upstream, then scatter to the two taps of each element (models/base.py:173-182)
+    # gather per-frame upstream, then scatter to the taps of each element (models/base.py:173-182, :194-224)
     g_frame = np.zeros(tm["f32"].shape, dtype=F64)
     np.add.at(g_frame, i_idx, g_a)
     np.add.at(g_frame, j_idx, g_b)
-    x0, rows = tm["x0"], tm["rows"]
-    x1 = np.minimum(x0 + 1, l - 1)
-    xs = np.minimum(np.maximum(np.asarray(val, dtype=F32) * F32(l - 1), F32(0)), F32(l - 1))
-    w = (xs - x0.astype(F32)).astype(F64)
+    rows = tm["ev"]["rows"]
     grad_lin = np.zeros((n_rows, l), dtype=F64)
-    np.add.at(grad_lin, (rows.ravel(), x0.ravel()), (g_frame * (1.0 - w)).ravel())
-    np.add.at(grad_lin, (rows.ravel(), x1.ravel()), (g_frame * w).ravel())
+    for tap, w in zip(tm["ev"]["taps"], tm["ev"]["weights"]):
+        np.add.at(grad_lin, (rows.ravel(), tap.ravel()), (g_frame * w).ravel())
     pens, gpens = curve_penalties(theta)
     loss = linloss.copy()
     grad = grad_lin.copy()

@@ -430,6 +430,87 @@ def gen_trainstep():
              thr=thr, coeffs=np.array(coeffs), n_steps=n_steps, **out)
 
 
+def gen_modes():
+    """The drivers with LOOKUP / CATMULL models (clair_torch/models/base.py:138-158, :184-226).  LOOKUP has no autograd
+    edge to the image: with std images the linearisation / linearity drivers raise, so those cases run without std; the
+    HDR merge still differentiates through the Gaussian weights."""
+    modes = {"lookup": InterpMode.LOOKUP, "catmull": InterpMode.CATMULL}
+    # compute_hdr_image
+    for mname, kw, bs, with_w, with_std in (
+            ("lookup", dict(seed=101, n=5, c=3, h=10, w=14, bits=8), 5, True, True),
+            ("lookup", dict(seed=102, n=5, c=3, h=8, w=11, bits=8), 2, True, True),
+            ("lookup", dict(seed=103, n=4, c=3, h=8, w=12, bits=8, std_mult=None), 4, False, False),
+            ("catmull", dict(seed=104, n=5, c=3, h=10, w=14, bits=8), 5, True, True),
+            ("catmull", dict(seed=105, n=6, c=3, h=9, w=13, bits=16), 4, True, True),
+            ("catmull", dict(seed=106, n=4, c=3, h=8, w=12, bits=8), 4, False, True),
+            ("catmull", dict(seed=107, n=3, c=1, h=6, w=10, bits=8), 3, True, True)):
+        vals, stds, t = make_stack(**kw)
+        theta = curve(kw["c"])
+        model = ICRFModelDirect(icrf=theta.clone(), interpolation_mode=modes[mname])
+        tv = [torch.from_numpy(v) for v in vals]
+        ts = None if stds is None else [torch.from_numpy(s) for s in stds]
+        mean, sigma = compute_hdr_image(loader(tv, ts, t, bs), "cpu", model, gaussian_value_weights if with_w else None)
+        save(f"hdr_{mname}_s{kw['seed']}", val=vals, std=stds, exposure=t, theta=theta, batch_size=bs, gaussian=int(with_w),
+             radiance=mean, sigma=sigma, mode=mname)
+    # linearize_dataset_generator
+    for mname, kw in (("lookup", dict(seed=111, n=2, c=3, h=5, w=7, bits=8, std_mult=None)),
+                      ("catmull", dict(seed=112, n=3, c=3, h=6, w=9, bits=8)),
+                      ("catmull", dict(seed=113, n=2, c=3, h=5, w=7, bits=16)),
+                      ("catmull", dict(seed=114, n=2, c=3, h=5, w=6, bits=8, std_mult=None))):
+        vals, stds, t = make_stack(**kw)
+        theta = curve(kw["c"])
+        model = ICRFModelDirect(icrf=theta.clone(), interpolation_mode=modes[mname])
+        tv = [torch.from_numpy(v) for v in vals]
+        ts = None if stds is None else [torch.from_numpy(s) for s in stds]
+        lin, sig = [], []
+        for a, b, _ in linearize_dataset_generator(loader(tv, ts, t, 1), "cpu", model):
+            lin.append(a.numpy())
+            sig.append(b.numpy())
+        save(f"linearize_{mname}_s{kw['seed']}", val=vals, std=stds, exposure=t, theta=theta, linearized=np.stack(lin),
+             sigma=np.stack(sig), mode=mname)
+    # measure_linearity
+    for mname, rel, unc, with_std in (("lookup", True, False, False), ("lookup", False, True, False),
+                                      ("catmull", True, True, True), ("catmull", True, False, True),
+                                      ("catmull", False, True, True), ("catmull", False, False, False)):
+        kw = dict(seed=121, n=6, c=3, h=12, w=16, bits=8)
+        if not with_std:
+            kw["std_mult"] = None
+        vals, stds, t = make_stack(**kw)
+        theta = curve(3)
+        model = ICRFModelDirect(icrf=theta.clone(), interpolation_mode=modes[mname])
+        tv = [torch.from_numpy(v) for v in vals]
+        ts = None if stds is None else [torch.from_numpy(s) for s in stds]
+        ratio, m, sd, err = measure_linearity(loader(tv, ts, t, len(tv)), "cpu", unc, rel, model)
+        save(f"linearity_{mname}_rel{int(rel)}_unc{int(unc)}_std{int(with_std)}", val=vals, std=stds, exposure=t, theta=theta,
+             ratio=ratio, mean=m, stddev=sd, errmean=err, mode=mname)
+    # train step, CATMULL (LOOKUP has no gradient to the table parameters' image edge and is not trainable with std)
+    for name, kw, rel, unc, thr, coeffs, with_std, power in (
+            ("catmull_script", dict(seed=131, n=6, c=3, h=14, w=20, bits=8), True, False, 0.25, (10.0, 1.0, 1.0, 1.0), True, 2.5),
+            ("catmull_defaults", dict(seed=132, n=5, c=3, h=12, w=17, bits=8), True, True, 0.1, (1.0, 1.0, 1.0, 1.0), True, 2.2)):
+        vals, stds, t = make_stack(**kw)
+        alpha, beta, gamma, delta = coeffs
+        model = ICRFModelDirect(n_points=256, channels=kw["c"], initial_power=power, interpolation_mode=InterpMode.CATMULL)
+        with torch.no_grad():
+            for c, p in enumerate(model.direct_params):
+                p.copy_(torch.linspace(0, 1, 256) ** (power + 0.15 * c))
+        model.update_icrf()
+        theta0 = model.icrf.detach().clone()
+        optimizers = [torch.optim.Adam(model.channel_params(c), lr=1e-3, amsgrad=False) for c in range(kw["c"])]
+        images, tstd, exposures = torch.from_numpy(vals), torch.from_numpy(stds), torch.from_numpy(t)
+        out = {}
+        n_steps = 3
+        for step in range(n_steps):
+            loss, spatial, lin, gtheta = train_step_reference(model, optimizers, images.clone(), tstd, exposures, rel=rel, unc=unc,
+                                                              alpha=alpha, beta=beta, gamma=gamma, delta=delta, thr=thr)
+            out[f"loss_{step}"] = loss
+            out[f"spatial_{step}"] = spatial
+            out[f"linloss_{step}"] = lin
+            out[f"grad_theta_{step}"] = gtheta
+            out[f"theta_after_{step}"] = model.icrf.detach().clone()
+        save(f"trainstep_{name}", val=vals, std=stds, exposure=t, theta0=theta0, rel=int(rel), unc=int(unc), thr=thr,
+             coeffs=np.array(coeffs), n_steps=n_steps, mode="catmull", **out)
+
+
 def gen_known_answers():
     out = {}
     # tests/unit/common/test_general_functions.py:292-319
@@ -477,12 +558,8 @@ def gen_known_answers():
 
 
 if __name__ == "__main__":
-    gen_known_answers()
-    gen_forward()
-    gen_catmull()
-    gen_frame_stats()
-    gen_artefacts()
-    gen_hdr()
-    gen_linearize()
-    gen_linearity()
-    gen_trainstep()
+    generators = {"known_answers": gen_known_answers, "forward": gen_forward, "catmull": gen_catmull, "frame_stats": gen_frame_stats,
+                  "artefacts": gen_artefacts, "hdr": gen_hdr, "linearize": gen_linearize, "linearity": gen_linearity,
+                  "trainstep": gen_trainstep, "modes": gen_modes}
+    for key in (sys.argv[1:] or list(generators)):       # e.g. `make_golden.py modes` regenerates one family only
+        generators[key]()

@@ -183,7 +183,7 @@ def test_kernels_do_not_write_outside_their_outputs(ct):
         lb, lin = carve(n * numel)
         gb, lsig = carve(n * numel)
         assert lib.clair_linearize(v.data_ptr(), s.data_ptr(), theta.data_ptr(), lin.data_ptr(), lsig.data_ptr(), n, 3, plane, 256,
-                                   None, stream) == 0
+                                   2, None, stream) == 0
         mb, mixed = carve(n * numel)
         eb, seff = carve(n * numel)
         dark = torch.rand_like(v) * 0.1

@@ -8,7 +8,7 @@ import pytest
 import torch
 from torch.utils.data import DataLoader
 
-from _helpers import golden, golden_names, max_abs_over_max, max_rel
+from _helpers import SIGMA_TOL, golden, golden_names, linear_golden_names, max_abs_over_max, max_rel, mode_of
 from oracle import clair_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -37,6 +37,8 @@ def _loader(ct, z, batch_size):
 
 def _model(ct, theta, mode=None):
     from clair_torch_b200 import ICRFModelDirect, InterpMode
+    if isinstance(mode, str):
+        mode = {"linear": InterpMode.LINEAR, "lookup": InterpMode.LOOKUP, "catmull": InterpMode.CATMULL}[mode]
     return ICRFModelDirect(icrf=torch.from_numpy(theta).clone(), interpolation_mode=mode or InterpMode.LINEAR).to(DEV)
 
 
@@ -136,16 +138,42 @@ def test_forward_table_gradient_matches_scatter(ct):
 @pytest.mark.parametrize("name", golden_names("hdr_"))
 def test_hdr_merge_golden(ct, name):
     z = golden(name)
-    model = _model(ct, z["theta"]) if "theta" in z else None
+    model = _model(ct, z["theta"], mode_of(z)) if "theta" in z else None
     weight_fn = (lambda img: img) if int(z["gaussian"]) else None
     rad, sig = ct.compute_hdr_image(_loader(ct, z, int(z["batch_size"])), DEV, model, weight_fn)
     assert rad.dtype == torch.float64 and tuple(rad.shape) == z["radiance"].shape
     assert max_rel(rad.cpu().numpy(), z["radiance"]) < TOL
     if "sigma" in z:
         assert sig.dtype == torch.float32
-        assert max_rel(sig.cpu().numpy(), z["sigma"]) < TOL
+        assert max_rel(sig.cpu().numpy(), z["sigma"]) < SIGMA_TOL[mode_of(z)]      # reference noise per mode, _helpers.py
     else:
         assert sig is None
+
+
+@pytest.mark.parametrize("mode,batch,gaussian", [("lookup", None, True), ("lookup", 3, True), ("catmull", None, True),
+                                                 ("catmull", 4, True), ("catmull", None, False)])
+def test_hdr_merge_modes_vs_oracle(ct, mode, batch, gaussian):
+    """LOOKUP / CATMULL models through the all-modes kernel against the float64 closed form, at the LINEAR bar (1e-5):
+    the kernel takes the cancelling difference v_n - mean_B in float64."""
+    val, std, t = ct.synthetic.make_stack(7, 3, 61, 83, bits=16, seed=77)
+    theta = ct.synthetic.reference_curve(3).numpy()
+    want_r, want_s = orc.hdr_merge(val.numpy(), std.numpy(), t, theta, gaussian, batch, mode=mode)
+    z = {"val": val.numpy(), "std": std.numpy(), "exposure": t}
+    rad, sig = ct.compute_hdr_image(_loader(ct, z, batch or 7), DEV, _model(ct, theta, mode), (lambda i: i) if gaussian else None)
+    assert max_rel(rad.cpu().numpy(), want_r) < TOL
+    assert max_rel(sig.cpu().numpy(), want_s) < TOL
+
+
+def test_hdr_merge_lookup_without_weights_raises_like_reference(ct):
+    val, std, t = ct.synthetic.make_stack(3, 3, 8, 12, seed=1)
+    z = {"val": val.numpy(), "std": std.numpy(), "exposure": t}
+    model = _model(ct, ct.synthetic.reference_curve(3).numpy(), "lookup")
+    with pytest.raises(RuntimeError):
+        ct.compute_hdr_image(_loader(ct, z, 3), DEV, model, None)
+    z.pop("std")
+    rad, sig = ct.compute_hdr_image(_loader(ct, z, 3), DEV, model, None)          # no std: nothing to differentiate, fine
+    want, _ = orc.hdr_merge(val.numpy(), None, t, model.icrf.cpu().numpy(), False, mode="lookup")
+    assert sig is None and max_rel(rad.cpu().numpy(), want) < TOL
 
 
 @pytest.mark.parametrize("bits,batch", [(8, None), (16, None), (8, 2), (16, 4)])
@@ -204,13 +232,16 @@ def test_hdr_merge_row_band_shards_equal_whole_image(ct):
 @pytest.mark.parametrize("name", golden_names("linearize_"))
 def test_linearize_bit_exact(ct, name):
     z = golden(name)
-    model = _model(ct, z["theta"])
+    model = _model(ct, z["theta"], mode_of(z))
     outs = list(ct.linearize_dataset_generator(_loader(ct, z, 1), DEV, model))
     assert len(outs) == z["val"].shape[0]
     for n, (lin, sig, meta) in enumerate(outs):
         assert lin.device.type == "cpu" and sig.device.type == "cpu"
         assert np.array_equal(lin.numpy(), z["linearized"][n])
-        assert np.array_equal(sig.numpy(), z["sigma"][n])
+        if mode_of(z) == "catmull":      # closed-form derivative vs the reference's fp32 autograd of the cubic weights
+            assert np.max(np.abs(sig.numpy() - z["sigma"][n])) <= 5e-5 * np.max(z["sigma"][n])
+        else:
+            assert np.array_equal(sig.numpy(), z["sigma"][n])
         assert float(meta["exposure_time"][0]) == float(z["exposure"][n])
 
 
@@ -225,7 +256,7 @@ def _linearity_flags(name):
 def test_measure_linearity_golden(ct, name):
     z = golden(name)
     rel, unc = _linearity_flags(name)
-    model = _model(ct, z["theta"]) if "theta" in z else None
+    model = _model(ct, z["theta"], mode_of(z)) if "theta" in z else None
     ratio, mean, std, err = ct.measure_linearity(_loader(ct, z, len(z["exposure"])), DEV, unc, rel, model)
     assert np.array_equal(ratio.cpu().numpy(), z["ratio"])
     assert max_rel(mean.cpu().numpy(), z["mean"]) < TOL
@@ -274,7 +305,56 @@ def test_pair_stats_degenerate_spread(ct):
 
 
 # ---- training step -----------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", golden_names("trainstep_"))
+@pytest.mark.parametrize("name", golden_names("trainstep_catmull"))
+def test_train_step_catmull_golden(ct, name):
+    """A CATMULL model trains through the composed device path (model kernels + torch pair algebra): loss and the
+    Adam-updated table of every recorded step, teacher-forced like the LINEAR test below."""
+    from clair_torch_b200 import ICRFModelDirect, InterpMode, train_icrf_step
+    z = golden(name)
+    val, std = torch.from_numpy(z["val"]).to(DEV), torch.from_numpy(z["std"]).to(DEV)
+    exposure = torch.from_numpy(z["exposure"])
+    a, b, g, d = (float(k) for k in z["coeffs"])
+    for step in range(int(z["n_steps"])):
+        theta = z["theta0"] if step == 0 else z[f"theta_after_{step - 1}"]
+        model = ICRFModelDirect(256, 3, InterpMode.CATMULL).to(DEV)
+        with torch.no_grad():
+            for c, p in enumerate(model.direct_params):
+                p.copy_(torch.from_numpy(theta[c]))
+        model.update_icrf()
+        opts = [torch.optim.SGD(model.channel_params(c), lr=1.0) for c in range(3)]     # theta - grad: exposes the gradient
+        loss = train_icrf_step(model, opts, val, std, exposure, use_relative_linearity_loss=bool(z["rel"]),
+                               use_uncertainty_weighting=bool(z["unc"]), alpha=a, beta=b, gamma=g, delta=d,
+                               exposure_ratio_threshold=float(z["thr"]))
+        assert max_rel(loss.cpu().numpy(), z[f"loss_{step}"]) < TOL
+        grad = theta.astype(np.float64) - model.icrf.detach().cpu().numpy().astype(np.float64)
+        want = z[f"grad_theta_{step}"]
+        assert np.max(np.abs(grad - want)) < 1e-5 * np.max(np.abs(want)) + 2e-7       # fp32 parameter update rounding
+
+
+def test_lookup_model_errors_and_table_gradient(ct):
+    """LOOKUP has no image edge: drivers that propagate std images through the model raise like the reference's autograd
+    call; the table edge (a gather) exists and matches a scatter of the upstream gradient."""
+    from clair_torch_b200 import ICRFModelDirect, InterpMode
+    val, std, t = ct.synthetic.make_stack(3, 3, 12, 20, seed=2)
+    z = {"val": val.numpy(), "std": std.numpy(), "exposure": t}
+    model = _model(ct, ct.synthetic.reference_curve(3).numpy(), "lookup")
+    with pytest.raises(RuntimeError):
+        list(ct.linearize_dataset_generator(_loader(ct, z, 1), DEV, model))
+    with pytest.raises(RuntimeError):
+        ct.measure_linearity(_loader(ct, z, 3), DEV, True, True, model)
+    m = ICRFModelDirect(256, 3, InterpMode.LOOKUP).to(DEV)
+    m.update_icrf()
+    g = torch.randn(val.shape, device=DEV)
+    m(val.to(DEV)).backward(g)
+    got = torch.stack([p.grad for p in m.direct_params]).cpu().numpy()
+    _, idx = orc.icrf_lookup(val.numpy(), m.icrf.detach().cpu().numpy())
+    want = np.zeros((3, 256))
+    chan = np.broadcast_to(np.arange(3).reshape(1, 3, 1, 1), idx.shape)
+    np.add.at(want, (chan.ravel(), idx.ravel()), g.cpu().numpy().astype(np.float64).ravel())
+    assert max_abs_over_max(got, want) < TOL
+
+
+@pytest.mark.parametrize("name", linear_golden_names("trainstep_"))
 def test_train_step_golden(ct, name):
     """Loss, spatial means, table gradient and the Adam-updated table of every recorded step, each step started
     from the reference's own table (teacher forcing: a sign-like first Adam step amplifies 1e-8-sized gradient
@@ -326,11 +406,13 @@ def test_train_icrf_step_updates_like_reference(ct):
     assert loss0.shape == (3,)
 
 
-def test_hdr_merge_zero_copy_pinned_host(ct):
-    """Pinned host batches are read by the kernel over PCIe and results can be written straight to pinned host
-    buffers: bit-identical to the staged path, for one batch and for several."""
+@pytest.mark.parametrize("staged", [True, False])
+def test_hdr_merge_pinned_host_stack(ct, staged):
+    """Pinned host batches are either streamed band by band by the copy engine while the kernel merges the previous band
+    (staged) or read by the kernel over PCIe (zero-copy), and results can be written straight to pinned host buffers:
+    bit-identical to the device-resident path, for one batch and for several."""
     from clair_torch_b200.datasets import ExposureStackDataset, custom_collate
-    val, std, t = ct.synthetic.make_stack(5, 3, 90, 160, seed=17)
+    val, std, t = ct.synthetic.make_stack(5, 3, 90, 161, seed=17)
     theta = ct.synthetic.reference_curve(3)
     model = _model(ct, theta.numpy())
     z = {"val": val.numpy(), "std": std.numpy(), "exposure": t}
@@ -338,9 +420,10 @@ def test_hdr_merge_zero_copy_pinned_host(ct):
     ds = ExposureStackDataset(list(val), list(std), list(t))
     for bs in (5, 2):
         loader = DataLoader(ds, batch_size=bs, shuffle=False, collate_fn=custom_collate, pin_memory=True)
-        rad_h = torch.empty((3, 90, 160), dtype=torch.float32).pin_memory()
-        sig_h = torch.empty((3, 90, 160), dtype=torch.float32).pin_memory()
-        rad, sig = ct.compute_hdr_image(loader, DEV, model, max, radiance_dtype=torch.float32, host_out=(rad_h, sig_h))
+        rad_h = torch.empty((3, 90, 161), dtype=torch.float32).pin_memory()
+        sig_h = torch.empty((3, 90, 161), dtype=torch.float32).pin_memory()
+        rad, sig = ct.compute_hdr_image(loader, DEV, model, max, radiance_dtype=torch.float32, host_out=(rad_h, sig_h),
+                                        staged=staged)
         torch.cuda.synchronize()
         assert rad.data_ptr() == rad_h.data_ptr() and not rad.is_cuda
         if bs == 5:
@@ -350,7 +433,33 @@ def test_hdr_merge_zero_copy_pinned_host(ct):
             assert max_rel(rad.numpy(), o_rad) < 2e-6 and max_rel(sig.numpy(), o_sig) < 5e-6
     with pytest.raises(ValueError):
         ct.compute_hdr_image(loader, DEV, model, max, radiance_dtype=torch.float32,
-                             host_out=(torch.empty((3, 90, 160)), torch.empty((3, 90, 160))))
+                             host_out=(torch.empty((3, 90, 161)), torch.empty((3, 90, 161))))
+
+
+@pytest.mark.parametrize("shape,bands", [((4, 3, 7, 11), 8), ((5, 3, 64, 48), 3), ((9, 3, 40, 52), 64), ((3, 1, 33, 31), 2)])
+def test_hdr_merge_staged_bands_equal_one_launch(ct, shape, bands):
+    """The band split of the staged entry point (any band count, planes smaller than one band, N in the register / parked
+    kernels, float64 radiance) is invisible in the result; uint8 codes and a LOOKUP model take the same route."""
+    n, c, h, w = shape
+    val, std, t = ct.synthetic.make_stack(n, c, h, w, seed=5 + n)
+    theta = ct.synthetic.reference_curve(c).to(DEV)
+    whole = ct.kernels.hdr_merge_update(ct.kernels.HdrMergeState(), val.to(DEV), std.to(DEV), t, theta, True, True)
+    banded = ct.kernels.hdr_merge_update(ct.kernels.HdrMergeState(), val.pin_memory(), std.pin_memory(), t, theta, True, True,
+                                         device=torch.device(DEV), staged=True, bands=bands)
+    assert torch.equal(whole[0], banded[0]) and torch.equal(whole[1], banded[1])
+    for mode in (ct._native.INTERP_LOOKUP, ct._native.INTERP_CATMULL):
+        a = ct.kernels.hdr_merge_update(ct.kernels.HdrMergeState(), val.to(DEV), std.to(DEV), t, theta, True, True, interp_mode=mode)
+        b = ct.kernels.hdr_merge_update(ct.kernels.HdrMergeState(), val.pin_memory(), std.pin_memory(), t, theta, True, True,
+                                        device=torch.device(DEV), staged=True, bands=bands, interp_mode=mode)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    if (h * w) % 4 == 0:
+        codes = torch.round(val * 255).to(torch.uint8)
+        from clair_torch_b200.datasets import StdSpec
+        spec = StdSpec("multiplier", 0.05)
+        a = ct.kernels.hdr_merge_update(ct.kernels.HdrMergeState(), codes.to(DEV), spec, t, theta, True, True)
+        b = ct.kernels.hdr_merge_update(ct.kernels.HdrMergeState(), codes.pin_memory(), spec, t, theta, True, True,
+                                        device=torch.device(DEV), staged=True, bands=bands)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
 
 
 @pytest.mark.parametrize("bits", [8, 16])

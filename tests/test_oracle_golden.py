@@ -8,7 +8,7 @@ the tighter bound the oracle actually meets asserted next to it.
 import numpy as np
 import pytest
 
-from _helpers import golden, golden_names, max_abs_over_max, max_rel
+from _helpers import SIGMA_TOL, golden, golden_names, linear_golden_names, max_abs_over_max, max_rel, mode_of
 from oracle import clair_oracle as orc
 
 TOL = 1e-5   # BASELINE.json north_star: radiance, uncertainty and loss within 1e-5 relative
@@ -109,11 +109,12 @@ def test_forward_all_codes(name):
 def test_hdr_merge(name):
     z = golden(name)
     rad, sig = orc.hdr_merge(z["val"], _opt(z, "std"), z["exposure"], _opt(z, "theta"), bool(z["gaussian"]),
-                             int(z["batch_size"]))
+                             int(z["batch_size"]), mode=mode_of(z))
     assert max_rel(rad.reshape(z["radiance"].shape), z["radiance"]) < 5e-7
     if "sigma" in z:
-        # the reference's own fp32 autograd carries ~5e-6 of cancellation noise at bright codes
-        assert max_rel(sig.reshape(z["sigma"].shape), z["sigma"]) < TOL
+        # the reference's own fp32 autograd carries ~5e-6 of cancellation noise at bright codes; more in the
+        # other modes (SIGMA_TOL in _helpers.py)
+        assert max_rel(sig.reshape(z["sigma"].shape), z["sigma"]) < SIGMA_TOL[mode_of(z)]
     else:
         assert sig is None
 
@@ -123,9 +124,12 @@ def test_linearize_bit_exact(name):
     z = golden(name)
     for n in range(z["val"].shape[0]):
         std = None if "std" not in z else z["std"][n:n + 1]
-        f, s = orc.linearize(z["val"][n:n + 1], std, z["theta"])
+        f, s = orc.linearize(z["val"][n:n + 1], std, z["theta"], mode=mode_of(z))
         assert np.array_equal(f[0], z["linearized"][n])
-        assert np.array_equal(s[0], z["sigma"][n])
+        if mode_of(z) == "catmull":     # the oracle's derivative is the closed form, the reference's its own fp32 autograd
+            assert np.max(np.abs(s[0] - z["sigma"][n])) <= 5e-5 * np.max(z["sigma"][n])
+        else:
+            assert np.array_equal(s[0], z["sigma"][n])
 
 
 # ---- linearity measurement ---------------------------------------------------------------------
@@ -140,7 +144,7 @@ def test_linearity_stats(name):
     z = golden(name)
     rel, unc = _linearity_flags(name)
     ratio, m, sd, em = orc.linearity_stats(z["val"], _opt(z, "std"), z["exposure"], _opt(z, "theta"), 0.2,
-                                           relative=rel, unc_weighting=unc)
+                                           relative=rel, unc_weighting=unc, mode=mode_of(z))
     assert np.array_equal(ratio, z["ratio"])
     assert max_rel(m, z["mean"]) < 1e-7
     assert max_rel(sd, z["stddev"]) < 1e-7
@@ -160,7 +164,7 @@ def test_train_step(name):
         theta = z["theta0"] if step == 0 else z[f"theta_after_{step - 1}"]
         out = orc.train_loss_and_grad(z["val"], _opt(z, "std"), z["exposure"], theta, float(z["thr"]),
                                       relative=bool(z["rel"]), unc_weighting=bool(z["unc"]),
-                                      coeffs=tuple(z["coeffs"]))
+                                      coeffs=tuple(z["coeffs"]), mode=mode_of(z))
         assert max_rel(out["loss"], z[f"loss_{step}"]) < 1e-6
         assert max_rel(out["linloss"], z[f"linloss_{step}"]) < 1e-6
         assert max_rel(out["spatial"], z[f"spatial_{step}"]) < 1e-6
@@ -186,7 +190,7 @@ def test_c_forward_bit_exact(name):
         assert np.array_equal(x0, orc.icrf_linear(z["x"], z["theta"])[2])
 
 
-@pytest.mark.parametrize("name", golden_names("hdr_"))
+@pytest.mark.parametrize("name", linear_golden_names("hdr_"))
 def test_c_hdr_merge(name):
     z = golden(name)
     rad, sig = corc.hdr_merge(z["val"], _opt(z, "std"), z["exposure"], _opt(z, "theta"), bool(z["gaussian"]),
@@ -196,14 +200,14 @@ def test_c_hdr_merge(name):
         assert max_rel(sig.reshape(z["sigma"].shape), z["sigma"]) < TOL
 
 
-@pytest.mark.parametrize("name", golden_names("linearize_"))
+@pytest.mark.parametrize("name", linear_golden_names("linearize_"))
 def test_c_linearize_bit_exact(name):
     z = golden(name)
     lin, sig = corc.linearize(z["val"], _opt(z, "std"), z["theta"])
     assert np.array_equal(lin, z["linearized"]) and np.array_equal(sig, z["sigma"])
 
 
-@pytest.mark.parametrize("name", golden_names("linearity_"))
+@pytest.mark.parametrize("name", linear_golden_names("linearity_"))
 def test_c_linearity_stats(name):
     z = golden(name)
     rel, unc = _linearity_flags(name)
@@ -214,7 +218,7 @@ def test_c_linearity_stats(name):
         assert max_rel(em, z["errmean"]) < 1e-12
 
 
-@pytest.mark.parametrize("name", golden_names("trainstep_"))
+@pytest.mark.parametrize("name", linear_golden_names("trainstep_"))
 def test_c_train_grad(name):
     z = golden(name)
     i, j, r = orc.exposure_pairs(z["exposure"], float(z["thr"]))
