@@ -185,7 +185,7 @@ def native_ingest_metrics(dev, lib, theta, t_host):
     torch.cuda.synchronize(dev)
     ms = a.elapsed_time(b) / reps
     units = N_FRAMES * HEIGHT * WIDTH / 1e6
-    # end to end: pinned uint8 stack in (staged band by band), pinned fp32 radiance + sigma out (stored by the kernel)
+    # end to end: pinned uint8 stack in, pinned fp32 radiance + sigma out, both over PCIe from inside the kernel (zero-copy)
     codes_h = sets[0].cpu().pin_memory()
     rad_h = torch.empty((CHANNELS, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
     sig_h = torch.empty_like(rad_h).pin_memory()

@@ -188,8 +188,9 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
 
     `val` / `std` may be pinned host tensors (`device` then names the GPU that runs the kernel), and
     `host_out=(radiance, sigma)` pinned host buffers make the kernel write its results straight to host memory.
-    Host stacks are `staged` by default: the copy engine streams bands of the planes into device buffers while the kernel
-    merges the previous band (clair_hdr_merge_staged); `staged=False` lets the kernel read the host memory itself (zero-copy).
+    fp32 host stacks are `staged` by default: the copy engine streams bands of the planes into device buffers while the
+    kernel merges the previous band (clair_hdr_merge_staged); `staged=False` (the default for integer codes) lets the
+    kernel read the host memory itself (zero-copy).
 
     `interp_mode`: the model's InterpMode (LINEAR: fused fast kernels; LOOKUP / CATMULL: the all-modes kernel).
 
@@ -271,7 +272,9 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     desc.radiance_dev, desc.sigma_dev = _ptr(radiance), _ptr(sigma)
     on_host = not val.is_cuda
     if staged is None:
-        staged = on_host
+        # measured (profiles/README.md): fp32 stacks are input-bound and gain from the copy engine's faster host reads;
+        # integer codes are output-bound (1-2 B in, 8 B out per pixel) and are quicker read in place by the kernel
+        staged = on_host and not codes
     if staged and not on_host:
         raise ValueError("staged=True is for pinned host stacks")
     with torch.cuda.device(dev):
