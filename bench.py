@@ -371,6 +371,8 @@ def secondary_metrics(dev):
     dark = torch.rand_like(val) * 0.06
     dark_std = dark * 0.1 + 1e-3
     ms6 = timed(lambda: kernels.dark_field_mix(val, std, dark, dark_std), 2, 20)
+    ms6f = timed(lambda: kernels.hdr_merge_update(st(), val, std, t, theta, True, True, radiance_dtype=torch.float32,
+                                                  dark=(dark, dark_std)), 2, 20)
     radiance, sigma = kernels.hdr_merge_update(st(), val, std, t, theta, True, True, radiance_dtype=torch.float32)
     flat = torch.rand_like(radiance) * 0.4 + 0.6
     flat_std = flat * 0.02
@@ -380,8 +382,12 @@ def secondary_metrics(dev):
     ms8 = timed(lambda: handler.update_values(val, None, table=theta), 2, 20)
     ec1 = N_FRAMES * CHANNELS * HEIGHT * WIDTH
     out["artefacts_c1"] = {"dark_mix_ms": ms6, "dark_mix_hbm_frac": ec1 * 24 / (ms6 * 1e-3) / 1e9 / peak,
+                           "dark_merge_fused_ms": ms6f,
+                           "dark_merge_fused_hbm_frac": (ec1 * 16 + CHANNELS * HEIGHT * WIDTH * 8) / (ms6f * 1e-3) / 1e9 / peak,
                            "flat_field_ms": ms7, "flat_field_hbm_frac": CHANNELS * HEIGHT * WIDTH * 24 / (ms7 * 1e-3) / 1e9 / peak,
-                           "note": "dark mix: 4 input + 2 output fp32 stacks; flat field: value, sigma, flat, flat_std, in place"}
+                           "note": "dark mix pre-pass: 4 input + 2 output fp32 stacks; dark_merge_fused: the c1 merge with the mix "
+                                   "done in its load (4 input stacks, radiance + sigma out); flat field: value, sigma, flat, "
+                                   "flat_std, in place"}
     out["frame_stats_c1"] = {"ms": ms8, "config": "5x3x1080x1920 batch, ICRF + running mean/M2 merge",
                              "hbm_frac": (ec1 * 4 + CHANNELS * HEIGHT * WIDTH * 32) / (ms8 * 1e-3) / 1e9 / peak}
     elems3 = 16 * CHANNELS * 2160 * 3840

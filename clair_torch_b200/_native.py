@@ -35,7 +35,9 @@ class MergeDesc(ctypes.Structure):
                 ("interp_mode", _c.c_int32), ("gaussian_weights", _c.c_int32), ("plane", _c.c_int64), ("plane_stride", _c.c_int64),
                 ("curve_row_base_host", _c.c_void_p), ("mean_state_dev", _c.c_void_p), ("wsum_state_dev", _c.c_void_p),
                 ("var_state_dev", _c.c_void_p), ("is_first", _c.c_int32), ("is_final", _c.c_int32), ("radiance_f64", _c.c_int32),
-                ("reserved", _c.c_int32), ("radiance_dev", _c.c_void_p), ("sigma_dev", _c.c_void_p)]
+                ("reserved", _c.c_int32), ("radiance_dev", _c.c_void_p), ("sigma_dev", _c.c_void_p),
+                ("dark_dev", _c.c_void_p), ("dark_std_dev", _c.c_void_p), ("height", _c.c_int32), ("width", _c.c_int32),
+                ("dark_threshold", _c.c_float), ("dark_alpha", _c.c_float)]
 
 
 # every symbol include/clair_b200.h declares, with its ctypes prototype

@@ -42,16 +42,18 @@ __global__ void __launch_bounds__(256) dark_mix_rows_kernel(const float *__restr
         const int col = static_cast<int>(grp) * VEC;
         const bool chained_left = lane > 0 && grp > 0;
         const bool chained_right = lane < 31 && grp + 1 < groups_per_row;
-        float x[VEC], blur[VEC];
-        blur3_row_group<VEC>(val + slab, static_cast<int>(row), col, g, active, chained_left, chained_right, x, blur);
-        if (!active) continue;
-        const int64_t o = slab + static_cast<int64_t>(item) * VEC;
+        RowGroup<VEC> rg;
+        row_group_load<VEC>(val + slab, static_cast<int>(row), col, g, active, chained_left, chained_right, rg);
+        const int64_t o = slab + static_cast<int64_t>(active ? item : 0u) * VEC;
         const Pack<VEC> dk = load_stream<VEC>(dark + o);
         Pack<VEC> sv, ds, xo, so;
         if constexpr (HAS_STD) {
             sv = load_stream<VEC>(std + o);
             ds = load_stream<VEC>(dark_std + o);
         }
+        float x[VEC], blur[VEC];
+        row_group_blur<VEC>(rg, col, g, chained_left, chained_right, x, blur);
+        if (!active) continue;
 #pragma unroll
         for (int k = 0; k < VEC; ++k)
             dark_mix_value<HAS_STD>(x[k], blur[k], HAS_STD ? sv.v[k] : 0.0f, dk.v[k], HAS_STD ? ds.v[k] : 0.0f, g, xo.v[k], so.v[k]);
@@ -240,7 +242,7 @@ extern "C" int clair_dark_field_mix(const float *val_dev, const float *std_dev, 
     if (vec > 1 && plane / vec < (1ll << 31)) {
         DarkGeometry g{height, width, threshold, alpha, -alpha * 1.4426950408889634f};
         const int64_t want = (plane / vec + 255) / 256;
-        const unsigned gx = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(want, (8ll * device_sm_count() + slabs - 1) / slabs)));
+        const unsigned gx = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(want, resident_blocks_per_channel(8, static_cast<int>(slabs)))));
         dim3 grid(gx, static_cast<unsigned>(slabs));
         const bool has_std = std_out_dev != nullptr;
         if (vec == 4) {
@@ -277,7 +279,7 @@ extern "C" int clair_flat_field_correct(void *value_dev, int value_f64, float *s
         if (q && reinterpret_cast<uintptr_t>(q) % 16 != 0) vec4 = false;
     const int vec = vec4 ? 4 : 1;
     const int64_t items = plane / vec;
-    const unsigned rblocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((items + 511) / 512, (8 * device_sm_count() + n_channels - 1) / n_channels)));
+    const unsigned rblocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((items + 511) / 512, resident_blocks_per_channel(8, n_channels))));
     dim3 rgrid(rblocks, n_channels), agrid(static_cast<unsigned>((items + 255) / 256), n_channels, n_images);
 #define FLAT_LAUNCH(V, VEC)                                                                                                    \
     do {                                                                                                                       \

@@ -20,43 +20,54 @@ struct DarkGeometry {
     float neg_alpha_log2e;      // -alpha * log2(e)
 };
 
-// All 32 lanes of the warp must call this together (`active` = this lane owns real pixels).
+// Two phases, so that a caller can put the loads of several planes in flight before the first shuffle (the compiler
+// does not move loads across warp-synchronous instructions):
+//   row_group_load   three row segments of VEC pixels (rows above / at / below, reflect padding) plus, for a warp's end
+//                    lanes only, the single neighbour pixels the adjacent lanes cannot supply (predicated loads)
+//   row_group_blur   neighbours by shuffle, 9-tap blur.  All 32 lanes of the warp must call it together.
 //   plane: first element of the (H, W) plane;  row, col: position of the lane's first pixel (col % VEC == 0, W % VEC == 0)
-//   chained: the lane to the left / right holds the adjacent pixels of the same row
+//   active: the lane owns real pixels;  chained_*: the lane to the left / right holds the adjacent pixels of the same row
 template <int VEC>
-__device__ __forceinline__ void blur3_row_group(const float *__restrict__ plane, int row, int col, const DarkGeometry &g,
-                                                bool active, bool chained_left, bool chained_right, float (&center)[VEC],
-                                                float (&blur)[VEC]) {
+struct RowGroup {
+    Pack<VEC> seg[3];
+    float edge_l[3], edge_r[3];
+};
+
+template <int VEC>
+__device__ __forceinline__ void row_group_load(const float *__restrict__ plane, int row, int col, const DarkGeometry &g, bool active,
+                                               bool chained_left, bool chained_right, RowGroup<VEC> &rg) {
     static_assert(VEC == 2 || VEC == 4, "row groups are 2 or 4 pixels wide");
     const int rows[3] = {row == 0 ? 1 : row - 1, row, row == g.H - 1 ? g.H - 2 : row + 1};     // reflect padding
-    Pack<VEC> seg[3];
+    const bool need_l = active && !chained_left && col > 0, need_r = active && !chained_right && col + VEC < g.W;
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
+        const float *seg = plane + static_cast<int64_t>(rows[j]) * g.W + col;
         if (active) {
-            seg[j] = load_stream<VEC>(plane + static_cast<int64_t>(rows[j]) * g.W + col);
+            rg.seg[j] = load_stream<VEC>(seg);
         } else {
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) seg[j].v[k] = 0.0f;
+            for (int k = 0; k < VEC; ++k) rg.seg[j].v[k] = 0.0f;
         }
+        rg.edge_l[j] = need_l ? __ldg(seg - 1) : 0.0f;
+        rg.edge_r[j] = need_r ? __ldg(seg + VEC) : 0.0f;
     }
+}
+
+template <int VEC>
+__device__ __forceinline__ void row_group_blur(const RowGroup<VEC> &rg, int col, const DarkGeometry &g, bool chained_left,
+                                               bool chained_right, float (&center)[VEC], float (&blur)[VEC]) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) { center[k] = seg[1].v[k]; blur[k] = 0.0f; }
+    for (int k = 0; k < VEC; ++k) { center[k] = rg.seg[1].v[k]; blur[k] = 0.0f; }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-        float left = __shfl_up_sync(0xffffffffu, seg[j].v[VEC - 1], 1);
-        float right = __shfl_down_sync(0xffffffffu, seg[j].v[0], 1);
-        if (!chained_left) {
-            left = seg[j].v[1];                                                        // col == 0: x[-1] = x[1]
-            if (active && col > 0) left = __ldg(plane + static_cast<int64_t>(rows[j]) * g.W + col - 1);
-        }
-        if (!chained_right) {
-            right = seg[j].v[VEC - 2];                                                 // row end: x[W] = x[W-2]
-            if (active && col + VEC < g.W) right = __ldg(plane + static_cast<int64_t>(rows[j]) * g.W + col + VEC);
-        }
+        float left = __shfl_up_sync(0xffffffffu, rg.seg[j].v[VEC - 1], 1);
+        float right = __shfl_down_sync(0xffffffffu, rg.seg[j].v[0], 1);
+        if (!chained_left) left = (col > 0) ? rg.edge_l[j] : rg.seg[j].v[1];                     // col == 0: x[-1] = x[1]
+        if (!chained_right) right = (col + VEC < g.W) ? rg.edge_r[j] : rg.seg[j].v[VEC - 2];     // row end: x[W] = x[W-2]
         float ext[VEC + 2];
         ext[0] = left;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) ext[k + 1] = seg[j].v[k];
+        for (int k = 0; k < VEC; ++k) ext[k + 1] = rg.seg[j].v[k];
         ext[VEC + 1] = right;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
@@ -78,7 +89,7 @@ __device__ __forceinline__ void dark_mix_value(float x, float blur, float s, flo
     x_out = fmaf(m, blur, (1.0f - m) * x);
     if constexpr (HAS_STD) {
         const float t = (blur - x) * g.alpha * m * (1.0f - m) * dark_std;
-        s_out = sqrtf(fmaf(s, s, t * t));
+        s_out = sqrt_approx(fmaf(s, s, t * t));
     }
 }
 

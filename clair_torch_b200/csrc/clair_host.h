@@ -25,6 +25,13 @@ void fill_rows(CurveRows &rows, const int32_t *curve_row_base_host, int n_channe
 
 int device_sm_count();
 
+// Grid x-extent of a persistent kernel launched as (x, n_channels) blocks with `blocks_per_sm` co-resident blocks per
+// SM: the largest x whose x * n_channels blocks are ALL resident at once.  Rounded DOWN on purpose — one block more
+// than fits waits for a free slot and then runs its full share of the work alone, doubling the kernel's duration.
+inline int64_t resident_blocks_per_channel(int blocks_per_sm, int n_channels) {
+    return std::max<int64_t>(1, static_cast<int64_t>(device_sm_count()) * std::max(blocks_per_sm, 1) / std::max(n_channels, 1));
+}
+
 // Developer tuning knobs (clair_set_tuning); 0 = library default.
 struct Tuning {
     int hdr_vec = 0;            // cap the pixels per thread of the HDR-merge kernel (1, 2, 4)

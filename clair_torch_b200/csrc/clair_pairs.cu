@@ -773,7 +773,7 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
             int per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
             per_sm = g_tuning.stats_blocks_per_sm > 0 ? g_tuning.stats_blocks_per_sm : std::max(per_sm, 1);
-            const int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, (static_cast<int64_t>(device_sm_count()) * per_sm + n_channels - 1) / n_channels));
+            const int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, resident_blocks_per_channel(per_sm, n_channels)));
             kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), warps * 32, smem, s>>>(p);
             return 0;
         };
@@ -885,7 +885,7 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
             per_sm = g_tuning.grad_blocks_per_sm > 0 ? g_tuning.grad_blocks_per_sm : std::max(per_sm, 1);
             const int64_t gx = std::min<int64_t>((n_groups + warps - 1) / warps,
-                                                 std::max<int64_t>(1, (static_cast<int64_t>(device_sm_count()) * per_sm + n_channels - 1) / n_channels));
+                                                 std::max<int64_t>(1, resident_blocks_per_channel(per_sm, n_channels)));
             kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), warps * 32, smem, s>>>(p);
             return 0;
         };

@@ -3,6 +3,7 @@
 // loads, the ICRF table lives in shared memory, all per-pixel reductions stay in registers and the outputs
 // are written once.  See DESIGN.md §3 for the derivation of the single-pass variance form.
 #include "clair_common.cuh"
+#include "clair_dark.cuh"
 #include "clair_host.h"
 
 #include <cstdio>
@@ -168,6 +169,9 @@ struct HdrParams {
     float std_value;          // multiplier or constant
     float code_max;           // integer ingest: x = fl32(code) / fl32(code_max)   (CastTo + Normalize)
     int src;                  // kSrcF32 / kSrcU8 / kSrcU16 (read by the all-modes kernel only; the others take it as a template)
+    const float *dark;        // fused dark-field mix (hdr_merge_dark_kernel): dark frames and their std, shaped like val
+    const float *dark_std;
+    DarkGeometry dg;
     CurveRows rows;
     FrameScale scale;
 };
@@ -422,6 +426,103 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
             }
         }
         hdr_finish<VEC, HAS_STD, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int n = 0; n < NF; ++n) {
+                const float g = fmaf(alpha, R[n][k], gamma * Q[n][k]);
+                acc = fmaf(g, g, acc);
+            }
+            return acc;
+        });
+    }
+}
+
+// ---- the fixed-N kernel with the dark-field mix fused into its load ----------------------
+// x' = m B(x) + (1 - m) x and s_eff (clair_dark.cuh) are formed in registers from the raw frame, its std and the dark
+// frame + std, so the mixed stack never exists in memory: 4 input stacks are read once instead of the pre-pass
+// writing and the merge re-reading two more.  2 pixels of one row per thread; the loop bound is warp-uniform because
+// the blur takes its left / right neighbours from the adjacent lanes.
+constexpr int kDarkChunk = 3;      // frames whose 18 loads are in flight together (chunks of 1..3 measured within 3 %)
+
+template <int NF, bool SINGLE>
+__global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrParams p) {
+    constexpr int VEC = 2;
+    extern __shared__ float2 s_tab[];
+    const int C = p.n_channels, L = p.lut;
+    const bool has_model = p.theta != nullptr;
+    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
+    __syncthreads();
+    const int c = blockIdx.y;
+    const int64_t frame_stride = static_cast<int64_t>(C) * p.stride;
+    const float lm1 = static_cast<float>(L - 1);
+    const bool gaussian = p.gaussian != 0;
+    const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
+    const uint32_t groups_per_row = static_cast<uint32_t>(p.dg.W / VEC);
+    const uint32_t item_stride = gridDim.x * kBlock;
+    const uint32_t first_item = blockIdx.x * kBlock + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u;
+    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
+    const uint32_t tab_bias = curve_row_bias(s_tab);
+    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
+    const float *val = static_cast<const float *>(p.val);
+
+    for (uint32_t item = first_item; item - lane < n_items; item += item_stride, cur.advance()) {
+        const bool active = item < n_items;
+        const uint32_t row = active ? item / groups_per_row : 0u;
+        const uint32_t grp = item - row * groups_per_row;
+        const int col = static_cast<int>(grp) * VEC;
+        const bool chained_left = lane > 0 && grp > 0;
+        const bool chained_right = lane < 31 && grp + 1 < groups_per_row;
+        const int64_t off = static_cast<int64_t>(c) * p.stride + (active ? item * VEC : 0u);
+        uint32_t bias[VEC];
+        {
+            uint32_t u = cur.u0;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                bias[k] = tab_bias + u * row_bytes;
+                u = (u + 1 == cur.C) ? 0u : u + 1;
+            }
+        }
+        float wsum[VEC], wv[VEC], R[NF][VEC], Q[NF][VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; }
+        // frames in chunks of kDarkChunk: all loads of a chunk are issued before its first shuffle
+#pragma unroll
+        for (int n0 = 0; n0 < NF; n0 += kDarkChunk) {
+            RowGroup<VEC> rg[kDarkChunk];
+            Pack<VEC> sv[kDarkChunk], dk[kDarkChunk], ds[kDarkChunk];
+#pragma unroll
+            for (int j = 0; j < kDarkChunk; ++j) {
+                if (n0 + j < NF) {
+                    const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
+                    row_group_load<VEC>(val + static_cast<int64_t>(n0 + j) * frame_stride + static_cast<int64_t>(c) * p.stride,
+                                        static_cast<int>(row), col, p.dg, active, chained_left, chained_right, rg[j]);
+                    sv[j] = load_stream<VEC>(p.std + o);
+                    dk[j] = load_stream<VEC>(p.dark + o);
+                    ds[j] = load_stream<VEC>(p.dark_std + o);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kDarkChunk; ++j) {
+                if (n0 + j < NF) {
+                    float x[VEC], blur[VEC];
+                    row_group_blur<VEC>(rg[j], col, p.dg, chained_left, chained_right, x, blur);
+                    const float it = p.scale.inv_t[n0 + j];
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) {
+                        float xm, sm;
+                        dark_mix_value<true>(x[k], blur[k], sv[j].v[k], dk[j].v[k], ds[j].v[k], p.dg, xm, sm);
+                        const HdrTerms t = hdr_terms(xm, sm, it, has_model, gaussian, bias[k], lm1, true);
+                        wsum[k] += t.w;
+                        wv[k] += t.wv;
+                        R[n0 + j][k] = t.R;
+                        Q[n0 + j][k] = t.Q;
+                    }
+                }
+            }
+        }
+        if (!active) continue;
+        hdr_finish<VEC, true, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
             float acc = 0.0f;
 #pragma unroll
             for (int n = 0; n < NF; ++n) {
@@ -829,11 +930,18 @@ namespace {
 // interp_mode: CLAIR_INTERP_LINEAR takes the fused fast kernels; LOOKUP / CATMULL the all-modes kernel.
 // plane_stride: elements between channel planes in EVERY buffer (0 = plane); > plane when the call covers a band of rows
 // of larger planes (all pointers then address the band's first pixel).
+struct DarkOptions {          // fused dark-field mix: dark == nullptr switches it off
+    const float *dark = nullptr, *dark_std = nullptr;
+    int height = 0, width = 0;
+    float threshold = 0.0f, alpha = 0.0f;
+};
+
 int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max, const float *std_dev, int std_mode,
                    float std_value, const double *exposure_host, int n_frames, const float *theta_dev, int n_channels,
                    int lut_size, int interp_mode, int64_t plane, int64_t plane_stride, const int32_t *curve_row_base_host,
                    int gaussian_weights, double *mean_state_dev, float *wsum_state_dev, float *var_state_dev, int is_first,
-                   int is_final, void *radiance_dev, int radiance_f64, float *sigma_dev, void *stream) {
+                   int is_final, void *radiance_dev, int radiance_f64, float *sigma_dev, void *stream,
+                   const DarkOptions &dark = DarkOptions()) {
     char msg[200];
     auto bad = [&](int code, const char *what) {
         std::snprintf(msg, sizeof(msg), "%s: %s", fn, what);
@@ -864,6 +972,49 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     fill_rows(p.rows, curve_row_base_host, n_channels, plane_stride);
     for (int n = 0; n < n_frames; ++n) p.scale.inv_t[n] = static_cast<float>(1.0 / exposure_host[n]);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (dark.dark != nullptr) {
+        // the fused form covers the configuration the drivers produce; everything else goes through the
+        // clair_dark_field_mix pre-pass
+        const bool ok = src == kSrcF32 && std_mode == kStdTensor && dark.dark_std != nullptr && !all_modes && n_frames <= kMaxFixedFrames &&
+                        dark.width >= 2 && dark.height >= 2 && dark.width % 2 == 0 &&
+                        static_cast<int64_t>(dark.height) * dark.width == plane && plane_stride == plane;
+        if (!ok)
+            return bad(CLAIR_E_MODE, "fused dark-field mix needs fp32 images with std and dark std, a LINEAR model, <= 8 frames, "
+                                     "an even width and whole dense planes; use clair_dark_field_mix otherwise");
+        for (const void *q : {val_dev, static_cast<const void *>(std_dev), static_cast<const void *>(dark.dark), static_cast<const void *>(dark.dark_std),
+                              static_cast<const void *>(wsum_state_dev), static_cast<const void *>(var_state_dev), static_cast<const void *>(sigma_dev),
+                              static_cast<const void *>(radiance_dev), static_cast<const void *>(mean_state_dev)})
+            if (q && reinterpret_cast<uintptr_t>(q) % 16 != 0) return bad(CLAIR_E_ARG, "fused dark-field mix needs 16-byte aligned buffers");
+        p.dark = dark.dark; p.dark_std = dark.dark_std;
+        p.dg = DarkGeometry{dark.height, dark.width, dark.threshold, dark.alpha, -dark.alpha * 1.4426950408889634f};
+        const size_t smem = theta_dev ? sizeof(float2) * n_channels * lut_size : 0;
+        const bool single = is_first && is_final;
+        const int64_t want_blocks = (plane / 2 + kBlock - 1) / kBlock;
+        auto launch_dark = [&](auto kernel) -> int {
+            if (int rc = ensure_smem(kernel, smem)) return rc;
+            int per_sm = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
+            per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : 2);
+            const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want_blocks, resident_blocks_per_channel(per_sm, n_channels)));
+            kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p);
+            return 0;
+        };
+        int rc = 0;
+#define DARK_NF(NF) rc = single ? launch_dark(hdr_merge_dark_kernel<NF, true>) : launch_dark(hdr_merge_dark_kernel<NF, false>)
+        switch (n_frames) {
+            case 1: DARK_NF(1); break;
+            case 2: DARK_NF(2); break;
+            case 3: DARK_NF(3); break;
+            case 4: DARK_NF(4); break;
+            case 5: DARK_NF(5); break;
+            case 6: DARK_NF(6); break;
+            case 7: DARK_NF(7); break;
+            default: DARK_NF(8); break;
+        }
+#undef DARK_NF
+        if (rc) return rc;
+        return launched("hdr_merge_dark_kernel");
+    }
     if (all_modes) {
         FrameScale64 scale{};
         for (int n = 0; n < n_frames; ++n) scale.inv_t[n] = 1.0 / exposure_host[n];
@@ -873,7 +1024,7 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
             int per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
             const int64_t want = (plane + kBlock - 1) / kBlock;
-            const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want, (static_cast<int64_t>(device_sm_count()) * std::max(per_sm, 1) * 2 + n_channels - 1) / n_channels));
+            const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want, resident_blocks_per_channel(std::max(per_sm, 1) * 2, n_channels)));
             kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p, scale);
             return 0;
         };
@@ -926,7 +1077,7 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
         // resident waves per persistent grid: 2 for the register kernel, 3 for the shared-memory-parked one (measured)
         per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : (parked ? 3 : 2));
-        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want_blocks, (static_cast<int64_t>(device_sm_count()) * per_sm + n_channels - 1) / n_channels));
+        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want_blocks, resident_blocks_per_channel(per_sm, n_channels)));
         kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p);
         return 0;
     };
@@ -1031,10 +1182,13 @@ int std_mode_of(const clair_merge_desc *d) {
 extern "C" int clair_hdr_merge(const clair_merge_desc *d, void *stream) {
     int src = kSrcF32;
     if (int rc = check_desc("clair_hdr_merge", d, src)) return rc;
+    DarkOptions dark;
+    dark.dark = d->dark_dev; dark.dark_std = d->dark_std_dev; dark.height = d->height; dark.width = d->width;
+    dark.threshold = d->dark_threshold; dark.alpha = d->dark_alpha;
     return hdr_merge_impl("clair_hdr_merge", d->val_dev, src, d->code_max, d->std_dev, std_mode_of(d), d->std_value, d->exposure_host,
                           d->n_frames, d->theta_dev, d->n_channels, d->lut_size, d->interp_mode, d->plane, d->plane_stride,
                           d->curve_row_base_host, d->gaussian_weights, d->mean_state_dev, d->wsum_state_dev, d->var_state_dev,
-                          d->is_first, d->is_final, d->radiance_dev, d->radiance_f64, d->sigma_dev, stream);
+                          d->is_first, d->is_final, d->radiance_dev, d->radiance_f64, d->sigma_dev, stream, dark);
 }
 
 // Host-resident stack: the copy engine moves band b+1 of every frame plane into the device staging buffers while the
@@ -1052,6 +1206,7 @@ extern "C" int clair_hdr_merge_staged(const clair_merge_desc *d, const void *val
     const int std_mode = std_mode_of(d);
     if (std_mode == kStdTensor && !std_host) return fail(CLAIR_E_ARG, "clair_hdr_merge_staged: std staging buffer without std_host");
     if (copy_stream == stream) return fail(CLAIR_E_ARG, "clair_hdr_merge_staged: copy_stream must differ from stream");
+    if (d->dark_dev) return fail(CLAIR_E_MODE, "clair_hdr_merge_staged: the dark-field mix needs whole planes on the device (clair_hdr_merge)");
     // bands of whole 1024-pixel blocks keep every band base 16-byte aligned for all element sizes
     constexpr int64_t kGranule = 1024;
     const int64_t granules = (d->plane + kGranule - 1) / kGranule;
@@ -1247,7 +1402,7 @@ extern "C" int clair_frame_stats_update(const float *val_dev, const float *weigh
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
         const int64_t want = (plane / vec + kBlock - 1) / kBlock;
-        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want, (static_cast<int64_t>(device_sm_count()) * std::max(per_sm, 1) * 2 + n_channels - 1) / n_channels));
+        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want, resident_blocks_per_channel(std::max(per_sm, 1) * 2, n_channels)));
         kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p);
         return 0;
     };

@@ -69,6 +69,7 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
         else:
             images, stds = stage_batch(val_batch, std_batch if std_is_tensor else None, dev, transforms)
             stds = stds if std_is_tensor else std_batch
+        fused_dark = None
         if dark_field_dataset is not None:
             # hot pixels of the matching dark frames select a blurred copy; image-std and dark-std variance terms fold
             # into one effective std (hdr_merge.py:76-92,107-126)
@@ -76,7 +77,10 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
                 raise NotImplementedError("dark-field correction takes normalised fp32 images (not raw integer codes)")
             dark_val, dark_std = matching_dark_frames(main_dataset, dark_field_dataset, index_batch, dev)
             if dark_val is not None:
-                images, stds = kernels.dark_field_mix(images, stds if torch.is_tensor(stds) else None, dark_val, dark_std)
+                if kernels.can_fuse_dark(images, stds, dark_std, interp_mode if table is not None else 2):
+                    fused_dark = (dark_val, dark_std)          # mixed in registers by the merge kernel itself
+                else:
+                    images, stds = kernels.dark_field_mix(images, stds if torch.is_tensor(stds) else None, dark_val, dark_std)
         if table is not None and interp_mode == 1 and stds is not None and weight_fn is None:
             # hdr_merge.py:107-112: autograd.grad of a mean that does not depend on the images
             raise RuntimeError("a LOOKUP model without weight_fn leaves the merged image independent of the input images: "
@@ -90,7 +94,7 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
                                           is_final=upcoming is None, radiance_dtype=out_dtype, device=dev,
                                           host_out=host_out if (upcoming is None and flat_field_dataset is None) else None,
                                           code_max=code_max, interp_mode=interp_mode,
-                                          staged=staged if not images.is_cuda else None)
+                                          staged=staged if not images.is_cuda else None, dark=fused_dark)
         current = upcoming
     if result is None:
         raise ValueError("the dataloader yielded no batches")

@@ -182,7 +182,7 @@ def _code_stack(t: torch.Tensor, allow_pinned: bool) -> torch.Tensor:
 def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
                      theta: Optional[torch.Tensor], gaussian_weights: bool, is_final: bool,
                      radiance_dtype: torch.dtype = _F64, row_base=None, device=None, host_out=None, code_max=None,
-                     interp_mode: int = _native.INTERP_LINEAR, staged: Optional[bool] = None, bands: int = 16):
+                     interp_mode: int = _native.INTERP_LINEAR, staged: Optional[bool] = None, bands: int = 16, dark=None):
     """One batch of compute_hdr_image (inference/hdr_merge.py:95-128).  Returns (radiance, sigma) when
     `is_final`, else None.  `exposure` is the collated float64 'exposure_time' (host tensor, array or list).
 
@@ -193,6 +193,10 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     kernel read the host memory itself (zero-copy).
 
     `interp_mode`: the model's InterpMode (LINEAR: fused fast kernels; LOOKUP / CATMULL: the all-modes kernel).
+
+    `dark=(dark_val, dark_std)` (stacks shaped like `val`, or with a leading 1) fuses the dark-field correction of
+    inference/hdr_merge.py:76-92,117-126 into the kernel's load when `can_fuse_dark` says so; otherwise run
+    `dark_field_mix` first and pass its outputs.
 
     Integer ingest: `val` may hold raw uint8 / uint16 codes; the kernel then applies the reference's
     CastTo(float32) + Normalize(max_val=code_max, min_val=0) itself (code_max defaults to 255 / 65535), and `std` may be
@@ -270,6 +274,13 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     desc.mean_state_dev, desc.wsum_state_dev, desc.var_state_dev = _ptr(state.mean), _ptr(state.wsum), _ptr(state.var)
     desc.is_first, desc.is_final, desc.radiance_f64 = int(is_first), int(is_final), int(radiance_dtype == _F64)
     desc.radiance_dev, desc.sigma_dev = _ptr(radiance), _ptr(sigma)
+    if dark is not None:
+        dark_val, dark_std = dark
+        if not can_fuse_dark(val, std, dark_std, interp_mode if th is not None else _native.INTERP_LINEAR):
+            raise ValueError("this batch cannot take the fused dark-field path (see can_fuse_dark): use dark_field_mix first")
+        dark_val, dark_std = _dark_stack(dark_val, val, "dark_field_val"), _dark_stack(dark_std, val, "dark_field_std")
+        desc.dark_dev, desc.dark_std_dev, desc.height, desc.width = _ptr(dark_val), _ptr(dark_std), h, w
+        desc.dark_threshold, desc.dark_alpha = DARK_THRESHOLD, DARK_ALPHA
     on_host = not val.is_cuda
     if staged is None:
         # measured (profiles/README.md): fp32 stacks are input-bound and gain from the copy engine's faster host reads;
@@ -395,6 +406,23 @@ def curve_penalties(theta: torch.Tensor, alpha: float, beta: float, gamma: float
 
 
 DARK_THRESHOLD, DARK_ALPHA = 0.05, 50.0     # inference/hdr_merge.py:90, common/general_functions.py:442
+
+
+def _dark_stack(t: torch.Tensor, like: torch.Tensor, name: str) -> torch.Tensor:
+    t = _stack(t.to(like.device), name)
+    if t.shape[0] == 1 and like.shape[0] > 1:
+        t = t.expand(like.shape[0], -1, -1, -1).contiguous()
+    if t.shape != like.shape:
+        raise ValueError(f"{name} batch dimension must be 1 or {like.shape[0]}, got {t.shape[0]}")
+    return t
+
+
+def can_fuse_dark(val, std, dark_std, interp_mode: int = _native.INTERP_LINEAR) -> bool:
+    """Whether hdr_merge_update can apply the dark-field correction inside the merge kernel (clair_merge_desc.dark_dev):
+    device-resident fp32 images with std and dark std, LINEAR model (or none), at most 8 frames, even width."""
+    return (torch.is_tensor(val) and val.is_cuda and val.dtype == _F32 and val.dim() == 4 and torch.is_tensor(std)
+            and dark_std is not None and interp_mode == _native.INTERP_LINEAR and val.shape[0] <= 8
+            and val.shape[3] % 2 == 0 and val.shape[2] >= 2)
 
 
 def dark_field_mix(val: torch.Tensor, std: Optional[torch.Tensor], dark: torch.Tensor, dark_std: Optional[torch.Tensor],

@@ -159,6 +159,8 @@ CLAIR_API int clair_hdr_merge_codes(const void *codes_dev, int code_bytes, float
  *                  (c * plane_stride + first_pixel) mod C.
  *   code_bytes     0: val_dev is fp32 and std_dev (may be NULL) its std, std_mode ignored;
  *                  1 / 2: val_dev holds uint8 / uint16 codes, see clair_hdr_merge_codes
+ *   dark_dev ...   dark-field correction of the batch fused into the load (inference/hdr_merge.py:76-92,117-126): the
+ *                  mixed images and their effective std are formed in registers instead of by a pre-pass
  * struct_bytes must be sizeof(clair_merge_desc); all other fields as the arguments of clair_hdr_merge_update.
  */
 typedef struct clair_merge_desc {
@@ -188,6 +190,16 @@ typedef struct clair_merge_desc {
     int32_t reserved;
     void *radiance_dev;
     float *sigma_dev;
+    /* fused dark-field correction (NULL dark_dev = off): see clair_dark_field_mix below for the arithmetic.  dark_dev /
+     * dark_std_dev are shaped like val_dev; height * width must equal plane.  Covered: fp32 images with std and dark std,
+     * LINEAR model or none, <= 8 frames per batch, even width, dense planes, 16-byte aligned buffers — otherwise the call
+     * returns CLAIR_E_MODE and the clair_dark_field_mix pre-pass is the way. */
+    const float *dark_dev;
+    const float *dark_std_dev;
+    int32_t height;
+    int32_t width;
+    float dark_threshold;
+    float dark_alpha;
 } clair_merge_desc;
 
 CLAIR_API int clair_hdr_merge(const clair_merge_desc *desc, void *stream);

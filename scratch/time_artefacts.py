@@ -30,3 +30,13 @@ for dt in (torch.float32, torch.float64):
     ms = timed(lambda k: kernels.flat_field_correct_(rads[k % 6], sigs[k % 6], flat, fstd, True))
     b = C*H*W*(2*rads[0].element_size() + 8 + 8 + rads[0].element_size() + 4)
     print(f"flat field {dt}: {ms*1e3:.1f} us  ({b/ms/1e6:.0f} GB/s incl. the reduce pass reads)")
+# fused dark merge vs pre-pass + merge
+t_host = np.ascontiguousarray(1e-3 * 2.0 ** np.arange(N))
+def fused(k):
+    v, s, d, ds = sets[k % 3]
+    kernels.hdr_merge_update(kernels.HdrMergeState(), v, s, t_host, theta, True, True, radiance_dtype=torch.float32, dark=(d, ds))
+def two_pass(k):
+    v, s, d, ds = sets[k % 3]
+    m, se = kernels.dark_field_mix(v, s, d, ds)
+    kernels.hdr_merge_update(kernels.HdrMergeState(), m, se, t_host, theta, True, True, radiance_dtype=torch.float32)
+print(f"dark-field merge fused: {timed(fused)*1e3:.1f} us;  pre-pass + merge: {timed(two_pass)*1e3:.1f} us")

@@ -583,6 +583,41 @@ def test_artefact_corrections_golden(ct, name):
         assert max_rel(lsig.numpy(), z["lin_sigma"][n]) < TOL
 
 
+@pytest.mark.parametrize("shape", [(4, 3, 50, 132), (5, 3, 33, 130), (3, 1, 2, 2), (8, 3, 21, 70), (2, 3, 64, 64)])
+def test_dark_field_row_groups_and_fused_merge(ct, shape):
+    """Even widths take the row-group pre-pass kernel (4 or 2 pixels per thread, neighbours by lane shuffle) and, inside
+    compute_hdr_image, the merge kernel with the dark-field mix fused into its load: both against the oracle, and the
+    fused merge against pre-pass + merge (same arithmetic, so 1e-6), for one batch and for several."""
+    from clair_torch_b200 import kernels
+    n, c, h, w = shape
+    rng = np.random.default_rng(n * 100 + w)
+    val, std, t = ct.synthetic.make_stack(n, c, h, w, bits=16, seed=w)
+    dark = rng.uniform(0, 0.02, size=val.shape).astype(np.float32)
+    hot = rng.random(val.shape) < 0.1
+    dark[hot] = rng.uniform(0.03, 0.4, size=int(hot.sum())).astype(np.float32)
+    dark_std = (0.1 * dark + 1e-3).astype(np.float32)
+    d_val, d_std = torch.from_numpy(dark).to(DEV), torch.from_numpy(dark_std).to(DEV)
+    o_mixed, o_seff = orc.dark_field_mix(val.numpy(), std.numpy(), dark, dark_std)
+    mixed, seff = kernels.dark_field_mix(val.to(DEV), std.to(DEV), d_val, d_std)
+    assert max_rel(mixed.cpu().numpy(), o_mixed, 1e-12) < 2e-6
+    assert max_rel(seff.cpu().numpy(), o_seff, 1e-12) < 5e-6
+    only_val, none = kernels.dark_field_mix(val.to(DEV), None, d_val, None)
+    assert none is None and torch.equal(only_val, mixed)
+    theta = ct.synthetic.reference_curve(c).to(DEV)
+    assert kernels.can_fuse_dark(val.to(DEV), std.to(DEV), d_std)
+    for batch in (n, max(1, n // 2)):
+        st_f, st_p = kernels.HdrMergeState(), kernels.HdrMergeState()
+        for a in range(0, n, batch):
+            sl = slice(a, min(a + batch, n))
+            last = sl.stop == n
+            fused = kernels.hdr_merge_update(st_f, val[sl].to(DEV), std[sl].to(DEV), t[sl], theta, True, last, dark=(d_val[sl], d_std[sl]))
+            pre = kernels.hdr_merge_update(st_p, mixed[sl], seff[sl], t[sl], theta, True, last)
+        assert max_rel(fused[0].cpu().numpy(), pre[0].cpu().numpy()) < 1e-6
+        assert max_rel(fused[1].cpu().numpy(), pre[1].cpu().numpy()) < 5e-6     # different FMA contraction in the two kernels
+        want_r, want_s = orc.hdr_merge(o_mixed, o_seff, t, theta.cpu().numpy(), True, batch)
+        assert max_rel(fused[0].cpu().numpy(), want_r) < TOL and max_rel(fused[1].cpu().numpy(), want_s) < TOL
+
+
 def test_dark_mix_and_flat_field_vs_oracle_larger(ct):
     from clair_torch_b200 import kernels
     rng = np.random.default_rng(9)
