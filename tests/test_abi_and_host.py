@@ -61,6 +61,53 @@ def test_argument_validation_without_gpu(native):
     assert lib.clair_set_tuning(b"no_such_knob", 1) == -1
 
 
+def test_descriptor_entry_points_validate_without_gpu(native):
+    lib = native.load()
+    assert lib.clair_hdr_merge(None, None) == -1 and b"null descriptor" in lib.clair_last_error()
+    d = native.MergeDesc()
+    d.struct_bytes = 8                                               # a caller built against another layout
+    assert lib.clair_hdr_merge(ctypes.byref(d), None) == -1 and b"bytes" in lib.clair_last_error()
+    d.struct_bytes = ctypes.sizeof(native.MergeDesc)
+    d.code_bytes = 3
+    assert lib.clair_hdr_merge(ctypes.byref(d), None) == -3
+    d.code_bytes = 0
+    assert lib.clair_hdr_merge(ctypes.byref(d), None) == -1          # null val / exposure
+    buf = ctypes.create_string_buffer(4096)
+    t = np.ones(4)
+    d.val_dev = d.std_dev = d.radiance_dev = d.sigma_dev = ctypes.addressof(buf)
+    d.exposure_host, d.n_frames, d.n_channels, d.lut_size, d.plane = t.ctypes.data, 4, 3, 256, 16
+    d.theta_dev, d.interp_mode, d.is_first, d.is_final = ctypes.addressof(buf), 9, 1, 1
+    assert lib.clair_hdr_merge(ctypes.byref(d), None) == -3 and b"interp_mode" in lib.clair_last_error()
+    d.interp_mode, d.plane_stride = native.INTERP_LINEAR, 8
+    assert lib.clair_hdr_merge(ctypes.byref(d), None) == -1 and b"plane_stride" in lib.clair_last_error()
+    d.plane_stride = 0
+    d.dark_dev, d.dark_std_dev, d.height, d.width = ctypes.addressof(buf), ctypes.addressof(buf), 3, 5    # odd width, H*W != plane
+    assert lib.clair_hdr_merge(ctypes.byref(d), None) == -3 and b"clair_dark_field_mix" in lib.clair_last_error()
+    d.dark_dev = None
+    assert lib.clair_hdr_merge_staged(ctypes.byref(d), None, None, 4, None, None) == -1                    # no host stack
+    assert lib.clair_hdr_merge_staged(ctypes.byref(d), ctypes.addressof(buf), ctypes.addressof(buf), 4, None, None) == -1
+    assert b"copy_stream" in lib.clair_last_error()
+    assert lib.clair_linearize(ctypes.addressof(buf), ctypes.addressof(buf), ctypes.addressof(buf), ctypes.addressof(buf),
+                               ctypes.addressof(buf), 1, 3, 16, 256, native.INTERP_LOOKUP, None, None) == -3   # LOOKUP with std
+
+
+def test_descriptor_layout_matches_the_header(native, tmp_path):
+    """The header is plain C, and ctypes' MergeDesc has the size and field offsets a C compiler gives clair_merge_desc."""
+    import subprocess
+    fields = [name for name, _ in native.MergeDesc._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "clair_b200.h"\nint main(void) {\n'
+                   '    printf("%zu\\n", sizeof(clair_merge_desc));\n'
+                   + "".join(f'    printf("%zu\\n", offsetof(clair_merge_desc, {f}));\n' for f in fields)
+                   + "    return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(native.MergeDesc)
+    assert out[1:] == [getattr(native.MergeDesc, f).offset for f in fields]
+
+
 def test_product_path_refuses_cpu():
     import clair_torch_b200 as ct
     from clair_torch_b200.datasets import ExposureStackDataset, custom_collate
