@@ -363,7 +363,7 @@ def secondary_metrics(dev):
     e2e_lin = (time.perf_counter() - t0) / 9 * 1e3
     out["linearize_c4_frames"]["e2e_ms_per_frame"] = e2e_lin
     out["linearize_c4_frames"]["e2e_mpixel_per_s"] = 24.0 / (e2e_lin * 1e-3)
-    out["linearize_c4_frames"]["e2e_note"] = "pinned host frame (val+std, 576 MB) in, pinned host lin+sigma (576 MB) out, zero-copy"
+    out["linearize_c4_frames"]["e2e_note"] = "pinned host frame (val+std, 576 MB) in, pinned host lin+sigma (576 MB) out; clair_linearize_staged: H2D copy, kernel and D2H copy of successive bands overlapped on three streams"
     del val, std, one_val, one_std, rad, hv, hs
     torch.cuda.empty_cache()
     # 8(f) rows at c1 size: dark-field mix pre-pass, flat-field correction, streaming frame statistics

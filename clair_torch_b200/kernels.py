@@ -28,9 +28,9 @@ def _stream(device: torch.device) -> int:
 _copy_streams: dict = {}
 
 
-def _copy_stream(device: torch.device) -> int:
-    """A per-device side stream for the host-to-device legs of the staged (copy / compute overlapped) entry points."""
-    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+def _copy_stream(device: torch.device, which: str = "in") -> int:
+    """Per-device side streams for the copy legs of the staged (copy / compute overlapped) entry points."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device(), which)
     st = _copy_streams.get(key)
     if st is None:
         st = _copy_streams[key] = torch.cuda.Stream(device=device)
@@ -119,12 +119,14 @@ def icrf_backward_theta(x: torch.Tensor, grad_y: torch.Tensor, channels: int, lu
 
 
 def linearize(val: torch.Tensor, std: Optional[torch.Tensor], theta: torch.Tensor, row_base=None, device=None,
-              pinned_out: bool = False, interp_mode: int = _native.INTERP_LINEAR):
+              pinned_out: bool = False, interp_mode: int = _native.INTERP_LINEAR, staged: Optional[bool] = None,
+              bands: int = 16):
     """(f(x), sqrt((f'(x) std)^2)) per image of an (N, C, H, W) stack.  inference/linearization.py:94-106.
 
     With `device`, `val` / `std` may be pinned host tensors (read over PCIe by the kernel); with `pinned_out` the two
     results are written straight into page-locked host tensors (torch's caching host allocator), which is what
-    linearize_dataset_generator hands to its consumer."""
+    linearize_dataset_generator hands to its consumer.  Host in AND host out is `staged` by default: three streams move
+    band b+1 in, linearise band b and move band b-1 out at the same time (clair_linearize_staged)."""
     lib = _native.load()
     if interp_mode == _native.INTERP_LOOKUP and std is not None:
         # linearization.py:100-105: autograd.grad of an output that does not depend on the image
@@ -142,7 +144,19 @@ def linearize(val: torch.Tensor, std: Optional[torch.Tensor], theta: torch.Tenso
         lin = torch.empty(tuple(val.shape), dtype=_F32, device=dev)
         sigma = torch.empty(tuple(val.shape), dtype=_F32, device=dev)
     keep, rows = _rows(row_base, c)
+    host_to_host = pinned_out and not val.is_cuda and (std is None or not std.is_cuda)
+    if staged is None:
+        staged = host_to_host
+    if staged and not host_to_host:
+        raise ValueError("staged=True is for pinned host inputs with pinned_out=True")
     with torch.cuda.device(dev):
+        if staged:
+            stage = [torch.empty(tuple(val.shape), dtype=_F32, device=dev) if need else None for need in (True, std is not None, True, True)]
+            rc = lib.clair_linearize_staged(_ptr(val), _ptr(std), _ptr(lin), _ptr(sigma), *(_ptr(b) for b in stage), _ptr(th), n, c,
+                                            h * w, th.shape[1], int(interp_mode), rows, int(bands), _copy_stream(dev, "in"),
+                                            _copy_stream(dev, "out"), _stream(dev))
+            _native.check(rc, "clair_linearize_staged")
+            return lin, sigma
         rc = lib.clair_linearize(_ptr(val), _ptr(std), _ptr(th), _ptr(lin), _ptr(sigma), n, c, h * w, th.shape[1],
                                  int(interp_mode), rows, _stream(dev))
     _native.check(rc, "clair_linearize")

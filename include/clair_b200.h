@@ -99,6 +99,19 @@ CLAIR_API int clair_linearize(const float *val_dev, const float *std_dev, const 
                     const int32_t *curve_row_base_host, void *stream);
 
 /*
+ * clair_linearize for images that live in page-locked HOST memory and whose results are wanted there too (the
+ * generator ends with .cpu(), inference/linearization.py:132): the planes are cut into n_bands bands of pixels; band b+1
+ * is copied in (in_stream), band b is linearised (stream) and band b-1 is copied out (out_stream) at the same time, so
+ * both PCIe directions stay busy.  *_stage_dev are device buffers shaped like the host arrays.  The three streams must
+ * differ; when the call returns, `stream` has been made to wait for the last device-to-host copy.
+ */
+CLAIR_API int clair_linearize_staged(const float *val_host, const float *std_host, float *lin_host, float *sigma_host,
+                           float *val_stage_dev, float *std_stage_dev, float *lin_stage_dev, float *sigma_stage_dev,
+                           const float *theta_dev, int n_frames, int n_channels, int64_t plane, int lut_size,
+                           int interp_mode, const int32_t *curve_row_base_host, int n_bands, void *in_stream,
+                           void *out_stream, void *stream);
+
+/*
  * One DataLoader batch of the exposure-weighted HDR merge with first-order uncertainty — replaces the
  * loop body of compute_hdr_image (inference/hdr_merge.py:95-128) including WBOMean.update_values
  * (common/statistics.py:64-109) and the autograd pass at :107-115, in closed form.

@@ -245,6 +245,25 @@ def test_linearize_bit_exact(ct, name):
         assert float(meta["exposure_time"][0]) == float(z["exposure"][n])
 
 
+@pytest.mark.parametrize("shape,bands", [((2, 3, 37, 53), 4), ((1, 3, 64, 96), 16), ((3, 1, 5, 7), 2), ((1, 3, 40, 1000), 64)])
+def test_linearize_staged_host_pipeline_is_bit_identical(ct, shape, bands):
+    """Pinned host frames in, pinned host results out through the three-stream band pipeline (and through the zero-copy
+    kernel): the same bits as the device-resident call, for every interpolation mode."""
+    from clair_torch_b200 import kernels
+    n, c, h, w = shape
+    val, std, _ = ct.synthetic.make_stack(n, c, h, w, bits=16, seed=h)
+    theta = ct.synthetic.reference_curve(c).to(DEV)
+    for mode in (ct._native.INTERP_LINEAR, ct._native.INTERP_CATMULL, ct._native.INTERP_LOOKUP):
+        s_dev = None if mode == ct._native.INTERP_LOOKUP else std.to(DEV)
+        s_host = None if mode == ct._native.INTERP_LOOKUP else std.pin_memory()
+        want = kernels.linearize(val.to(DEV), s_dev, theta, interp_mode=mode)
+        for staged in (True, False):
+            got = kernels.linearize(val.pin_memory(), s_host, theta, device=torch.device(DEV), pinned_out=True, interp_mode=mode,
+                                    staged=staged, bands=bands)
+            torch.cuda.current_stream().synchronize()
+            assert got[0].is_pinned() and torch.equal(got[0], want[0].cpu()) and torch.equal(got[1], want[1].cpu())
+
+
 # ---- linearity measurement ---------------------------------------------------------------------------
 def _linearity_flags(name):
     if name == "linearity_u16_w11":
