@@ -23,6 +23,8 @@ MAX_PAIRS = 2016
 INTERP_LOOKUP = 1
 INTERP_LINEAR = 2
 INTERP_CATMULL = 3
+CODES_PLANAR = 0
+CODES_HWC_BGR = 1
 
 _c = ctypes
 
@@ -35,7 +37,7 @@ class MergeDesc(ctypes.Structure):
                 ("interp_mode", _c.c_int32), ("gaussian_weights", _c.c_int32), ("plane", _c.c_int64), ("plane_stride", _c.c_int64),
                 ("curve_row_base_host", _c.c_void_p), ("mean_state_dev", _c.c_void_p), ("wsum_state_dev", _c.c_void_p),
                 ("var_state_dev", _c.c_void_p), ("is_first", _c.c_int32), ("is_final", _c.c_int32), ("radiance_f64", _c.c_int32),
-                ("reserved", _c.c_int32), ("radiance_dev", _c.c_void_p), ("sigma_dev", _c.c_void_p),
+                ("code_layout", _c.c_int32), ("radiance_dev", _c.c_void_p), ("sigma_dev", _c.c_void_p),
                 ("dark_dev", _c.c_void_p), ("dark_std_dev", _c.c_void_p), ("height", _c.c_int32), ("width", _c.c_int32),
                 ("dark_threshold", _c.c_float), ("dark_alpha", _c.c_float)]
 
@@ -99,7 +101,7 @@ class NativeLibraryError(RuntimeError):
 
 def build(verbose: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into clair_torch_b200/lib/libclair_b200.so (nvcc cross-compiles without a GPU)."""
-    cmd = ["make", "-C", CSRC_DIR, "-j4"]
+    cmd = ["make", "-C", CSRC_DIR, "-j6"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)

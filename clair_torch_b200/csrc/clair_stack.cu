@@ -2,17 +2,9 @@
 // first-order uncertainty.  sm_100a, HBM-bound: every input element is read once with 128-bit streaming
 // loads, the ICRF table lives in shared memory, all per-pixel reductions stay in registers and the outputs
 // are written once.  See DESIGN.md §3 for the derivation of the single-pass variance form.
-#include "clair_common.cuh"
-#include "clair_dark.cuh"
-#include "clair_host.h"
-
-#include <cstdio>
+#include "clair_merge.cuh"
 
 namespace clair {
-
-constexpr int kBlock = 256;
-constexpr int kFrameChunk = 4;          // frames whose loads are in flight together (8 x LDG.128 / thread)
-constexpr float kHdrNegScaleLog2e = -43.28085122666890f;  // -30 * log2(e): training/losses.py:193 default scale 30 (hdr_merge.py:95)
 
 // =====================================================================================================
 // ICRF forward / linearise
@@ -145,570 +137,6 @@ __global__ void __launch_bounds__(kBlock) icrf_catmull_kernel(const ForwardParam
     }
 }
 
-// =====================================================================================================
-// HDR merge + uncertainty
-// =====================================================================================================
-struct HdrParams {
-    const void *val;          // fp32 values, or uint8 / uint16 codes (integer ingest)
-    const float *std;
-    const float *theta;       // nullptr = identity
-    double *mean_state;
-    float *wsum_state;
-    float *var_state;
-    void *radiance;
-    float *sigma;
-    int64_t plane;            // pixels of this call (a whole plane, or a band of rows of it)
-    int64_t stride;           // elements between channel planes in every buffer (= plane unless the call is a row band)
-    int n_frames;
-    int n_channels;
-    int lut;
-    int gaussian;
-    int is_first;
-    int is_final;
-    int radiance_f64;
-    int std_mode;             // kStdNone / kStdTensor / kStdMultiplier / kStdConstant
-    float std_value;          // multiplier or constant
-    float code_max;           // integer ingest: x = fl32(code) / fl32(code_max)   (CastTo + Normalize)
-    int src;                  // kSrcF32 / kSrcU8 / kSrcU16 (read by the all-modes kernel only; the others take it as a template)
-    const float *dark;        // fused dark-field mix (hdr_merge_dark_kernel): dark frames and their std, shaped like val
-    const float *dark_std;
-    DarkGeometry dg;
-    CurveRows rows;
-    FrameScale scale;
-};
-
-constexpr int kStdNone = 0, kStdTensor = 1, kStdMultiplier = 2, kStdConstant = 3;
-constexpr int kSrcF32 = 0, kSrcU8 = 1, kSrcU16 = 2;
-
-// One frame's VEC pixel values.  SRC = kSrcF32: the fp32 stack the reference hands over.  kSrcU8 / kSrcU16: the raw
-// integer codes, normalised in-register exactly like the reference's CPU transforms do it (CastTo(float32) then
-// Normalize(max_val, min_val=0): an IEEE fp32 division, clair_torch/common/general_functions.py:378) — 8-bit codes
-// go through a 256-entry table of those quotients, 16-bit codes through __fdiv_rn.
-template <int SRC, int VEC>
-__device__ __forceinline__ Pack<VEC> load_pixels(const void *base, int64_t o, float code_max, const float *s_x) {
-    if constexpr (SRC == kSrcF32) {
-        return load_stream<VEC>(static_cast<const float *>(base) + o);
-    } else if constexpr (SRC == kSrcU8) {
-        static_assert(VEC == 4, "integer ingest is 4 pixels per thread");
-        const uint32_t w = __ldcs(reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(base) + o));
-        Pack<VEC> r;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r.v[k] = s_x[(w >> (8 * k)) & 0xffu];
-        return r;
-    } else {
-        static_assert(VEC == 4, "integer ingest is 4 pixels per thread");
-        const uint2 w = __ldcs(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(base) + o));
-        Pack<VEC> r;
-        r.v[0] = __fdiv_rn(static_cast<float>(w.x & 0xffffu), code_max);
-        r.v[1] = __fdiv_rn(static_cast<float>(w.x >> 16), code_max);
-        r.v[2] = __fdiv_rn(static_cast<float>(w.y & 0xffffu), code_max);
-        r.v[3] = __fdiv_rn(static_cast<float>(w.y >> 16), code_max);
-        return r;
-    }
-}
-
-// The std of one frame's VEC pixels: a tensor, or synthesised the way MultiFileMapDataset does for missing std
-// images (clair_torch/datasets/base.py:128-133): value * multiplier, or a constant.
-// STD: 1 = tensor, 2 = synthesised (compile-time, so the tensor loads of the fp32 path stay unconditional and are
-// hoisted with the value loads)
-template <int VEC, int STD>
-__device__ __forceinline__ Pack<VEC> load_std(const HdrParams &p, int64_t o, const Pack<VEC> &x) {
-    if constexpr (STD == 1) {
-        return load_stream<VEC>(p.std + o);
-    } else {
-        Pack<VEC> r;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) r.v[k] = (p.std_mode == kStdMultiplier) ? __fmul_rn(x.v[k], p.std_value) : p.std_value;
-        return r;
-    }
-}
-
-// Per frame element (all fp32):
-//   w = exp(-30 (x-.5)^2) | 1,   q = w'/w = -60 (x-.5) | 0,   v = f(x)/t
-//   R = s w (f'(x)/t + q v),     Q = s w q
-// so that  s * d mean_new/dx = alpha R + gamma Q  with the per-pixel constants
-//   alpha = (W_B/W) / (W_B + 1e-6),   gamma = (W_A/W^2)(mean_B - mean_A) - alpha mean_B
-// (closed form of the autograd pass of inference/hdr_merge.py:107-115).
-struct HdrTerms {
-    float w, wv, R, Q;
-};
-
-__device__ __forceinline__ HdrTerms hdr_terms(float x, float s, float it, bool has_model, bool gaussian,
-                                              uint32_t row_bias, float lm1, bool has_std) {
-    HdrTerms o;
-    float f = x, fp = 1.0f;
-    if (has_model) icrf_linear_biased(x, row_bias, lm1, f, fp);
-    float w = 1.0f, q = 0.0f;
-    if (gaussian) {
-        float d;
-        w = gaussian_weight(x, kHdrNegScaleLog2e, d);
-        q = -60.0f * d;
-    }
-    const float v = f * it;
-    o.w = w;
-    o.wv = w * v;
-    if (has_std) {
-        const float ws = w * s;
-        o.R = ws * fmaf(q, v, fp * it);
-        o.Q = ws * q;
-    } else {
-        o.R = 0.0f; o.Q = 0.0f;
-    }
-    return o;
-}
-
-// Merge of the batch sums with the running state (common/statistics.py:88-109) and the output stage, shared by
-// both kernels.  `var_update(k, alpha, gamma)` returns sum_n (alpha R_n + gamma Q_n)^2 for pixel k.
-// SINGLE = the whole stack is this one batch (is_first && is_final): no state traffic, no float64.
-template <int VEC, bool HAS_STD, bool SINGLE, typename VarFn>
-__device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, const float (&wsum)[VEC], const float (&wv)[VEC],
-                                           VarFn var_update) {
-    if constexpr (SINGLE) {
-        Pack<VEC> rad, sg;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            const float wbe = wsum[k] + 1e-6f;                    // statistics.py:76 (fp32 add)
-            float inv = rcp_approx(wbe);
-            inv = fmaf(fmaf(-wbe, inv, 1.0f), inv, inv);          // one Newton step: <= 1 ulp
-            const float mean_b = wv[k] * inv;
-            // W = 0.0 + W_B so W_B/W is exactly 1; an all-zero-weight pixel gives 0/0 = NaN as in the reference
-            const float frac = (wsum[k] != 0.0f) ? 1.0f : __int_as_float(0x7fc00000);
-            rad.v[k] = frac * mean_b;
-            if constexpr (HAS_STD) {
-                const float alpha = frac * inv;
-                sg.v[k] = sqrt_approx(var_update(k, alpha, -alpha * mean_b));
-            }
-        }
-        if (p.radiance_f64) {
-            double r64[VEC];
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) r64[k] = static_cast<double>(rad.v[k]);
-            store_stream_f64<VEC>(static_cast<double *>(p.radiance) + off, r64);
-        } else {
-            store_stream<VEC>(static_cast<float *>(p.radiance) + off, rad);
-        }
-        if constexpr (HAS_STD) store_stream<VEC>(p.sigma + off, sg);
-        return;
-    }
-    double mean_new[VEC];
-    Pack<VEC> wtot, var_new;
-    Pack<VEC> w_a, var_a;
-    double mean_a[VEC];
-    const bool first = p.is_first != 0;
-    if (!first) {
-        w_a = load_stream<VEC>(p.wsum_state + off);
-        if constexpr (HAS_STD) var_a = load_stream<VEC>(p.var_state + off);
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) mean_a[k] = __ldcs(p.mean_state + off + k);
-    } else {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) { w_a.v[k] = 0.0f; var_a.v[k] = 0.0f; mean_a[k] = 0.0; }
-    }
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-        const float wbe = wsum[k] + 1e-6f;
-        float inv = rcp_approx(wbe);
-        inv = fmaf(fmaf(-wbe, inv, 1.0f), inv, inv);
-        const float mean_b = wv[k] * inv;
-        float alpha, gamma;
-        if (first) {
-            const float frac = (wsum[k] != 0.0f) ? 1.0f : __int_as_float(0x7fc00000);
-            mean_new[k] = static_cast<double>(frac * mean_b);
-            wtot.v[k] = wsum[k];
-            alpha = frac * inv;
-            gamma = -alpha * mean_b;
-        } else {
-            const float wt = w_a.v[k] + wsum[k];                  // statistics.py:104
-            const float frac = wsum[k] / wt;                      // statistics.py:106
-            const double dm = static_cast<double>(mean_b) - mean_a[k];
-            mean_new[k] = mean_a[k] + static_cast<double>(frac) * dm;
-            wtot.v[k] = wt;
-            alpha = frac * inv;
-            gamma = static_cast<float>(static_cast<double>(w_a.v[k]) / (static_cast<double>(wt) * wt) * dm) - alpha * mean_b;
-        }
-        if constexpr (HAS_STD) var_new.v[k] = var_a.v[k] + var_update(k, alpha, gamma);
-    }
-    if (p.is_final) {
-        if (p.radiance_f64) {
-            store_stream_f64<VEC>(static_cast<double *>(p.radiance) + off, mean_new);
-        } else {
-            Pack<VEC> r;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) r.v[k] = static_cast<float>(mean_new[k]);
-            store_stream<VEC>(static_cast<float *>(p.radiance) + off, r);
-        }
-        if constexpr (HAS_STD) {
-            Pack<VEC> sg;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) sg.v[k] = sqrt_approx(var_new.v[k]);
-            store_stream<VEC>(p.sigma + off, sg);
-        }
-    } else {
-        store_stream_f64<VEC>(p.mean_state + off, mean_new);
-        store_stream<VEC>(p.wsum_state + off, wtot);
-        if constexpr (HAS_STD) store_stream<VEC>(p.var_state + off, var_new);
-    }
-}
-
-// Table-row bookkeeping of a persistent thread: element (c, pix) reads row (pix + base(c)) mod C, so the VEC
-// row addresses rotate by (stride mod C) per trip; one modulo per thread instead of one per trip.
-template <int VEC>
-struct RowCursor {
-    uint32_t u0, du, C;
-    __device__ __forceinline__ RowCursor(uint32_t first_pix, uint32_t pix_stride, uint32_t row_base, uint32_t channels)
-        : u0((first_pix + row_base) % channels), du(pix_stride % channels), C(channels) {}
-    __device__ __forceinline__ void advance() { u0 += du; u0 = (u0 >= C) ? u0 - C : u0; }
-};
-
-// ---- main kernel: N known at compile time (1..kMaxFixedFrames) -------------------------------------------
-// Persistent blocks; one thread owns VEC adjacent pixels of one channel per loop trip.  All 2N vector loads of
-// the trip are issued before the first use; (R_n, Q_n) stay in registers until mean_B is known, so the variance
-// is a plain sum of squares of the actual (small) per-frame terms: no cancellation, everything in fp32.
-constexpr int kMaxFixedFrames = 8;
-
-template <int VEC, int NF, int STD, bool SINGLE, int SRC>
-__global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams p) {
-    constexpr bool HAS_STD = STD != 0;
-    extern __shared__ float2 s_tab[];
-    const int C = p.n_channels, L = p.lut;
-    const bool has_model = p.theta != nullptr;
-    float *s_x = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));     // kSrcU8: code -> fl32(code)/code_max
-    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
-    if constexpr (SRC == kSrcU8) {
-        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
-    }
-    __syncthreads();
-    const int c = blockIdx.y;
-    const int64_t frame_stride = static_cast<int64_t>(C) * p.stride;
-    const float lm1 = static_cast<float>(L - 1);
-    const bool gaussian = p.gaussian != 0;
-    const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
-    const uint32_t item_stride = gridDim.x * kBlock;
-    const uint32_t first_item = blockIdx.x * kBlock + threadIdx.x;
-    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
-    const uint32_t tab_bias = curve_row_bias(s_tab);
-    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
-
-    for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
-        const uint32_t pix = item * VEC;
-        const int64_t off = static_cast<int64_t>(c) * p.stride + pix;
-        uint32_t bias[VEC];
-        {
-            uint32_t u = cur.u0;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                bias[k] = tab_bias + u * row_bytes;
-                u = (u + 1 == cur.C) ? 0u : u + 1;
-            }
-        }
-        float wsum[VEC], wv[VEC], R[NF][VEC], Q[NF][VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; }
-        {
-            Pack<VEC> xv[NF], sv[NF];
-#pragma unroll
-            for (int n = 0; n < NF; ++n) {
-                const int64_t o = off + static_cast<int64_t>(n) * frame_stride;
-                xv[n] = load_pixels<SRC, VEC>(p.val, o, p.code_max, s_x);
-                if constexpr (HAS_STD) sv[n] = load_std<VEC, STD>(p, o, xv[n]);
-            }
-#pragma unroll
-            for (int n = 0; n < NF; ++n) {
-                const float it = p.scale.inv_t[n];
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) {
-                    const HdrTerms t = hdr_terms(xv[n].v[k], HAS_STD ? sv[n].v[k] : 0.0f, it, has_model, gaussian, bias[k], lm1,
-                                                 HAS_STD);
-                    wsum[k] += t.w;
-                    wv[k] += t.wv;
-                    R[n][k] = t.R;
-                    Q[n][k] = t.Q;
-                }
-            }
-        }
-        hdr_finish<VEC, HAS_STD, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int n = 0; n < NF; ++n) {
-                const float g = fmaf(alpha, R[n][k], gamma * Q[n][k]);
-                acc = fmaf(g, g, acc);
-            }
-            return acc;
-        });
-    }
-}
-
-// ---- the fixed-N kernel with the dark-field mix fused into its load ----------------------
-// x' = m B(x) + (1 - m) x and s_eff (clair_dark.cuh) are formed in registers from the raw frame, its std and the dark
-// frame + std, so the mixed stack never exists in memory: 4 input stacks are read once instead of the pre-pass
-// writing and the merge re-reading two more.  2 pixels of one row per thread; the loop bound is warp-uniform because
-// the blur takes its left / right neighbours from the adjacent lanes.
-constexpr int kDarkChunk = 3;      // frames whose 18 loads are in flight together (chunks of 1..3 measured within 3 %)
-
-template <int NF, bool SINGLE>
-__global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrParams p) {
-    constexpr int VEC = 2;
-    extern __shared__ float2 s_tab[];
-    const int C = p.n_channels, L = p.lut;
-    const bool has_model = p.theta != nullptr;
-    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
-    __syncthreads();
-    const int c = blockIdx.y;
-    const int64_t frame_stride = static_cast<int64_t>(C) * p.stride;
-    const float lm1 = static_cast<float>(L - 1);
-    const bool gaussian = p.gaussian != 0;
-    const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
-    const uint32_t groups_per_row = static_cast<uint32_t>(p.dg.W / VEC);
-    const uint32_t item_stride = gridDim.x * kBlock;
-    const uint32_t first_item = blockIdx.x * kBlock + threadIdx.x;
-    const uint32_t lane = threadIdx.x & 31u;
-    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
-    const uint32_t tab_bias = curve_row_bias(s_tab);
-    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
-    const float *val = static_cast<const float *>(p.val);
-
-    for (uint32_t item = first_item; item - lane < n_items; item += item_stride, cur.advance()) {
-        const bool active = item < n_items;
-        const uint32_t row = active ? item / groups_per_row : 0u;
-        const uint32_t grp = item - row * groups_per_row;
-        const int col = static_cast<int>(grp) * VEC;
-        const bool chained_left = lane > 0 && grp > 0;
-        const bool chained_right = lane < 31 && grp + 1 < groups_per_row;
-        const int64_t off = static_cast<int64_t>(c) * p.stride + (active ? item * VEC : 0u);
-        uint32_t bias[VEC];
-        {
-            uint32_t u = cur.u0;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                bias[k] = tab_bias + u * row_bytes;
-                u = (u + 1 == cur.C) ? 0u : u + 1;
-            }
-        }
-        float wsum[VEC], wv[VEC], R[NF][VEC], Q[NF][VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; }
-        // frames in chunks of kDarkChunk: all loads of a chunk are issued before its first shuffle
-#pragma unroll
-        for (int n0 = 0; n0 < NF; n0 += kDarkChunk) {
-            RowGroup<VEC> rg[kDarkChunk];
-            Pack<VEC> sv[kDarkChunk], dk[kDarkChunk], ds[kDarkChunk];
-#pragma unroll
-            for (int j = 0; j < kDarkChunk; ++j) {
-                if (n0 + j < NF) {
-                    const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
-                    row_group_load<VEC>(val + static_cast<int64_t>(n0 + j) * frame_stride + static_cast<int64_t>(c) * p.stride,
-                                        static_cast<int>(row), col, p.dg, active, chained_left, chained_right, rg[j]);
-                    sv[j] = load_stream<VEC>(p.std + o);
-                    dk[j] = load_stream<VEC>(p.dark + o);
-                    ds[j] = load_stream<VEC>(p.dark_std + o);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kDarkChunk; ++j) {
-                if (n0 + j < NF) {
-                    float x[VEC], blur[VEC];
-                    row_group_blur<VEC>(rg[j], col, p.dg, chained_left, chained_right, x, blur);
-                    const float it = p.scale.inv_t[n0 + j];
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) {
-                        float xm, sm;
-                        dark_mix_value<true>(x[k], blur[k], sv[j].v[k], dk[j].v[k], ds[j].v[k], p.dg, xm, sm);
-                        const HdrTerms t = hdr_terms(xm, sm, it, has_model, gaussian, bias[k], lm1, true);
-                        wsum[k] += t.w;
-                        wv[k] += t.wv;
-                        R[n0 + j][k] = t.R;
-                        Q[n0 + j][k] = t.Q;
-                    }
-                }
-            }
-        }
-        if (!active) continue;
-        hdr_finish<VEC, true, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
-            float acc = 0.0f;
-#pragma unroll
-            for (int n = 0; n < NF; ++n) {
-                const float g = fmaf(alpha, R[n][k], gamma * Q[n][k]);
-                acc = fmaf(g, g, acc);
-            }
-            return acc;
-        });
-    }
-}
-
-// ---- 9 <= N <= ~40: the same two-step evaluation with (R_n, Q_n) parked in shared memory ---------------------
-// N is a runtime value; frames are loaded in chunks of four.  Each thread owns a private, conflict-free column
-// rq[(n*2 + which)*VEC + k][tid], so registers stay low (occupancy is bounded by shared memory instead: 4 KB x N per
-// 256-thread block at 2 px/thread) and the variance is again a plain fp32 sum of squares.
-template <int VEC, int STD, bool SINGLE, int SRC>
-__global__ void __launch_bounds__(kBlock) hdr_merge_smem_kernel(const HdrParams p) {
-    constexpr bool HAS_STD = STD != 0;
-    static_assert(HAS_STD, "without std images there is no second step");
-    extern __shared__ float2 s_tab[];
-    const int C = p.n_channels, L = p.lut;
-    const bool has_model = p.theta != nullptr;
-    float *s_x = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
-    float *s_rq = s_x + (SRC == kSrcU8 ? 256 : 0) + threadIdx.x;
-    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
-    if constexpr (SRC == kSrcU8) {
-        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
-    }
-    __syncthreads();
-    const int c = blockIdx.y;
-    const int64_t frame_stride = static_cast<int64_t>(C) * p.stride;
-    const float lm1 = static_cast<float>(L - 1);
-    const bool gaussian = p.gaussian != 0;
-    const int N = p.n_frames;
-    const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
-    const uint32_t item_stride = gridDim.x * kBlock;
-    const uint32_t first_item = blockIdx.x * kBlock + threadIdx.x;
-    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
-    const uint32_t tab_bias = curve_row_bias(s_tab);
-    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
-
-    for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
-        const uint32_t pix = item * VEC;
-        const int64_t off = static_cast<int64_t>(c) * p.stride + pix;
-        uint32_t bias[VEC];
-        {
-            uint32_t u = cur.u0;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) { bias[k] = tab_bias + u * row_bytes; u = (u + 1 == cur.C) ? 0u : u + 1; }
-        }
-        float wsum[VEC], wv[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; }
-        for (int n0 = 0; n0 < N; n0 += kFrameChunk) {
-            Pack<VEC> xv[kFrameChunk], sv[kFrameChunk];
-#pragma unroll
-            for (int j = 0; j < kFrameChunk; ++j) {
-                if (n0 + j < N) {
-                    const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
-                    xv[j] = load_pixels<SRC, VEC>(p.val, o, p.code_max, s_x);
-                    sv[j] = load_std<VEC, STD>(p, o, xv[j]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kFrameChunk; ++j) {
-                if (n0 + j < N) {
-                    const float it = p.scale.inv_t[n0 + j];
-                    float *col = s_rq + (n0 + j) * (2 * VEC * kBlock);
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) {
-                        const HdrTerms t = hdr_terms(xv[j].v[k], sv[j].v[k], it, has_model, gaussian, bias[k], lm1, true);
-                        wsum[k] += t.w;
-                        wv[k] += t.wv;
-                        col[k * kBlock] = t.R;
-                        col[(VEC + k) * kBlock] = t.Q;
-                    }
-                }
-            }
-        }
-        hdr_finish<VEC, true, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
-            float acc0 = 0.0f, acc1 = 0.0f;
-            const float *col = s_rq + k * kBlock;
-            int n = 0;
-            for (; n + 4 <= N; n += 4) {                      // four frames per trip: eight independent LDS in flight
-                float r[4], q[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    r[j] = col[(n + j) * (2 * VEC * kBlock)];
-                    q[j] = col[(n + j) * (2 * VEC * kBlock) + VEC * kBlock];
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float g = fmaf(alpha, r[j], gamma * q[j]);
-                    if (j & 1) acc1 = fmaf(g, g, acc1); else acc0 = fmaf(g, g, acc0);
-                }
-            }
-            for (; n < N; ++n) {
-                const float g = fmaf(alpha, col[n * (2 * VEC * kBlock)], gamma * col[n * (2 * VEC * kBlock) + VEC * kBlock]);
-                acc0 = fmaf(g, g, acc0);
-            }
-            return acc0 + acc1;
-        });
-    }
-}
-
-// ---- fallback for N > kMaxFixedFrames: single pass, N dynamic --------------------------------------------
-// sum_n (alpha R_n + gamma Q_n)^2 = alpha^2 SRR + 2 alpha gamma SRQ + gamma^2 SQQ needs only three running
-// sums, but the expansion cancels (|gamma Q| can be ~14x the result), so the three sums are float64.
-template <int VEC, int STD, int SRC>
-__global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
-    constexpr bool HAS_STD = STD != 0;
-    extern __shared__ float2 s_tab[];
-    const int C = p.n_channels, L = p.lut;
-    const bool has_model = p.theta != nullptr;
-    float *s_x = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
-    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
-    if constexpr (SRC == kSrcU8) {
-        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
-    }
-    __syncthreads();
-    const int c = blockIdx.y;
-    const int64_t frame_stride = static_cast<int64_t>(C) * p.stride;
-    const float lm1 = static_cast<float>(L - 1);
-    const bool gaussian = p.gaussian != 0;
-    const int N = p.n_frames;
-    const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
-    const uint32_t item_stride = gridDim.x * kBlock;
-    const uint32_t first_item = blockIdx.x * kBlock + threadIdx.x;
-    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
-    const uint32_t tab_bias = curve_row_bias(s_tab);
-    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
-
-    for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
-        const uint32_t pix = item * VEC;
-        const int64_t off = static_cast<int64_t>(c) * p.stride + pix;
-        uint32_t bias[VEC];
-        {
-            uint32_t u = cur.u0;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) {
-                bias[k] = tab_bias + u * row_bytes;
-                u = (u + 1 == cur.C) ? 0u : u + 1;
-            }
-        }
-        float wsum[VEC], wv[VEC];
-        double srr[VEC], srq[VEC], sqq[VEC];
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; srr[k] = 0.0; srq[k] = 0.0; sqq[k] = 0.0; }
-        for (int n0 = 0; n0 < N; n0 += kFrameChunk) {
-            Pack<VEC> xv[kFrameChunk], sv[kFrameChunk];
-#pragma unroll
-            for (int j = 0; j < kFrameChunk; ++j) {
-                if (n0 + j < N) {
-                    const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
-                    xv[j] = load_pixels<SRC, VEC>(p.val, o, p.code_max, s_x);
-                    if constexpr (HAS_STD) sv[j] = load_std<VEC, STD>(p, o, xv[j]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < kFrameChunk; ++j) {
-                if (n0 + j < N) {
-                    const float it = p.scale.inv_t[n0 + j];
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) {
-                        const HdrTerms t = hdr_terms(xv[j].v[k], HAS_STD ? sv[j].v[k] : 0.0f, it, has_model, gaussian,
-                                                     bias[k], lm1, HAS_STD);
-                        wsum[k] += t.w;
-                        wv[k] += t.wv;
-                        if constexpr (HAS_STD) {
-                            const double R = static_cast<double>(t.R), Q = static_cast<double>(t.Q);
-                            srr[k] = fma(R, R, srr[k]);
-                            srq[k] = fma(R, Q, srq[k]);
-                            sqq[k] = fma(Q, Q, sqq[k]);
-                        }
-                    }
-                }
-            }
-        }
-        hdr_finish<VEC, HAS_STD, false>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
-            const double a = static_cast<double>(alpha), g = static_cast<double>(gamma);
-            return static_cast<float>(fmax(a * a * srr[k] + 2.0 * a * g * srq[k] + g * g * sqq[k], 0.0));
-        });
-    }
-}
-
 // ---- LOOKUP / CATMULL models -------------------------------------------------------------------------------
 // Off the fast path (the reference default is LINEAR): one pixel per thread, any input kind, two passes over the
 // frames.  Pass 1 forms W_B and sum w v in float64; pass 2 re-reads
@@ -720,8 +148,9 @@ struct FrameScale64 {
     double inv_t[CLAIR_MAX_FRAMES];
 };
 
-__device__ __forceinline__ float load_any_pixel(const HdrParams &p, int64_t o) {
+__device__ __forceinline__ float load_any_pixel(const HdrParams &p, int64_t o, int n, int c, int64_t pix) {
     if (p.src == kSrcF32) return __ldg(static_cast<const float *>(p.val) + o);
+    if (p.hwc) o = (static_cast<int64_t>(n) * p.plane + pix) * 3 + (2 - c);
     if (p.src == kSrcU8) return __fdiv_rn(static_cast<float>(__ldg(static_cast<const uint8_t *>(p.val) + o)), p.code_max);
     return __fdiv_rn(static_cast<float>(__ldg(static_cast<const uint16_t *>(p.val) + o)), p.code_max);
 }
@@ -763,7 +192,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_modes_kernel(const HdrParams
         const float2 *row = s_tab + u * L;
         double wsum = 0.0, wv = 0.0;
         for (int n = 0; n < N; ++n) {
-            const float x = load_any_pixel(p, off + n * frame_stride);
+            const float x = load_any_pixel(p, off + n * frame_stride, n, c, pix);
             float f, fp, d;
             icrf_mode_eval<MODE>(x, row, L, lm1, f, fp);
             const float w = gaussian ? gaussian_weight(x, kHdrNegScaleLog2e, d) : 1.0f;
@@ -791,7 +220,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_modes_kernel(const HdrParams
         if (has_std) {
             for (int n = 0; n < N; ++n) {
                 const int64_t o = off + n * frame_stride;
-                const float x = load_any_pixel(p, o);
+                const float x = load_any_pixel(p, o, n, c, pix);
                 const float sd = load_any_std(p, o, x);
                 float f, fp, d = 0.0f;
                 icrf_mode_eval<MODE>(x, row, L, lm1, f, fp);
@@ -826,15 +255,6 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_modes_kernel(const HdrParams
 using namespace clair;
 
 namespace {
-
-template <typename K>
-int ensure_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
-        if (e != cudaSuccess) return fail_cuda(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-    }
-    return 0;
-}
 
 int pick_vec(int64_t plane, std::initializer_list<const void *> ptrs) {
     // frame / channel slabs start at multiples of `plane` elements, so plane % VEC == 0 keeps every slab aligned
@@ -1028,6 +448,7 @@ struct DarkOptions {          // fused dark-field mix: dark == nullptr switches 
     const float *dark = nullptr, *dark_std = nullptr;
     int height = 0, width = 0;
     float threshold = 0.0f, alpha = 0.0f;
+    int hwc = 0;              // integer codes in the interleaved (H, W, 3) BGR camera layout
 };
 
 int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max, const float *std_dev, int std_mode,
@@ -1048,6 +469,11 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     if (plane_stride == 0) plane_stride = plane;
     if (plane_stride < plane) return bad(CLAIR_E_ARG, "plane_stride must be 0 or >= plane");
     const bool all_modes = theta_dev != nullptr && interp_mode != CLAIR_INTERP_LINEAR;
+    if (dark.hwc) {
+        if (src == kSrcF32 || n_channels != 3 || plane_stride != plane)
+            return bad(CLAIR_E_MODE, "the interleaved BGR layout is for uint8 / uint16 codes of dense 3-channel frames");
+        if (dark.dark) return bad(CLAIR_E_MODE, "the fused dark-field mix takes planar fp32 images");
+    }
     if (all_modes && interp_mode != CLAIR_INTERP_LOOKUP && interp_mode != CLAIR_INTERP_CATMULL)
         return bad(CLAIR_E_MODE, "interp_mode must be CLAIR_INTERP_LOOKUP, _LINEAR or _CATMULL");
     if (std_mode == kStdTensor && !std_dev) return bad(CLAIR_E_ARG, "std_mode = tensor needs std_dev");
@@ -1061,6 +487,7 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     p.mean_state = mean_state_dev; p.wsum_state = wsum_state_dev; p.var_state = var_state_dev;
     p.radiance = radiance_dev; p.sigma = sigma_dev;
     p.plane = plane; p.stride = plane_stride; p.n_frames = n_frames; p.n_channels = n_channels; p.lut = lut_size; p.src = src;
+    p.hwc = dark.hwc;
     p.gaussian = gaussian_weights; p.is_first = is_first; p.is_final = is_final; p.radiance_f64 = radiance_f64;
     p.std_mode = std_mode; p.std_value = std_value; p.code_max = code_max;
     fill_rows(p.rows, curve_row_base_host, n_channels, plane_stride);
@@ -1138,6 +565,7 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     if (src != kSrcF32) {
         // four codes per 32- / 64-bit load
         const size_t code_bytes = src == kSrcU8 ? 1 : 2;
+        if (dark.hwc && plane % 4 != 0) vec = 0;             // 12 codes per thread: every frame must start 4-pixel aligned
         if (vec != 4 || reinterpret_cast<uintptr_t>(val_dev) % (4 * code_bytes) != 0)
             return bad(CLAIR_E_ARG, "integer ingest needs H*W % 4 == 0 and 16-byte aligned output / std / state buffers");
     }
@@ -1162,59 +590,15 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         if (vec_cap < vec) vec = vec_cap;
         if (parked) smem += sizeof(float) * 2 * vec * kBlock * static_cast<size_t>(n_frames);
     }
-    const int64_t items = plane / vec;
-    const int64_t want_blocks = (items + kBlock - 1) / kBlock;
-    // persistent grid: a whole number of resident waves (blocks/SM from the occupancy calculator), split over C
-    auto launch = [&](auto kernel) -> int {
-        if (int rc = ensure_smem(kernel, smem)) return rc;
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
-        // resident waves per persistent grid: 2 for the register kernel, 3 for the shared-memory-parked one (measured)
-        per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : (parked ? 3 : 2));
-        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want_blocks, resident_blocks_per_channel(per_sm, n_channels)));
-        kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p);
-        return 0;
-    };
-    int rc = 0;
-#define FIXED_NF(V, NF, ST, SRC) (single ? launch(hdr_merge_fixed_kernel<V, NF, ST, true, SRC>) : launch(hdr_merge_fixed_kernel<V, NF, ST, false, SRC>))
-#define FIXED(V, ST, SRC)                                   \
-    switch (n_frames) {                                     \
-        case 1: rc = FIXED_NF(V, 1, ST, SRC); break;        \
-        case 2: rc = FIXED_NF(V, 2, ST, SRC); break;        \
-        case 3: rc = FIXED_NF(V, 3, ST, SRC); break;        \
-        case 4: rc = FIXED_NF(V, 4, ST, SRC); break;        \
-        case 5: rc = FIXED_NF(V, 5, ST, SRC); break;        \
-        case 6: rc = FIXED_NF(V, 6, ST, SRC); break;        \
-        case 7: rc = FIXED_NF(V, 7, ST, SRC); break;        \
-        default: rc = FIXED_NF(V, 8, ST, SRC); break;       \
-    }
-#define DYN(V, ST, SRC) rc = launch(hdr_merge_kernel<V, ST, SRC>)
-#define PARKED(V, ST, SRC) rc = single ? launch(hdr_merge_smem_kernel<V, ST, true, SRC>) : launch(hdr_merge_smem_kernel<V, ST, false, SRC>)
-#define BY_STD(V, SRC)                                                          \
-    if (std_mode == kStdNone) { DYN(V, 0, SRC); }                               \
-    else if (std_mode == kStdTensor) { if (fixed) { FIXED(V, 1, SRC) } else if (parked) { PARKED(V, 1, SRC); } else { DYN(V, 1, SRC); } } \
-    else { if (fixed) { FIXED(V, 2, SRC) } else if (parked) { PARKED(V, 2, SRC); } else { DYN(V, 2, SRC); } }
-    if (src == kSrcU8) { BY_STD(4, kSrcU8) }
-    else if (src == kSrcU16) { BY_STD(4, kSrcU16) }
-    else if (std_mode == kStdNone) {
-        if (vec == 4) DYN(4, 0, kSrcF32); else if (vec == 2) DYN(2, 0, kSrcF32); else DYN(1, 0, kSrcF32);
-    } else if (std_mode != kStdTensor) {
-        return bad(CLAIR_E_MODE, "synthesised std needs integer codes");
-    } else if (parked) {
-        if (vec == 2) rc = single ? launch(hdr_merge_smem_kernel<2, 1, true, kSrcF32>) : launch(hdr_merge_smem_kernel<2, 1, false, kSrcF32>);
-        else rc = single ? launch(hdr_merge_smem_kernel<1, 1, true, kSrcF32>) : launch(hdr_merge_smem_kernel<1, 1, false, kSrcF32>);
-    } else if (vec == 4) {
-        if (fixed) { FIXED(4, 1, kSrcF32) } else { DYN(4, 1, kSrcF32); }
-    } else if (vec == 2) {
-        if (fixed) { FIXED(2, 1, kSrcF32) } else { DYN(2, 1, kSrcF32); }
-    } else {
-        if (fixed) { FIXED(1, 1, kSrcF32) } else { DYN(1, 1, kSrcF32); }
-    }
-#undef BY_STD
-#undef PARKED
-#undef DYN
-#undef FIXED
-#undef FIXED_NF
+    MergeLaunch m{};
+    m.p = p; m.smem = smem; m.want_blocks = (plane / vec + kBlock - 1) / kBlock;
+    m.fixed = fixed; m.parked = parked; m.single = single;
+    m.std_mode = std_mode; m.n_frames = n_frames; m.n_channels = n_channels; m.stream = s;
+    int rc;
+    if (src != kSrcF32) rc = dark.hwc ? launch_merge_codes_hwc(m, src == kSrcU8) : launch_merge_codes_planar(m, src == kSrcU8);
+    else if (vec == 4) rc = launch_merge_by_std<4, kSrcF32>(m);
+    else if (vec == 2) rc = launch_merge_by_std<2, kSrcF32>(m);
+    else rc = launch_merge_by_std<1, kSrcF32>(m);
     if (rc) return rc;
     return launched("hdr_merge_kernel");
 }
@@ -1279,6 +663,9 @@ extern "C" int clair_hdr_merge(const clair_merge_desc *d, void *stream) {
     DarkOptions dark;
     dark.dark = d->dark_dev; dark.dark_std = d->dark_std_dev; dark.height = d->height; dark.width = d->width;
     dark.threshold = d->dark_threshold; dark.alpha = d->dark_alpha;
+    if (d->code_layout != CLAIR_CODES_PLANAR && d->code_layout != CLAIR_CODES_HWC_BGR)
+        return fail(CLAIR_E_MODE, "clair_hdr_merge: code_layout must be CLAIR_CODES_PLANAR or CLAIR_CODES_HWC_BGR");
+    dark.hwc = d->code_layout == CLAIR_CODES_HWC_BGR;
     return hdr_merge_impl("clair_hdr_merge", d->val_dev, src, d->code_max, d->std_dev, std_mode_of(d), d->std_value, d->exposure_host,
                           d->n_frames, d->theta_dev, d->n_channels, d->lut_size, d->interp_mode, d->plane, d->plane_stride,
                           d->curve_row_base_host, d->gaussian_weights, d->mean_state_dev, d->wsum_state_dev, d->var_state_dev,
@@ -1301,6 +688,7 @@ extern "C" int clair_hdr_merge_staged(const clair_merge_desc *d, const void *val
     if (std_mode == kStdTensor && !std_host) return fail(CLAIR_E_ARG, "clair_hdr_merge_staged: std staging buffer without std_host");
     if (copy_stream == stream) return fail(CLAIR_E_ARG, "clair_hdr_merge_staged: copy_stream must differ from stream");
     if (d->dark_dev) return fail(CLAIR_E_MODE, "clair_hdr_merge_staged: the dark-field mix needs whole planes on the device (clair_hdr_merge)");
+    if (d->code_layout != CLAIR_CODES_PLANAR) return fail(CLAIR_E_MODE, "clair_hdr_merge_staged: planar stacks only (interleaved codes: clair_hdr_merge reads them in place)");
     // bands of whole 1024-pixel blocks keep every band base 16-byte aligned for all element sizes
     constexpr int64_t kGranule = 1024;
     const int64_t granules = (d->plane + kGranule - 1) / kGranule;

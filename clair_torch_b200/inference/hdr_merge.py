@@ -13,7 +13,7 @@ from ._common import (as_device, check_artefact_dataset, matching_dark_frames, m
 def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFModelBase] = None,
                       weight_fn: Optional[Callable] = None, flat_field_dataset=None, gpu_transforms=None,
                       dark_field_dataset=None, *, radiance_dtype: Optional[torch.dtype] = None, host_out=None,
-                      code_max: Optional[float] = None, staged: Optional[bool] = None):
+                      code_max: Optional[float] = None, staged: Optional[bool] = None, code_layout: str = "planar"):
     """Exposure-weighted HDR merge of a stationary exposure stack with first-order uncertainty.
 
     Each DataLoader batch goes through ONE fused kernel (ICRF evaluation, Gaussian weights, weighted running mean
@@ -39,7 +39,8 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
     normalised fp32 images; the kernel then performs the reference's CastTo(float32) + Normalize(max_val=code_max,
     min_val=0) on load (code_max defaults to 255 / 65535), and the std batch may be a `datasets.StdSpec`
     (MissingStdMode.MULTIPLIER / CONSTANT evaluated in-register).  Results are bit-identical to feeding the
-    CPU-transformed fp32 images; 4-8x fewer bytes cross PCIe and HBM.
+    CPU-transformed fp32 images; 4-8x fewer bytes cross PCIe and HBM.  With `code_layout="hwc_bgr"` the code batches are
+    (N, H, W, 3) BGR — `cv2.imread` output, stacked — and CvToTorch is fused into the load as well.
     """
     if not isinstance(dataloader, DataLoader):
         raise TypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
@@ -94,7 +95,8 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
                                           is_final=upcoming is None, radiance_dtype=out_dtype, device=dev,
                                           host_out=host_out if (upcoming is None and flat_field_dataset is None) else None,
                                           code_max=code_max, interp_mode=interp_mode,
-                                          staged=staged if not images.is_cuda else None, dark=fused_dark)
+                                          staged=staged if not images.is_cuda else None, dark=fused_dark,
+                                          code_layout=code_layout)
         current = upcoming
     if result is None:
         raise ValueError("the dataloader yielded no batches")

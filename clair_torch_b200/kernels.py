@@ -196,7 +196,8 @@ def _code_stack(t: torch.Tensor, allow_pinned: bool) -> torch.Tensor:
 def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
                      theta: Optional[torch.Tensor], gaussian_weights: bool, is_final: bool,
                      radiance_dtype: torch.dtype = _F64, row_base=None, device=None, host_out=None, code_max=None,
-                     interp_mode: int = _native.INTERP_LINEAR, staged: Optional[bool] = None, bands: int = 16, dark=None):
+                     interp_mode: int = _native.INTERP_LINEAR, staged: Optional[bool] = None, bands: int = 16, dark=None,
+                     code_layout: str = "planar"):
     """One batch of compute_hdr_image (inference/hdr_merge.py:95-128).  Returns (radiance, sigma) when
     `is_final`, else None.  `exposure` is the collated float64 'exposure_time' (host tensor, array or list).
 
@@ -205,6 +206,10 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     fp32 host stacks are `staged` by default: the copy engine streams bands of the planes into device buffers while the
     kernel merges the previous band (clair_hdr_merge_staged); `staged=False` (the default for integer codes) lets the
     kernel read the host memory itself (zero-copy).
+
+    `code_layout="hwc_bgr"`: the integer codes are (N, H, W, 3) in OpenCV's BGR order, i.e. what `cv2.imread` returns,
+    stacked; the reference's CvToTorch transform (BGR -> RGB, HWC -> CHW) then happens inside the kernel's load.  Outputs,
+    std tensors and running state stay planar (3, H, W) RGB.
 
     `interp_mode`: the model's InterpMode (LINEAR: fused fast kernels; LOOKUP / CATMULL: the all-modes kernel).
 
@@ -237,11 +242,23 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     dev = torch.device(device) if device is not None else val.device
     if val.is_cuda and val.device != dev:
         raise ValueError("val_batch lives on a different device than the one requested")
-    if std is not None and std.shape != val.shape:
+    if std is not None and code_layout == "planar" and std.shape != val.shape:
         raise ValueError("std_batch must have the same shape as val_batch")
+    if std is not None and code_layout != "planar" and tuple(std.shape) != (val.shape[0], 3, val.shape[1], val.shape[2]):
+        raise ValueError("with code_layout='hwc_bgr' a std tensor must be planar (N, 3, H, W)")
     if code_max is not None and not codes:
         raise ValueError("code_max only applies to uint8 / uint16 value codes")
-    n, c, h, w = val.shape
+    if code_layout not in ("planar", "hwc_bgr"):
+        raise ValueError(f"code_layout must be 'planar' or 'hwc_bgr', got {code_layout!r}")
+    hwc = code_layout == "hwc_bgr"
+    if hwc:
+        if not codes or val.shape[3] != 3:
+            raise ValueError("code_layout='hwc_bgr' takes uint8 / uint16 codes of shape (N, H, W, 3)")
+        n, h, w, c = val.shape
+        if (h * w) % 4 != 0:
+            raise ValueError("code_layout='hwc_bgr' needs H*W to be a multiple of 4")
+    else:
+        n, c, h, w = val.shape
     if torch.is_tensor(exposure):
         exposure = exposure.detach().cpu().numpy()
     t = np.ascontiguousarray(np.asarray(exposure, dtype=np.float64).reshape(-1))
@@ -287,6 +304,7 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     desc.curve_row_base_host = keep.ctypes.data if keep is not None else None
     desc.mean_state_dev, desc.wsum_state_dev, desc.var_state_dev = _ptr(state.mean), _ptr(state.wsum), _ptr(state.var)
     desc.is_first, desc.is_final, desc.radiance_f64 = int(is_first), int(is_final), int(radiance_dtype == _F64)
+    desc.code_layout = _native.CODES_HWC_BGR if hwc else _native.CODES_PLANAR
     desc.radiance_dev, desc.sigma_dev = _ptr(radiance), _ptr(sigma)
     if dark is not None:
         dark_val, dark_std = dark
@@ -299,7 +317,7 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     if staged is None:
         # measured (profiles/README.md): fp32 stacks are input-bound and gain from the copy engine's faster host reads;
         # integer codes are output-bound (1-2 B in, 8 B out per pixel) and are quicker read in place by the kernel
-        staged = on_host and not codes
+        staged = on_host and not codes and not hwc
     if staged and not on_host:
         raise ValueError("staged=True is for pinned host stacks")
     with torch.cuda.device(dev):

@@ -174,8 +174,14 @@ CLAIR_API int clair_hdr_merge_codes(const void *codes_dev, int code_bytes, float
  *                  1 / 2: val_dev holds uint8 / uint16 codes, see clair_hdr_merge_codes
  *   dark_dev ...   dark-field correction of the batch fused into the load (inference/hdr_merge.py:76-92,117-126): the
  *                  mixed images and their effective std are formed in registers instead of by a pre-pass
+ *   code_layout    CLAIR_CODES_PLANAR: val_dev is (n_frames, C, plane).  CLAIR_CODES_HWC_BGR (integer codes, C = 3, plane a
+ *                  multiple of 4): val_dev is (n_frames, H, W, 3) exactly as OpenCV hands a colour image over, and the
+ *                  CvToTorch transform (clair_torch/common/general_functions.py:315-336: BGR -> RGB, HWC -> CHW) happens in
+ *                  the kernel's address arithmetic; std_dev, state and outputs stay planar RGB.
  * struct_bytes must be sizeof(clair_merge_desc); all other fields as the arguments of clair_hdr_merge_update.
  */
+#define CLAIR_CODES_PLANAR 0
+#define CLAIR_CODES_HWC_BGR 1
 typedef struct clair_merge_desc {
     uint32_t struct_bytes;
     int32_t code_bytes;
@@ -200,7 +206,7 @@ typedef struct clair_merge_desc {
     int32_t is_first;
     int32_t is_final;
     int32_t radiance_f64;
-    int32_t reserved;
+    int32_t code_layout;        /* CLAIR_CODES_PLANAR, or CLAIR_CODES_HWC_BGR for uint8 / uint16 codes */
     void *radiance_dev;
     float *sigma_dev;
     /* fused dark-field correction (NULL dark_dev = off): see clair_dark_field_mix below for the arithmetic.  dark_dev /

@@ -516,6 +516,35 @@ def test_hdr_merge_integer_ingest_is_bit_identical(ct, bits):
                 assert torch.equal(got[1], want[1]), (name, split)
 
 
+@pytest.mark.parametrize("bits,n", [(8, 5), (16, 4), (8, 9), (16, 12)])
+def test_hdr_merge_interleaved_bgr_codes_equal_planar(ct, bits, n):
+    """code_layout='hwc_bgr': (N, H, W, 3) BGR camera buffers give the same bits as the planar RGB codes the reference's
+    CvToTorch would have produced from them — register, parked and all-modes kernels, device and pinned host memory."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.datasets import StdSpec
+    val, _, t = ct.synthetic.make_stack(n, 3, 30, 44, bits=bits, seed=bits + n)
+    maxval = float(2 ** bits - 1)
+    planar = torch.round(val * maxval).to(torch.uint8 if bits == 8 else torch.uint16)
+    # what cv2.imread hands over: height x width x (B, G, R)
+    camera = torch.stack([planar[:, 2], planar[:, 1], planar[:, 0]], dim=-1).contiguous()
+    assert camera.shape == (n, 30, 44, 3)
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    std_tensor = (val * 0.03 + 0.001)
+    for std_p in (StdSpec("multiplier", 0.05), StdSpec("constant", 0.02), std_tensor.to(DEV), None):
+        for mode in (ct._native.INTERP_LINEAR, ct._native.INTERP_LOOKUP):
+            want = kernels.hdr_merge_update(kernels.HdrMergeState(), planar.to(DEV), std_p, t, theta, True, True, interp_mode=mode)
+            got = kernels.hdr_merge_update(kernels.HdrMergeState(), camera.to(DEV), std_p, t, theta, True, True, interp_mode=mode,
+                                           code_layout="hwc_bgr")
+            assert torch.equal(got[0], want[0])
+            assert (got[1] is None and want[1] is None) or torch.equal(got[1], want[1])
+    host = kernels.hdr_merge_update(kernels.HdrMergeState(), camera.pin_memory(), StdSpec("multiplier", 0.05), t, theta, True, True,
+                                    device=torch.device(DEV), code_layout="hwc_bgr")
+    dev = kernels.hdr_merge_update(kernels.HdrMergeState(), planar.to(DEV), StdSpec("multiplier", 0.05), t, theta, True, True)
+    assert torch.equal(host[0], dev[0]) and torch.equal(host[1], dev[1])
+    with pytest.raises(ValueError):
+        kernels.hdr_merge_update(kernels.HdrMergeState(), val.to(DEV), None, t, theta, True, True, code_layout="hwc_bgr")
+
+
 def test_hdr_merge_integer_ingest_against_reference_fixture(ct):
     """The 16-bit reference fixture fed as uint16 codes through the public API (DataLoader + StdSpec)."""
     from clair_torch_b200.datasets import ExposureStackDataset, StdSpec, custom_collate
