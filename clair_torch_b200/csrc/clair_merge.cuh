@@ -56,7 +56,7 @@ __host__ __device__ constexpr bool src_is_u8(int src) { return src == kSrcU8 || 
 // integer codes, normalised in-register exactly like the reference's CPU transforms do it (CastTo(float32) then
 // Normalize(max_val, min_val=0): an IEEE fp32 division, clair_torch/common/general_functions.py:378) — 8-bit codes
 // go through a 256-entry table of those quotients, 16-bit codes through __fdiv_rn.
-// Interleaved camera layout (`hwc`): the codes are (n_frames, H, W, 3) in OpenCV's BGR order and channel c of the planar
+// Interleaved camera layout (`hwc`): the codes are (n_frames, H, W, 3) in OpenCV's BGR order (p.stride pixels per frame) and channel c of the planar
 // tensor is byte / halfword 2 - c of each pixel — the CvToTorch transform (common/general_functions.py:315-336) folded
 // into the address.  Four pixels of one channel are 4 of the 12 codes a thread loads.
 __device__ __forceinline__ uint32_t pick_byte(uint32_t w0, uint32_t w1, uint32_t w2, int j) {      // byte j of a 12-byte window
@@ -78,7 +78,7 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int 
         Pack<VEC> r;
         if constexpr (SRC == kSrcU8Hwc) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(p.val) +
-                                                                     (static_cast<int64_t>(n) * p.plane + pix) * 3);
+                                                                     (static_cast<int64_t>(n) * p.stride + pix) * 3);
             const uint32_t w0 = __ldcs(src), w1 = __ldcs(src + 1), w2 = __ldcs(src + 2);
             const int j0 = 2 - c;                              // uniform over the block
 #pragma unroll
@@ -100,7 +100,7 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int 
         Pack<VEC> r;
         if constexpr (SRC == kSrcU16Hwc) {
             const uint2 *src = reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(p.val) +
-                                                               (static_cast<int64_t>(n) * p.plane + pix) * 3);
+                                                               (static_cast<int64_t>(n) * p.stride + pix) * 3);
             const uint2 a = __ldcs(src), b = __ldcs(src + 1), cc = __ldcs(src + 2);
             const int j0 = 2 - c;
 #pragma unroll

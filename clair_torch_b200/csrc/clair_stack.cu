@@ -150,7 +150,7 @@ struct FrameScale64 {
 
 __device__ __forceinline__ float load_any_pixel(const HdrParams &p, int64_t o, int n, int c, int64_t pix) {
     if (p.src == kSrcF32) return __ldg(static_cast<const float *>(p.val) + o);
-    if (p.hwc) o = (static_cast<int64_t>(n) * p.plane + pix) * 3 + (2 - c);
+    if (p.hwc) o = (static_cast<int64_t>(n) * p.stride + pix) * 3 + (2 - c);
     if (p.src == kSrcU8) return __fdiv_rn(static_cast<float>(__ldg(static_cast<const uint8_t *>(p.val) + o)), p.code_max);
     return __fdiv_rn(static_cast<float>(__ldg(static_cast<const uint16_t *>(p.val) + o)), p.code_max);
 }
@@ -470,8 +470,8 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     if (plane_stride < plane) return bad(CLAIR_E_ARG, "plane_stride must be 0 or >= plane");
     const bool all_modes = theta_dev != nullptr && interp_mode != CLAIR_INTERP_LINEAR;
     if (dark.hwc) {
-        if (src == kSrcF32 || n_channels != 3 || plane_stride != plane)
-            return bad(CLAIR_E_MODE, "the interleaved BGR layout is for uint8 / uint16 codes of dense 3-channel frames");
+        if (src == kSrcF32 || n_channels != 3)
+            return bad(CLAIR_E_MODE, "the interleaved BGR layout is for uint8 / uint16 codes of 3-channel frames");
         if (dark.dark) return bad(CLAIR_E_MODE, "the fused dark-field mix takes planar fp32 images");
     }
     if (all_modes && interp_mode != CLAIR_INTERP_LOOKUP && interp_mode != CLAIR_INTERP_CATMULL)
@@ -565,7 +565,7 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     if (src != kSrcF32) {
         // four codes per 32- / 64-bit load
         const size_t code_bytes = src == kSrcU8 ? 1 : 2;
-        if (dark.hwc && plane % 4 != 0) vec = 0;             // 12 codes per thread: every frame must start 4-pixel aligned
+        if (dark.hwc && plane_stride % 4 != 0) vec = 0;      // 12 codes per thread: every frame must start 4-pixel aligned
         if (vec != 4 || reinterpret_cast<uintptr_t>(val_dev) % (4 * code_bytes) != 0)
             return bad(CLAIR_E_ARG, "integer ingest needs H*W % 4 == 0 and 16-byte aligned output / std / state buffers");
     }
@@ -688,7 +688,9 @@ extern "C" int clair_hdr_merge_staged(const clair_merge_desc *d, const void *val
     if (std_mode == kStdTensor && !std_host) return fail(CLAIR_E_ARG, "clair_hdr_merge_staged: std staging buffer without std_host");
     if (copy_stream == stream) return fail(CLAIR_E_ARG, "clair_hdr_merge_staged: copy_stream must differ from stream");
     if (d->dark_dev) return fail(CLAIR_E_MODE, "clair_hdr_merge_staged: the dark-field mix needs whole planes on the device (clair_hdr_merge)");
-    if (d->code_layout != CLAIR_CODES_PLANAR) return fail(CLAIR_E_MODE, "clair_hdr_merge_staged: planar stacks only (interleaved codes: clair_hdr_merge reads them in place)");
+    if (d->code_layout != CLAIR_CODES_PLANAR && d->code_layout != CLAIR_CODES_HWC_BGR)
+        return fail(CLAIR_E_MODE, "clair_hdr_merge_staged: code_layout must be CLAIR_CODES_PLANAR or CLAIR_CODES_HWC_BGR");
+    const bool hwc = d->code_layout == CLAIR_CODES_HWC_BGR;
     // bands of whole 1024-pixel blocks keep every band base 16-byte aligned for all element sizes
     constexpr int64_t kGranule = 1024;
     const int64_t granules = (d->plane + kGranule - 1) / kGranule;
@@ -715,6 +717,8 @@ extern "C" int clair_hdr_merge_staged(const clair_merge_desc *d, const void *val
     STAGED_CUDA(new_event(free_ev));
     STAGED_CUDA(cudaEventRecord(free_ev, ks));
     STAGED_CUDA(cudaStreamWaitEvent(cs, free_ev, 0));
+    DarkOptions band_opts;
+    band_opts.hwc = hwc ? 1 : 0;
     int32_t full_base[CLAIR_MAX_CHANNELS], band_base[CLAIR_MAX_CHANNELS];
     for (int c = 0; c < C; ++c)
         full_base[c] = d->curve_row_base_host ? d->curve_row_base_host[c] : static_cast<int32_t>((static_cast<int64_t>(c) * d->plane) % C);
@@ -723,10 +727,12 @@ extern "C" int clair_hdr_merge_staged(const clair_merge_desc *d, const void *val
         const int64_t p0 = std::min<int64_t>(d->plane, granules * b / bands * kGranule);
         const int64_t p1 = (b + 1 == bands) ? d->plane : std::min<int64_t>(d->plane, granules * (b + 1) / bands * kGranule);
         if (p1 <= p0) continue;
-        const size_t pitch = static_cast<size_t>(d->plane) * esz, width = static_cast<size_t>(p1 - p0) * esz;
-        char *val_stage = static_cast<char *>(const_cast<void *>(d->val_dev)) + p0 * esz;
-        STAGED_CUDA(cudaMemcpy2DAsync(val_stage, pitch, static_cast<const char *>(val_host) + p0 * esz, pitch, width, slabs,
-                                      cudaMemcpyHostToDevice, cs));
+        // planar: one row per (frame, channel) plane; interleaved: one row per frame, three codes per pixel
+        const size_t px_bytes = hwc ? 3 * esz : esz;
+        const size_t pitch = static_cast<size_t>(d->plane) * px_bytes, width = static_cast<size_t>(p1 - p0) * px_bytes;
+        char *val_stage = static_cast<char *>(const_cast<void *>(d->val_dev)) + p0 * px_bytes;
+        STAGED_CUDA(cudaMemcpy2DAsync(val_stage, pitch, static_cast<const char *>(val_host) + p0 * px_bytes, pitch, width,
+                                      hwc ? static_cast<size_t>(d->n_frames) : slabs, cudaMemcpyHostToDevice, cs));
         if (std_mode == kStdTensor)
             STAGED_CUDA(cudaMemcpy2DAsync(const_cast<float *>(d->std_dev) + p0, static_cast<size_t>(d->plane) * 4, std_host + p0,
                                           static_cast<size_t>(d->plane) * 4, static_cast<size_t>(p1 - p0) * 4, slabs,
@@ -741,7 +747,7 @@ extern "C" int clair_hdr_merge_staged(const clair_merge_desc *d, const void *val
         rc = hdr_merge_impl(fn, val_stage, src, d->code_max, at(d->std_dev), std_mode, d->std_value, d->exposure_host, d->n_frames,
                             d->theta_dev, C, d->lut_size, d->interp_mode, p1 - p0, d->plane, band_base, d->gaussian_weights,
                             at(d->mean_state_dev), at(d->wsum_state_dev), at(d->var_state_dev), d->is_first, d->is_final, rad,
-                            d->radiance_f64, at(d->sigma_dev), stream);
+                            d->radiance_f64, at(d->sigma_dev), stream, band_opts);
     }
 #undef STAGED_CUDA
     cleanup();      // events are released once the work recorded on them has completed

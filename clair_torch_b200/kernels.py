@@ -196,7 +196,7 @@ def _code_stack(t: torch.Tensor, allow_pinned: bool) -> torch.Tensor:
 def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
                      theta: Optional[torch.Tensor], gaussian_weights: bool, is_final: bool,
                      radiance_dtype: torch.dtype = _F64, row_base=None, device=None, host_out=None, code_max=None,
-                     interp_mode: int = _native.INTERP_LINEAR, staged: Optional[bool] = None, bands: int = 16, dark=None,
+                     interp_mode: int = _native.INTERP_LINEAR, staged: Optional[bool] = None, bands: Optional[int] = None, dark=None,
                      code_layout: str = "planar"):
     """One batch of compute_hdr_image (inference/hdr_merge.py:95-128).  Returns (radiance, sigma) when
     `is_final`, else None.  `exposure` is the collated float64 'exposure_time' (host tensor, array or list).
@@ -317,9 +317,12 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     if staged is None:
         # measured (profiles/README.md): fp32 stacks are input-bound and gain from the copy engine's faster host reads;
         # integer codes are output-bound (1-2 B in, 8 B out per pixel) and are quicker read in place by the kernel
-        staged = on_host and not codes and not hwc
+        # (interleaved codes are staged: in place, each of the three channel blocks would pull all three channels' bytes)
+        staged = on_host and (not codes or hwc)
     if staged and not on_host:
         raise ValueError("staged=True is for pinned host stacks")
+    if bands is None:
+        bands = 4 if codes else 16          # measured optimum: few large bands when the input is small (scratch/hwc_sweep.py)
     with torch.cuda.device(dev):
         if staged:
             stage_val = torch.empty(val.shape, dtype=val.dtype, device=dev)

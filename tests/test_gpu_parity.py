@@ -537,10 +537,11 @@ def test_hdr_merge_interleaved_bgr_codes_equal_planar(ct, bits, n):
                                            code_layout="hwc_bgr")
             assert torch.equal(got[0], want[0])
             assert (got[1] is None and want[1] is None) or torch.equal(got[1], want[1])
-    host = kernels.hdr_merge_update(kernels.HdrMergeState(), camera.pin_memory(), StdSpec("multiplier", 0.05), t, theta, True, True,
-                                    device=torch.device(DEV), code_layout="hwc_bgr")
     dev = kernels.hdr_merge_update(kernels.HdrMergeState(), planar.to(DEV), StdSpec("multiplier", 0.05), t, theta, True, True)
-    assert torch.equal(host[0], dev[0]) and torch.equal(host[1], dev[1])
+    for staged, bands in ((None, 16), (True, 3), (False, 1)):      # default = staged band pipeline; False = read in place
+        host = kernels.hdr_merge_update(kernels.HdrMergeState(), camera.pin_memory(), StdSpec("multiplier", 0.05), t, theta, True, True,
+                                        device=torch.device(DEV), code_layout="hwc_bgr", staged=staged, bands=bands)
+        assert torch.equal(host[0], dev[0]) and torch.equal(host[1], dev[1])
     with pytest.raises(ValueError):
         kernels.hdr_merge_update(kernels.HdrMergeState(), val.to(DEV), None, t, theta, True, True, code_layout="hwc_bgr")
 
