@@ -204,3 +204,29 @@ def test_kernels_do_not_write_outside_their_outputs(ct):
         assert intact(rb, numel) and intact(sb, numel) and intact(lb, n * numel) and intact(gb, n * numel)
         assert intact(mb, n * numel) and intact(eb, n * numel) and all(intact(b, numel) for b, _ in states)
         assert intact(sums_b, p * 3 * 5)
+
+
+def test_staged_host_pipelines_back_to_back_without_sync(ct):
+    """The staged entry points recycle device staging buffers (torch's caching allocator hands the same blocks to the next
+    call) while copies and kernels of the previous call may still be in flight: 12 merges and 12 linearisations of
+    alternating inputs are queued without any synchronisation and every result is checked afterwards."""
+    from clair_torch_b200 import kernels
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    stacks = [ct.synthetic.make_stack(5, 3, 120, 200, bits=16, seed=s) for s in (1, 2, 3)]
+    want = [kernels.hdr_merge_update(kernels.HdrMergeState(), v.to(DEV), s.to(DEV), t, theta, True, True, radiance_dtype=torch.float32)
+            for v, s, t in stacks]
+    want_lin = [kernels.linearize(v.to(DEV), s.to(DEV), theta) for v, s, _ in stacks]
+    pinned = [(v.pin_memory(), s.pin_memory(), t) for v, s, t in stacks]
+    outs, lins = [], []
+    for k in range(12):
+        v, s, t = pinned[k % 3]
+        rad = torch.empty((3, 120, 200), dtype=torch.float32).pin_memory()
+        sig = torch.empty_like(rad).pin_memory()
+        kernels.hdr_merge_update(kernels.HdrMergeState(), v, s, t, theta, True, True, radiance_dtype=torch.float32,
+                                 device=torch.device(DEV), host_out=(rad, sig), staged=True, bands=5)
+        outs.append((rad, sig))
+        lins.append(kernels.linearize(v, s, theta, device=torch.device(DEV), pinned_out=True, staged=True, bands=7))
+    torch.cuda.synchronize()
+    for k in range(12):
+        assert torch.equal(outs[k][0], want[k % 3][0].cpu()) and torch.equal(outs[k][1], want[k % 3][1].cpu()), k
+        assert torch.equal(lins[k][0], want_lin[k % 3][0].cpu()) and torch.equal(lins[k][1], want_lin[k % 3][1].cpu()), k
