@@ -36,6 +36,7 @@ inline int64_t resident_blocks_per_channel(int blocks_per_sm, int n_channels) {
 struct Tuning {
     int hdr_vec = 0;            // cap the pixels per thread of the HDR-merge kernel (1, 2, 4)
     int hdr_waves = 0;          // resident waves per persistent grid
+    int hdr_fixed_max = 0;      // largest N that takes the register kernel (fp32 stacks)
     int hdr_force_dynamic = 0;  // use the N-dynamic float64-sum kernel even for N <= 8
     int stats_blocks_per_sm = 0;
     int grad_blocks_per_sm = 0;

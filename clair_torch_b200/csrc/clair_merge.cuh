@@ -279,7 +279,8 @@ struct RowCursor {
 // Persistent blocks; one thread owns VEC adjacent pixels of one channel per loop trip.  All 2N vector loads of
 // the trip are issued before the first use; (R_n, Q_n) stay in registers until mean_B is known, so the variance
 // is a plain sum of squares of the actual (small) per-frame terms: no cancellation, everything in fp32.
-constexpr int kMaxFixedFrames = 8;
+constexpr int kMaxFixedFrames = 8;         // integer ingest and the dark-field variant
+constexpr int kMaxFixedFramesF32 = 16;     // fp32 stacks, 2 pixels per thread: (R_n, Q_n) of 16 frames still fit the register file
 
 template <int VEC, int NF, int STD, bool SINGLE, int SRC>
 __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams p) {
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_smem_kernel(const HdrParams 
             }
         }
         hdr_finish<VEC, true, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
-            float acc0 = 0.0f, acc1 = 0.0f;
+            float acc = 0.0f;                                 // one accumulator, frame order: the same bits as the register kernel
             const float *col = s_rq + k * kBlock;
             int n = 0;
             for (; n + 4 <= N; n += 4) {                      // four frames per trip: eight independent LDS in flight
@@ -532,14 +533,14 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_smem_kernel(const HdrParams 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float g = fmaf(alpha, r[j], gamma * q[j]);
-                    if (j & 1) acc1 = fmaf(g, g, acc1); else acc0 = fmaf(g, g, acc0);
+                    acc = fmaf(g, g, acc);
                 }
             }
             for (; n < N; ++n) {
                 const float g = fmaf(alpha, col[n * (2 * VEC * kBlock)], gamma * col[n * (2 * VEC * kBlock) + VEC * kBlock]);
-                acc0 = fmaf(g, g, acc0);
+                acc = fmaf(g, g, acc);
             }
-            return acc0 + acc1;
+            return acc;
         });
     }
 }
@@ -650,8 +651,9 @@ int launch_merge_kernel(K kernel, const MergeLaunch &m) {
     if (int rc = ensure_smem(kernel, m.smem)) return rc;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, m.smem);
-    // resident waves per persistent grid: 2 for the register kernel, 3 for the shared-memory-parked one (measured)
-    per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : (m.parked ? 3 : 2));
+    // resident waves per persistent grid (measured): 2 for the register kernel up to 8 frames, 3 beyond and for the
+    // shared-memory-parked kernel
+    per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : ((m.parked || m.n_frames > kMaxFixedFrames) ? 3 : 2));
     const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(m.want_blocks, resident_blocks_per_channel(per_sm, m.n_channels)));
     kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(m.n_channels)), kBlock, m.smem, m.stream>>>(m.p);
     return 0;
@@ -672,7 +674,22 @@ int launch_merge_by_std(const MergeLaunch &m) {
         case 5: return CLAIR_FIXED_NF(5, ST);           \
         case 6: return CLAIR_FIXED_NF(6, ST);           \
         case 7: return CLAIR_FIXED_NF(7, ST);           \
-        default: return CLAIR_FIXED_NF(8, ST);          \
+        case 8: return CLAIR_FIXED_NF(8, ST);           \
+        default:                                        \
+            if constexpr (SRC == kSrcF32 && V <= 2) {   \
+                switch (m.n_frames) {                   \
+                    case 9: return CLAIR_FIXED_NF(9, ST);   \
+                    case 10: return CLAIR_FIXED_NF(10, ST); \
+                    case 11: return CLAIR_FIXED_NF(11, ST); \
+                    case 12: return CLAIR_FIXED_NF(12, ST); \
+                    case 13: return CLAIR_FIXED_NF(13, ST); \
+                    case 14: return CLAIR_FIXED_NF(14, ST); \
+                    case 15: return CLAIR_FIXED_NF(15, ST); \
+                    default: return CLAIR_FIXED_NF(16, ST); \
+                }                                       \
+            } else {                                    \
+                return CLAIR_FIXED_NF(8, ST);           \
+            }                                           \
     }
 #define CLAIR_PARKED(ST) \
     (m.single ? launch_merge_kernel(hdr_merge_smem_kernel<V, ST, true, SRC>, m) : launch_merge_kernel(hdr_merge_smem_kernel<V, ST, false, SRC>, m))

@@ -572,7 +572,8 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     size_t smem = (theta_dev ? sizeof(float2) * n_channels * lut_size : 0) + (src == kSrcU8 ? 256 * sizeof(float) : 0);
     const bool single = is_first && is_final;
     // integer ingest takes 4 codes per load, which leaves no registers for more than 8 frames of (R_n, Q_n)
-    const bool fixed = has_std && n_frames <= (src == kSrcF32 ? kMaxFixedFrames : 8) && !g_tuning.hdr_force_dynamic;
+    const int fixed_max_f32 = g_tuning.hdr_fixed_max > 0 ? std::min(g_tuning.hdr_fixed_max, kMaxFixedFramesF32) : kMaxFixedFramesF32;
+    const bool fixed = has_std && !g_tuning.hdr_force_dynamic && n_frames <= (src == kSrcF32 ? fixed_max_f32 : kMaxFixedFrames);
     // measured on B200 (profiles/): with fp32 input 2 pixels per thread keep the fixed-N kernel at 40 registers
     // (6 blocks/SM); 4 pixels per thread need 64.  Integer ingest always takes 4 codes per load.
     // 9 .. ~40 frames: (R_n, Q_n) parked in shared memory, 2 pixels per thread (1 when H*W is odd)
@@ -586,7 +587,8 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         const int park_vec = std::min(vec, 2);
         const size_t park_bytes = sizeof(float) * 2 * park_vec * kBlock * static_cast<size_t>(n_frames);
         parked = has_std && !fixed && !g_tuning.hdr_force_dynamic && smem + park_bytes <= 110 * 1024;   // >= 2 blocks per SM
-        const int vec_cap = g_tuning.hdr_vec > 0 ? g_tuning.hdr_vec : ((fixed || parked) ? 2 : 4);
+        // the register kernel beyond 8 frames exists for 1 and 2 pixels per thread only
+        const int vec_cap = (fixed && n_frames > kMaxFixedFrames) ? 2 : (g_tuning.hdr_vec > 0 ? g_tuning.hdr_vec : ((fixed || parked) ? 2 : 4));
         if (vec_cap < vec) vec = vec_cap;
         if (parked) smem += sizeof(float) * 2 * vec * kBlock * static_cast<size_t>(n_frames);
     }
