@@ -1,12 +1,15 @@
 #!/usr/bin/env python
 """Benchmark of the headline metric: HDR-merge throughput in Mpixel*frames/s (BASELINE.json).
 
-Workload: a 5-frame 8-bit RGB 1920x1080 synthetic exposure stack handed over as
-fp32 value + fp32 std images, fixed 256-entry ICRF with distinct rows (LINEAR), Gaussian weights, whole stack in
-one batch, radiance + uncertainty written as fp32.  One "step" = one merge of one stack.
+Workload (SURVEY.md §8(d), config c4 = BASELINE.json configs[3], the configuration the "at 1/2/4/8 B200" metric is quoted
+on): every rank owns its share of the 64 stacks of 9 frames x 24 MP (4000x6000) 16-bit RGB, handed over as fp32 value +
+fp32 std images; fixed 256-entry ICRF with distinct rows (LINEAR), Gaussian weights, whole stack in one batch, radiance +
+uncertainty written as fp32.  One "step" = one merge of one stack (216 Mpixel*frames, 5.76 GB of algorithmic traffic).
+`--workload c1` selects the reference's own CPU-sized case instead (configs[0], 5 x 1080p 8-bit); the default run
+reports it under `extra`.
 
   value     kernel-only: stacks resident in HBM, K back-to-back launches through the C ABI, CUDA events.
-            Four distinct stacks (995 MB) are rotated so no step finds its inputs in the 126 MB L2.
+            Distinct stacks are rotated (each is 5.2 GB, far beyond the 126 MB L2).
   e2e       the same merge through the public API (compute_hdr_image) from PINNED HOST buffers, with the
             host->device copy of the stack and the device->host read of radiance + uncertainty inside the
             timed region.
@@ -30,21 +33,34 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_FRAMES, CHANNELS, HEIGHT, WIDTH, BITS, LUT = 5, 3, 1080, 1920, 8, 256
-ALGO_BYTES_PER_PIXEL_FRAME = CHANNELS * (4 * 2 + 8 / N_FRAMES)      # C*(b_in(1+sigma) + 8/N) = 28.8
+N_FRAMES, CHANNELS, HEIGHT, WIDTH, BITS, LUT = 5, 3, 1080, 1920, 8, 256       # c1 geometry (secondary metrics)
 METRIC = "hdr_merge_mpixel_frames_per_s"
-WORKLOAD = ("c1: HDR merge, 5x 8-bit RGB 1920x1080 synthetic exposure stack as fp32 val+std, 256-entry LINEAR ICRF "
-            "(distinct rows), gaussian weights, first-order uncertainty, fp32 radiance+sigma")
+WORKLOADS = {
+    "c4": {"n": 9, "c": 3, "h": 4000, "w": 6000, "bits": 16, "seed": 4567, "n_sets": 3,
+           "kernel": "clair::hdr_merge_fixed_kernel<2,9,1,true,0> (2 px/thread, N=9 in registers, single batch)",
+           "label": ("c4: HDR merge of 9-frame 24 MP (4000x6000) 16-bit RGB synthetic exposure stacks as fp32 val+std, sharded "
+                     "by stack (each rank merges its share of the 64 stacks), 256-entry LINEAR ICRF (distinct rows), gaussian "
+                     "weights, first-order uncertainty, fp32 radiance+sigma")},
+    "c1": {"n": 5, "c": 3, "h": 1080, "w": 1920, "bits": 8, "seed": 1234, "n_sets": 4,
+           "kernel": "clair::hdr_merge_fixed_kernel<2,5,1,true,0> (2 px/thread, N=5 in registers, single batch)",
+           "label": ("c1: HDR merge, 5x 8-bit RGB 1920x1080 synthetic exposure stack as fp32 val+std, 256-entry LINEAR ICRF "
+                     "(distinct rows), gaussian weights, first-order uncertainty, fp32 radiance+sigma")},
+}
 
 
-def ncu_traffic():
+def algo_bytes_per_pixel_frame(cfg):
+    """C*(b_in(1+sigma) + 8/N) with fp32 val + std in and fp32 radiance + sigma out."""
+    return cfg["c"] * (4 * 2 + 8 / cfg["n"])
+
+
+def ncu_traffic(key):
     """DRAM bytes per launch of the headline kernel from the committed ncu --set full capture (profiles/)."""
     path = os.path.join(ROOT, "profiles", "r1_hdr_traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as fh:
-        d = json.load(fh)
-    return d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"]
+        d = json.load(fh).get(key)
+    return None if d is None else d["dram_bytes_read_per_launch"] + d["dram_bytes_write_per_launch"]
 
 
 def peaks():
@@ -100,20 +116,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_rate(rows, repeats=1):
+def cpu_oracle_rate(cfg, rows, repeats=1):
     """Mpixel*frames/s of the CPU oracle (C + OpenMP port of the reference algorithm, all host threads) on the
-    first `rows` rows of the c1 stack.  Returns (rate, seconds per merge, threads)."""
+    first `rows` rows of one stack of the workload.  Returns (rate, seconds per merge, threads)."""
     import clair_torch_b200.synthetic as syn
     from oracle import c_oracle as corc
-    val, std, t = syn.make_stack(N_FRAMES, CHANNELS, rows, WIDTH, bits=BITS, seed=1234)
-    theta = syn.reference_curve(CHANNELS, LUT).numpy()
+    val, std, t = syn.make_stack(cfg["n"], cfg["c"], rows, cfg["w"], bits=cfg["bits"], seed=cfg["seed"])
+    theta = syn.reference_curve(cfg["c"], LUT).numpy()
     v, s = val.numpy(), std.numpy()
     corc.hdr_merge(v[:, :, :8], s[:, :, :8], t, theta, True)          # warm-up (thread pool, page faults)
     t0 = time.perf_counter()
     for _ in range(repeats):
         corc.hdr_merge(v, s, t, theta, True)
     dt = (time.perf_counter() - t0) / repeats
-    return N_FRAMES * rows * WIDTH / dt / 1e6, dt, corc.max_threads()
+    return cfg["n"] * rows * cfg["w"] / dt / 1e6, dt, corc.max_threads()
 
 
 REFERENCE_NOTE = ("the reference itself is pure Python/torch and cannot travel to the GPU box; its own CPU path measured in "
@@ -126,12 +142,14 @@ def run_reference(args, rank, world):
         return
     import clair_torch_b200.synthetic as syn
     from oracle import c_oracle as corc
-    # size the per-step sample so that K steps stay within ~2 minutes: calibrate on 135 rows
-    _, dt135, threads = cpu_oracle_rate(135)
+    cfg = WORKLOADS[args.workload]
+    # size the per-step sample so that K steps stay within ~2 minutes: calibrate on a thin band of rows
+    probe = 64
+    _, dt_probe, threads = cpu_oracle_rate(cfg, probe)
     budget_s = 100.0
-    rows = int(max(8, min(HEIGHT, 135 * budget_s / max(dt135 * max(args.steps + args.warmup, 1), 1e-9))))
-    val, std, t = syn.make_stack(N_FRAMES, CHANNELS, rows, WIDTH, bits=BITS, seed=1234)
-    theta = syn.reference_curve(CHANNELS, LUT).numpy()
+    rows = int(max(8, min(cfg["h"], 1000, probe * budget_s / max(dt_probe * max(args.steps + args.warmup, 1), 1e-9))))
+    val, std, t = syn.make_stack(cfg["n"], cfg["c"], rows, cfg["w"], bits=cfg["bits"], seed=cfg["seed"])
+    theta = syn.reference_curve(cfg["c"], LUT).numpy()
     v, s = val.numpy(), std.numpy()
     for _ in range(args.warmup):
         corc.hdr_merge(v, s, t, theta, True)
@@ -139,13 +157,13 @@ def run_reference(args, rank, world):
     for _ in range(args.steps):
         corc.hdr_merge(v, s, t, theta, True)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    value = N_FRAMES * rows * WIDTH / dt / 1e6
-    sample = (f"rows 0..{rows} of {HEIGHT} of one c1 stack per step ({rows / HEIGHT:.3f} of the workload), C/OpenMP oracle "
-              f"port of the reference algorithm; {REFERENCE_NOTE}")
+    value = cfg["n"] * rows * cfg["w"] / dt / 1e6
+    sample = (f"rows 0..{rows} of {cfg['h']} of one {args.workload} stack per step ({rows / cfg['h']:.3f} of the workload), "
+              f"C/OpenMP oracle port of the reference algorithm; {REFERENCE_NOTE}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel*frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
+            "config": {"workload": cfg["label"], "sample": sample},
             "cpu_baseline": {"value": value, "unit": "Mpixel*frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -371,19 +389,10 @@ def secondary_metrics(dev):
     del val, std
     torch.cuda.empty_cache()
     peak = peaks()[0]
-    # c4: one stack of 9 frames x 24 MP 16-bit (fp32 val + std): merge, then per-frame linearisation
-    val, std, t = ct.synthetic.make_stack(9, CHANNELS, 4000, 6000, bits=16, seed=4567, device=dev)
-    rad = torch.empty((CHANNELS, 4000, 6000), dtype=torch.float32, device=dev)
+    # per-frame linearisation of the c4 frames (24 MP, 16-bit as fp32 val + std)
+    val, std, t = ct.synthetic.make_stack(3, CHANNELS, 4000, 6000, bits=16, seed=4567, device=dev)
+    rad = None
     st = kernels.HdrMergeState
-
-    def merge9():
-        return kernels.hdr_merge_update(st(), val, std, t, theta, True, True, radiance_dtype=torch.float32)
-
-    ms4 = timed(merge9, 2, 10)
-    e4 = 9 * CHANNELS * 4000 * 6000
-    out["hdr_merge_c4_stack"] = {"ms": ms4, "config": "1 stack: 9x3x4000x6000 16-bit as fp32 val+std",
-                                 "mpixel_frames_per_s": 9 * 24.0 / (ms4 * 1e-3),
-                                 "hbm_frac": (e4 * 8 + CHANNELS * 24e6 * 8) / (ms4 * 1e-3) / 1e9 / peak}
     one_val, one_std = val[:3].contiguous(), std[:3].contiguous()
     ms5 = timed(lambda: kernels.linearize(one_val, one_std, theta), 2, 10)
     out["linearize_c4_frames"] = {"ms_per_frame": ms5 / 3, "config": "3 frames of 3x4000x6000, f(x) and sigma",
@@ -441,61 +450,34 @@ def secondary_metrics(dev):
     return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=10)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the c2 training / c3 linearity secondary timings")
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    if args.warmup < 3:
-        args.warmup = 3
-
+def hdr_merge_bench(cfg, key, dev, lib, rank, world, steps, warmup, e2e_steps, sample_clocks=True):
+    """Kernel-only and end-to-end timing of the HDR merge on workload `cfg` (one rank's view).  Returns a dict; the
+    timed regions are bracketed by a barrier + synchronize on both sides and reduced with MAX over ranks."""
+    import ctypes
     import numpy as np
     import torch
     import torch.distributed as dist
     from torch.utils.data import DataLoader
 
     import clair_torch_b200 as ct
-    from clair_torch_b200 import kernels
 
-    local_cpus = bind_to_gpu_numa_node(local_rank)
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = ct._native.load()
-    for item in filter(None, os.environ.get("CLAIR_TUNE", "").split(",")):     # kernel tuning experiments only
-        key, _, val = item.partition("=")
-        ct._native.check(lib.clair_set_tuning(key.encode(), int(val)), "clair_set_tuning")
-
-    # ---- device-resident stacks: each rank owns its own stacks (sharding by stack, no data-path collective) ----
-    n_sets = 4
-    theta = ct.synthetic.reference_curve(CHANNELS, LUT).to(dev)
+    n, c, h, w = cfg["n"], cfg["c"], cfg["h"], cfg["w"]
+    n_sets = cfg["n_sets"]
+    theta = ct.synthetic.reference_curve(c, LUT).to(dev)
+    # device-resident stacks: each rank owns its own stacks (sharding by stack, no data-path collective)
     stacks = []
     for k in range(n_sets):
-        val, std, t = ct.synthetic.make_stack(N_FRAMES, CHANNELS, HEIGHT, WIDTH, bits=BITS, seed=1234 + 97 * rank + k,
-                                              device=dev)
+        val, std, t = ct.synthetic.make_stack(n, c, h, w, bits=cfg["bits"], seed=cfg["seed"] + 97 * rank + k, device=dev)
         stacks.append((val, std))
-    radiance = torch.empty((CHANNELS, HEIGHT, WIDTH), dtype=torch.float32, device=dev)
+    radiance = torch.empty((c, h, w), dtype=torch.float32, device=dev)
     sigma = torch.empty_like(radiance)
     t_host = np.ascontiguousarray(t)
-    import ctypes
     stream = torch.cuda.current_stream(dev)
 
     def launch(k):
         val, std = stacks[k % n_sets]
-        rc = lib.clair_hdr_merge_update(val.data_ptr(), std.data_ptr(), t_host.ctypes.data_as(ctypes.c_void_p), N_FRAMES,
-                                        theta.data_ptr(), CHANNELS, LUT, HEIGHT * WIDTH, None, 1, None, None, None, 1, 1,
+        rc = lib.clair_hdr_merge_update(val.data_ptr(), std.data_ptr(), t_host.ctypes.data_as(ctypes.c_void_p), n,
+                                        theta.data_ptr(), c, LUT, h * w, None, 1, None, None, None, 1, 1,
                                         radiance.data_ptr(), 0, sigma.data_ptr(), stream.cuda_stream)
         ct._native.check(rc, "clair_hdr_merge_update")
 
@@ -504,37 +486,40 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for k in range(args.warmup):
+    def max_over_ranks(x):
+        if world > 1:
+            tt = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        return x
+
+    for k in range(warmup):
         launch(k)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0 and sample_clocks:
         sampler.start()
     launches_before = ct._native.launch_count()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     start.record(stream)
-    for k in range(args.steps):
+    for k in range(steps):
         launch(k)
     stop.record(stream)
     barrier()
-    kernel_ms = start.elapsed_time(stop)
+    kernel_ms = max_over_ranks(start.elapsed_time(stop))
     launches = ct._native.launch_count() - launches_before
-    clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        tt = torch.tensor([kernel_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        kernel_ms = float(tt.item())
-    ms_per_step = kernel_ms / args.steps
-    units_per_step = N_FRAMES * HEIGHT * WIDTH / 1e6                        # Mpixel*frames per stack
-    value = world * units_per_step / (ms_per_step * 1e-3)
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+    ms_per_step = kernel_ms / steps
+    units_per_step = n * h * w / 1e6                                        # Mpixel*frames per stack
 
     # ---- end to end through the public API from pinned host memory ----
     val_h = stacks[0][0].cpu().pin_memory()
     std_h = stacks[0][1].cpu().pin_memory()
-    rad_h = torch.empty((CHANNELS, HEIGHT, WIDTH), dtype=torch.float32).pin_memory()
+    del stacks[1:]                                                          # make room for the staging buffers
+    rad_h = torch.empty((c, h, w), dtype=torch.float32).pin_memory()
     sig_h = torch.empty_like(rad_h).pin_memory()
-    batch = (torch.arange(N_FRAMES), val_h, std_h, {"exposure_time": torch.from_numpy(t_host)})
+    batch = (torch.arange(n), val_h, std_h, {"exposure_time": torch.from_numpy(t_host)})
 
     class OneBatch(torch.utils.data.Dataset):
         def __len__(self):
@@ -558,59 +543,112 @@ def main():
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.e2e_steps):
+    for _ in range(e2e_steps):
         e2e_step()
     e1.record(stream)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), wall_ms) / args.e2e_steps
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms) / e2e_steps)
+    peak, peak_src = peaks()
+    algo_bytes = algo_bytes_per_pixel_frame(cfg) * n * h * w                  # per launch = per stack
+    achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+    return {
+        "ms_per_step": ms_per_step, "value": world * units_per_step / (ms_per_step * 1e-3), "launches": int(launches),
+        "clocks": clocks, "n_sets": n_sets, "stack_bytes": 2 * n * c * h * w * 4,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": ncu_traffic(key), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                     "kernel": cfg["kernel"]},
+        "e2e": {"value": world * units_per_step / (e2e_ms * 1e-3), "unit": "Mpixel*frames/s",
+                "h2d_bytes_per_step": val_h.numel() * 4 + std_h.numel() * 4, "d2h_bytes_per_step": 2 * rad_h.numel() * 4,
+                "ms_per_step": e2e_ms,
+                "api": "clair_torch_b200.compute_hdr_image(pinned host batch, host_out=pinned buffers): clair_hdr_merge_staged, "
+                       "16 bands, H2D copy overlapped with the band kernels, results stored to pinned host memory by the kernel"},
+        "theta": theta, "t_host": t_host,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    # default K: one rank's share of c4 is 8 stacks, so a job is a burst of a few milliseconds; 200 back-to-back merges
+    # (~0.2 s) already run into the board's power cap (SM clock 1965 -> ~1550 MHz), longer runs only more so
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary timings (c1 merge, c2 training, c3 linearity, ...)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+
+    import clair_torch_b200 as ct
+
+    local_cpus = bind_to_gpu_numa_node(local_rank)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
-    e2e_value = world * units_per_step / (e2e_ms * 1e-3)
-    h2d = val_h.numel() * 4 + std_h.numel() * 4
-    d2h = rad_h.numel() * 4 + sig_h.numel() * 4
+        dist.init_process_group("nccl", device_id=dev)
+    lib = ct._native.load()
+    for item in filter(None, os.environ.get("CLAIR_TUNE", "").split(",")):     # kernel tuning experiments only
+        key, _, val = item.partition("=")
+        ct._native.check(lib.clair_set_tuning(key.encode(), int(val)), "clair_set_tuning")
+
+    cfg = WORKLOADS[args.workload]
+    res = hdr_merge_bench(cfg, args.workload, dev, lib, rank, world, args.steps, args.warmup, args.e2e_steps)
+    torch.cuda.empty_cache()
 
     dp = None
     if world > 1 and not args.no_extras:
-        del stacks
-        torch.cuda.empty_cache()
         dp = dp_training_metrics(dev, rank, world)       # collective: every rank takes part
     if rank == 0:
-        peak, peak_src = peaks()
-        algo_bytes = ALGO_BYTES_PER_PIXEL_FRAME * N_FRAMES * HEIGHT * WIDTH          # per launch = per stack
-        achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rows = HEIGHT
-            rate, dt, threads = cpu_oracle_rate(rows, repeats=20)
+            rows = min(cfg["h"], 1080 if args.workload == "c1" else 400)
+            reps = 20 if args.workload == "c1" else 10
+            rate, dt, threads = cpu_oracle_rate(cfg, rows, repeats=reps)
             cpu = {"value": rate, "unit": "Mpixel*frames/s", "cores": threads, "kind": "port",
-                   "sample": f"20 merges of the full c1 stack ({rows} rows), C/OpenMP oracle port, {dt:.3f} s per merge; "
-                             + REFERENCE_NOTE}
+                   "sample": f"{reps} merges of rows 0..{rows} of {cfg['h']} of one {args.workload} stack "
+                             f"({cfg['n'] * rows * cfg['w'] / 1e6:.1f} Mpixel*frames each), C/OpenMP oracle port, "
+                             f"{dt:.3f} s per merge; " + REFERENCE_NOTE}
         extra = None
         if world > 1 and dp is not None:
             extra = {"dp_train_c5": dp}
         if world == 1 and not args.no_extras:
-            stacks = None
+            extra = {}
+            other = "c1" if args.workload == "c4" else "c4"
+            r2 = hdr_merge_bench(WORKLOADS[other], other, dev, lib, 0, 1, 300 if other == "c1" else 50, 5, 3, sample_clocks=False)
             torch.cuda.empty_cache()
-            extra = secondary_metrics(dev)
-            extra["native_ingest_c1"] = native_ingest_metrics(dev, lib, theta, t_host)
+            extra[f"hdr_merge_{other}"] = {"workload": WORKLOADS[other]["label"], "ms_per_step": r2["ms_per_step"],
+                                           "mpixel_frames_per_s": r2["value"], "roofline": r2["roofline"],
+                                           "e2e": {k: v for k, v in r2["e2e"].items() if k != "api"}}
+            c1 = res if args.workload == "c1" else r2
+            extra.update(secondary_metrics(dev))
+            extra["native_ingest_c1"] = native_ingest_metrics(dev, lib, c1["theta"], c1["t_host"])
             extra["dp_train_c5"] = dp_training_metrics(dev, 0, 1)
+        res["e2e"]["host_cpus_bound"] = local_cpus
         line = {
-            "metric": METRIC, "value": value, "unit": "Mpixel*frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": res["value"], "unit": "Mpixel*frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "stacks_per_rank_rotated": n_sets,
-                       "l2": "4 distinct stacks (995 MB) rotated per step, each far larger than the 126 MB L2",
+            "config": {"workload": cfg["label"], "stacks_per_rank_rotated": res["n_sets"],
+                       "l2": f"{res['n_sets']} distinct stacks of {res['stack_bytes'] / 1e6:.0f} MB rotated per step, each far "
+                             "larger than the 126 MB L2",
                        "sharding": "by stack, one rank per GPU, no data-path collective"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                         "kernel": "clair::hdr_merge_fixed_kernel<2,5,true,true> (2 px/thread, N=5 in registers, single batch)"},
+            "roofline": res["roofline"],
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "host_cpus_bound": local_cpus, "api": "clair_torch_b200.compute_hdr_image(pinned host batch, host_out=pinned buffers): clair_hdr_merge_staged, 16 bands, H2D copy overlapped with the band kernels, results stored to pinned host memory by the kernel"},
-            "gpu_launches": int(launches), "clocks": clocks, "extra": extra,
+            "e2e": res["e2e"],
+            "gpu_launches": res["launches"], "clocks": res["clocks"], "extra": extra,
         }
         print(json.dumps(line))
     if world > 1:

@@ -146,13 +146,14 @@ __device__ __forceinline__ Pack<VEC> load_std(const HdrParams &p, int64_t o, con
 // (closed form of the autograd pass of inference/hdr_merge.py:107-115).
 struct HdrTerms {
     float w, wv, R, Q;
+    float P, v;      // P = s w f'/t (R without the weight-derivative part) and v: only the one-frame case reads them
 };
 
 __device__ __forceinline__ HdrTerms hdr_terms(float x, float s, float it, bool has_model, bool gaussian,
                                               uint32_t row_bias, float lm1, bool has_std) {
     HdrTerms o;
     float f = x, fp = 1.0f;
-    if (has_model) icrf_linear_biased(x, row_bias, lm1, f, fp);
+    if (has_model) icrf_linear_slope(x, row_bias, lm1, f, fp);
     float w = 1.0f, q = 0.0f;
     if (gaussian) {
         float d;
@@ -164,18 +165,33 @@ __device__ __forceinline__ HdrTerms hdr_terms(float x, float s, float it, bool h
     o.wv = w * v;
     if (has_std) {
         const float ws = w * s;
-        o.R = ws * fmaf(q, v, fp * it);
+        const float t1 = fp * it;
+        o.R = ws * fmaf(q, v, t1);
         o.Q = ws * q;
+        o.P = ws * t1;
     } else {
-        o.R = 0.0f; o.Q = 0.0f;
+        o.R = 0.0f; o.Q = 0.0f; o.P = 0.0f;
     }
+    o.v = v;
     return o;
+}
+
+// A one-frame batch: mean_B = w v / (w + 1e-6), so v - mean_B = v * 1e-6 / (w + 1e-6) EXACTLY, while the generic
+// R - mean_B Q has to recover that 1e-3..1e-6-sized difference from a cancellation (visible where f' = 0: a saturated
+// pixel).  Returns s w [f'/t + q (v - mean_B)], the alpha-part of the gradient, cancellation-free.
+__device__ __forceinline__ float one_frame_gradient(const HdrTerms &t) {
+    const float wbe = t.w + 1e-6f;
+    float inv = rcp_approx(wbe);
+    inv = fmaf(fmaf(-wbe, inv, 1.0f), inv, inv);
+    return fmaf(t.Q * t.v, 1e-6f * inv, t.P);
 }
 
 // Merge of the batch sums with the running state (common/statistics.py:88-109) and the output stage, shared by
 // both kernels.  `var_update(k, alpha, gamma)` returns sum_n (alpha R_n + gamma Q_n)^2 for pixel k.
 // SINGLE = the whole stack is this one batch (is_first && is_final): no state traffic, no float64.
-template <int VEC, bool HAS_STD, bool SINGLE, typename VarFn>
+// ONE = the batch is a single frame and the caller's R already holds the exact alpha-part of the gradient (see
+// one_frame_gradient): gamma then carries the running-state term only.
+template <int VEC, bool HAS_STD, bool SINGLE, bool ONE = false, typename VarFn>
 __device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, const float (&wsum)[VEC], const float (&wv)[VEC],
                                            VarFn var_update) {
     if constexpr (SINGLE) {
@@ -190,8 +206,10 @@ __device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, cons
             const float frac = (wsum[k] != 0.0f) ? 1.0f : __int_as_float(0x7fc00000);
             rad.v[k] = frac * mean_b;
             if constexpr (HAS_STD) {
+                // sum_n (alpha R_n - alpha mean_B Q_n)^2 = alpha^2 sum_n (R_n - mean_B Q_n)^2: SINGLE callers' var_update
+                // takes rho = -mean_B as its last argument and returns the unit sum (one FMA less per frame)
                 const float alpha = frac * inv;
-                sg.v[k] = sqrt_approx(var_update(k, alpha, -alpha * mean_b));
+                sg.v[k] = alpha * sqrt_approx(var_update(k, 1.0f, ONE ? 0.0f : -mean_b));
             }
         }
         if (p.radiance_f64) {
@@ -231,7 +249,7 @@ __device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, cons
             mean_new[k] = static_cast<double>(frac * mean_b);
             wtot.v[k] = wsum[k];
             alpha = frac * inv;
-            gamma = -alpha * mean_b;
+            gamma = ONE ? 0.0f : -alpha * mean_b;
         } else {
             const float wt = w_a.v[k] + wsum[k];                  // statistics.py:104
             const float frac = wsum[k] / wt;                      // statistics.py:106
@@ -239,7 +257,7 @@ __device__ __forceinline__ void hdr_finish(const HdrParams &p, int64_t off, cons
             mean_new[k] = mean_a[k] + static_cast<double>(frac) * dm;
             wtot.v[k] = wt;
             alpha = frac * inv;
-            gamma = static_cast<float>(static_cast<double>(w_a.v[k]) / (static_cast<double>(wt) * wt) * dm) - alpha * mean_b;
+            gamma = static_cast<float>(static_cast<double>(w_a.v[k]) / (static_cast<double>(wt) * wt) * dm) - (ONE ? 0.0f : alpha * mean_b);
         }
         if constexpr (HAS_STD) var_new.v[k] = var_a.v[k] + var_update(k, alpha, gamma);
     }
@@ -289,7 +307,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
     const int C = p.n_channels, L = p.lut;
     const bool has_model = p.theta != nullptr;
     float *s_x = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));     // kSrcU8: code -> fl32(code)/code_max
-    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
+    if (has_model) stage_curve_slopes(s_tab, p.theta, C, L);
     if constexpr (src_is_u8(SRC)) {
         for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
     }
@@ -337,16 +355,16 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
                                                  HAS_STD);
                     wsum[k] += t.w;
                     wv[k] += t.wv;
-                    R[n][k] = t.R;
+                    R[n][k] = (NF == 1) ? one_frame_gradient(t) : t.R;
                     Q[n][k] = t.Q;
                 }
             }
         }
-        hdr_finish<VEC, HAS_STD, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+        hdr_finish<VEC, HAS_STD, SINGLE, NF == 1>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
             float acc = 0.0f;
 #pragma unroll
             for (int n = 0; n < NF; ++n) {
-                const float g = fmaf(alpha, R[n][k], gamma * Q[n][k]);
+                const float g = SINGLE ? fmaf(gamma, Q[n][k], R[n][k]) : fmaf(alpha, R[n][k], gamma * Q[n][k]);
                 acc = fmaf(g, g, acc);
             }
             return acc;
@@ -367,7 +385,7 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrPara
     extern __shared__ float2 s_tab[];
     const int C = p.n_channels, L = p.lut;
     const bool has_model = p.theta != nullptr;
-    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
+    if (has_model) stage_curve_slopes(s_tab, p.theta, C, L);
     __syncthreads();
     const int c = blockIdx.y;
     const int64_t frame_stride = static_cast<int64_t>(C) * p.stride;
@@ -432,18 +450,18 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrPara
                         const HdrTerms t = hdr_terms(xm, sm, it, has_model, gaussian, bias[k], lm1, true);
                         wsum[k] += t.w;
                         wv[k] += t.wv;
-                        R[n0 + j][k] = t.R;
+                        R[n0 + j][k] = (NF == 1) ? one_frame_gradient(t) : t.R;
                         Q[n0 + j][k] = t.Q;
                     }
                 }
             }
         }
         if (!active) continue;
-        hdr_finish<VEC, true, SINGLE>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+        hdr_finish<VEC, true, SINGLE, NF == 1>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
             float acc = 0.0f;
 #pragma unroll
             for (int n = 0; n < NF; ++n) {
-                const float g = fmaf(alpha, R[n][k], gamma * Q[n][k]);
+                const float g = SINGLE ? fmaf(gamma, Q[n][k], R[n][k]) : fmaf(alpha, R[n][k], gamma * Q[n][k]);
                 acc = fmaf(g, g, acc);
             }
             return acc;
@@ -464,7 +482,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_smem_kernel(const HdrParams 
     const bool has_model = p.theta != nullptr;
     float *s_x = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
     float *s_rq = s_x + (src_is_u8(SRC) ? 256 : 0) + threadIdx.x;
-    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
+    if (has_model) stage_curve_slopes(s_tab, p.theta, C, L);
     if constexpr (src_is_u8(SRC)) {
         for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
     }
@@ -532,12 +550,13 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_smem_kernel(const HdrParams 
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float g = fmaf(alpha, r[j], gamma * q[j]);
+                    const float g = SINGLE ? fmaf(gamma, q[j], r[j]) : fmaf(alpha, r[j], gamma * q[j]);
                     acc = fmaf(g, g, acc);
                 }
             }
             for (; n < N; ++n) {
-                const float g = fmaf(alpha, col[n * (2 * VEC * kBlock)], gamma * col[n * (2 * VEC * kBlock) + VEC * kBlock]);
+                const float rn = col[n * (2 * VEC * kBlock)], qn = col[n * (2 * VEC * kBlock) + VEC * kBlock];
+                const float g = SINGLE ? fmaf(gamma, qn, rn) : fmaf(alpha, rn, gamma * qn);
                 acc = fmaf(g, g, acc);
             }
             return acc;
@@ -555,7 +574,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
     const int C = p.n_channels, L = p.lut;
     const bool has_model = p.theta != nullptr;
     float *s_x = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
-    if (has_model) stage_curve_pairs(s_tab, p.theta, C, L);
+    if (has_model) stage_curve_slopes(s_tab, p.theta, C, L);
     if constexpr (src_is_u8(SRC)) {
         for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
     }
