@@ -213,4 +213,48 @@ __device__ __forceinline__ float gaussian_weight(float x, float neg_scale_log2e,
 
 __device__ __forceinline__ int wrap_inc(int u, int C) { return (u + 1 == C) ? 0 : u + 1; }
 
+// ---- packed fp32x2 arithmetic: sm_100a issues FFMA2 / FMUL2 / FADD2, two IEEE fp32 results per issue slot ----
+// The pair kernels are bound by instruction issue, not by HBM, and give every lane two adjacent pixels, so their
+// add / mul / fma chains run on 64-bit register pairs.  min / max / compare / MUFU have no packed form.
+// ptxas contracts a packed mul feeding a packed add into FFMA2 even with .rn: nothing that selects an integer
+// (LUT index, mask) may be written as such a pair.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f32x2 splat2(float v) { return pack2(v, v); }
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2_rd(f32x2 a, f32x2 b) {      // round towards -inf: the floor trick of floor_small
+    f32x2 d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 lds2(const float *p) { return *reinterpret_cast<const f32x2 *>(p); }
+__device__ __forceinline__ void sts2(float *p, f32x2 v) { *reinterpret_cast<f32x2 *>(p) = v; }
+
 }  // namespace clair

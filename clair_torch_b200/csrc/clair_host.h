@@ -39,9 +39,12 @@ struct Tuning {
     int hdr_fixed_max = 0;      // largest N that takes the register kernel (fp32 stacks)
     int hdr_force_dynamic = 0;  // use the N-dynamic float64-sum kernel even for N <= 8
     int stats_blocks_per_sm = 0;
+    int stats_warps = 0;        // block shape of the statistics kernel (both must be set)
+    int stats_slots = 0;
     int grad_blocks_per_sm = 0;
     int grad_pix = 0;           // 1 forces one pixel per lane in the gradient kernel
     int grad_warps = 0;         // warps per block of the gradient kernel
+    int grad_copies = 0;        // replicated gradient tables the pair-gradient kernel spreads its reductions over
 };
 extern Tuning g_tuning;
 

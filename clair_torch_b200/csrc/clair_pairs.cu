@@ -16,7 +16,10 @@ constexpr float kPairNegScaleLog2e = -14.426950408889634f;   // -10 * log2(e); t
 constexpr int kMaxPairsPerLaunch = 256;   // the pair table travels as a kernel argument
 constexpr int kStatsTile = 128;           // pixels per shared-memory tile in the statistics kernel (power of two)
 constexpr int kMaxSlots = 4;              // pairs a warp carries in registers in the statistics kernel
-constexpr int kGradCopies = 64;           // replicated gradient tables the REDs are spread over
+constexpr int kGradCopies = 64;           // replicated gradient tables the REDs of the scatter kernels are spread over
+constexpr int kMaxGradCopies = 1024;      // the workspace holds this many
+constexpr int kPairGradCopies = 1024;     // pair-gradient kernel: the L2 reductions are the bound, and hot table entries
+                                          // serialise — c5 gradient 3.84 / 3.44 / 2.35 / 2.40 ms with 64 / 256 / 1024 / 4096 copies
 constexpr int kFlushTiles = 8;            // tiles between flushes of the fp32 partial sums into float64 (32 terms per lane)
 
 struct PairTable {
@@ -40,6 +43,7 @@ struct PairParams {
     int lut;
     int n_pairs;                 // pairs in this launch
     int unc_weighting;
+    int n_copies;                // gradient: replicated tables in use
     float valid_lo, valid_hi;
     uint32_t mod_magic;          // ceil(2^16 / C): x mod C for x < 2^13 without a divide
     CurveRows rows;
@@ -307,6 +311,306 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
 }
 
 // =====================================================================================================
+// Statistics kernel, packed form (the default: H*W % 4 == 0, 16-byte aligned stacks).  Same block / tile / slot
+// organisation as above, but every lane works on two adjacent pixels held as fp32x2 register pairs — the kernel
+// is bound by instruction issue and FFMA2 / FMUL2 / FADD2 retire two fp32 results per slot:
+//   * staging: one item = 4 pixels of one frame = two packed halves; table over (g0, g1 - g0);
+//   * pair phase: 64-bit shared loads, validity folded into the Gaussian weight as kMaskedWeight (gi + gj < 0
+//     <=> masked), 0/1 mask as a float pair so the masked sums are plain packed multiply-adds;
+//   * FULL: the fp32 partial sums of both halves share one pivot per (lane, slot): the first valid loss seen.
+// Measured on the c3 stack (16 x 4K, 29 pairs): 8930 -> ~5000 warp instructions per tile.
+// =====================================================================================================
+constexpr float kMaskedWeight = -1.0e30f;  // gw of a masked element: no sum with finite weights gets back above 0
+
+__device__ __forceinline__ f32x2 rcp_fast2(f32x2 x) {     // 2 x MUFU.RCP + one packed Newton step
+    float x0, x1;
+    unpack2(x, x0, x1);
+    const f32x2 r = pack2(rcp_approx(x0), rcp_approx(x1));
+    return fma2(fma2(sub2(0ull, x), r, splat2(1.0f)), r, r);
+}
+
+template <bool HAS_STD, bool RELATIVE>
+struct FrameTerms2 {
+    f32x2 f, gw, sig, rel;
+};
+
+// per-frame terms of two adjacent pixels (see FrameTerms); `live` = the pixels exist
+template <bool HAS_STD, bool RELATIVE>
+__device__ __forceinline__ FrameTerms2<HAS_STD, RELATIVE> frame_terms2(float x0, float x1, float s0, float s1, bool has_model,
+                                                                      uint32_t bias0, uint32_t bias1, float lm1, float lo, float hi,
+                                                                      bool live) {
+    FrameTerms2<HAS_STD, RELATIVE> t;
+    const f32x2 x2 = pack2(x0, x1);
+    float f0 = x0, f1 = x1, fp0 = 1.0f, fp1 = 1.0f;
+    if (has_model) {
+        float r0, r1;
+        unpack2(mul2(x2, splat2(lm1)), r0, r1);                          // image * (L - 1), rounded once
+        const float xs0 = fminf(fmaxf(r0, 0.0f), lm1), xs1 = fminf(fmaxf(r1, 0.0f), lm1);
+        const f32x2 xs2 = pack2(xs0, xs1);
+        const f32x2 two23 = splat2(8388608.0f);
+        const f32x2 t2 = add2_rd(xs2, two23);
+        float t0, t1, w0, w1;
+        unpack2(t2, t0, t1);
+        unpack2(sub2(xs2, sub2(t2, two23)), w0, w1);
+        float g00, dg0, g01, dg1;
+        asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g00), "=f"(dg0) : "r"(static_cast<uint32_t>(__float_as_int(t0)) * 8u + bias0));
+        asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g01), "=f"(dg1) : "r"(static_cast<uint32_t>(__float_as_int(t1)) * 8u + bias1));
+        f0 = fmaf(w0, dg0, g00);
+        f1 = fmaf(w1, dg1, g01);
+        if constexpr (HAS_STD) {
+            fp0 = (xs0 == r0) ? __fmul_rn(dg0, lm1) : 0.0f;
+            fp1 = (xs1 == r1) ? __fmul_rn(dg1, lm1) : 0.0f;
+        }
+    }
+    t.f = pack2(f0, f1);
+    const f32x2 d2 = add2(x2, splat2(-0.5f));
+    float e0, e1;
+    unpack2(mul2(mul2(d2, d2), splat2(kPairNegScaleLog2e)), e0, e1);
+    t.gw = pack2((live && x0 >= lo && x0 <= hi) ? exp2f_approx(e0) : kMaskedWeight,
+                 (live && x1 >= lo && x1 <= hi) ? exp2f_approx(e1) : kMaskedWeight);
+    t.sig = 0ull;
+    t.rel = 0ull;
+    if constexpr (HAS_STD) {
+        const float sg0 = fabsf(__fmul_rn(fp0, s0)), sg1 = fabsf(__fmul_rn(fp1, s1));
+        t.sig = pack2(sg0, sg1);
+        if constexpr (RELATIVE) t.rel = mul2(t.sig, rcp_fast2(pack2(fmaxf(f0, 1e-6f), fmaxf(f1, 1e-6f))));   // losses.py:55,58
+    }
+    return t;
+}
+
+// TRIPS = staging items per thread (N * 32 items <= TRIPS * blockDim.x): an item's frame, tile offset, table rows and
+// shared-memory slot never change, and the loads of the NEXT tile are issued before the pair phase of the current one,
+// so their HBM latency is hidden behind it.
+template <int SLOTS, bool ERR, bool RELATIVE, bool FULL, int TRIPS>
+__global__ void __launch_bounds__(512) pair_stats2_kernel(const PairParams p) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int C = p.n_channels, L = p.lut, N = p.n_frames;
+    const bool has_model = p.theta != nullptr;
+    float2 *s_tab = reinterpret_cast<float2 *>(s_raw);
+    // tile layout [frame][array][pixel]:  0: f   1: gw   2: sig (ERR)   3: sig / max(f, 1e-6) (ERR && RELATIVE)
+    constexpr int kArr = 2 + (ERR ? (RELATIVE ? 2 : 1) : 0);
+    constexpr int kFrameFloats = kArr * kStatsTile;
+    float *s_tile = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
+    if (has_model) stage_curve_slopes(s_tab, p.theta, C, L);
+
+    const int c = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_warps = blockDim.x >> 5;
+    const float lm1 = static_cast<float>(L - 1);
+    const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
+    const float *val_c = p.val + static_cast<int64_t>(c) * p.plane;
+    const int64_t std_minus_val = ERR ? (p.std - p.val) : 0;
+    const bool unc = p.unc_weighting != 0;
+    const uint32_t tab_bias = curve_row_bias(s_tab);
+    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
+    const uint32_t uC = static_cast<uint32_t>(C);
+    const uint32_t plane = static_cast<uint32_t>(p.plane);
+
+    double d0[SLOTS], d1[SLOTS], d2[SLOTS], d3[SLOTS], d4[SLOTS];
+    f32x2 t0[SLOTS], t1[SLOTS], t2[SLOTS], t3[SLOTS], t4[SLOTS];    // fp32 partials (two halves) of the last <= kFlushTiles tiles
+    float pivot[SLOTS];
+    bool have[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        d0[s] = 0.0; d1[s] = 0.0; d2[s] = 0.0; d3[s] = 0.0; d4[s] = 0.0;
+        t0[s] = 0ull; t1[s] = 0ull; t2[s] = 0ull; t3[s] = 0ull; t4[s] = 0ull;
+        pivot[s] = 0.0f; have[s] = false;
+    }
+    auto halves = [](f32x2 v) { float a, b; unpack2(v, a, b); return static_cast<double>(a) + static_cast<double>(b); };
+    auto flush = [&]() {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            d0[s] += halves(t0[s]); t0[s] = 0ull;
+            d1[s] += halves(t1[s]); t1[s] = 0ull;
+            if constexpr (FULL) {
+                d2[s] += halves(t2[s]); t2[s] = 0ull;
+                if constexpr (ERR) { d3[s] += halves(t3[s]); t3[s] = 0ull; }
+                d4[s] += halves(t4[s]); t4[s] = 0ull;
+            }
+        }
+    };
+    int since_flush = 0;
+
+    const uint32_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
+    // per-thread staging items: frame n, pixel offset q inside the tile, source pointer, shared-memory slot, table row
+    const float *src[TRIPS];
+    float *dst[TRIPS];
+    uint32_t qoff[TRIPS], urow[TRIPS];
+    bool active[TRIPS];
+    const uint32_t du_tile = (gridDim.x * kStatsTile) % uC;
+#pragma unroll
+    for (int t = 0; t < TRIPS; ++t) {
+        const int item = threadIdx.x + t * blockDim.x;
+        const int n = item >> 5;
+        active[t] = n < N;
+        qoff[t] = (static_cast<uint32_t>(item) & 31u) * 4u;
+        src[t] = val_c + static_cast<int64_t>(active[t] ? n : 0) * frame_stride + qoff[t];
+        dst[t] = s_tile + (active[t] ? n : 0) * kFrameFloats + qoff[t];
+        urow[t] = (blockIdx.x * kStatsTile + qoff[t] + static_cast<uint32_t>(p.rows.base(c))) % uC;   // row of the item's first pixel
+    }
+    float4 xv[TRIPS], sv[TRIPS];
+    auto prefetch = [&](uint32_t tile) {
+        const uint32_t pix0 = tile * kStatsTile;
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            xv[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            sv[t] = xv[t];
+            if (active[t] && tile < n_tiles && pix0 + qoff[t] < plane) {       // plane % 4 == 0: the whole item is in or out
+                xv[t] = __ldcs(reinterpret_cast<const float4 *>(src[t] + pix0));
+                if constexpr (ERR) sv[t] = __ldcs(reinterpret_cast<const float4 *>(src[t] + pix0 + std_minus_val));
+            }
+        }
+    };
+    prefetch(blockIdx.x);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        __syncthreads();   // previous tile fully consumed (also orders the table staging on the first pass)
+        const uint32_t pix0 = tile * kStatsTile;
+        // phase A: one item = 4 adjacent pixels of one frame, loaded one tile ahead
+#pragma unroll
+        for (int t = 0; t < TRIPS; ++t) {
+            if (active[t]) {
+                const bool live = pix0 + qoff[t] < plane;
+                uint32_t u = urow[t];
+                uint32_t bias[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { bias[k] = tab_bias + u * row_bytes; u = (u + 1 == uC) ? 0u : u + 1; }
+                const auto a = frame_terms2<ERR, RELATIVE>(xv[t].x, xv[t].y, sv[t].x, sv[t].y, has_model, bias[0], bias[1], lm1,
+                                                           p.valid_lo, p.valid_hi, live);
+                const auto b = frame_terms2<ERR, RELATIVE>(xv[t].z, xv[t].w, sv[t].z, sv[t].w, has_model, bias[2], bias[3], lm1,
+                                                           p.valid_lo, p.valid_hi, live);
+                *reinterpret_cast<ulonglong2 *>(dst[t]) = make_ulonglong2(a.f, b.f);
+                *reinterpret_cast<ulonglong2 *>(dst[t] + kStatsTile) = make_ulonglong2(a.gw, b.gw);
+                if constexpr (ERR) {
+                    *reinterpret_cast<ulonglong2 *>(dst[t] + 2 * kStatsTile) = make_ulonglong2(a.sig, b.sig);
+                    if constexpr (RELATIVE) *reinterpret_cast<ulonglong2 *>(dst[t] + 3 * kStatsTile) = make_ulonglong2(a.rel, b.rel);
+                }
+                urow[t] += du_tile;
+                urow[t] = (urow[t] >= uC) ? urow[t] - uC : urow[t];
+            }
+        }
+        prefetch(tile + gridDim.x);
+        __syncthreads();
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int pr = warp + s * n_warps;
+            if (pr < p.n_pairs) {
+                const float *fi = s_tile + p.pairs.i[pr] * kFrameFloats + lane * 2;
+                const float *fj = s_tile + p.pairs.j[pr] * kFrameFloats + lane * 2;
+                const float r_hi = p.pairs.r_hi[pr];
+                const f32x2 nrh2 = splat2(-r_hi), nrl2 = splat2(-p.pairs.r_lo[pr]);
+                f32x2 a0 = t0[s], a1 = t1[s], a2 = t2[s], a3 = t3[s], a4 = t4[s];
+                float k = pivot[s];
+                bool hv = have[s];
+#pragma unroll
+                for (int it = 0; it < kStatsTile / 64; ++it) {
+                    const int q = 64 * it;
+                    const f32x2 av = lds2(fi + q), bv = lds2(fj + q);
+                    const f32x2 wg = add2(lds2(fi + kStatsTile + q), lds2(fj + kStatsTile + q));   // < 0 <=> masked
+                    const f32x2 d = fma2(bv, nrl2, fma2(bv, nrh2, av));                          // a - b r
+                    f32x2 inv = 0ull, ell2;
+                    if constexpr (RELATIVE) {
+                        inv = rcp_fast2(fma2(bv, splat2(r_hi), splat2(1e-6f)));                     // 1 / (expected + 1e-6), losses.py:45
+                        ell2 = mul2(d, inv);
+                    } else {
+                        ell2 = d;
+                    }
+                    float l0, l1, g0, g1;
+                    unpack2(ell2, l0, l1);
+                    unpack2(wg, g0, g1);
+                    const bool v0 = g0 >= 0.0f, v1 = g1 >= 0.0f;
+                    // |.| (es can be negative once the curve dips below 0); a masked element's loss may be anything
+                    // (even Inf / NaN): it is replaced by 0 so that its zero weight really removes it
+                    l0 = v0 ? fabsf(l0) : 0.0f;
+                    l1 = v1 ? fabsf(l1) : 0.0f;
+                    f32x2 wt = pack2(fmaxf(g0, 0.0f), fmaxf(g1, 0.0f));
+                    f32x2 err = 0ull;
+                    if constexpr (ERR) {
+                        const f32x2 sa = lds2(fi + 2 * kStatsTile + q);
+                        float s0, s1;
+                        if constexpr (RELATIVE) {
+                            const f32x2 e1 = mul2(sa, inv);
+                            const f32x2 e2 = mul2(mul2(av, lds2(fj + 3 * kStatsTile + q)), inv);
+                            unpack2(fma2(e1, e1, fma2(e2, e2, splat2(1e-6f))), s0, s1);            // losses.py:57-60
+                        } else {
+                            const f32x2 rs = mul2(lds2(fj + 2 * kStatsTile + q), splat2(r_hi));
+                            unpack2(fma2(sa, sa, mul2(rs, rs)), s0, s1);                            // losses.py:62
+                        }
+                        const float er0 = v0 ? sqrt_approx(s0) : 0.0f, er1 = v1 ? sqrt_approx(s1) : 0.0f;
+                        err = pack2(er0, er1);
+                        if (unc) {                                                                  // losses.py:97
+                            float u0, u1;
+                            unpack2(rcp_fast2(add2(err, splat2(1e-6f))), u0, u1);
+                            wt = add2(wt, pack2(v0 ? u0 : 0.0f, v1 ? u1 : 0.0f));
+                        }
+                    }
+                    if constexpr (FULL) {
+                        if (!hv) {                                    // the pivot: the first valid loss this lane sees
+                            k = v0 ? l0 : (v1 ? l1 : k);
+                            hv = v0 || v1;
+                        }
+                        const f32x2 vm = pack2(v0 ? 1.0f : 0.0f, v1 ? 1.0f : 0.0f);
+                        const f32x2 dl = mul2(vm, sub2(pack2(l0, l1), splat2(k)));
+                        const f32x2 wdl = mul2(wt, dl);
+                        a0 = add2(a0, wt);
+                        a1 = add2(a1, wdl);
+                        a2 = fma2(wdl, dl, a2);
+                        if constexpr (ERR) a3 = add2(a3, err);
+                        a4 = add2(a4, vm);
+                    } else {
+                        a0 = add2(a0, wt);
+                        a1 = fma2(wt, pack2(l0, l1), a1);
+                    }
+                }
+                t0[s] = a0; t1[s] = a1;
+                if constexpr (FULL) {
+                    t2[s] = a2;
+                    if constexpr (ERR) t3[s] = a3;
+                    t4[s] = a4;
+                    pivot[s] = k;
+                    have[s] = hv;
+                }
+            }
+        }
+        if (++since_flush == kFlushTiles) { flush(); since_flush = 0; }
+    }
+    flush();
+
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+        const int pr = warp + s * n_warps;
+        if (pr < p.n_pairs) {     // warp-uniform
+            // back to pivot 0 in float64:  sum w l = B + k W,  sum w l^2 = A + 2 k B + k^2 W
+            const double kd = static_cast<double>(pivot[s]);
+            double v0 = d0[s];
+            double v1 = FULL ? d1[s] + kd * d0[s] : d1[s];
+            double v2 = FULL ? d2[s] + 2.0 * kd * d1[s] + kd * kd * d0[s] : 0.0;
+            double v3 = d3[s];
+            double v4 = d4[s];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+                if constexpr (FULL) {
+                    v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+                    if constexpr (ERR) v3 += __shfl_xor_sync(0xffffffffu, v3, o);
+                    v4 += __shfl_xor_sync(0xffffffffu, v4, o);
+                }
+            }
+            if (lane == 0) {
+                double *out = p.sums + (static_cast<int64_t>(pr) * C + c) * 5;
+                atomicAdd(out + 0, v0);
+                atomicAdd(out + 1, v1);
+                if constexpr (FULL) {
+                    atomicAdd(out + 2, v2);
+                    if constexpr (ERR) atomicAdd(out + 3, v3);
+                    atomicAdd(out + 4, v4);
+                }
+            }
+        }
+    }
+}
+
+// =====================================================================================================
 // Gradient kernel.  Each warp owns 32 pixels of one channel at a time: the per-frame terms of those pixels
 // go to the warp's private shared-memory slice, every pair is visited by the same lane that owns the pixel
 // (so the per-frame upstream G[n] accumulates without atomics; runs of pairs with the same first frame keep
@@ -360,7 +664,7 @@ __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
     const float *val_c = p.val + static_cast<int64_t>(c) * p.plane;
     const int64_t std_minus_val = ERR ? (p.std - p.val) : 0;
     const int lp = L + 2;
-    float *copy = p.hist + static_cast<int64_t>((blockIdx.x * n_warps + warp) % kGradCopies) * (2 * C * lp);
+    float *copy = p.hist + static_cast<int64_t>((blockIdx.x * n_warps + warp) % p.n_copies) * (2 * C * lp);
     const uint32_t tab_bias = curve_row_bias(s_tab);
     const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
     const uint32_t uC = static_cast<uint32_t>(C);
@@ -515,6 +819,281 @@ __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
     }
 }
 
+// =====================================================================================================
+// Gradient kernel, packed form (the default: H*W even, 8-byte aligned stacks).  Same algorithm as above with two
+// adjacent pixels per lane held as fp32x2 register pairs, so the add / mul / fma chains issue as FFMA2 / FMUL2 /
+// FADD2 — the kernel is bound by instruction issue and shared-memory bandwidth, not by HBM.  Differences:
+//   * the body of a trip is lane-private (the slice columns are [lane][2]): no warp synchronisation, the last
+//     partial group simply drops its dead lanes;
+//   * validity is folded into the Gaussian weight as a large negative number: gi + gj < 0 <=> the pair element is
+//     masked, and max(gi + gj, 0) is the weight (one FMNMX instead of two compares and two selects);
+//   * a run of pairs with the same first frame keeps that frame's terms and its gradient sum in registers
+//     (4 shared-memory accesses per pair instead of 6);
+//   * table over (g0, g1 - g0): f = g0 + w (g1 - g0) in one FMA (within 1 ulp of the reference's form);
+//   * frame pointers advance by a constant, tap addresses are 32-bit offsets from one base: a trip of N = 2,
+//     P = 1 went from 459 to under 200 warp instructions.
+// =====================================================================================================
+
+// One predicated vector reduction per element: both taps in one L2 operation.  The kernel is bound by exactly these:
+// red.global.add.v2.f32 sustains 176 G operations/s on random table entries and ~110 G/s on 16 hot ones
+// (scratch/smem_atomics.cu).  A block-private table in shared memory does not help on sm_100a — there is no native
+// floating-point shared atomic, and the compiler's ATOMS.CAST.SPIN loop (or a 64-bit CAS loop) collapses on the hot
+// entries that real exposure stacks produce (dark frames put a warp's 64 pixels on a few dozen entries): measured
+// 0.52 ms (fp32 atomicAdd x2) and 3.1 ms (CAS.64) against 0.46 ms for this form on the c2 stack.  Integer
+// fixed-point shared atomics are native and fast but cannot cover the 1/es range of the relative loss (5 decades).
+__device__ __forceinline__ void red_add_v2_if(float *addr, float a, float b, float g) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %3, 0f00000000;\n\t@p red.global.add.v2.f32 [%0], {%1, %2};\n\t}"
+                 ::"l"(addr), "f"(a), "f"(b), "f"(g));
+}
+
+template <bool ERR, bool RELATIVE>
+__global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int C = p.n_channels, L = p.lut, N = p.n_frames, P = p.n_pairs;
+    const int c = blockIdx.y;
+    float2 *s_tab = reinterpret_cast<float2 *>(s_raw);
+    float *s_up = reinterpret_cast<float *>(s_tab + C * L);      // U[p, c] and mean[p, c] of this channel
+    float *s_mean = s_up + P;
+    const uint32_t lp = static_cast<uint32_t>(L + 2);
+    stage_curve_slopes(s_tab, p.theta, C, L);
+    for (int k = threadIdx.x; k < P; k += blockDim.x) {
+        s_up[k] = static_cast<float>(p.upstream[static_cast<int64_t>(k) * C + c]);
+        s_mean[k] = static_cast<float>(p.mean[static_cast<int64_t>(k) * C + c]);
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_warps = blockDim.x >> 5;
+    // warp-private slice, layout [frame][array][lane][2]
+    //   0: f   1: gw   2: xs   3: G (per-frame upstream)   4: sigma (ERR)   5: 1 / max(f, 1e-6) (ERR && RELATIVE)
+    constexpr int kArrays = ERR ? 6 : 4;
+    constexpr int kArr = 64;
+    constexpr int kFrameFloats = kArrays * kArr;
+    float *slice = s_mean + P + warp * (N * kFrameFloats) + lane * 2;
+
+    const float lm1 = static_cast<float>(L - 1);
+    const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
+    const float *val_c = p.val + static_cast<int64_t>(c) * p.plane;
+    const int64_t std_minus_val = ERR ? (p.std - p.val) : 0;
+    float *copy = p.hist + static_cast<int64_t>((blockIdx.x * n_warps + warp) % p.n_copies) * (2 * C * lp);
+    const uint32_t odd_step = static_cast<uint32_t>(C) * lp + 1u;     // A[u][x0] -> B[u][x0 + 1]
+    const uint32_t tab_bias = curve_row_bias(s_tab);
+    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
+    const uint32_t uC = static_cast<uint32_t>(C);
+    const uint32_t plane = static_cast<uint32_t>(p.plane);
+    const float lo = p.valid_lo, hi = p.valid_hi;
+    const f32x2 two23 = splat2(8388608.0f);
+
+    const uint32_t n_groups = (plane + 63u) / 64u;
+    const uint32_t grp_stride = gridDim.x * n_warps;
+    uint32_t grp = blockIdx.x * n_warps + warp;
+    uint32_t u0 = (grp * 64u + lane * 2u + static_cast<uint32_t>(p.rows.base(c))) % uC;
+    const uint32_t du = (grp_stride * 64u) % uC;
+    for (; grp < n_groups; grp += grp_stride) {
+        const uint32_t pix = grp * 64u + lane * 2u;
+        if (pix >= plane) break;                         // plane % 2 == 0; nothing below crosses lanes
+        const uint32_t u1 = (u0 + 1u == uC) ? 0u : u0 + 1u;
+        const uint32_t bias0 = tab_bias + u0 * row_bytes, bias1 = tab_bias + u1 * row_bytes;
+
+        // ---- per-frame terms into the slice ----
+        auto stage = [&](int n, float2 xin, float2 sin) {
+            const f32x2 x2 = pack2(xin.x, xin.y);
+            float r0, r1;
+            unpack2(mul2(x2, splat2(lm1)), r0, r1);                       // image * (L - 1), rounded once
+            const float xs0 = fminf(fmaxf(r0, 0.0f), lm1), xs1 = fminf(fmaxf(r1, 0.0f), lm1);
+            const f32x2 xs2 = pack2(xs0, xs1);
+            const f32x2 t2 = add2_rd(xs2, two23);
+            const f32x2 w2 = sub2(xs2, sub2(t2, two23));
+            float t0, t1, w0, w1;
+            unpack2(t2, t0, t1);
+            unpack2(w2, w0, w1);
+            float g00, dg0, g01, dg1;
+            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g00), "=f"(dg0) : "r"(static_cast<uint32_t>(__float_as_int(t0)) * 8u + bias0));
+            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g01), "=f"(dg1) : "r"(static_cast<uint32_t>(__float_as_int(t1)) * 8u + bias1));
+            const float f0 = fmaf(w0, dg0, g00), f1 = fmaf(w1, dg1, g01);
+            const f32x2 d2 = add2(x2, splat2(-0.5f));
+            float e0, e1;
+            unpack2(mul2(mul2(d2, d2), splat2(kPairNegScaleLog2e)), e0, e1);
+            const float gw0 = (xin.x >= lo && xin.x <= hi) ? exp2f_approx(e0) : kMaskedWeight;
+            const float gw1 = (xin.y >= lo && xin.y <= hi) ? exp2f_approx(e1) : kMaskedWeight;
+            float *dst = slice + n * kFrameFloats;
+            sts2(dst, pack2(f0, f1));
+            sts2(dst + kArr, pack2(gw0, gw1));
+            sts2(dst + 2 * kArr, xs2);
+            sts2(dst + 3 * kArr, 0ull);
+            if constexpr (ERR) {
+                const float fp0 = (xs0 == r0) ? __fmul_rn(dg0, lm1) : 0.0f;
+                const float fp1 = (xs1 == r1) ? __fmul_rn(dg1, lm1) : 0.0f;
+                sts2(dst + 4 * kArr, pack2(fabsf(__fmul_rn(fp0, sin.x)), fabsf(__fmul_rn(fp1, sin.y))));
+                if constexpr (RELATIVE) sts2(dst + 5 * kArr, pack2(rcp_approx(fmaxf(f0, 1e-6f)), rcp_approx(fmaxf(f1, 1e-6f))));
+            }
+        };
+        {
+            const float *src = val_c + pix;
+            int n = 0;
+            for (; n + 4 <= N; n += 4) {                 // four frames' loads in flight
+                float2 xv[4], sv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    xv[j] = __ldcs(reinterpret_cast<const float2 *>(src));
+                    sv[j] = ERR ? __ldcs(reinterpret_cast<const float2 *>(src + std_minus_val)) : make_float2(0.0f, 0.0f);
+                    src += frame_stride;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) stage(n + j, xv[j], sv[j]);
+            }
+            if (n + 2 <= N) {
+                float2 xv[2], sv[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    xv[j] = __ldcs(reinterpret_cast<const float2 *>(src));
+                    sv[j] = ERR ? __ldcs(reinterpret_cast<const float2 *>(src + std_minus_val)) : make_float2(0.0f, 0.0f);
+                    src += frame_stride;
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) stage(n + j, xv[j], sv[j]);
+                n += 2;
+            }
+            if (n < N) {
+                const float2 xv = __ldcs(reinterpret_cast<const float2 *>(src));
+                const float2 sv = ERR ? __ldcs(reinterpret_cast<const float2 *>(src + std_minus_val)) : make_float2(0.0f, 0.0f);
+                stage(n, xv, sv);
+            }
+        }
+
+        // ---- all pairs of the lane's two pixels ----
+        int cur_i = -1;
+        const float *fi = slice;
+        f32x2 acc_i = 0ull, a2 = 0ull, gi2 = 0ull, sa2 = 0ull;
+        for (int pr = 0; pr < P; ++pr) {
+            const int pi = p.pairs.i[pr];
+            if (pi != cur_i) {                                   // uniform across the warp
+                if (cur_i >= 0) sts2(const_cast<float *>(fi) + 3 * kArr, add2(lds2(fi + 3 * kArr), acc_i));
+                cur_i = pi;
+                fi = slice + pi * kFrameFloats;
+                acc_i = 0ull;
+                a2 = lds2(fi);
+                gi2 = lds2(fi + kArr);
+                if constexpr (ERR) sa2 = lds2(fi + 4 * kArr);
+            }
+            float *fj = slice + p.pairs.j[pr] * kFrameFloats;
+            const float r_hi = p.pairs.r_hi[pr];
+            const f32x2 nrh2 = splat2(-r_hi), nrl2 = splat2(-p.pairs.r_lo[pr]);
+            const float up_pr = s_up[pr];
+            const f32x2 b2 = lds2(fj);
+            const f32x2 wg2 = add2(gi2, lds2(fj + kArr));                    // < 0 <=> masked
+            const f32x2 gj_acc = lds2(fj + 3 * kArr);
+            const f32x2 d2 = fma2(b2, nrl2, fma2(b2, nrh2, a2));             // a - b r, r = r_hi + r_lo
+            float wg0, wg1;
+            unpack2(wg2, wg0, wg1);
+            f32x2 ga2, gb2;
+            if constexpr (RELATIVE) {
+                float es0, es1;
+                unpack2(fma2(b2, splat2(r_hi), splat2(1e-6f)), es0, es1);
+                // MUFU.RCP alone (~1 ulp): the gate on the gradient is 1e-5 of its maximum
+                const f32x2 inv2 = pack2(rcp_approx(es0), rcp_approx(es1));
+                const f32x2 q2 = mul2(d2, inv2);
+                float q0, q1;
+                unpack2(q2, q0, q1);
+                f32x2 wu2;                                                   // weight * upstream, 0 where masked
+                f32x2 extra_a = 0ull, extra_b = 0ull;
+                if constexpr (ERR) {
+                    // the inverse-uncertainty weight depends on the curve through a, es and max(b, 1e-6)
+                    const f32x2 up2 = pack2(wg0 >= 0.0f ? up_pr : 0.0f, wg1 >= 0.0f ? up_pr : 0.0f);
+                    const f32x2 ib2 = lds2(fj + 5 * kArr);
+                    const f32x2 e1 = mul2(sa2, inv2);
+                    const f32x2 c2 = mul2(mul2(lds2(fj + 4 * kArr), ib2), inv2);
+                    const f32x2 e2 = mul2(a2, c2);
+                    const f32x2 ss = fma2(e1, e1, mul2(e2, e2));             // e1^2 + e2^2
+                    float T0, T1;
+                    unpack2(add2(ss, splat2(1e-6f)), T0, T1);
+                    const float rerr0 = rsqrt_approx(T0), rerr1 = rsqrt_approx(T1);          // 1 / err
+                    const f32x2 rerr2 = pack2(rerr0, rerr1);
+                    float ew0, ew1;
+                    unpack2(fma2(pack2(T0, T1), rerr2, splat2(1e-6f)), ew0, ew1);            // err + 1e-6
+                    const f32x2 rw2 = pack2(rcp_approx(ew0), rcp_approx(ew1));
+                    wu2 = mul2(add2(wg2, rw2), up2);
+                    // dm/dWt * dWt/derr * derr/dT = (l - m) U * (-rw^2) * 1/(2 err)
+                    const f32x2 lm2 = add2(pack2(fabsf(q0), fabsf(q1)), splat2(-s_mean[pr]));
+                    const f32x2 kk = mul2(mul2(mul2(lm2, up2), mul2(mul2(rw2, rw2), splat2(-0.5f))), rerr2);
+                    float b0, b1;
+                    unpack2(b2, b0, b1);
+                    const f32x2 e2sq_ib = mul2(mul2(e2, e2), ib2);
+                    const f32x2 dT_dbs = mul2(e2sq_ib, pack2(b0 >= 1e-6f ? -2.0f : 0.0f, b1 >= 1e-6f ? -2.0f : 0.0f));
+                    const f32x2 dT_des = mul2(mul2(inv2, splat2(-2.0f)), ss);
+                    extra_a = mul2(kk, mul2(mul2(e2, c2), splat2(2.0f)));
+                    extra_b = mul2(kk, fma2(dT_des, splat2(r_hi), dT_dbs));
+                } else {
+                    wu2 = mul2(pack2(fmaxf(wg0, 0.0f), fmaxf(wg1, 0.0f)), splat2(up_pr));
+                }
+                // sign(q) * (wt U / es) with sign(0) = 0, as torch.abs' backward has it
+                float m0, m1;
+                unpack2(mul2(wu2, inv2), m0, m1);
+                m0 = (q0 != 0.0f) ? m0 : 0.0f;
+                m1 = (q1 != 0.0f) ? m1 : 0.0f;
+                const f32x2 base2 = pack2(__int_as_float(__float_as_int(m0) ^ (__float_as_int(q0) & 0x80000000)),
+                                          __int_as_float(__float_as_int(m1) ^ (__float_as_int(q1) & 0x80000000)));
+                // dl/da = sgn / es;  dl/db = -sgn r (a + 1e-6) / es^2
+                const f32x2 ae2 = mul2(add2(a2, splat2(1e-6f)), inv2);
+                if constexpr (ERR) {
+                    ga2 = add2(base2, extra_a);
+                    gb2 = fma2(mul2(base2, nrh2), ae2, extra_b);
+                } else {
+                    ga2 = base2;
+                    gb2 = mul2(mul2(base2, nrh2), ae2);
+                }
+            } else {
+                float d0, d1;
+                unpack2(d2, d0, d1);
+                f32x2 wu2;
+                if constexpr (ERR) {
+                    const f32x2 rs2 = mul2(lds2(fj + 4 * kArr), splat2(r_hi));
+                    float v0, v1;
+                    unpack2(fma2(sa2, sa2, mul2(rs2, rs2)), v0, v1);
+                    // constant with respect to the curve
+                    const f32x2 rw2 = pack2(rcp_approx(sqrt_approx(v0) + 1e-6f), rcp_approx(sqrt_approx(v1) + 1e-6f));
+                    wu2 = mul2(add2(wg2, rw2), pack2(wg0 >= 0.0f ? up_pr : 0.0f, wg1 >= 0.0f ? up_pr : 0.0f));
+                } else {
+                    wu2 = mul2(pack2(fmaxf(wg0, 0.0f), fmaxf(wg1, 0.0f)), splat2(up_pr));
+                }
+                float m0, m1;
+                unpack2(wu2, m0, m1);
+                m0 = (d0 != 0.0f) ? m0 : 0.0f;
+                m1 = (d1 != 0.0f) ? m1 : 0.0f;
+                ga2 = pack2(__int_as_float(__float_as_int(m0) ^ (__float_as_int(d0) & 0x80000000)),
+                            __int_as_float(__float_as_int(m1) ^ (__float_as_int(d1) & 0x80000000)));
+                gb2 = mul2(ga2, nrh2);
+            }
+            acc_i = add2(acc_i, ga2);
+            sts2(fj + 3 * kArr, add2(gj_acc, gb2));
+        }
+        if (cur_i >= 0) sts2(const_cast<float *>(fi) + 3 * kArr, add2(lds2(fi + 3 * kArr), acc_i));
+
+        // ---- one vectorised reduction per frame element: {G (1 - w), G w} at the element's two taps ----
+        const uint32_t pre0 = u0 * lp - 0x4B000000u, pre1 = u1 * lp - 0x4B000000u;
+        for (int n = 0; n < N; ++n) {
+            const float *fr = slice + n * kFrameFloats;
+            const f32x2 g2 = lds2(fr + 3 * kArr);
+            const f32x2 xs2 = lds2(fr + 2 * kArr);
+            const f32x2 t2 = add2_rd(xs2, two23);
+            const f32x2 w2 = sub2(xs2, sub2(t2, two23));
+            float t0, t1, g0, g1, lo0, lo1, hi0, hi1;
+            unpack2(t2, t0, t1);
+            unpack2(g2, g0, g1);
+            unpack2(mul2(g2, sub2(splat2(1.0f), w2)), lo0, lo1);
+            unpack2(mul2(g2, w2), hi0, hi1);
+            const uint32_t bits0 = static_cast<uint32_t>(__float_as_int(t0)), bits1 = static_cast<uint32_t>(__float_as_int(t1));
+            // bits = 0x4B000000 | x0: even x0 -> A[u][x0], odd x0 -> B[u][x0 + 1] (8-byte aligned either way)
+            const uint32_t off0 = (bits0 & 1u) * odd_step + bits0 + pre0;
+            const uint32_t off1 = (bits1 & 1u) * odd_step + bits1 + pre1;
+            red_add_v2_if(copy + off0, lo0, hi0, g0);
+            red_add_v2_if(copy + off1, lo1, hi1, g1);
+        }
+        u0 += du;
+        u0 = (u0 >= uC) ? u0 - uC : u0;
+    }
+}
+
 // Scatter of an arbitrary upstream image: the table gradient of clair_icrf_forward (LINEAR).
 __global__ void __launch_bounds__(256) icrf_backward_theta_kernel(const float *__restrict__ x, const float *__restrict__ gy,
                                                                   float *hist, int64_t plane, int C, int L, CurveRows rows) {
@@ -568,14 +1147,14 @@ __global__ void __launch_bounds__(256) icrf_lookup_backward_kernel(const float *
 }
 
 // grad[u][k] += sum over copies of A[u][k] + B[u][k+1], in float64; one warp per table entry
-__global__ void __launch_bounds__(256) grad_finalize_kernel(const float *__restrict__ hist, double *grad, int C, int L) {
+__global__ void __launch_bounds__(256) grad_finalize_kernel(const float *__restrict__ hist, double *grad, int C, int L, int n_copies) {
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (i >= C * L) return;
     const int u = i / L, k = i - u * L;
     const int lp = L + 2;
     double acc = 0.0;
-    for (int r = lane; r < kGradCopies; r += 32) {
+    for (int r = lane; r < n_copies; r += 32) {
         const float *copy = hist + static_cast<int64_t>(r) * (2 * C * lp);
         acc += static_cast<double>(copy[u * lp + k]) + static_cast<double>(copy[C * lp + u * lp + k + 1]);
     }
@@ -705,15 +1284,20 @@ int set_smem(K kernel, size_t bytes) {
 // Choose warps per block W and register slots S (W*S >= pairs in the launch) from an instruction-count model of one
 // tile: every warp stages ceil(N*items/ (32 W)) items of VA pixels (cost_item each) and then walks S pair slots of
 // kStatsTile/32 pixels each (cost_pair per pixel).  Block time per tile ~ that sum; SM throughput ~ 1 / (W * sum).
+// The packed kernel (va == 4) keeps its staging items in registers, at most two per thread: W >= ceil(N / 2).
 void pick_stats_shape(int count, int n_frames, int va, bool err, bool full, int &warps, int &slots) {
-    const int cost_item = va * (err ? 50 : 40) + 12;
-    const int cost_pair = (kStatsTile / 32) * ((full ? 30 : 21) + (err ? 16 : 0));
+    const bool packed = va == 4;
+    const int cost_item = packed ? (err ? 150 : 100) : va * (err ? 50 : 40) + 12;
+    const int cost_pair = packed ? (full ? (err ? 130 : 75) : (err ? 100 : 55))
+                                 : (kStatsTile / 32) * ((full ? 30 : 21) + (err ? 16 : 0));
     const int items = n_frames * (kStatsTile / va);
     long best = -1;
     warps = 8; slots = kMaxSlots;
     for (int s = 1; s <= kMaxSlots; ++s) {
+        if (s == 3) continue;                         // slot counts instantiated: 1, 2, 4
         for (int w = 2; w <= 16; ++w) {
             if (w * s < count) continue;
+            if (packed && 2 * w < n_frames) continue;
             const int trips = (items + 32 * w - 1) / (32 * w);
             const long cost = static_cast<long>(w) * (static_cast<long>(trips) * cost_item + static_cast<long>(s) * cost_pair);
             if (best < 0 || cost < best) { best = cost; warps = w; slots = s; }
@@ -754,7 +1338,7 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
     const bool vec_ok = plane % 4 == 0 && reinterpret_cast<uintptr_t>(val_dev) % 16 == 0 &&
                         (!err || reinterpret_cast<uintptr_t>(std_dev) % 16 == 0) &&
                         (theta_dev == nullptr || (n_channels * lut_size) % 2 == 0);   // tile starts 16-byte aligned after the table
-    const int va = vec_ok ? 4 : 1;
+    const int va = (vec_ok && n_frames <= 32) ? 4 : 1;     // the packed kernel holds <= 2 staging items per thread, 16 warps
     const int n_launches = (n_pairs + per_launch - 1) / per_launch;
     int first = 0;
     for (int l = 0; l < n_launches; ++l) {
@@ -767,6 +1351,13 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
         if (int rc = fill_pairs(fn, p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
         int warps, slots;
         pick_stats_shape(count, n_frames, va, err, full != 0, warps, slots);
+        if (g_tuning.stats_warps > 0 && g_tuning.stats_slots > 0 && g_tuning.stats_warps * g_tuning.stats_slots >= count &&
+            g_tuning.stats_warps <= 16 && 2 * g_tuning.stats_warps >= n_frames &&
+            (g_tuning.stats_slots == 1 || g_tuning.stats_slots == 2 || g_tuning.stats_slots == 4)) {
+            warps = g_tuning.stats_warps;
+            slots = g_tuning.stats_slots;
+        }
+        const int trips = (n_frames + warps - 1) / warps;      // staging items per thread of the packed kernel (1 or 2)
         const int64_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
         auto launch = [&](auto kernel) -> int {
             if (int rc = set_smem(kernel, smem)) return rc;
@@ -778,7 +1369,9 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
             return 0;
         };
         int rc = 0;
-#define STATS_FLAGS(S, E, R, F) (va == 4 ? launch(pair_stats_kernel<S, E, R, F, 4>) : launch(pair_stats_kernel<S, E, R, F, 1>))
+#define STATS_FLAGS(S, E, R, F)                                                                        \
+    (va == 4 ? (trips == 1 ? launch(pair_stats2_kernel<S, E, R, F, 1>) : launch(pair_stats2_kernel<S, E, R, F, 2>)) \
+             : launch(pair_stats_kernel<S, E, R, F, 1>))
 #define STATS_CASE(S)                                                                                   \
     case S:                                                                                             \
         if (err) {                                                                                      \
@@ -792,7 +1385,6 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
         switch (slots) {
             STATS_CASE(1)
             STATS_CASE(2)
-            STATS_CASE(3)
             default:
             STATS_CASE(4)
         }
@@ -827,13 +1419,13 @@ extern "C" int clair_pair_means(const float *val_dev, const float *std_dev, int 
 
 extern "C" size_t clair_grad_workspace_bytes(int n_channels, int lut_size) {
     if (n_channels <= 0 || lut_size <= 0) return 0;
-    return sizeof(float) * kGradCopies * 2 * static_cast<size_t>(n_channels) * (lut_size + 2);
+    return sizeof(float) * kMaxGradCopies * 2 * static_cast<size_t>(n_channels) * (lut_size + 2);
 }
 
 namespace {
-int finalize_grad(const float *hist, double *grad, int C, int L, cudaStream_t s) {
+int finalize_grad(const float *hist, double *grad, int C, int L, int n_copies, cudaStream_t s) {
     const int n = C * L;
-    grad_finalize_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(hist, grad, C, L);
+    grad_finalize_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(hist, grad, C, L, n_copies);
     return launched("grad_finalize_kernel");
 }
 }  // namespace
@@ -856,7 +1448,9 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
         return fail(CLAIR_E_ARG, "clair_pair_grad: workspace too small or misaligned (see clair_grad_workspace_bytes)");
     if (n_pairs == 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (cudaError_t e = cudaMemsetAsync(workspace_dev, 0, need, s); e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(workspace)");
+    const int n_copies = g_tuning.grad_copies > 0 ? std::min(g_tuning.grad_copies, kMaxGradCopies) : kPairGradCopies;
+    if (cudaError_t e = cudaMemsetAsync(workspace_dev, 0, need / kMaxGradCopies * n_copies, s); e != cudaSuccess)
+        return fail_cuda(e, "cudaMemsetAsync(workspace)");
     const bool err = std_dev != nullptr && unc_weighting;
     int first = 0;
     while (first < n_pairs) {
@@ -876,6 +1470,7 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
         p.upstream = upstream_dev + static_cast<int64_t>(first) * n_channels;
         p.mean = mean_dev + static_cast<int64_t>(first) * n_channels;
         p.hist = static_cast<float *>(workspace_dev);
+        p.n_copies = n_copies;
         p.n_pairs = count;
         if (int rc = fill_pairs(fn, p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
         const int64_t n_groups = (plane + 32 * pixn - 1) / (32 * pixn);
@@ -890,7 +1485,7 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
             return 0;
         };
         int rc;
-#define GRAD_FLAGS(E, R) (pixn == 2 ? launch(pair_grad_kernel<E, R, 2>) : launch(pair_grad_kernel<E, R, 1>))
+#define GRAD_FLAGS(E, R) (pixn == 2 ? launch(pair_grad2_kernel<E, R>) : launch(pair_grad_kernel<E, R, 1>))
         if (err) rc = relative ? GRAD_FLAGS(true, true) : GRAD_FLAGS(true, false);
         else rc = relative ? GRAD_FLAGS(false, true) : GRAD_FLAGS(false, false);
 #undef GRAD_FLAGS
@@ -898,7 +1493,7 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
         if (int rc2 = launched("pair_grad_kernel")) return rc2;
         first += count;
     }
-    return finalize_grad(static_cast<const float *>(workspace_dev), grad_theta_dev, n_channels, lut_size, s);
+    return finalize_grad(static_cast<const float *>(workspace_dev), grad_theta_dev, n_channels, lut_size, n_copies, s);
 }
 
 extern "C" int clair_icrf_backward_theta(const float *x_dev, const float *grad_y_dev, double *grad_theta_dev,
@@ -915,7 +1510,8 @@ extern "C" int clair_icrf_backward_theta(const float *x_dev, const float *grad_y
     const int64_t slabs = static_cast<int64_t>(n_frames) * n_channels;
     if (slabs > 65535) return fail(CLAIR_E_LIMIT, "clair_icrf_backward_theta: n_frames*n_channels exceeds 65535");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (cudaError_t e = cudaMemsetAsync(workspace_dev, 0, need, s); e != cudaSuccess) return fail_cuda(e, "cudaMemsetAsync(workspace)");
+    if (cudaError_t e = cudaMemsetAsync(workspace_dev, 0, need / kMaxGradCopies * kGradCopies, s); e != cudaSuccess)
+        return fail_cuda(e, "cudaMemsetAsync(workspace)");
     CurveRows rows;
     fill_rows(rows, curve_row_base_host, n_channels, plane);
     dim3 grid(static_cast<unsigned>((plane + 255) / 256), static_cast<unsigned>(slabs));
@@ -929,7 +1525,7 @@ extern "C" int clair_icrf_backward_theta(const float *x_dev, const float *grad_y
         icrf_backward_theta_kernel<<<grid, 256, 0, s>>>(x_dev, grad_y_dev, static_cast<float *>(workspace_dev), plane, n_channels,
                                                         lut_size, rows);
     if (int rc = launched("icrf_backward_theta_kernel")) return rc;
-    return finalize_grad(static_cast<const float *>(workspace_dev), grad_theta_dev, n_channels, lut_size, s);
+    return finalize_grad(static_cast<const float *>(workspace_dev), grad_theta_dev, n_channels, lut_size, kGradCopies, s);
 }
 
 extern "C" int clair_pair_upstream(const double *sums_dev, int n_pairs, int n_channels, double *linloss_dev, double *mean_dev,

@@ -42,7 +42,7 @@ def test_header_symbols_are_exported(native):
 
 def test_argument_validation_without_gpu(native):
     lib = native.load()
-    assert lib.clair_grad_workspace_bytes(3, 256) == 4 * 64 * 2 * 3 * 258
+    assert lib.clair_grad_workspace_bytes(3, 256) == 4 * 1024 * 2 * 3 * 258
     # null buffers are rejected before any CUDA call
     rc = lib.clair_hdr_merge_update(None, None, None, 5, None, 3, 256, 100, None, 1, None, None, None, 1, 1, None, 0, None, None)
     assert rc == -1 and b"null" in lib.clair_last_error()
