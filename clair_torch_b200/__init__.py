@@ -11,8 +11,8 @@ from .common.enums import InterpMode
 from .inference import (compute_hdr_image, compute_video_mean_and_std, linearize_dataset_generator,
                         measure_linearity)
 from .models import ICRFModelBase, ICRFModelDirect, ICRFModelPCA
-from .training import train_icrf, train_icrf_step
+from .training import GraphedTrainStep, train_icrf, train_icrf_step
 
 __version__ = "0.1.0"
 __all__ = ["InterpMode", "ICRFModelBase", "ICRFModelDirect", "ICRFModelPCA", "compute_hdr_image", "linearize_dataset_generator",
-           "measure_linearity", "compute_video_mean_and_std", "train_icrf", "train_icrf_step"]
+           "measure_linearity", "compute_video_mean_and_std", "train_icrf", "train_icrf_step", "GraphedTrainStep"]

@@ -89,8 +89,19 @@ def train_icrf_step(icrf_model: ICRFModelBase, optimizers: list[Optimizer], imag
         return _composed_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs,
                                     use_relative_linearity_loss, use_uncertainty_weighting, alpha, beta, gamma, delta,
                                     lower_valid_threshold, upper_valid_threshold)
+    return _linear_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, use_relative_linearity_loss,
+                              use_uncertainty_weighting, alpha, beta, gamma, delta, lower_valid_threshold,
+                              upper_valid_threshold, row_base, reduce_fn)
+
+
+def _linear_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, use_relative_linearity_loss,
+                       use_uncertainty_weighting, alpha, beta, gamma, delta, lower_valid_threshold, upper_valid_threshold,
+                       row_base=None, reduce_fn=None, table=None):
+    """The LINEAR-mode step on the fused kernels.  `table` overrides where the kernels read the curve from (the
+    captured step reads a static copy, see GraphedTrainStep); the autograd edge is always icrf_model.icrf."""
     curve = icrf_model.icrf                                        # (C, L); a function of the parameters after update_icrf
-    table = curve.detach()
+    if table is None:
+        table = curve.detach()
     connected = curve.requires_grad                                # False on the very first step (SURVEY.md Q5)
     linearity_loss, _, grad = linearity_loss_and_table_grad(
         images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold, upper_valid_threshold,
@@ -111,13 +122,84 @@ def train_icrf_step(icrf_model: ICRFModelBase, optimizers: list[Optimizer], imag
     return loss.detach()
 
 
+def _capturable(optimizers) -> bool:
+    """Optimisers whose step keeps all of its state on the device (torch's `capturable=True` family)."""
+    return bool(optimizers) and all(all(pg.get("capturable", False) for pg in opt.param_groups) for opt in optimizers)
+
+
+def _hyper_key(optimizers):
+    """Every python-side hyper-parameter a captured optimiser step bakes into its kernels (a scheduler changes lr)."""
+    return tuple(tuple((k, v if isinstance(v, (int, float, bool, tuple, type(None))) else id(v))
+                       for k, v in sorted(pg.items()) if k != "params") for opt in optimizers for pg in opt.param_groups)
+
+
+class GraphedTrainStep:
+    """train_icrf_step for ONE device-resident batch, captured once as a CUDA graph and replayed.
+
+    A step is ~35 launches (2 large kernels, 4 small ones, the autograd edge table -> parameters, the optimisers,
+    update_icrf) and the GPU finishes them faster than Python can enqueue them: replaying the captured sequence makes the
+    step GPU-bound.  Requirements: InterpMode.LINEAR, optimisers created with `capturable=True`, the model already
+    connected to its parameters (at least one eager step has run), no cross-rank reduction.
+    The kernels read the curve from a static copy that the captured sequence refreshes after update_icrf, and the
+    autograd edge is rebuilt inside the capture so that its backward runs on the capturing stream.
+    """
+
+    def __init__(self, icrf_model: ICRFModelBase, optimizers: list[Optimizer], images: torch.Tensor,
+                 stds: Optional[torch.Tensor], exposures: torch.Tensor, *, use_relative_linearity_loss=True,
+                 use_uncertainty_weighting=True, alpha=1.0, beta=1.0, gamma=1.0, delta=1.0, lower_valid_threshold=1 / 255,
+                 upper_valid_threshold=254 / 255, exposure_ratio_threshold=0.1):
+        if icrf_model.interpolation_mode is not InterpMode.LINEAR:
+            raise NotImplementedError("GraphedTrainStep: InterpMode.LINEAR only")
+        if not _capturable(optimizers):
+            raise ValueError("GraphedTrainStep needs optimisers created with capturable=True")
+        if not icrf_model.icrf.requires_grad:
+            raise RuntimeError("GraphedTrainStep: run one eager train_icrf_step first (the first step only connects the "
+                               "table to the parameters)")
+        # no reference to the batch is kept: the step replays only while a batch sits at the captured address (make_key)
+        self.key = self.make_key(optimizers, images, stds, exposures)
+        i_idx, j_idx, ratio_pairs = get_valid_exposure_pairs(exposures, exposure_ratio_threshold)
+        self._table = icrf_model.icrf.detach().clone()
+        args = (use_relative_linearity_loss, use_uncertainty_weighting, alpha, beta, gamma, delta, lower_valid_threshold,
+                upper_valid_threshold)
+        self.graph = torch.cuda.CUDAGraph()
+        # let go of the eager autograd edge: its AccumulateGrad nodes are bound to the eager stream, and they would be
+        # reused (and invalidate the capture) for as long as anything keeps them alive
+        icrf_model._icrf = icrf_model.icrf.detach()
+        with torch.cuda.graph(self.graph):
+            icrf_model.update_icrf()                               # same values; a fresh edge on the capturing stream
+            for optimizer in optimizers:
+                optimizer.zero_grad()
+            loss = _linear_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, *args,
+                                      table=self._table)
+            self._table.copy_(icrf_model.icrf.detach())
+            self._loss = loss
+            self._curve = icrf_model.icrf                          # lives in the graph's memory, refreshed by every replay
+        # capture does not execute anything: give the model a valid table again until the first replay
+        self._model = icrf_model
+        icrf_model.update_icrf()
+
+    @staticmethod
+    def make_key(optimizers, images, stds, exposures):
+        exp = tuple(float(t) for t in torch.as_tensor(exposures).reshape(-1).tolist())
+        return (images.data_ptr(), tuple(images.shape), None if stds is None else stds.data_ptr(), exp, _hyper_key(optimizers))
+
+    def __call__(self) -> torch.Tensor:
+        self.graph.replay()
+        self._model._icrf = self._curve
+        return self._loss.clone()
+
+
 def train_icrf(dataloader: DataLoader, batch_size: int, device, icrf_model: ICRFModelBase,
                optimizers: Optional[list[Optimizer]] = None, schedulers: Optional[list] = None,
                use_relative_linearity_loss: bool = True, use_uncertainty_weighting: bool = True, epochs: int = 150,
                patience: int = 300, alpha: float = 1.0, beta: float = 1.0, gamma: float = 1.0, delta: float = 1.0,
                lower_valid_threshold: float = 1 / 255, upper_valid_threshold: float = 254 / 255,
-               exposure_ratio_threshold: float = 0.1, *, verbose: bool = True) -> ICRFModelBase:
-    """Training loop with the reference's signature, defaults, early stopping and scheduler handling."""
+               exposure_ratio_threshold: float = 0.1, *, verbose: bool = True, use_cuda_graph: bool = True) -> ICRFModelBase:
+    """Training loop with the reference's signature, defaults, early stopping and scheduler handling.
+
+    `use_cuda_graph`: a batch that stays at the same device address from one epoch to the next (a device-resident
+    dataset) with capturable optimisers (the default ones are) is stepped through GraphedTrainStep from its third visit
+    on; anything else takes the eager step."""
     if not isinstance(dataloader, DataLoader):
         raise TypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
     if not isinstance(icrf_model, ICRFModelBase):
@@ -129,7 +211,8 @@ def train_icrf(dataloader: DataLoader, batch_size: int, device, icrf_model: ICRF
     if batch_size == 1:
         raise ValueError("Batch size must be larger than 1.")
     if optimizers is None:
-        optimizers = [torch.optim.Adam(icrf_model.channel_params(c), lr=1e-3, amsgrad=False) for c in range(channels)]
+        optimizers = [torch.optim.Adam(icrf_model.channel_params(c), lr=1e-3, amsgrad=False, capturable=True)
+                      for c in range(channels)]
     previous_lrs = [pg["lr"] for opt in optimizers for pg in opt.param_groups]
     if schedulers is None:
         schedulers = [None] * len(optimizers)
@@ -139,6 +222,11 @@ def train_icrf(dataloader: DataLoader, batch_size: int, device, icrf_model: ICRF
     epochs_without_improvement = [0] * channels
     icrf_model.train()
     icrf_model.plot_icrf()
+    step_kw = dict(use_relative_linearity_loss=use_relative_linearity_loss, use_uncertainty_weighting=use_uncertainty_weighting,
+                   alpha=alpha, beta=beta, gamma=gamma, delta=delta, lower_valid_threshold=lower_valid_threshold,
+                   upper_valid_threshold=upper_valid_threshold, exposure_ratio_threshold=exposure_ratio_threshold)
+    graphable = (use_cuda_graph and icrf_model.interpolation_mode is InterpMode.LINEAR and _capturable(optimizers))
+    seen, graphs = {}, {}                                          # batch key -> eager visits / captured step
     for epoch in range(epochs):
         running_loss = torch.zeros(channels if len(optimizers) > 1 else (), dtype=torch.float64, device=dev)
         for _, val_batch, std_batch, meta_batch in dataloader:
@@ -147,12 +235,16 @@ def train_icrf(dataloader: DataLoader, batch_size: int, device, icrf_model: ICRF
                 if verbose:
                     print("Skipped batch due to single image.")
                 continue
-            running_loss += train_icrf_step(
-                icrf_model, optimizers, images, stds, meta_batch["exposure_time"],
-                use_relative_linearity_loss=use_relative_linearity_loss,
-                use_uncertainty_weighting=use_uncertainty_weighting, alpha=alpha, beta=beta, gamma=gamma, delta=delta,
-                lower_valid_threshold=lower_valid_threshold, upper_valid_threshold=upper_valid_threshold,
-                exposure_ratio_threshold=exposure_ratio_threshold)
+            exposures = meta_batch["exposure_time"]
+            if graphable:
+                key = GraphedTrainStep.make_key(optimizers, images, stds, exposures)
+                if key not in graphs and seen.get(key, 0) >= 2 and icrf_model.icrf.requires_grad and len(graphs) < 8:
+                    graphs[key] = GraphedTrainStep(icrf_model, optimizers, images, stds, exposures, **step_kw)
+                if key in graphs:
+                    running_loss += graphs[key]()
+                    continue
+                seen[key] = seen.get(key, 0) + 1
+            running_loss += train_icrf_step(icrf_model, optimizers, images, stds, exposures, **step_kw)
         avg_loss = (running_loss / len(dataloader)).cpu().numpy().reshape(-1)
         if verbose:
             print(f"Epoch {epoch + 1} Loss: {avg_loss}")

@@ -425,6 +425,64 @@ def test_train_icrf_step_updates_like_reference(ct):
     assert loss0.shape == (3,)
 
 
+@pytest.mark.parametrize("unc", [False, True])
+def test_graphed_train_step_equals_eager_steps(ct, unc):
+    """GraphedTrainStep (one captured CUDA graph, replayed) walks the same trajectory as eager train_icrf_step calls with
+    the same capturable optimisers: losses and tables agree step by step (the float64 atomics of the statistics kernel
+    make the last bits run-to-run noise, hence a tolerance instead of equality)."""
+    val, std, t = ct.synthetic.make_stack(6, 3, 96, 128, bits=8, seed=77, device=DEV)
+    exposure = torch.from_numpy(t)
+    kw = dict(use_relative_linearity_loss=True, use_uncertainty_weighting=unc, alpha=10.0, beta=1.0, gamma=1.0, delta=1.0,
+              exposure_ratio_threshold=0.2)
+
+    def fresh():
+        model = ct.ICRFModelDirect(256, 3, initial_power=2.5).to(DEV)
+        opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3, capturable=True) for c in range(3)]
+        return model, opts
+
+    m_e, o_e = fresh()
+    eager = [ct.train_icrf_step(m_e, o_e, val, std, exposure, **kw).cpu().numpy() for _ in range(7)]
+    m_g, o_g = fresh()
+    losses = [ct.train_icrf_step(m_g, o_g, val, std, exposure, **kw).cpu().numpy() for _ in range(2)]
+    before = ct._native.launch_count()
+    step = ct.GraphedTrainStep(m_g, o_g, val, std, exposure, **kw)
+    assert ct._native.launch_count() - before >= 4          # the fused kernels were captured, not executed eagerly
+    losses += [step().cpu().numpy() for _ in range(5)]
+    for a, b in zip(eager, losses):
+        assert max_rel(b, a) < 1e-6
+    assert max_abs_over_max(m_g.icrf.detach().cpu().numpy(), m_e.icrf.detach().cpu().numpy()) < 1e-6
+    assert m_g.icrf.requires_grad
+    # a plain (host-stepped) Adam cannot be captured
+    plain = [torch.optim.Adam(m_g.channel_params(c), lr=1e-3) for c in range(3)]
+    with pytest.raises(ValueError):
+        ct.GraphedTrainStep(m_g, plain, val, std, exposure, **kw)
+
+
+def test_train_icrf_replays_a_graph_for_device_resident_batches(ct):
+    """train_icrf with its default (capturable) optimisers and a dataset that lives on the device: from the third epoch
+    on the step is a graph replay; the result matches the eager loop."""
+    from torch.utils.data import DataLoader
+    from clair_torch_b200.datasets import ExposureStackDataset, custom_collate
+    val, std, t = ct.synthetic.make_stack(6, 3, 64, 96, bits=8, seed=78, device=DEV)
+
+    class OneBatch(torch.utils.data.Dataset):
+        def __len__(self):
+            return 1
+
+        def __getitem__(self, i):
+            return torch.arange(6), val, std, {"exposure_time": torch.from_numpy(t)}
+
+    loader = DataLoader(OneBatch(), batch_size=None, shuffle=False)
+    out = {}
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        model = ct.ICRFModelDirect(256, 3, initial_power=2.5).to(DEV)
+        ct.train_icrf(loader, 6, DEV, model, use_uncertainty_weighting=False, epochs=12, verbose=False, use_cuda_graph=graphed)
+        out[graphed] = model.icrf.detach().cpu().numpy()
+    assert max_abs_over_max(out[True], out[False]) < 1e-6
+    assert np.abs(out[True] - np.linspace(0, 1, 256) ** 2.5).max() > 1e-4      # it did train
+
+
 @pytest.mark.parametrize("staged", [True, False])
 def test_hdr_merge_pinned_host_stack(ct, staged):
     """Pinned host batches are either streamed band by band by the copy engine while the kernel merges the previous band
