@@ -57,6 +57,15 @@ def train_icrf_step_data_parallel(icrf_model, optimizers, band_images, band_stds
                            reduce_fn=lambda t: all_reduce_sum_(t, group), **step_kwargs)
 
 
+def graphed_train_step_data_parallel(icrf_model, optimizers, band_images, band_stds, exposures, row_base, group=None,
+                                     **step_kwargs):
+    """train_icrf_step_data_parallel captured as one CUDA graph (kernels, both all-reduces, optimisers); call the returned
+    object once per step.  Needs capturable optimisers and one eager step before (see GraphedTrainStep)."""
+    from .training.icrf_training import GraphedTrainStep
+    return GraphedTrainStep(icrf_model, optimizers, band_images, band_stds, exposures, row_base=row_base,
+                            reduce_fn=lambda t: all_reduce_sum_(t, group), **step_kwargs)
+
+
 def measure_linearity_band(band_images, band_stds, exposures, table: Optional[torch.Tensor], row_base,
                            use_uncertainty_weighting=True, use_relative_linearity_loss=True, group=None):
     """measure_linearity on a row band with the spatial sums all-reduced: every rank returns the full-image result."""

@@ -139,7 +139,8 @@ class GraphedTrainStep:
     A step is ~35 launches (2 large kernels, 4 small ones, the autograd edge table -> parameters, the optimisers,
     update_icrf) and the GPU finishes them faster than Python can enqueue them: replaying the captured sequence makes the
     step GPU-bound.  Requirements: InterpMode.LINEAR, optimisers created with `capturable=True`, the model already
-    connected to its parameters (at least one eager step has run), no cross-rank reduction.
+    connected to its parameters (at least one eager step has run).  `row_base` / `reduce_fn` are the
+    row-band arguments of train_icrf_step: an NCCL all-reduce passed as `reduce_fn` is captured with the kernels.
     The kernels read the curve from a static copy that the captured sequence refreshes after update_icrf, and the
     autograd edge is rebuilt inside the capture so that its backward runs on the capturing stream.
     """
@@ -147,7 +148,7 @@ class GraphedTrainStep:
     def __init__(self, icrf_model: ICRFModelBase, optimizers: list[Optimizer], images: torch.Tensor,
                  stds: Optional[torch.Tensor], exposures: torch.Tensor, *, use_relative_linearity_loss=True,
                  use_uncertainty_weighting=True, alpha=1.0, beta=1.0, gamma=1.0, delta=1.0, lower_valid_threshold=1 / 255,
-                 upper_valid_threshold=254 / 255, exposure_ratio_threshold=0.1):
+                 upper_valid_threshold=254 / 255, exposure_ratio_threshold=0.1, row_base=None, reduce_fn=None):
         if icrf_model.interpolation_mode is not InterpMode.LINEAR:
             raise NotImplementedError("GraphedTrainStep: InterpMode.LINEAR only")
         if not _capturable(optimizers):
@@ -170,7 +171,7 @@ class GraphedTrainStep:
             for optimizer in optimizers:
                 optimizer.zero_grad()
             loss = _linear_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, *args,
-                                      table=self._table)
+                                      row_base=row_base, reduce_fn=reduce_fn, table=self._table)
             self._table.copy_(icrf_model.icrf.detach())
             self._loss = loss
             self._curve = icrf_model.icrf                          # lives in the graph's memory, refreshed by every replay
