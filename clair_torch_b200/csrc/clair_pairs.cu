@@ -834,13 +834,16 @@ __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
 //     P = 1 went from 459 to under 200 warp instructions.
 // =====================================================================================================
 
-// One predicated vector reduction per element: both taps in one L2 operation.  The kernel is bound by exactly these:
-// red.global.add.v2.f32 sustains 176 G operations/s on random table entries and ~110 G/s on 16 hot ones
-// (scratch/smem_atomics.cu).  A block-private table in shared memory does not help on sm_100a — there is no native
-// floating-point shared atomic, and the compiler's ATOMS.CAST.SPIN loop (or a 64-bit CAS loop) collapses on the hot
-// entries that real exposure stacks produce (dark frames put a warp's 64 pixels on a few dozen entries): measured
-// 0.52 ms (fp32 atomicAdd x2) and 3.1 ms (CAS.64) against 0.46 ms for this form on the c2 stack.  Integer
-// fixed-point shared atomics are native and fast but cannot cover the 1/es range of the relative loss (5 decades).
+// One predicated vector reduction per element: both taps in one L2 operation into one of kPairGradCopies replicated
+// tables.  red.global.add.v2.f32 sustains 176 G operations/s on random table entries and ~110 G/s on 16 hot ones
+// (scratch/smem_atomics.cu); hot entries are what real exposure stacks produce (a dark frame puts a warp's 64 pixels on
+// a few dozen entries), hence the 1024 copies.  Block-private tables in shared memory were tried three ways and all
+// lost on the c2 / c5 stacks (0.35 / 2.35 ms in this form):
+//   * fp32 atomicAdd x2 — sm_100a has no native floating-point shared atomic, it is an ATOMS.CAST.SPIN loop: 0.52 / 3.19 ms;
+//   * one 64-bit CAS loop per element: collapses on hot entries, 3.1 / 8.3 ms;
+//   * 64-bit fixed point on native integer shared atomics (returning add on the low word, carry into the high word,
+//     pipelined one frame deep; > 790 G/s in isolation): 0.44 / 3.18 ms — the 12 KB table costs a resident block and the
+//     kernel is then bound by latency at 12-15 warps per SM, not by the reductions.
 __device__ __forceinline__ void red_add_v2_if(float *addr, float a, float b, float g) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %3, 0f00000000;\n\t@p red.global.add.v2.f32 [%0], {%1, %2};\n\t}"
                  ::"l"(addr), "f"(a), "f"(b), "f"(g));

@@ -28,6 +28,14 @@ __global__ void __launch_bounds__(128) k(float *out, int iters, int spread) {
             atomicAdd(&h[2 * bin], a);
         } else if (MODE == 4) {     // u64 atomicAdd (CAST.SPIN.64)
             atomicAdd(reinterpret_cast<u64 *>(&h[2 * bin]), 0x0000000100000001ull);
+        } else if (MODE == 6) {     // 64-bit fixed point: returning 32-bit add on the low word, carry / borrow into the high word
+            unsigned *w = reinterpret_cast<unsigned *>(h);
+            const float v = (rng(s) & 1) ? -a * 1000.5f : a * 777.25f;
+            const long long x = static_cast<long long>(__float2ll_rn(v * 1048576.0f));
+            const unsigned lo = static_cast<unsigned>(x);
+            const unsigned old = atomicAdd(&w[2 * bin], lo);
+            const int hi = static_cast<int>(x >> 32) + ((old + lo < old) ? 1 : 0);
+            if (hi != 0) atomicAdd(reinterpret_cast<int *>(&w[2 * bin + 1]), hi);
         } else if (MODE == 5) {     // global red v2
             asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(out + 2 * ((bin + blockIdx.x % 64 * BINS))), "f"(a), "f"(b));
         }
@@ -55,6 +63,7 @@ int main() {
         run<3>("1x atomicAdd(float) smem", out, spread);
         run<4>("atomicAdd(u64) smem", out, spread);
         run<5>("red.global.add.v2.f32", out, spread);
+        run<6>("fixed-point lo/hi int smem", out, spread);
     }
     return 0;
 }
