@@ -313,7 +313,7 @@ def dp_training_metrics(dev, rank, world):
     exposures = torch.tensor([0.01, 0.02], dtype=torch.float64)
     rb = cd.band_row_base(CHANNELS, height, width, r0)
     model = ct.ICRFModelDirect(256, CHANNELS, ct.InterpMode.LINEAR, 2.5).to(dev)
-    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3, capturable=True) for c in range(CHANNELS)]
+    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3, capturable=True, fused=True) for c in range(CHANNELS)]
     kw = dict(use_relative_linearity_loss=True, use_uncertainty_weighting=False, alpha=10.0, beta=1.0, gamma=1.0, delta=1.0,
               exposure_ratio_threshold=0.25)
     step = lambda: cd.train_icrf_step_data_parallel(model, opts, val, std, exposures, rb, **kw)
@@ -375,8 +375,8 @@ def secondary_metrics(dev):
     val, std, t = ct.synthetic.make_stack(10, CHANNELS, HEIGHT, WIDTH, bits=8, seed=2345, device=dev)
     exposures = torch.from_numpy(t)
     model = ct.ICRFModelDirect(256, CHANNELS, ct.InterpMode.LINEAR, 2.5).to(dev)
-    # capturable Adam = train_icrf's default optimisers: the step is replayed as one CUDA graph (GraphedTrainStep)
-    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3, capturable=True) for c in range(CHANNELS)]
+    # capturable, fused Adam = train_icrf's default optimisers: the step is replayed as one CUDA graph (GraphedTrainStep)
+    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3, capturable=True, fused=True) for c in range(CHANNELS)]
     kw = dict(use_relative_linearity_loss=True, use_uncertainty_weighting=False, alpha=10.0, beta=1.0, gamma=1.0,
               delta=1.0, exposure_ratio_threshold=0.25)
     ms_eager = timed(lambda: ct.train_icrf_step(model, opts, val, std, exposures, **kw), 3, 20)

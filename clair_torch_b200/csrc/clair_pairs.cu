@@ -1149,21 +1149,33 @@ __global__ void __launch_bounds__(256) icrf_lookup_backward_kernel(const float *
     atomicAdd(copy + icrf_lookup_index(__ldcs(x + o), static_cast<float>(L - 1)), g);
 }
 
-// grad[u][k] += sum over copies of A[u][k] + B[u][k+1], in float64; one warp per table entry
+// grad[u][k] += sum over copies of A[u][k] + B[u][k+1], in float64.  Lanes own consecutive table entries (coalesced
+// reads of a copy's row), the 8 warps of a block own interleaved copies of the block's chunk of 128, and one float64
+// atomic per (entry, chunk) folds the chunks: 26 -> 5 us at 1024 copies against one warp per entry striding over the copies.
+constexpr int kFinalizeChunk = 128;
 __global__ void __launch_bounds__(256) grad_finalize_kernel(const float *__restrict__ hist, double *grad, int C, int L, int n_copies) {
-    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (i >= C * L) return;
-    const int u = i / L, k = i - u * L;
+    __shared__ double s_part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;                     // table entry
     const int lp = L + 2;
+    const bool live = i < C * L;
+    const int u = live ? i / L : 0, k = live ? i - u * L : 0;
+    const int first = blockIdx.y * kFinalizeChunk, last = min(first + kFinalizeChunk, n_copies);
     double acc = 0.0;
-    for (int r = lane; r < n_copies; r += 32) {
-        const float *copy = hist + static_cast<int64_t>(r) * (2 * C * lp);
-        acc += static_cast<double>(copy[u * lp + k]) + static_cast<double>(copy[C * lp + u * lp + k + 1]);
+    if (live) {
+        const int64_t stride = static_cast<int64_t>(2) * C * lp;
+        const float *a = hist + u * lp + k, *b = hist + C * lp + u * lp + k + 1;
+        for (int r = first + warp; r < last; r += 8)
+            acc += static_cast<double>(a[r * stride]) + static_cast<double>(b[r * stride]);
     }
+    s_part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && live) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) grad[i] += acc;
+        for (int w = 1; w < 8; ++w) acc += s_part[w][lane];
+        if (gridDim.y == 1) grad[i] += acc;
+        else atomicAdd(grad + i, acc);
+    }
 }
 
 // =====================================================================================================
@@ -1428,7 +1440,8 @@ extern "C" size_t clair_grad_workspace_bytes(int n_channels, int lut_size) {
 namespace {
 int finalize_grad(const float *hist, double *grad, int C, int L, int n_copies, cudaStream_t s) {
     const int n = C * L;
-    grad_finalize_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(hist, grad, C, L, n_copies);
+    const dim3 grid(static_cast<unsigned>((n + 31) / 32), static_cast<unsigned>((n_copies + kFinalizeChunk - 1) / kFinalizeChunk));
+    grad_finalize_kernel<<<grid, 256, 0, s>>>(hist, grad, C, L, n_copies);
     return launched("grad_finalize_kernel");
 }
 }  // namespace

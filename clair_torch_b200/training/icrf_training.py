@@ -212,7 +212,8 @@ def train_icrf(dataloader: DataLoader, batch_size: int, device, icrf_model: ICRF
     if batch_size == 1:
         raise ValueError("Batch size must be larger than 1.")
     if optimizers is None:
-        optimizers = [torch.optim.Adam(icrf_model.channel_params(c), lr=1e-3, amsgrad=False, capturable=True)
+        # the reference's per-channel Adam(lr=1e-3); fused = one kernel per optimiser step, capturable = state on the device
+        optimizers = [torch.optim.Adam(icrf_model.channel_params(c), lr=1e-3, amsgrad=False, capturable=True, fused=True)
                       for c in range(channels)]
     previous_lrs = [pg["lr"] for opt in optimizers for pg in opt.param_groups]
     if schedulers is None:

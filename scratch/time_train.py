@@ -23,7 +23,7 @@ def timed(fn, reps=50):
 
 for unc, thr in ((False, 0.25), (True, 0.1)):
     model = ct.ICRFModelDirect(256, 3, ct.InterpMode.LINEAR, 2.5).to(dev)
-    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3, capturable=True) for c in range(3)]
+    opts = [torch.optim.Adam(model.channel_params(c), lr=1e-3, capturable=True, fused=True) for c in range(3)]
     kw = dict(use_relative_linearity_loss=True, use_uncertainty_weighting=unc, alpha=10.0, beta=1.0, gamma=1.0, delta=1.0,
               exposure_ratio_threshold=thr)
     eager = timed(lambda: ct.train_icrf_step(model, opts, val, std, exposures, **kw))
