@@ -170,23 +170,30 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
-def native_ingest_metrics(dev, lib, theta, t_host):
-    """c1 again, but handing over what the camera produced: uint8 codes + MissingStdMode.MULTIPLIER(0.05) evaluated
-    in the kernel (reported separately from the fp32-boundary headline)."""
+def native_ingest_metrics(dev, lib, theta, t_host, cfg=None, reps=400, e2e_reps=20, camera=True):
+    """The workload again (c1 by default), but handing over what the camera produced: uint8 / uint16 codes +
+    MissingStdMode.MULTIPLIER(0.05) evaluated in the kernel (reported separately from the
+    fp32-boundary headline)."""
     import ctypes
     import torch
     import clair_torch_b200 as ct
     from clair_torch_b200.datasets import StdSpec
+    cfg = cfg or WORKLOADS["c1"]
+    N_FRAMES, CHANNELS, HEIGHT, WIDTH, BITS = cfg["n"], cfg["c"], cfg["h"], cfg["w"], cfg["bits"]     # shadow the c1 globals
+    maxval = float(2 ** BITS - 1)
+    code_dtype, code_kind, code_bytes = (torch.uint8, 1, 1) if BITS == 8 else (torch.uint16, 2, 2)
+    n_sets = 4 if BITS == 8 else 2
     stream = torch.cuda.current_stream(dev)
     sets = []
-    for k in range(4):
+    for k in range(n_sets):
         val, _, _ = ct.synthetic.make_stack(N_FRAMES, CHANNELS, HEIGHT, WIDTH, bits=BITS, seed=4321 + k, device=dev)
-        sets.append(torch.round(val * 255.0).to(torch.uint8))
+        sets.append(torch.round(val * maxval).to(torch.int32).to(code_dtype))
+        del val
     radiance = torch.empty((CHANNELS, HEIGHT, WIDTH), dtype=torch.float32, device=dev)
     sigma = torch.empty_like(radiance)
 
     def launch(k):
-        rc = lib.clair_hdr_merge_codes(sets[k % 4].data_ptr(), 1, 255.0, None, 2, 0.05, t_host.ctypes.data_as(ctypes.c_void_p),
+        rc = lib.clair_hdr_merge_codes(sets[k % n_sets].data_ptr(), code_kind, maxval, None, 2, 0.05, t_host.ctypes.data_as(ctypes.c_void_p),
                                        N_FRAMES, theta.data_ptr(), CHANNELS, LUT, HEIGHT * WIDTH, None, 1, None, None, None, 1, 1,
                                        radiance.data_ptr(), 0, sigma.data_ptr(), stream.cuda_stream)
         ct._native.check(rc, "clair_hdr_merge_codes")
@@ -195,7 +202,6 @@ def native_ingest_metrics(dev, lib, theta, t_host):
         launch(k)
     torch.cuda.synchronize(dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 400
     a.record(stream)
     for k in range(reps):
         launch(k)
@@ -226,10 +232,19 @@ def native_ingest_metrics(dev, lib, theta, t_host):
         e2e()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    for _ in range(20):
+    for _ in range(e2e_reps):
         e2e()
     torch.cuda.synchronize(dev)
-    e2e_ms = (time.perf_counter() - t0) / 20 * 1e3
+    e2e_ms = (time.perf_counter() - t0) / e2e_reps * 1e3
+    algo = N_FRAMES * CHANNELS * HEIGHT * WIDTH * code_bytes + CHANNELS * HEIGHT * WIDTH * 8
+    out = {"config": f"{cfg['label'].split(':')[0]} as uint{8 * code_bytes} codes, CastTo+Normalize({int(maxval)}) and std = 0.05*value fused "
+                     "into the load",
+           "kernel_ms": ms, "mpixel_frames_per_s": units / (ms * 1e-3), "dram_bytes_per_pixel_frame": algo / (N_FRAMES * HEIGHT * WIDTH),
+           "hbm_frac": algo / (ms * 1e-3) / 1e9 / peaks()[0],
+           "e2e_ms": e2e_ms, "e2e_mpixel_frames_per_s": units / (e2e_ms * 1e-3), "e2e_h2d_bytes": codes_h.numel() * code_bytes,
+           "e2e_d2h_bytes": 2 * rad_h.numel() * 4}
+    if not camera:
+        return out
     # the same stack as the camera delivers it: (N, H, W, 3) BGR (cv2.imread layout), CvToTorch fused into the load as well
     from clair_torch_b200 import kernels
     cam = [torch.stack([c8[:, 2], c8[:, 1], c8[:, 0]], dim=-1).contiguous() for c8 in sets[:2]]
@@ -271,15 +286,9 @@ def native_ingest_metrics(dev, lib, theta, t_host):
         e2e_cam()
     torch.cuda.synchronize(dev)
     e2e_cam_ms = (time.perf_counter() - t0) / 20 * 1e3
-    algo = N_FRAMES * CHANNELS * HEIGHT * WIDTH * 1 + CHANNELS * HEIGHT * WIDTH * 8
-    return {"config": "c1 as uint8 codes, CastTo+Normalize(255) and std = 0.05*value fused into the load",
-            "camera_layout": {"config": "same codes as (N, H, W, 3) BGR camera buffers, CvToTorch fused into the load too",
-                              "kernel_ms": ms_cam, "e2e_ms": e2e_cam_ms,
-                              "e2e_mpixel_frames_per_s": units / (e2e_cam_ms * 1e-3)},
-            "kernel_ms": ms, "mpixel_frames_per_s": units / (ms * 1e-3), "dram_bytes_per_pixel_frame": algo / (N_FRAMES * HEIGHT * WIDTH),
-            "hbm_frac": algo / (ms * 1e-3) / 1e9 / peaks()[0],
-            "e2e_ms": e2e_ms, "e2e_mpixel_frames_per_s": units / (e2e_ms * 1e-3), "e2e_h2d_bytes": codes_h.numel(),
-            "e2e_d2h_bytes": 2 * rad_h.numel() * 4}
+    out["camera_layout"] = {"config": "same codes as (N, H, W, 3) BGR camera buffers, CvToTorch fused into the load too",
+                            "kernel_ms": ms_cam, "e2e_ms": e2e_cam_ms, "e2e_mpixel_frames_per_s": units / (e2e_cam_ms * 1e-3)}
+    return out
 
 
 def bind_to_gpu_numa_node(index):
@@ -653,6 +662,11 @@ def main():
             c1 = res if args.workload == "c1" else r2
             extra.update(secondary_metrics(dev))
             extra["native_ingest_c1"] = native_ingest_metrics(dev, lib, c1["theta"], c1["t_host"])
+            torch.cuda.empty_cache()
+            c4 = res if args.workload == "c4" else r2
+            extra["native_ingest_c4"] = native_ingest_metrics(dev, lib, c4["theta"], c4["t_host"], WORKLOADS["c4"], reps=30,
+                                                              e2e_reps=5, camera=False)
+            torch.cuda.empty_cache()
             extra["dp_train_c5"] = dp_training_metrics(dev, 0, 1)
         res["e2e"]["host_cpus_bound"] = local_cpus
         line = {

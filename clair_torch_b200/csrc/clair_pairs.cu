@@ -1310,7 +1310,7 @@ void pick_stats_shape(int count, int n_frames, int va, bool err, bool full, int 
     warps = 8; slots = kMaxSlots;
     for (int s = 1; s <= kMaxSlots; ++s) {
         if (s == 3) continue;                         // slot counts instantiated: 1, 2, 4
-        for (int w = 2; w <= 16; ++w) {
+        for (int w = packed ? 1 : 2; w <= 16; ++w) {    // a single exposure pair (N = 2, one pair) runs as one-warp blocks
             if (w * s < count) continue;
             if (packed && 2 * w < n_frames) continue;
             const int trips = (items + 32 * w - 1) / (32 * w);
