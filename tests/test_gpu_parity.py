@@ -483,6 +483,42 @@ def test_train_icrf_replays_a_graph_for_device_resident_batches(ct):
     assert np.abs(out[True] - np.linspace(0, 1, 256) ** 2.5).max() > 1e-4      # it did train
 
 
+def test_train_icrf_recaptures_when_a_scheduler_changes_the_learning_rate(ct):
+    """A captured optimiser step bakes the learning rate into its kernels: when a scheduler changes it, train_icrf must
+    capture a new step (the batch key includes the optimisers' hyper-parameters) — same trajectory as the eager loop."""
+    from torch.utils.data import DataLoader
+    val, std, t = ct.synthetic.make_stack(5, 3, 64, 96, bits=8, seed=79, device=DEV)
+
+    class OneBatch(torch.utils.data.Dataset):
+        def __len__(self):
+            return 1
+
+        def __getitem__(self, i):
+            return torch.arange(5), val, std, {"exposure_time": torch.from_numpy(t)}
+
+    class Halve:                       # ReduceLROnPlateau's calling convention: step(metric)
+        def __init__(self, opt):
+            self.opt, self.calls = opt, 0
+
+        def step(self, metric):
+            self.calls += 1
+            if self.calls % 4 == 0:
+                for pg in self.opt.param_groups:
+                    pg["lr"] = pg["lr"] * 0.5
+
+    loader = DataLoader(OneBatch(), batch_size=None, shuffle=False)
+    out = {}
+    for graphed in (False, True):
+        model = ct.ICRFModelDirect(256, 3, initial_power=2.5).to(DEV)
+        opts = [torch.optim.Adam(model.channel_params(c), lr=2e-3, capturable=True) for c in range(3)]
+        scheds = [Halve(o) for o in opts]
+        ct.train_icrf(loader, 5, DEV, model, opts, scheds, use_uncertainty_weighting=False, epochs=14, verbose=False,
+                      use_cuda_graph=graphed)
+        out[graphed] = model.icrf.detach().cpu().numpy()
+        assert opts[0].param_groups[0]["lr"] == pytest.approx(2e-3 / 8)
+    assert max_abs_over_max(out[True], out[False]) < 1e-6
+
+
 @pytest.mark.parametrize("staged", [True, False])
 def test_hdr_merge_pinned_host_stack(ct, staged):
     """Pinned host batches are either streamed band by band by the copy engine while the kernel merges the previous band
