@@ -444,7 +444,24 @@ def secondary_metrics(dev):
     out["linearize_c4_frames"]["e2e_ms_per_frame"] = e2e_lin
     out["linearize_c4_frames"]["e2e_mpixel_per_s"] = 24.0 / (e2e_lin * 1e-3)
     out["linearize_c4_frames"]["e2e_note"] = "pinned host frame (val+std, 576 MB) in, pinned host lin+sigma (576 MB) out; clair_linearize_staged: H2D copy, kernel and D2H copy of successive bands overlapped on three streams"
-    del val, std, one_val, one_std, rad, hv, hs
+    # the same frames handed over as the camera's uint16 codes: CastTo + Normalize + std = 0.05*value in the kernel's load
+    from clair_torch_b200.datasets import StdSpec
+    hc = torch.round(one_val * 65535.0).to(torch.int32).to(torch.uint16).cpu().pin_memory()
+    ds_c = ExposureStackDataset(list(hc), StdSpec("multiplier", 0.05), list(t[:3]))
+    code_collate = lambda b: (torch.tensor([b[0][0]]), b[0][1].unsqueeze(0), b[0][2],
+                              {"exposure_time": torch.tensor([b[0][3]["exposure_time"]], dtype=torch.float64)})
+    code_loader = DataLoader(ds_c, batch_size=1, shuffle=False, collate_fn=code_collate)
+    for _ in ct.linearize_dataset_generator(code_loader, dev, lin_model):
+        pass
+    t0 = time.perf_counter()
+    for _ in range(3):
+        for _ in ct.linearize_dataset_generator(code_loader, dev, lin_model):
+            pass
+    e2e_codes = (time.perf_counter() - t0) / 9 * 1e3
+    out["linearize_c4_frames"]["e2e_codes_ms_per_frame"] = e2e_codes
+    out["linearize_c4_frames"]["e2e_codes_note"] = ("pinned host uint16 codes (144 MB) in, pinned host lin+sigma (576 MB) out, both "
+                                                    "over PCIe from inside clair_linearize_codes")
+    del val, std, one_val, one_std, rad, hv, hs, hc
     torch.cuda.empty_cache()
     # 8(f) rows at c1 size: dark-field mix pre-pass, flat-field correction, streaming frame statistics
     val, std, t = ct.synthetic.make_stack(N_FRAMES, CHANNELS, HEIGHT, WIDTH, bits=8, seed=99, device=dev)

@@ -55,6 +55,9 @@ _PROTOTYPES = {
                                              _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "clair_linearize": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                    _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "clair_linearize_codes": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_float, _c.c_void_p, _c.c_int, _c.c_float, _c.c_void_p,
+                                         _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_void_p,
+                                         _c.c_void_p]),
     "clair_linearize_staged": (_c.c_int, [_c.c_void_p] * 9 + [_c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p,
                                           _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "clair_hdr_merge_update": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int,

@@ -78,6 +78,73 @@ __global__ void __launch_bounds__(kBlock) icrf_forward_kernel(const ForwardParam
     }
 }
 
+// Linearisation straight from the camera's integer codes (SURVEY.md 8(f) rank 2 for the lineariser): the reference's CPU
+// transforms CastTo + Normalize (x = fl32(code) / fl32(code_max), an IEEE division: a 256-entry table of quotients for
+// 8-bit codes, __fdiv_rn for 16-bit ones) and the missing-std synthesis of MultiFileMapDataset (std = x * m or a
+// constant, clair_torch/datasets/base.py:128-133) happen in the load, so a frame crosses PCIe / HBM as 1 or 2 bytes per
+// sample instead of 8.  Four codes per thread; results are bit-identical to feeding the CPU-transformed fp32 image.
+struct LinearizeCodesParams {
+    const void *codes;
+    const float *std;         // kStdTensor only
+    const float *theta;
+    float *lin, *sigma;
+    int64_t plane;            // H*W, a multiple of 4
+    int n_channels, lut;
+    int std_mode;             // kStdNone / kStdTensor / kStdMultiplier / kStdConstant
+    float std_value, code_max;
+    CurveRows rows;
+};
+
+template <int BYTES>
+__global__ void __launch_bounds__(kBlock) linearize_codes_kernel(const LinearizeCodesParams p) {
+    extern __shared__ float2 s_tab[];
+    const int C = p.n_channels, L = p.lut;
+    float *s_x = reinterpret_cast<float *>(s_tab + C * L);           // 8-bit: code -> fl32(code) / code_max
+    stage_curve_pairs(s_tab, p.theta, C, L);
+    if constexpr (BYTES == 1) {
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
+    }
+    __syncthreads();
+    const int64_t pix = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * 4;
+    if (pix >= p.plane) return;
+    const int slab = blockIdx.y;                    // n * C + c
+    const int c = slab % C;
+    const int64_t off = static_cast<int64_t>(slab) * p.plane + pix;
+    const float lm1 = static_cast<float>(L - 1);
+    Pack<4> xv;
+    if constexpr (BYTES == 1) {
+        const uint32_t w = __ldcs(reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(p.codes) + off));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xv.v[k] = s_x[(w >> (8 * k)) & 0xffu];
+    } else {
+        const uint2 w = __ldcs(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(p.codes) + off));
+        xv.v[0] = __fdiv_rn(static_cast<float>(w.x & 0xffffu), p.code_max);
+        xv.v[1] = __fdiv_rn(static_cast<float>(w.x >> 16), p.code_max);
+        xv.v[2] = __fdiv_rn(static_cast<float>(w.y & 0xffffu), p.code_max);
+        xv.v[3] = __fdiv_rn(static_cast<float>(w.y >> 16), p.code_max);
+    }
+    Pack<4> sv;
+    if (p.std_mode == kStdTensor) {
+        sv = load_stream<4>(p.std + off);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            sv.v[k] = (p.std_mode == kStdMultiplier) ? __fmul_rn(xv.v[k], p.std_value) : (p.std_mode == kStdConstant ? p.std_value : 0.0f);
+    }
+    Pack<4> yv, gv;
+    int u = static_cast<int>((pix + p.rows.base(c)) % C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const IcrfTap t = icrf_linear(xv.v[k], s_tab + u * L, lm1);
+        yv.v[k] = t.f;
+        const float g = (p.std_mode != kStdNone) ? __fmul_rn(t.fp, sv.v[k]) : 0.0f;     // sqrt((f' * s)^2), linearization.py:106,132
+        gv.v[k] = sqrtf(__fmul_rn(g, g));
+        u = wrap_inc(u, C);
+    }
+    store_stream<4>(p.lin + off, yv);
+    store_stream<4>(p.sigma + off, gv);
+}
+
 // CATMULL mode (models/base.py:184-226): four taps x0-1 .. x0+2 (clamped), Catmull-Rom weights of t = xs - x0 in the
 // reference's left-to-right fp32 op order (so the value is bit-exact), rows per the same k-mod-C rule as LINEAR.
 // The derivative is the closed form sum_i w_i'(t) g_i (L-1) (the reference's autograd result differs from it by its own
@@ -360,6 +427,41 @@ extern "C" int clair_linearize(const float *val_dev, const float *std_dev, const
                                const int32_t *curve_row_base_host, void *stream) {
     return linearize_impl("clair_linearize", val_dev, std_dev, theta_dev, lin_dev, sigma_dev, n_frames, n_channels, plane, plane,
                           lut_size, interp_mode, curve_row_base_host, stream);
+}
+
+extern "C" int clair_linearize_codes(const void *codes_dev, int code_bytes, float code_max, const float *std_dev, int std_mode,
+                                     float std_value, const float *theta_dev, float *lin_dev, float *sigma_dev, int n_frames,
+                                     int n_channels, int64_t plane, int lut_size, const int32_t *curve_row_base_host,
+                                     void *stream) {
+    const char *fn = "clair_linearize_codes";
+    if (!codes_dev || !theta_dev || !lin_dev || !sigma_dev) return fail(CLAIR_E_ARG, "clair_linearize_codes: null buffer");
+    if (code_bytes != 1 && code_bytes != 2) return fail(CLAIR_E_MODE, "clair_linearize_codes: code_bytes must be 1 (uint8) or 2 (uint16)");
+    if (!(code_max > 0.0f)) return fail(CLAIR_E_ARG, "clair_linearize_codes: code_max must be positive");
+    if (std_mode < kStdNone || std_mode > kStdConstant) return fail(CLAIR_E_MODE, "clair_linearize_codes: unknown std_mode");
+    if (std_mode == kStdTensor && !std_dev) return fail(CLAIR_E_ARG, "clair_linearize_codes: std_mode = tensor needs std_dev");
+    if (int rc = check_geometry(fn, n_frames, n_channels, plane, lut_size, false)) return rc;
+    const int64_t slabs = static_cast<int64_t>(n_frames) * n_channels;
+    if (slabs > 65535) return fail(CLAIR_E_LIMIT, "clair_linearize_codes: n_frames*n_channels exceeds 65535");
+    const uintptr_t align = reinterpret_cast<uintptr_t>(codes_dev) % (4 * code_bytes) | reinterpret_cast<uintptr_t>(lin_dev) % 16 |
+                            reinterpret_cast<uintptr_t>(sigma_dev) % 16 | (std_mode == kStdTensor ? reinterpret_cast<uintptr_t>(std_dev) % 16 : 0);
+    if (plane % 4 != 0 || align != 0)
+        return fail(CLAIR_E_ARG, "clair_linearize_codes: H*W must be a multiple of 4 and the buffers aligned for 4-sample accesses");
+    LinearizeCodesParams p{};
+    p.codes = codes_dev; p.std = std_dev; p.theta = theta_dev; p.lin = lin_dev; p.sigma = sigma_dev;
+    p.plane = plane; p.n_channels = n_channels; p.lut = lut_size;
+    p.std_mode = std_mode; p.std_value = std_value; p.code_max = code_max;
+    fill_rows(p.rows, curve_row_base_host, n_channels, plane);
+    const size_t smem = sizeof(float2) * n_channels * lut_size + (code_bytes == 1 ? 256 * sizeof(float) : 0);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    dim3 grid(static_cast<unsigned>((plane / 4 + kBlock - 1) / kBlock), static_cast<unsigned>(slabs));
+    if (code_bytes == 1) {
+        if (int rc = ensure_smem(linearize_codes_kernel<1>, smem)) return rc;
+        linearize_codes_kernel<1><<<grid, kBlock, smem, s>>>(p);
+    } else {
+        if (int rc = ensure_smem(linearize_codes_kernel<2>, smem)) return rc;
+        linearize_codes_kernel<2><<<grid, kBlock, smem, s>>>(p);
+    }
+    return launched("linearize_codes_kernel");
 }
 
 // Host in, host out: band b+1 travels to the device (copy engine, in_stream) and band b-1 back to the host (second copy

@@ -35,10 +35,20 @@ def linearize_dataset_generator(dataloader: DataLoader, device, icrf_model: ICRF
         _, flat_val, flat_std, _ = flatfield_dataset.get_matching_artefact_images([main_dataset.files[0]])
     for index_batch, val_batch, std_batch, meta_batch in dataloader:
         plain = dark_field_dataset is None and flat_val is None and not transforms
+        codes = val_batch.dtype in (torch.uint8, torch.uint16)
+        if codes and not plain:
+            raise NotImplementedError("integer-code batches are linearised without artefact corrections / gpu transforms: "
+                                      "hand over normalised fp32 images for those")
+        std_is_tensor = torch.is_tensor(std_batch)
+        if std_batch is not None and not std_is_tensor and not codes:
+            raise ValueError("a StdSpec is evaluated by the integer-ingest kernel: pass uint8 / uint16 value codes with it")
         zero_copy = (plain and not val_batch.is_cuda and val_batch.is_pinned() and val_batch.is_contiguous()
-                     and (std_batch is None or (std_batch.is_pinned() and std_batch.is_contiguous())))
+                     and (not std_is_tensor or (std_batch.is_pinned() and std_batch.is_contiguous())))
         if zero_copy:
             images, stds = val_batch, std_batch          # read over PCIe by the kernel itself
+        elif codes:                                      # integer ingest: 1-2 bytes per sample cross PCIe
+            images = val_batch.to(device=dev, non_blocking=True)
+            stds = std_batch.to(device=dev, non_blocking=True) if std_is_tensor else std_batch
         else:
             images, stds = stage_batch(val_batch, std_batch, dev, transforms)
         if dark_field_dataset is not None:                # linearization.py:73-91,108-116

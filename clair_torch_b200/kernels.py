@@ -118,16 +118,26 @@ def icrf_backward_theta(x: torch.Tensor, grad_y: torch.Tensor, channels: int, lu
     return grad
 
 
-def linearize(val: torch.Tensor, std: Optional[torch.Tensor], theta: torch.Tensor, row_base=None, device=None,
+def linearize(val: torch.Tensor, std, theta: torch.Tensor, row_base=None, device=None,
               pinned_out: bool = False, interp_mode: int = _native.INTERP_LINEAR, staged: Optional[bool] = None,
-              bands: int = 16):
+              bands: int = 16, code_max=None):
     """(f(x), sqrt((f'(x) std)^2)) per image of an (N, C, H, W) stack.  inference/linearization.py:94-106.
 
     With `device`, `val` / `std` may be pinned host tensors (read over PCIe by the kernel); with `pinned_out` the two
     results are written straight into page-locked host tensors (torch's caching host allocator), which is what
     linearize_dataset_generator hands to its consumer.  Host in AND host out is `staged` by default: three streams move
-    band b+1 in, linearise band b and move band b-1 out at the same time (clair_linearize_staged)."""
+    band b+1 in, linearise band b and move band b-1 out at the same time (clair_linearize_staged).
+
+    Integer ingest: `val` may hold raw uint8 / uint16 codes (device or pinned host memory); the kernel applies the
+    reference's CastTo(float32) + Normalize(max_val=code_max) itself (code_max defaults to 255 / 65535) and `std` may be a
+    `datasets.StdSpec` instead of a tensor (clair_linearize_codes; LINEAR models)."""
     lib = _native.load()
+    if isinstance(val, torch.Tensor) and val.dtype in _CODE_DTYPES:
+        return _linearize_codes(lib, val, std, theta, row_base, device, pinned_out, interp_mode, code_max)
+    if code_max is not None:
+        raise ValueError("code_max only applies to uint8 / uint16 value codes")
+    if std is not None and not torch.is_tensor(std):
+        raise ValueError("a StdSpec is evaluated by the integer-ingest kernel: pass uint8 / uint16 value codes with it")
     if interp_mode == _native.INTERP_LOOKUP and std is not None:
         # linearization.py:100-105: autograd.grad of an output that does not depend on the image
         raise RuntimeError("a LOOKUP model has no derivative with respect to the image: std images cannot be propagated "
@@ -160,6 +170,38 @@ def linearize(val: torch.Tensor, std: Optional[torch.Tensor], theta: torch.Tenso
         rc = lib.clair_linearize(_ptr(val), _ptr(std), _ptr(th), _ptr(lin), _ptr(sigma), n, c, h * w, th.shape[1],
                                  int(interp_mode), rows, _stream(dev))
     _native.check(rc, "clair_linearize")
+    return lin, sigma
+
+
+def _linearize_codes(lib, val, std, theta, row_base, device, pinned_out, interp_mode, code_max):
+    """linearize() for uint8 / uint16 codes: CastTo + Normalize and the std synthesis happen in the kernel's load."""
+    if interp_mode != _native.INTERP_LINEAR:
+        raise NotImplementedError("integer ingest of the lineariser evaluates the ICRF in InterpMode.LINEAR")
+    val = _code_stack(val, device is not None)
+    std_mode, std_value = 0, 0.0
+    if std is not None and not torch.is_tensor(std):
+        if not hasattr(std, "mode") or std.mode not in _STD_MODES:
+            raise TypeError(f"std_batch must be a tensor, None or a StdSpec, got {type(std)}")
+        std_mode, std_value, std = _STD_MODES[std.mode], float(np.float32(std.value)), None
+    elif std is not None:
+        std = _stack(std, "std_batch", allow_pinned=device is not None)
+        if std.shape != val.shape:
+            raise ValueError("std_batch must have the same shape as val_batch")
+        std_mode = 1
+    dev = torch.device(device) if device is not None else val.device
+    n, c, h, w = val.shape
+    if (h * w) % 4 != 0:
+        raise ValueError("integer ingest needs H*W to be a multiple of 4")
+    th = _table(theta, dev, c)
+    code_bytes, default_max = _CODE_DTYPES[val.dtype]
+    kw = dict(dtype=_F32, pin_memory=True) if pinned_out else dict(dtype=_F32, device=dev)
+    lin, sigma = torch.empty(tuple(val.shape), **kw), torch.empty(tuple(val.shape), **kw)
+    keep, rows = _rows(row_base, c)
+    with torch.cuda.device(dev):
+        rc = lib.clair_linearize_codes(_ptr(val), code_bytes, float(default_max if code_max is None else code_max), _ptr(std),
+                                       std_mode, std_value, _ptr(th), _ptr(lin), _ptr(sigma), n, c, h * w, th.shape[1], rows,
+                                       _stream(dev))
+    _native.check(rc, "clair_linearize_codes")
     return lin, sigma
 
 

@@ -99,6 +99,19 @@ CLAIR_API int clair_linearize(const float *val_dev, const float *std_dev, const 
                     const int32_t *curve_row_base_host, void *stream);
 
 /*
+ * clair_linearize straight from the camera's integer codes — the reference's CPU transforms CastTo + Normalize
+ * (common/transforms.py:107-190: x = fl32(code) / fl32(code_max), an IEEE division) and the missing-std synthesis of
+ * MultiFileMapDataset (datasets/base.py:128-133) are evaluated in the kernel's load, so a frame is read as 1 or 2 bytes
+ * per sample.  Bit-identical to clair_linearize on the CPU-transformed fp32 image.  LINEAR models only.
+ *   codes_dev   (n_frames, C, plane) uint8 (code_bytes = 1) or uint16 (code_bytes = 2); plane a multiple of 4.  May be
+ *               page-locked host memory (mapped): the kernel then reads it over PCIe.
+ *   std_mode    0 none (sigma = 0), 1 std_dev tensor (n_frames, C, plane) fp32, 2 std = x * std_value, 3 std = std_value
+ */
+CLAIR_API int clair_linearize_codes(const void *codes_dev, int code_bytes, float code_max, const float *std_dev, int std_mode,
+                          float std_value, const float *theta_dev, float *lin_dev, float *sigma_dev, int n_frames,
+                          int n_channels, int64_t plane, int lut_size, const int32_t *curve_row_base_host, void *stream);
+
+/*
  * clair_linearize for images that live in page-locked HOST memory and whose results are wanted there too (the
  * generator ends with .cpu(), inference/linearization.py:132): the planes are cut into n_bands bands of pixels; band b+1
  * is copied in (in_stream), band b is linearised (stream) and band b-1 is copied out (out_stream) at the same time, so

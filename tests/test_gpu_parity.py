@@ -654,6 +654,52 @@ def test_hdr_merge_integer_ingest_against_reference_fixture(ct):
     assert max_rel(sig.cpu().numpy(), z["sigma"]) < TOL
 
 
+@pytest.mark.parametrize("bits", [8, 16])
+def test_linearize_integer_ingest_is_bit_identical(ct, bits):
+    """clair_linearize_codes: raw uint8 / uint16 codes + in-kernel CastTo / Normalize / std synthesis give exactly what the
+    CPU-transformed fp32 images give through clair_linearize — std as a tensor, as value * m, as a constant, and absent;
+    device-resident and pinned-host codes; through kernels.linearize and through linearize_dataset_generator."""
+    from clair_torch_b200.datasets import ExposureStackDataset, StdSpec
+    maxval = 255.0 if bits == 8 else 65535.0
+    val, std, t = ct.synthetic.make_stack(3, 3, 46, 64, bits=bits, seed=31 + bits)
+    codes = torch.round(val * maxval).to(torch.uint8 if bits == 8 else torch.uint16)
+    x = codes.to(torch.float32) / maxval                                    # CastTo + Normalize on the CPU
+    assert torch.equal(x, val)
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    m = float(np.float32(0.05))
+    cases = [(std, std), (StdSpec("multiplier", 0.05), x * m), (StdSpec("constant", 0.01), torch.full_like(x, 0.01)), (None, None)]
+    for spec, std_f32 in cases:
+        ref_lin, ref_sig = ct.kernels.linearize(x.to(DEV), None if std_f32 is None else std_f32.to(DEV), theta)
+        s_dev = spec.to(DEV) if torch.is_tensor(spec) else spec
+        lin, sig = ct.kernels.linearize(codes.to(DEV), s_dev, theta)
+        assert torch.equal(lin, ref_lin) and torch.equal(sig, ref_sig)
+        s_pin = spec.pin_memory() if torch.is_tensor(spec) else spec
+        lin_h, sig_h = ct.kernels.linearize(codes.pin_memory(), s_pin, theta, device=torch.device(DEV), pinned_out=True)
+        torch.cuda.synchronize()
+        assert not lin_h.is_cuda and torch.equal(lin_h, ref_lin.cpu()) and torch.equal(sig_h, ref_sig.cpu())
+    # a 12-bit camera in 16-bit words: code_max = 4095
+    if bits == 16:
+        c12 = (codes.to(torch.int32) >> 4).to(torch.uint16)
+        x12 = c12.to(torch.float32) / 4095.0
+        a = ct.kernels.linearize(c12.to(DEV), StdSpec("multiplier", 0.05), theta, code_max=4095.0)
+        b = ct.kernels.linearize(x12.to(DEV), (x12 * m).to(DEV), theta)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # the generator: one image per batch, codes in pinned host memory, results on the host
+    model = _model(ct, theta.cpu().numpy())
+    ds = ExposureStackDataset(list(codes.pin_memory()), StdSpec("multiplier", 0.05), list(t))
+    view = lambda b: (torch.tensor([b[0][0]]), b[0][1].unsqueeze(0), b[0][2], {"exposure_time": torch.tensor([b[0][3]["exposure_time"]])})
+    ref_lin, ref_sig = ct.kernels.linearize(x.to(DEV), (x * m).to(DEV), theta)
+    for k, (lin, sig, meta) in enumerate(ct.linearize_dataset_generator(DataLoader(ds, batch_size=1, collate_fn=view), DEV, model)):
+        assert torch.equal(lin, ref_lin[k].cpu()) and torch.equal(sig, ref_sig[k].cpu())
+    # errors: StdSpec without codes, odd plane, non-LINEAR model
+    with pytest.raises(ValueError):
+        ct.kernels.linearize(x.to(DEV), StdSpec("multiplier", 0.05), theta)
+    with pytest.raises(ValueError):
+        ct.kernels.linearize(codes[:, :, :3, :5].contiguous().to(DEV), None, theta)
+    with pytest.raises(NotImplementedError):
+        ct.kernels.linearize(codes.to(DEV), None, theta, interp_mode=ct._native.INTERP_LOOKUP)
+
+
 # ---- streaming frame statistics (SURVEY.md 8(f) rank 3) -------------------------------------------------
 def test_wbomeanvar_golden(ct):
     from clair_torch_b200.common.statistics import WBOMeanVar
