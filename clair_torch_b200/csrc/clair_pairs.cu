@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
 //   * pair phase: 64-bit shared loads, validity folded into the Gaussian weight as kMaskedWeight (gi + gj < 0
 //     <=> masked), 0/1 mask as a float pair so the masked sums are plain packed multiply-adds;
 //   * FULL: the fp32 partial sums of both halves share one pivot per (lane, slot): the first valid loss seen.
-// Measured on the c3 stack (16 x 4K, 29 pairs): 8930 -> ~5000 warp instructions per tile.
+// Measured on the c3 stack (16 x 4K, 29 pairs): 8930 -> 7540 warp instructions per tile (1.74 G -> 1.46 G per launch);
+// c2 means pass 156 M -> 105 M.
 // =====================================================================================================
 constexpr float kMaskedWeight = -1.0e30f;  // gw of a masked element: no sum with finite weights gets back above 0
 
@@ -832,7 +833,7 @@ __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
 //     (4 shared-memory accesses per pair instead of 6);
 //   * table over (g0, g1 - g0): f = g0 + w (g1 - g0) in one FMA (within 1 ulp of the reference's form);
 //   * frame pointers advance by a constant, tap addresses are 32-bit offsets from one base: a trip of N = 2,
-//     P = 1 went from 459 to under 200 warp instructions.
+//     P = 1 went from 459 to 283 warp instructions, the c2 launch from 253 M to 156 M.
 // =====================================================================================================
 
 // One predicated vector reduction per element: both taps in one L2 operation into one of kPairGradCopies replicated
