@@ -110,6 +110,37 @@ def test_pair_kernels_many_pairs_and_odd_sizes(ct):
         assert max_abs_over_max(grad.cpu().numpy(), o_grad) < 1e-5
 
 
+@pytest.mark.parametrize("n,pairs,h,w", [(2, "all", 30, 36), (3, "first", 8, 100), (7, "sparse", 24, 40), (12, "sparse", 20, 52),
+                                         (20, "first", 12, 44), (32, "sparse", 8, 36), (33, "sparse", 8, 36), (9, "all", 5, 28)])
+def test_packed_pair_kernels_block_shapes(ct, n, pairs, h, w):
+    """The packed (fp32x2) pair kernels over their block shapes: a single exposure pair (one-warp blocks), fewer warps than
+    frames (two staging items per thread), 32 frames (the most the packed statistics kernel holds) and 33 (scalar
+    fallback), planes that end inside a tile and inside a warp's 64-pixel group; with and without the uncertainty term,
+    relative and absolute loss.  Checked against the C oracle."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.inference.measure_linearity import spatial_statistics
+    from clair_torch_b200.training import linearity_loss_and_table_grad
+    val, std, _ = ct.synthetic.make_stack(n, 3, h, w, bits=16, seed=100 + n)
+    t = 1e-3 * 1.25 ** np.arange(n)
+    theta = ct.synthetic.reference_curve(3)
+    i, j, r = orc.exposure_pairs(t, 0.0)
+    if pairs == "first":
+        i, j, r = i[:1], j[:1], r[:1]
+    elif pairs == "sparse":
+        i, j, r = i[::5], j[::5], r[::5]
+    dv, ds, dt = val.to(DEV), std.to(DEV), theta.to(DEV)
+    for relative, unc in ((True, True), (True, False), (False, True)):
+        sums = kernels.pair_stats(dv, ds, i, j, r, dt, 1 / 255, 254 / 255, relative, unc)
+        mean, sd, err = spatial_statistics(sums.cpu(), True)
+        o_mean, o_sd, o_err = corc.pair_stats(val.numpy(), std.numpy(), i, j, r, theta.numpy(), relative=relative, unc_weighting=unc)
+        assert max_rel(mean.numpy(), o_mean) < 2e-6 and max_rel(err.numpy(), o_err) < 2e-6
+        assert np.all(np.abs(sd.numpy() - o_sd) <= 1e-5 * o_sd + 2e-8 * o_mean)
+        lin, spatial, grad = linearity_loss_and_table_grad(dv, ds, i, j, r, dt, 1 / 255, 254 / 255, relative, unc)
+        o_lin, o_m, o_grad = corc.train_grad(val.numpy(), std.numpy(), i, j, r, theta.numpy(), relative=relative, unc_weighting=unc)
+        assert max_rel(lin.cpu().numpy(), o_lin) < 2e-6
+        assert max_abs_over_max(grad.cpu().numpy(), o_grad) < 1e-5
+
+
 def test_all_pairs_masked_gives_zero_loss_and_gradient(ct):
     from clair_torch_b200.training import linearity_loss_and_table_grad
     val = torch.zeros((3, 3, 8, 8))                                      # every pixel below the validity threshold
