@@ -846,6 +846,7 @@ __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
 //   * 64-bit fixed point on native integer shared atomics (returning add on the low word, carry into the high word,
 //     pipelined one frame deep; > 790 G/s in isolation): 0.44 / 3.18 ms — the 12 KB table costs a resident block and the
 //     kernel is then bound by latency at 12-15 warps per SM, not by the reductions.
+// One copy per lane instead of per warp is slower too (0.38 ms): lanes of a warp instruction that meet in a sector are merged.
 __device__ __forceinline__ void red_add_v2_if(float *addr, float a, float b, float g) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %3, 0f00000000;\n\t@p red.global.add.v2.f32 [%0], {%1, %2};\n\t}"
                  ::"l"(addr), "f"(a), "f"(b), "f"(g));
