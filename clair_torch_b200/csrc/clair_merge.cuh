@@ -158,21 +158,72 @@ __device__ __forceinline__ HdrTerms hdr_terms(float x, float s, float it, bool h
     if (gaussian) {
         float d;
         w = gaussian_weight(x, kHdrNegScaleLog2e, d);
-        q = -60.0f * d;
+        q = __fmul_rn(-60.0f, d);
     }
-    const float v = f * it;
+    // every rounding below is explicit (no implicit contraction): hdr_terms2 is the same sequence on fp32x2 pairs and the
+    // two must agree to the bit (callers accumulate sum w v as fmaf(w, v, sum))
+    const float v = __fmul_rn(f, it);
     o.w = w;
-    o.wv = w * v;
+    o.wv = __fmul_rn(w, v);
     if (has_std) {
-        const float ws = w * s;
-        const float t1 = fp * it;
-        o.R = ws * fmaf(q, v, t1);
-        o.Q = ws * q;
-        o.P = ws * t1;
+        const float ws = __fmul_rn(w, s);
+        const float t1 = __fmul_rn(fp, it);
+        o.R = __fmul_rn(ws, fmaf(q, v, t1));
+        o.Q = __fmul_rn(ws, q);
+        o.P = __fmul_rn(ws, t1);
     } else {
         o.R = 0.0f; o.Q = 0.0f; o.P = 0.0f;
     }
     o.v = v;
+    return o;
+}
+
+// hdr_terms for two adjacent pixels on packed fp32x2 arithmetic (FMUL2 / FADD2 / FFMA2: two results per issue slot;
+// the merge kernel is HBM-bound in bursts but runs into the board's power cap in long runs, where fewer issued
+// instructions buy clock).  Bit-identical to two hdr_terms calls.  P and v of the one-frame case are not produced.
+struct HdrTerms2 {
+    f32x2 w, v, R, Q;
+};
+
+__device__ __forceinline__ HdrTerms2 hdr_terms2(float x0, float x1, float s0, float s1, float it, bool has_model, bool gaussian,
+                                                uint32_t bias0, uint32_t bias1, float lm1, bool has_std) {
+    HdrTerms2 o;
+    const f32x2 x2 = pack2(x0, x1);
+    f32x2 f2 = x2, fp2 = splat2(1.0f);
+    if (has_model) {
+        float r0, r1;
+        unpack2(mul2(x2, splat2(lm1)), r0, r1);                          // image * (L - 1)
+        const float xs0 = fminf(fmaxf(r0, 0.0f), lm1), xs1 = fminf(fmaxf(r1, 0.0f), lm1);
+        const f32x2 xs2 = pack2(xs0, xs1);
+        const f32x2 two23 = splat2(8388608.0f);
+        const f32x2 t2 = add2_rd(xs2, two23);
+        float t0, t1, w0, w1;
+        unpack2(t2, t0, t1);
+        unpack2(sub2(xs2, sub2(t2, two23)), w0, w1);
+        float g00, dg0, g01, dg1;
+        asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g00), "=f"(dg0) : "r"(static_cast<uint32_t>(__float_as_int(t0)) * 8u + bias0));
+        asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g01), "=f"(dg1) : "r"(static_cast<uint32_t>(__float_as_int(t1)) * 8u + bias1));
+        f2 = pack2(fmaf(w0, dg0, g00), fmaf(w1, dg1, g01));
+        fp2 = pack2((xs0 == r0) ? __fmul_rn(dg0, lm1) : 0.0f, (xs1 == r1) ? __fmul_rn(dg1, lm1) : 0.0f);
+    }
+    f32x2 w2 = splat2(1.0f), q2 = 0ull;
+    if (gaussian) {
+        const f32x2 d2 = add2(x2, splat2(-0.5f));
+        float e0, e1;
+        unpack2(mul2(splat2(kHdrNegScaleLog2e), mul2(d2, d2)), e0, e1);
+        w2 = pack2(exp2f_approx(e0), exp2f_approx(e1));
+        q2 = mul2(splat2(-60.0f), d2);
+    }
+    o.v = mul2(f2, splat2(it));
+    o.w = w2;
+    if (has_std) {
+        const f32x2 ws = mul2(w2, pack2(s0, s1));
+        const f32x2 t1 = mul2(fp2, splat2(it));
+        o.R = mul2(ws, fma2(q2, o.v, t1));
+        o.Q = mul2(ws, q2);
+    } else {
+        o.R = 0ull; o.Q = 0ull;
+    }
     return o;
 }
 
@@ -335,7 +386,95 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
                 u = (u + 1 == cur.C) ? 0u : u + 1;
             }
         }
-        float wsum[VEC], wv[VEC], R[NF][VEC], Q[NF][VEC];
+        float wsum[VEC], wv[VEC];
+        if constexpr (VEC % 2 == 0 && NF > 1) {
+            // pixel pairs on packed fp32x2 arithmetic; (R_n, Q_n) stay packed until the per-pixel epilogue
+            constexpr int HV = VEC / 2;
+            f32x2 wsum2[HV], wv2[HV], R2[NF][HV], Q2[NF][HV];
+#pragma unroll
+            for (int h = 0; h < HV; ++h) { wsum2[h] = 0ull; wv2[h] = 0ull; }
+            {
+                Pack<VEC> xv[NF], sv[NF];
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    const int64_t o = off + static_cast<int64_t>(n) * frame_stride;
+                    xv[n] = load_pixels<SRC, VEC>(p, n, c, pix, o, s_x);
+                    if constexpr (HAS_STD) sv[n] = load_std<VEC, STD>(p, o, xv[n]);
+                }
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    const float it = p.scale.inv_t[n];
+#pragma unroll
+                    for (int h = 0; h < HV; ++h) {
+                        const HdrTerms2 t = hdr_terms2(xv[n].v[2 * h], xv[n].v[2 * h + 1], HAS_STD ? sv[n].v[2 * h] : 0.0f,
+                                                       HAS_STD ? sv[n].v[2 * h + 1] : 0.0f, it, has_model, gaussian, bias[2 * h],
+                                                       bias[2 * h + 1], lm1, HAS_STD);
+                        wsum2[h] = add2(wsum2[h], t.w);
+                        wv2[h] = fma2(t.w, t.v, wv2[h]);
+                        R2[n][h] = t.R;
+                        Q2[n][h] = t.Q;
+                    }
+                }
+            }
+            if constexpr (SINGLE) {
+                // the single-batch epilogue of hdr_finish on pixel pairs (the same operations, so the same bits)
+                Pack<VEC> rad, sg;
+#pragma unroll
+                for (int h = 0; h < HV; ++h) {
+                    const f32x2 wbe = add2(wsum2[h], splat2(1e-6f));                 // statistics.py:76 (fp32 add)
+                    float b0, b1, ws0, ws1;
+                    unpack2(wbe, b0, b1);
+                    unpack2(wsum2[h], ws0, ws1);
+                    f32x2 inv = pack2(rcp_approx(b0), rcp_approx(b1));
+                    inv = fma2(fma2(sub2(0ull, wbe), inv, splat2(1.0f)), inv, inv);  // one Newton step: <= 1 ulp
+                    const f32x2 mean_b = mul2(wv2[h], inv);
+                    const float nan = __int_as_float(0x7fc00000);                    // an all-zero-weight pixel: 0/0 as in the reference
+                    const f32x2 frac = pack2(ws0 != 0.0f ? 1.0f : nan, ws1 != 0.0f ? 1.0f : nan);
+                    unpack2(mul2(frac, mean_b), rad.v[2 * h], rad.v[2 * h + 1]);
+                    if constexpr (HAS_STD) {
+                        const f32x2 rho = sub2(0ull, mean_b);
+                        f32x2 acc = 0ull;
+#pragma unroll
+                        for (int n = 0; n < NF; ++n) {
+                            const f32x2 g = fma2(rho, Q2[n][h], R2[n][h]);
+                            acc = fma2(g, g, acc);
+                        }
+                        float a0, a1;
+                        unpack2(acc, a0, a1);
+                        unpack2(mul2(mul2(frac, inv), pack2(sqrt_approx(a0), sqrt_approx(a1))), sg.v[2 * h], sg.v[2 * h + 1]);
+                    }
+                }
+                if (p.radiance_f64) {
+                    double r64[VEC];
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) r64[k] = static_cast<double>(rad.v[k]);
+                    store_stream_f64<VEC>(static_cast<double *>(p.radiance) + off, r64);
+                } else {
+                    store_stream<VEC>(static_cast<float *>(p.radiance) + off, rad);
+                }
+                if constexpr (HAS_STD) store_stream<VEC>(p.sigma + off, sg);
+            } else {
+#pragma unroll
+            for (int h = 0; h < HV; ++h) {
+                unpack2(wsum2[h], wsum[2 * h], wsum[2 * h + 1]);
+                unpack2(wv2[h], wv[2 * h], wv[2 * h + 1]);
+            }
+            hdr_finish<VEC, HAS_STD, SINGLE, false>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    float r0, r1, q0, q1;
+                    unpack2(R2[n][k >> 1], r0, r1);
+                    unpack2(Q2[n][k >> 1], q0, q1);
+                    const float r = (k & 1) ? r1 : r0, q = (k & 1) ? q1 : q0;
+                    const float g = SINGLE ? fmaf(gamma, q, r) : fmaf(alpha, r, __fmul_rn(gamma, q));
+                    acc = fmaf(g, g, acc);
+                }
+                return acc;
+            });
+            }
+        } else {
+        float R[NF][VEC], Q[NF][VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; }
         {
@@ -354,7 +493,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
                     const HdrTerms t = hdr_terms(xv[n].v[k], HAS_STD ? sv[n].v[k] : 0.0f, it, has_model, gaussian, bias[k], lm1,
                                                  HAS_STD);
                     wsum[k] += t.w;
-                    wv[k] += t.wv;
+                    wv[k] = fmaf(t.w, t.v, wv[k]);
                     R[n][k] = (NF == 1) ? one_frame_gradient(t) : t.R;
                     Q[n][k] = t.Q;
                 }
@@ -364,11 +503,12 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
             float acc = 0.0f;
 #pragma unroll
             for (int n = 0; n < NF; ++n) {
-                const float g = SINGLE ? fmaf(gamma, Q[n][k], R[n][k]) : fmaf(alpha, R[n][k], gamma * Q[n][k]);
+                const float g = SINGLE ? fmaf(gamma, Q[n][k], R[n][k]) : fmaf(alpha, R[n][k], __fmul_rn(gamma, Q[n][k]));
                 acc = fmaf(g, g, acc);
             }
             return acc;
         });
+        }
     }
 }
 
@@ -449,7 +589,7 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrPara
                         dark_mix_value<true>(x[k], blur[k], sv[j].v[k], dk[j].v[k], ds[j].v[k], p.dg, xm, sm);
                         const HdrTerms t = hdr_terms(xm, sm, it, has_model, gaussian, bias[k], lm1, true);
                         wsum[k] += t.w;
-                        wv[k] += t.wv;
+                        wv[k] = fmaf(t.w, t.v, wv[k]);
                         R[n0 + j][k] = (NF == 1) ? one_frame_gradient(t) : t.R;
                         Q[n0 + j][k] = t.Q;
                     }
@@ -530,7 +670,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_smem_kernel(const HdrParams 
                     for (int k = 0; k < VEC; ++k) {
                         const HdrTerms t = hdr_terms(xv[j].v[k], sv[j].v[k], it, has_model, gaussian, bias[k], lm1, true);
                         wsum[k] += t.w;
-                        wv[k] += t.wv;
+                        wv[k] = fmaf(t.w, t.v, wv[k]);
                         col[k * kBlock] = t.R;
                         col[(VEC + k) * kBlock] = t.Q;
                     }
@@ -626,7 +766,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_kernel(const HdrParams p) {
                         const HdrTerms t = hdr_terms(xv[j].v[k], HAS_STD ? sv[j].v[k] : 0.0f, it, has_model, gaussian,
                                                      bias[k], lm1, HAS_STD);
                         wsum[k] += t.w;
-                        wv[k] += t.wv;
+                        wv[k] = fmaf(t.w, t.v, wv[k]);
                         if constexpr (HAS_STD) {
                             const double R = static_cast<double>(t.R), Q = static_cast<double>(t.Q);
                             srr[k] = fma(R, R, srr[k]);
