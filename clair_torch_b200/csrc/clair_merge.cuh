@@ -39,6 +39,7 @@ struct HdrParams {
     int std_mode;             // kStdNone / kStdTensor / kStdMultiplier / kStdConstant
     float std_value;          // multiplier or constant
     float code_max;           // integer ingest: x = fl32(code) / fl32(code_max)   (CastTo + Normalize)
+    float code_rcp;           // fl32(1 / code_max) when normalise_code16's short division is exact for all 65536 codes, else 0
     int src;                  // kSrcF32 / kSrcU8 / kSrcU16 (read by the all-modes kernel only; the others take it as a template)
     int hwc;                  // integer codes are (n_frames, H, W, 3) BGR-interleaved instead of planar
     const float *dark;        // fused dark-field mix (hdr_merge_dark_kernel): dark frames and their std, shaped like val
@@ -69,13 +70,50 @@ __device__ __forceinline__ uint32_t pick_half(const uint2 &a, const uint2 &b, co
     return (j & 1) ? (w >> 16) : (w & 0xffffu);
 }
 
-template <int SRC, int VEC>
+// fl32(code) / fl32(code_max) for a 16-bit code, bit-identical to the IEEE division of the reference's Normalize.
+// The code becomes a float without the conversion unit (2^23 + code is exact, subtracting 2^23 leaves fl32(code)).
+// SHORT: the quotient is q0 = a * rcp corrected once by its exact residual, q = fma(fma(-q0, d, a), rcp, q0) — the
+// correctly rounded a / d when rcp is the correctly rounded 1 / d (Markstein).  The host only selects a SHORT kernel (the
+// register kernels) after checking that against a / d for every one of the 65536 codes (exact_code_reciprocal,
+// clair_stack.cu; p.code_rcp != 0).  Against __fdiv_rn this drops MUFU.RCP, I2F and the division's range-check branch:
+// two of the three XU-pipe operations per element.
+template <bool SHORT>
+__device__ __forceinline__ float normalise_code16(uint32_t code, const HdrParams &p) {
+    const float a = __fsub_rn(__int_as_float(0x4B000000u | code), 8388608.0f);
+    if constexpr (SHORT) {
+        const float q0 = __fmul_rn(a, p.code_rcp);
+        return fmaf(fmaf(-q0, p.code_max, a), p.code_rcp, q0);
+    } else {
+        return __fdiv_rn(a, p.code_max);
+    }
+}
+
+template <int SRC, int VEC, bool SHORT = false>
 __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int c, uint32_t pix, int64_t o, const float *s_x) {
     if constexpr (SRC == kSrcF32) {
         return load_stream<VEC>(static_cast<const float *>(p.val) + o);
     } else if constexpr (src_is_u8(SRC)) {
-        static_assert(VEC == 4, "integer ingest is 4 pixels per thread");
+        static_assert(VEC == 4 || VEC == 2, "integer ingest is 4 pixels per thread (2 in the 9..16-frame register kernel)");
         Pack<VEC> r;
+        if constexpr (VEC == 2) {
+            // two pixels: one 16-bit load, or the 6 bytes of two BGR pixels as three (the pair starts 2-byte aligned)
+            if constexpr (SRC == kSrcU8Hwc) {
+                const uint16_t *src = reinterpret_cast<const uint16_t *>(static_cast<const uint8_t *>(p.val) +
+                                                                         (static_cast<int64_t>(n) * p.stride + pix) * 3);
+                const uint32_t h0 = __ldcs(src), h1 = __ldcs(src + 1), h2 = __ldcs(src + 2);
+                const uint32_t w0 = h0 | (h1 << 16);          // bytes 0..3, h2 = bytes 4..5
+                const int j0 = 2 - c;
+                const uint32_t c0 = (w0 >> (8 * j0)) & 0xffu;                                   // byte j0
+                const uint32_t c1 = j0 == 0 ? (w0 >> 24) : ((h2 >> (8 * (j0 - 1))) & 0xffu);    // byte 3 + j0
+                r.v[0] = s_x[c0];
+                r.v[1] = s_x[c1];
+            } else {
+                const uint32_t w = __ldcs(reinterpret_cast<const uint16_t *>(static_cast<const uint8_t *>(p.val) + o));
+                r.v[0] = s_x[w & 0xffu];
+                r.v[1] = s_x[w >> 8];
+            }
+            return r;
+        }
         if constexpr (SRC == kSrcU8Hwc) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(p.val) +
                                                                      (static_cast<int64_t>(n) * p.stride + pix) * 3);
@@ -96,8 +134,26 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int 
         for (int k = 0; k < 4; ++k) r.v[k] = s_x[(w >> (8 * k)) & 0xffu];
         return r;
     } else {
-        static_assert(VEC == 4, "integer ingest is 4 pixels per thread");
+        static_assert(VEC == 4 || VEC == 2, "integer ingest is 4 pixels per thread (2 in the 9..16-frame register kernel)");
         Pack<VEC> r;
+        if constexpr (VEC == 2) {
+            // two pixels: one 32-bit load, or the 12 bytes of two BGR pixels as three
+            if constexpr (SRC == kSrcU16Hwc) {
+                const uint32_t *src = reinterpret_cast<const uint32_t *>(static_cast<const uint16_t *>(p.val) +
+                                                                         (static_cast<int64_t>(n) * p.stride + pix) * 3);
+                const uint32_t w0 = __ldcs(src), w1 = __ldcs(src + 1), w2 = __ldcs(src + 2);   // halfwords 0..5
+                const int j0 = 2 - c;
+                const uint32_t c0 = j0 == 0 ? (w0 & 0xffffu) : (j0 == 1 ? (w0 >> 16) : (w1 & 0xffffu));   // halfword j0
+                const uint32_t c1 = j0 == 0 ? (w1 >> 16) : (j0 == 1 ? (w2 & 0xffffu) : (w2 >> 16));       // halfword 3 + j0
+                r.v[0] = normalise_code16<SHORT>(c0, p);
+                r.v[1] = normalise_code16<SHORT>(c1, p);
+            } else {
+                const uint32_t w = __ldcs(reinterpret_cast<const uint32_t *>(static_cast<const uint16_t *>(p.val) + o));
+                r.v[0] = normalise_code16<SHORT>(w & 0xffffu, p);
+                r.v[1] = normalise_code16<SHORT>(w >> 16, p);
+            }
+            return r;
+        }
         if constexpr (SRC == kSrcU16Hwc) {
             const uint2 *src = reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(p.val) +
                                                                (static_cast<int64_t>(n) * p.stride + pix) * 3);
@@ -109,15 +165,15 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int 
                 if (j0 == 0) code = pick_half(a, b, cc, 3 * k);
                 else if (j0 == 1) code = pick_half(a, b, cc, 3 * k + 1);
                 else code = pick_half(a, b, cc, 3 * k + 2);
-                r.v[k] = __fdiv_rn(static_cast<float>(code), p.code_max);
+                r.v[k] = normalise_code16<SHORT>(code, p);
             }
             return r;
         }
         const uint2 w = __ldcs(reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(p.val) + o));
-        r.v[0] = __fdiv_rn(static_cast<float>(w.x & 0xffffu), p.code_max);
-        r.v[1] = __fdiv_rn(static_cast<float>(w.x >> 16), p.code_max);
-        r.v[2] = __fdiv_rn(static_cast<float>(w.y & 0xffffu), p.code_max);
-        r.v[3] = __fdiv_rn(static_cast<float>(w.y >> 16), p.code_max);
+        r.v[0] = normalise_code16<SHORT>(w.x & 0xffffu, p);
+        r.v[1] = normalise_code16<SHORT>(w.x >> 16, p);
+        r.v[2] = normalise_code16<SHORT>(w.y & 0xffffu, p);
+        r.v[3] = normalise_code16<SHORT>(w.y >> 16, p);
         return r;
     }
 }
@@ -398,7 +454,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
 #pragma unroll
                 for (int n = 0; n < NF; ++n) {
                     const int64_t o = off + static_cast<int64_t>(n) * frame_stride;
-                    xv[n] = load_pixels<SRC, VEC>(p, n, c, pix, o, s_x);
+                    xv[n] = load_pixels<SRC, VEC, true>(p, n, c, pix, o, s_x);
                     if constexpr (HAS_STD) sv[n] = load_std<VEC, STD>(p, o, xv[n]);
                 }
 #pragma unroll
@@ -482,7 +538,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
 #pragma unroll
             for (int n = 0; n < NF; ++n) {
                 const int64_t o = off + static_cast<int64_t>(n) * frame_stride;
-                xv[n] = load_pixels<SRC, VEC>(p, n, c, pix, o, s_x);
+                xv[n] = load_pixels<SRC, VEC, true>(p, n, c, pix, o, s_x);
                 if constexpr (HAS_STD) sv[n] = load_std<VEC, STD>(p, o, xv[n]);
             }
 #pragma unroll
@@ -873,8 +929,37 @@ int launch_merge_by_std(const MergeLaunch &m) {
 #undef CLAIR_FIXED_NF
 }
 
-// integer ingest, 4 codes per thread: planar (clair_merge_codes.cu) and interleaved BGR (clair_merge_codes_hwc.cu)
+// Integer ingest of 9..16 frames: the register kernel at 2 codes per thread (the packed pixel-pair path), so that the
+// 9 x 24 MP 16-bit stacks of BASELINE config c4 do not fall to the shared-memory-parked kernel when they are handed over as
+// codes.  Only the instantiations this range needs (std as a tensor or synthesised; N = 9..16).
+template <int SRC>
+int launch_merge_codes_wide(const MergeLaunch &m) {
+#define CLAIR_WIDE_NF(NF, ST) \
+    (m.single ? launch_merge_kernel(hdr_merge_fixed_kernel<2, NF, ST, true, SRC>, m) : launch_merge_kernel(hdr_merge_fixed_kernel<2, NF, ST, false, SRC>, m))
+#define CLAIR_WIDE(ST)                                \
+    switch (m.n_frames) {                             \
+        case 9: return CLAIR_WIDE_NF(9, ST);          \
+        case 10: return CLAIR_WIDE_NF(10, ST);        \
+        case 11: return CLAIR_WIDE_NF(11, ST);        \
+        case 12: return CLAIR_WIDE_NF(12, ST);        \
+        case 13: return CLAIR_WIDE_NF(13, ST);        \
+        case 14: return CLAIR_WIDE_NF(14, ST);        \
+        case 15: return CLAIR_WIDE_NF(15, ST);        \
+        case 16: return CLAIR_WIDE_NF(16, ST);        \
+        default: return fail(CLAIR_E_ARG, "hdr merge: the 2-code register kernel takes 9..16 frames"); \
+    }
+    if (m.std_mode == kStdTensor) { CLAIR_WIDE(1) }
+    if (m.std_mode == kStdMultiplier || m.std_mode == kStdConstant) { CLAIR_WIDE(2) }
+    return fail(CLAIR_E_ARG, "hdr merge: the register kernels need a std source");
+#undef CLAIR_WIDE
+#undef CLAIR_WIDE_NF
+}
+
+// integer ingest, 4 codes per thread: planar (clair_merge_codes.cu) and interleaved BGR (clair_merge_codes_hwc.cu);
+// 2 codes per thread for 9..16 frames (clair_merge_codes_wide.cu, clair_merge_codes_hwc_wide.cu)
 int launch_merge_codes_planar(const MergeLaunch &m, bool u8);
 int launch_merge_codes_hwc(const MergeLaunch &m, bool u8);
+int launch_merge_codes_planar_wide(const MergeLaunch &m, bool u8);
+int launch_merge_codes_hwc_wide(const MergeLaunch &m, bool u8);
 
 }  // namespace clair

@@ -3,6 +3,8 @@
 // loads, the ICRF table lives in shared memory, all per-pixel reductions stay in registers and the outputs
 // are written once.  See DESIGN.md §3 for the derivation of the single-pass variance form.
 #include "clair_merge.cuh"
+#include <cmath>
+#include <mutex>
 
 namespace clair {
 
@@ -553,6 +555,29 @@ struct DarkOptions {          // fused dark-field mix: dark == nullptr switches 
     int hwc = 0;              // integer codes in the interleaved (H, W, 3) BGR camera layout
 };
 
+// normalise_code16 (clair_merge.cuh) divides by code_max as q0 = a * rcp, q = fma(fma(-q0, d, a), rcp, q0).  Returns rcp when
+// that equals the IEEE quotient a / d for EVERY 16-bit code a (checked here, once per code_max: 65536 divisions), else 0 and
+// the kernel keeps __fdiv_rn.  65535, 4095, 1023 pass; the check is what makes an arbitrary caller-supplied code_max safe.
+float exact_code_reciprocal(float code_max) {
+    static std::mutex mu;
+    static float cached_max = 0.0f, cached_rcp = 0.0f;
+    std::lock_guard<std::mutex> lock(mu);
+    if (code_max == cached_max) return cached_rcp;
+    const volatile float d = code_max;
+    const float rcp = 1.0f / d;
+    bool exact = std::isfinite(rcp) && rcp > 0.0f;
+    for (uint32_t k = 0; exact && k < 65536u; ++k) {
+        const volatile float a = static_cast<float>(k);
+        const float q0 = a * rcp;
+        const float q = std::fmaf(std::fmaf(-q0, d, a), rcp, q0);
+        const float want = a / d;
+        exact = (q == want) && !(q == 0.0f && k != 0);
+    }
+    cached_max = code_max;
+    cached_rcp = exact ? rcp : 0.0f;
+    return cached_rcp;
+}
+
 int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max, const float *std_dev, int std_mode,
                    float std_value, const double *exposure_host, int n_frames, const float *theta_dev, int n_channels,
                    int lut_size, int interp_mode, int64_t plane, int64_t plane_stride, const int32_t *curve_row_base_host,
@@ -592,6 +617,7 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     p.hwc = dark.hwc;
     p.gaussian = gaussian_weights; p.is_first = is_first; p.is_final = is_final; p.radiance_f64 = radiance_f64;
     p.std_mode = std_mode; p.std_value = std_value; p.code_max = code_max;
+    p.code_rcp = src == kSrcU16 ? exact_code_reciprocal(code_max) : 0.0f;
     fill_rows(p.rows, curve_row_base_host, n_channels, plane_stride);
     for (int n = 0; n < n_frames; ++n) p.scale.inv_t[n] = static_cast<float>(1.0 / exposure_host[n]);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -673,9 +699,13 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     }
     size_t smem = (theta_dev ? sizeof(float2) * n_channels * lut_size : 0) + (src == kSrcU8 ? 256 * sizeof(float) : 0);
     const bool single = is_first && is_final;
-    // integer ingest takes 4 codes per load, which leaves no registers for more than 8 frames of (R_n, Q_n)
-    const int fixed_max_f32 = g_tuning.hdr_fixed_max > 0 ? std::min(g_tuning.hdr_fixed_max, kMaxFixedFramesF32) : kMaxFixedFramesF32;
-    const bool fixed = has_std && !g_tuning.hdr_force_dynamic && n_frames <= (src == kSrcF32 ? fixed_max_f32 : kMaxFixedFrames);
+    // integer ingest takes 4 codes per load, which leaves no registers for more than 8 frames of (R_n, Q_n): 9..16 frames
+    // take 2 codes per load (`wide`), like the fp32 stacks
+    const int fixed_max = g_tuning.hdr_fixed_max > 0 ? std::min(g_tuning.hdr_fixed_max, kMaxFixedFramesF32) : kMaxFixedFramesF32;
+    // the register kernels normalise 16-bit codes with the short division: only when it is exact for this code_max
+    const bool fixed = has_std && !g_tuning.hdr_force_dynamic && n_frames <= fixed_max && (src != kSrcU16 || p.code_rcp != 0.0f);
+    const bool wide = src != kSrcF32 && fixed && n_frames > kMaxFixedFrames;
+    if (wide) vec = 2;
     // measured on B200 (profiles/): with fp32 input 2 pixels per thread keep the fixed-N kernel at 40 registers
     // (6 blocks/SM); 4 pixels per thread need 64.  Integer ingest always takes 4 codes per load.
     // 9 .. ~40 frames: (R_n, Q_n) parked in shared memory, 2 pixels per thread (1 when H*W is odd)
@@ -699,7 +729,8 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     m.fixed = fixed; m.parked = parked; m.single = single;
     m.std_mode = std_mode; m.n_frames = n_frames; m.n_channels = n_channels; m.stream = s;
     int rc;
-    if (src != kSrcF32) rc = dark.hwc ? launch_merge_codes_hwc(m, src == kSrcU8) : launch_merge_codes_planar(m, src == kSrcU8);
+    if (wide) rc = dark.hwc ? launch_merge_codes_hwc_wide(m, src == kSrcU8) : launch_merge_codes_planar_wide(m, src == kSrcU8);
+    else if (src != kSrcF32) rc = dark.hwc ? launch_merge_codes_hwc(m, src == kSrcU8) : launch_merge_codes_planar(m, src == kSrcU8);
     else if (vec == 4) rc = launch_merge_by_std<4, kSrcF32>(m);
     else if (vec == 2) rc = launch_merge_by_std<2, kSrcF32>(m);
     else rc = launch_merge_by_std<1, kSrcF32>(m);

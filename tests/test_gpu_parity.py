@@ -640,6 +640,42 @@ def test_hdr_merge_interleaved_bgr_codes_equal_planar(ct, bits, n):
         kernels.hdr_merge_update(kernels.HdrMergeState(), val.to(DEV), None, t, theta, True, True, code_layout="hwc_bgr")
 
 
+@pytest.mark.parametrize("n", [9, 10, 11, 13, 14, 15, 16])
+def test_hdr_merge_integer_ingest_9_to_16_frames(ct, n):
+    """9..16 frames of uint8 / uint16 codes (planar and BGR camera layout) give the bits of the fp32 stack, which takes the
+    fp32 register kernel, and stay within tolerance of the oracle — whichever kernel the frame count selects for codes
+    (the 2-code register kernel or the shared-memory-parked one), one batch and two."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.datasets import StdSpec
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    for bits in (16, 8):
+        val, _, t = ct.synthetic.make_stack(n, 3, 72, 100, bits=bits, seed=100 * bits + n)
+        maxval = float(2 ** bits - 1)
+        codes = torch.round(val * maxval).to(torch.uint8 if bits == 8 else torch.uint16)
+        assert torch.equal(codes.to(torch.float32) / maxval, val)
+        camera = torch.stack([codes[:, 2], codes[:, 1], codes[:, 0]], dim=-1).contiguous()
+        std_tensor = val * 0.03 + 0.001
+        for std_codes, std_f32 in ((StdSpec("multiplier", 0.05), val * torch.tensor(0.05)), (std_tensor, std_tensor)):
+            for split in (None, 7):
+                def run(v, s, **kw):
+                    st = kernels.HdrMergeState()
+                    out = None
+                    for a, b in ([(0, n)] if split is None else [(0, split), (split, n)]):
+                        sb = s[a:b].contiguous().to(DEV) if torch.is_tensor(s) else s
+                        out = kernels.hdr_merge_update(st, v[a:b].contiguous().to(DEV), sb, t[a:b], theta, True, b == n,
+                                                       radiance_dtype=torch.float32, **kw)
+                    return out
+                want = run(val, std_f32)
+                if split is None:
+                    single = want
+                for name, got in (("planar", run(codes, std_codes)), ("camera", run(camera, std_codes, code_layout="hwc_bgr"))):
+                    assert torch.equal(got[0], want[0]), (bits, name, split)
+                    assert torch.equal(got[1], want[1]), (bits, name, split)
+        o_rad, o_sig = orc.hdr_merge(val.numpy(), std_tensor.numpy(), np.asarray(t, dtype=np.float64), theta.cpu().numpy())
+        assert max_rel(single[0].cpu().numpy(), o_rad) < TOL      # the one-batch merge with std as a tensor
+        assert max_rel(single[1].cpu().numpy(), o_sig) < TOL
+
+
 def test_hdr_merge_integer_ingest_against_reference_fixture(ct):
     """The 16-bit reference fixture fed as uint16 codes through the public API (DataLoader + StdSpec)."""
     from clair_torch_b200.datasets import ExposureStackDataset, StdSpec, custom_collate
