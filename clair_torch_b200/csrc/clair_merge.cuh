@@ -52,6 +52,7 @@ struct HdrParams {
 constexpr int kStdNone = 0, kStdTensor = 1, kStdMultiplier = 2, kStdConstant = 3;
 constexpr int kSrcF32 = 0, kSrcU8 = 1, kSrcU16 = 2, kSrcU8Hwc = 3, kSrcU16Hwc = 4;   // Hwc: interleaved BGR camera layout
 __host__ __device__ constexpr bool src_is_u8(int src) { return src == kSrcU8 || src == kSrcU8Hwc; }
+__host__ __device__ constexpr bool src_is_hwc(int src) { return src == kSrcU8Hwc || src == kSrcU16Hwc; }
 
 // One frame's VEC pixel values.  SRC = kSrcF32: the fp32 stack the reference hands over.  kSrcU8 / kSrcU16: the raw
 // integer codes, normalised in-register exactly like the reference's CPU transforms do it (CastTo(float32) then
@@ -100,7 +101,7 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int 
             if constexpr (SRC == kSrcU8Hwc) {
                 const uint16_t *src = reinterpret_cast<const uint16_t *>(static_cast<const uint8_t *>(p.val) +
                                                                          (static_cast<int64_t>(n) * p.stride + pix) * 3);
-                const uint32_t h0 = __ldcs(src), h1 = __ldcs(src + 1), h2 = __ldcs(src + 2);
+                const uint32_t h0 = __ldca(src), h1 = __ldca(src + 1), h2 = __ldca(src + 2);
                 const uint32_t w0 = h0 | (h1 << 16);          // bytes 0..3, h2 = bytes 4..5
                 const int j0 = 2 - c;
                 const uint32_t c0 = (w0 >> (8 * j0)) & 0xffu;                                   // byte j0
@@ -117,7 +118,7 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int 
         if constexpr (SRC == kSrcU8Hwc) {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(p.val) +
                                                                      (static_cast<int64_t>(n) * p.stride + pix) * 3);
-            const uint32_t w0 = __ldcs(src), w1 = __ldcs(src + 1), w2 = __ldcs(src + 2);
+            const uint32_t w0 = __ldca(src), w1 = __ldca(src + 1), w2 = __ldca(src + 2);
             const int j0 = 2 - c;                              // uniform over the block
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -141,7 +142,7 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int 
             if constexpr (SRC == kSrcU16Hwc) {
                 const uint32_t *src = reinterpret_cast<const uint32_t *>(static_cast<const uint16_t *>(p.val) +
                                                                          (static_cast<int64_t>(n) * p.stride + pix) * 3);
-                const uint32_t w0 = __ldcs(src), w1 = __ldcs(src + 1), w2 = __ldcs(src + 2);   // halfwords 0..5
+                const uint32_t w0 = __ldca(src), w1 = __ldca(src + 1), w2 = __ldca(src + 2);   // halfwords 0..5
                 const int j0 = 2 - c;
                 const uint32_t c0 = j0 == 0 ? (w0 & 0xffffu) : (j0 == 1 ? (w0 >> 16) : (w1 & 0xffffu));   // halfword j0
                 const uint32_t c1 = j0 == 0 ? (w1 >> 16) : (j0 == 1 ? (w2 & 0xffffu) : (w2 >> 16));       // halfword 3 + j0
@@ -157,7 +158,7 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int 
         if constexpr (SRC == kSrcU16Hwc) {
             const uint2 *src = reinterpret_cast<const uint2 *>(static_cast<const uint16_t *>(p.val) +
                                                                (static_cast<int64_t>(n) * p.stride + pix) * 3);
-            const uint2 a = __ldcs(src), b = __ldcs(src + 1), cc = __ldcs(src + 2);
+            const uint2 a = __ldca(src), b = __ldca(src + 1), cc = __ldca(src + 2);
             const int j0 = 2 - c;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -407,8 +408,22 @@ struct RowCursor {
 constexpr int kMaxFixedFrames = 8;         // integer ingest and the dark-field variant
 constexpr int kMaxFixedFramesF32 = 16;     // fp32 stacks, 2 pixels per thread: (R_n, Q_n) of 16 frames still fit the register file
 
+// Camera layout: the channel loop costs ~25 registers (per-frame addresses stay live across it).  Where the single-batch kernel
+// held three blocks per SM without it, it is held there (measured, c4 as uint16 camera codes: 1.45 ms at two blocks per SM,
+// 1.18 ms at three; 11 frames 3.06 -> 1.44 ms); the multi-batch variants would spill under that cap and keep the default.
+// 0 = no residency request (a request of 1 lifts ptxas' default register heuristics: the planar kernels grew from 64 to 102+
+// registers and lost a quarter of their speed).
+#ifndef CLAIR_FOLD_MIN_BLOCKS
+#define CLAIR_FOLD_MIN_BLOCKS 3
+#endif
+__host__ __device__ constexpr int fixed_min_blocks(int src, int vec, int nf, bool single) {
+    if (!src_is_hwc(src)) return 0;
+    if (single && ((vec == 2 && nf <= 13) || (vec == 4 && nf <= 5))) return CLAIR_FOLD_MIN_BLOCKS;
+    return ((vec == 2 && nf == 16) || (vec == 4 && nf == 8)) ? 2 : 0;       // these two would otherwise take 134 / 168 registers
+}
+
 template <int VEC, int NF, int STD, bool SINGLE, int SRC>
-__global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams p) {
+__global__ void __launch_bounds__(kBlock, fixed_min_blocks(SRC, VEC, NF, SINGLE)) hdr_merge_fixed_kernel(const HdrParams p) {
     constexpr bool HAS_STD = STD != 0;
     extern __shared__ float2 s_tab[];
     const int C = p.n_channels, L = p.lut;
@@ -419,23 +434,37 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
         for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
     }
     __syncthreads();
-    const int c = blockIdx.y;
+    // Camera layout (FOLD): the three channels of a pixel share their bytes, so a thread merges them in turn — the first
+    // channel's loads bring the codes into L1, the other two hit there (ld.global.ca).  One block per channel (gridDim.y)
+    // read the stack from DRAM three times (ncu: 3.89 GB for the 1.30 GB of a c4 stack of uint16 codes).
+    constexpr bool FOLD = src_is_hwc(SRC);
+    const int c_first = FOLD ? 0 : static_cast<int>(blockIdx.y), c_last = FOLD ? C : c_first + 1;
     const int64_t frame_stride = static_cast<int64_t>(C) * p.stride;
     const float lm1 = static_cast<float>(L - 1);
     const bool gaussian = p.gaussian != 0;
     const uint32_t n_items = static_cast<uint32_t>(p.plane / VEC);
     const uint32_t item_stride = gridDim.x * kBlock;
     const uint32_t first_item = blockIdx.x * kBlock + threadIdx.x;
-    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
+    RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, FOLD ? 0u : static_cast<uint32_t>(p.rows.base(c_first)), static_cast<uint32_t>(C));
+    // FOLD: the cursor follows the pixel alone; channel c adds (row base of c) mod C  (3 channels, checked by the host)
+    const uint32_t row_shift0 = FOLD ? static_cast<uint32_t>(p.rows.base(0)) % cur.C : 0u;
+    const uint32_t row_shift1 = FOLD ? static_cast<uint32_t>(p.rows.base(1)) % cur.C : 0u;
+    const uint32_t row_shift2 = FOLD ? static_cast<uint32_t>(p.rows.base(2)) % cur.C : 0u;
     const uint32_t tab_bias = curve_row_bias(s_tab);
     const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
 
     for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
         const uint32_t pix = item * VEC;
+#pragma unroll 1
+        for (int c = c_first; c < c_last; ++c) {
         const int64_t off = static_cast<int64_t>(c) * p.stride + pix;
         uint32_t bias[VEC];
         {
             uint32_t u = cur.u0;
+            if constexpr (FOLD) {
+                u += (c == 0) ? row_shift0 : ((c == 1) ? row_shift1 : row_shift2);
+                u = (u >= cur.C) ? u - cur.C : u;
+            }
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
                 bias[k] = tab_bias + u * row_bytes;
@@ -565,6 +594,7 @@ __global__ void __launch_bounds__(kBlock) hdr_merge_fixed_kernel(const HdrParams
             return acc;
         });
         }
+        }   // channel
     }
 }
 
@@ -861,16 +891,18 @@ struct MergeLaunch {
 };
 
 // persistent grid: a whole number of resident waves (blocks/SM from the occupancy calculator), split over the channels
+// `fold`: the register kernels on the camera layout loop over the channels inside the thread (gridDim.y = 1)
 template <typename K>
-int launch_merge_kernel(K kernel, const MergeLaunch &m) {
+int launch_merge_kernel(K kernel, const MergeLaunch &m, bool fold = false) {
     if (int rc = ensure_smem(kernel, m.smem)) return rc;
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, m.smem);
     // resident waves per persistent grid (measured): 2 for the register kernel up to 8 frames, 3 beyond and for the
     // shared-memory-parked kernel
     per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : ((m.parked || m.n_frames > kMaxFixedFrames) ? 3 : 2));
-    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(m.want_blocks, resident_blocks_per_channel(per_sm, m.n_channels)));
-    kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(m.n_channels)), kBlock, m.smem, m.stream>>>(m.p);
+    const int grid_channels = fold ? 1 : m.n_channels;
+    const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(m.want_blocks, resident_blocks_per_channel(per_sm, grid_channels)));
+    kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(grid_channels)), kBlock, m.smem, m.stream>>>(m.p);
     return 0;
 }
 
@@ -879,7 +911,7 @@ int launch_merge_kernel(K kernel, const MergeLaunch &m) {
 template <int V, int SRC>
 int launch_merge_by_std(const MergeLaunch &m) {
 #define CLAIR_FIXED_NF(NF, ST) \
-    (m.single ? launch_merge_kernel(hdr_merge_fixed_kernel<V, NF, ST, true, SRC>, m) : launch_merge_kernel(hdr_merge_fixed_kernel<V, NF, ST, false, SRC>, m))
+    (m.single ? launch_merge_kernel(hdr_merge_fixed_kernel<V, NF, ST, true, SRC>, m, src_is_hwc(SRC)) : launch_merge_kernel(hdr_merge_fixed_kernel<V, NF, ST, false, SRC>, m, src_is_hwc(SRC)))
 #define CLAIR_FIXED(ST)                                 \
     switch (m.n_frames) {                               \
         case 1: return CLAIR_FIXED_NF(1, ST);           \
@@ -935,7 +967,7 @@ int launch_merge_by_std(const MergeLaunch &m) {
 template <int SRC>
 int launch_merge_codes_wide(const MergeLaunch &m) {
 #define CLAIR_WIDE_NF(NF, ST) \
-    (m.single ? launch_merge_kernel(hdr_merge_fixed_kernel<2, NF, ST, true, SRC>, m) : launch_merge_kernel(hdr_merge_fixed_kernel<2, NF, ST, false, SRC>, m))
+    (m.single ? launch_merge_kernel(hdr_merge_fixed_kernel<2, NF, ST, true, SRC>, m, src_is_hwc(SRC)) : launch_merge_kernel(hdr_merge_fixed_kernel<2, NF, ST, false, SRC>, m, src_is_hwc(SRC)))
 #define CLAIR_WIDE(ST)                                \
     switch (m.n_frames) {                             \
         case 9: return CLAIR_WIDE_NF(9, ST);          \

@@ -30,8 +30,11 @@ def make_stack(n_frames: int, channels: int, height: int, width: int, bits: int 
     t = exposure_times(n_frames, first_exposure)
     maxval = float(2 ** bits - 1)
     val = torch.empty((n_frames, channels, height, width), dtype=torch.float32, device=dev)
+    # a tensor divisor: torch's CUDA division by a Python scalar multiplies by its reciprocal, which is not fl32(code / max)
+    # for ~3 % of the 16-bit codes; the CPU-made and device-made stacks of one seed must hold the same IEEE quotients
+    divisor = torch.tensor(maxval, dtype=torch.float32, device=dev)
     for k in range(n_frames):
         v = torch.clamp(scene * float(4.0 * t[k] / t[-1]), 0.0, 1.0) ** (1.0 / 2.2)
-        val[k] = torch.round(v * maxval) / maxval      # fp32 true division, as Normalize does
+        val[k] = torch.round(v * maxval) / divisor      # fp32 true division, as Normalize does
     std = None if std_multiplier is None else val * std_multiplier
     return val, std, t

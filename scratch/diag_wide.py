@@ -15,7 +15,7 @@ theta = ct.synthetic.reference_curve(3).to(dev)
 for n in [int(a) for a in sys.argv[1:]] or [16]:
     val, _, t = ct.synthetic.make_stack(n, 3, h, w, bits=16, seed=4321, device=dev)
     codes = torch.round(val * 65535.0).to(torch.int32).to(torch.uint16)
-    assert torch.equal(codes.to(torch.float32) / 65535.0, val)
+    assert torch.equal(codes.to(torch.float32) / torch.tensor(65535.0, device=dev), val)      # IEEE quotients (a tensor divisor)
     std = val * torch.tensor(0.05, device=dev)
 
     def merge(v, s, **kw):

@@ -8,7 +8,8 @@ from clair_torch_b200.common.statistics import WBOMeanVar
 from clair_torch_b200.training import linearity_loss_and_table_grad
 dev = "cuda:0"
 theta = ct.synthetic.reference_curve(3).to(dev)
-for n, h, w in ((5, 17, 23), (3, 16, 20), (9, 9, 14), (41, 6, 8)):
+only_wide = len(sys.argv) > 1 and sys.argv[1] == "wide"      # just the 9..16-frame integer ingest
+for n, h, w in () if only_wide else ((5, 17, 23), (3, 16, 20), (9, 9, 14), (41, 6, 8)):
     val, std, _ = ct.synthetic.make_stack(n, 3, h, w, bits=16, seed=n)
     t = 1e-3 * 1.2 ** np.arange(n)
     v, s = val.to(dev), std.to(dev)
@@ -39,6 +40,16 @@ for n, h, w in ((5, 17, 23), (3, 16, 20), (9, 9, 14), (41, 6, 8)):
     kernels.flat_field_correct_(rad, sig, torch.rand(3, h, w) + 0.5, torch.rand(3, h, w) * 0.01, True)
     hm = WBOMeanVar()
     hm.update_values(v, None, table=theta); hm.update_values(v, torch.rand_like(v))
+# integer ingest of 9..16 frames (the 2-code register kernel), planar and camera layout, exact-fit planes (no slack behind them)
+for n, h, w in ((9, 10, 14), (12, 6, 6), (16, 2, 2), (13, 30, 44)):
+    val, std, _ = ct.synthetic.make_stack(n, 3, h, w, bits=16, seed=n)
+    t = 1e-3 * 1.2 ** np.arange(n)
+    for scale, dt in ((65535, torch.uint16), (255, torch.uint8)):
+        codes = torch.round(val * scale).to(dt)
+        camera = torch.stack([codes[:, 2], codes[:, 1], codes[:, 0]], dim=-1).contiguous().to(dev)
+        for sp in (StdSpec("multiplier", 0.05), std.to(dev)):
+            kernels.hdr_merge_update(kernels.HdrMergeState(), codes.to(dev), sp, t, theta, True, True)
+            kernels.hdr_merge_update(kernels.HdrMergeState(), camera, sp, t, theta, True, True, code_layout="hwc_bgr")
 pen_grad = torch.zeros((3, 256), dtype=torch.float64, device=dev)
 kernels.curve_penalties(theta, 1.0, 1.0, 1.0, 1.0, pen_grad)
 torch.cuda.synchronize()
