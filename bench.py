@@ -258,11 +258,12 @@ def native_ingest_metrics(dev, lib, theta, t_host, cfg=None, reps=400, e2e_reps=
         launch_cam(k)
     torch.cuda.synchronize(dev)
     a.record(stream)
-    for k in range(100):
+    cam_reps = min(100, reps)
+    for k in range(cam_reps):
         launch_cam(k)
     b.record(stream)
     torch.cuda.synchronize(dev)
-    ms_cam = a.elapsed_time(b) / 100
+    ms_cam = a.elapsed_time(b) / cam_reps
     cam_h = cam[0].cpu().pin_memory()
     batch_cam = (torch.arange(N_FRAMES), cam_h, spec, {"exposure_time": torch.from_numpy(t_host)})
 
@@ -282,10 +283,10 @@ def native_ingest_metrics(dev, lib, theta, t_host, cfg=None, reps=400, e2e_reps=
         e2e_cam()
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    for _ in range(20):
+    for _ in range(e2e_reps):
         e2e_cam()
     torch.cuda.synchronize(dev)
-    e2e_cam_ms = (time.perf_counter() - t0) / 20 * 1e3
+    e2e_cam_ms = (time.perf_counter() - t0) / e2e_reps * 1e3
     out["camera_layout"] = {"config": "same codes as (N, H, W, 3) BGR camera buffers, CvToTorch fused into the load too",
                             "kernel_ms": ms_cam, "e2e_ms": e2e_cam_ms, "e2e_mpixel_frames_per_s": units / (e2e_cam_ms * 1e-3)}
     return out
@@ -686,7 +687,7 @@ def main():
             torch.cuda.empty_cache()
             c4 = res if args.workload == "c4" else r2
             extra["native_ingest_c4"] = native_ingest_metrics(dev, lib, c4["theta"], c4["t_host"], WORKLOADS["c4"], reps=30,
-                                                              e2e_reps=5, camera=False)
+                                                              e2e_reps=5, camera=True)
             torch.cuda.empty_cache()
             extra["dp_train_c5"] = dp_training_metrics(dev, 0, 1)
         res["e2e"]["host_cpus_bound"] = local_cpus
