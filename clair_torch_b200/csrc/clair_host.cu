@@ -82,6 +82,7 @@ extern "C" int clair_set_tuning(const char *key, int value) {
     if (k == "hdr_vec") g_tuning.hdr_vec = value;
     else if (k == "hdr_waves") g_tuning.hdr_waves = value;
     else if (k == "hdr_force_dynamic") g_tuning.hdr_force_dynamic = value;
+    else if (k == "hdr_prefetch") g_tuning.hdr_prefetch = value;
     else if (k == "stats_blocks_per_sm") g_tuning.stats_blocks_per_sm = value;
     else if (k == "grad_blocks_per_sm") g_tuning.grad_blocks_per_sm = value;
     else if (k == "grad_pix") g_tuning.grad_pix = value;

@@ -42,6 +42,7 @@ struct HdrParams {
     float code_rcp;           // fl32(1 / code_max) when normalise_code16's short division is exact for all 65536 codes, else 0
     int src;                  // kSrcF32 / kSrcU8 / kSrcU16 (read by the all-modes kernel only; the others take it as a template)
     int hwc;                  // integer codes are (n_frames, H, W, 3) BGR-interleaved instead of planar
+    int prefetch;             // camera-layout register kernels: 1 / 2 = prefetch the next trip's codes into L1 / L2, 0 = off
     const float *dark;        // fused dark-field mix (hdr_merge_dark_kernel): dark frames and their std, shaped like val
     const float *dark_std;
     DarkGeometry dg;
@@ -455,6 +456,20 @@ __global__ void __launch_bounds__(kBlock, fixed_min_blocks(SRC, VEC, NF, SINGLE)
 
     for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
         const uint32_t pix = item * VEC;
+        if constexpr (FOLD) {
+            // the codes of the next trip, requested while this trip's three channels are merged: their first use then finds
+            // them on the chip instead of waiting on DRAM at two or three blocks per SM
+            if (p.prefetch != 0 && item + item_stride < n_items) {
+                constexpr int kCodeBytes = src_is_u8(SRC) ? 1 : 2;
+                const char *next = static_cast<const char *>(p.val) + static_cast<int64_t>(pix + item_stride * VEC) * (3 * kCodeBytes);
+                const int64_t frame_bytes = p.stride * (3 * kCodeBytes);
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    if (p.prefetch == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(next + n * frame_bytes));
+                    else asm volatile("prefetch.global.L2 [%0];" ::"l"(next + n * frame_bytes));
+                }
+            }
+        }
 #pragma unroll 1
         for (int c = c_first; c < c_last; ++c) {
         const int64_t off = static_cast<int64_t>(c) * p.stride + pix;

@@ -9,7 +9,9 @@ import clair_torch_b200 as ct  # noqa: E402
 from clair_torch_b200.datasets import StdSpec  # noqa: E402
 
 dev = torch.device("cuda:0")
-ct._native.load()
+lib = ct._native.load()
+import os  # noqa: E402
+lib.clair_set_tuning(b"hdr_prefetch", int(os.environ.get("CLAIR_PREFETCH", "0")))     # camera layout: 1 = L1, 2 = L2
 theta = ct.synthetic.reference_curve(3).to(dev)
 for cfg in sys.argv[1:] or ["5:1080:1920:8"]:
     n, h, w, bits = (int(a) for a in cfg.split(":"))
