@@ -676,6 +676,32 @@ def test_hdr_merge_integer_ingest_9_to_16_frames(ct, n):
         assert max_rel(single[1].cpu().numpy(), o_sig) < TOL
 
 
+@pytest.mark.parametrize("code_max", [65535.0, 4095.0, 1023.0, 60000.0, 65536.0, 1e5])
+def test_hdr_merge_every_16_bit_code_normalises_like_the_ieee_division(ct, code_max):
+    """The register kernels divide 16-bit codes by code_max as q0 = a*rcp corrected by one exact residual
+    (normalise_code16, clair_merge.cuh); the reference's Normalize is an IEEE division.  Every one of the 65 536 codes, in
+    every frame (each frame a different permutation of them; 0..code_max for the narrower ranges), through the 4-code (3, 8 frames) and 2-code (9, 16 frames)
+    register kernels, planar and camera layout: the bits of the CPU-divided fp32 stack."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.datasets import StdSpec
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    idx = torch.arange(65536, dtype=torch.int64)
+    for n in (3, 8, 9, 16):
+        n_codes = min(65536, int(code_max) + 1)                  # a 12-bit camera delivers 0..4095
+        frames = [(((idx * (2 * k + 1) + 977 * c) % 65536) % n_codes).reshape(256, 256) for k in range(n) for c in range(3)]
+        codes = torch.stack(frames).reshape(n, 3, 256, 256).to(torch.int32).to(torch.uint16)
+        val = codes.to(torch.float32) / code_max                 # CastTo + Normalize on the CPU: a true division
+        t = ct.synthetic.exposure_times(n, 1e-3)
+        camera = torch.stack([codes[:, 2], codes[:, 1], codes[:, 0]], dim=-1).contiguous()
+        want = kernels.hdr_merge_update(kernels.HdrMergeState(), val.to(DEV), (val * torch.tensor(0.05)).to(DEV), t, theta, True, True,
+                                        radiance_dtype=torch.float32)
+        for buf, kw in ((codes, {}), (camera, {"code_layout": "hwc_bgr"})):
+            got = kernels.hdr_merge_update(kernels.HdrMergeState(), buf.to(DEV), StdSpec("multiplier", 0.05), t, theta, True, True,
+                                           radiance_dtype=torch.float32, code_max=code_max, **kw)
+            for g, w in zip(got, want):
+                assert torch.equal(torch.nan_to_num(g, nan=-1.0), torch.nan_to_num(w, nan=-1.0)), (n, kw)
+
+
 def test_hdr_merge_integer_ingest_against_reference_fixture(ct):
     """The 16-bit reference fixture fed as uint16 codes through the public API (DataLoader + StdSpec)."""
     from clair_torch_b200.datasets import ExposureStackDataset, StdSpec, custom_collate
