@@ -58,10 +58,12 @@ __host__ __device__ constexpr bool src_is_hwc(int src) { return src == kSrcU8Hwc
 // One frame's VEC pixel values.  SRC = kSrcF32: the fp32 stack the reference hands over.  kSrcU8 / kSrcU16: the raw
 // integer codes, normalised in-register exactly like the reference's CPU transforms do it (CastTo(float32) then
 // Normalize(max_val, min_val=0): an IEEE fp32 division, clair_torch/common/general_functions.py:378) — 8-bit codes
-// go through a 256-entry table of those quotients, 16-bit codes through __fdiv_rn.
+// go through a 256-entry table of those quotients, 16-bit codes through normalise_code16 (__fdiv_rn, or its exact
+// reciprocal form in the register kernels).
 // Interleaved camera layout (`hwc`): the codes are (n_frames, H, W, 3) in OpenCV's BGR order (p.stride pixels per frame) and channel c of the planar
 // tensor is byte / halfword 2 - c of each pixel — the CvToTorch transform (common/general_functions.py:315-336) folded
-// into the address.  Four pixels of one channel are 4 of the 12 codes a thread loads.
+// into the address.  Four pixels of one channel are 4 of the 12 codes a thread loads (two pixels: 2 of 6); the register kernels
+// merge the three channels in turn in one thread, so the codes leave DRAM once (FOLD, hdr_merge_fixed_kernel).
 __device__ __forceinline__ uint32_t pick_byte(uint32_t w0, uint32_t w1, uint32_t w2, int j) {      // byte j of a 12-byte window
     const uint32_t w = j < 4 ? w0 : (j < 8 ? w1 : w2);
     return (w >> (8 * (j & 3))) & 0xffu;

@@ -710,7 +710,7 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
     const bool wide = src != kSrcF32 && fixed && n_frames > kMaxFixedFrames;
     if (wide) vec = 2;
     // measured on B200 (profiles/): with fp32 input 2 pixels per thread keep the fixed-N kernel at 40 registers
-    // (6 blocks/SM); 4 pixels per thread need 64.  Integer ingest always takes 4 codes per load.
+    // (6 blocks/SM); 4 pixels per thread need 64.  Integer ingest takes 4 codes per load up to 8 frames, 2 from 9 to 16.
     // 9 .. ~40 frames: (R_n, Q_n) parked in shared memory, 2 pixels per thread (1 when H*W is odd)
     bool parked = false;
     if (src != kSrcF32) {
