@@ -254,6 +254,45 @@ def linearize(val, std, theta, flat_offset=0, mode="linear"):
 
 
 # ----------------------------------------------------------------------------------------------
+# Image ingest: what the reference's transform chain and datasets do to a camera buffer before the hot path sees it
+# ----------------------------------------------------------------------------------------------
+def cv_to_torch(x):
+    """CvToTorch (common/transforms.py:67-84, common/general_functions.py:315-336): an OpenCV image (H,W) or (H,W,3) BGR
+    becomes (1,H,W) or (3,H,W) RGB."""
+    x = np.asarray(x)
+    if x.ndim == 2:
+        return x[None]
+    if x.ndim == 3 and x.shape[2] == 3:
+        return np.transpose(x[:, :, [2, 1, 0]], (2, 0, 1))
+    raise ValueError(f"Unexpected image shape: {x.shape}")
+
+
+def cast_normalize(codes, max_val, min_val=0.0, target_range=(0.0, 1.0)):
+    """CastTo(float32) then Normalize(max_val, min_val) (common/transforms.py:107-131,161-183;
+    common/general_functions.py:373-388): ((x - min) / (max - min)) * span + target_min, every step an fp32 op with the
+    Python scalars rounded to fp32 — for min 0 and the default range that is fl32(code) / fl32(max), an IEEE division."""
+    x = np.asarray(codes).astype(F32)
+    denominator = max_val - min_val                      # Python floats (:376)
+    if denominator == 0:
+        raise ValueError("Normalization range is zero (min == max); cannot normalize.")
+    x = (x - F32(min_val)) / F32(denominator)
+    lo, hi = target_range
+    return (x * F32(hi - lo) + F32(lo)).astype(F32)
+
+
+def missing_std(val, mode, value):
+    """The std image a dataset makes up when no std file exists (datasets/base.py:35,128-133): None, a constant plane, or
+    val * fl32(value)."""
+    if mode == "none":
+        return None
+    if mode == "constant":
+        return np.full_like(np.asarray(val, dtype=F32), F32(value))
+    if mode == "multiplier":
+        return (np.asarray(val, dtype=F32) * F32(value)).astype(F32)
+    raise ValueError(f"Unsupported MissingStdMode: {mode}")
+
+
+# ----------------------------------------------------------------------------------------------
 # Exposure pairs, validity mask, pair loss statistics
 # ----------------------------------------------------------------------------------------------
 def exposure_pairs(exposure, threshold=None):

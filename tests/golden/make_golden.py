@@ -20,6 +20,8 @@ times, the ICRF table) and what the reference returned for them:
   trainstep_*.npz    the step body of train_icrf (clair_torch/training/icrf_training.py:96-156),
                      rebuilt from the reference's own functions because train_icrf
                      itself crashes on CPU at :92
+  ingest_*.npz       CvToTorch + CastTo + Normalize on a camera buffer of integer codes, and the synthesised std
+                     (clair_torch/common/transforms.py:67-190, clair_torch/datasets/base.py:128-133)
   known_answers.npz  the known-answer vectors the reference's own unit tests pin
                      (tests/unit/common/test_general_functions.py:292-391,
                       tests/unit/common/test_statistics.py, tests/unit/training/test_losses.py)
@@ -557,9 +559,33 @@ def gen_known_answers():
     save("known_answers", **out)
 
 
+def gen_ingest():
+    """The transform chain in front of the hot path: a camera buffer (H, W, 3) BGR of integer codes through the
+    reference's CvToTorch -> CastTo(float32) -> Normalize(max_val, min_val=0) (common/transforms.py), and the std image its datasets
+    synthesise when no std file exists (datasets/base.py:35,128-133 — the two expressions are repeated here because the dataset
+    class only runs on files)."""
+    from clair_torch.common.transforms import CastTo, CvToTorch, Normalize
+    rng = np.random.default_rng(2024)
+    for bits, dtype, tdtype in ((8, np.uint8, torch.uint8), (16, np.uint16, torch.uint16)):
+        for max_val in ((255,) if bits == 8 else (65535, 4095)):
+            n_codes = max_val + 1                         # every code of the range, in each channel, in a different order
+            side = {256: 32, 4096: 64, 65536: 256}[n_codes]
+            planes = [rng.permutation(np.arange(side * side) % n_codes).reshape(side, side) for _ in range(3)]
+            camera = np.stack(planes, axis=-1).astype(dtype)  # (H, W, 3), OpenCV's B, G, R
+            x = torch.from_numpy(camera.astype(np.int32)).to(tdtype) if bits == 16 else torch.from_numpy(camera)
+            for tf in (CvToTorch(), CastTo(data_type=torch.float32), Normalize(max_val=max_val, min_val=0)):
+                x = tf(x)
+            shared_std_tensor = torch.tensor(0.05)        # datasets/base.py:35
+            std_mult = x * shared_std_tensor              # :133
+            std_const = torch.tensor(0.01).expand_as(x)   # :131
+            save(f"ingest_u{bits}_max{max_val}", camera=camera, max_val=np.float64(max_val), val=x.contiguous(),
+                 std_multiplier=std_mult.contiguous(), std_constant=std_const.contiguous(), multiplier=np.float64(0.05),
+                 constant=np.float64(0.01))
+
+
 if __name__ == "__main__":
     generators = {"known_answers": gen_known_answers, "forward": gen_forward, "catmull": gen_catmull, "frame_stats": gen_frame_stats,
                   "artefacts": gen_artefacts, "hdr": gen_hdr, "linearize": gen_linearize, "linearity": gen_linearity,
-                  "trainstep": gen_trainstep, "modes": gen_modes}
+                  "trainstep": gen_trainstep, "modes": gen_modes, "ingest": gen_ingest}
     for key in (sys.argv[1:] or list(generators)):       # e.g. `make_golden.py modes` regenerates one family only
         generators[key]()

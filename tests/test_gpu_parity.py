@@ -702,6 +702,32 @@ def test_hdr_merge_every_16_bit_code_normalises_like_the_ieee_division(ct, code_
                 assert torch.equal(torch.nan_to_num(g, nan=-1.0), torch.nan_to_num(w, nan=-1.0)), (n, kw)
 
 
+@pytest.mark.parametrize("name", golden_names("ingest_"))
+def test_hdr_merge_camera_codes_against_reference_transform_fixture(ct, name):
+    """The camera buffers of the ingest fixtures (every code of the range) handed over untouched — code_layout hwc_bgr, code_max,
+    StdSpec — merge to the bits of the frames the reference's CvToTorch + CastTo + Normalize made of them, with the std images
+    its datasets synthesise."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.datasets import StdSpec
+    z = golden(name)
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    shifts = (0, 5, 11, 2, 7, 13, 3, 9, 1, 6)                   # frame k = the fixture's frame rolled along the width
+    for n in (3, 10):
+        t = ct.synthetic.exposure_times(n, 1e-3)
+        camera = torch.from_numpy(np.stack([np.roll(z["camera"], s, axis=1) for s in shifts[:n]]).astype(np.int32))
+        camera = camera.to(torch.uint8 if z["camera"].dtype == np.uint8 else torch.uint16)
+
+        def frames(key):
+            return torch.from_numpy(np.stack([np.roll(z[key], s, axis=2) for s in shifts[:n]]))
+        for spec, std_key in ((StdSpec("multiplier", float(z["multiplier"])), "std_multiplier"),
+                              (StdSpec("constant", float(z["constant"])), "std_constant")):
+            want = kernels.hdr_merge_update(kernels.HdrMergeState(), frames("val").to(DEV), frames(std_key).to(DEV), t, theta, True, True,
+                                            radiance_dtype=torch.float32)
+            got = kernels.hdr_merge_update(kernels.HdrMergeState(), camera.to(DEV), spec, t, theta, True, True,
+                                           radiance_dtype=torch.float32, code_max=float(z["max_val"]), code_layout="hwc_bgr")
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]), (n, std_key)
+
+
 def test_hdr_merge_integer_ingest_against_reference_fixture(ct):
     """The 16-bit reference fixture fed as uint16 codes through the public API (DataLoader + StdSpec)."""
     from clair_torch_b200.datasets import ExposureStackDataset, StdSpec, custom_collate

@@ -279,3 +279,27 @@ def test_artefact_corrections(name):
             lin, v = orc.flat_field_correct(lin, v, z["flat"][0], z["flat_std"][0], False)
         assert max_rel(lin[0], z["linearized"][i]) < 2e-6
         assert max_rel(np.sqrt(v[0]), z["lin_sigma"][i]) < TOL
+
+
+@pytest.mark.parametrize("name", golden_names("ingest_"))
+def test_ingest_chain_bit_exact(name):
+    """CvToTorch + CastTo(float32) + Normalize(max, 0) on a camera buffer holding every code of its range, and
+    the std the datasets synthesise — the oracle's restatement against what the reference's transforms returned, to the bit.
+    For min 0 and the default target range the chain is fl32(code) / fl32(max): the quotient the CUDA ingest kernels form."""
+    z = golden(name)
+    val = orc.cast_normalize(orc.cv_to_torch(z["camera"]), float(z["max_val"]))
+    assert val.dtype == np.float32 and np.array_equal(val, z["val"])
+    planar_codes = orc.cv_to_torch(z["camera"]).astype(np.float32)
+    assert np.array_equal(planar_codes / np.float32(z["max_val"]), z["val"])
+    assert np.array_equal(orc.missing_std(val, "multiplier", float(z["multiplier"])), z["std_multiplier"])
+    assert np.array_equal(orc.missing_std(val, "constant", float(z["constant"])), z["std_constant"])
+    assert orc.missing_std(val, "none", 0.0) is None
+    with pytest.raises(ValueError):
+        orc.cast_normalize(z["camera"], 5.0, 5.0)
+    with pytest.raises(ValueError):
+        orc.cv_to_torch(np.zeros((4, 4, 2), dtype=np.uint8))
+    assert orc.cv_to_torch(np.zeros((4, 5), dtype=np.uint8)).shape == (1, 4, 5)
+    # a non-trivial range exercises the general form: ((x - min) / (max - min)) * span + target_min in fp32
+    x = orc.cv_to_torch(z["camera"]).astype(np.float32)
+    want = ((x - np.float32(3.0)) / np.float32(float(z["max_val"]) - 3.0)) * np.float32(2.0) + np.float32(-1.0)
+    assert np.array_equal(orc.cast_normalize(orc.cv_to_torch(z["camera"]), float(z["max_val"]), 3.0, (-1.0, 1.0)), want)
