@@ -121,6 +121,7 @@ def cpu_oracle_rate(cfg, rows, repeats=1):
     first `rows` rows of one stack of the workload.  Returns (rate, seconds per merge, threads)."""
     import clair_torch_b200.synthetic as syn
     from oracle import c_oracle as corc
+    threads = corc.use_all_host_threads()                             # torchrun exports OMP_NUM_THREADS=1
     val, std, t = syn.make_stack(cfg["n"], cfg["c"], rows, cfg["w"], bits=cfg["bits"], seed=cfg["seed"])
     theta = syn.reference_curve(cfg["c"], LUT).numpy()
     v, s = val.numpy(), std.numpy()
@@ -129,45 +130,149 @@ def cpu_oracle_rate(cfg, rows, repeats=1):
     for _ in range(repeats):
         corc.hdr_merge(v, s, t, theta, True)
     dt = (time.perf_counter() - t0) / repeats
-    return cfg["n"] * rows * cfg["w"] / dt / 1e6, dt, corc.max_threads()
+    return cfg["n"] * rows * cfg["w"] / dt / 1e6, dt, threads
 
 
-REFERENCE_NOTE = ("the reference itself is pure Python/torch and cannot travel to the GPU box; its own CPU path measured in "
-                  "the build container was 5.8 Mpixel*frames/s on 8 cores (BASELINE.md section 2)")
+def shared_config(cfg):
+    """The `config` object both arms print (identical, so the driver can pair the lines)."""
+    return {"workload": cfg["label"],
+            "stacks_per_rank_rotated": cfg["n_sets"],
+            "l2": f"{cfg['n_sets']} distinct stacks of {2 * cfg['n'] * cfg['c'] * cfg['h'] * cfg['w'] * 4 / 1e6:.0f} MB rotated "
+                  "per step, each far larger than the 126 MB L2",
+            "sharding": "by stack, one rank per GPU, no data-path collective",
+            "cpu_arm": "the reference arm / cpu_baseline run the reference's own compute_hdr_image (torch CPU, all host threads) "
+                       "on a band of rows of one stack per step; the metric is a throughput, so the band size cancels"}
+
+
+class ReferenceHdr:
+    """The reference's own compute_hdr_image (oracle/_ref, torch CPU, every host thread) on rows 0..rows of one stack of
+    the workload; falls back to the C/OpenMP port only when oracle/_ref did not travel."""
+
+    def __init__(self, cfg, rows):
+        import clair_torch_b200.synthetic as syn
+        from oracle import reference_runner as rr
+        self.cfg, self.rows = cfg, rows
+        val, std, self.t = syn.make_stack(cfg["n"], cfg["c"], rows, cfg["w"], bits=cfg["bits"], seed=cfg["seed"])
+        self.v, self.s = val.numpy(), std.numpy()
+        self.theta = syn.reference_curve(cfg["c"], LUT).numpy()
+        self.kind = "reference" if rr.available() else "port"
+        if self.kind == "reference":
+            self.threads = rr.use_all_host_threads()
+            self.rr = rr
+        else:
+            from oracle import c_oracle as corc
+            self.threads = corc.use_all_host_threads()
+            self.corc = corc
+        self.units = cfg["n"] * rows * cfg["w"] / 1e6
+
+    def step(self):
+        """One merge of the band; returns seconds."""
+        if self.kind == "reference":
+            return self.rr.hdr_merge(self.v, self.s, self.t, self.theta, True)[2]
+        t0 = time.perf_counter()
+        self.corc.hdr_merge(self.v, self.s, self.t, self.theta, True)
+        return time.perf_counter() - t0
+
+    def describe(self, steps):
+        what = ("clair_torch.inference.hdr_merge.compute_hdr_image of the unmodified reference (oracle/_ref), torch CPU"
+                if self.kind == "reference" else "C/OpenMP oracle port of the reference algorithm (oracle/_ref absent)")
+        return (f"{steps} merges of rows 0..{self.rows} of {self.cfg['h']} of one stack ({self.units:.2f} Mpixel*frames each, "
+                f"{self.rows / self.cfg['h']:.4f} of a stack); {what}, {self.threads} threads")
+
+
+def reference_rows(cfg, budget_s, n_steps):
+    """Rows of one stack per step so that n_steps steps of the reference take about budget_s (calibrated on a thin band)."""
+    probe_rows = 16
+    probe = ReferenceHdr(cfg, probe_rows)
+    probe.step()
+    dt = min(probe.step(), probe.step())
+    rows = int(probe_rows * budget_s / max(dt * max(n_steps, 1), 1e-9))
+    # >= 32 rows keeps torch's per-op overhead small; <= 400 rows of a 24 MP frame keeps the reference's temporaries < 30 GB
+    cap = 400 if cfg["w"] > 2000 else cfg["h"]
+    return max(32, min(cfg["h"], cap, rows))
+
+
+def cpu_baseline_hdr(cfg, budget_s=12.0, steps=3):
+    """cpu_baseline object for the HDR merge: the reference itself, with the C/OpenMP port as a second stated number."""
+    rows = reference_rows(cfg, budget_s, steps + 1)
+    ref = ReferenceHdr(cfg, rows)
+    ref.step()
+    dts = sorted(ref.step() for _ in range(steps))
+    dt = dts[len(dts) // 2]
+    port_rate, port_dt, port_threads = cpu_oracle_rate(cfg, min(cfg["h"], 400), repeats=3)
+    return {"value": ref.units / dt, "unit": "Mpixel*frames/s", "cores": ref.threads, "kind": ref.kind,
+            "sample": ref.describe(steps) + f", median {dt:.3f} s per merge",
+            "port": {"value": port_rate, "unit": "Mpixel*frames/s", "cores": port_threads,
+                     "what": "oracle/clair_oracle.c (C + OpenMP restatement, closed-form variance), the checker the parity "
+                             "tests use at full size; reported for scale only"}}
 
 
 def run_reference(args, rank, world):
-    """`--impl reference`: the CPU implementation of the path (oracle port, all host threads), K timed steps."""
+    """`--impl reference`: the reference's own CPU implementation of the path, K timed steps on rank 0."""
     if rank != 0:
         return
-    import clair_torch_b200.synthetic as syn
-    from oracle import c_oracle as corc
     cfg = WORKLOADS[args.workload]
-    # size the per-step sample so that K steps stay within ~2 minutes: calibrate on a thin band of rows
-    probe = 64
-    _, dt_probe, threads = cpu_oracle_rate(cfg, probe)
-    budget_s = 100.0
-    rows = int(max(8, min(cfg["h"], 1000, probe * budget_s / max(dt_probe * max(args.steps + args.warmup, 1), 1e-9))))
-    val, std, t = syn.make_stack(cfg["n"], cfg["c"], rows, cfg["w"], bits=cfg["bits"], seed=cfg["seed"])
-    theta = syn.reference_curve(cfg["c"], LUT).numpy()
-    v, s = val.numpy(), std.numpy()
+    rows = reference_rows(cfg, 75.0, args.steps + args.warmup)
+    ref = ReferenceHdr(cfg, rows)
     for _ in range(args.warmup):
-        corc.hdr_merge(v, s, t, theta, True)
+        ref.step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        corc.hdr_merge(v, s, t, theta, True)
+        ref.step()
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    value = cfg["n"] * rows * cfg["w"] / dt / 1e6
-    sample = (f"rows 0..{rows} of {cfg['h']} of one {args.workload} stack per step ({rows / cfg['h']:.3f} of the workload), "
-              f"C/OpenMP oracle port of the reference algorithm; {REFERENCE_NOTE}")
+    value = ref.units / dt
+    sample = ref.describe(args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel*frames/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["label"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "Mpixel*frames/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": shared_config(cfg),
+            "cpu_baseline": {"value": value, "unit": "Mpixel*frames/s", "cores": ref.threads, "kind": ref.kind, "sample": sample},
             "e2e": {"value": value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def cpu_baseline_train_c2(budget_rows=120):
+    """The reference's train-step body (icrf_training.py:105-156, oracle/reference_runner.TrainStep) on a band of rows of
+    the c2 stack; a step's cost is linear in the pixel count, so the full-frame figure is the stated extrapolation."""
+    import clair_torch_b200.synthetic as syn
+    from oracle import reference_runner as rr
+    if not rr.available():
+        return None
+    threads = rr.use_all_host_threads()
+    val, std, t = syn.make_stack(10, CHANNELS, budget_rows, WIDTH, bits=8, seed=2345)
+    step = rr.TrainStep(val.numpy(), std.numpy(), t, channels=CHANNELS, relative=True, unc_weighting=False, alpha=10.0, beta=1.0,
+                        gamma=1.0, delta=1.0, threshold=0.25)
+    step()                                   # step 0 only connects the table to the parameters (SURVEY.md Q5)
+    dts = sorted(step()[3] for _ in range(2))
+    dt = dts[0]
+    full = dt * HEIGHT / budget_rows
+    return {"value": 1.0 / full, "unit": "steps/s", "cores": threads, "kind": "reference",
+            "measured_s_per_step_on_sample": dt, "extrapolated_s_per_full_step": full,
+            "sample": f"rows 0..{budget_rows} of {HEIGHT} of the c2 stack (10x3x{budget_rows}x{WIDTH}, P=17), step body of "
+                      "clair_torch/training/icrf_training.py:105-156 from the reference's own functions, torch CPU; the full "
+                      "frame needs ~29 GB of (P,C,H,W) temporaries, so the per-step time is scaled by H/rows (labelled "
+                      "extrapolation, BASELINE.md section 3)"}
+
+
+def cpu_baseline_linearity_c3(rows=96):
+    """The reference's measure_linearity on a band of rows of the c3 stack (the full 4K stack needs ~250 GB of temporaries)."""
+    import clair_torch_b200.synthetic as syn
+    from oracle import reference_runner as rr
+    if not rr.available():
+        return None
+    threads = rr.use_all_host_threads()
+    val, std, t = syn.make_stack(16, CHANNELS, rows, 3840, bits=16, seed=3456)
+    theta = syn.reference_curve(CHANNELS, LUT).numpy()
+    v, s = val.numpy(), std.numpy()
+    rr.measure_linearity(v[:, :, :8], s[:, :, :8], t, theta, True, True)
+    dt = rr.measure_linearity(v, s, t, theta, True, True)[4]
+    full = dt * 2160 / rows
+    return {"value": full * 1e3, "unit": "ms", "cores": threads, "kind": "reference", "measured_s_on_sample": dt,
+            "extrapolated_ms_full": full * 1e3,
+            "sample": f"rows 0..{rows} of 2160 of the c3 stack (16x3x{rows}x3840, P=29), clair_torch.inference.measure_linearity "
+                      "of the unmodified reference, torch CPU; scaled by H/rows (labelled extrapolation: the full stack would "
+                      "need ~250 GB)"}
 
 
 def native_ingest_metrics(dev, lib, theta, t_host, cfg=None, reps=400, e2e_reps=20, camera=True):
@@ -662,14 +767,9 @@ def main():
         dp = dp_training_metrics(dev, rank, world)       # collective: every rank takes part
     if rank == 0:
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            rows = min(cfg["h"], 1080 if args.workload == "c1" else 400)
-            reps = 20 if args.workload == "c1" else 10
-            rate, dt, threads = cpu_oracle_rate(cfg, rows, repeats=reps)
-            cpu = {"value": rate, "unit": "Mpixel*frames/s", "cores": threads, "kind": "port",
-                   "sample": f"{reps} merges of rows 0..{rows} of {cfg['h']} of one {args.workload} stack "
-                             f"({cfg['n'] * rows * cfg['w'] / 1e6:.1f} Mpixel*frames each), C/OpenMP oracle port, "
-                             f"{dt:.3f} s per merge; " + REFERENCE_NOTE}
+        if not args.no_cpu_baseline:
+            # bounded sample on rank 0 (the other ranks idle at the final barrier); printed at every N
+            cpu = cpu_baseline_hdr(cfg, budget_s=12.0 if world == 1 else 6.0)
         extra = None
         if world > 1 and dp is not None:
             extra = {"dp_train_c5": dp}
@@ -683,6 +783,14 @@ def main():
                                            "e2e": {k: v for k, v in r2["e2e"].items() if k != "api"}}
             c1 = res if args.workload == "c1" else r2
             extra.update(secondary_metrics(dev))
+            if not args.no_cpu_baseline:
+                extra["icrf_train_c2"]["cpu_baseline"] = cpu_baseline_train_c2()
+                extra["linearity_c3"]["cpu_baseline"] = cpu_baseline_linearity_c3()
+                for key, unit in (("icrf_train_c2", "steps_per_s"), ("linearity_c3", "ms")):
+                    cb = extra[key]["cpu_baseline"]
+                    if cb is not None:
+                        extra[key]["speedup_vs_cpu_reference"] = (extra[key]["steps_per_s"] / cb["value"] if unit == "steps_per_s"
+                                                                  else cb["value"] / extra[key]["ms"])
             extra["native_ingest_c1"] = native_ingest_metrics(dev, lib, c1["theta"], c1["t_host"])
             torch.cuda.empty_cache()
             c4 = res if args.workload == "c4" else r2
@@ -695,10 +803,7 @@ def main():
             "metric": METRIC, "value": res["value"], "unit": "Mpixel*frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["label"], "stacks_per_rank_rotated": res["n_sets"],
-                       "l2": f"{res['n_sets']} distinct stacks of {res['stack_bytes'] / 1e6:.0f} MB rotated per step, each far "
-                             "larger than the 126 MB L2",
-                       "sharding": "by stack, one rank per GPU, no data-path collective"},
+            "config": shared_config(cfg),
             "roofline": res["roofline"],
             "cpu_baseline": cpu,
             "e2e": res["e2e"],

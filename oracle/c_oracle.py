@@ -36,6 +36,19 @@ def max_threads() -> int:
     return int(lib().oracle_max_threads())
 
 
+def use_all_host_threads() -> int:
+    """torch.distributed.run exports OMP_NUM_THREADS=1 and launchers may pin a rank to a few cores: a CPU baseline
+    that is meant to use the whole host undoes both.  Returns the OpenMP thread count in effect."""
+    n = os.cpu_count() or 1
+    try:
+        os.sched_setaffinity(0, range(n))
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    lib().oracle_set_threads(int(n))
+    return max_threads()
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(_c.c_void_p)
 

@@ -402,3 +402,13 @@ int oracle_max_threads(void) {
     return 1;
 #endif
 }
+
+/* torch.distributed.run exports OMP_NUM_THREADS=1: bench.py's CPU legs ask for the host's cores explicitly */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    extern void omp_set_num_threads(int);
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
