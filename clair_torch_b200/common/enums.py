@@ -6,7 +6,7 @@ class InterpMode(Enum):
     """How ICRFModelBase.forward evaluates the (C, L) table."""
     LOOKUP = auto()   # nearest sample, round-half-even, no gradient
     LINEAR = auto()   # two-tap interpolation (default everywhere in the reference)
-    CATMULL = auto()  # four-tap Catmull-Rom (model forward / backward only; the fused merge and pair kernels are LINEAR)
+    CATMULL = auto()  # four-tap Catmull-Rom
 
 
 class VarianceMode(Enum):

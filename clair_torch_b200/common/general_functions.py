@@ -8,6 +8,7 @@ tensor-returning forms are NOT used by compute_hdr_image / measure_linearity / t
 from typing import Optional
 
 import torch
+from .errors import ArgumentTypeError
 
 
 def get_valid_exposure_pairs(increasing_exposure_values: torch.Tensor,
@@ -18,9 +19,9 @@ def get_valid_exposure_pairs(increasing_exposure_values: torch.Tensor,
     dtype of the exposures), on the device of the exposures.
     """
     if not isinstance(increasing_exposure_values, torch.Tensor):
-        raise TypeError("increasing_exposure_values must be a torch.Tensor")
+        raise ArgumentTypeError("increasing_exposure_values must be a torch.Tensor")
     if exposure_ratio_threshold is not None and not isinstance(exposure_ratio_threshold, (int, float)):
-        raise TypeError("exposure_ratio_threshold must be a float or None")
+        raise ArgumentTypeError("exposure_ratio_threshold must be a float or None")
     t = increasing_exposure_values
     n = t.shape[0]
     i_idx, j_idx = torch.triu_indices(n, n, offset=1)

@@ -12,6 +12,7 @@ import torch
 
 from .. import _native
 from .enums import VarianceMode
+from .errors import ArgumentTypeError
 
 
 class WBOMean:
@@ -19,7 +20,7 @@ class WBOMean:
         if isinstance(dim, int):
             dim = (dim,)
         else:
-            raise TypeError(f"Expected dim as int or tuple of int, got {type(dim)}")     # as statistics.py:24-27
+            raise ArgumentTypeError(f"Expected dim as int or tuple of int, got {type(dim)}")     # as statistics.py:24-27
         if dim != (0,):
             raise NotImplementedError("the kernel-backed running statistics reduce over the frame dimension (dim=0)")
         self._dim = dim

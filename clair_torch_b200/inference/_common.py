@@ -5,11 +5,12 @@ import torch
 
 from ..common.enums import InterpMode
 from ..models.base import ICRFModelBase
+from ..common.errors import ArgumentTypeError
 
 
 def as_device(device) -> torch.device:
     if not isinstance(device, (str, torch.device)):
-        raise TypeError(f"device must be a str or torch.device, got {type(device)}")
+        raise ArgumentTypeError(f"device must be a str or torch.device, got {type(device)}")
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError(f"clair_torch_b200 runs on CUDA devices only (got device={device!r}); there is no CPU path")
@@ -42,7 +43,7 @@ def model_table(icrf_model: Optional[ICRFModelBase], device):
     if icrf_model is None:
         return None, _NATIVE_MODE[InterpMode.LINEAR]
     if not isinstance(icrf_model, ICRFModelBase):
-        raise TypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
+        raise ArgumentTypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
     return icrf_model.icrf.detach().to(device=device, dtype=torch.float32), _NATIVE_MODE[icrf_model.interpolation_mode]
 
 
@@ -51,7 +52,7 @@ def linear_table(icrf_model: Optional[ICRFModelBase], device) -> Optional[torch.
     if icrf_model is None:
         return None
     if not isinstance(icrf_model, ICRFModelBase):
-        raise TypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
+        raise ArgumentTypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
     if icrf_model.interpolation_mode is not InterpMode.LINEAR:
         raise NotImplementedError("the fused B200 kernels evaluate the ICRF in InterpMode.LINEAR (the reference default); "
                                   f"got {icrf_model.interpolation_mode}")
@@ -62,7 +63,7 @@ def check_artefact_dataset(name, ds):
     """Artefact datasets are duck-typed: the reference's Flat/DarkFieldArtefactMapDataset (file matching is host
     bookkeeping, out of scope) or datasets.InMemoryArtefactDataset — anything with get_matching_artefact_images."""
     if ds is not None and not hasattr(ds, "get_matching_artefact_images"):
-        raise TypeError(f"{name} must provide get_matching_artefact_images(frame_settings_list)")
+        raise ArgumentTypeError(f"{name} must provide get_matching_artefact_images(frame_settings_list)")
 
 
 def matching_dark_frames(main_dataset, dark_field_dataset, index_batch, device):

@@ -1,4 +1,5 @@
 """HDR merge driver — call-compatible with clair_torch/inference/hdr_merge.py:19-155."""
+import collections
 from typing import Callable, Optional
 
 import torch
@@ -8,6 +9,7 @@ from .. import kernels
 from ..models.base import ICRFModelBase
 from ._common import (as_device, check_artefact_dataset, matching_dark_frames, model_table, normalise_transforms,
                       stage_batch)
+from ..common.errors import ArgumentTypeError
 
 
 def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFModelBase] = None,
@@ -28,7 +30,8 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
     the copy engine moves the next band of every frame to the device while the kernel merges the current one
     (`staged=False`: the kernel reads the host memory itself over PCIe instead); pageable batches are copied to the
     device first like the reference does.  `host_out=(radiance, sigma)`, two pinned (C,H,W) host tensors, makes the
-    kernel write the results straight to host memory (they are then what is returned).
+    kernel write the results straight to host memory (they are then what is returned, and the call synchronises the
+    stream before returning them, as it does whenever it read a host-resident batch in place).
 
     Models in any InterpMode are accepted: LINEAR (the reference default) runs the fused fast kernels, LOOKUP and
     CATMULL an all-modes kernel.  As in the reference, a LOOKUP model has no derivative with respect to the image, so
@@ -43,9 +46,9 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
     (N, H, W, 3) BGR — `cv2.imread` output, stacked — and CvToTorch is fused into the load as well.
     """
     if not isinstance(dataloader, DataLoader):
-        raise TypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
+        raise ArgumentTypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
     if weight_fn is not None and not callable(weight_fn):
-        raise TypeError("weight_fn must be callable or None")
+        raise ArgumentTypeError("weight_fn must be callable or None")
     dev = as_device(device)
     check_artefact_dataset("flat_field_dataset", flat_field_dataset)
     check_artefact_dataset("dark_field_dataset", dark_field_dataset)
@@ -55,6 +58,10 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
 
     state = kernels.HdrMergeState()
     result = None
+    # Page-locked host batches are read by the kernels / the copy engine through raw pointers, which torch's caching host
+    # allocator knows nothing about: every such batch is kept alive here until an event recorded behind its last reader
+    # has completed (a DataLoader pin thread would otherwise get the block back and overwrite it mid-read).
+    in_flight = collections.deque()
     batches = iter(dataloader)
     current = next(batches, None)
     while current is not None:
@@ -97,6 +104,12 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
                                           code_max=code_max, interp_mode=interp_mode,
                                           staged=staged if not images.is_cuda else None, dark=fused_dark,
                                           code_layout=code_layout)
+        if not images.is_cuda:
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+            in_flight.append((done, images, stds))
+            while in_flight and in_flight[0][0].query():
+                in_flight.popleft()
         current = upcoming
     if result is None:
         raise ValueError("the dataloader yielded no batches")
@@ -110,4 +123,9 @@ def compute_hdr_image(dataloader: DataLoader, device, icrf_model: Optional[ICRFM
             if sigma is not None:
                 host_out[1].copy_(sigma, non_blocking=True)
             radiance, sigma = host_out[0], (host_out[1] if sigma is not None else None)
+    if in_flight or not radiance.is_cuda:
+        # host-resident inputs must outlive their readers, and host-resident results are returned ready to use (the
+        # reference's results are; INTEGRATION.md "synchronisation")
+        torch.cuda.current_stream(dev).synchronize()
+        in_flight.clear()
     return radiance.squeeze(), (sigma.squeeze() if sigma is not None else None)

@@ -10,13 +10,14 @@ from ..common.enums import VarianceMode
 from ..common.statistics import WBOMeanVar
 from ..models.base import ICRFModelBase
 from ._common import as_device, linear_table
+from ..common.errors import ArgumentTypeError
 
 
 def compute_video_mean_and_std(dataloader: DataLoader, device, icrf_model: Optional[ICRFModelBase] = None):
     """(mean (C,H,W), std of the mean (C,H,W)) over all frames of all batches; frames are optionally linearised
     first.  One fused pass per batch (ICRF + running mean / M2 merge)."""
     if not isinstance(dataloader, DataLoader):
-        raise TypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
+        raise ArgumentTypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
     dev = as_device(device)
     table = linear_table(icrf_model, dev)
     handler = WBOMeanVar(dim=0, variance_mode=VarianceMode.SAMPLE_FREQUENCY)

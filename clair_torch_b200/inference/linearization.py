@@ -8,6 +8,7 @@ from .. import kernels
 from ..models.base import ICRFModelBase
 from ._common import (as_device, check_artefact_dataset, matching_dark_frames, model_table, normalise_transforms,
                       stage_batch)
+from ..common.errors import ArgumentTypeError
 
 
 def linearize_dataset_generator(dataloader: DataLoader, device, icrf_model: ICRFModelBase, flatfield_dataset=None,
@@ -19,9 +20,9 @@ def linearize_dataset_generator(dataloader: DataLoader, device, icrf_model: ICRF
     dataset has no std images, :97).  The device->host copy uses pinned staging buffers.
     """
     if not isinstance(dataloader, DataLoader):
-        raise TypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
+        raise ArgumentTypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
     if not isinstance(icrf_model, ICRFModelBase):
-        raise TypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
+        raise ArgumentTypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
     dev = as_device(device)
     if not dataloader.batch_size == 1:
         raise ValueError("For linearization only batch_size of 1 is allowed.")

@@ -9,6 +9,7 @@ from ..common.enums import InterpMode
 from ..common.general_functions import get_pairwise_valid_pixel_mask, get_valid_exposure_pairs
 from ..models.base import ICRFModelBase
 from ._common import as_device, linear_table, stage_batch
+from ..common.errors import ArgumentTypeError
 
 RATIO_THRESHOLD = 0.2                     # measure_linearity.py:45
 VALID_LO, VALID_HI = 1 / 255, 254 / 255   # measure_linearity.py:46
@@ -60,10 +61,10 @@ def measure_linearity(dataloader: DataLoader, device, use_uncertainty_weighting:
     loop), so pass the whole stack as one batch.
     """
     if not isinstance(dataloader, DataLoader):
-        raise TypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
+        raise ArgumentTypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
     for flag in (use_uncertainty_weighting, use_relative_linearity_loss):
         if not isinstance(flag, bool):
-            raise TypeError("use_uncertainty_weighting / use_relative_linearity_loss must be bool")
+            raise ArgumentTypeError("use_uncertainty_weighting / use_relative_linearity_loss must be bool")
     dev = as_device(device)
     fused = icrf_model is None or not isinstance(icrf_model, ICRFModelBase) or icrf_model.interpolation_mode is InterpMode.LINEAR
     table = linear_table(icrf_model, dev) if fused else None

@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from . import _native
+from .common.errors import ArgumentTypeError
 
 _F32 = torch.float32
 _F64 = torch.float64
@@ -42,13 +43,13 @@ def _stack(t: torch.Tensor, name: str, allow_pinned: bool = False) -> torch.Tens
     With `allow_pinned`, a contiguous page-locked HOST tensor is accepted as well: the kernel then reads it over PCIe
     directly (every input element is read exactly once, so staging it in HBM first only adds a copy)."""
     if not isinstance(t, torch.Tensor):
-        raise TypeError(f"{name} must be a torch.Tensor, got {type(t)}")
+        raise ArgumentTypeError(f"{name} must be a torch.Tensor, got {type(t)}")
     if not t.is_cuda:
         if allow_pinned and t.is_pinned() and t.is_contiguous() and t.dtype == _F32 and t.dim() == 4:
             return t.detach()
         raise RuntimeError(f"{name} must live on a CUDA device: clair_torch_b200 has no CPU path")
     if t.dtype != _F32:
-        raise TypeError(f"{name} must be float32, got {t.dtype}")
+        raise ArgumentTypeError(f"{name} must be float32, got {t.dtype}")
     if t.dim() != 4:
         raise ValueError(f"{name} must have shape (N, C, H, W), got {tuple(t.shape)}")
     return t.detach().contiguous()
@@ -181,7 +182,7 @@ def _linearize_codes(lib, val, std, theta, row_base, device, pinned_out, interp_
     std_mode, std_value = 0, 0.0
     if std is not None and not torch.is_tensor(std):
         if not hasattr(std, "mode") or std.mode not in _STD_MODES:
-            raise TypeError(f"std_batch must be a tensor, None or a StdSpec, got {type(std)}")
+            raise ArgumentTypeError(f"std_batch must be a tensor, None or a StdSpec, got {type(std)}")
         std_mode, std_value, std = _STD_MODES[std.mode], float(np.float32(std.value)), None
     elif std is not None:
         std = _stack(std, "std_batch", allow_pinned=device is not None)
@@ -264,7 +265,7 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     a `datasets.StdSpec` (std = value * m, or a constant) instead of a tensor."""
     lib = _native.load()
     if not isinstance(val, torch.Tensor):
-        raise TypeError(f"val_batch must be a torch.Tensor, got {type(val)}")
+        raise ArgumentTypeError(f"val_batch must be a torch.Tensor, got {type(val)}")
     codes = val.dtype in _CODE_DTYPES
     if codes:
         val = _code_stack(val, device is not None)
@@ -273,7 +274,7 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     std_mode, std_value = 0, 0.0
     if std is not None and not torch.is_tensor(std):
         if not hasattr(std, "mode") or std.mode not in _STD_MODES:
-            raise TypeError(f"std_batch must be a tensor, None or a StdSpec, got {type(std)}")
+            raise ArgumentTypeError(f"std_batch must be a tensor, None or a StdSpec, got {type(std)}")
         std_mode, std_value, std = _STD_MODES[std.mode], float(np.float32(std.value)), None
         if not codes:
             raise ValueError("a StdSpec is evaluated by the integer-ingest kernel: pass uint8 / uint16 value codes with it")
@@ -316,7 +317,7 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
     radiance = sigma = None
     if is_final:
         if radiance_dtype not in (_F32, _F64):
-            raise TypeError("radiance_dtype must be torch.float32 or torch.float64")
+            raise ArgumentTypeError("radiance_dtype must be torch.float32 or torch.float64")
         if host_out is not None:
             radiance, sigma = host_out
             ok = (radiance.is_pinned() and radiance.is_contiguous() and tuple(radiance.shape) == (c, h, w)

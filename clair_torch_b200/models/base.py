@@ -8,6 +8,7 @@ from torch import nn
 
 from .. import _native, kernels
 from ..common.enums import InterpMode
+from ..common.errors import ArgumentTypeError
 
 
 class _TableFn(torch.autograd.Function):
@@ -48,10 +49,10 @@ class ICRFModelBase(nn.Module, ABC):
                  icrf: Optional[torch.Tensor] = None):
         super().__init__()
         if not isinstance(interpolation_mode, InterpMode):
-            raise TypeError(f"interpolation_mode must be an InterpMode, got {type(interpolation_mode)}")
+            raise ArgumentTypeError(f"interpolation_mode must be an InterpMode, got {type(interpolation_mode)}")
         if icrf is not None:
             if not isinstance(icrf, torch.Tensor):
-                raise TypeError("icrf must be a torch.Tensor")
+                raise ArgumentTypeError("icrf must be a torch.Tensor")
             channels, n_points = icrf.shape          # overrides n_points / channels, base.py:59-60
         self._channels = channels
         self._initial_power = initial_power

@@ -6,6 +6,7 @@ from torch import nn
 
 from ..common.enums import InterpMode
 from .base import ICRFModelBase
+from ..common.errors import ArgumentTypeError
 
 
 class ICRFModelDirect(ICRFModelBase):
@@ -43,7 +44,7 @@ class ICRFModelPCA(ICRFModelBase):
     def __init__(self, pca_basis: torch.Tensor, interpolation_mode: InterpMode = InterpMode.LINEAR,
                  initial_power: float = 2.5, icrf: Optional[torch.Tensor] = None) -> None:
         if not isinstance(pca_basis, torch.Tensor) or pca_basis.dim() != 3:
-            raise TypeError("pca_basis must be a (n_points, num_components, channels) tensor")
+            raise ArgumentTypeError("pca_basis must be a (n_points, num_components, channels) tensor")
         n_points, num_components, channels = pca_basis.shape
         super().__init__(n_points, channels, interpolation_mode, initial_power, icrf)
         self.p = nn.ParameterList([nn.Parameter(torch.tensor(2.0)) for _ in range(channels)])

@@ -16,6 +16,7 @@ from ..common.general_functions import get_valid_exposure_pairs
 from ..models.base import ICRFModelBase
 from ..inference._common import as_device, stage_batch
 from ..common.enums import InterpMode
+from ..common.errors import ArgumentTypeError
 
 
 def linearity_loss_and_table_grad(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
@@ -202,11 +203,11 @@ def train_icrf(dataloader: DataLoader, batch_size: int, device, icrf_model: ICRF
     dataset) with capturable optimisers (the default ones are) is stepped through GraphedTrainStep from its third visit
     on; anything else takes the eager step."""
     if not isinstance(dataloader, DataLoader):
-        raise TypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
+        raise ArgumentTypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
     if not isinstance(icrf_model, ICRFModelBase):
-        raise TypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
+        raise ArgumentTypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
     if not isinstance(batch_size, int):
-        raise TypeError("batch_size must be an int")
+        raise ArgumentTypeError("batch_size must be an int")
     dev = as_device(device)
     channels = icrf_model.channels
     if batch_size == 1:

@@ -214,6 +214,14 @@ def test_error_conventions_match_reference():
         ct.train_icrf(DataLoader(ds, batch_size=1, collate_fn=custom_collate), 1, "cuda", model)
     with pytest.raises(TypeError):
         ct.compute_hdr_image("not a loader", "cuda")
+    # the reference's functions are @typechecked: the error a reference user catches is typeguard's (not a TypeError)
+    import typeguard
+    for bad_call in (lambda: ct.compute_hdr_image("not a loader", "cuda"),
+                     lambda: ct.measure_linearity(DataLoader(ds, batch_size=3, collate_fn=custom_collate), "cuda", "yes"),
+                     lambda: ct.train_icrf("not a loader", 2, "cuda", model),
+                     lambda: ct.ICRFModelDirect(interpolation_mode="LINEAR")):
+        with pytest.raises(typeguard.TypeCheckError):
+            bad_call()
     with pytest.raises(TypeError):
         ct.ICRFModelDirect(interpolation_mode="LINEAR")
     with pytest.raises(TypeError):

@@ -261,3 +261,78 @@ def test_staged_host_pipelines_back_to_back_without_sync(ct):
     for k in range(12):
         assert torch.equal(outs[k][0], want[k % 3][0].cpu()) and torch.equal(outs[k][1], want[k % 3][1].cpu()), k
         assert torch.equal(lins[k][0], want_lin[k % 3][0].cpu()) and torch.equal(lins[k][1], want_lin[k % 3][1].cpu()), k
+
+
+class _RecyclingPinnedBatches(torch.utils.data.Dataset):
+    """Whole pinned batches handed out from a pool that behaves like torch's caching host allocator: a buffer whose
+    tensor nobody references any more is considered free and is immediately overwritten (poisoned) before it is reused."""
+
+    def __init__(self, batches):
+        import weakref
+        self.batches, self.weakref = batches, weakref
+        self.slots, self.poisoned = [], 0          # slots: [val base, std base, weakref of the handed-out view]
+
+    def __len__(self):
+        return len(self.batches)
+
+    def __getitem__(self, i):
+        idx, val, std, meta = self.batches[i]
+        slot = None
+        for s in self.slots:
+            if s[2] is not None and s[2]() is None:            # released by the consumer: "freed" pinned memory
+                s[0].fill_(float("nan"))
+                s[1].fill_(float("nan"))
+                s[2] = None
+                self.poisoned += 1
+            if s[2] is None and slot is None and s[0].shape == val.shape:
+                slot = s
+        if slot is None:
+            slot = [torch.empty(val.shape, dtype=val.dtype).pin_memory(), torch.empty(std.shape, dtype=std.dtype).pin_memory(), None]
+            self.slots.append(slot)
+        slot[0].copy_(val)
+        slot[1].copy_(std)
+        view = slot[0].view(val.shape)                          # a fresh tensor object over the pooled pinned storage
+        slot[2] = self.weakref.ref(view)
+        return idx, view, slot[1].view(std.shape), meta
+
+
+@pytest.mark.parametrize("staged", [True, False])
+def test_pinned_batches_stay_alive_until_the_gpu_has_read_them(ct, staged):
+    """compute_hdr_image hands pinned host pointers to the copy engine / the kernels; it must keep every batch referenced
+    until an event behind its last reader has completed.  The pool above poisons a buffer the moment it is dropped, as a
+    DataLoader pin thread re-using a freed block would."""
+    n, per_batch = 12, 3
+    val, std, t = ct.synthetic.make_stack(n, 3, 512, 1024, bits=16, seed=77)
+    theta = ct.synthetic.reference_curve(3)
+    batches = []
+    for b in range(0, n, per_batch):
+        sl = slice(b, b + per_batch)
+        batches.append((torch.arange(b, b + per_batch), val[sl].contiguous(), std[sl].contiguous(),
+                        {"exposure_time": torch.from_numpy(t[sl])}))
+    ds = _RecyclingPinnedBatches(batches)
+    loader = DataLoader(ds, batch_size=None, shuffle=False)
+    model = ct.ICRFModelDirect(icrf=theta.clone()).to(DEV)
+    rad, sig = ct.compute_hdr_image(loader, DEV, model, max, staged=staged)
+    torch.cuda.synchronize()
+    dev_loader = DataLoader(ct.datasets.ExposureStackDataset(list(val.to(DEV)), list(std.to(DEV)), list(t)), batch_size=per_batch,
+                            shuffle=False, collate_fn=ct.datasets.custom_collate)
+    want_rad, want_sig = ct.compute_hdr_image(dev_loader, DEV, model, max)
+    assert not torch.isnan(rad).any() and not torch.isnan(sig).any()
+    assert torch.equal(rad, want_rad) and torch.equal(sig, want_sig)
+
+
+def test_host_out_results_are_ready_when_compute_hdr_image_returns(ct):
+    """host_out buffers are written by the kernel (or a non_blocking copy): the call synchronises before returning them."""
+    val, std, t = ct.synthetic.make_stack(6, 3, 1024, 1536, bits=16, seed=5)
+    theta = ct.synthetic.reference_curve(3)
+    model = ct.ICRFModelDirect(icrf=theta.clone()).to(DEV)
+    loader = DataLoader(ct.datasets.ExposureStackDataset(list(val.to(DEV)), list(std.to(DEV)), list(t)), batch_size=6, shuffle=False,
+                        collate_fn=ct.datasets.custom_collate)
+    want_rad, want_sig = ct.compute_hdr_image(loader, DEV, model, max, radiance_dtype=torch.float32)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        rad_h = torch.full((3, 1024, 1536), float("nan")).pin_memory()
+        sig_h = torch.full((3, 1024, 1536), float("nan")).pin_memory()
+        rad, sig = ct.compute_hdr_image(loader, DEV, model, max, radiance_dtype=torch.float32, host_out=(rad_h, sig_h))
+        got_rad, got_sig = rad.numpy().copy(), sig.numpy().copy()          # read immediately, no synchronize
+        assert np.array_equal(got_rad, want_rad.cpu().numpy()) and np.array_equal(got_sig, want_sig.cpu().numpy())
