@@ -15,7 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CLAIR_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libclair_b200.so")   # env: kernel experiments
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_FRAMES = 64
 MAX_CHANNELS = 8
 MAX_LUT = 1024
@@ -56,8 +56,8 @@ _PROTOTYPES = {
     "clair_linearize": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                    _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "clair_linearize_codes": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_float, _c.c_void_p, _c.c_int, _c.c_float, _c.c_void_p,
-                                         _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_void_p,
-                                         _c.c_void_p]),
+                                         _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int,
+                                         _c.c_void_p, _c.c_void_p]),
     "clair_linearize_staged": (_c.c_int, [_c.c_void_p] * 9 + [_c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_void_p,
                                           _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "clair_hdr_merge_update": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int,
@@ -75,20 +75,20 @@ _PROTOTYPES = {
     "clair_flat_field_correct": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                             _c.c_int64, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "clair_frame_stats_update": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int,
-                                            _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
+                                            _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                             _c.c_void_p]),
     "clair_pair_stats": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p,
-                                    _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
+                                    _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
                                     _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "clair_pair_means": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p,
-                                    _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
+                                    _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
                                     _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "clair_pair_upstream": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                        _c.c_void_p, _c.c_void_p]),
     "clair_curve_penalties": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_float, _c.c_float, _c.c_float,
                                          _c.c_float, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "clair_pair_grad": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p,
-                                   _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_void_p,
+                                   _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
                                    _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                    _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
 }

@@ -34,7 +34,8 @@ class WBOMean:
     def internal_detach(self, *, in_place: bool = True):
         """The state never carries an autograd graph here; kept for call compatibility."""
 
-    def _update(self, batch_values: torch.Tensor, batch_weights: Optional[torch.Tensor], table=None):
+    def _update(self, batch_values: torch.Tensor, batch_weights: Optional[torch.Tensor], table=None,
+                interp_mode: int = _native.INTERP_LINEAR):
         from ..kernels import _ptr, _stack, _stream, _table
         lib = _native.load()
         val = _stack(batch_values, "batch_values")
@@ -48,7 +49,7 @@ class WBOMean:
             self._mean, self._m2, self._sum_of_weights, self._sum_of_squared_weights = make(), make(), make(), make()
         with torch.cuda.device(val.device):
             rc = lib.clair_frame_stats_update(_ptr(val), _ptr(wts), _ptr(th), n, c, h * w, 0 if th is None else th.shape[1],
-                                              None, _ptr(self._mean), _ptr(self._m2), _ptr(self._sum_of_weights),
+                                              int(interp_mode), None, _ptr(self._mean), _ptr(self._m2), _ptr(self._sum_of_weights),
                                               _ptr(self._sum_of_squared_weights), int(self._batches == 0), _stream(val.device))
         _native.check(rc, "clair_frame_stats_update")
         self._batches += 1
@@ -77,7 +78,9 @@ class WBOMeanVar(WBOMean):
             return self.m2 * (1 / (w - w2 / w))
         return self.m2 * (1 / w)
 
-    def update_values(self, batch_values: torch.Tensor, batch_weights: Optional[torch.Tensor] = None, *, table=None):
-        """Returns (mean, m2) like the reference.  `table` (C, L) linearises the frames inside the same pass."""
-        self._update(batch_values, batch_weights, table)
+    def update_values(self, batch_values: torch.Tensor, batch_weights: Optional[torch.Tensor] = None, *, table=None,
+                      interp_mode: int = _native.INTERP_LINEAR):
+        """Returns (mean, m2) like the reference.  `table` (C, L) linearises the frames inside the same pass
+        (`interp_mode`: the InterpMode of the model the table belongs to)."""
+        self._update(batch_values, batch_weights, table, interp_mode)
         return self.mean, self.m2

@@ -211,6 +211,68 @@ __device__ __forceinline__ float gaussian_weight(float x, float neg_scale_log2e,
     return exp2f_approx(__fmul_rn(neg_scale_log2e, __fmul_rn(d, d)));
 }
 
+// CATMULL mode (models/base.py:184-226): four taps x0-1 .. x0+2 (clamped), Catmull-Rom weights of t = xs - x0 in the
+// reference's left-to-right fp32 op order (so the value is bit-exact), rows per the same k-mod-C rule as LINEAR.
+// The derivative is the closed form sum_i w_i'(t) g_i (L-1) (the reference's autograd result differs from it by its own
+// fp32 rounding, ~3e-5 of the maximum).
+struct CatmullTaps {
+    int idx[4];
+    float w[4];
+    float dw[4];
+};
+
+// taps from the clamped scaled position xs = clamp(x (L-1), 0, L-1); `inside` = the clamp changed nothing (its backward
+// passes the gradient exactly then)
+__device__ __forceinline__ CatmullTaps catmull_taps_xs(float xs, bool inside_clamp, int L) {
+    CatmullTaps c;
+    const float lm1 = static_cast<float>(L - 1);
+    int x0;
+    const float fl = floor_small(xs, x0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c.idx[k] = min(max(x0 + k - 1, 0), L - 1);
+    const float t = fminf(fmaxf(__fsub_rn(xs, fl), 0.0f), 1.0f);
+    const float t2 = __fmul_rn(t, t), t3 = __fmul_rn(t2, t);
+    c.w[0] = __fsub_rn(__fadd_rn(__fmul_rn(-0.5f, t3), t2), __fmul_rn(0.5f, t));
+    c.w[1] = __fadd_rn(__fsub_rn(__fmul_rn(1.5f, t3), __fmul_rn(2.5f, t2)), 1.0f);
+    c.w[2] = __fadd_rn(__fadd_rn(__fmul_rn(-1.5f, t3), __fmul_rn(2.0f, t2)), __fmul_rn(0.5f, t));
+    c.w[3] = __fsub_rn(__fmul_rn(0.5f, t3), __fmul_rn(0.5f, t2));
+    const float inside = inside_clamp ? lm1 : 0.0f;
+    c.dw[0] = inside * (-1.5f * t2 + 2.0f * t - 0.5f);
+    c.dw[1] = inside * (4.5f * t2 - 5.0f * t);
+    c.dw[2] = inside * (-4.5f * t2 + 4.0f * t + 0.5f);
+    c.dw[3] = inside * (1.5f * t2 - t);
+    return c;
+}
+
+__device__ __forceinline__ CatmullTaps catmull_taps(float x, int L) {
+    const float lm1 = static_cast<float>(L - 1);
+    const float xs_raw = __fmul_rn(x, lm1);
+    const float xs = fminf(fmaxf(xs_raw, 0.0f), lm1);
+    return catmull_taps_xs(xs, xs == xs_raw, L);
+}
+
+// f and autograd's df/dx of a LOOKUP (models/base.py:138-158: nearest sample, no image edge) or CATMULL model from a
+// table row whose .x entries are theta[u][k] (either staging layout above)
+template <int MODE>
+__device__ __forceinline__ void icrf_mode_eval(float x, const float2 *row, int L, float lm1, float &f, float &fp) {
+    if constexpr (MODE == CLAIR_INTERP_LOOKUP) {
+        f = row[icrf_lookup_index(x, lm1)].x;
+        fp = 0.0f;
+    } else {
+        const CatmullTaps t = catmull_taps(x, L);
+        const float g0 = row[t.idx[0]].x, g1 = row[t.idx[1]].x, g2 = row[t.idx[2]].x, g3 = row[t.idx[3]].x;
+        f = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t.w[0], g0), __fmul_rn(t.w[1], g1)), __fmul_rn(t.w[2], g2)),
+                      __fmul_rn(t.w[3], g3));
+        fp = t.dw[0] * g0 + t.dw[1] * g1 + t.dw[2] * g2 + t.dw[3] * g3;
+    }
+}
+
+// runtime-mode form of the same, for kernels that are not specialised per mode
+__device__ __forceinline__ void icrf_mode_eval_rt(int mode, float x, const float2 *row, int L, float lm1, float &f, float &fp) {
+    if (mode == CLAIR_INTERP_LOOKUP) icrf_mode_eval<CLAIR_INTERP_LOOKUP>(x, row, L, lm1, f, fp);
+    else icrf_mode_eval<CLAIR_INTERP_CATMULL>(x, row, L, lm1, f, fp);
+}
+
 __device__ __forceinline__ int wrap_inc(int u, int C) { return (u + 1 == C) ? 0 : u + 1; }
 
 // ---- packed fp32x2 arithmetic: sm_100a issues FFMA2 / FMUL2 / FADD2, two IEEE fp32 results per issue slot ----

@@ -44,6 +44,7 @@ struct PairParams {
     int n_pairs;                 // pairs in this launch
     int unc_weighting;
     int n_copies;                // gradient: replicated tables in use
+    int mode;                    // CLAIR_INTERP_* of the model the table belongs to
     float valid_lo, valid_hi;
     uint32_t mod_magic;          // ceil(2^16 / C): x mod C for x < 2^13 without a divide
     CurveRows rows;
@@ -75,6 +76,22 @@ __device__ __forceinline__ FrameTerms frame_terms(float x, float s, bool has_mod
         icrf_linear_biased(x, row_bias, lm1, t.f, fp);
         t.xs = fminf(fmaxf(__fmul_rn(x, lm1), 0.0f), lm1);
     }
+    t.sig = HAS_STD ? fabsf(__fmul_rn(fp, s)) : 0.0f;
+    float d;
+    const float g = gaussian_weight(x, kPairNegScaleLog2e, d);
+    t.gw = (x >= lo && x <= hi) ? g : -1.0f;
+    return t;
+}
+
+// The same terms for a LOOKUP / CATMULL model (models/base.py:138-158, :184-226); `row` is the table row the element
+// reads (.x entries): the true channel row for LOOKUP, the k-mod-C row for CATMULL.
+template <bool HAS_STD>
+__device__ __forceinline__ FrameTerms frame_terms_mode(int mode, float x, float s, const float2 *row, int L, float lm1, float lo,
+                                                       float hi) {
+    FrameTerms t;
+    float fp;
+    icrf_mode_eval_rt(mode, x, row, L, lm1, t.f, fp);
+    t.xs = fminf(fmaxf(__fmul_rn(x, lm1), 0.0f), lm1);
     t.sig = HAS_STD ? fabsf(__fmul_rn(fp, s)) : 0.0f;
     float d;
     const float g = gaussian_weight(x, kPairNegScaleLog2e, d);
@@ -186,10 +203,13 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
             }
             uint32_t u = mod_small(u_tile + q, uC, p.mod_magic);
             Pack<VA> of, og, os, ob;
+            const bool linear = p.mode == CLAIR_INTERP_LINEAR || !has_model;
 #pragma unroll
             for (int k = 0; k < VA; ++k) {
-                const FrameTerms t = frame_terms<ERR>(xv.v[k], sv.v[k], has_model, tab_bias + u * row_bytes, lm1, p.valid_lo,
-                                                      p.valid_hi);
+                const FrameTerms t = linear
+                    ? frame_terms<ERR>(xv.v[k], sv.v[k], has_model, tab_bias + u * row_bytes, lm1, p.valid_lo, p.valid_hi)
+                    : frame_terms_mode<ERR>(p.mode, xv.v[k], sv.v[k], s_tab + (p.mode == CLAIR_INTERP_LOOKUP ? c : u) * L, L, lm1,
+                                            p.valid_lo, p.valid_hi);
                 u = (u + 1 == uC) ? 0u : u + 1;
                 of.v[k] = t.f;
                 og.v[k] = live ? t.gw : -1.0f;
@@ -335,15 +355,25 @@ struct FrameTerms2 {
     f32x2 f, gw, sig, rel;
 };
 
-// per-frame terms of two adjacent pixels (see FrameTerms); `live` = the pixels exist
-template <bool HAS_STD, bool RELATIVE>
+// table rows of a LOOKUP / CATMULL model for the two pixels (only read by the MODES instantiations)
+struct ModeRows {
+    const float2 *row0, *row1;
+    int mode, L;
+};
+
+// per-frame terms of two adjacent pixels (see FrameTerms); `live` = the pixels exist.  MODES = the table belongs to a
+// LOOKUP / CATMULL model (evaluated per pixel through `mr`); otherwise LINEAR over the (g0, g1 - g0) table.
+template <bool HAS_STD, bool RELATIVE, bool MODES = false>
 __device__ __forceinline__ FrameTerms2<HAS_STD, RELATIVE> frame_terms2(float x0, float x1, float s0, float s1, bool has_model,
                                                                       uint32_t bias0, uint32_t bias1, float lm1, float lo, float hi,
-                                                                      bool live) {
+                                                                      bool live, const ModeRows mr = ModeRows{}) {
     FrameTerms2<HAS_STD, RELATIVE> t;
     const f32x2 x2 = pack2(x0, x1);
     float f0 = x0, f1 = x1, fp0 = 1.0f, fp1 = 1.0f;
-    if (has_model) {
+    if constexpr (MODES) {
+        icrf_mode_eval_rt(mr.mode, x0, mr.row0, mr.L, lm1, f0, fp0);
+        icrf_mode_eval_rt(mr.mode, x1, mr.row1, mr.L, lm1, f1, fp1);
+    } else if (has_model) {
         float r0, r1;
         unpack2(mul2(x2, splat2(lm1)), r0, r1);                          // image * (L - 1), rounded once
         const float xs0 = fminf(fmaxf(r0, 0.0f), lm1), xs1 = fminf(fmaxf(r1, 0.0f), lm1);
@@ -382,7 +412,8 @@ __device__ __forceinline__ FrameTerms2<HAS_STD, RELATIVE> frame_terms2(float x0,
 // TRIPS = staging items per thread (N * 32 items <= TRIPS * blockDim.x): an item's frame, tile offset, table rows and
 // shared-memory slot never change, and the loads of the NEXT tile are issued before the pair phase of the current one,
 // so their HBM latency is hidden behind it.
-template <int SLOTS, bool ERR, bool RELATIVE, bool FULL, int TRIPS>
+// MODES: the model is LOOKUP / CATMULL (only the staging phase differs: the pair phase works on the staged per-frame terms).
+template <int SLOTS, bool ERR, bool RELATIVE, bool FULL, int TRIPS, bool MODES = false>
 // (two-slot kernels are held to 64 registers = two 16-warp blocks per SM: c3 2.07 -> 1.93 ms with 48 B of spills)
 __global__ void __launch_bounds__(512, (SLOTS == 2) ? 2 : 1) pair_stats2_kernel(const PairParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -476,10 +507,21 @@ __global__ void __launch_bounds__(512, (SLOTS == 2) ? 2 : 1) pair_stats2_kernel(
                 uint32_t bias[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { bias[k] = tab_bias + u * row_bytes; u = (u + 1 == uC) ? 0u : u + 1; }
-                const auto a = frame_terms2<ERR, RELATIVE>(xv[t].x, xv[t].y, sv[t].x, sv[t].y, has_model, bias[0], bias[1], lm1,
-                                                           p.valid_lo, p.valid_hi, live);
-                const auto b = frame_terms2<ERR, RELATIVE>(xv[t].z, xv[t].w, sv[t].z, sv[t].w, has_model, bias[2], bias[3], lm1,
-                                                           p.valid_lo, p.valid_hi, live);
+                ModeRows mra{}, mrb{};
+                if constexpr (MODES) {
+                    // LOOKUP reads the true channel row (base.py:148-158), CATMULL the k-mod-C row like LINEAR (:217-219)
+                    const bool lookup = p.mode == CLAIR_INTERP_LOOKUP;
+                    const float2 *rows[4];
+                    uint32_t ur = urow[t];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { rows[k] = s_tab + (lookup ? static_cast<uint32_t>(c) : ur) * L; ur = (ur + 1 == uC) ? 0u : ur + 1; }
+                    mra = ModeRows{rows[0], rows[1], p.mode, L};
+                    mrb = ModeRows{rows[2], rows[3], p.mode, L};
+                }
+                const auto a = frame_terms2<ERR, RELATIVE, MODES>(xv[t].x, xv[t].y, sv[t].x, sv[t].y, has_model, bias[0], bias[1], lm1,
+                                                                  p.valid_lo, p.valid_hi, live, mra);
+                const auto b = frame_terms2<ERR, RELATIVE, MODES>(xv[t].z, xv[t].w, sv[t].z, sv[t].w, has_model, bias[2], bias[3], lm1,
+                                                                  p.valid_lo, p.valid_hi, live, mrb);
                 *reinterpret_cast<ulonglong2 *>(dst[t]) = make_ulonglong2(a.f, b.f);
                 *reinterpret_cast<ulonglong2 *>(dst[t] + kStatsTile) = make_ulonglong2(a.gw, b.gw);
                 if constexpr (ERR) {
@@ -636,6 +678,20 @@ __device__ __forceinline__ void scatter_taps(float *copy, int C, int L, int u, f
     red_add_v2(base, g * (1.0f - w), g * w);
 }
 
+// LOOKUP / CATMULL models: one tap of weight 1 at the nearest sample (the gather of models/base.py:158 under autograd) or
+// the four Catmull-Rom taps (:219-226), plain fp32 reductions into the A half of a replicated table.  `row` = the true
+// channel for LOOKUP, the k-mod-C row for CATMULL; `xs` = clamp(x (L-1), 0, L-1).
+__device__ __forceinline__ void scatter_taps_mode(float *copy, int L, int mode, int row, float xs, float g) {
+    float *dst = copy + row * (L + 2);
+    if (mode == CLAIR_INTERP_LOOKUP) {
+        atomicAdd(dst + static_cast<int>(rintf(xs)), g);        // rint(clamp(.)) == clamp(rint(.)): the bounds are integers
+    } else {
+        const CatmullTaps t = catmull_taps_xs(xs, true, L);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) atomicAdd(dst + t.idx[k], g * t.w[k]);
+    }
+}
+
 template <bool ERR, bool RELATIVE, int PIX>
 __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -707,7 +763,11 @@ __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
                     Pack<PIX> of, og, ox, oz, os, oi;
 #pragma unroll
                     for (int k = 0; k < PIX; ++k) {
-                        const FrameTerms t = frame_terms<ERR>(xv[j].v[k], sv[j].v[k], true, bias[k], lm1, p.valid_lo, p.valid_hi);
+                        const FrameTerms t = (p.mode == CLAIR_INTERP_LINEAR)
+                            ? frame_terms<ERR>(xv[j].v[k], sv[j].v[k], true, bias[k], lm1, p.valid_lo, p.valid_hi)
+                            : frame_terms_mode<ERR>(p.mode, xv[j].v[k], sv[j].v[k],
+                                                    s_tab + (p.mode == CLAIR_INTERP_LOOKUP ? static_cast<uint32_t>(c) : (u0 + k) % uC) * L,
+                                                    L, lm1, p.valid_lo, p.valid_hi);
                         of.v[k] = t.f; og.v[k] = live ? t.gw : -1.0f; ox.v[k] = t.xs; oz.v[k] = 0.0f;
                         if constexpr (ERR) { os.v[k] = t.sig; oi.v[k] = rcp_approx(fmaxf(t.f, 1e-6f)); }
                     }
@@ -812,7 +872,10 @@ __global__ void __launch_bounds__(256) pair_grad_kernel(const PairParams p) {
             uint32_t u = u0;
 #pragma unroll
             for (int k = 0; k < PIX; ++k) {
-                if (g.v[k] != 0.0f) scatter_taps(copy, C, L, static_cast<int>(u), xs.v[k], g.v[k]);
+                if (g.v[k] != 0.0f) {
+                    if (p.mode == CLAIR_INTERP_LINEAR) scatter_taps(copy, C, L, static_cast<int>(u), xs.v[k], g.v[k]);
+                    else scatter_taps_mode(copy, L, p.mode, p.mode == CLAIR_INTERP_LOOKUP ? c : static_cast<int>(u), xs.v[k], g.v[k]);
+                }
                 u = (u + 1 == uC) ? 0u : u + 1;
             }
         }
@@ -852,7 +915,8 @@ __device__ __forceinline__ void red_add_v2_if(float *addr, float a, float b, flo
                  ::"l"(addr), "f"(a), "f"(b), "f"(g));
 }
 
-template <bool ERR, bool RELATIVE>
+// MODES: the model is LOOKUP / CATMULL — per-frame terms and the final tap scatter differ, the pair algebra does not.
+template <bool ERR, bool RELATIVE, bool MODES = false>
 __global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int C = p.n_channels, L = p.lut, N = p.n_frames, P = p.n_pairs;
@@ -908,15 +972,27 @@ __global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
             unpack2(mul2(x2, splat2(lm1)), r0, r1);                       // image * (L - 1), rounded once
             const float xs0 = fminf(fmaxf(r0, 0.0f), lm1), xs1 = fminf(fmaxf(r1, 0.0f), lm1);
             const f32x2 xs2 = pack2(xs0, xs1);
-            const f32x2 t2 = add2_rd(xs2, two23);
-            const f32x2 w2 = sub2(xs2, sub2(t2, two23));
-            float t0, t1, w0, w1;
-            unpack2(t2, t0, t1);
-            unpack2(w2, w0, w1);
-            float g00, dg0, g01, dg1;
-            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g00), "=f"(dg0) : "r"(static_cast<uint32_t>(__float_as_int(t0)) * 8u + bias0));
-            asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g01), "=f"(dg1) : "r"(static_cast<uint32_t>(__float_as_int(t1)) * 8u + bias1));
-            const float f0 = fmaf(w0, dg0, g00), f1 = fmaf(w1, dg1, g01);
+            float f0, f1, fp0 = 0.0f, fp1 = 0.0f;
+            if constexpr (MODES) {
+                const bool lookup = p.mode == CLAIR_INTERP_LOOKUP;
+                icrf_mode_eval_rt(p.mode, xin.x, s_tab + (lookup ? static_cast<uint32_t>(c) : u0) * L, L, lm1, f0, fp0);
+                icrf_mode_eval_rt(p.mode, xin.y, s_tab + (lookup ? static_cast<uint32_t>(c) : u1) * L, L, lm1, f1, fp1);
+            } else {
+                const f32x2 t2 = add2_rd(xs2, two23);
+                const f32x2 w2 = sub2(xs2, sub2(t2, two23));
+                float t0, t1, w0, w1;
+                unpack2(t2, t0, t1);
+                unpack2(w2, w0, w1);
+                float g00, dg0, g01, dg1;
+                asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g00), "=f"(dg0) : "r"(static_cast<uint32_t>(__float_as_int(t0)) * 8u + bias0));
+                asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(g01), "=f"(dg1) : "r"(static_cast<uint32_t>(__float_as_int(t1)) * 8u + bias1));
+                f0 = fmaf(w0, dg0, g00);
+                f1 = fmaf(w1, dg1, g01);
+                if constexpr (ERR) {
+                    fp0 = (xs0 == r0) ? __fmul_rn(dg0, lm1) : 0.0f;
+                    fp1 = (xs1 == r1) ? __fmul_rn(dg1, lm1) : 0.0f;
+                }
+            }
             const f32x2 d2 = add2(x2, splat2(-0.5f));
             float e0, e1;
             unpack2(mul2(mul2(d2, d2), splat2(kPairNegScaleLog2e)), e0, e1);
@@ -928,8 +1004,6 @@ __global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
             sts2(dst + 2 * kArr, xs2);
             sts2(dst + 3 * kArr, 0ull);
             if constexpr (ERR) {
-                const float fp0 = (xs0 == r0) ? __fmul_rn(dg0, lm1) : 0.0f;
-                const float fp1 = (xs1 == r1) ? __fmul_rn(dg1, lm1) : 0.0f;
                 sts2(dst + 4 * kArr, pack2(fabsf(__fmul_rn(fp0, sin.x)), fabsf(__fmul_rn(fp1, sin.y))));
                 if constexpr (RELATIVE) sts2(dst + 5 * kArr, pack2(rcp_approx(fmaxf(f0, 1e-6f)), rcp_approx(fmaxf(f1, 1e-6f))));
             }
@@ -1081,6 +1155,15 @@ __global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
             const float *fr = slice + n * kFrameFloats;
             const f32x2 g2 = lds2(fr + 3 * kArr);
             const f32x2 xs2 = lds2(fr + 2 * kArr);
+            if constexpr (MODES) {
+                float ga, gb, xa, xb;
+                unpack2(g2, ga, gb);
+                unpack2(xs2, xa, xb);
+                const bool lookup = p.mode == CLAIR_INTERP_LOOKUP;
+                if (ga != 0.0f) scatter_taps_mode(copy, L, p.mode, lookup ? c : static_cast<int>(u0), xa, ga);
+                if (gb != 0.0f) scatter_taps_mode(copy, L, p.mode, lookup ? c : static_cast<int>(u1), xb, gb);
+                continue;
+            }
             const f32x2 t2 = add2_rd(xs2, two23);
             const f32x2 w2 = sub2(xs2, sub2(t2, two23));
             float t0, t1, g0, g1, lo0, lo1, hi0, hi1;
@@ -1324,8 +1407,9 @@ void pick_stats_shape(int count, int n_frames, int va, bool err, bool full, int 
 }
 
 void common_params(PairParams &p, const float *val, const float *std, const float *theta, int n_frames, int n_channels,
-                   int64_t plane, int lut, const int32_t *row_base_host, float lo, float hi, int unc) {
+                   int64_t plane, int lut, const int32_t *row_base_host, float lo, float hi, int unc, int mode) {
     p.val = val; p.std = std; p.theta = theta;
+    p.mode = theta ? mode : CLAIR_INTERP_LINEAR;
     p.plane = plane; p.n_frames = n_frames; p.n_channels = n_channels; p.lut = lut;
     p.unc_weighting = unc; p.valid_lo = lo; p.valid_hi = hi;
     p.mod_magic = (65536u + n_channels - 1) / n_channels;
@@ -1334,11 +1418,29 @@ void common_params(PairParams &p, const float *val, const float *std, const floa
 
 }  // namespace
 
+// the mode argument shared by the pair entry points: LINEAR, or LOOKUP / CATMULL with the reference's restriction that a
+// LOOKUP model has no derivative to carry std images through (measure_linearity.py:57-63 raises there)
+static int check_pair_mode(const char *fn, int interp_mode, const float *theta_dev, const float *std_dev) {
+    if (interp_mode != CLAIR_INTERP_LINEAR && interp_mode != CLAIR_INTERP_LOOKUP && interp_mode != CLAIR_INTERP_CATMULL) {
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "%s: interp_mode must be CLAIR_INTERP_LOOKUP, _LINEAR or _CATMULL", fn);
+        return fail(CLAIR_E_MODE, buf);
+    }
+    if (interp_mode == CLAIR_INTERP_LOOKUP && theta_dev && std_dev) {
+        char buf[160];
+        std::snprintf(buf, sizeof(buf), "%s: a LOOKUP model has no derivative to propagate std images through", fn);
+        return fail(CLAIR_E_MODE, buf);
+    }
+    return 0;
+}
+
 static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
                            const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host, int n_pairs,
-                           const float *theta_dev, int lut_size, const int32_t *curve_row_base_host, float valid_lo,
+                           const float *theta_dev, int lut_size, int interp_mode, const int32_t *curve_row_base_host, float valid_lo,
                            float valid_hi, int relative, int unc_weighting, int full, double *sums_dev, void *stream) {
     const char *fn = full ? "clair_pair_stats" : "clair_pair_means";
+    if (int rc = check_pair_mode(fn, interp_mode, theta_dev, std_dev)) return rc;
+    const bool modes = theta_dev != nullptr && interp_mode != CLAIR_INTERP_LINEAR;
     if (!val_dev || !sums_dev) return fail(CLAIR_E_ARG, "clair_pair_stats: null buffer");
     if (n_pairs < 0 || (n_pairs > 0 && (!pair_i_host || !pair_j_host || !pair_ratio_host)))
         return fail(CLAIR_E_ARG, "clair_pair_stats: pair table missing");
@@ -1363,7 +1465,7 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
         const int count = (n_pairs - first + (n_launches - l) - 1) / (n_launches - l);   // balanced chunks
         PairParams p{};
         common_params(p, val_dev, err ? std_dev : nullptr, theta_dev, n_frames, n_channels, plane, lut_size, curve_row_base_host,
-                      valid_lo, valid_hi, unc_weighting);
+                      valid_lo, valid_hi, unc_weighting, interp_mode);
         p.sums = sums_dev + static_cast<int64_t>(first) * n_channels * 5;
         p.n_pairs = count;
         if (int rc = fill_pairs(fn, p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
@@ -1374,6 +1476,12 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
             (g_tuning.stats_slots == 1 || g_tuning.stats_slots == 2 || g_tuning.stats_slots == 4)) {
             warps = g_tuning.stats_warps;
             slots = g_tuning.stats_slots;
+        }
+        if (modes && va == 4) {
+            // LOOKUP / CATMULL models: one shape (4 register slots, two staging items per thread) keeps the number of
+            // instantiations down; the pair phase is the LINEAR kernels' own
+            slots = kMaxSlots;
+            warps = std::max((count + kMaxSlots - 1) / kMaxSlots, (n_frames + 1) / 2);
         }
         const int trips = (n_frames + warps - 1) / warps;      // staging items per thread of the packed kernel (1 or 2)
         const int64_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
@@ -1388,7 +1496,8 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
         };
         int rc = 0;
 #define STATS_FLAGS(S, E, R, F)                                                                        \
-    (va == 4 ? (trips == 1 ? launch(pair_stats2_kernel<S, E, R, F, 1>) : launch(pair_stats2_kernel<S, E, R, F, 2>)) \
+    (va == 4 ? (modes ? launch(pair_stats2_kernel<kMaxSlots, E, R, F, 2, true>)                          \
+                      : (trips == 1 ? launch(pair_stats2_kernel<S, E, R, F, 1>) : launch(pair_stats2_kernel<S, E, R, F, 2>))) \
              : launch(pair_stats_kernel<S, E, R, F, 1>))
 #define STATS_CASE(S)                                                                                   \
     case S:                                                                                             \
@@ -1417,21 +1526,23 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
 
 extern "C" int clair_pair_stats(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
                                 const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
-                                int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
+                                int n_pairs, const float *theta_dev, int lut_size, int interp_mode,
+                                const int32_t *curve_row_base_host,
                                 float valid_lo, float valid_hi, int relative, int unc_weighting, double *sums_dev,
                                 void *stream) {
     return pair_stats_impl(val_dev, std_dev, n_frames, n_channels, plane, pair_i_host, pair_j_host, pair_ratio_host, n_pairs,
-                           theta_dev, lut_size, curve_row_base_host, valid_lo, valid_hi, relative, unc_weighting, 1, sums_dev,
+                           theta_dev, lut_size, interp_mode, curve_row_base_host, valid_lo, valid_hi, relative, unc_weighting, 1, sums_dev,
                            stream);
 }
 
 extern "C" int clair_pair_means(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
                                 const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
-                                int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
+                                int n_pairs, const float *theta_dev, int lut_size, int interp_mode,
+                                const int32_t *curve_row_base_host,
                                 float valid_lo, float valid_hi, int relative, int unc_weighting, double *sums_dev,
                                 void *stream) {
     return pair_stats_impl(val_dev, std_dev, n_frames, n_channels, plane, pair_i_host, pair_j_host, pair_ratio_host, n_pairs,
-                           theta_dev, lut_size, curve_row_base_host, valid_lo, valid_hi, relative, unc_weighting, 0, sums_dev,
+                           theta_dev, lut_size, interp_mode, curve_row_base_host, valid_lo, valid_hi, relative, unc_weighting, 0, sums_dev,
                            stream);
 }
 
@@ -1451,7 +1562,8 @@ int finalize_grad(const float *hist, double *grad, int C, int L, int n_copies, c
 
 extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
                                const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
-                               int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
+                               int n_pairs, const float *theta_dev, int lut_size, int interp_mode,
+                               const int32_t *curve_row_base_host,
                                float valid_lo, float valid_hi, int relative, int unc_weighting,
                                const double *upstream_dev, const double *mean_dev, double *grad_theta_dev,
                                void *workspace_dev, size_t workspace_bytes, void *stream) {
@@ -1460,6 +1572,8 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
         return fail(CLAIR_E_ARG, "clair_pair_grad: null buffer");
     if (n_pairs < 0 || (n_pairs > 0 && (!pair_i_host || !pair_j_host || !pair_ratio_host)))
         return fail(CLAIR_E_ARG, "clair_pair_grad: pair table missing");
+    if (int rc = check_pair_mode(fn, interp_mode, theta_dev, std_dev)) return rc;
+    const bool modes = interp_mode != CLAIR_INTERP_LINEAR;
     if (int rc = check_geometry(fn, n_frames, n_channels, plane, lut_size, true)) return rc;
     if (n_pairs > CLAIR_MAX_PAIRS) return fail(CLAIR_E_LIMIT, "clair_pair_grad: more than CLAIR_MAX_PAIRS pairs");
     const size_t need = clair_grad_workspace_bytes(n_channels, lut_size);
@@ -1485,7 +1599,7 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
         const size_t smem = fixed_bytes + per_warp * warps;
         PairParams p{};
         common_params(p, val_dev, err ? std_dev : nullptr, theta_dev, n_frames, n_channels, plane, lut_size, curve_row_base_host,
-                      valid_lo, valid_hi, unc_weighting);
+                      valid_lo, valid_hi, unc_weighting, interp_mode);
         p.upstream = upstream_dev + static_cast<int64_t>(first) * n_channels;
         p.mean = mean_dev + static_cast<int64_t>(first) * n_channels;
         p.hist = static_cast<float *>(workspace_dev);
@@ -1504,7 +1618,8 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
             return 0;
         };
         int rc;
-#define GRAD_FLAGS(E, R) (pixn == 2 ? launch(pair_grad2_kernel<E, R>) : launch(pair_grad_kernel<E, R, 1>))
+#define GRAD_FLAGS(E, R) \
+    (pixn == 2 ? (modes ? launch(pair_grad2_kernel<E, R, true>) : launch(pair_grad2_kernel<E, R>)) : launch(pair_grad_kernel<E, R, 1>))
         if (err) rc = relative ? GRAD_FLAGS(true, true) : GRAD_FLAGS(true, false);
         else rc = relative ? GRAD_FLAGS(false, true) : GRAD_FLAGS(false, false);
 #undef GRAD_FLAGS

@@ -94,6 +94,7 @@ struct LinearizeCodesParams {
     int n_channels, lut;
     int std_mode;             // kStdNone / kStdTensor / kStdMultiplier / kStdConstant
     float std_value, code_max;
+    int mode;                 // CLAIR_INTERP_* of the model
     CurveRows rows;
 };
 
@@ -137,7 +138,9 @@ __global__ void __launch_bounds__(kBlock) linearize_codes_kernel(const Linearize
     int u = static_cast<int>((pix + p.rows.base(c)) % C);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const IcrfTap t = icrf_linear(xv.v[k], s_tab + u * L, lm1);
+        IcrfTap t;
+        if (p.mode == CLAIR_INTERP_LINEAR) t = icrf_linear(xv.v[k], s_tab + u * L, lm1);
+        else icrf_mode_eval_rt(p.mode, xv.v[k], s_tab + (p.mode == CLAIR_INTERP_LOOKUP ? c : u) * L, L, lm1, t.f, t.fp);
         yv.v[k] = t.f;
         const float g = (p.std_mode != kStdNone) ? __fmul_rn(t.fp, sv.v[k]) : 0.0f;     // sqrt((f' * s)^2), linearization.py:106,132
         gv.v[k] = sqrtf(__fmul_rn(g, g));
@@ -145,39 +148,6 @@ __global__ void __launch_bounds__(kBlock) linearize_codes_kernel(const Linearize
     }
     store_stream<4>(p.lin + off, yv);
     store_stream<4>(p.sigma + off, gv);
-}
-
-// CATMULL mode (models/base.py:184-226): four taps x0-1 .. x0+2 (clamped), Catmull-Rom weights of t = xs - x0 in the
-// reference's left-to-right fp32 op order (so the value is bit-exact), rows per the same k-mod-C rule as LINEAR.
-// The derivative is the closed form sum_i w_i'(t) g_i (L-1) (the reference's autograd result differs from it by its own
-// fp32 rounding, ~3e-5 of the maximum).
-struct CatmullTaps {
-    int idx[4];
-    float w[4];
-    float dw[4];
-};
-
-__device__ __forceinline__ CatmullTaps catmull_taps(float x, int L) {
-    CatmullTaps c;
-    const float lm1 = static_cast<float>(L - 1);
-    const float xs_raw = __fmul_rn(x, lm1);
-    const float xs = fminf(fmaxf(xs_raw, 0.0f), lm1);
-    int x0;
-    const float fl = floor_small(xs, x0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) c.idx[k] = min(max(x0 + k - 1, 0), L - 1);
-    const float t = fminf(fmaxf(__fsub_rn(xs, fl), 0.0f), 1.0f);
-    const float t2 = __fmul_rn(t, t), t3 = __fmul_rn(t2, t);
-    c.w[0] = __fsub_rn(__fadd_rn(__fmul_rn(-0.5f, t3), t2), __fmul_rn(0.5f, t));
-    c.w[1] = __fadd_rn(__fsub_rn(__fmul_rn(1.5f, t3), __fmul_rn(2.5f, t2)), 1.0f);
-    c.w[2] = __fadd_rn(__fadd_rn(__fmul_rn(-1.5f, t3), __fmul_rn(2.0f, t2)), __fmul_rn(0.5f, t));
-    c.w[3] = __fsub_rn(__fmul_rn(0.5f, t3), __fmul_rn(0.5f, t2));
-    const float inside = (xs == xs_raw) ? lm1 : 0.0f;
-    c.dw[0] = inside * (-1.5f * t2 + 2.0f * t - 0.5f);
-    c.dw[1] = inside * (4.5f * t2 - 5.0f * t);
-    c.dw[2] = inside * (-4.5f * t2 + 4.0f * t + 0.5f);
-    c.dw[3] = inside * (1.5f * t2 - t);
-    return c;
 }
 
 // grid: (ceil(plane / kBlock), n_frames * C); one element per thread (CATMULL is off the hot path)
@@ -227,20 +197,6 @@ __device__ __forceinline__ float load_any_pixel(const HdrParams &p, int64_t o, i
 __device__ __forceinline__ float load_any_std(const HdrParams &p, int64_t o, float x) {
     if (p.std_mode == kStdTensor) return __ldg(p.std + o);
     return (p.std_mode == kStdMultiplier) ? __fmul_rn(x, p.std_value) : p.std_value;
-}
-
-template <int MODE>
-__device__ __forceinline__ void icrf_mode_eval(float x, const float2 *row, int L, float lm1, float &f, float &fp) {
-    if constexpr (MODE == CLAIR_INTERP_LOOKUP) {
-        f = row[icrf_lookup_index(x, lm1)].x;
-        fp = 0.0f;
-    } else {
-        const CatmullTaps t = catmull_taps(x, L);
-        const float g0 = row[t.idx[0]].x, g1 = row[t.idx[1]].x, g2 = row[t.idx[2]].x, g3 = row[t.idx[3]].x;
-        f = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t.w[0], g0), __fmul_rn(t.w[1], g1)), __fmul_rn(t.w[2], g2)),
-                      __fmul_rn(t.w[3], g3));
-        fp = t.dw[0] * g0 + t.dw[1] * g1 + t.dw[2] * g2 + t.dw[3] * g3;
-    }
 }
 
 template <int MODE>
@@ -433,10 +389,14 @@ extern "C" int clair_linearize(const float *val_dev, const float *std_dev, const
 
 extern "C" int clair_linearize_codes(const void *codes_dev, int code_bytes, float code_max, const float *std_dev, int std_mode,
                                      float std_value, const float *theta_dev, float *lin_dev, float *sigma_dev, int n_frames,
-                                     int n_channels, int64_t plane, int lut_size, const int32_t *curve_row_base_host,
-                                     void *stream) {
+                                     int n_channels, int64_t plane, int lut_size, int interp_mode,
+                                     const int32_t *curve_row_base_host, void *stream) {
     const char *fn = "clair_linearize_codes";
     if (!codes_dev || !theta_dev || !lin_dev || !sigma_dev) return fail(CLAIR_E_ARG, "clair_linearize_codes: null buffer");
+    if (interp_mode != CLAIR_INTERP_LINEAR && interp_mode != CLAIR_INTERP_LOOKUP && interp_mode != CLAIR_INTERP_CATMULL)
+        return fail(CLAIR_E_MODE, "clair_linearize_codes: interp_mode must be CLAIR_INTERP_LOOKUP, _LINEAR or _CATMULL");
+    if (interp_mode == CLAIR_INTERP_LOOKUP && std_mode != kStdNone)
+        return fail(CLAIR_E_MODE, "clair_linearize_codes: a LOOKUP model has no derivative to propagate std images through");
     if (code_bytes != 1 && code_bytes != 2) return fail(CLAIR_E_MODE, "clair_linearize_codes: code_bytes must be 1 (uint8) or 2 (uint16)");
     if (!(code_max > 0.0f)) return fail(CLAIR_E_ARG, "clair_linearize_codes: code_max must be positive");
     if (std_mode < kStdNone || std_mode > kStdConstant) return fail(CLAIR_E_MODE, "clair_linearize_codes: unknown std_mode");
@@ -451,7 +411,7 @@ extern "C" int clair_linearize_codes(const void *codes_dev, int code_bytes, floa
     LinearizeCodesParams p{};
     p.codes = codes_dev; p.std = std_dev; p.theta = theta_dev; p.lin = lin_dev; p.sigma = sigma_dev;
     p.plane = plane; p.n_channels = n_channels; p.lut = lut_size;
-    p.std_mode = std_mode; p.std_value = std_value; p.code_max = code_max;
+    p.std_mode = std_mode; p.std_value = std_value; p.code_max = code_max; p.mode = interp_mode;
     fill_rows(p.rows, curve_row_base_host, n_channels, plane);
     const size_t smem = sizeof(float2) * n_channels * lut_size + (code_bytes == 1 ? 256 * sizeof(float) : 0);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -911,6 +871,7 @@ struct FrameStatsParams {
     float *mean, *m2, *wsum, *wsq;
     int64_t plane;
     int n_frames, n_channels, lut, is_first;
+    int mode;                 // CLAIR_INTERP_* of the model
     CurveRows rows;
 };
 
@@ -938,12 +899,13 @@ __global__ void __launch_bounds__(kBlock) frame_stats_kernel(const FrameStatsPar
     for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
         const uint32_t pix = item * VEC;
         const int64_t off = static_cast<int64_t>(c) * p.plane + pix;
-        uint32_t bias[VEC];
+        uint32_t bias[VEC], urow[VEC];
         {
             uint32_t u = cur.u0;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) { bias[k] = tab_bias + u * row_bytes; u = (u + 1 == cur.C) ? 0u : u + 1; }
+            for (int k = 0; k < VEC; ++k) { urow[k] = u; bias[k] = tab_bias + u * row_bytes; u = (u + 1 == cur.C) ? 0u : u + 1; }
         }
+        const bool linear = p.mode == CLAIR_INTERP_LINEAR, lookup = p.mode == CLAIR_INTERP_LOOKUP;
         float w0[VEC], w2[VEC], s1[VEC], s2[VEC], pivot[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) { w0[k] = 0.0f; w2[k] = 0.0f; s1[k] = 0.0f; s2[k] = 0.0f; pivot[k] = 0.0f; }
@@ -963,7 +925,11 @@ __global__ void __launch_bounds__(kBlock) frame_stats_kernel(const FrameStatsPar
 #pragma unroll
                     for (int k = 0; k < VEC; ++k) {
                         float v = xv[j].v[k];
-                        if (has_model) { float fp; icrf_linear_biased(v, bias[k], lm1, v, fp); }
+                        if (has_model) {
+                            float fp;
+                            if (linear) icrf_linear_biased(v, bias[k], lm1, v, fp);
+                            else icrf_mode_eval_rt(p.mode, v, s_tab + (lookup ? static_cast<uint32_t>(c) : urow[k]) * L, L, lm1, v, fp);
+                        }
                         const float w = weighted ? wv[j].v[k] : 1.0f;
                         if (n0 + j == 0) pivot[k] = v;
                         const float d = v - pivot[k];
@@ -1008,14 +974,19 @@ __global__ void __launch_bounds__(kBlock) frame_stats_kernel(const FrameStatsPar
 }  // namespace clair
 
 extern "C" int clair_frame_stats_update(const float *val_dev, const float *weights_dev, const float *theta_dev, int n_frames,
-                                        int n_channels, int64_t plane, int lut_size, const int32_t *curve_row_base_host,
+                                        int n_channels, int64_t plane, int lut_size, int interp_mode,
+                                        const int32_t *curve_row_base_host,
                                         float *mean_state_dev, float *m2_state_dev, float *wsum_state_dev,
                                         float *wsq_state_dev, int is_first, void *stream) {
     if (!val_dev || !mean_state_dev || !m2_state_dev || !wsum_state_dev || !wsq_state_dev)
         return fail(CLAIR_E_ARG, "clair_frame_stats_update: null buffer");
     if (theta_dev == nullptr && lut_size <= 0) lut_size = 2;
+    if (theta_dev == nullptr) interp_mode = CLAIR_INTERP_LINEAR;
+    if (interp_mode != CLAIR_INTERP_LINEAR && interp_mode != CLAIR_INTERP_LOOKUP && interp_mode != CLAIR_INTERP_CATMULL)
+        return fail(CLAIR_E_MODE, "clair_frame_stats_update: interp_mode must be CLAIR_INTERP_LOOKUP, _LINEAR or _CATMULL");
     if (int rc = check_geometry("clair_frame_stats_update", n_frames, n_channels, plane, lut_size, false)) return rc;
     FrameStatsParams p{};
+    p.mode = interp_mode;
     p.val = val_dev; p.weights = weights_dev; p.theta = theta_dev;
     p.mean = mean_state_dev; p.m2 = m2_state_dev; p.wsum = wsum_state_dev; p.wsq = wsq_state_dev;
     p.plane = plane; p.n_frames = n_frames; p.n_channels = n_channels; p.lut = lut_size; p.is_first = is_first;

@@ -35,28 +35,16 @@ def normalise_transforms(gpu_transforms) -> list:
     return [gpu_transforms]
 
 
-_NATIVE_MODE = {InterpMode.LOOKUP: 1, InterpMode.LINEAR: 2, InterpMode.CATMULL: 3}     # CLAIR_INTERP_*
+NATIVE_MODE = {InterpMode.LOOKUP: 1, InterpMode.LINEAR: 2, InterpMode.CATMULL: 3}     # CLAIR_INTERP_*
 
 
 def model_table(icrf_model: Optional[ICRFModelBase], device):
     """(table (C, L) or None, CLAIR_INTERP_* code) of the model a driver was given (any interpolation mode)."""
     if icrf_model is None:
-        return None, _NATIVE_MODE[InterpMode.LINEAR]
+        return None, NATIVE_MODE[InterpMode.LINEAR]
     if not isinstance(icrf_model, ICRFModelBase):
         raise ArgumentTypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
-    return icrf_model.icrf.detach().to(device=device, dtype=torch.float32), _NATIVE_MODE[icrf_model.interpolation_mode]
-
-
-def linear_table(icrf_model: Optional[ICRFModelBase], device) -> Optional[torch.Tensor]:
-    """The (C, L) table the fused kernels evaluate in LINEAR mode, or None for `icrf_model=None`."""
-    if icrf_model is None:
-        return None
-    if not isinstance(icrf_model, ICRFModelBase):
-        raise ArgumentTypeError(f"icrf_model must be an ICRFModelBase, got {type(icrf_model)}")
-    if icrf_model.interpolation_mode is not InterpMode.LINEAR:
-        raise NotImplementedError("the fused B200 kernels evaluate the ICRF in InterpMode.LINEAR (the reference default); "
-                                  f"got {icrf_model.interpolation_mode}")
-    return icrf_model.icrf.detach().to(device=device, dtype=torch.float32)
+    return icrf_model.icrf.detach().to(device=device, dtype=torch.float32), NATIVE_MODE[icrf_model.interpolation_mode]
 
 
 def check_artefact_dataset(name, ds):

@@ -9,7 +9,7 @@ from torch.utils.data import DataLoader
 from ..common.enums import VarianceMode
 from ..common.statistics import WBOMeanVar
 from ..models.base import ICRFModelBase
-from ._common import as_device, linear_table
+from ._common import as_device, model_table
 from ..common.errors import ArgumentTypeError
 
 
@@ -19,13 +19,13 @@ def compute_video_mean_and_std(dataloader: DataLoader, device, icrf_model: Optio
     if not isinstance(dataloader, DataLoader):
         raise ArgumentTypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
     dev = as_device(device)
-    table = linear_table(icrf_model, dev)
+    table, interp_mode = model_table(icrf_model, dev)
     handler = WBOMeanVar(dim=0, variance_mode=VarianceMode.SAMPLE_FREQUENCY)
     number_of_frames = 0
     for _, val_batch, _, _ in dataloader:
         frames = val_batch.to(device=dev, non_blocking=True)
         number_of_frames += frames.shape[0]
-        handler.update_values(frames, None, table=table)
+        handler.update_values(frames, None, table=table, interp_mode=interp_mode)
     if number_of_frames == 0:
         raise ValueError("the dataloader yielded no batches")
     return handler.mean.squeeze(), torch.sqrt(handler.variance().squeeze()) / math.sqrt(number_of_frames)

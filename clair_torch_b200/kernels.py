@@ -131,7 +131,7 @@ def linearize(val: torch.Tensor, std, theta: torch.Tensor, row_base=None, device
 
     Integer ingest: `val` may hold raw uint8 / uint16 codes (device or pinned host memory); the kernel applies the
     reference's CastTo(float32) + Normalize(max_val=code_max) itself (code_max defaults to 255 / 65535) and `std` may be a
-    `datasets.StdSpec` instead of a tensor (clair_linearize_codes; LINEAR models)."""
+    `datasets.StdSpec` instead of a tensor (clair_linearize_codes; models in any InterpMode)."""
     lib = _native.load()
     if isinstance(val, torch.Tensor) and val.dtype in _CODE_DTYPES:
         return _linearize_codes(lib, val, std, theta, row_base, device, pinned_out, interp_mode, code_max)
@@ -176,9 +176,10 @@ def linearize(val: torch.Tensor, std, theta: torch.Tensor, row_base=None, device
 
 def _linearize_codes(lib, val, std, theta, row_base, device, pinned_out, interp_mode, code_max):
     """linearize() for uint8 / uint16 codes: CastTo + Normalize and the std synthesis happen in the kernel's load."""
-    if interp_mode != _native.INTERP_LINEAR:
-        raise NotImplementedError("integer ingest of the lineariser evaluates the ICRF in InterpMode.LINEAR")
     val = _code_stack(val, device is not None)
+    if interp_mode == _native.INTERP_LOOKUP and std is not None:
+        raise RuntimeError("a LOOKUP model has no derivative with respect to the image: std images cannot be propagated "
+                           "(the reference raises here too)")
     std_mode, std_value = 0, 0.0
     if std is not None and not torch.is_tensor(std):
         if not hasattr(std, "mode") or std.mode not in _STD_MODES:
@@ -200,8 +201,8 @@ def _linearize_codes(lib, val, std, theta, row_base, device, pinned_out, interp_
     keep, rows = _rows(row_base, c)
     with torch.cuda.device(dev):
         rc = lib.clair_linearize_codes(_ptr(val), code_bytes, float(default_max if code_max is None else code_max), _ptr(std),
-                                       std_mode, std_value, _ptr(th), _ptr(lin), _ptr(sigma), n, c, h * w, th.shape[1], rows,
-                                       _stream(dev))
+                                       std_mode, std_value, _ptr(th), _ptr(lin), _ptr(sigma), n, c, h * w, th.shape[1],
+                                       int(interp_mode), rows, _stream(dev))
     _native.check(rc, "clair_linearize_codes")
     return lin, sigma
 
@@ -395,16 +396,25 @@ def _pair_arrays(i_idx, j_idx, ratio):
     return pi, pj, pr
 
 
+def _check_lookup_std(theta, std, interp_mode):
+    if theta is not None and std is not None and interp_mode == _native.INTERP_LOOKUP:
+        # measure_linearity.py:57-63 / icrf_training.py:117-124: autograd.grad of an output that does not depend on the image
+        raise RuntimeError("a LOOKUP model has no derivative with respect to the image: std images cannot be propagated "
+                           "(the reference raises here too)")
+
+
 def pair_stats(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, ratio,
                theta: Optional[torch.Tensor], valid_lo: float, valid_hi: float, relative: bool,
                unc_weighting: bool, row_base=None, out: Optional[torch.Tensor] = None,
-               means_only: bool = False) -> torch.Tensor:
+               means_only: bool = False, interp_mode: int = _native.INTERP_LINEAR) -> torch.Tensor:
     """(P, C, 5) float64 sums [sum MWt, sum MWt l, sum MWt l^2, sum M err, sum M] for one batch
-    (only the first two when `means_only`, the training-step variant).
+    (only the first two when `means_only`, the training-step variant).  `interp_mode` is the InterpMode of the model
+    `theta` belongs to (any of the three).
     training/losses.py:13-108, common/general_functions.py:118-178,276-312."""
     lib = _native.load()
     val = _stack(val, "val_batch")
     std = None if std is None else _stack(std, "std_batch")
+    _check_lookup_std(theta, std, interp_mode)
     n, c, h, w = val.shape
     pi, pj, pr = _pair_arrays(i_idx, j_idx, ratio)
     p = pi.shape[0]
@@ -416,7 +426,7 @@ def pair_stats(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, rat
         entry = lib.clair_pair_means if means_only else lib.clair_pair_stats
         rc = entry(
             _ptr(val), _ptr(std), n, c, h * w, pi.ctypes.data_as(ctypes.c_void_p),
-            pj.ctypes.data_as(ctypes.c_void_p), pr.ctypes.data_as(ctypes.c_void_p), p, _ptr(th), lut, rows,
+            pj.ctypes.data_as(ctypes.c_void_p), pr.ctypes.data_as(ctypes.c_void_p), p, _ptr(th), lut, int(interp_mode), rows,
             float(np.float32(valid_lo)), float(np.float32(valid_hi)), int(bool(relative)), int(bool(unc_weighting)),
             _ptr(sums), _stream(val.device))
     _native.check(rc, "clair_pair_stats")
@@ -425,11 +435,13 @@ def pair_stats(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, rat
 
 def pair_grad(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, ratio, theta: torch.Tensor,
               valid_lo: float, valid_hi: float, relative: bool, unc_weighting: bool, upstream: torch.Tensor,
-              mean: torch.Tensor, row_base=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              mean: torch.Tensor, row_base=None, out: Optional[torch.Tensor] = None,
+              interp_mode: int = _native.INTERP_LINEAR) -> torch.Tensor:
     """(C, L) float64 gradient of the linearity loss with respect to the table."""
     lib = _native.load()
     val = _stack(val, "val_batch")
     std = None if std is None else _stack(std, "std_batch")
+    _check_lookup_std(theta, std, interp_mode)
     n, c, h, w = val.shape
     pi, pj, pr = _pair_arrays(i_idx, j_idx, ratio)
     p = pi.shape[0]
@@ -445,7 +457,7 @@ def pair_grad(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, rati
     with torch.cuda.device(val.device):
         rc = lib.clair_pair_grad(
             _ptr(val), _ptr(std), n, c, h * w, pi.ctypes.data_as(ctypes.c_void_p),
-            pj.ctypes.data_as(ctypes.c_void_p), pr.ctypes.data_as(ctypes.c_void_p), p, _ptr(th), lut, rows,
+            pj.ctypes.data_as(ctypes.c_void_p), pr.ctypes.data_as(ctypes.c_void_p), p, _ptr(th), lut, int(interp_mode), rows,
             float(np.float32(valid_lo)), float(np.float32(valid_hi)), int(bool(relative)), int(bool(unc_weighting)),
             _ptr(up), _ptr(mn), _ptr(grad), _ptr(ws), ws.numel() * 4, _stream(val.device))
     _native.check(rc, "clair_pair_grad")

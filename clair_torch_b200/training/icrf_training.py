@@ -11,17 +11,16 @@ import torch
 from torch.optim import Optimizer
 from torch.utils.data import DataLoader
 
-from .. import kernels
+from .. import _native, kernels
 from ..common.general_functions import get_valid_exposure_pairs
 from ..models.base import ICRFModelBase
-from ..inference._common import as_device, stage_batch
-from ..common.enums import InterpMode
+from ..inference._common import NATIVE_MODE, as_device, stage_batch
 from ..common.errors import ArgumentTypeError
 
 
 def linearity_loss_and_table_grad(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
                                   upper_valid_threshold, use_relative_linearity_loss, use_uncertainty_weighting,
-                                  want_grad=True, row_base=None, reduce_fn=None):
+                                  want_grad=True, row_base=None, reduce_fn=None, interp_mode=_native.INTERP_LINEAR):
     """Linearity loss per channel (C,) float64, spatial means (P, C), and d(sum_c loss_c)/d table (C, L) float64.
 
     `reduce_fn`, if given, is applied in place to the (P, C, 5) sums and to the (C, L) gradient: the data-parallel
@@ -29,7 +28,7 @@ def linearity_loss_and_table_grad(images, stds, i_idx, j_idx, ratio_pairs, table
     """
     sums = kernels.pair_stats(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
                               upper_valid_threshold, use_relative_linearity_loss, use_uncertainty_weighting,
-                              row_base=row_base, means_only=True)
+                              row_base=row_base, means_only=True, interp_mode=interp_mode)
     if reduce_fn is not None:
         reduce_fn(sums)
     linearity_loss, spatial, upstream, mean_for_grad = kernels.pair_upstream(sums)
@@ -37,37 +36,10 @@ def linearity_loss_and_table_grad(images, stds, i_idx, j_idx, ratio_pairs, table
     if want_grad:
         grad = kernels.pair_grad(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
                                  upper_valid_threshold, use_relative_linearity_loss, use_uncertainty_weighting,
-                                 upstream, mean_for_grad, row_base=row_base)
+                                 upstream, mean_for_grad, row_base=row_base, interp_mode=interp_mode)
         if reduce_fn is not None:
             reduce_fn(grad)
     return linearity_loss, spatial, grad
-
-
-def _composed_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, relative, unc_weighting, alpha, beta,
-                         gamma, delta, lo, hi):
-    """LOOKUP / CATMULL models: the reference's step (icrf_training.py:105-156) through autograd, with the model's
-    forward, derivative and table-gradient kernels underneath and the pair algebra as torch ops (see
-    inference.measure_linearity.composed_linearity_terms).  Off the measured path: the reference default is LINEAR."""
-    from ..inference.measure_linearity import composed_linearity_terms
-    from .losses import (compute_endpoint_penalty, compute_monotonicity_penalty, compute_range_penalty,
-                         compute_smoothness_penalty)
-    curve = icrf_model.icrf
-    with torch.enable_grad():
-        spatial, _, _ = composed_linearity_terms(icrf_model, images, stds, i_idx, j_idx, ratio_pairs, lo, hi, relative,
-                                                 unc_weighting, create_graph=True)
-        linearity_loss = torch.sqrt((spatial ** 2).sum(dim=0))
-        loss = (linearity_loss + alpha * compute_monotonicity_penalty(curve, per_channel=True)
-                + beta * compute_range_penalty(curve, per_channel=True)
-                + gamma * compute_endpoint_penalty(curve, per_channel=True)
-                + delta * compute_smoothness_penalty(curve, per_channel=True))
-        if curve.requires_grad:
-            loss.sum().backward()            # the C backward() calls of :148-149 accumulate exactly this
-    for optimizer in optimizers:
-        optimizer.step()
-    icrf_model.update_icrf()
-    if len(optimizers) == 1:
-        loss = torch.sum(loss)
-    return loss.detach()
 
 
 def train_icrf_step(icrf_model: ICRFModelBase, optimizers: list[Optimizer], images: torch.Tensor,
@@ -84,22 +56,16 @@ def train_icrf_step(icrf_model: ICRFModelBase, optimizers: list[Optimizer], imag
     i_idx, j_idx, ratio_pairs = get_valid_exposure_pairs(exposures, exposure_ratio_threshold)
     for optimizer in optimizers:
         optimizer.zero_grad()
-    if icrf_model.interpolation_mode is not InterpMode.LINEAR:
-        if row_base is not None or reduce_fn is not None:
-            raise NotImplementedError("row-band sharded training uses the fused kernels: InterpMode.LINEAR only")
-        return _composed_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs,
-                                    use_relative_linearity_loss, use_uncertainty_weighting, alpha, beta, gamma, delta,
-                                    lower_valid_threshold, upper_valid_threshold)
-    return _linear_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, use_relative_linearity_loss,
+    return _fused_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, use_relative_linearity_loss,
                               use_uncertainty_weighting, alpha, beta, gamma, delta, lower_valid_threshold,
                               upper_valid_threshold, row_base, reduce_fn)
 
 
-def _linear_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, use_relative_linearity_loss,
-                       use_uncertainty_weighting, alpha, beta, gamma, delta, lower_valid_threshold, upper_valid_threshold,
-                       row_base=None, reduce_fn=None, table=None):
-    """The LINEAR-mode step on the fused kernels.  `table` overrides where the kernels read the curve from (the
-    captured step reads a static copy, see GraphedTrainStep); the autograd edge is always icrf_model.icrf."""
+def _fused_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, use_relative_linearity_loss,
+                      use_uncertainty_weighting, alpha, beta, gamma, delta, lower_valid_threshold, upper_valid_threshold,
+                      row_base=None, reduce_fn=None, table=None):
+    """The step on the fused kernels, for a model in any InterpMode.  `table` overrides where the kernels read the curve
+    from (the captured step reads a static copy, see GraphedTrainStep); the autograd edge is always icrf_model.icrf."""
     curve = icrf_model.icrf                                        # (C, L); a function of the parameters after update_icrf
     if table is None:
         table = curve.detach()
@@ -107,7 +73,7 @@ def _linear_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio
     linearity_loss, _, grad = linearity_loss_and_table_grad(
         images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold, upper_valid_threshold,
         use_relative_linearity_loss, use_uncertainty_weighting, want_grad=connected, row_base=row_base,
-        reduce_fn=reduce_fn)
+        reduce_fn=reduce_fn, interp_mode=NATIVE_MODE[icrf_model.interpolation_mode])
     if grad is None:
         grad = torch.zeros(tuple(table.shape), dtype=torch.float64, device=table.device)
     penalties = kernels.curve_penalties(table, alpha, beta, gamma, delta, grad)     # adds d penalties / d table to grad
@@ -139,7 +105,7 @@ class GraphedTrainStep:
 
     A step is ~35 launches (2 large kernels, 4 small ones, the autograd edge table -> parameters, the optimisers,
     update_icrf) and the GPU finishes them faster than Python can enqueue them: replaying the captured sequence makes the
-    step GPU-bound.  Requirements: InterpMode.LINEAR, optimisers created with `capturable=True`, the model already
+    step GPU-bound.  Requirements: optimisers created with `capturable=True`, the model already
     connected to its parameters (at least one eager step has run).  `row_base` / `reduce_fn` are the
     row-band arguments of train_icrf_step: an NCCL all-reduce passed as `reduce_fn` is captured with the kernels.
     The kernels read the curve from a static copy that the captured sequence refreshes after update_icrf, and the
@@ -150,8 +116,6 @@ class GraphedTrainStep:
                  stds: Optional[torch.Tensor], exposures: torch.Tensor, *, use_relative_linearity_loss=True,
                  use_uncertainty_weighting=True, alpha=1.0, beta=1.0, gamma=1.0, delta=1.0, lower_valid_threshold=1 / 255,
                  upper_valid_threshold=254 / 255, exposure_ratio_threshold=0.1, row_base=None, reduce_fn=None):
-        if icrf_model.interpolation_mode is not InterpMode.LINEAR:
-            raise NotImplementedError("GraphedTrainStep: InterpMode.LINEAR only")
         if not _capturable(optimizers):
             raise ValueError("GraphedTrainStep needs optimisers created with capturable=True")
         if not icrf_model.icrf.requires_grad:
@@ -171,7 +135,7 @@ class GraphedTrainStep:
             icrf_model.update_icrf()                               # same values; a fresh edge on the capturing stream
             for optimizer in optimizers:
                 optimizer.zero_grad()
-            loss = _linear_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, *args,
+            loss = _fused_train_step(icrf_model, optimizers, images, stds, i_idx, j_idx, ratio_pairs, *args,
                                       row_base=row_base, reduce_fn=reduce_fn, table=self._table)
             self._table.copy_(icrf_model.icrf.detach())
             self._loss = loss
@@ -228,7 +192,7 @@ def train_icrf(dataloader: DataLoader, batch_size: int, device, icrf_model: ICRF
     step_kw = dict(use_relative_linearity_loss=use_relative_linearity_loss, use_uncertainty_weighting=use_uncertainty_weighting,
                    alpha=alpha, beta=beta, gamma=gamma, delta=delta, lower_valid_threshold=lower_valid_threshold,
                    upper_valid_threshold=upper_valid_threshold, exposure_ratio_threshold=exposure_ratio_threshold)
-    graphable = (use_cuda_graph and icrf_model.interpolation_mode is InterpMode.LINEAR and _capturable(optimizers))
+    graphable = use_cuda_graph and _capturable(optimizers)
     seen, graphs = {}, {}                                          # batch key -> eager visits / captured step
     for epoch in range(epochs):
         running_loss = torch.zeros(channels if len(optimizers) > 1 else (), dtype=torch.float64, device=dev)

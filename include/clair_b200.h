@@ -37,7 +37,7 @@ extern "C" {
 #define CLAIR_API
 #endif
 
-#define CLAIR_ABI_VERSION 2
+#define CLAIR_ABI_VERSION 3
 #define CLAIR_MAX_FRAMES 64     /* exposure frames per batch (exposure times travel as kernel arguments) */
 #define CLAIR_MAX_CHANNELS 8
 #define CLAIR_MAX_LUT 1024      /* ICRF samples per channel (reference default 256) */
@@ -110,7 +110,8 @@ CLAIR_API int clair_linearize(const float *val_dev, const float *std_dev, const 
  */
 CLAIR_API int clair_linearize_codes(const void *codes_dev, int code_bytes, float code_max, const float *std_dev, int std_mode,
                           float std_value, const float *theta_dev, float *lin_dev, float *sigma_dev, int n_frames,
-                          int n_channels, int64_t plane, int lut_size, const int32_t *curve_row_base_host, void *stream);
+                          int n_channels, int64_t plane, int lut_size, int interp_mode, const int32_t *curve_row_base_host,
+                          void *stream);
 
 /*
  * clair_linearize for images that live in page-locked HOST memory and whose results are wanted there too (the
@@ -282,12 +283,13 @@ CLAIR_API int clair_flat_field_correct(void *value_dev, int value_f64, float *si
  * (clair_torch/inference/inferential_statistics.py:19-49); SURVEY.md §8(f) rank 3.
  *   val_dev       (n_frames, C, plane) fp32 batch of frames (any n_frames)
  *   weights_dev   same shape, or NULL (then W_B = n_frames, as statistics.py:226-229)
- *   theta_dev     (C, L) table to linearise the frames first (LINEAR), or NULL
+ *   theta_dev     (C, L) table to linearise the frames first (interp_mode = the model's InterpMode), or NULL
  *   mean / m2 / wsum / wsq state   (C, plane) fp32 each: running mean, M2, sum of weights, sum of squared weights;
  *                 overwritten when is_first, merged (Chan / West) otherwise
  */
 CLAIR_API int clair_frame_stats_update(const float *val_dev, const float *weights_dev, const float *theta_dev, int n_frames,
-                             int n_channels, int64_t plane, int lut_size, const int32_t *curve_row_base_host,
+                             int n_channels, int64_t plane, int lut_size, int interp_mode,
+                             const int32_t *curve_row_base_host,
                              float *mean_state_dev, float *m2_state_dev, float *wsum_state_dev, float *wsq_state_dev,
                              int is_first, void *stream);
 
@@ -301,6 +303,10 @@ CLAIR_API int clair_frame_stats_update(const float *val_dev, const float *weight
  *
  *   pair_i_host, pair_j_host, pair_ratio_host   P pairs from get_valid_exposure_pairs (int32, int32, float64)
  *   theta_dev            (C, L) table or NULL (identity linearisation, measure_linearity.py:53)
+ *   interp_mode          the model's InterpMode (ignored when theta_dev is NULL): CLAIR_INTERP_LINEAR (models/base.py:160-182),
+ *                        CLAIR_INTERP_CATMULL (:184-226) or CLAIR_INTERP_LOOKUP (:138-158).  A LOOKUP model has no derivative
+ *                        with respect to the image, so std_dev must be NULL with it (CLAIR_E_MODE; the reference's
+ *                        autograd.grad raises at measure_linearity.py:57-63 / icrf_training.py:117-124)
  *   valid_lo, valid_hi   inclusive validity range, compared in fp32 (training default 1/255, 254/255)
  *   relative             use_relative_linearity_loss
  *   unc_weighting        use_uncertainty_weighting (only has an effect when std_dev != NULL)
@@ -312,7 +318,8 @@ CLAIR_API int clair_frame_stats_update(const float *val_dev, const float *weight
  */
 CLAIR_API int clair_pair_stats(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
                      const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
-                     int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
+                     int n_pairs, const float *theta_dev, int lut_size, int interp_mode,
+                     const int32_t *curve_row_base_host,
                      float valid_lo, float valid_hi, int relative, int unc_weighting, double *sums_dev,
                      void *stream);
 
@@ -323,7 +330,8 @@ CLAIR_API int clair_pair_stats(const float *val_dev, const float *std_dev, int n
  */
 CLAIR_API int clair_pair_means(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
                      const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
-                     int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
+                     int n_pairs, const float *theta_dev, int lut_size, int interp_mode,
+                     const int32_t *curve_row_base_host,
                      float valid_lo, float valid_hi, int relative, int unc_weighting, double *sums_dev,
                      void *stream);
 
@@ -348,7 +356,9 @@ CLAIR_API int clair_curve_penalties(const float *theta_dev, int n_channels, int 
 /*
  * Gradient of the linearity loss of one train_icrf step with respect to the ICRF table — replaces the C
  * `loss[c].backward(retain_graph=True)` passes (training/icrf_training.py:148-149) for the linearity term,
- * in closed form.  Arguments as clair_pair_stats, plus
+ * in closed form.  With CLAIR_INTERP_CATMULL the upstream of each frame element goes to its four
+ * Catmull-Rom taps (models/base.py:219-226), with CLAIR_INTERP_LOOKUP to its nearest sample in the true channel row
+ * (:158).  Arguments as clair_pair_stats, plus
  *   upstream_dev    (P, C) float64: U[p,c] = dLoss_c/dmean[p,c] / max(s0[p,c],1e-8)
  *   mean_dev        (P, C) float64: the spatial means (needed when the weights depend on the curve)
  *   grad_theta_dev  (C, L) float64, ACCUMULATED into (zero it first).
@@ -356,7 +366,8 @@ CLAIR_API int clair_curve_penalties(const float *theta_dev, int n_channels, int 
  */
 CLAIR_API int clair_pair_grad(const float *val_dev, const float *std_dev, int n_frames, int n_channels, int64_t plane,
                     const int32_t *pair_i_host, const int32_t *pair_j_host, const double *pair_ratio_host,
-                    int n_pairs, const float *theta_dev, int lut_size, const int32_t *curve_row_base_host,
+                    int n_pairs, const float *theta_dev, int lut_size, int interp_mode,
+                    const int32_t *curve_row_base_host,
                     float valid_lo, float valid_hi, int relative, int unc_weighting,
                     const double *upstream_dev, const double *mean_dev, double *grad_theta_dev,
                     void *workspace_dev, size_t workspace_bytes, void *stream);

@@ -221,7 +221,7 @@ def test_kernels_do_not_write_outside_their_outputs(ct):
         assert lib.clair_dark_field_mix(v.data_ptr(), s.data_ptr(), dark.data_ptr(), dark.data_ptr(), n, 3, h, w, 0.05, 50.0,
                                         mixed.data_ptr(), seff.data_ptr(), stream) == 0
         states = [carve(numel) for _ in range(4)]
-        assert lib.clair_frame_stats_update(v.data_ptr(), None, theta.data_ptr(), n, 3, plane, 256, None, states[0][1].data_ptr(),
+        assert lib.clair_frame_stats_update(v.data_ptr(), None, theta.data_ptr(), n, 3, plane, 256, 2, None, states[0][1].data_ptr(),
                                             states[1][1].data_ptr(), states[2][1].data_ptr(), states[3][1].data_ptr(), 1, stream) == 0
         i, j, r = orc.exposure_pairs(t, 0.0)
         i32, j32 = np.ascontiguousarray(i, dtype=np.int32), np.ascontiguousarray(j, dtype=np.int32)
@@ -230,7 +230,7 @@ def test_kernels_do_not_write_outside_their_outputs(ct):
         if n <= 16:
             assert lib.clair_pair_stats(v.data_ptr(), s.data_ptr(), n, 3, plane, i32.ctypes.data_as(ctypes.c_void_p),
                                         j32.ctypes.data_as(ctypes.c_void_p), r.ctypes.data_as(ctypes.c_void_p), p, theta.data_ptr(), 256,
-                                        None, 1 / 255, 254 / 255, 1, 1, sums.data_ptr(), stream) == 0
+                                        2, None, 1 / 255, 254 / 255, 1, 1, sums.data_ptr(), stream) == 0
         torch.cuda.synchronize()
         assert intact(rb, numel) and intact(sb, numel) and intact(lb, n * numel) and intact(gb, n * numel)
         assert intact(mb, n * numel) and intact(eb, n * numel) and all(intact(b, numel) for b, _ in states)

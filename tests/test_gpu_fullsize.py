@@ -38,15 +38,23 @@ def test_c1_full_size_against_c_oracle(ct):
     assert torch.isfinite(rad).all() and torch.isfinite(sig).all() and (sig >= 0).all()
 
 
-def test_c4_stack_shape_16bit_nine_frames(ct):
-    """One c4-style stack (9 frames, 16-bit), cropped to 1/8 of 24 MP so the oracle stays in seconds: exercises the
-    N > 8 single-pass kernel with float64 sums."""
-    val, std, t = ct.synthetic.make_stack(9, 3, 500, 6000, bits=16, seed=4567, device=DEV)
+def test_c4_full_stack_against_c_oracle(ct):
+    """Config 4: one whole 9-frame 24 MP (4000 x 6000) 16-bit stack, fp32 val + std (the N = 9 register kernel the bench
+    times), every pixel against the C oracle; and the same stack as uint16 camera codes is bit-identical."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.datasets import StdSpec
+    val, std, t = ct.synthetic.make_stack(9, 3, 4000, 6000, bits=16, seed=4567, device=DEV)
     theta = ct.synthetic.reference_curve(3)
     rad, sig = _merge(ct, val, std, t, theta.to(DEV))
     o_rad, o_sig = corc.hdr_merge(val.cpu().numpy(), std.cpu().numpy(), t, theta.numpy(), True)
     assert max_rel(rad.cpu().numpy(), o_rad) < 2e-6
     assert max_rel(sig.cpu().numpy(), o_sig) < 5e-6
+    del o_rad, o_sig, std
+    codes = torch.round(val * 65535.0).to(torch.int32).to(torch.uint16)
+    del val
+    rad_c, sig_c = kernels.hdr_merge_update(kernels.HdrMergeState(), codes, StdSpec("multiplier", 0.05), t, theta.to(DEV), True, True,
+                                            radiance_dtype=torch.float32)
+    assert torch.equal(rad_c, rad) and torch.equal(sig_c, sig)
 
 
 def test_merge_properties_at_c1_size(ct):
@@ -118,11 +126,20 @@ def test_c2_training_step_full_size_against_c_oracle(ct):
         assert max_abs_over_max(grad.cpu().numpy(), o_grad) < TOL
 
 
-def test_c3_linearity_quarter_size_against_c_oracle(ct):
-    """Config 3 shape (16 exposures, 16-bit, P = 29) on a 540-row crop of the 4K frame."""
+def _mask_counts_torch(val, i, j, lo, hi):
+    """Population count of get_pairwise_valid_pixel_mask (common/general_functions.py:276-312) per (pair, channel) with
+    plain torch compares on the device: inclusive bounds, compared in fp32."""
+    lo32, hi32 = float(np.float32(lo)), float(np.float32(hi))
+    ok = (val >= lo32) & (val <= hi32)
+    return torch.stack([(ok[int(a)] & ok[int(b)]).sum(dim=(1, 2)) for a, b in zip(i, j)]).to(torch.float64)
+
+
+def test_c3_linearity_full_size_against_c_oracle(ct):
+    """Config 3: 16 exposures of 4K (2160 x 3840) 16-bit RGB, P = 29, uncertainty-weighted relative loss — all three
+    outputs against the C oracle at full size, and the validity-mask population counts exactly."""
     from clair_torch_b200 import kernels
     from clair_torch_b200.inference.measure_linearity import spatial_statistics
-    val, std, t = ct.synthetic.make_stack(16, 3, 540, 3840, bits=16, seed=3456, device=DEV)
+    val, std, t = ct.synthetic.make_stack(16, 3, 2160, 3840, bits=16, seed=3456, device=DEV)
     theta = ct.synthetic.reference_curve(3)
     i, j, r = ct.common.get_valid_exposure_pairs(torch.from_numpy(t), 0.2)
     assert len(i) == 29
@@ -132,11 +149,49 @@ def test_c3_linearity_quarter_size_against_c_oracle(ct):
     assert max_rel(mean.cpu().numpy(), o_mean) < 2e-6
     assert max_rel(sd.cpu().numpy(), o_sd) < 2e-6
     assert max_rel(err.cpu().numpy(), o_err) < 2e-6
-    # the validity mask, through its population count, is exact
+    assert torch.equal(sums[..., 4], _mask_counts_torch(val, i, j, 1 / 255, 254 / 255))
+    # and against the numpy oracle's boolean mask on a crop
     mask = orc.pair_valid_mask(val[:, :, :64].cpu().numpy(), i.numpy(), j.numpy(), 1 / 255, 254 / 255)
     part = kernels.pair_stats(val[:, :, :64].contiguous(), std[:, :, :64].contiguous(), i, j, r, theta.to(DEV), 1 / 255,
                               254 / 255, True, True)
     assert np.array_equal(part[..., 4].cpu().numpy(), mask.sum(axis=(2, 3)).astype(np.float64))
+
+
+def test_c5_exposure_pair_full_size_against_c_oracle(ct):
+    """Config 5: one 100.7 MP (8192 x 12288) 16-bit exposure pair, script settings (P = 1): loss, spatial mean, mask count
+    and table gradient of the whole image against the C oracle; a 4-band split with all-reduced (here: added) sums and
+    gradient reproduces it — what the data-parallel step computes."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.training import linearity_loss_and_table_grad
+    h, w = 8192, 12288
+    val, std, _ = ct.synthetic.make_stack(2, 3, h, w, bits=16, seed=5678, device=DEV)
+    t = np.array([0.01, 0.02])
+    theta = torch.stack([torch.linspace(0, 1, 256) ** (2.5 + 0.15 * c) for c in range(3)])
+    i, j, r = ct.common.get_valid_exposure_pairs(torch.from_numpy(t), 0.25)
+    assert len(i) == 1
+    lin, spatial, grad = linearity_loss_and_table_grad(val, std, i, j, r, theta.to(DEV), 1 / 255, 254 / 255, True, False)
+    o_lin, o_mean, o_grad = corc.train_grad(val.cpu().numpy(), std.cpu().numpy(), i.numpy(), j.numpy(), r.numpy(), theta.numpy(),
+                                            relative=True, unc_weighting=False)
+    assert max_rel(lin.cpu().numpy(), o_lin) < 2e-6
+    assert max_rel(spatial.cpu().numpy(), o_mean) < 2e-6
+    assert max_abs_over_max(grad.cpu().numpy(), o_grad) < TOL
+    sums = kernels.pair_stats(val, std, i, j, r, theta.to(DEV), 1 / 255, 254 / 255, True, False)
+    assert torch.equal(sums[..., 4], _mask_counts_torch(val, i, j, 1 / 255, 254 / 255))
+    # row bands: sums added, upstream from the total, gradients added
+    bands = [(0, 2048), (2048, 4100), (4100, 6001), (6001, h)]
+    acc = torch.zeros((1, 3, 5), dtype=torch.float64, device=DEV)
+    parts = []
+    for r0, r1 in bands:
+        rb = kernels.shard_row_base(3, h, w, r0)
+        bv, bs = val[:, :, r0:r1].contiguous(), std[:, :, r0:r1].contiguous()
+        parts.append((bv, bs, rb))
+        kernels.pair_stats(bv, bs, i, j, r, theta.to(DEV), 1 / 255, 254 / 255, True, False, row_base=rb, out=acc, means_only=True)
+    lin_b, mean_b, up, mfg = kernels.pair_upstream(acc)
+    g_acc = torch.zeros((3, 256), dtype=torch.float64, device=DEV)
+    for bv, bs, rb in parts:
+        kernels.pair_grad(bv, bs, i, j, r, theta.to(DEV), 1 / 255, 254 / 255, True, False, up, mfg, row_base=rb, out=g_acc)
+    assert max_rel(lin_b.cpu().numpy(), o_lin) < 2e-6
+    assert max_abs_over_max(g_acc.cpu().numpy(), o_grad) < TOL
 
 
 def test_row_band_statistics_add_up(ct):

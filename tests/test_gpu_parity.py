@@ -326,8 +326,8 @@ def test_pair_stats_degenerate_spread(ct):
 # ---- training step -----------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", golden_names("trainstep_catmull"))
 def test_train_step_catmull_golden(ct, name):
-    """A CATMULL model trains through the composed device path (model kernels + torch pair algebra): loss and the
-    Adam-updated table of every recorded step, teacher-forced like the LINEAR test below."""
+    """A CATMULL model trains through the same fused pair kernels as a LINEAR one (four-tap evaluation and scatter): loss
+    and the updated table of every recorded step, teacher-forced like the LINEAR test below."""
     from clair_torch_b200 import ICRFModelDirect, InterpMode, train_icrf_step
     z = golden(name)
     val, std = torch.from_numpy(z["val"]).to(DEV), torch.from_numpy(z["std"]).to(DEV)
@@ -348,6 +348,87 @@ def test_train_step_catmull_golden(ct, name):
         grad = theta.astype(np.float64) - model.icrf.detach().cpu().numpy().astype(np.float64)
         want = z[f"grad_theta_{step}"]
         assert np.max(np.abs(grad - want)) < 1e-5 * np.max(np.abs(want)) + 2e-7       # fp32 parameter update rounding
+
+
+@pytest.mark.parametrize("mode,with_std", [("catmull", True), ("catmull", False), ("lookup", False)])
+@pytest.mark.parametrize("shape", [(6, 3, 40, 64), (5, 3, 21, 35), (7, 1, 30, 50), (4, 4, 17, 26)])
+def test_pair_kernels_all_modes_vs_oracle(ct, mode, with_std, shape):
+    """The fused pair kernels with LOOKUP / CATMULL models (models/base.py:138-158, :184-226) against the numpy oracle:
+    statistics in all flag combinations and the table gradient — packed kernels (H*W % 4 == 0), the scalar ones (odd
+    planes) and channel counts other than 3."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.inference.measure_linearity import spatial_statistics
+    n, c, h, w = shape
+    val, std, t = ct.synthetic.make_stack(n, c, h, w, bits=16, seed=n * 100 + w)
+    if not with_std:
+        std = None
+    theta = ct.synthetic.reference_curve(c)
+    code = {"lookup": ct._native.INTERP_LOOKUP, "catmull": ct._native.INTERP_CATMULL}[mode]
+    i_idx, j_idx, ratio = ct.common.get_valid_exposure_pairs(torch.from_numpy(t), 0.1)
+    dv, ds = val.to(DEV), None if std is None else std.to(DEV)
+    for relative in (True, False):
+        for unc in (True, False):
+            sums = kernels.pair_stats(dv, ds, i_idx, j_idx, ratio, theta.to(DEV), 1 / 255, 254 / 255, relative, unc, interp_mode=code)
+            mean, sd, err = spatial_statistics(sums, with_std)
+            _, o_mean, o_sd, o_err = orc.linearity_stats(val.numpy(), None if std is None else std.numpy(), t, theta.numpy(), 0.1,
+                                                         relative=relative, unc_weighting=unc, mode=mode)
+            assert max_rel(mean.cpu().numpy(), o_mean) < TOL and max_rel(sd.cpu().numpy(), o_sd) < TOL
+            if with_std:
+                assert max_rel(err.cpu().numpy(), o_err) < TOL
+            from clair_torch_b200.training import linearity_loss_and_table_grad
+            lin, spatial, grad = linearity_loss_and_table_grad(dv, ds, i_idx, j_idx, ratio, theta.to(DEV), 1 / 255, 254 / 255,
+                                                               relative, unc, interp_mode=code)
+            o = orc.train_loss_and_grad(val.numpy(), None if std is None else std.numpy(), t, theta.numpy(), 0.1, relative=relative,
+                                        unc_weighting=unc, mode=mode)
+            assert max_rel(lin.cpu().numpy(), o["linloss"]) < TOL
+            assert max_abs_over_max(grad.cpu().numpy(), o["grad_lin"]) < TOL
+
+
+@pytest.mark.parametrize("mode", ["catmull", "lookup"])
+def test_row_band_and_graphed_training_in_every_mode(ct, mode):
+    """Row-band sharding (sums and gradient added over bands, the all-reduce of the data-parallel step) and the CUDA-graph
+    step work for LOOKUP / CATMULL models like they do for LINEAR ones."""
+    from clair_torch_b200 import ICRFModelDirect, InterpMode, kernels
+    from clair_torch_b200.training import linearity_loss_and_table_grad
+    imode = {"catmull": InterpMode.CATMULL, "lookup": InterpMode.LOOKUP}[mode]
+    code = {"lookup": ct._native.INTERP_LOOKUP, "catmull": ct._native.INTERP_CATMULL}[mode]
+    val, std, t = ct.synthetic.make_stack(6, 3, 60, 100, bits=16, seed=91)
+    dv = val.to(DEV)
+    ds = std.to(DEV) if mode == "catmull" else None
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    i_idx, j_idx, ratio = ct.common.get_valid_exposure_pairs(torch.from_numpy(t), 0.1)
+    lin_w, sp_w, g_w = linearity_loss_and_table_grad(dv, ds, i_idx, j_idx, ratio, theta, 1 / 255, 254 / 255, True, True, interp_mode=code)
+    acc = torch.zeros((len(i_idx), 3, 5), dtype=torch.float64, device=DEV)
+    bands = [(0, 17), (17, 41), (41, 60)]
+    for r0, r1 in bands:
+        rb = kernels.shard_row_base(3, 60, 100, r0)
+        kernels.pair_stats(dv[:, :, r0:r1].contiguous(), None if ds is None else ds[:, :, r0:r1].contiguous(), i_idx, j_idx, ratio, theta,
+                           1 / 255, 254 / 255, True, True, row_base=rb, out=acc, means_only=True, interp_mode=code)
+    lin_b, mean_b, up, mfg = kernels.pair_upstream(acc)
+    g_b = torch.zeros((3, 256), dtype=torch.float64, device=DEV)
+    for r0, r1 in bands:
+        rb = kernels.shard_row_base(3, 60, 100, r0)
+        kernels.pair_grad(dv[:, :, r0:r1].contiguous(), None if ds is None else ds[:, :, r0:r1].contiguous(), i_idx, j_idx, ratio, theta,
+                          1 / 255, 254 / 255, True, True, up, mfg, row_base=rb, out=g_b, interp_mode=code)
+    assert torch.allclose(lin_b, lin_w, rtol=1e-7, atol=0) and (g_b - g_w).abs().max() <= 1e-6 * g_w.abs().max()
+    # graph replay == eager steps (8-bit codes sit exactly on table samples, so no table entry receives a gradient that is
+    # pure rounding noise — Adam's first steps move every entry by +-lr whatever the magnitude of its gradient)
+    def fresh():
+        m = ICRFModelDirect(256, 3, imode, 2.5).to(DEV)
+        return m, [torch.optim.Adam(m.channel_params(c), lr=1e-3, capturable=True) for c in range(3)]
+    kw = dict(use_relative_linearity_loss=True, use_uncertainty_weighting=True, alpha=10.0, exposure_ratio_threshold=0.2)
+    val, std, t = ct.synthetic.make_stack(6, 3, 96, 128, bits=8, seed=77)
+    dv = val.to(DEV)
+    ds = std.to(DEV) if mode == "catmull" else None
+    m1, o1 = fresh()
+    eager = [ct.train_icrf_step(m1, o1, dv, ds, torch.from_numpy(t), **kw) for _ in range(5)]
+    m2, o2 = fresh()
+    first = [ct.train_icrf_step(m2, o2, dv, ds, torch.from_numpy(t), **kw) for _ in range(2)]
+    step = ct.GraphedTrainStep(m2, o2, dv, ds, torch.from_numpy(t), **kw)
+    replayed = [step() for _ in range(3)]
+    for a, b in zip(eager, first + replayed):
+        assert max_rel(b.cpu().numpy(), a.cpu().numpy()) < 1e-6
+    assert max_abs_over_max(m2.icrf.detach().cpu().numpy(), m1.icrf.detach().cpu().numpy()) < 1e-6
 
 
 def test_lookup_model_errors_and_table_gradient(ct):
@@ -779,13 +860,19 @@ def test_linearize_integer_ingest_is_bit_identical(ct, bits):
     ref_lin, ref_sig = ct.kernels.linearize(x.to(DEV), (x * m).to(DEV), theta)
     for k, (lin, sig, meta) in enumerate(ct.linearize_dataset_generator(DataLoader(ds, batch_size=1, collate_fn=view), DEV, model)):
         assert torch.equal(lin, ref_lin[k].cpu()) and torch.equal(sig, ref_sig[k].cpu())
-    # errors: StdSpec without codes, odd plane, non-LINEAR model
+    # LOOKUP / CATMULL models take the same integer-ingest kernel
+    for mode, spec, std_f32 in ((ct._native.INTERP_CATMULL, StdSpec("multiplier", 0.05), x * m), (ct._native.INTERP_CATMULL, None, None),
+                                (ct._native.INTERP_LOOKUP, None, None)):
+        a = ct.kernels.linearize(codes.to(DEV), spec, theta, interp_mode=mode)
+        b = ct.kernels.linearize(x.to(DEV), None if std_f32 is None else std_f32.to(DEV), theta, interp_mode=mode)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # errors: StdSpec without codes, odd plane, std images through a LOOKUP model (as the reference's autograd call)
     with pytest.raises(ValueError):
         ct.kernels.linearize(x.to(DEV), StdSpec("multiplier", 0.05), theta)
     with pytest.raises(ValueError):
         ct.kernels.linearize(codes[:, :, :3, :5].contiguous().to(DEV), None, theta)
-    with pytest.raises(NotImplementedError):
-        ct.kernels.linearize(codes.to(DEV), None, theta, interp_mode=ct._native.INTERP_LOOKUP)
+    with pytest.raises(RuntimeError):
+        ct.kernels.linearize(codes.to(DEV), StdSpec("multiplier", 0.05), theta, interp_mode=ct._native.INTERP_LOOKUP)
 
 
 # ---- streaming frame statistics -------------------------------------------------
@@ -815,6 +902,23 @@ def test_compute_video_mean_and_std_golden(ct, name):
     mean, sem = ct.compute_video_mean_and_std(loader, DEV, model)
     assert max_rel(mean.cpu().numpy(), z["mean"]) < TOL
     assert max_rel(sem.cpu().numpy(), z["sem"]) < 3e-5
+
+
+@pytest.mark.parametrize("mode", ["catmull", "lookup"])
+def test_video_statistics_with_lookup_and_catmull_models(ct, mode):
+    """compute_video_mean_and_std linearises inside the statistics kernel for any InterpMode: equal to running the model's
+    own forward kernel first and the statistics on its output."""
+    from clair_torch_b200.common.statistics import WBOMeanVar
+    from clair_torch_b200.datasets import ExposureStackDataset, custom_collate
+    val, _, t = ct.synthetic.make_stack(9, 3, 24, 40, bits=8, seed=3, std_multiplier=None)
+    model = _model(ct, ct.synthetic.reference_curve(3).numpy(), mode)
+    loader = DataLoader(ExposureStackDataset(list(val), None, list(t)), batch_size=4, shuffle=False, collate_fn=custom_collate)
+    mean, sem = ct.compute_video_mean_and_std(loader, DEV, model)
+    h = WBOMeanVar(dim=0, variance_mode=ct.common.VarianceMode.SAMPLE_FREQUENCY)
+    for _, vb, _, _ in loader:
+        h.update_values(model(vb.to(DEV)).detach(), None)
+    assert torch.equal(mean, h.mean.squeeze())
+    assert torch.equal(sem, torch.sqrt(h.variance().squeeze()) / 3.0)
 
 
 def test_frame_stats_large_vs_oracle(ct):
