@@ -226,6 +226,7 @@ using namespace clair;
 extern "C" int clair_dark_field_mix(const float *val_dev, const float *std_dev, const float *dark_dev, const float *dark_std_dev,
                                     int n_frames, int n_channels, int height, int width, float threshold, float alpha,
                                     float *val_out_dev, float *std_out_dev, void *stream) {
+    NvtxRange nvtx_range_("clair_dark_field_mix");
     if (!val_dev || !dark_dev || !val_out_dev) return fail(CLAIR_E_ARG, "clair_dark_field_mix: null buffer");
     if ((std_out_dev != nullptr) && (!std_dev || !dark_std_dev))
         return fail(CLAIR_E_ARG, "clair_dark_field_mix: std and dark_std are required when an effective std is requested");
@@ -264,6 +265,7 @@ extern "C" int clair_dark_field_mix(const float *val_dev, const float *std_dev, 
 extern "C" int clair_flat_field_correct(void *value_dev, int value_f64, float *sigma_dev, const float *flat_dev,
                                         const float *flat_std_dev, int n_images, int n_channels, int64_t plane, int mean_in_graph,
                                         double *scratch_dev, void *stream) {
+    NvtxRange nvtx_range_("clair_flat_field_correct");
     if (!value_dev || !flat_dev || !scratch_dev) return fail(CLAIR_E_ARG, "clair_flat_field_correct: null buffer");
     if (n_images <= 0 || n_channels <= 0 || n_channels > CLAIR_MAX_CHANNELS || plane <= 0)
         return fail(CLAIR_E_ARG, "clair_flat_field_correct: bad geometry");

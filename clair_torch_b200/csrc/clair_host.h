@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include <algorithm>
@@ -11,6 +12,15 @@
 #include "clair_common.cuh"
 
 namespace clair {
+
+// NVTX range around the host side of an entry point (header-only NVTX 3: a no-op unless a profiler injects itself), so a
+// timeline shows merge / statistics / gradient calls by name
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 // records `msg` as the calling thread's last error and returns `code`
 int fail(int code, const char *msg);
@@ -42,6 +52,7 @@ struct Tuning {
     int stats_blocks_per_sm = 0;
     int stats_warps = 0;        // block shape of the statistics kernel (both must be set)
     int stats_slots = 0;
+    int stats_buffers = 0;      // tile buffers of the packed statistics kernel (1 or 2)
     int grad_blocks_per_sm = 0;
     int grad_pix = 0;           // 1 forces one pixel per lane in the gradient kernel
     int grad_warps = 0;         // warps per block of the gradient kernel

@@ -45,6 +45,7 @@ struct PairParams {
     int unc_weighting;
     int n_copies;                // gradient: replicated tables in use
     int mode;                    // CLAIR_INTERP_* of the model the table belongs to
+    int stats_buffers;           // statistics: tile buffers in shared memory (2 = staging overlaps the pair phase)
     float valid_lo, valid_hi;
     uint32_t mod_magic;          // ceil(2^16 / C): x mod C for x < 2^13 without a divide
     CurveRows rows;
@@ -341,6 +342,12 @@ __global__ void __launch_bounds__(512) pair_stats_kernel(const PairParams p) {
 // Measured on the c3 stack (16 x 4K, 29 pairs): 8930 -> 7540 warp instructions per tile (1.74 G -> 1.46 G per launch);
 // c2 means pass 156 M -> 105 M.
 // =====================================================================================================
+#ifndef STATS_MAXT
+#define STATS_MAXT(S) 512
+#endif
+#ifndef STATS_MINB
+#define STATS_MINB(S) ((S) == 2 ? 2 : 1)
+#endif
 constexpr float kMaskedWeight = -1.0e30f;  // gw of a masked element: no sum with finite weights gets back above 0
 
 __device__ __forceinline__ f32x2 rcp_fast2(f32x2 x) {     // 2 x MUFU.RCP + one packed Newton step
@@ -393,20 +400,31 @@ __device__ __forceinline__ FrameTerms2<HAS_STD, RELATIVE> frame_terms2(float x0,
             fp1 = (xs1 == r1) ? __fmul_rn(dg1, lm1) : 0.0f;
         }
     }
-    t.f = pack2(f0, f1);
     const f32x2 d2 = add2(x2, splat2(-0.5f));
     float e0, e1;
     unpack2(mul2(mul2(d2, d2), splat2(kPairNegScaleLog2e)), e0, e1);
-    t.gw = pack2((live && x0 >= lo && x0 <= hi) ? exp2f_approx(e0) : kMaskedWeight,
-                 (live && x1 >= lo && x1 <= hi) ? exp2f_approx(e1) : kMaskedWeight);
+    const bool ok0 = live && x0 >= lo && x0 <= hi, ok1 = live && x1 >= lo && x1 <= hi;
+    t.gw = pack2(ok0 ? exp2f_approx(e0) : kMaskedWeight, ok1 ? exp2f_approx(e1) : kMaskedWeight);
+    // a masked pixel carries f = 1: every pair it takes part in then has a finite loss and error, and the pair phase
+    // removes it with a 0 / 1 factor instead of selects (0 * Inf would be NaN)
+    f0 = ok0 ? f0 : 1.0f;
+    f1 = ok1 ? f1 : 1.0f;
+    t.f = pack2(f0, f1);
     t.sig = 0ull;
     t.rel = 0ull;
     if constexpr (HAS_STD) {
-        const float sg0 = fabsf(__fmul_rn(fp0, s0)), sg1 = fabsf(__fmul_rn(fp1, s1));
+        const float sg0 = ok0 ? fabsf(__fmul_rn(fp0, s0)) : 0.0f, sg1 = ok1 ? fabsf(__fmul_rn(fp1, s1)) : 0.0f;
         t.sig = pack2(sg0, sg1);
-        if constexpr (RELATIVE) t.rel = mul2(t.sig, rcp_fast2(pack2(fmaxf(f0, 1e-6f), fmaxf(f1, 1e-6f))));   // losses.py:55,58
+        // sigma / max(f, 1e-6), losses.py:55,58 (MUFU.RCP alone: <= 1 ulp, the statistics are gated at 1e-5)
+        if constexpr (RELATIVE) t.rel = mul2(t.sig, pack2(rcp_approx(fmaxf(f0, 1e-6f)), rcp_approx(fmaxf(f1, 1e-6f))));
     }
     return t;
+}
+
+__device__ __forceinline__ float mul_sat(float a, float b) {        // clamp(a * b, 0, 1); NaN -> 0
+    float r;
+    asm("mul.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
 }
 
 // TRIPS = staging items per thread (N * 32 items <= TRIPS * blockDim.x): an item's frame, tile offset, table rows and
@@ -415,7 +433,7 @@ __device__ __forceinline__ FrameTerms2<HAS_STD, RELATIVE> frame_terms2(float x0,
 // MODES: the model is LOOKUP / CATMULL (only the staging phase differs: the pair phase works on the staged per-frame terms).
 template <int SLOTS, bool ERR, bool RELATIVE, bool FULL, int TRIPS, bool MODES = false>
 // (two-slot kernels are held to 64 registers = two 16-warp blocks per SM: c3 2.07 -> 1.93 ms with 48 B of spills)
-__global__ void __launch_bounds__(512, (SLOTS == 2) ? 2 : 1) pair_stats2_kernel(const PairParams p) {
+__global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_stats2_kernel(const PairParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int C = p.n_channels, L = p.lut, N = p.n_frames;
     const bool has_model = p.theta != nullptr;
@@ -439,8 +457,13 @@ __global__ void __launch_bounds__(512, (SLOTS == 2) ? 2 : 1) pair_stats2_kernel(
     const uint32_t uC = static_cast<uint32_t>(C);
     const uint32_t plane = static_cast<uint32_t>(p.plane);
 
+    // Running sums: fp32 partials (two halves per lane) of the last <= kFlushTiles tiles around a per-lane pivot, flushed
+    // into float64 running sums in registers.  (Tried and measured slower on c3, 1.76 -> 1.89-1.97 ms: no float64 state in
+    // registers, each flush a float64 warp reduction + atomics; pair constants hoisted out of the tile loop; one block of
+    // 106 uncapped registers per SM; 8 warps x 4 slots at 80 / 126 registers.  The 64-register cap makes ptxas recompute
+    // staging addresses and thread indices per tile, but 32 resident warps per SM are worth more than those instructions.)
     double d0[SLOTS], d1[SLOTS], d2[SLOTS], d3[SLOTS], d4[SLOTS];
-    f32x2 t0[SLOTS], t1[SLOTS], t2[SLOTS], t3[SLOTS], t4[SLOTS];    // fp32 partials (two halves) of the last <= kFlushTiles tiles
+    f32x2 t0[SLOTS], t1[SLOTS], t2[SLOTS], t3[SLOTS], t4[SLOTS];
     float pivot[SLOTS];
     bool have[SLOTS];
 #pragma unroll
@@ -467,7 +490,7 @@ __global__ void __launch_bounds__(512, (SLOTS == 2) ? 2 : 1) pair_stats2_kernel(
     const uint32_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
     // per-thread staging items: frame n, pixel offset q inside the tile, source pointer, shared-memory slot, table row
     const float *src[TRIPS];
-    float *dst[TRIPS];
+    uint32_t dst[TRIPS];                 // float offset of the item inside a tile buffer
     uint32_t qoff[TRIPS], urow[TRIPS];
     bool active[TRIPS];
     const uint32_t du_tile = (gridDim.x * kStatsTile) % uC;
@@ -478,7 +501,7 @@ __global__ void __launch_bounds__(512, (SLOTS == 2) ? 2 : 1) pair_stats2_kernel(
         active[t] = n < N;
         qoff[t] = (static_cast<uint32_t>(item) & 31u) * 4u;
         src[t] = val_c + static_cast<int64_t>(active[t] ? n : 0) * frame_stride + qoff[t];
-        dst[t] = s_tile + (active[t] ? n : 0) * kFrameFloats + qoff[t];
+        dst[t] = static_cast<uint32_t>((active[t] ? n : 0) * kFrameFloats) + qoff[t];
         urow[t] = (blockIdx.x * kStatsTile + qoff[t] + static_cast<uint32_t>(p.rows.base(c))) % uC;   // row of the item's first pixel
     }
     float4 xv[TRIPS], sv[TRIPS];
@@ -494,11 +517,9 @@ __global__ void __launch_bounds__(512, (SLOTS == 2) ? 2 : 1) pair_stats2_kernel(
             }
         }
     };
-    prefetch(blockIdx.x);
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        __syncthreads();   // previous tile fully consumed (also orders the table staging on the first pass)
+    // phase A: one item = 4 adjacent pixels of one frame, loaded one tile ahead; per-frame terms into tile buffer `buf`
+    auto stage = [&](uint32_t tile, float *buf) {
         const uint32_t pix0 = tile * kStatsTile;
-        // phase A: one item = 4 adjacent pixels of one frame, loaded one tile ahead
 #pragma unroll
         for (int t = 0; t < TRIPS; ++t) {
             if (active[t]) {
@@ -522,24 +543,26 @@ __global__ void __launch_bounds__(512, (SLOTS == 2) ? 2 : 1) pair_stats2_kernel(
                                                                   p.valid_lo, p.valid_hi, live, mra);
                 const auto b = frame_terms2<ERR, RELATIVE, MODES>(xv[t].z, xv[t].w, sv[t].z, sv[t].w, has_model, bias[2], bias[3], lm1,
                                                                   p.valid_lo, p.valid_hi, live, mrb);
-                *reinterpret_cast<ulonglong2 *>(dst[t]) = make_ulonglong2(a.f, b.f);
-                *reinterpret_cast<ulonglong2 *>(dst[t] + kStatsTile) = make_ulonglong2(a.gw, b.gw);
+                float *out = buf + dst[t];
+                *reinterpret_cast<ulonglong2 *>(out) = make_ulonglong2(a.f, b.f);
+                *reinterpret_cast<ulonglong2 *>(out + kStatsTile) = make_ulonglong2(a.gw, b.gw);
                 if constexpr (ERR) {
-                    *reinterpret_cast<ulonglong2 *>(dst[t] + 2 * kStatsTile) = make_ulonglong2(a.sig, b.sig);
-                    if constexpr (RELATIVE) *reinterpret_cast<ulonglong2 *>(dst[t] + 3 * kStatsTile) = make_ulonglong2(a.rel, b.rel);
+                    *reinterpret_cast<ulonglong2 *>(out + 2 * kStatsTile) = make_ulonglong2(a.sig, b.sig);
+                    if constexpr (RELATIVE) *reinterpret_cast<ulonglong2 *>(out + 3 * kStatsTile) = make_ulonglong2(a.rel, b.rel);
                 }
                 urow[t] += du_tile;
                 urow[t] = (urow[t] >= uC) ? urow[t] - uC : urow[t];
             }
         }
-        prefetch(tile + gridDim.x);
-        __syncthreads();
+    };
+    // phase B: warp w walks its pairs over the staged tile; all masking is arithmetic (vm = 0 / 1 per pixel)
+    auto pairs = [&](const float *buf) {
 #pragma unroll
         for (int s = 0; s < SLOTS; ++s) {
             const int pr = warp + s * n_warps;
             if (pr < p.n_pairs) {
-                const float *fi = s_tile + p.pairs.i[pr] * kFrameFloats + lane * 2;
-                const float *fj = s_tile + p.pairs.j[pr] * kFrameFloats + lane * 2;
+                const float *fi = buf + p.pairs.i[pr] * kFrameFloats + lane * 2;
+                const float *fj = buf + p.pairs.j[pr] * kFrameFloats + lane * 2;
                 const float r_hi = p.pairs.r_hi[pr];
                 const f32x2 nrh2 = splat2(-r_hi), nrl2 = splat2(-p.pairs.r_lo[pr]);
                 f32x2 a0 = t0[s], a1 = t1[s], a2 = t2[s], a3 = t3[s], a4 = t4[s];
@@ -551,58 +574,67 @@ __global__ void __launch_bounds__(512, (SLOTS == 2) ? 2 : 1) pair_stats2_kernel(
                     const f32x2 av = lds2(fi + q), bv = lds2(fj + q);
                     const f32x2 wg = add2(lds2(fi + kStatsTile + q), lds2(fj + kStatsTile + q));   // < 0 <=> masked
                     const f32x2 d = fma2(bv, nrl2, fma2(bv, nrh2, av));                          // a - b r
+                    float g0, g1;
+                    unpack2(wg, g0, g1);
+                    const f32x2 vm = pack2(mul_sat(g0, 1.0e30f), mul_sat(g1, 1.0e30f));           // 1 valid, 0 masked
+                    f32x2 wt = mul2(wg, vm);                                                      // Gaussian part of the weight
                     f32x2 inv = 0ull, ell2;
                     if constexpr (RELATIVE) {
-                        inv = rcp_fast2(fma2(bv, splat2(r_hi), splat2(1e-6f)));                     // 1 / (expected + 1e-6), losses.py:45
+                        float es0, es1;
+                        unpack2(fma2(bv, splat2(r_hi), splat2(1e-6f)), es0, es1);                 // expected + 1e-6, losses.py:45
+                        inv = pack2(rcp_approx(es0), rcp_approx(es1));
                         ell2 = mul2(d, inv);
                     } else {
                         ell2 = d;
                     }
-                    float l0, l1, g0, g1;
-                    unpack2(ell2, l0, l1);
-                    unpack2(wg, g0, g1);
-                    const bool v0 = g0 >= 0.0f, v1 = g1 >= 0.0f;
-                    // |.| (es can be negative once the curve dips below 0); a masked element's loss may be anything
-                    // (even Inf / NaN): it is replaced by 0 so that its zero weight really removes it
-                    l0 = v0 ? fabsf(l0) : 0.0f;
-                    l1 = v1 ? fabsf(l1) : 0.0f;
-                    f32x2 wt = pack2(fmaxf(g0, 0.0f), fmaxf(g1, 0.0f));
+                    ell2 &= 0x7fffffff7fffffffull;                                                // |.|: es can be negative once the curve dips below 0
                     f32x2 err = 0ull;
                     if constexpr (ERR) {
                         const f32x2 sa = lds2(fi + 2 * kStatsTile + q);
-                        float s0, s1;
                         if constexpr (RELATIVE) {
                             const f32x2 e1 = mul2(sa, inv);
                             const f32x2 e2 = mul2(mul2(av, lds2(fj + 3 * kStatsTile + q)), inv);
-                            unpack2(fma2(e1, e1, fma2(e2, e2, splat2(1e-6f))), s0, s1);            // losses.py:57-60
+                            const f32x2 T = fma2(e1, e1, fma2(e2, e2, splat2(1e-6f)));          // losses.py:57-60; T >= 1e-6
+                            float T0, T1;
+                            unpack2(T, T0, T1);
+                            const f32x2 rs = pack2(rsqrt_approx(T0), rsqrt_approx(T1));           // 1 / err
+                            err = mul2(T, rs);
+                            if (unc) {                                                            // losses.py:97: 1 / (err + 1e-6)
+                                // = rs / (1 + x), x = 1e-6 rs <= 1e-3: 1 - x + x^2 is exact to 1e-9
+                                const f32x2 x = mul2(rs, splat2(1e-6f));
+                                const f32x2 pq = sub2(fma2(x, x, splat2(1.0f)), x);
+                                wt = fma2(mul2(rs, pq), vm, wt);
+                            }
                         } else {
-                            const f32x2 rs = mul2(lds2(fj + 2 * kStatsTile + q), splat2(r_hi));
-                            unpack2(fma2(sa, sa, mul2(rs, rs)), s0, s1);                            // losses.py:62
-                        }
-                        const float er0 = v0 ? sqrt_approx(s0) : 0.0f, er1 = v1 ? sqrt_approx(s1) : 0.0f;
-                        err = pack2(er0, er1);
-                        if (unc) {                                                                  // losses.py:97
-                            float u0, u1;
-                            unpack2(rcp_fast2(add2(err, splat2(1e-6f))), u0, u1);
-                            wt = add2(wt, pack2(v0 ? u0 : 0.0f, v1 ? u1 : 0.0f));
+                            const f32x2 rsb = mul2(lds2(fj + 2 * kStatsTile + q), splat2(r_hi));
+                            float s0, s1;
+                            unpack2(fma2(sa, sa, mul2(rsb, rsb)), s0, s1);                        // losses.py:62
+                            err = pack2(sqrt_approx(s0), sqrt_approx(s1));
+                            if (unc) {
+                                float u0, u1;
+                                unpack2(add2(err, splat2(1e-6f)), u0, u1);
+                                wt = fma2(pack2(rcp_approx(u0), rcp_approx(u1)), vm, wt);
+                            }
                         }
                     }
                     if constexpr (FULL) {
                         if (!hv) {                                    // the pivot: the first valid loss this lane sees
-                            k = v0 ? l0 : (v1 ? l1 : k);
-                            hv = v0 || v1;
+                            float l0, l1, m0, m1;
+                            unpack2(ell2, l0, l1);
+                            unpack2(vm, m0, m1);
+                            k = (m0 != 0.0f) ? l0 : ((m1 != 0.0f) ? l1 : k);
+                            hv = (m0 != 0.0f) || (m1 != 0.0f);
                         }
-                        const f32x2 vm = pack2(v0 ? 1.0f : 0.0f, v1 ? 1.0f : 0.0f);
-                        const f32x2 dl = mul2(vm, sub2(pack2(l0, l1), splat2(k)));
+                        const f32x2 dl = mul2(vm, sub2(ell2, splat2(k)));
                         const f32x2 wdl = mul2(wt, dl);
                         a0 = add2(a0, wt);
                         a1 = add2(a1, wdl);
                         a2 = fma2(wdl, dl, a2);
-                        if constexpr (ERR) a3 = add2(a3, err);
+                        if constexpr (ERR) a3 = fma2(err, vm, a3);
                         a4 = add2(a4, vm);
                     } else {
                         a0 = add2(a0, wt);
-                        a1 = fma2(wt, pack2(l0, l1), a1);
+                        a1 = fma2(wt, ell2, a1);
                     }
                 }
                 t0[s] = a0; t1[s] = a1;
@@ -615,7 +647,32 @@ __global__ void __launch_bounds__(512, (SLOTS == 2) ? 2 : 1) pair_stats2_kernel(
                 }
             }
         }
-        if (++since_flush == kFlushTiles) { flush(); since_flush = 0; }
+    };
+
+    // Tile pipeline.  Two tile buffers (p.stats_buffers == 2): phase A of tile k+1 and phase B of tile k run between the
+    // same pair of barriers, so a tile costs ONE block barrier and a warp goes from staging straight into its pairs; with
+    // one buffer (very long stacks, where a second buffer would cost a resident block) it is A, barrier, B, barrier.
+    const uint32_t nb = static_cast<uint32_t>(p.stats_buffers);
+    const uint32_t buf_floats = static_cast<uint32_t>(N) * kFrameFloats;
+    prefetch(blockIdx.x);
+    __syncthreads();                    // the table is staged
+    uint32_t k_it = 0;
+    for (uint32_t tile = blockIdx.x;; tile += gridDim.x, ++k_it) {
+        const bool stage_live = tile < n_tiles;
+        const bool pairs_live = (nb == 1) ? stage_live : (k_it > 0);
+        if (!stage_live && !pairs_live) break;
+        if (nb == 1) __syncthreads();   // previous tile fully consumed (also orders the table staging on the first pass)
+        if (stage_live) {
+            stage(tile, s_tile + (nb == 2 ? (k_it & 1u) * buf_floats : 0u));
+            prefetch(tile + gridDim.x);
+        }
+        if (nb == 1) __syncthreads();
+        if (pairs_live) {
+            pairs(s_tile + (nb == 2 ? ((k_it + 1u) & 1u) * buf_floats : 0u));
+            if (++since_flush == kFlushTiles) { flush(); since_flush = 0; }
+        }
+        if (nb == 2) __syncthreads();
+        if (!stage_live) break;
     }
     flush();
 
@@ -1439,6 +1496,7 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
                            const float *theta_dev, int lut_size, int interp_mode, const int32_t *curve_row_base_host, float valid_lo,
                            float valid_hi, int relative, int unc_weighting, int full, double *sums_dev, void *stream) {
     const char *fn = full ? "clair_pair_stats" : "clair_pair_means";
+    NvtxRange nvtx_range_("clair_pair_stats");
     if (int rc = check_pair_mode(fn, interp_mode, theta_dev, std_dev)) return rc;
     const bool modes = theta_dev != nullptr && interp_mode != CLAIR_INTERP_LINEAR;
     if (!val_dev || !sums_dev) return fail(CLAIR_E_ARG, "clair_pair_stats: null buffer");
@@ -1452,13 +1510,20 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
     // the uncertainty term is only evaluated (and the std images only read) when something uses it
     const bool err = std_dev != nullptr && (full || unc_weighting);
     const int arrays = 2 + (err ? (relative ? 2 : 1) : 0);
-    const size_t smem = (theta_dev ? sizeof(float2) * n_channels * lut_size : 0) + sizeof(float) * arrays * n_frames * kStatsTile;
+    const size_t table_bytes = theta_dev ? sizeof(float2) * n_channels * lut_size : 0;
+    const size_t tile_bytes = sizeof(float) * arrays * n_frames * kStatsTile;
+    size_t smem = table_bytes + tile_bytes;
     const int per_launch = 16 * kMaxSlots;   // 64 pairs: 16 warps x 4 register slots
     // 128-bit staging loads need H*W % 4 == 0 and 16-byte aligned stacks (every frame / channel slab then is, too)
     const bool vec_ok = plane % 4 == 0 && reinterpret_cast<uintptr_t>(val_dev) % 16 == 0 &&
                         (!err || reinterpret_cast<uintptr_t>(std_dev) % 16 == 0) &&
                         (theta_dev == nullptr || (n_channels * lut_size) % 2 == 0);   // tile starts 16-byte aligned after the table
     const int va = (vec_ok && n_frames <= 32) ? 4 : 1;     // the packed kernel holds <= 2 staging items per thread, 16 warps
+    // packed kernel: a second tile buffer lets staging overlap the pair phase (one barrier per tile) as long as two
+    // blocks still fit an SM
+    int buffers = (va == 4 && table_bytes + 2 * tile_bytes <= 110 * 1024) ? 2 : 1;
+    if (va == 4 && (g_tuning.stats_buffers == 1 || g_tuning.stats_buffers == 2)) buffers = g_tuning.stats_buffers;
+    if (va == 4 && buffers == 2) smem = table_bytes + 2 * tile_bytes;
     const int n_launches = (n_pairs + per_launch - 1) / per_launch;
     int first = 0;
     for (int l = 0; l < n_launches; ++l) {
@@ -1468,6 +1533,7 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
                       valid_lo, valid_hi, unc_weighting, interp_mode);
         p.sums = sums_dev + static_cast<int64_t>(first) * n_channels * 5;
         p.n_pairs = count;
+        p.stats_buffers = buffers;
         if (int rc = fill_pairs(fn, p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
         int warps, slots;
         pick_stats_shape(count, n_frames, va, err, full != 0, warps, slots);
@@ -1568,6 +1634,7 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
                                const double *upstream_dev, const double *mean_dev, double *grad_theta_dev,
                                void *workspace_dev, size_t workspace_bytes, void *stream) {
     const char *fn = "clair_pair_grad";
+    NvtxRange nvtx_range_("clair_pair_grad");
     if (!val_dev || !theta_dev || !upstream_dev || !mean_dev || !grad_theta_dev || !workspace_dev)
         return fail(CLAIR_E_ARG, "clair_pair_grad: null buffer");
     if (n_pairs < 0 || (n_pairs > 0 && (!pair_i_host || !pair_j_host || !pair_ratio_host)))

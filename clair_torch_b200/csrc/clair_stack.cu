@@ -297,6 +297,7 @@ int pick_vec(int64_t plane, std::initializer_list<const void *> ptrs) {
 extern "C" int clair_icrf_forward(const float *x_dev, const float *theta_dev, float *y_dev, float *dydx_dev,
                                   int n_frames, int n_channels, int64_t plane, int lut_size, int interp_mode,
                                   const int32_t *curve_row_base_host, void *stream) {
+    NvtxRange nvtx_range_("clair_icrf_forward");
     if (!x_dev || !theta_dev || !y_dev) return fail(CLAIR_E_ARG, "clair_icrf_forward: null buffer");
     if (int rc = check_geometry("clair_icrf_forward", n_frames, n_channels, plane, lut_size, /*limit_frames=*/false)) return rc;
     if (interp_mode != CLAIR_INTERP_LINEAR && interp_mode != CLAIR_INTERP_LOOKUP && interp_mode != CLAIR_INTERP_CATMULL)
@@ -336,6 +337,7 @@ namespace {
 int linearize_impl(const char *fn, const float *val_dev, const float *std_dev, const float *theta_dev, float *lin_dev,
                    float *sigma_dev, int n_frames, int n_channels, int64_t plane, int64_t stride, int lut_size, int interp_mode,
                    const int32_t *curve_row_base_host, void *stream) {
+    NvtxRange nvtx_range_(fn);
     char msg[160];
     auto bad = [&](int code, const char *what) {
         std::snprintf(msg, sizeof(msg), "%s: %s", fn, what);
@@ -391,6 +393,7 @@ extern "C" int clair_linearize_codes(const void *codes_dev, int code_bytes, floa
                                      float std_value, const float *theta_dev, float *lin_dev, float *sigma_dev, int n_frames,
                                      int n_channels, int64_t plane, int lut_size, int interp_mode,
                                      const int32_t *curve_row_base_host, void *stream) {
+    NvtxRange nvtx_range_("clair_linearize_codes");
     const char *fn = "clair_linearize_codes";
     if (!codes_dev || !theta_dev || !lin_dev || !sigma_dev) return fail(CLAIR_E_ARG, "clair_linearize_codes: null buffer");
     if (interp_mode != CLAIR_INTERP_LINEAR && interp_mode != CLAIR_INTERP_LOOKUP && interp_mode != CLAIR_INTERP_CATMULL)
@@ -544,6 +547,7 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
                    int gaussian_weights, double *mean_state_dev, float *wsum_state_dev, float *var_state_dev, int is_first,
                    int is_final, void *radiance_dev, int radiance_f64, float *sigma_dev, void *stream,
                    const DarkOptions &dark = DarkOptions()) {
+    NvtxRange nvtx_range_(fn);
     char msg[200];
     auto bad = [&](int code, const char *what) {
         std::snprintf(msg, sizeof(msg), "%s: %s", fn, what);
@@ -978,6 +982,7 @@ extern "C" int clair_frame_stats_update(const float *val_dev, const float *weigh
                                         const int32_t *curve_row_base_host,
                                         float *mean_state_dev, float *m2_state_dev, float *wsum_state_dev,
                                         float *wsq_state_dev, int is_first, void *stream) {
+    NvtxRange nvtx_range_("clair_frame_stats_update");
     if (!val_dev || !mean_state_dev || !m2_state_dev || !wsum_state_dev || !wsq_state_dev)
         return fail(CLAIR_E_ARG, "clair_frame_stats_update: null buffer");
     if (theta_dev == nullptr && lut_size <= 0) lut_size = 2;

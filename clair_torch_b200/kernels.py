@@ -358,15 +358,20 @@ def hdr_merge_update(state: HdrMergeState, val: torch.Tensor, std, exposure,
         desc.dark_dev, desc.dark_std_dev, desc.height, desc.width = _ptr(dark_val), _ptr(dark_std), h, w
         desc.dark_threshold, desc.dark_alpha = DARK_THRESHOLD, DARK_ALPHA
     on_host = not val.is_cuda
+    big = val.numel() * val.element_size() >= (128 << 20)
     if staged is None:
         # measured (profiles/README.md): fp32 stacks are input-bound and gain from the copy engine's faster host reads;
-        # integer codes are output-bound (1-2 B in, 8 B out per pixel) and are quicker read in place by the kernel
-        # (interleaved codes are staged: in place, each of the three channel blocks would pull all three channels' bytes)
-        staged = on_host and (not codes or hwc)
+        # small integer stacks (1-2 B in, 8 B out per pixel: c1 is 31 MB) are quicker read in place by the kernel, large ones
+        # (c4: 1.3 GB of codes) go through the copy engine in many bands — 26.2 ms against 29.6 ms read in place, with the
+        # two copy engines alone needing 24.6 ms for the same traffic (scratch/e2e_codes_c4.py);
+        # interleaved codes are always staged: in place, each of the three channel blocks would pull all three channels' bytes
+        staged = on_host and (not codes or hwc or big)
     if staged and not on_host:
         raise ValueError("staged=True is for pinned host stacks")
     if bands is None:
-        bands = 4 if codes else 16          # measured optimum: few large bands when the input is small (scratch/hwc_sweep.py)
+        # few large bands when the input is small (scratch/hwc_sweep.py), many when it is large: only the first band's copy
+        # and the last band's kernel are not overlapped
+        bands = (48 if big else 4) if codes else 16
     with torch.cuda.device(dev):
         if staged:
             stage_val = torch.empty(val.shape, dtype=val.dtype, device=dev)

@@ -426,9 +426,10 @@ def test_row_band_and_graphed_training_in_every_mode(ct, mode):
     first = [ct.train_icrf_step(m2, o2, dv, ds, torch.from_numpy(t), **kw) for _ in range(2)]
     step = ct.GraphedTrainStep(m2, o2, dv, ds, torch.from_numpy(t), **kw)
     replayed = [step() for _ in range(3)]
+    # (four-tap CATMULL weights of both signs: the order of the fp32 reductions shows in the 6th digit after a few Adam steps)
     for a, b in zip(eager, first + replayed):
-        assert max_rel(b.cpu().numpy(), a.cpu().numpy()) < 1e-6
-    assert max_abs_over_max(m2.icrf.detach().cpu().numpy(), m1.icrf.detach().cpu().numpy()) < 1e-6
+        assert max_rel(b.cpu().numpy(), a.cpu().numpy()) < 1e-5
+    assert max_abs_over_max(m2.icrf.detach().cpu().numpy(), m1.icrf.detach().cpu().numpy()) < 1e-5
 
 
 def test_lookup_model_errors_and_table_gradient(ct):
