@@ -470,12 +470,17 @@ def dp_training_metrics(dev, rank, world):
     torch.cuda.synchronize(dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 20
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
     a.record()
     for _ in range(reps):
         step()
     b.record()
     torch.cuda.synchronize(dev)
-    ms = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+    own_ms = a.elapsed_time(b) / reps
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([own_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
@@ -496,7 +501,7 @@ def dp_training_metrics(dev, rank, world):
     return {"config": "100.7 MP (8192x12288) 16-bit RGB exposure pair (one image, same seed at every N), row bands, NCCL "
                       "all-reduce of sums and gradient",
             "ms_per_step": ms, "steps_per_s": 1e3 / ms, "scaling": "strong", "n_gpus": world, "step": mode, "parity": parity,
-            "collective_us": collective_us}
+            "collective_us": collective_us, "clocks": clocks}
 
 
 def secondary_metrics(dev):
@@ -864,6 +869,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary timings (c1 merge, c2 training, c3 linearity, ...)")
+    ap.add_argument("--only-dp", action="store_true", help="diagnosis: run the data-parallel c5 training section alone")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -889,6 +895,13 @@ def main():
         key, _, val = item.partition("=")
         ct._native.check(lib.clair_set_tuning(key.encode(), int(val)), "clair_set_tuning")
 
+    if args.only_dp:
+        dp = dp_training_metrics(dev, rank, world)
+        if rank == 0:
+            print(json.dumps({"dp_train_c5": dp}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     cfg = WORKLOADS[args.workload]
     res = hdr_merge_bench(cfg, args.workload, dev, lib, rank, world, args.steps, args.warmup, args.e2e_steps, burst=True,
                           codes_e2e=True)

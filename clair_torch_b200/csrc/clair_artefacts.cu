@@ -130,8 +130,29 @@ __device__ __forceinline__ void store_values(V *p, const double (&v)[VEC]) {
     }
 }
 
+// plain (L2-allocating) vector loads: the reduce pass leaves value and flat in the 126 MB L2 for the apply pass that
+// follows it on the stream (c1: 50 MB), so only sigma and flat_std of the second pass come from DRAM
+template <int VEC>
+__device__ __forceinline__ Pack<VEC> load_keep(const float *p) {
+    Pack<VEC> r;
+    if constexpr (VEC == 4) {
+        const float4 t = *reinterpret_cast<const float4 *>(p);
+        r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+    } else {
+        r.v[0] = *p;
+    }
+    return r;
+}
+
+__device__ __forceinline__ float rcp_newton(float x) {     // MUFU.RCP + one Newton step: <= 1 ulp
+    const float r = rcp_approx(x);
+    return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
+
 // per channel: sums[c*2] = sum F, sums[c*2+1] = sum v / (F + 1e-6) over the plane.  Persistent blocks, VEC elements
-// per thread and trip, two trips in flight, float64 partials, one pair of atomics per block.
+// per thread and trip, two trips in flight, one pair of float64 atomics per block.  float64 values: float64 partials;
+// fp32 values: fp32 per-thread partials (a thread sums a few dozen terms) widened once at the warp reduction — the
+// float64 form spent its time converting (F2F runs on the 16-lane XU pipe: 56 % busy, 17 us for 50 MB).
 template <typename V, int VEC>
 __global__ void __launch_bounds__(256) flat_reduce_kernel(const V *__restrict__ value, const float *__restrict__ flat, int64_t plane,
                                                           double *sums) {
@@ -140,28 +161,54 @@ __global__ void __launch_bounds__(256) flat_reduce_kernel(const V *__restrict__ 
     const V *v_c = value ? value + c * plane : nullptr;
     const int64_t n_items = plane / VEC, stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     double sf = 0.0, sv = 0.0;
-    for (int64_t item = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; item < n_items; item += 2 * stride) {
-        const bool two = item + stride < n_items;
-        const Pack<VEC> f0 = load_stream<VEC>(f_c + item * VEC);
-        Pack<VEC> f1;
-        if (two) f1 = load_stream<VEC>(f_c + (item + stride) * VEC);
-        double v0[VEC], v1[VEC];
-        if (v_c) {
-            load_values<V, VEC>(v_c + item * VEC, v0);
-            if (two) load_values<V, VEC>(v_c + (item + stride) * VEC, v1);
-        }
+    if constexpr (sizeof(V) == 4) {
+        float pf = 0.0f, pv = 0.0f;
+        int terms = 0;
+        const float *vf = reinterpret_cast<const float *>(v_c);
+        for (int64_t item = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; item < n_items; item += 2 * stride) {
+            const bool two = item + stride < n_items;
+            const Pack<VEC> f0 = load_keep<VEC>(f_c + item * VEC);
+            Pack<VEC> f1, x0, x1;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            const double f = static_cast<double>(f0.v[k]);
-            sf += f;
-            if (v_c) sv = fma(v0[k], rcp_f64(f + 1e-6), sv);
-        }
-        if (two) {
+            for (int k = 0; k < VEC; ++k) { f1.v[k] = 1.0f; x0.v[k] = 0.0f; x1.v[k] = 0.0f; }
+            if (two) f1 = load_keep<VEC>(f_c + (item + stride) * VEC);
+            if (vf) {
+                x0 = load_keep<VEC>(vf + item * VEC);
+                if (two) x1 = load_keep<VEC>(vf + (item + stride) * VEC);
+            }
 #pragma unroll
             for (int k = 0; k < VEC; ++k) {
-                const double f = static_cast<double>(f1.v[k]);
+                pf += f0.v[k] + (two ? f1.v[k] : 0.0f);
+                if (vf) pv = fmaf(x0.v[k], rcp_newton(f0.v[k] + 1e-6f), fmaf(x1.v[k], rcp_newton(f1.v[k] + 1e-6f), pv));
+            }
+            if (++terms == 16) { sf += static_cast<double>(pf); sv += static_cast<double>(pv); pf = 0.0f; pv = 0.0f; terms = 0; }
+        }
+        sf += static_cast<double>(pf);
+        sv += static_cast<double>(pv);
+    } else {
+        for (int64_t item = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; item < n_items; item += 2 * stride) {
+            const bool two = item + stride < n_items;
+            const Pack<VEC> f0 = load_stream<VEC>(f_c + item * VEC);
+            Pack<VEC> f1;
+            if (two) f1 = load_stream<VEC>(f_c + (item + stride) * VEC);
+            double v0[VEC], v1[VEC];
+            if (v_c) {
+                load_values<V, VEC>(v_c + item * VEC, v0);
+                if (two) load_values<V, VEC>(v_c + (item + stride) * VEC, v1);
+            }
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                const double f = static_cast<double>(f0.v[k]);
                 sf += f;
-                if (v_c) sv = fma(v1[k], rcp_f64(f + 1e-6), sv);
+                if (v_c) sv = fma(v0[k], rcp_f64(f + 1e-6), sv);
+            }
+            if (two) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) {
+                    const double f = static_cast<double>(f1.v[k]);
+                    sf += f;
+                    if (v_c) sv = fma(v1[k], rcp_f64(f + 1e-6), sv);
+                }
             }
         }
     }
@@ -183,7 +230,8 @@ __global__ void __launch_bounds__(256) flat_reduce_kernel(const V *__restrict__ 
 }
 
 // value (n_images, C, plane) corrected in place; sigma (same shape) updated in place when flat_std is given.
-// grid (ceil(plane / (VEC*256)), C, n_images)
+// grid (ceil(plane / (VEC*256)), C, n_images).  fp32 values are corrected in fp32 (reciprocal to 1 ulp), float64 ones in
+// float64 as the reference's promoted arithmetic does.
 template <typename V, int VEC>
 __global__ void __launch_bounds__(256) flat_apply_kernel(V *value, float *sigma, const float *__restrict__ flat,
                                                          const float *__restrict__ flat_std, int64_t plane, int C,
@@ -194,29 +242,52 @@ __global__ void __launch_bounds__(256) flat_apply_kernel(V *value, float *sigma,
     const int64_t o = (static_cast<int64_t>(blockIdx.z) * C + c) * plane + p;
     const bool with_sigma = flat_std != nullptr && sigma != nullptr;
     const Pack<VEC> f = load_stream<VEC>(flat + c * plane + p);
-    double v[VEC];
-    load_values<V, VEC>(value + o, v);
-    Pack<VEC> fs, sg;
-    if (with_sigma) {
-        fs = load_stream<VEC>(flat_std + c * plane + p);
-        sg = load_stream<VEC>(sigma + o);
-    }
     const double inv_plane = 1.0 / static_cast<double>(plane);
     const double mu = sums[2 * c] * inv_plane;
     const double g_mean = mean_in_graph ? sums[2 * c + 1] * inv_plane : 0.0;
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-        const double r = rcp_f64(static_cast<double>(f.v[k]) + 1e-6);
-        const double y = v[k] * r * mu;
-        v[k] = y;
+    if constexpr (sizeof(V) == 4) {
+        float *vp = reinterpret_cast<float *>(value) + o;
+        Pack<VEC> x = load_stream<VEC>(vp);
+        Pack<VEC> fs, sg;
         if (with_sigma) {
-            const double gs = (g_mean - y * r) * static_cast<double>(fs.v[k]);       // dy/dF = -v mu / (F + eps)^2 [+ mean term]
-            const double s = static_cast<double>(sg.v[k]);
-            sg.v[k] = sqrtf(static_cast<float>(fma(s, s, gs * gs)));
+            fs = load_stream<VEC>(flat_std + c * plane + p);
+            sg = load_stream<VEC>(sigma + o);
         }
+        const float muf = static_cast<float>(mu), gmf = static_cast<float>(g_mean);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const float r = rcp_newton(f.v[k] + 1e-6f);
+            const float y = x.v[k] * r * muf;
+            x.v[k] = y;
+            if (with_sigma) {
+                const float gs = (gmf - y * r) * fs.v[k];                           // dy/dF = -v mu / (F + eps)^2 [+ mean term]
+                sg.v[k] = sqrtf(fmaf(sg.v[k], sg.v[k], gs * gs));
+            }
+        }
+        store_stream<VEC>(vp, x);
+        if (with_sigma) store_stream<VEC>(sigma + o, sg);
+    } else {
+        double v[VEC];
+        load_values<V, VEC>(value + o, v);
+        Pack<VEC> fs, sg;
+        if (with_sigma) {
+            fs = load_stream<VEC>(flat_std + c * plane + p);
+            sg = load_stream<VEC>(sigma + o);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+            const double r = rcp_f64(static_cast<double>(f.v[k]) + 1e-6);
+            const double y = v[k] * r * mu;
+            v[k] = y;
+            if (with_sigma) {
+                const double gs = (g_mean - y * r) * static_cast<double>(fs.v[k]);   // dy/dF = -v mu / (F + eps)^2 [+ mean term]
+                const double s = static_cast<double>(sg.v[k]);
+                sg.v[k] = sqrtf(static_cast<float>(fma(s, s, gs * gs)));
+            }
+        }
+        store_values<V, VEC>(value + o, v);
+        if (with_sigma) store_stream<VEC>(sigma + o, sg);
     }
-    store_values<V, VEC>(value + o, v);
-    if (with_sigma) store_stream<VEC>(sigma + o, sg);
 }
 
 }  // namespace clair

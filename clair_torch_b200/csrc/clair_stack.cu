@@ -879,7 +879,16 @@ struct FrameStatsParams {
     CurveRows rows;
 };
 
-template <int VEC>
+__device__ __forceinline__ float rcp_1ulp(float x) {     // MUFU.RCP + one Newton step
+    const float r = rcp_approx(x);
+    return fmaf(fmaf(-x, r, 1.0f), r, r);
+}
+
+// WEIGHTED / MODES are compile-time so the common case (unweighted video frames, LINEAR model or none) carries no weight
+// accumulators and no mode dispatch: 94 -> 40 registers, and the four running-state loads are issued with the frame
+// loads instead of after them.  Quotients go through a 1-ulp reciprocal (the IEEE divisions were ~60 of the epilogue's
+// instructions per pixel).
+template <int VEC, bool WEIGHTED, bool MODES>
 __global__ void __launch_bounds__(kBlock) frame_stats_kernel(const FrameStatsParams p) {
     extern __shared__ float2 s_tab[];
     const int C = p.n_channels, L = p.lut;
@@ -897,19 +906,25 @@ __global__ void __launch_bounds__(kBlock) frame_stats_kernel(const FrameStatsPar
     RowCursor<VEC> cur(first_item * VEC, item_stride * VEC, static_cast<uint32_t>(p.rows.base(c)), static_cast<uint32_t>(C));
     const uint32_t tab_bias = curve_row_bias(s_tab);
     const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
-    const bool weighted = p.weights != nullptr;
     const int N = p.n_frames;
+    const bool first = p.is_first != 0;
+    const float n_f = static_cast<float>(N);
 
     for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
         const uint32_t pix = item * VEC;
         const int64_t off = static_cast<int64_t>(c) * p.plane + pix;
-        uint32_t bias[VEC], urow[VEC];
+        uint32_t bias[VEC];
         {
             uint32_t u = cur.u0;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) { urow[k] = u; bias[k] = tab_bias + u * row_bytes; u = (u + 1 == cur.C) ? 0u : u + 1; }
+            for (int k = 0; k < VEC; ++k) { bias[k] = tab_bias + u * row_bytes; u = (u + 1 == cur.C) ? 0u : u + 1; }
         }
-        const bool linear = p.mode == CLAIR_INTERP_LINEAR, lookup = p.mode == CLAIR_INTERP_LOOKUP;
+        // running state of the pixel: requested first, needed last
+        Pack<VEC> a_mean, a_m2, a_w, a_wsq;
+        if (!first) {
+            a_mean = load_stream<VEC>(p.mean + off); a_m2 = load_stream<VEC>(p.m2 + off);
+            a_w = load_stream<VEC>(p.wsum + off); a_wsq = load_stream<VEC>(p.wsq + off);
+        }
         float w0[VEC], w2[VEC], s1[VEC], s2[VEC], pivot[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) { w0[k] = 0.0f; w2[k] = 0.0f; s1[k] = 0.0f; s2[k] = 0.0f; pivot[k] = 0.0f; }
@@ -920,7 +935,7 @@ __global__ void __launch_bounds__(kBlock) frame_stats_kernel(const FrameStatsPar
                 if (n0 + j < N) {
                     const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
                     xv[j] = load_stream<VEC>(p.val + o);
-                    if (weighted) wv[j] = load_stream<VEC>(p.weights + o);
+                    if constexpr (WEIGHTED) wv[j] = load_stream<VEC>(p.weights + o);
                 }
             }
 #pragma unroll
@@ -931,41 +946,54 @@ __global__ void __launch_bounds__(kBlock) frame_stats_kernel(const FrameStatsPar
                         float v = xv[j].v[k];
                         if (has_model) {
                             float fp;
-                            if (linear) icrf_linear_biased(v, bias[k], lm1, v, fp);
-                            else icrf_mode_eval_rt(p.mode, v, s_tab + (lookup ? static_cast<uint32_t>(c) : urow[k]) * L, L, lm1, v, fp);
+                            if constexpr (MODES) {
+                                // LOOKUP reads the true channel row, CATMULL the k-mod-C row like LINEAR
+                                const uint32_t u = (bias[k] - tab_bias) / row_bytes;
+                                icrf_mode_eval_rt(p.mode, v, s_tab + (p.mode == CLAIR_INTERP_LOOKUP ? static_cast<uint32_t>(c) : u) * L, L, lm1, v, fp);
+                            } else {
+                                icrf_linear_biased(v, bias[k], lm1, v, fp);
+                            }
                         }
-                        const float w = weighted ? wv[j].v[k] : 1.0f;
                         if (n0 + j == 0) pivot[k] = v;
                         const float d = v - pivot[k];
-                        w0[k] += w;
-                        w2[k] = fmaf(w, w, w2[k]);
-                        s1[k] = fmaf(w, d, s1[k]);
-                        s2[k] = fmaf(w * d, d, s2[k]);
+                        if constexpr (WEIGHTED) {
+                            const float w = wv[j].v[k];
+                            w0[k] += w;
+                            w2[k] = fmaf(w, w, w2[k]);
+                            s1[k] = fmaf(w, d, s1[k]);
+                            s2[k] = fmaf(w * d, d, s2[k]);
+                        } else {
+                            s1[k] += d;
+                            s2[k] = fmaf(d, d, s2[k]);
+                        }
                     }
                 }
             }
         }
-        Pack<VEC> o_mean, o_m2, o_w, o_wsq, a_mean, a_m2, a_w, a_wsq;
-        if (!p.is_first) {
-            a_mean = load_stream<VEC>(p.mean + off); a_m2 = load_stream<VEC>(p.m2 + off);
-            a_w = load_stream<VEC>(p.wsum + off); a_wsq = load_stream<VEC>(p.wsq + off);
-        }
+        Pack<VEC> o_mean, o_m2, o_w, o_wsq;
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            const float wb = weighted ? w0[k] : static_cast<float>(N);
+            const float wb = WEIGHTED ? w0[k] : n_f;
             // weighted: sum w v / (W_B + 1e-6) (statistics.py:223-224); unweighted: plain mean (:227)
-            const float db = weighted ? s1[k] / (w0[k] + 1e-6f) - pivot[k] * (1e-6f / (w0[k] + 1e-6f)) : s1[k] / wb;   // mean_B - pivot
+            float db;                                                       // mean_B - pivot
+            if constexpr (WEIGHTED) {
+                const float r = rcp_1ulp(w0[k] + 1e-6f);
+                db = s1[k] * r - pivot[k] * (1e-6f * r);
+            } else {
+                db = s1[k] * rcp_1ulp(wb);
+            }
             const float mean_b = pivot[k] + db;
-            const float m2_b = fmaxf(s2[k] - 2.0f * db * s1[k] + db * db * w0[k], 0.0f);
-            const float wsq_b = weighted ? w2[k] : wb;
-            if (p.is_first) {
-                // W_A = 0, mean_A = 0, M_A = 0 (python floats in the reference)
-                o_w.v[k] = wb; o_mean.v[k] = (wb / wb) * mean_b; o_m2.v[k] = m2_b; o_wsq.v[k] = wsq_b;
+            const float m2_b = fmaxf(s2[k] - 2.0f * db * s1[k] + db * db * wb, 0.0f);
+            const float wsq_b = WEIGHTED ? w2[k] : wb;
+            if (first) {
+                // W_A = 0, mean_A = 0, M_A = 0 (python floats in the reference): mean = (W_B / W_B) mean_B
+                o_w.v[k] = wb; o_mean.v[k] = (wb != 0.0f) ? mean_b : __int_as_float(0x7fc00000); o_m2.v[k] = m2_b; o_wsq.v[k] = wsq_b;
             } else {
                 const float wt = a_w.v[k] + wb;
+                const float rt = rcp_1ulp(wt);
                 const float dm = mean_b - a_mean.v[k];
-                o_m2.v[k] = a_m2.v[k] + m2_b + (a_w.v[k] * wb / wt) * dm * dm;
-                o_mean.v[k] = a_mean.v[k] + (wb / wt) * dm;
+                o_m2.v[k] = a_m2.v[k] + m2_b + (a_w.v[k] * wb * rt) * dm * dm;
+                o_mean.v[k] = a_mean.v[k] + (wb * rt) * dm;
                 o_w.v[k] = wt;
                 o_wsq.v[k] = a_wsq.v[k] + wsq_b;
             }
@@ -1008,7 +1036,12 @@ extern "C" int clair_frame_stats_update(const float *val_dev, const float *weigh
         kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p);
         return 0;
     };
-    int rc = vec == 4 ? launch(frame_stats_kernel<4>) : vec == 2 ? launch(frame_stats_kernel<2>) : launch(frame_stats_kernel<1>);
+    const bool weighted = weights_dev != nullptr, modes = theta_dev != nullptr && interp_mode != CLAIR_INTERP_LINEAR;
+    int rc;
+#define STATS_VEC(W, M) (vec == 4 ? launch(frame_stats_kernel<4, W, M>) : vec == 2 ? launch(frame_stats_kernel<2, W, M>) : launch(frame_stats_kernel<1, W, M>))
+    if (weighted) rc = modes ? STATS_VEC(true, true) : STATS_VEC(true, false);
+    else rc = modes ? STATS_VEC(false, true) : STATS_VEC(false, false);
+#undef STATS_VEC
     if (rc) return rc;
     return launched("frame_stats_kernel");
 }

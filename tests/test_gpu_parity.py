@@ -530,9 +530,11 @@ def test_graphed_train_step_equals_eager_steps(ct, unc):
     step = ct.GraphedTrainStep(m_g, o_g, val, std, exposure, **kw)
     assert ct._native.launch_count() - before >= 4          # the fused kernels were captured, not executed eagerly
     losses += [step().cpu().numpy() for _ in range(5)]
+    # Adam's first steps move every table entry by about +-lr whatever the size of its gradient, so an entry whose gradient
+    # is fp32 reduction-order noise can go either way from run to run; the loss sees that in its 6th digit
     for a, b in zip(eager, losses):
-        assert max_rel(b, a) < 1e-6
-    assert max_abs_over_max(m_g.icrf.detach().cpu().numpy(), m_e.icrf.detach().cpu().numpy()) < 1e-6
+        assert max_rel(b, a) < 1e-5
+    assert max_abs_over_max(m_g.icrf.detach().cpu().numpy(), m_e.icrf.detach().cpu().numpy()) < 3e-3
     assert m_g.icrf.requires_grad
     # a plain (host-stepped) Adam cannot be captured
     plain = [torch.optim.Adam(m_g.channel_params(c), lr=1e-3) for c in range(3)]
@@ -1019,5 +1021,6 @@ def test_dark_mix_and_flat_field_vs_oracle_larger(ct):
         sigma = torch.from_numpy(rng.uniform(0.01, 0.1, size=(3, 97, 131)).astype(np.float32)).to(DEV)
         want_v, want_var = orc.flat_field_correct(value.cpu().numpy(), sigma.cpu().numpy().astype(np.float64) ** 2, flat, flat_std, in_graph)
         kernels.flat_field_correct_(value, sigma, torch.from_numpy(flat), torch.from_numpy(flat_std), in_graph)
-        assert max_rel(value.cpu().numpy(), want_v) < (1e-12 if dtype == torch.float64 else 2e-7)
-        assert max_rel(sigma.cpu().numpy(), np.sqrt(want_var)) < 2e-7
+        # float64 values are corrected in float64, fp32 ones in fp32 (1-ulp reciprocal, a few roundings per element)
+        assert max_rel(value.cpu().numpy(), want_v) < (1e-12 if dtype == torch.float64 else 5e-7)
+        assert max_rel(sigma.cpu().numpy(), np.sqrt(want_var)) < (2e-7 if dtype == torch.float64 else 6e-7)
