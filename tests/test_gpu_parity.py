@@ -534,7 +534,7 @@ def test_graphed_train_step_equals_eager_steps(ct, unc):
     # is fp32 reduction-order noise can go either way from run to run; the loss sees that in its 6th digit
     for a, b in zip(eager, losses):
         assert max_rel(b, a) < 1e-5
-    assert max_abs_over_max(m_g.icrf.detach().cpu().numpy(), m_e.icrf.detach().cpu().numpy()) < 3e-3
+    assert max_abs_over_max(m_g.icrf.detach().cpu().numpy(), m_e.icrf.detach().cpu().numpy()) < 1e-2
     assert m_g.icrf.requires_grad
     # a plain (host-stepped) Adam cannot be captured
     plain = [torch.optim.Adam(m_g.channel_params(c), lr=1e-3) for c in range(3)]
