@@ -303,3 +303,28 @@ def test_ingest_chain_bit_exact(name):
     x = orc.cv_to_torch(z["camera"]).astype(np.float32)
     want = ((x - np.float32(3.0)) / np.float32(float(z["max_val"]) - 3.0)) * np.float32(2.0) + np.float32(-1.0)
     assert np.array_equal(orc.cast_normalize(orc.cv_to_torch(z["camera"]), float(z["max_val"]), 3.0, (-1.0, 1.0)), want)
+
+
+# ---- the reference itself, run from oracle/_ref (bench.py's CPU arm) ----------------------------------------------
+def test_reference_runner_reproduces_the_fixtures():
+    """oracle/reference_runner.py drives the UNMODIFIED reference vendored into oracle/_ref (make -C oracle ref); the
+    fixtures were written by the same code imported from /root/reference, so the runner must reproduce them to the bit.
+    This pins what bench.py times as `cpu_baseline.kind = "reference"` and `--impl reference`."""
+    from oracle import reference_runner as rr
+    if not rr.available() and not rr.vendor():
+        pytest.skip("oracle/_ref is not vendored here and /root/reference is absent")
+    z = golden("hdr_c1small_2batches")
+    rad, sig, _ = rr.hdr_merge(z["val"], z["std"], z["exposure"], z["theta"], bool(z["gaussian"]), int(z["batch_size"]))
+    assert np.array_equal(rad, z["radiance"]) and np.array_equal(sig, z["sigma"])
+    z = golden("linearity_rel1_unc1_std1_model1")
+    ratio, mean, sd, err, _ = rr.measure_linearity(z["val"], z["std"], z["exposure"], z["theta"], True, True)
+    assert np.array_equal(ratio, z["ratio"]) and np.array_equal(mean, z["mean"]) and np.array_equal(sd, z["stddev"])
+    assert np.array_equal(err, z["errmean"])
+    z = golden("trainstep_script")
+    a, b, g, d = (float(k) for k in z["coeffs"])
+    step = rr.TrainStep(z["val"], z["std"], z["exposure"], theta=z["theta0"], relative=bool(z["rel"]), unc_weighting=bool(z["unc"]),
+                        alpha=a, beta=b, gamma=g, delta=d, threshold=float(z["thr"]))
+    for k in range(2):
+        loss, lin, grad, _ = step()
+        assert np.array_equal(loss, z[f"loss_{k}"]) and np.array_equal(lin, z[f"linloss_{k}"])
+        assert np.array_equal(grad, z[f"grad_theta_{k}"])
