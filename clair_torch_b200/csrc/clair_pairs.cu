@@ -973,8 +973,14 @@ __device__ __forceinline__ void red_add_v2_if(float *addr, float a, float b, flo
 }
 
 // MODES: the model is LOOKUP / CATMULL — per-frame terms and the final tap scatter differ, the pair algebra does not.
-template <bool ERR, bool RELATIVE, bool MODES = false>
+// FUSED (one exposure pair, no uncertainty weights: the "100 MP exposure pair" of BASELINE config 5): statistics and
+// gradient in ONE pass over the stack.  With a single pair the upstream factor U[c] = dLoss_c / dmean / D is one scalar
+// per channel, so the kernel scatters the un-normalised gradient (U = 1) into a table PER CHANNEL BLOCK c — the table
+// rows u interleave channels (Q1), hence C tables of C rows — and accumulates sum M Wt, sum M Wt l beside it;
+// clair_pair_fused_combine applies U afterwards (after the all-reduce when the image is sharded).
+template <bool ERR, bool RELATIVE, bool MODES = false, bool FUSED = false>
 __global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
+    static_assert(!(FUSED && ERR), "the fused single-pair pass has no uncertainty weights");
     extern __shared__ __align__(16) unsigned char s_raw[];
     const int C = p.n_channels, L = p.lut, N = p.n_frames, P = p.n_pairs;
     const int c = blockIdx.y;
@@ -984,13 +990,17 @@ __global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
     const uint32_t lp = static_cast<uint32_t>(L + 2);
     stage_curve_slopes(s_tab, p.theta, C, L);
     for (int k = threadIdx.x; k < P; k += blockDim.x) {
-        s_up[k] = static_cast<float>(p.upstream[static_cast<int64_t>(k) * C + c]);
-        s_mean[k] = static_cast<float>(p.mean[static_cast<int64_t>(k) * C + c]);
+        s_up[k] = FUSED ? 1.0f : static_cast<float>(p.upstream[static_cast<int64_t>(k) * C + c]);
+        s_mean[k] = FUSED ? 0.0f : static_cast<float>(p.mean[static_cast<int64_t>(k) * C + c]);
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_warps = blockDim.x >> 5;
+    // FUSED: running sum M Wt, sum M Wt l of the single pair (fp32 per lane for <= 16 trips, then float64)
+    f32x2 fs0 = 0ull, fs1 = 0ull;
+    double fd0 = 0.0, fd1 = 0.0;
+    int fused_trips = 0;
     // warp-private slice, layout [frame][array][lane][2]
     //   0: f   1: gw   2: xs   3: G (per-frame upstream)   4: sigma (ERR)   5: 1 / max(f, 1e-6) (ERR && RELATIVE)
     constexpr int kArrays = ERR ? 6 : 4;
@@ -1002,7 +1012,9 @@ __global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
     const int64_t frame_stride = static_cast<int64_t>(C) * p.plane;
     const float *val_c = p.val + static_cast<int64_t>(c) * p.plane;
     const int64_t std_minus_val = ERR ? (p.std - p.val) : 0;
-    float *copy = p.hist + static_cast<int64_t>((blockIdx.x * n_warps + warp) % p.n_copies) * (2 * C * lp);
+    const int64_t copy_index = FUSED ? static_cast<int64_t>((blockIdx.x * n_warps + warp) % p.n_copies) * C + c
+                                     : static_cast<int64_t>((blockIdx.x * n_warps + warp) % p.n_copies);
+    float *copy = p.hist + copy_index * (2 * C * lp);
     const uint32_t odd_step = static_cast<uint32_t>(C) * lp + 1u;     // A[u][x0] -> B[u][x0 + 1]
     const uint32_t tab_bias = curve_row_bias(s_tab);
     const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
@@ -1132,6 +1144,11 @@ __global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
                 const f32x2 q2 = mul2(d2, inv2);
                 float q0, q1;
                 unpack2(q2, q0, q1);
+                if constexpr (FUSED) {          // the statistics of the pair: weight and weight * |loss|, masked elements out
+                    const f32x2 wv = pack2(fmaxf(wg0, 0.0f), fmaxf(wg1, 0.0f));
+                    fs0 = add2(fs0, wv);
+                    fs1 = fma2(wv, pack2(wg0 >= 0.0f ? fabsf(q0) : 0.0f, wg1 >= 0.0f ? fabsf(q1) : 0.0f), fs1);
+                }
                 f32x2 wu2;                                                   // weight * upstream, 0 where masked
                 f32x2 extra_a = 0ull, extra_b = 0ull;
                 if constexpr (ERR) {
@@ -1182,6 +1199,11 @@ __global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
             } else {
                 float d0, d1;
                 unpack2(d2, d0, d1);
+                if constexpr (FUSED) {
+                    const f32x2 wv = pack2(fmaxf(wg0, 0.0f), fmaxf(wg1, 0.0f));
+                    fs0 = add2(fs0, wv);
+                    fs1 = fma2(wv, pack2(wg0 >= 0.0f ? fabsf(d0) : 0.0f, wg1 >= 0.0f ? fabsf(d1) : 0.0f), fs1);
+                }
                 f32x2 wu2;
                 if constexpr (ERR) {
                     const f32x2 rs2 = mul2(lds2(fj + 4 * kArr), splat2(r_hi));
@@ -1237,6 +1259,76 @@ __global__ void __launch_bounds__(256) pair_grad2_kernel(const PairParams p) {
         }
         u0 += du;
         u0 = (u0 >= uC) ? u0 - uC : u0;
+        if constexpr (FUSED) {
+            if (++fused_trips == 16) {
+                float a, b;
+                unpack2(fs0, a, b); fd0 += static_cast<double>(a) + static_cast<double>(b);
+                unpack2(fs1, a, b); fd1 += static_cast<double>(a) + static_cast<double>(b);
+                fs0 = 0ull; fs1 = 0ull; fused_trips = 0;
+            }
+        }
+    }
+    if constexpr (FUSED) {
+        float a, b;
+        unpack2(fs0, a, b); fd0 += static_cast<double>(a) + static_cast<double>(b);
+        unpack2(fs1, a, b); fd1 += static_cast<double>(a) + static_cast<double>(b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fd0 += __shfl_xor_sync(0xffffffffu, fd0, o);
+            fd1 += __shfl_xor_sync(0xffffffffu, fd1, o);
+        }
+        if (lane == 0) {
+            atomicAdd(p.sums + static_cast<int64_t>(c) * 5 + 0, fd0);
+            atomicAdd(p.sums + static_cast<int64_t>(c) * 5 + 1, fd1);
+        }
+    }
+}
+
+// Fused single-pair pass, second half: T[c][u][k] += sum over copies of A[u][k] + B[u][k+1] of channel block c's tables
+// (float64, laid out (C, C, L) behind the (1, C, 5) sums).
+__global__ void __launch_bounds__(256) fused_finalize_kernel(const float *__restrict__ hist, double *tables, int C, int L, int n_copies) {
+    __shared__ double s_part[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;                     // entry (u, k) of one channel block's table
+    const int c = blockIdx.y;
+    const int lp = L + 2;
+    const bool live = i < C * L;
+    const int u = live ? i / L : 0, k = live ? i - u * L : 0;
+    double acc = 0.0;
+    if (live) {
+        const int64_t table = static_cast<int64_t>(2) * C * lp, stride = table * C;
+        const float *a = hist + c * table + u * lp + k, *b = hist + c * table + C * lp + u * lp + k + 1;
+        for (int r = warp; r < n_copies; r += 8)
+            acc += static_cast<double>(a[r * stride]) + static_cast<double>(b[r * stride]);
+    }
+    s_part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && live) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) acc += s_part[w][lane];
+        tables[(static_cast<int64_t>(c) * C + u) * L + k] += acc;
+    }
+}
+
+// Fused single-pair pass, last step (after the all-reduce of a sharded image): mean[c] = s1 / max(s0, 1e-8), loss[c] =
+// sqrt(mean^2), U[c] = mean / loss / max(s0, 1e-8) (training/icrf_training.py:133-136 and the head of the closed-form
+// backward) and grad[u][k] += sum_c U[c] T[c][u][k].
+__global__ void __launch_bounds__(256) fused_combine_kernel(const double *__restrict__ fused, int C, int L, double *linloss,
+                                                            double *mean, double *grad) {
+    __shared__ double s_u[CLAIR_MAX_CHANNELS];
+    if (threadIdx.x < C) {
+        const double s0 = fused[threadIdx.x * 5 + 0], s1 = fused[threadIdx.x * 5 + 1];
+        const double m = s1 / fmax(s0, 1e-8);
+        const double l = sqrt(m * m);
+        s_u[threadIdx.x] = (l > 0.0) ? m / l / fmax(s0, 1e-8) : 0.0;
+        if (blockIdx.x == 0) { mean[threadIdx.x] = m; linloss[threadIdx.x] = l; }
+    }
+    __syncthreads();
+    const double *tables = fused + C * 5;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < C * L; e += gridDim.x * blockDim.x) {
+        double acc = 0.0;
+        for (int c = 0; c < C; ++c) acc += s_u[c] * tables[static_cast<int64_t>(c) * C * L + e];
+        if (grad != nullptr) grad[e] += acc;
     }
 }
 
@@ -1695,6 +1787,78 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
         first += count;
     }
     return finalize_grad(static_cast<const float *>(workspace_dev), grad_theta_dev, n_channels, lut_size, n_copies, s);
+}
+
+extern "C" size_t clair_pair_fused_doubles(int n_channels, int lut_size) {
+    if (n_channels <= 0 || lut_size <= 0) return 0;
+    return static_cast<size_t>(n_channels) * 5 + static_cast<size_t>(n_channels) * n_channels * lut_size;
+}
+
+extern "C" int clair_pair_fused(const float *val_dev, int n_frames, int n_channels, int64_t plane, const int32_t *pair_i_host,
+                                const int32_t *pair_j_host, const double *pair_ratio_host, int n_pairs, const float *theta_dev,
+                                int lut_size, int interp_mode, const int32_t *curve_row_base_host, float valid_lo, float valid_hi,
+                                int relative, double *fused_dev, void *workspace_dev, size_t workspace_bytes, void *stream) {
+    const char *fn = "clair_pair_fused";
+    NvtxRange nvtx_range_(fn);
+    if (!val_dev || !theta_dev || !fused_dev || !workspace_dev || !pair_i_host || !pair_j_host || !pair_ratio_host)
+        return fail(CLAIR_E_ARG, "clair_pair_fused: null buffer");
+    if (n_pairs != 1) return fail(CLAIR_E_MODE, "clair_pair_fused: the single-pass form is defined for exactly one exposure pair");
+    if (int rc = check_pair_mode(fn, interp_mode, theta_dev, nullptr)) return rc;
+    if (int rc = check_geometry(fn, n_frames, n_channels, plane, lut_size, true)) return rc;
+    if (plane % 2 != 0 || reinterpret_cast<uintptr_t>(val_dev) % 8 != 0)
+        return fail(CLAIR_E_ARG, "clair_pair_fused: H*W must be even and the stack 8-byte aligned (use the two-pass entry points otherwise)");
+    const size_t need = clair_grad_workspace_bytes(n_channels, lut_size);
+    if (workspace_bytes < need || reinterpret_cast<uintptr_t>(workspace_dev) % 16 != 0)
+        return fail(CLAIR_E_ARG, "clair_pair_fused: workspace too small or misaligned (see clair_grad_workspace_bytes)");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int n_copies = std::max(1, (g_tuning.grad_copies > 0 ? std::min(g_tuning.grad_copies, kMaxGradCopies) : kPairGradCopies) / n_channels);
+    const size_t table_bytes = need / kMaxGradCopies;
+    if (cudaError_t e = cudaMemsetAsync(workspace_dev, 0, table_bytes * n_copies * n_channels, s); e != cudaSuccess)
+        return fail_cuda(e, "cudaMemsetAsync(workspace)");
+    const bool modes = interp_mode != CLAIR_INTERP_LINEAR;
+    const size_t fixed_bytes = sizeof(float2) * n_channels * lut_size + sizeof(float) * (2 * 1 + 2);
+    const size_t per_warp = sizeof(float) * 4 * n_frames * 64;
+    const size_t want_warps = g_tuning.grad_warps > 0 ? static_cast<size_t>(g_tuning.grad_warps) : 4;
+    const int warps = static_cast<int>(std::max<size_t>(1, std::min<size_t>(want_warps, (200 * 1024 - fixed_bytes) / per_warp)));
+    const size_t smem = fixed_bytes + per_warp * warps;
+    PairParams p{};
+    common_params(p, val_dev, nullptr, theta_dev, n_frames, n_channels, plane, lut_size, curve_row_base_host, valid_lo, valid_hi, 0,
+                  interp_mode);
+    p.sums = fused_dev;
+    p.hist = static_cast<float *>(workspace_dev);
+    p.n_copies = n_copies;
+    p.n_pairs = 1;
+    if (int rc = fill_pairs(fn, p.pairs, pair_i_host, pair_j_host, pair_ratio_host, 0, 1, n_frames)) return rc;
+    const int64_t n_groups = (plane + 63) / 64;
+    auto launch = [&](auto kernel) -> int {
+        if (int rc = set_smem(kernel, smem)) return rc;
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
+        per_sm = g_tuning.grad_blocks_per_sm > 0 ? g_tuning.grad_blocks_per_sm : std::max(per_sm, 1);
+        const int64_t gx = std::min<int64_t>((n_groups + warps - 1) / warps, std::max<int64_t>(1, resident_blocks_per_channel(per_sm, n_channels)));
+        kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), warps * 32, smem, s>>>(p);
+        return 0;
+    };
+    int rc;
+    if (relative) rc = modes ? launch(pair_grad2_kernel<false, true, true, true>) : launch(pair_grad2_kernel<false, true, false, true>);
+    else rc = modes ? launch(pair_grad2_kernel<false, false, true, true>) : launch(pair_grad2_kernel<false, false, false, true>);
+    if (rc) return rc;
+    if (int rc2 = launched("pair_grad2_kernel<fused>")) return rc2;
+    const dim3 grid(static_cast<unsigned>((n_channels * lut_size + 31) / 32), static_cast<unsigned>(n_channels));
+    fused_finalize_kernel<<<grid, 256, 0, s>>>(static_cast<const float *>(workspace_dev), fused_dev + n_channels * 5, n_channels, lut_size,
+                                               n_copies);
+    return launched("fused_finalize_kernel");
+}
+
+extern "C" int clair_pair_fused_combine(const double *fused_dev, int n_channels, int lut_size, double *linloss_dev, double *mean_dev,
+                                        double *grad_theta_dev, void *stream) {
+    if (!fused_dev || !linloss_dev || !mean_dev) return fail(CLAIR_E_ARG, "clair_pair_fused_combine: null buffer");
+    if (n_channels <= 0 || n_channels > CLAIR_MAX_CHANNELS || lut_size < 2 || lut_size > CLAIR_MAX_LUT)
+        return fail(CLAIR_E_LIMIT, "clair_pair_fused_combine: bad table shape");
+    const int blocks = std::max(1, (n_channels * lut_size + 255) / 256);
+    fused_combine_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(fused_dev, n_channels, lut_size, linloss_dev, mean_dev,
+                                                                                grad_theta_dev);
+    return launched("fused_combine_kernel");
 }
 
 extern "C" int clair_icrf_backward_theta(const float *x_dev, const float *grad_y_dev, double *grad_theta_dev,

@@ -469,6 +469,49 @@ def pair_grad(val: torch.Tensor, std: Optional[torch.Tensor], i_idx, j_idx, rati
     return grad
 
 
+def pair_fused(val: torch.Tensor, i_idx, j_idx, ratio, theta: torch.Tensor, valid_lo: float, valid_hi: float, relative: bool,
+               row_base=None, out: Optional[torch.Tensor] = None, interp_mode: int = _native.INTERP_LINEAR) -> torch.Tensor:
+    """Single-pass statistics + un-normalised table gradient of ONE exposure pair without uncertainty weighting
+    (clair_pair_fused): float64 buffer [(1, C, 5) sums | (C, C, L) tables], accumulated into `out` when given."""
+    lib = _native.load()
+    val = _stack(val, "val_batch")
+    n, c, h, w = val.shape
+    pi, pj, pr = _pair_arrays(i_idx, j_idx, ratio)
+    th = _table(theta, val.device, c)
+    lut = th.shape[1]
+    size = lib.clair_pair_fused_doubles(c, lut)
+    buf = torch.zeros(size, dtype=_F64, device=val.device) if out is None else out
+    ws = _workspace(val.device, c, lut)
+    keep, rows = _rows(row_base, c)
+    with torch.cuda.device(val.device):
+        rc = lib.clair_pair_fused(_ptr(val), n, c, h * w, pi.ctypes.data_as(ctypes.c_void_p), pj.ctypes.data_as(ctypes.c_void_p),
+                                  pr.ctypes.data_as(ctypes.c_void_p), pi.shape[0], _ptr(th), lut, int(interp_mode), rows,
+                                  float(np.float32(valid_lo)), float(np.float32(valid_hi)), int(bool(relative)), _ptr(buf), _ptr(ws),
+                                  ws.numel() * 4, _stream(val.device))
+    _native.check(rc, "clair_pair_fused")
+    return buf
+
+
+def can_fuse_pair(val: torch.Tensor, std, n_pairs: int, unc_weighting: bool) -> bool:
+    """Whether a training step can take the single-pass kernel: exactly one exposure pair, weights that do not depend on
+    the uncertainty, an even plane and an 8-byte aligned fp32 stack."""
+    return (n_pairs == 1 and not (unc_weighting and std is not None) and torch.is_tensor(val) and val.is_cuda and val.dtype == _F32
+            and val.dim() == 4 and (val.shape[2] * val.shape[3]) % 2 == 0 and val.is_contiguous() and val.data_ptr() % 8 == 0)
+
+
+def pair_fused_combine(fused: torch.Tensor, channels: int, lut: int, want_grad: bool = True):
+    """(linloss (C,), mean (1, C), grad (C, L) | None), float64, from the (all-reduced) buffer of pair_fused."""
+    lib = _native.load()
+    dev = fused.device
+    linloss = torch.empty((channels,), dtype=_F64, device=dev)
+    mean = torch.empty((1, channels), dtype=_F64, device=dev)
+    grad = torch.zeros((channels, lut), dtype=_F64, device=dev) if want_grad else None
+    with torch.cuda.device(dev):
+        rc = lib.clair_pair_fused_combine(_ptr(fused), channels, lut, _ptr(linloss), _ptr(mean), _ptr(grad), _stream(dev))
+    _native.check(rc, "clair_pair_fused_combine")
+    return linloss, mean, grad
+
+
 def pair_upstream(sums: torch.Tensor):
     """(linloss (C,), mean (P,C), upstream (P,C), mean_for_grad (P,C)) float64 from the (P,C,5) sums, on the device."""
     lib = _native.load()

@@ -26,6 +26,14 @@ def linearity_loss_and_table_grad(images, stds, i_idx, j_idx, ratio_pairs, table
     `reduce_fn`, if given, is applied in place to the (P, C, 5) sums and to the (C, L) gradient: the data-parallel
     trainer passes an NCCL all-reduce here (spatial shards of one image add their sums).
     """
+    if want_grad and table is not None and kernels.can_fuse_pair(images, stds, len(ratio_pairs), use_uncertainty_weighting):
+        # one exposure pair, weights independent of the uncertainty: statistics and gradient in ONE pass over the stack and,
+        # when sharded, ONE all-reduce (the upstream factor is a scalar per channel and is applied afterwards)
+        fused = kernels.pair_fused(images, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold, upper_valid_threshold,
+                                   use_relative_linearity_loss, row_base=row_base, interp_mode=interp_mode)
+        if reduce_fn is not None:
+            reduce_fn(fused)
+        return kernels.pair_fused_combine(fused, table.shape[0], table.shape[1])
     sums = kernels.pair_stats(images, stds, i_idx, j_idx, ratio_pairs, table, lower_valid_threshold,
                               upper_valid_threshold, use_relative_linearity_loss, use_uncertainty_weighting,
                               row_base=row_base, means_only=True, interp_mode=interp_mode)

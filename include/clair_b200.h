@@ -372,6 +372,28 @@ CLAIR_API int clair_pair_grad(const float *val_dev, const float *std_dev, int n_
                     const double *upstream_dev, const double *mean_dev, double *grad_theta_dev,
                     void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/*
+ * One training step's statistics AND table gradient in a single pass over the stack, for the case of exactly one exposure
+ * pair without uncertainty weighting (BASELINE config 5: data-parallel training on 100 MP exposure pairs; replaces
+ * clair_pair_means + clair_pair_upstream + clair_pair_grad for training/icrf_training.py:105-149).  With one pair the
+ * upstream factor of the closed-form backward is one scalar per channel, so the kernel scatters the un-normalised gradient
+ * and the scalar is applied afterwards:
+ *   fused_dev   clair_pair_fused_doubles(C, L) float64, ACCUMULATED into (zero it first):
+ *               [c*5 + 0] sum M*Wt, [c*5 + 1] sum M*Wt*l of channel c (the (1, C, 5) layout of clair_pair_stats), then
+ *               T[c][u][k] (C, C, L): the un-normalised table gradient of the elements of channel c.
+ *               Row-band shards of one image add (all-reduce) this ONE buffer.
+ *   clair_pair_fused_combine: mean[c] = s1/max(s0,1e-8), linloss[c] = sqrt(mean^2), U[c] = mean/linloss/max(s0,1e-8),
+ *               grad_theta[u][k] += sum_c U[c] T[c][u][k]   (grad_theta_dev (C, L) float64, may be NULL: loss only).
+ * Other arguments as clair_pair_grad.  n_pairs must be 1 (CLAIR_E_MODE otherwise); H*W even, 8-byte aligned stack.
+ */
+CLAIR_API size_t clair_pair_fused_doubles(int n_channels, int lut_size);
+CLAIR_API int clair_pair_fused(const float *val_dev, int n_frames, int n_channels, int64_t plane, const int32_t *pair_i_host,
+                     const int32_t *pair_j_host, const double *pair_ratio_host, int n_pairs, const float *theta_dev,
+                     int lut_size, int interp_mode, const int32_t *curve_row_base_host, float valid_lo, float valid_hi,
+                     int relative, double *fused_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+CLAIR_API int clair_pair_fused_combine(const double *fused_dev, int n_channels, int lut_size, double *linloss_dev,
+                             double *mean_dev, double *grad_theta_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -432,6 +432,48 @@ def test_row_band_and_graphed_training_in_every_mode(ct, mode):
     assert max_abs_over_max(m2.icrf.detach().cpu().numpy(), m1.icrf.detach().cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("mode", ["linear", "catmull", "lookup"])
+@pytest.mark.parametrize("relative", [True, False])
+def test_single_pair_fused_pass_matches_two_pass_and_oracle(ct, mode, relative):
+    """One exposure pair without uncertainty weights takes clair_pair_fused (statistics + un-normalised gradient in one pass,
+    upstream applied afterwards): equal to the two-pass kernels and to the numpy oracle; row bands accumulate into one
+    buffer (the single all-reduce of the data-parallel step)."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.training import linearity_loss_and_table_grad
+    code = {"linear": ct._native.INTERP_LINEAR, "lookup": ct._native.INTERP_LOOKUP, "catmull": ct._native.INTERP_CATMULL}[mode]
+    h, w = 50, 84
+    val, std, _ = ct.synthetic.make_stack(2, 3, h, w, bits=16, seed=17)
+    if mode == "lookup":
+        std = None
+    t = np.array([0.01, 0.02])
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    i_idx, j_idx, ratio = ct.common.get_valid_exposure_pairs(torch.from_numpy(t), 0.25)
+    assert len(i_idx) == 1
+    dv, ds = val.to(DEV), None if std is None else std.to(DEV)
+    assert kernels.can_fuse_pair(dv, ds, 1, False)
+    lin, spatial, grad = linearity_loss_and_table_grad(dv, ds, i_idx, j_idx, ratio, theta, 1 / 255, 254 / 255, relative, False,
+                                                       interp_mode=code)
+    o = orc.train_loss_and_grad(val.numpy(), None if std is None else std.numpy(), t, theta.cpu().numpy(), 0.25, relative=relative,
+                                unc_weighting=False, mode=mode)
+    assert max_rel(lin.cpu().numpy(), o["linloss"]) < TOL and max_rel(spatial.cpu().numpy(), o["spatial"]) < TOL
+    assert max_abs_over_max(grad.cpu().numpy(), o["grad_lin"]) < TOL
+    # the two-pass kernels (what more than one pair takes)
+    sums = kernels.pair_stats(dv, ds, i_idx, j_idx, ratio, theta, 1 / 255, 254 / 255, relative, False, means_only=True, interp_mode=code)
+    lin2, mean2, up, mfg = kernels.pair_upstream(sums)
+    grad2 = kernels.pair_grad(dv, ds, i_idx, j_idx, ratio, theta, 1 / 255, 254 / 255, relative, False, up, mfg, interp_mode=code)
+    assert max_rel(lin.cpu().numpy(), lin2.cpu().numpy()) < 1e-6 and max_abs_over_max(grad.cpu().numpy(), grad2.cpu().numpy()) < 2e-6
+    # row bands into one buffer
+    buf = None
+    for r0, r1 in ((0, 13), (13, 30), (30, h)):
+        rb = kernels.shard_row_base(3, h, w, r0)
+        buf = kernels.pair_fused(dv[:, :, r0:r1].contiguous(), i_idx, j_idx, ratio, theta, 1 / 255, 254 / 255, relative, row_base=rb,
+                                 out=buf, interp_mode=code)
+    lin_b, _, grad_b = kernels.pair_fused_combine(buf, 3, 256)
+    assert max_rel(lin_b.cpu().numpy(), lin.cpu().numpy()) < 1e-7 and max_abs_over_max(grad_b.cpu().numpy(), grad.cpu().numpy()) < 1e-6
+    # with uncertainty weights (and std images) the step keeps the two-pass kernels
+    assert not kernels.can_fuse_pair(dv, dv, 1, True) and not kernels.can_fuse_pair(dv, ds, 2, False)
+
+
 def test_lookup_model_errors_and_table_gradient(ct):
     """LOOKUP has no image edge: drivers that propagate std images through the model raise like the reference's autograd
     call; the table edge (a gather) exists and matches a scatter of the upstream gradient."""
