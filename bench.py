@@ -559,7 +559,38 @@ def secondary_metrics(dev):
         return spatial_statistics(sums, True)
 
     ms3 = timed(lin, 2, 10)
-    del val, std
+    # end to end through measure_linearity from pinned host memory: fp32 val + std (3.19 GB over PCIe) against the camera's
+    # uint16 codes + StdSpec (0.80 GB, normalised on the device by clair_expand_codes)
+    from torch.utils.data import DataLoader as _DL
+    from clair_torch_b200.datasets import StdSpec as _Spec
+    lin_model = ct.ICRFModelDirect(icrf=theta.clone()).to(dev)
+
+    def one_batch_loader(batch):
+        class One(torch.utils.data.Dataset):
+            def __len__(self):
+                return 1
+
+            def __getitem__(self, i):
+                return batch
+
+        return _DL(One(), batch_size=None, shuffle=False)
+
+    meta = {"exposure_time": torch.from_numpy(t)}
+    codes_h = torch.round(val * 65535.0).to(torch.int32).to(torch.uint16).cpu().pin_memory()
+    l_codes = one_batch_loader((torch.arange(16), codes_h, _Spec("multiplier", 0.05), meta))
+    l_f32 = one_batch_loader((torch.arange(16), val.cpu().pin_memory(), std.cpu().pin_memory(), meta))
+
+    def wall(loader, reps=3):
+        ct.measure_linearity(loader, dev, True, True, lin_model)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out_ = ct.measure_linearity(loader, dev, True, True, lin_model)
+            out_[1].cpu()
+        return (time.perf_counter() - t0) / reps * 1e3
+
+    e2e3_f32, e2e3_codes = wall(l_f32), wall(l_codes)
+    del val, std, codes_h, l_codes, l_f32
     torch.cuda.empty_cache()
     peak = peaks()[0]
     # per-frame linearisation of the c4 frames (24 MP, 16-bit as fp32 val + std)
@@ -636,7 +667,10 @@ def secondary_metrics(dev):
     elems3 = 16 * CHANNELS * 2160 * 3840
     out["linearity_c3"] = {"ms": ms3, "pairs": int(len(i_idx)), "config": "16x3x2160x3840 16-bit, thr 0.2, relative, unc. weighting",
                            "pair_elements_per_s": len(i_idx) * CHANNELS * 2160 * 3840 / (ms3 * 1e-3),
-                           "hbm_frac": elems3 * 8 / (ms3 * 1e-3) / 1e9 / peaks()[0]}
+                           "hbm_frac": elems3 * 8 / (ms3 * 1e-3) / 1e9 / peaks()[0],
+                           "e2e_ms_fp32_host_batch": e2e3_f32, "e2e_ms_uint16_codes_host_batch": e2e3_codes,
+                           "e2e_note": "measure_linearity(pinned host batch) incl. H2D and the D2H read of the result: fp32 val + std "
+                                       "(3.19 GB) vs uint16 codes + StdSpec (0.80 GB, CastTo + Normalize + std on the device)"}
     return out
 
 

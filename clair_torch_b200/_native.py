@@ -91,6 +91,8 @@ _PROTOTYPES = {
                                    _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p,
                                    _c.c_float, _c.c_float, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
                                    _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "clair_expand_codes": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_float, _c.c_int, _c.c_float, _c.c_int64, _c.c_void_p, _c.c_void_p,
+                                      _c.c_void_p]),
     "clair_pair_fused_doubles": (_c.c_size_t, [_c.c_int, _c.c_int]),
     "clair_pair_fused": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                     _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_float, _c.c_float, _c.c_int, _c.c_void_p,

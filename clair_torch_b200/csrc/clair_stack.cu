@@ -429,6 +429,57 @@ extern "C" int clair_linearize_codes(const void *codes_dev, int code_bytes, floa
     return launched("linearize_codes_kernel");
 }
 
+// Camera codes -> the fp32 value (and std) stacks the pair kernels take: CastTo + Normalize + missing-std synthesis on the
+// device, so that a 16-bit stack crosses PCIe as 2 bytes per sample instead of 8 (SURVEY.md 8(f) rank 2 for
+// measure_linearity / train_icrf, whose kernels are instruction-bound and re-read nothing: expanding once in HBM costs
+// ~0.6 ms for the c3 stack against 45 ms less on the link).  4 codes per thread, IEEE division like the CPU transform.
+namespace clair {
+template <int BYTES>
+__global__ void __launch_bounds__(kBlock) expand_codes_kernel(const void *__restrict__ codes, float code_max, int std_mode, float std_value,
+                                                             int64_t n_quads, float *__restrict__ val, float *__restrict__ std) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kBlock;
+    for (int64_t q = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; q < n_quads; q += stride) {
+        uint32_t c[4];
+        if constexpr (BYTES == 1) {
+            const uint32_t w = __ldcs(static_cast<const uint32_t *>(codes) + q);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) c[k] = (w >> (8 * k)) & 0xffu;
+        } else {
+            const uint2 w = __ldcs(static_cast<const uint2 *>(codes) + q);
+            c[0] = w.x & 0xffffu; c[1] = w.x >> 16; c[2] = w.y & 0xffffu; c[3] = w.y >> 16;
+        }
+        Pack<4> x, s;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            x.v[k] = __fdiv_rn(static_cast<float>(c[k]), code_max);
+            s.v[k] = (std_mode == kStdMultiplier) ? __fmul_rn(x.v[k], std_value) : std_value;
+        }
+        store_stream<4>(val + 4 * q, x);
+        if (std != nullptr) store_stream<4>(std + 4 * q, s);
+    }
+}
+}  // namespace clair
+
+extern "C" int clair_expand_codes(const void *codes_dev, int code_bytes, float code_max, int std_mode, float std_value,
+                                  int64_t n_elements, float *val_dev, float *std_dev, void *stream) {
+    NvtxRange nvtx_range_("clair_expand_codes");
+    if (!codes_dev || !val_dev) return fail(CLAIR_E_ARG, "clair_expand_codes: null buffer");
+    if (code_bytes != 1 && code_bytes != 2) return fail(CLAIR_E_MODE, "clair_expand_codes: code_bytes must be 1 (uint8) or 2 (uint16)");
+    if (!(code_max > 0.0f)) return fail(CLAIR_E_ARG, "clair_expand_codes: code_max must be positive");
+    if (std_mode != kStdNone && std_mode != kStdMultiplier && std_mode != kStdConstant)
+        return fail(CLAIR_E_MODE, "clair_expand_codes: std_mode must be 0 (none), 2 (multiplier) or 3 (constant)");
+    if ((std_mode != kStdNone) != (std_dev != nullptr)) return fail(CLAIR_E_ARG, "clair_expand_codes: std_dev goes with std_mode 2 / 3");
+    if (n_elements <= 0 || n_elements % 4 != 0 || reinterpret_cast<uintptr_t>(codes_dev) % (4 * code_bytes) != 0 ||
+        reinterpret_cast<uintptr_t>(val_dev) % 16 != 0 || reinterpret_cast<uintptr_t>(std_dev) % 16 != 0)
+        return fail(CLAIR_E_ARG, "clair_expand_codes: the element count must be a multiple of 4 and the buffers aligned for 4-sample accesses");
+    const int64_t quads = n_elements / 4;
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>((quads + kBlock - 1) / kBlock, static_cast<int64_t>(device_sm_count()) * 16));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (code_bytes == 1) expand_codes_kernel<1><<<grid, kBlock, 0, s>>>(codes_dev, code_max, std_mode, std_value, quads, val_dev, std_dev);
+    else expand_codes_kernel<2><<<grid, kBlock, 0, s>>>(codes_dev, code_max, std_mode, std_value, quads, val_dev, std_dev);
+    return launched("expand_codes_kernel");
+}
+
 // Host in, host out: band b+1 travels to the device (copy engine, in_stream) and band b-1 back to the host (second copy
 // engine, out_stream) while the kernel linearises band b.  Both PCIe directions run at once (49.9 GB/s each way measured
 // with the two copy engines; a kernel reading and writing pinned host memory itself reaches 39 GB/s each way).

@@ -17,10 +17,23 @@ def as_device(device) -> torch.device:
     return dev
 
 
-def stage_batch(val_batch, std_batch, device, gpu_transforms=None):
-    """inference/hdr_merge.py:64-71: copy value / std images to the device and run the optional gpu transforms."""
-    images = val_batch.to(device=device, non_blocking=True)
-    stds = std_batch.to(device=device, non_blocking=True) if std_batch is not None else None
+def stage_batch(val_batch, std_batch, device, gpu_transforms=None, code_max=None, expand_codes=False):
+    """inference/hdr_merge.py:64-71: copy value / std images to the device and run the optional gpu transforms.
+    `expand_codes` — integer ingest for the pair drivers (the merge / linearise kernels ingest codes
+    themselves): a uint8 / uint16 code batch is copied as it is and normalised on the device (`kernels.expand_codes`), with
+    a `StdSpec` std batch synthesised there as well."""
+    if expand_codes and torch.is_tensor(val_batch) and val_batch.dtype in (torch.uint8, torch.uint16):
+        from .. import kernels
+        if std_batch is not None and torch.is_tensor(std_batch):
+            images, _ = kernels.expand_codes(val_batch, None, code_max, device)
+            stds = std_batch.to(device=device, non_blocking=True)
+        else:
+            images, stds = kernels.expand_codes(val_batch, std_batch, code_max, device)
+    else:
+        if expand_codes and std_batch is not None and not torch.is_tensor(std_batch):
+            raise ValueError("a StdSpec is evaluated on the device from integer codes: pass uint8 / uint16 value codes with it")
+        images = val_batch.to(device=device, non_blocking=True)
+        stds = std_batch.to(device=device, non_blocking=True) if std_batch is not None else None
     for transform in gpu_transforms or ():
         if transform is not None:
             images = transform(images)

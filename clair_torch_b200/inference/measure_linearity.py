@@ -27,11 +27,16 @@ def spatial_statistics(sums: torch.Tensor, with_errors: bool):
 
 
 def measure_linearity(dataloader: DataLoader, device, use_uncertainty_weighting: bool = True,
-                      use_relative_linearity_loss: bool = True, icrf_model: Optional[ICRFModelBase] = None):
+                      use_relative_linearity_loss: bool = True, icrf_model: Optional[ICRFModelBase] = None, *,
+                      code_max: Optional[float] = None):
     """(exposure ratios (P,), spatial loss mean (P,C), its std (P,C), its mean uncertainty (P,C) | None), float64.
 
     One fused kernel pass over the batch for a model in any InterpMode (LINEAR, LOOKUP, CATMULL) or none; as in the
     reference, a LOOKUP model together with std images raises RuntimeError (it has no derivative to propagate them through).
+
+    Integer ingest: a batch may carry the raw uint8 / uint16 camera codes (and a `datasets.StdSpec` instead of std images);
+    CastTo + Normalize(max_val=code_max, default 255 / 65535) and the std synthesis then run on the device, and the stack
+    crosses PCIe as 1-2 bytes per sample — bit-identical to handing over the CPU-transformed fp32 images.
 
     Like the reference, only the FIRST batch of the dataloader is measured (the `return` at :74 sits inside the
     loop), so pass the whole stack as one batch.
@@ -44,7 +49,7 @@ def measure_linearity(dataloader: DataLoader, device, use_uncertainty_weighting:
     dev = as_device(device)
     table, interp_mode = model_table(icrf_model, dev)          # any InterpMode: the kernels evaluate all three
     for _, val_batch, std_batch, meta_batch in dataloader:
-        images, stds = stage_batch(val_batch, std_batch, dev)
+        images, stds = stage_batch(val_batch, std_batch, dev, code_max=code_max, expand_codes=True)
         exposures = meta_batch["exposure_time"]
         i_idx, j_idx, ratio_pairs = get_valid_exposure_pairs(exposures, RATIO_THRESHOLD)
         sums = kernels.pair_stats(images, stds, i_idx, j_idx, ratio_pairs, table, VALID_LO, VALID_HI,

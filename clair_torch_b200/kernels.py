@@ -207,6 +207,34 @@ def _linearize_codes(lib, val, std, theta, row_base, device, pinned_out, interp_
     return lin, sigma
 
 
+def expand_codes(codes: torch.Tensor, std=None, code_max=None, device=None):
+    """(fp32 value stack, fp32 std stack | None) from uint8 / uint16 camera codes: CastTo(float32) + Normalize(max_val=code_max)
+    and, for a `datasets.StdSpec`, the synthesised std, evaluated on the device (clair_expand_codes; bit-identical to the
+    reference's CPU transforms).  `codes` may sit in (pinned) host memory: it crosses PCIe as 1-2 bytes per sample."""
+    lib = _native.load()
+    if not torch.is_tensor(codes) or codes.dtype not in _CODE_DTYPES:
+        raise TypeError("codes must be a uint8 / uint16 tensor")
+    dev = torch.device(device) if device is not None else codes.device
+    if dev.type != "cuda":
+        raise RuntimeError("expand_codes runs on a CUDA device: clair_torch_b200 has no CPU path")
+    codes = codes.detach().contiguous().to(device=dev, non_blocking=True)
+    if codes.numel() % 4 != 0:
+        raise ValueError("integer ingest needs the element count to be a multiple of 4")
+    code_bytes, default_max = _CODE_DTYPES[codes.dtype]
+    std_mode, std_value = 0, 0.0
+    if std is not None:
+        if not hasattr(std, "mode") or std.mode not in _STD_MODES:
+            raise TypeError(f"std must be None or a StdSpec, got {type(std)}")
+        std_mode, std_value = _STD_MODES[std.mode], float(np.float32(std.value))
+    val = torch.empty(tuple(codes.shape), dtype=_F32, device=dev)
+    sd = torch.empty(tuple(codes.shape), dtype=_F32, device=dev) if std_mode else None
+    with torch.cuda.device(dev):
+        rc = lib.clair_expand_codes(_ptr(codes), code_bytes, float(default_max if code_max is None else code_max), std_mode, std_value,
+                                    codes.numel(), _ptr(val), _ptr(sd), _stream(dev))
+    _native.check(rc, "clair_expand_codes")
+    return val, sd
+
+
 class HdrMergeState:
     """Running (mean, sum of weights, variance) of the merge — WBOMean's state (common/statistics.py:27-29)
     plus hdr_merge.py's running_variance, kept as device buffers between DataLoader batches."""

@@ -168,12 +168,16 @@ def train_icrf(dataloader: DataLoader, batch_size: int, device, icrf_model: ICRF
                use_relative_linearity_loss: bool = True, use_uncertainty_weighting: bool = True, epochs: int = 150,
                patience: int = 300, alpha: float = 1.0, beta: float = 1.0, gamma: float = 1.0, delta: float = 1.0,
                lower_valid_threshold: float = 1 / 255, upper_valid_threshold: float = 254 / 255,
-               exposure_ratio_threshold: float = 0.1, *, verbose: bool = True, use_cuda_graph: bool = True) -> ICRFModelBase:
+               exposure_ratio_threshold: float = 0.1, *, verbose: bool = True, use_cuda_graph: bool = True,
+               code_max: Optional[float] = None) -> ICRFModelBase:
     """Training loop with the reference's signature, defaults, early stopping and scheduler handling.
 
     `use_cuda_graph`: a batch that stays at the same device address from one epoch to the next (a device-resident
     dataset) with capturable optimisers (the default ones are) is stepped through GraphedTrainStep from its third visit
-    on; anything else takes the eager step."""
+    on; anything else takes the eager step.
+
+    Batches may carry raw uint8 / uint16 camera codes (and a `datasets.StdSpec` for the std): they are normalised on the
+    device (`code_max` defaults to 255 / 65535), see measure_linearity."""
     if not isinstance(dataloader, DataLoader):
         raise ArgumentTypeError(f"dataloader must be a torch DataLoader, got {type(dataloader)}")
     if not isinstance(icrf_model, ICRFModelBase):
@@ -205,7 +209,7 @@ def train_icrf(dataloader: DataLoader, batch_size: int, device, icrf_model: ICRF
     for epoch in range(epochs):
         running_loss = torch.zeros(channels if len(optimizers) > 1 else (), dtype=torch.float64, device=dev)
         for _, val_batch, std_batch, meta_batch in dataloader:
-            images, stds = stage_batch(val_batch, std_batch, dev)
+            images, stds = stage_batch(val_batch, std_batch, dev, code_max=code_max, expand_codes=True)
             if images.shape[0] < 2:
                 if verbose:
                     print("Skipped batch due to single image.")

@@ -114,6 +114,18 @@ CLAIR_API int clair_linearize_codes(const void *codes_dev, int code_bytes, float
                           void *stream);
 
 /*
+ * Camera codes -> the normalised fp32 value stack (and its synthesised std stack) on the device: the reference's CastTo +
+ * Normalize CPU transforms (common/transforms.py:107-190: x = fl32(code) / fl32(code_max), an IEEE division) and the
+ * missing-std synthesis of MultiFileMapDataset (datasets/base.py:128-133), for the drivers whose kernels take fp32 stacks —
+ * measure_linearity and train_icrf (inference/measure_linearity.py:41-43, training/icrf_training.py:96-98): the stack then
+ * crosses PCIe as 1 or 2 bytes per sample.  Bit-identical to the CPU transforms.
+ *   codes_dev   n_elements uint8 / uint16 codes (any shape, n_elements a multiple of 4), device memory
+ *   std_mode    0: no std (std_dev NULL) | 2: std = x * std_value | 3: std = std_value
+ */
+CLAIR_API int clair_expand_codes(const void *codes_dev, int code_bytes, float code_max, int std_mode, float std_value,
+                       int64_t n_elements, float *val_dev, float *std_dev, void *stream);
+
+/*
  * clair_linearize for images that live in page-locked HOST memory and whose results are wanted there too (the
  * generator ends with .cpu(), inference/linearization.py:132): the planes are cut into n_bands bands of pixels; band b+1
  * is copied in (in_stream), band b is linearised (stream) and band b-1 is copied out (out_stream) at the same time, so

@@ -920,6 +920,42 @@ def test_linearize_integer_ingest_is_bit_identical(ct, bits):
         ct.kernels.linearize(codes.to(DEV), StdSpec("multiplier", 0.05), theta, interp_mode=ct._native.INTERP_LOOKUP)
 
 
+@pytest.mark.parametrize("bits", [8, 16])
+def test_pair_drivers_from_integer_codes_are_bit_identical(ct, bits):
+    """measure_linearity and a train_icrf step fed with raw uint8 / uint16 codes + StdSpec (normalised on the device by
+    clair_expand_codes) equal the same calls on the CPU-transformed fp32 images; every code of the 8-bit range and a sweep
+    of the 16-bit range normalises like the IEEE division."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.datasets import ExposureStackDataset, StdSpec, custom_collate
+    maxval = 255.0 if bits == 8 else 65535.0
+    dt = torch.uint8 if bits == 8 else torch.uint16
+    val, _, t = ct.synthetic.make_stack(6, 3, 40, 64, bits=bits, seed=21 + bits, std_multiplier=None)
+    codes = torch.round(val * maxval).to(torch.int32).to(dt)
+    x = codes.to(torch.float32) / maxval
+    m = float(np.float32(0.05))
+    xv, xs = kernels.expand_codes(codes.pin_memory(), StdSpec("multiplier", 0.05), device=DEV)
+    assert torch.equal(xv.cpu(), x) and torch.equal(xs.cpu(), x * m)
+    every = torch.arange(0, 256 if bits == 8 else 65536, dtype=torch.int32).to(dt)
+    ev, es = kernels.expand_codes(every.to(DEV), StdSpec("constant", 0.01))
+    assert torch.equal(ev.cpu(), every.to(torch.float32) / maxval) and torch.equal(es.cpu(), torch.full((every.numel(),), 0.01))
+    c12 = kernels.expand_codes(every.to(DEV), None, code_max=4095.0)[0]
+    assert torch.equal(c12.cpu(), every.to(torch.float32) / 4095.0)
+    model = _model(ct, ct.synthetic.reference_curve(3).numpy())
+    ds_codes = ExposureStackDataset(list(codes), StdSpec("multiplier", 0.05), list(t))
+    ds_f32 = ExposureStackDataset(list(x), list(x * m), list(t))
+    got = ct.measure_linearity(DataLoader(ds_codes, batch_size=6, collate_fn=custom_collate), DEV, True, True, model)
+    want = ct.measure_linearity(DataLoader(ds_f32, batch_size=6, collate_fn=custom_collate), DEV, True, True, model)
+    assert torch.equal(got[0], want[0])
+    for a, b in zip(got[1:], want[1:]):
+        assert max_rel(a.cpu().numpy(), b.cpu().numpy()) < 1e-12          # same kernels on the same bits; float64 atomics order
+    losses = []
+    for ds in (ds_codes, ds_f32):
+        mdl = ct.ICRFModelDirect(256, 3, initial_power=2.2).to(DEV)
+        ct.train_icrf(DataLoader(ds, batch_size=6, collate_fn=custom_collate), 6, DEV, mdl, epochs=2, verbose=False, use_cuda_graph=False)
+        losses.append(mdl.icrf.detach().cpu().numpy())
+    assert max_rel(losses[0], losses[1], 1e-6) < 1e-5
+
+
 # ---- streaming frame statistics (SURVEY.md 8(f) rank 3) -------------------------------------------------
 def test_wbomeanvar_golden(ct):
     from clair_torch_b200.common.statistics import WBOMeanVar
