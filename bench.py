@@ -97,6 +97,10 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)            # nvidia-smi holds driver locks while it runs: be sure it is gone
+        except Exception:                        # noqa: BLE001
+            self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.lines:
@@ -464,27 +468,42 @@ def dp_training_metrics(dev, rank, world):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # every rank must take the same path
     if flag.item() == 1.0:
         step, mode = graphed, "cuda graph (kernels, NCCL all-reduces and optimisers captured)"
-    for _ in range(3):
+    for _ in range(10):
         step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 20
-    sampler = ClockSampler(dev.index or 0)
-    if rank == 0:
-        sampler.start()
+    reps = 50
+    # (no nvidia-smi sampling here: the step is ~35 short launches per replay, and a polling nvidia-smi on a many-GPU box
+    # holds driver locks long enough to show in it)
     a.record()
     for _ in range(reps):
         step()
     b.record()
     torch.cuda.synchronize(dev)
     own_ms = a.elapsed_time(b) / reps
-    clocks = sampler.stop() if rank == 0 else None
     ms = torch.tensor([own_ms], dtype=torch.float64, device=dev)
+    ms_min = ms.clone()
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+        dist.all_reduce(ms_min, op=dist.ReduceOp.MIN)
+    ms, ms_min = float(ms.item()), float(ms_min.item())
+    # this rank's kernels alone (no collective, no optimiser): what the band costs on the device
+    def local_pass():
+        linearity_loss_and_table_grad(val, std, i_idx, j_idx, ratio, table, 1 / 255, 254 / 255, True, False, row_base=rb)
+    for _ in range(3):
+        local_pass()
+    torch.cuda.synchronize(dev)
+    a.record()
+    for _ in range(10):
+        local_pass()
+    b.record()
+    torch.cuda.synchronize(dev)
+    local_ms = torch.tensor([a.elapsed_time(b) / 10], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(local_ms, op=dist.ReduceOp.MAX)
+    local_ms = float(local_ms.item())
     # what does not shrink with N: the all-reduce alone (eager launches back to back, outside the graph)
     collective_us = None
     fused = torch.zeros(CHANNELS * 5 + CHANNELS * CHANNELS * LUT, dtype=torch.float64, device=dev)
@@ -501,7 +520,8 @@ def dp_training_metrics(dev, rank, world):
     return {"config": "100.7 MP (8192x12288) 16-bit RGB exposure pair (one image, same seed at every N), row bands, one pass "
                       "over the band and one NCCL all-reduce (sums + un-normalised gradient tables, 18.6 KB) per step",
             "ms_per_step": ms, "steps_per_s": 1e3 / ms, "scaling": "strong", "n_gpus": world, "step": mode, "parity": parity,
-            "collective_us": collective_us, "clocks": clocks}
+            "ms_per_step_fastest_rank": ms_min, "local_kernels_ms": local_ms,
+            "collective_us": collective_us}
 
 
 def secondary_metrics(dev):

@@ -488,60 +488,76 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
     int since_flush = 0;
 
     const uint32_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
-    // per-thread staging items: frame n, pixel offset q inside the tile, source pointer, shared-memory slot, table row
-    const float *src[TRIPS];
+    // Per-thread staging items: everything that does not change from tile to tile is set up once — the source pointer only
+    // advances by the grid's tile stride, the pixel position by the same (it is the bounds check), and because the host
+    // sizes the grid so that its stride in pixels is a multiple of C, the table rows of an item's four pixels never change
+    // (their biased shared-memory addresses are kept, not recomputed).  ncu's source page had 230 of 490 instructions per
+    // tile in this phase, a third of them address arithmetic.
+    const float *src[TRIPS];             // this thread's item in the tile that is loaded next
     uint32_t dst[TRIPS];                 // float offset of the item inside a tile buffer
-    uint32_t qoff[TRIPS], urow[TRIPS];
-    bool active[TRIPS];
-    const uint32_t du_tile = (gridDim.x * kStatsTile) % uC;
+    uint32_t pixn[TRIPS];                // first pixel of the item in the tile that is loaded next (>= plane: nothing left)
+    uint32_t pixs[TRIPS];                // ... in the tile that is staged next
+    uint32_t bias[TRIPS][4];             // biased table-row addresses of the item's four pixels
+    const uint32_t tile_stride = gridDim.x * kStatsTile;
+    const bool rows_fixed = (tile_stride % uC) == 0u;
+    uint32_t urow[TRIPS];
 #pragma unroll
     for (int t = 0; t < TRIPS; ++t) {
         const int item = threadIdx.x + t * blockDim.x;
         const int n = item >> 5;
-        active[t] = n < N;
-        qoff[t] = (static_cast<uint32_t>(item) & 31u) * 4u;
-        src[t] = val_c + static_cast<int64_t>(active[t] ? n : 0) * frame_stride + qoff[t];
-        dst[t] = static_cast<uint32_t>((active[t] ? n : 0) * kFrameFloats) + qoff[t];
-        urow[t] = (blockIdx.x * kStatsTile + qoff[t] + static_cast<uint32_t>(p.rows.base(c))) % uC;   // row of the item's first pixel
+        const bool on = n < N;
+        const uint32_t qoff = (static_cast<uint32_t>(item) & 31u) * 4u;
+        pixn[t] = on ? blockIdx.x * kStatsTile + qoff : plane;
+        pixs[t] = pixn[t];
+        src[t] = val_c + static_cast<int64_t>(on ? n : 0) * frame_stride + blockIdx.x * kStatsTile + qoff;
+        dst[t] = static_cast<uint32_t>((on ? n : 0) * kFrameFloats) + qoff;
+        urow[t] = (blockIdx.x * kStatsTile + qoff + static_cast<uint32_t>(p.rows.base(c))) % uC;   // row of the item's first pixel
+        uint32_t u = urow[t];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { bias[t][k] = tab_bias + u * row_bytes; u = (u + 1 == uC) ? 0u : u + 1; }
     }
     float4 xv[TRIPS], sv[TRIPS];
-    auto prefetch = [&](uint32_t tile) {
-        const uint32_t pix0 = tile * kStatsTile;
+    auto prefetch = [&]() {
 #pragma unroll
         for (int t = 0; t < TRIPS; ++t) {
             xv[t] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             sv[t] = xv[t];
-            if (active[t] && tile < n_tiles && pix0 + qoff[t] < plane) {       // plane % 4 == 0: the whole item is in or out
-                xv[t] = __ldcs(reinterpret_cast<const float4 *>(src[t] + pix0));
-                if constexpr (ERR) sv[t] = __ldcs(reinterpret_cast<const float4 *>(src[t] + pix0 + std_minus_val));
+            if (pixn[t] < plane) {                                             // plane % 4 == 0: the whole item is in or out
+                xv[t] = __ldcs(reinterpret_cast<const float4 *>(src[t]));
+                if constexpr (ERR) sv[t] = __ldcs(reinterpret_cast<const float4 *>(src[t] + std_minus_val));
             }
+            // tile_stride < 2^32 - plane is checked on the host, so the position saturates instead of wrapping
+            pixn[t] = (pixn[t] < plane) ? pixn[t] + tile_stride : plane;
+            src[t] += tile_stride;
         }
     };
     // phase A: one item = 4 adjacent pixels of one frame, loaded one tile ahead; per-frame terms into tile buffer `buf`
-    auto stage = [&](uint32_t tile, float *buf) {
-        const uint32_t pix0 = tile * kStatsTile;
+    auto stage = [&](float *buf) {
 #pragma unroll
         for (int t = 0; t < TRIPS; ++t) {
-            if (active[t]) {
-                const bool live = pix0 + qoff[t] < plane;
-                uint32_t u = urow[t];
-                uint32_t bias[4];
+            if (threadIdx.x + t * blockDim.x < static_cast<unsigned>(N) * 32u) {
+                const bool live = pixs[t] < plane;
+                pixs[t] = live ? pixs[t] + tile_stride : plane;
+                if (!rows_fixed) {              // (grids smaller than C blocks per channel)
+                    uint32_t u = urow[t];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { bias[k] = tab_bias + u * row_bytes; u = (u + 1 == uC) ? 0u : u + 1; }
+                    for (int k = 0; k < 4; ++k) { bias[t][k] = tab_bias + u * row_bytes; u = (u + 1 == uC) ? 0u : u + 1; }
+                    urow[t] += tile_stride % uC;
+                    urow[t] = (urow[t] >= uC) ? urow[t] - uC : urow[t];
+                }
                 ModeRows mra{}, mrb{};
                 if constexpr (MODES) {
                     // LOOKUP reads the true channel row (base.py:148-158), CATMULL the k-mod-C row like LINEAR (:217-219)
                     const bool lookup = p.mode == CLAIR_INTERP_LOOKUP;
                     const float2 *rows[4];
-                    uint32_t ur = urow[t];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) { rows[k] = s_tab + (lookup ? static_cast<uint32_t>(c) : ur) * L; ur = (ur + 1 == uC) ? 0u : ur + 1; }
+                    for (int k = 0; k < 4; ++k) rows[k] = s_tab + (lookup ? static_cast<uint32_t>(c) : (bias[t][k] - tab_bias) / row_bytes) * L;
                     mra = ModeRows{rows[0], rows[1], p.mode, L};
                     mrb = ModeRows{rows[2], rows[3], p.mode, L};
                 }
-                const auto a = frame_terms2<ERR, RELATIVE, MODES>(xv[t].x, xv[t].y, sv[t].x, sv[t].y, has_model, bias[0], bias[1], lm1,
+                const auto a = frame_terms2<ERR, RELATIVE, MODES>(xv[t].x, xv[t].y, sv[t].x, sv[t].y, has_model, bias[t][0], bias[t][1], lm1,
                                                                   p.valid_lo, p.valid_hi, live, mra);
-                const auto b = frame_terms2<ERR, RELATIVE, MODES>(xv[t].z, xv[t].w, sv[t].z, sv[t].w, has_model, bias[2], bias[3], lm1,
+                const auto b = frame_terms2<ERR, RELATIVE, MODES>(xv[t].z, xv[t].w, sv[t].z, sv[t].w, has_model, bias[t][2], bias[t][3], lm1,
                                                                   p.valid_lo, p.valid_hi, live, mrb);
                 float *out = buf + dst[t];
                 *reinterpret_cast<ulonglong2 *>(out) = make_ulonglong2(a.f, b.f);
@@ -550,8 +566,6 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
                     *reinterpret_cast<ulonglong2 *>(out + 2 * kStatsTile) = make_ulonglong2(a.sig, b.sig);
                     if constexpr (RELATIVE) *reinterpret_cast<ulonglong2 *>(out + 3 * kStatsTile) = make_ulonglong2(a.rel, b.rel);
                 }
-                urow[t] += du_tile;
-                urow[t] = (urow[t] >= uC) ? urow[t] - uC : urow[t];
             }
         }
     };
@@ -654,7 +668,7 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
     // one buffer (very long stacks, where a second buffer would cost a resident block) it is A, barrier, B, barrier.
     const uint32_t nb = static_cast<uint32_t>(p.stats_buffers);
     const uint32_t buf_floats = static_cast<uint32_t>(N) * kFrameFloats;
-    prefetch(blockIdx.x);
+    prefetch();
     __syncthreads();                    // the table is staged
     uint32_t k_it = 0;
     for (uint32_t tile = blockIdx.x;; tile += gridDim.x, ++k_it) {
@@ -663,8 +677,8 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
         if (!stage_live && !pairs_live) break;
         if (nb == 1) __syncthreads();   // previous tile fully consumed (also orders the table staging on the first pass)
         if (stage_live) {
-            stage(tile, s_tile + (nb == 2 ? (k_it & 1u) * buf_floats : 0u));
-            prefetch(tile + gridDim.x);
+            stage(s_tile + (nb == 2 ? (k_it & 1u) * buf_floats : 0u));
+            prefetch();
         }
         if (nb == 1) __syncthreads();
         if (pairs_live) {
@@ -1607,7 +1621,7 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
     size_t smem = table_bytes + tile_bytes;
     const int per_launch = 16 * kMaxSlots;   // 64 pairs: 16 warps x 4 register slots
     // 128-bit staging loads need H*W % 4 == 0 and 16-byte aligned stacks (every frame / channel slab then is, too)
-    const bool vec_ok = plane % 4 == 0 && reinterpret_cast<uintptr_t>(val_dev) % 16 == 0 &&
+    const bool vec_ok = plane % 4 == 0 && plane < (1ll << 31) && reinterpret_cast<uintptr_t>(val_dev) % 16 == 0 &&
                         (!err || reinterpret_cast<uintptr_t>(std_dev) % 16 == 0) &&
                         (theta_dev == nullptr || (n_channels * lut_size) % 2 == 0);   // tile starts 16-byte aligned after the table
     const int va = (vec_ok && n_frames <= 32) ? 4 : 1;     // the packed kernel holds <= 2 staging items per thread, 16 warps
@@ -1648,7 +1662,9 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
             int per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
             per_sm = g_tuning.stats_blocks_per_sm > 0 ? g_tuning.stats_blocks_per_sm : std::max(per_sm, 1);
-            const int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, resident_blocks_per_channel(per_sm, n_channels)));
+            int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, resident_blocks_per_channel(per_sm, n_channels)));
+            // a grid stride that is a multiple of C pixels keeps every staging item on the same table rows in all its tiles
+            if (gx > n_channels) gx -= gx % n_channels;
             kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), warps * 32, smem, s>>>(p);
             return 0;
         };
