@@ -940,7 +940,7 @@ __device__ __forceinline__ float rcp_1ulp(float x) {     // MUFU.RCP + one Newto
 // loads instead of after them.  Quotients go through a 1-ulp reciprocal (the IEEE divisions were ~60 of the epilogue's
 // instructions per pixel).
 template <int VEC, bool WEIGHTED, bool MODES>
-__global__ void __launch_bounds__(kBlock) frame_stats_kernel(const FrameStatsParams p) {
+__global__ void __launch_bounds__(kBlock, WEIGHTED ? 2 : 4) frame_stats_kernel(const FrameStatsParams p) {
     extern __shared__ float2 s_tab[];
     const int C = p.n_channels, L = p.lut;
     const bool has_model = p.theta != nullptr;

@@ -1,9 +1,9 @@
 """The eight loss functions re-exported by clair_torch/training/__init__.py:6-14.
 
-The four curve penalties act on the (C, L) table (768 numbers) and stay in torch, on the product path of
-train_icrf.  The four per-pixel functions are kept for call compatibility only: train_icrf and
-measure_linearity here never materialise their (P, C, H, W) results — the fused kernels
-(clair_pair_stats / clair_pair_grad) compute the same quantities per pixel in registers.
+All eight are kept as torch functions for call compatibility only.  train_icrf evaluates the four curve penalties and
+their gradients on the device (clair_curve_penalties, one kernel), and train_icrf / measure_linearity never materialise
+the (P, C, H, W) results of the four per-pixel functions — the fused kernels (clair_pair_stats / clair_pair_grad /
+clair_pair_fused) compute the same quantities per pixel in registers.
 """
 from typing import Optional
 
