@@ -89,6 +89,7 @@ extern "C" int clair_set_tuning(const char *key, int value) {
     else if (k == "hdr_fixed_max") g_tuning.hdr_fixed_max = value;
     else if (k == "grad_warps") g_tuning.grad_warps = value;
     else if (k == "grad_copies") g_tuning.grad_copies = value;
+    else if (k == "hdr_tma") g_tuning.hdr_tma = value;
     else if (k == "stats_warps") g_tuning.stats_warps = value;
     else if (k == "stats_buffers") g_tuning.stats_buffers = value;
     else if (k == "stats_slots") g_tuning.stats_slots = value;

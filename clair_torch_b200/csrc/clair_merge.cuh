@@ -52,8 +52,35 @@ struct HdrParams {
 
 constexpr int kStdNone = 0, kStdTensor = 1, kStdMultiplier = 2, kStdConstant = 3;
 constexpr int kSrcF32 = 0, kSrcU8 = 1, kSrcU16 = 2, kSrcU8Hwc = 3, kSrcU16Hwc = 4;   // Hwc: interleaved BGR camera layout
-__host__ __device__ constexpr bool src_is_u8(int src) { return src == kSrcU8 || src == kSrcU8Hwc; }
-__host__ __device__ constexpr bool src_is_hwc(int src) { return src == kSrcU8Hwc || src == kSrcU16Hwc; }
+// ...Tma: the same camera layout, a block's contiguous codes of every frame brought into shared memory by bulk copies
+// (cp.async.bulk + mbarrier, one trip ahead) instead of per-thread strided loads
+constexpr int kSrcU8HwcTma = 5, kSrcU16HwcTma = 6;
+__host__ __device__ constexpr bool src_is_u8(int src) { return src == kSrcU8 || src == kSrcU8Hwc || src == kSrcU8HwcTma; }
+__host__ __device__ constexpr bool src_is_tma(int src) { return src == kSrcU8HwcTma || src == kSrcU16HwcTma; }
+__host__ __device__ constexpr bool src_is_hwc(int src) { return src == kSrcU8Hwc || src == kSrcU16Hwc || src_is_tma(src); }
+
+// ---- bulk-copy staging (sm_90+ TMA without a tensor map: 1-D, 16-byte granular) ------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 // One frame's VEC pixel values.  SRC = kSrcF32: the fp32 stack the reference hands over.  kSrcU8 / kSrcU16: the raw
 // integer codes, normalised in-register exactly like the reference's CPU transforms do it (CastTo(float32) then
@@ -93,7 +120,8 @@ __device__ __forceinline__ float normalise_code16(uint32_t code, const HdrParams
 }
 
 template <int SRC, int VEC, bool SHORT = false>
-__device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int c, uint32_t pix, int64_t o, const float *s_x) {
+__device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int c, uint32_t pix, int64_t o, const float *s_x,
+                                                 const unsigned char *stage = nullptr, uint32_t stage_frame_bytes = 0) {
     if constexpr (SRC == kSrcF32) {
         return load_stream<VEC>(static_cast<const float *>(p.val) + o);
     } else if constexpr (src_is_u8(SRC)) {
@@ -101,10 +129,20 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int 
         Pack<VEC> r;
         if constexpr (VEC == 2) {
             // two pixels: one 16-bit load, or the 6 bytes of two BGR pixels as three (the pair starts 2-byte aligned)
+            if constexpr (SRC == kSrcU8HwcTma) {
+                // staged frame: the channel's two bytes straight from the thread's 6-byte window (byte loads, no selects)
+                const uint8_t *src = stage + n * stage_frame_bytes + threadIdx.x * 6 + (2 - c);
+                r.v[0] = s_x[src[0]];
+                r.v[1] = s_x[src[3]];
+                return r;
+            }
             if constexpr (SRC == kSrcU8Hwc) {
-                const uint16_t *src = reinterpret_cast<const uint16_t *>(static_cast<const uint8_t *>(p.val) +
-                                                                         (static_cast<int64_t>(n) * p.stride + pix) * 3);
-                const uint32_t h0 = __ldca(src), h1 = __ldca(src + 1), h2 = __ldca(src + 2);
+                uint32_t h0, h1, h2;
+                {
+                    const uint16_t *src = reinterpret_cast<const uint16_t *>(static_cast<const uint8_t *>(p.val) +
+                                                                             (static_cast<int64_t>(n) * p.stride + pix) * 3);
+                    h0 = __ldca(src); h1 = __ldca(src + 1); h2 = __ldca(src + 2);
+                }
                 const uint32_t w0 = h0 | (h1 << 16);          // bytes 0..3, h2 = bytes 4..5
                 const int j0 = 2 - c;
                 const uint32_t c0 = (w0 >> (8 * j0)) & 0xffu;                                   // byte j0
@@ -142,10 +180,21 @@ __device__ __forceinline__ Pack<VEC> load_pixels(const HdrParams &p, int n, int 
         Pack<VEC> r;
         if constexpr (VEC == 2) {
             // two pixels: one 32-bit load, or the 12 bytes of two BGR pixels as three
+            if constexpr (SRC == kSrcU16HwcTma) {
+                // staged frame: the channel's two halfwords straight from the thread's 12-byte window (a lane stride of 3
+                // banks: conflict-free), no word loads + selects
+                const uint16_t *src = reinterpret_cast<const uint16_t *>(stage + n * stage_frame_bytes) + threadIdx.x * 6 + (2 - c);
+                r.v[0] = normalise_code16<SHORT>(src[0], p);
+                r.v[1] = normalise_code16<SHORT>(src[3], p);
+                return r;
+            }
             if constexpr (SRC == kSrcU16Hwc) {
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(static_cast<const uint16_t *>(p.val) +
-                                                                         (static_cast<int64_t>(n) * p.stride + pix) * 3);
-                const uint32_t w0 = __ldca(src), w1 = __ldca(src + 1), w2 = __ldca(src + 2);   // halfwords 0..5
+                uint32_t w0, w1, w2;                                                            // halfwords 0..5
+                {
+                    const uint32_t *src = reinterpret_cast<const uint32_t *>(static_cast<const uint16_t *>(p.val) +
+                                                                             (static_cast<int64_t>(n) * p.stride + pix) * 3);
+                    w0 = __ldca(src); w1 = __ldca(src + 1); w2 = __ldca(src + 2);
+                }
                 const int j0 = 2 - c;
                 const uint32_t c0 = j0 == 0 ? (w0 & 0xffffu) : (j0 == 1 ? (w0 >> 16) : (w1 & 0xffffu));   // halfword j0
                 const uint32_t c1 = j0 == 0 ? (w1 >> 16) : (j0 == 1 ? (w2 & 0xffffu) : (w2 >> 16));       // halfword 3 + j0
@@ -436,6 +485,26 @@ __global__ void __launch_bounds__(kBlock, fixed_min_blocks(SRC, VEC, NF, SINGLE)
     if constexpr (src_is_u8(SRC)) {
         for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
     }
+    // Camera layout, staged (TMA): per trip the block's 256 x VEC pixels are 3 * VEC * 256 contiguous codes of every frame.
+    // One thread requests them a trip ahead with one bulk copy per frame into a two-stage shared-memory ring (an mbarrier
+    // per stage counts the bytes in); the threads then read their 6 / 12 bytes per frame from shared memory, all three
+    // channels from the same words, instead of waiting on 12-byte-strided global loads.
+    constexpr bool TMA = src_is_tma(SRC);
+    static_assert(!TMA || VEC == 2, "the staged camera kernels are the 2-pixel register kernels");
+    constexpr uint32_t kStageFrameBytes = kBlock * VEC * 3 * (src_is_u8(SRC) ? 1 : 2);
+    constexpr uint32_t kStageBytes = kStageFrameBytes * NF;
+    unsigned char *s_stage = nullptr;
+    uint64_t *s_bar = nullptr;
+    if constexpr (TMA) {
+        const uintptr_t after = reinterpret_cast<uintptr_t>(s_x + (src_is_u8(SRC) ? 256 : 0));
+        s_stage = reinterpret_cast<unsigned char *>((after + 127) & ~static_cast<uintptr_t>(127));
+        s_bar = reinterpret_cast<uint64_t *>(s_stage + 2 * kStageBytes);
+        if (threadIdx.x == 0) {
+            mbar_init(s_bar, 1);
+            mbar_init(s_bar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     __syncthreads();
     // Camera layout (FOLD): the three channels of a pixel share their bytes, so a thread merges them in turn — the first
     // channel's loads bring the codes into L1, the other two hit there (ld.global.ca).  One block per channel (gridDim.y)
@@ -456,9 +525,36 @@ __global__ void __launch_bounds__(kBlock, fixed_min_blocks(SRC, VEC, NF, SINGLE)
     const uint32_t tab_bias = curve_row_bias(s_tab);
     const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
 
-    for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
+    // TMA: bulk copies of one trip of this block (pixels [first, first + 256 VEC) of every frame) into stage `st`
+    auto request_trip = [&](uint32_t block_first_item, uint32_t st) {
+        constexpr uint32_t kPixBytes = 3 * (src_is_u8(SRC) ? 1 : 2);
+        const uint32_t first_pix = block_first_item * VEC;
+        const uint32_t n_pix = min(static_cast<uint32_t>(kBlock * VEC), static_cast<uint32_t>(p.plane) - first_pix);
+        const uint32_t bytes = n_pix * kPixBytes;                    // a multiple of 16: the host checked H*W % 16 == 0
+        mbar_expect_tx(s_bar + st, bytes * NF);
+        const char *src = static_cast<const char *>(p.val) + static_cast<int64_t>(first_pix) * kPixBytes;
+        const int64_t frame_bytes = p.stride * kPixBytes;
+#pragma unroll
+        for (int n = 0; n < NF; ++n) bulk_copy_g2s(s_stage + st * kStageBytes + n * kStageFrameBytes, src + n * frame_bytes, bytes, s_bar + st);
+    };
+    uint32_t trip = 0;
+    if constexpr (TMA) {
+        if (threadIdx.x == 0) {
+            const uint32_t b0 = blockIdx.x * kBlock;
+            if (b0 < n_items) request_trip(b0, 0);
+            if (b0 + item_stride < n_items) request_trip(b0 + item_stride, 1);
+        }
+    }
+    // (TMA: the loop bound is the block's, so that every thread reaches the barrier that frees a stage)
+    for (uint32_t item = first_item; TMA ? (item - threadIdx.x < n_items) : (item < n_items); item += item_stride, cur.advance(), ++trip) {
         const uint32_t pix = item * VEC;
-        if constexpr (FOLD) {
+        const unsigned char *stage = nullptr;
+        if constexpr (TMA) {
+            mbar_wait(s_bar + (trip & 1u), (trip >> 1) & 1u);
+            stage = s_stage + (trip & 1u) * kStageBytes;
+        }
+        if (!TMA || item < n_items) {
+        if constexpr (FOLD && !TMA) {
             // the codes of the next trip, requested while this trip's three channels are merged: their first use then finds
             // them on the chip instead of waiting on DRAM at two or three blocks per SM
             if (p.prefetch != 0 && item + item_stride < n_items) {
@@ -500,7 +596,7 @@ __global__ void __launch_bounds__(kBlock, fixed_min_blocks(SRC, VEC, NF, SINGLE)
 #pragma unroll
                 for (int n = 0; n < NF; ++n) {
                     const int64_t o = off + static_cast<int64_t>(n) * frame_stride;
-                    xv[n] = load_pixels<SRC, VEC, true>(p, n, c, pix, o, s_x);
+                    xv[n] = load_pixels<SRC, VEC, true>(p, n, c, pix, o, s_x, stage, kStageFrameBytes);
                     if constexpr (HAS_STD) sv[n] = load_std<VEC, STD>(p, o, xv[n]);
                 }
 #pragma unroll
@@ -612,6 +708,12 @@ __global__ void __launch_bounds__(kBlock, fixed_min_blocks(SRC, VEC, NF, SINGLE)
         });
         }
         }   // channel
+        }   // item in range
+        if constexpr (TMA) {
+            __syncthreads();                                         // every thread has read this trip's stage
+            const uint32_t ahead = item - threadIdx.x + 2u * item_stride;
+            if (threadIdx.x == 0 && ahead < n_items) request_trip(ahead, trip & 1u);
+        }
     }
 }
 
@@ -1010,5 +1112,6 @@ int launch_merge_codes_planar(const MergeLaunch &m, bool u8);
 int launch_merge_codes_hwc(const MergeLaunch &m, bool u8);
 int launch_merge_codes_planar_wide(const MergeLaunch &m, bool u8);
 int launch_merge_codes_hwc_wide(const MergeLaunch &m, bool u8);
+int launch_merge_codes_hwc_wide_tma(const MergeLaunch &m, bool u8);
 
 }  // namespace clair

@@ -742,12 +742,18 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         if (vec_cap < vec) vec = vec_cap;
         if (parked) smem += sizeof(float) * 2 * vec * kBlock * static_cast<size_t>(n_frames);
     }
+    // camera layout, 9..16 frames: the block's contiguous codes come in by bulk copies (two-stage ring in shared memory)
+    // when every copy is 16-byte granular: H*W, the plane stride and the base address
+    const bool tma = wide && dark.hwc && g_tuning.hdr_tma >= 0 && plane % 16 == 0 && plane_stride % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(val_dev) % 16 == 0;
+    if (tma) smem += 128 + 2 * static_cast<size_t>(n_frames) * kBlock * 2 * 3 * (src == kSrcU8 ? 1 : 2) + 16;
     MergeLaunch m{};
     m.p = p; m.smem = smem; m.want_blocks = (plane / vec + kBlock - 1) / kBlock;
     m.fixed = fixed; m.parked = parked; m.single = single;
     m.std_mode = std_mode; m.n_frames = n_frames; m.n_channels = n_channels; m.stream = s;
     int rc;
-    if (wide) rc = dark.hwc ? launch_merge_codes_hwc_wide(m, src == kSrcU8) : launch_merge_codes_planar_wide(m, src == kSrcU8);
+    if (wide && tma) rc = launch_merge_codes_hwc_wide_tma(m, src == kSrcU8);
+    else if (wide) rc = dark.hwc ? launch_merge_codes_hwc_wide(m, src == kSrcU8) : launch_merge_codes_planar_wide(m, src == kSrcU8);
     else if (src != kSrcF32) rc = dark.hwc ? launch_merge_codes_hwc(m, src == kSrcU8) : launch_merge_codes_planar(m, src == kSrcU8);
     else if (vec == 4) rc = launch_merge_by_std<4, kSrcF32>(m);
     else if (vec == 2) rc = launch_merge_by_std<2, kSrcF32>(m);

@@ -766,6 +766,48 @@ def test_hdr_merge_interleaved_bgr_codes_equal_planar(ct, bits, n):
         kernels.hdr_merge_update(kernels.HdrMergeState(), val.to(DEV), None, t, theta, True, True, code_layout="hwc_bgr")
 
 
+@pytest.mark.parametrize("bits,n,shape", [(16, 9, (36, 48)), (8, 12, (36, 48)), (16, 16, (40, 64)), (16, 9, (1088, 1936)), (8, 10, (544, 1936))])
+def test_hdr_merge_camera_codes_through_the_bulk_copy_stage(ct, bits, n, shape):
+    """9..16 frames of (N, H, W, 3) camera codes with H*W % 16 == 0 take the register kernel whose codes arrive in shared
+    memory by cp.async.bulk (two-stage ring, one trip ahead): bit-identical to the planar codes and to the per-thread-load
+    form of the same kernel — single trips with a partial tail, and many trips per block (one resident wave)."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.datasets import StdSpec
+    h, w = shape
+    assert (h * w) % 16 == 0
+    val, _, t = ct.synthetic.make_stack(n, 3, h, w, bits=bits, seed=3 * bits + n, device=DEV)
+    maxval = float(2 ** bits - 1)
+    planar = torch.round(val * maxval).to(torch.int32).to(torch.uint8 if bits == 8 else torch.uint16)
+    camera = torch.stack([planar[:, 2], planar[:, 1], planar[:, 0]], dim=-1).contiguous()
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    lib = ct._native.load()
+    spec = StdSpec("multiplier", 0.05)
+    want = kernels.hdr_merge_update(kernels.HdrMergeState(), planar, spec, t, theta, True, True)
+    try:
+        for waves in (0, 1):
+            ct._native.check(lib.clair_set_tuning(b"hdr_waves", waves), "tune")
+            got = kernels.hdr_merge_update(kernels.HdrMergeState(), camera, spec, t, theta, True, True, code_layout="hwc_bgr")
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+        ct._native.check(lib.clair_set_tuning(b"hdr_tma", -1), "tune")
+        plain = kernels.hdr_merge_update(kernels.HdrMergeState(), camera, spec, t, theta, True, True, code_layout="hwc_bgr")
+        assert torch.equal(plain[0], want[0]) and torch.equal(plain[1], want[1])
+    finally:
+        lib.clair_set_tuning(b"hdr_waves", 0)
+        lib.clair_set_tuning(b"hdr_tma", 0)
+    # std as a tensor, two batches, and the staged host pipeline (bands of larger planes)
+    std = (val * 0.03 + 0.001)
+    st_a, st_b = kernels.HdrMergeState(), kernels.HdrMergeState()
+    half = n // 2
+    if n - half >= 9:
+        for sl, last in ((slice(0, half), False), (slice(half, n), True)):
+            a = kernels.hdr_merge_update(st_a, planar[sl].contiguous(), std[sl].contiguous(), t[sl], theta, True, last)
+            b = kernels.hdr_merge_update(st_b, camera[sl].contiguous(), std[sl].contiguous(), t[sl], theta, True, last, code_layout="hwc_bgr")
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    host = kernels.hdr_merge_update(kernels.HdrMergeState(), camera.cpu().pin_memory(), spec, t, theta, True, True, device=torch.device(DEV),
+                                    code_layout="hwc_bgr", staged=True, bands=3)
+    assert torch.equal(host[0], want[0]) and torch.equal(host[1], want[1])
+
+
 @pytest.mark.parametrize("n", [9, 10, 11, 13, 14, 15, 16])
 def test_hdr_merge_integer_ingest_9_to_16_frames(ct, n):
     """9..16 frames of uint8 / uint16 codes (planar and BGR camera layout) give the bits of the fp32 stack, which takes the
