@@ -59,29 +59,6 @@ __host__ __device__ constexpr bool src_is_u8(int src) { return src == kSrcU8 || 
 __host__ __device__ constexpr bool src_is_tma(int src) { return src == kSrcU8HwcTma || src == kSrcU16HwcTma; }
 __host__ __device__ constexpr bool src_is_hwc(int src) { return src == kSrcU8Hwc || src == kSrcU16Hwc || src_is_tma(src); }
 
-// ---- bulk-copy staging (sm_90+ TMA without a tensor map: 1-D, 16-byte granular) ------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // One frame's VEC pixel values.  SRC = kSrcF32: the fp32 stack the reference hands over.  kSrcU8 / kSrcU16: the raw
 // integer codes, normalised in-register exactly like the reference's CPU transforms do it (CastTo(float32) then
 // Normalize(max_val, min_val=0): an IEEE fp32 division, clair_torch/common/general_functions.py:378) — 8-bit codes
