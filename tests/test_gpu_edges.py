@@ -336,3 +336,47 @@ def test_host_out_results_are_ready_when_compute_hdr_image_returns(ct):
         rad, sig = ct.compute_hdr_image(loader, DEV, model, max, radiance_dtype=torch.float32, host_out=(rad_h, sig_h))
         got_rad, got_sig = rad.numpy().copy(), sig.numpy().copy()          # read immediately, no synchronize
         assert np.array_equal(got_rad, want_rad.cpu().numpy()) and np.array_equal(got_sig, want_sig.cpu().numpy())
+
+
+def test_single_pair_step_falls_back_when_it_cannot_fuse(ct):
+    """An odd plane (or std images with uncertainty weighting) keeps the two-pass kernels; both routes agree with the oracle."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.training import linearity_loss_and_table_grad
+    val, std, _ = ct.synthetic.make_stack(2, 3, 7, 9, bits=16, seed=4)           # 63 pixels: odd
+    t = np.array([0.01, 0.02])
+    theta = ct.synthetic.reference_curve(3)
+    i, j, r = ct.common.get_valid_exposure_pairs(torch.from_numpy(t), 0.25)
+    dv, ds = val.to(DEV), std.to(DEV)
+    assert not kernels.can_fuse_pair(dv, ds, 1, False)
+    for unc in (False, True):
+        lin, spatial, grad = linearity_loss_and_table_grad(dv, ds, i, j, r, theta.to(DEV), 1 / 255, 254 / 255, True, unc)
+        o = orc.train_loss_and_grad(val.numpy(), std.numpy(), t, theta.numpy(), 0.25, relative=True, unc_weighting=unc)
+        assert max_rel(lin.cpu().numpy(), o["linloss"]) < 1e-5 and max_abs_over_max(grad.cpu().numpy(), o["grad_lin"]) < 1e-5
+    with pytest.raises(ValueError):
+        kernels.pair_fused(dv, i, j, r, theta.to(DEV), 1 / 255, 254 / 255, True)                  # odd plane
+    val6, _, t6 = ct.synthetic.make_stack(3, 3, 8, 8, bits=8, seed=1)
+    i6, j6, r6 = ct.common.get_valid_exposure_pairs(torch.from_numpy(t6), 0.1)
+    with pytest.raises(ValueError):
+        kernels.pair_fused(val6.to(DEV), i6, j6, r6, theta.to(DEV), 1 / 255, 254 / 255, True)    # more than one pair
+
+
+def test_integer_code_batches_reject_what_they_cannot_take(ct):
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.datasets import ExposureStackDataset, StdSpec, custom_collate
+    codes = torch.randint(0, 255, (3, 3, 5, 7), dtype=torch.uint8)                # 315 elements: not a multiple of 4
+    with pytest.raises(ValueError):
+        kernels.expand_codes(codes.to(DEV))
+    with pytest.raises(TypeError):
+        kernels.expand_codes(codes.to(torch.float32).to(DEV))
+    with pytest.raises(TypeError):
+        kernels.expand_codes(torch.zeros(8, dtype=torch.uint8, device=DEV), std=0.05)
+    # a LOOKUP model cannot carry a std — synthesised or not — through measure_linearity (the reference's autograd raises)
+    good = torch.randint(0, 255, (3, 3, 8, 8), dtype=torch.uint8)
+    ds = ExposureStackDataset(list(good), StdSpec("multiplier", 0.05), [0.01, 0.02, 0.04])
+    model = ct.ICRFModelDirect(256, 3, ct.InterpMode.LOOKUP).to(DEV)
+    with pytest.raises(RuntimeError):
+        ct.measure_linearity(DataLoader(ds, batch_size=3, collate_fn=custom_collate), DEV, True, True, model)
+    # a StdSpec needs integer codes to be evaluated from
+    ds_f = ExposureStackDataset(list(good.to(torch.float32) / 255), StdSpec("multiplier", 0.05), [0.01, 0.02, 0.04])
+    with pytest.raises(ValueError):
+        ct.measure_linearity(DataLoader(ds_f, batch_size=3, collate_fn=custom_collate), DEV, True, True, None)
