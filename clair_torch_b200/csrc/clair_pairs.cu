@@ -14,7 +14,8 @@ namespace clair {
 
 constexpr float kPairNegScaleLog2e = -14.426950408889634f;   // -10 * log2(e); training/losses.py:212 default scale 10
 constexpr int kMaxPairsPerLaunch = 256;   // the pair table travels as a kernel argument
-constexpr int kStatsTile = 128;           // pixels per shared-memory tile in the statistics kernel (power of two)
+constexpr int kStatsTile = 128;           // pixels per shared-memory tile in the statistics kernels (power of two)
+constexpr int kMeansTile = 256;           // ... of the packed kernel's training variant (sum w, sum w l only: registers to spare)
 constexpr int kMaxSlots = 4;              // pairs a warp carries in registers in the statistics kernel
 constexpr int kGradCopies = 64;           // replicated gradient tables the REDs of the scatter kernels are spread over
 constexpr int kMaxGradCopies = 1024;      // the workspace holds this many
@@ -431,7 +432,10 @@ __device__ __forceinline__ float mul_sat(float a, float b) {        // clamp(a *
 // shared-memory slot never change, and the loads of the NEXT tile are issued before the pair phase of the current one,
 // so their HBM latency is hidden behind it.
 // MODES: the model is LOOKUP / CATMULL (only the staging phase differs: the pair phase works on the staged per-frame terms).
-template <int SLOTS, bool ERR, bool RELATIVE, bool FULL, int TRIPS, bool MODES = false>
+// TILE: pixels per tile — 128 for the FULL statistics (five packed accumulators per slot at 64 registers), 256 for the
+// training variant (two accumulators: the larger tile halves the barriers and the per-tile bookkeeping; c2 means pass
+// 0.167 -> 0.148 ms, c3-sized 1.02 -> 0.91 ms; the FULL kernel at 256 spills and loses: 1.69 -> 1.82 ms)
+template <int SLOTS, bool ERR, bool RELATIVE, bool FULL, int TRIPS, bool MODES = false, int TILE = kStatsTile>
 // (two-slot kernels are held to 64 registers = two 16-warp blocks per SM: c3 2.07 -> 1.93 ms with 48 B of spills)
 __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_stats2_kernel(const PairParams p) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
     float2 *s_tab = reinterpret_cast<float2 *>(s_raw);
     // tile layout [frame][array][pixel]:  0: f   1: gw   2: sig (ERR)   3: sig / max(f, 1e-6) (ERR && RELATIVE)
     constexpr int kArr = 2 + (ERR ? (RELATIVE ? 2 : 1) : 0);
-    constexpr int kFrameFloats = kArr * kStatsTile;
+    constexpr int kFrameFloats = kArr * TILE;
     float *s_tile = reinterpret_cast<float *>(s_tab + (has_model ? C * L : 0));
     if (has_model) stage_curve_slopes(s_tab, p.theta, C, L);
 
@@ -487,7 +491,7 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
     };
     int since_flush = 0;
 
-    const uint32_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
+    const uint32_t n_tiles = (plane + TILE - 1) / TILE;
     // Per-thread staging items: everything that does not change from tile to tile is set up once — the source pointer only
     // advances by the grid's tile stride, the pixel position by the same (it is the bounds check), and because the host
     // sizes the grid so that its stride in pixels is a multiple of C, the table rows of an item's four pixels never change
@@ -498,20 +502,21 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
     uint32_t pixn[TRIPS];                // first pixel of the item in the tile that is loaded next (>= plane: nothing left)
     uint32_t pixs[TRIPS];                // ... in the tile that is staged next
     uint32_t bias[TRIPS][4];             // biased table-row addresses of the item's four pixels
-    const uint32_t tile_stride = gridDim.x * kStatsTile;
+    const uint32_t tile_stride = gridDim.x * TILE;
     const bool rows_fixed = (tile_stride % uC) == 0u;
     uint32_t urow[TRIPS];
 #pragma unroll
     for (int t = 0; t < TRIPS; ++t) {
         const int item = threadIdx.x + t * blockDim.x;
-        const int n = item >> 5;
+        constexpr int kItemsPerFrame = TILE / 4;
+        const int n = item / kItemsPerFrame;
         const bool on = n < N;
-        const uint32_t qoff = (static_cast<uint32_t>(item) & 31u) * 4u;
-        pixn[t] = on ? blockIdx.x * kStatsTile + qoff : plane;
+        const uint32_t qoff = (static_cast<uint32_t>(item) & (kItemsPerFrame - 1)) * 4u;
+        pixn[t] = on ? blockIdx.x * TILE + qoff : plane;
         pixs[t] = pixn[t];
-        src[t] = val_c + static_cast<int64_t>(on ? n : 0) * frame_stride + blockIdx.x * kStatsTile + qoff;
+        src[t] = val_c + static_cast<int64_t>(on ? n : 0) * frame_stride + blockIdx.x * TILE + qoff;
         dst[t] = static_cast<uint32_t>((on ? n : 0) * kFrameFloats) + qoff;
-        urow[t] = (blockIdx.x * kStatsTile + qoff + static_cast<uint32_t>(p.rows.base(c))) % uC;   // row of the item's first pixel
+        urow[t] = (blockIdx.x * TILE + qoff + static_cast<uint32_t>(p.rows.base(c))) % uC;   // row of the item's first pixel
         uint32_t u = urow[t];
 #pragma unroll
         for (int k = 0; k < 4; ++k) { bias[t][k] = tab_bias + u * row_bytes; u = (u + 1 == uC) ? 0u : u + 1; }
@@ -535,7 +540,7 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
     auto stage = [&](float *buf) {
 #pragma unroll
         for (int t = 0; t < TRIPS; ++t) {
-            if (threadIdx.x + t * blockDim.x < static_cast<unsigned>(N) * 32u) {
+            if (threadIdx.x + t * blockDim.x < static_cast<unsigned>(N) * (TILE / 4)) {
                 const bool live = pixs[t] < plane;
                 pixs[t] = live ? pixs[t] + tile_stride : plane;
                 if (!rows_fixed) {              // (grids smaller than C blocks per channel)
@@ -561,10 +566,10 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
                                                                   p.valid_lo, p.valid_hi, live, mrb);
                 float *out = buf + dst[t];
                 *reinterpret_cast<ulonglong2 *>(out) = make_ulonglong2(a.f, b.f);
-                *reinterpret_cast<ulonglong2 *>(out + kStatsTile) = make_ulonglong2(a.gw, b.gw);
+                *reinterpret_cast<ulonglong2 *>(out + TILE) = make_ulonglong2(a.gw, b.gw);
                 if constexpr (ERR) {
-                    *reinterpret_cast<ulonglong2 *>(out + 2 * kStatsTile) = make_ulonglong2(a.sig, b.sig);
-                    if constexpr (RELATIVE) *reinterpret_cast<ulonglong2 *>(out + 3 * kStatsTile) = make_ulonglong2(a.rel, b.rel);
+                    *reinterpret_cast<ulonglong2 *>(out + 2 * TILE) = make_ulonglong2(a.sig, b.sig);
+                    if constexpr (RELATIVE) *reinterpret_cast<ulonglong2 *>(out + 3 * TILE) = make_ulonglong2(a.rel, b.rel);
                 }
             }
         }
@@ -583,10 +588,10 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
                 float k = pivot[s];
                 bool hv = have[s];
 #pragma unroll
-                for (int it = 0; it < kStatsTile / 64; ++it) {
+                for (int it = 0; it < TILE / 64; ++it) {
                     const int q = 64 * it;
                     const f32x2 av = lds2(fi + q), bv = lds2(fj + q);
-                    const f32x2 wg = add2(lds2(fi + kStatsTile + q), lds2(fj + kStatsTile + q));   // < 0 <=> masked
+                    const f32x2 wg = add2(lds2(fi + TILE + q), lds2(fj + TILE + q));   // < 0 <=> masked
                     const f32x2 d = fma2(bv, nrl2, fma2(bv, nrh2, av));                          // a - b r
                     float g0, g1;
                     unpack2(wg, g0, g1);
@@ -604,10 +609,10 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
                     ell2 &= 0x7fffffff7fffffffull;                                                // |.|: es can be negative once the curve dips below 0
                     f32x2 err = 0ull;
                     if constexpr (ERR) {
-                        const f32x2 sa = lds2(fi + 2 * kStatsTile + q);
+                        const f32x2 sa = lds2(fi + 2 * TILE + q);
                         if constexpr (RELATIVE) {
                             const f32x2 e1 = mul2(sa, inv);
-                            const f32x2 e2 = mul2(mul2(av, lds2(fj + 3 * kStatsTile + q)), inv);
+                            const f32x2 e2 = mul2(mul2(av, lds2(fj + 3 * TILE + q)), inv);
                             const f32x2 T = fma2(e1, e1, fma2(e2, e2, splat2(1e-6f)));          // losses.py:57-60; T >= 1e-6
                             float T0, T1;
                             unpack2(T, T0, T1);
@@ -620,7 +625,7 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
                                 wt = fma2(mul2(rs, pq), vm, wt);
                             }
                         } else {
-                            const f32x2 rsb = mul2(lds2(fj + 2 * kStatsTile + q), splat2(r_hi));
+                            const f32x2 rsb = mul2(lds2(fj + 2 * TILE + q), splat2(r_hi));
                             float s0, s1;
                             unpack2(fma2(sa, sa, mul2(rsb, rsb)), s0, s1);                        // losses.py:62
                             err = pack2(sqrt_approx(s0), sqrt_approx(s1));
@@ -1549,19 +1554,19 @@ int set_smem(K kernel, size_t bytes) {
 // tile: every warp stages ceil(N*items/ (32 W)) items of VA pixels (cost_item each) and then walks S pair slots of
 // kStatsTile/32 pixels each (cost_pair per pixel).  Block time per tile ~ that sum; SM throughput ~ 1 / (W * sum).
 // The packed kernel (va == 4) keeps its staging items in registers, at most two per thread: W >= ceil(N / 2).
-void pick_stats_shape(int count, int n_frames, int va, bool err, bool full, int &warps, int &slots) {
+void pick_stats_shape(int count, int n_frames, int va, bool err, bool full, int tile, int &warps, int &slots) {
     const bool packed = va == 4;
     const int cost_item = packed ? (err ? 150 : 100) : va * (err ? 50 : 40) + 12;
     const int cost_pair = packed ? (full ? (err ? 130 : 75) : (err ? 100 : 55))
-                                 : (kStatsTile / 32) * ((full ? 30 : 21) + (err ? 16 : 0));
-    const int items = n_frames * (kStatsTile / va);
+                                 : (tile / 32) * ((full ? 30 : 21) + (err ? 16 : 0));
+    const int items = n_frames * (tile / va);
     long best = -1;
     warps = 8; slots = kMaxSlots;
     for (int s = 1; s <= kMaxSlots; ++s) {
         if (s == 3) continue;                         // slot counts instantiated: 1, 2, 4
         for (int w = packed ? 1 : 2; w <= 16; ++w) {    // a single exposure pair (N = 2, one pair) runs as one-warp blocks
             if (w * s < count) continue;
-            if (packed && 2 * w < n_frames) continue;
+            if (packed && 2 * w < n_frames * (tile / 128)) continue;
             const int trips = (items + 32 * w - 1) / (32 * w);
             const long cost = static_cast<long>(w) * (static_cast<long>(trips) * cost_item + static_cast<long>(s) * cost_pair);
             if (best < 0 || cost < best) { best = cost; warps = w; slots = s; }
@@ -1617,14 +1622,17 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
     const bool err = std_dev != nullptr && (full || unc_weighting);
     const int arrays = 2 + (err ? (relative ? 2 : 1) : 0);
     const size_t table_bytes = theta_dev ? sizeof(float2) * n_channels * lut_size : 0;
-    const size_t tile_bytes = sizeof(float) * arrays * n_frames * kStatsTile;
-    size_t smem = table_bytes + tile_bytes;
     const int per_launch = 16 * kMaxSlots;   // 64 pairs: 16 warps x 4 register slots
     // 128-bit staging loads need H*W % 4 == 0 and 16-byte aligned stacks (every frame / channel slab then is, too)
     const bool vec_ok = plane % 4 == 0 && plane < (1ll << 31) && reinterpret_cast<uintptr_t>(val_dev) % 16 == 0 &&
                         (!err || reinterpret_cast<uintptr_t>(std_dev) % 16 == 0) &&
                         (theta_dev == nullptr || (n_channels * lut_size) % 2 == 0);   // tile starts 16-byte aligned after the table
-    const int va = (vec_ok && n_frames <= 32) ? 4 : 1;     // the packed kernel holds <= 2 staging items per thread, 16 warps
+    // the packed training variant works on 256-pixel tiles when its staging items still fit two per thread
+    // (a single exposure pair is all staging and no pair work: c5 means pass 0.89 ms on 128-pixel tiles, 1.04 ms on 256)
+    const int tile = (!full && vec_ok && !modes && n_frames * 2 <= 32 && n_pairs >= 4) ? kMeansTile : kStatsTile;
+    const size_t tile_bytes = sizeof(float) * arrays * n_frames * tile;
+    size_t smem = table_bytes + tile_bytes;
+    const int va = (vec_ok && n_frames * (tile / 128) <= 32) ? 4 : 1;     // the packed kernel holds <= 2 staging items per thread, 16 warps
     // packed kernel: a second tile buffer lets staging overlap the pair phase (one barrier per tile) as long as two
     // blocks still fit an SM
     int buffers = (va == 4 && table_bytes + 2 * tile_bytes <= 110 * 1024) ? 2 : 1;
@@ -1642,9 +1650,9 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
         p.stats_buffers = buffers;
         if (int rc = fill_pairs(fn, p.pairs, pair_i_host, pair_j_host, pair_ratio_host, first, count, n_frames)) return rc;
         int warps, slots;
-        pick_stats_shape(count, n_frames, va, err, full != 0, warps, slots);
+        pick_stats_shape(count, n_frames, va, err, full != 0, va == 4 ? tile : kStatsTile, warps, slots);
         if (g_tuning.stats_warps > 0 && g_tuning.stats_slots > 0 && g_tuning.stats_warps * g_tuning.stats_slots >= count &&
-            g_tuning.stats_warps <= 16 && 2 * g_tuning.stats_warps >= n_frames &&
+            g_tuning.stats_warps <= 16 && 2 * g_tuning.stats_warps >= n_frames * (tile / 128) &&
             (g_tuning.stats_slots == 1 || g_tuning.stats_slots == 2 || g_tuning.stats_slots == 4)) {
             warps = g_tuning.stats_warps;
             slots = g_tuning.stats_slots;
@@ -1653,10 +1661,10 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
             // LOOKUP / CATMULL models: one shape (4 register slots, two staging items per thread) keeps the number of
             // instantiations down; the pair phase is the LINEAR kernels' own
             slots = kMaxSlots;
-            warps = std::max((count + kMaxSlots - 1) / kMaxSlots, (n_frames + 1) / 2);
+            warps = std::max((count + kMaxSlots - 1) / kMaxSlots, (n_frames * (tile / 128) + 1) / 2);
         }
-        const int trips = (n_frames + warps - 1) / warps;      // staging items per thread of the packed kernel (1 or 2)
-        const int64_t n_tiles = (plane + kStatsTile - 1) / kStatsTile;
+        const int trips = (n_frames * (tile / 128) + warps - 1) / warps;      // staging items per thread of the packed kernel (1 or 2)
+        const int64_t n_tiles = (plane + (va == 4 ? tile : kStatsTile) - 1) / (va == 4 ? tile : kStatsTile);
         auto launch = [&](auto kernel) -> int {
             if (int rc = set_smem(kernel, smem)) return rc;
             int per_sm = 1;
@@ -1669,9 +1677,12 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
             return 0;
         };
         int rc = 0;
+#define STATS_TRIPS(S, E, R, F, M, T) \
+    (trips == 1 ? launch(pair_stats2_kernel<S, E, R, F, 1, M, T>) : launch(pair_stats2_kernel<S, E, R, F, 2, M, T>))
 #define STATS_FLAGS(S, E, R, F)                                                                        \
-    (va == 4 ? (modes ? launch(pair_stats2_kernel<kMaxSlots, E, R, F, 2, true>)                          \
-                      : (trips == 1 ? launch(pair_stats2_kernel<S, E, R, F, 1>) : launch(pair_stats2_kernel<S, E, R, F, 2>))) \
+    (va == 4 ? (modes ? launch(pair_stats2_kernel<kMaxSlots, E, R, F, 2, true, kStatsTile>)               \
+                      : ((!F && tile == kMeansTile) ? STATS_TRIPS(S, E, R, F, false, kMeansTile)           \
+                                                    : STATS_TRIPS(S, E, R, F, false, kStatsTile)))         \
              : launch(pair_stats_kernel<S, E, R, F, 1>))
 #define STATS_CASE(S)                                                                                   \
     case S:                                                                                             \
@@ -1690,6 +1701,7 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
             STATS_CASE(4)
         }
 #undef STATS_FLAGS
+#undef STATS_TRIPS
 #undef STATS_CASE
         if (rc) return rc;
         if (int rc2 = launched("pair_stats_kernel")) return rc2;
