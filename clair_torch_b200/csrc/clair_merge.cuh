@@ -740,7 +740,12 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrPara
                 u = (u + 1 == cur.C) ? 0u : u + 1;
             }
         }
-        float wsum[VEC], wv[VEC], R[NF][VEC], Q[NF][VEC];
+        // The two pixels of the thread go through the merge arithmetic as one packed fp32x2 pair (hdr_terms2, as in
+        // hdr_merge_fixed_kernel): the kernel is instruction-bound (blur + mix + merge), not HBM-bound.  A single frame keeps
+        // the scalar form (its gradient is the exact one-frame expression).
+        constexpr bool PACKED = NF > 1;
+        float wsum[VEC], wv[VEC], R[PACKED ? 1 : NF][VEC], Q[PACKED ? 1 : NF][VEC];
+        f32x2 wsum2 = 0ull, wv2 = 0ull, R2[PACKED ? NF : 1], Q2[PACKED ? NF : 1];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) { wsum[k] = 0.0f; wv[k] = 0.0f; }
         // frames in chunks of kDarkChunk: all loads of a chunk are issued before its first shuffle
@@ -765,29 +770,90 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrPara
                     float x[VEC], blur[VEC];
                     row_group_blur<VEC>(rg[j], col, p.dg, chained_left, chained_right, x, blur);
                     const float it = p.scale.inv_t[n0 + j];
+                    float xm[VEC], sm[VEC];
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) {
-                        float xm, sm;
-                        dark_mix_value<true>(x[k], blur[k], sv[j].v[k], dk[j].v[k], ds[j].v[k], p.dg, xm, sm);
-                        const HdrTerms t = hdr_terms(xm, sm, it, has_model, gaussian, bias[k], lm1, true);
-                        wsum[k] += t.w;
-                        wv[k] = fmaf(t.w, t.v, wv[k]);
-                        R[n0 + j][k] = (NF == 1) ? one_frame_gradient(t) : t.R;
-                        Q[n0 + j][k] = t.Q;
+                    for (int k = 0; k < VEC; ++k) dark_mix_value<true>(x[k], blur[k], sv[j].v[k], dk[j].v[k], ds[j].v[k], p.dg, xm[k], sm[k]);
+                    if constexpr (PACKED) {
+                        const HdrTerms2 t = hdr_terms2(xm[0], xm[1], sm[0], sm[1], it, has_model, gaussian, bias[0], bias[1], lm1, true);
+                        wsum2 = add2(wsum2, t.w);
+                        wv2 = fma2(t.w, t.v, wv2);
+                        R2[n0 + j] = t.R;
+                        Q2[n0 + j] = t.Q;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) {
+                            const HdrTerms t = hdr_terms(xm[k], sm[k], it, has_model, gaussian, bias[k], lm1, true);
+                            wsum[k] += t.w;
+                            wv[k] = fmaf(t.w, t.v, wv[k]);
+                            R[n0 + j][k] = one_frame_gradient(t);
+                            Q[n0 + j][k] = t.Q;
+                        }
                     }
                 }
             }
         }
         if (!active) continue;
-        hdr_finish<VEC, true, SINGLE, NF == 1>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
-            float acc = 0.0f;
+        if constexpr (PACKED) {
+            if constexpr (SINGLE) {
+                // the single-batch epilogue of hdr_merge_fixed_kernel on the pixel pair (same operations, same bits)
+                Pack<VEC> rad, sg;
+                const f32x2 wbe = add2(wsum2, splat2(1e-6f));                     // statistics.py:76 (fp32 add)
+                float b0, b1, ws0, ws1;
+                unpack2(wbe, b0, b1);
+                unpack2(wsum2, ws0, ws1);
+                f32x2 inv = pack2(rcp_approx(b0), rcp_approx(b1));
+                inv = fma2(fma2(sub2(0ull, wbe), inv, splat2(1.0f)), inv, inv);      // one Newton step: <= 1 ulp
+                const f32x2 mean_b = mul2(wv2, inv);
+                const float nan = __int_as_float(0x7fc00000);                        // an all-zero-weight pixel: 0/0 as in the reference
+                const f32x2 frac = pack2(ws0 != 0.0f ? 1.0f : nan, ws1 != 0.0f ? 1.0f : nan);
+                unpack2(mul2(frac, mean_b), rad.v[0], rad.v[1]);
+                const f32x2 rho = sub2(0ull, mean_b);
+                f32x2 acc = 0ull;
 #pragma unroll
-            for (int n = 0; n < NF; ++n) {
-                const float g = SINGLE ? fmaf(gamma, Q[n][k], R[n][k]) : fmaf(alpha, R[n][k], gamma * Q[n][k]);
-                acc = fmaf(g, g, acc);
+                for (int n = 0; n < NF; ++n) {
+                    const f32x2 g = fma2(rho, Q2[n], R2[n]);
+                    acc = fma2(g, g, acc);
+                }
+                float a0, a1;
+                unpack2(acc, a0, a1);
+                unpack2(mul2(mul2(frac, inv), pack2(sqrt_approx(a0), sqrt_approx(a1))), sg.v[0], sg.v[1]);
+                if (p.radiance_f64) {
+                    double r64[VEC];
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) r64[k] = static_cast<double>(rad.v[k]);
+                    store_stream_f64<VEC>(static_cast<double *>(p.radiance) + off, r64);
+                } else {
+                    store_stream<VEC>(static_cast<float *>(p.radiance) + off, rad);
+                }
+                store_stream<VEC>(p.sigma + off, sg);
+            } else {
+                unpack2(wsum2, wsum[0], wsum[1]);
+                unpack2(wv2, wv[0], wv[1]);
+                hdr_finish<VEC, true, SINGLE, false>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int n = 0; n < NF; ++n) {
+                        float r0, r1, q0, q1;
+                        unpack2(R2[n], r0, r1);
+                        unpack2(Q2[n], q0, q1);
+                        const float r = (k & 1) ? r1 : r0, q = (k & 1) ? q1 : q0;
+                        const float g = fmaf(alpha, r, __fmul_rn(gamma, q));
+                        acc = fmaf(g, g, acc);
+                    }
+                    return acc;
+                });
             }
-            return acc;
-        });
+        } else {
+            hdr_finish<VEC, true, SINGLE, true>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+                float acc = 0.0f;
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    const float g = SINGLE ? fmaf(gamma, Q[n][k], R[n][k]) : fmaf(alpha, R[n][k], gamma * Q[n][k]);
+                    acc = fmaf(g, g, acc);
+                }
+                return acc;
+            });
+        }
     }
 }
 
