@@ -609,6 +609,37 @@ def test_train_icrf_replays_a_graph_for_device_resident_batches(ct):
     assert np.abs(out[True] - np.linspace(0, 1, 256) ** 2.5).max() > 1e-4      # it did train
 
 
+def test_train_icrf_on_one_exposure_pair_takes_the_single_pass_step_in_a_graph(ct):
+    """Batches of two frames (one exposure pair, BASELINE config 5) without uncertainty weighting: train_icrf's step is the
+    single-pass kernel + combine, eager and captured; both loops end at the same table, and the loss of a step equals the
+    two-pass formulation's."""
+    from torch.utils.data import DataLoader
+    val, std, _ = ct.synthetic.make_stack(2, 3, 96, 128, bits=8, seed=79, device=DEV)
+    t = np.array([0.01, 0.02])
+
+    class OneBatch(torch.utils.data.Dataset):
+        def __len__(self):
+            return 1
+
+        def __getitem__(self, i):
+            return torch.arange(2), val, std, {"exposure_time": torch.from_numpy(t)}
+
+    loader = DataLoader(OneBatch(), batch_size=None, shuffle=False)
+    out = {}
+    for graphed in (False, True):
+        model = ct.ICRFModelDirect(256, 3, initial_power=2.5).to(DEV)
+        before = ct._native.launch_count()
+        ct.train_icrf(loader, 2, DEV, model, use_uncertainty_weighting=False, epochs=10, verbose=False, use_cuda_graph=graphed,
+                      exposure_ratio_threshold=0.25)
+        out[graphed] = model.icrf.detach().cpu().numpy()
+        launches = ct._native.launch_count() - before
+        # eager: the first step only connects the table (means pass, upstream, penalties), the other nine are 4 library
+        # launches each (single pass, its finalize, combine, penalties) instead of the two-pass step's 6
+        assert (launches == 39 if not graphed else launches == 11), launches     # graphed: 3 + 4 eager, 4 at capture, replays are not counted
+    assert max_abs_over_max(out[True], out[False]) < 1e-5
+    assert np.abs(out[True] - np.linspace(0, 1, 256) ** 2.5).max() > 1e-4      # it did train
+
+
 def test_train_icrf_recaptures_when_a_scheduler_changes_the_learning_rate(ct):
     """A captured optimiser step bakes the learning rate into its kernels: when a scheduler changes it, train_icrf must
     capture a new step (the batch key includes the optimisers' hyper-parameters) — same trajectory as the eager loop."""
