@@ -256,3 +256,18 @@ def test_shard_row_base_matches_flat_index_rule():
         base = kernels.shard_row_base(c, h, w, r0)
         for ch in range(c):
             assert base[ch] == rows_full[0, ch, r0, 0]
+
+
+def test_cpu_baseline_threads_survive_torchrun_environment():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arms of bench.py must still use every host core
+    (round 1's reference arm ran on one thread at N >= 2).  Checked in a child process with that environment."""
+    import os
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.path.insert(0, %r); from oracle import c_oracle, reference_runner as rr; import torch; "
+            "print(c_oracle.use_all_host_threads(), rr.use_all_host_threads(), len(os.sched_getaffinity(0)))" % ROOT)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    omp, torch_threads, cpus = (int(x) for x in out.stdout.split())
+    assert omp == cpus and torch_threads == cpus and cpus == (os.cpu_count() or 1)
