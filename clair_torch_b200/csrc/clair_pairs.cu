@@ -469,12 +469,11 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
     double d0[SLOTS], d1[SLOTS], d2[SLOTS], d3[SLOTS], d4[SLOTS];
     f32x2 t0[SLOTS], t1[SLOTS], t2[SLOTS], t3[SLOTS], t4[SLOTS];
     float pivot[SLOTS];
-    bool have[SLOTS];
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
         d0[s] = 0.0; d1[s] = 0.0; d2[s] = 0.0; d3[s] = 0.0; d4[s] = 0.0;
         t0[s] = 0ull; t1[s] = 0ull; t2[s] = 0ull; t3[s] = 0ull; t4[s] = 0ull;
-        pivot[s] = 0.0f; have[s] = false;
+        pivot[s] = -1.0f;       // < 0: this lane has not seen a valid loss yet (losses are >= 0)
     }
     auto halves = [](f32x2 v) { float a, b; unpack2(v, a, b); return static_cast<double>(a) + static_cast<double>(b); };
     auto flush = [&]() {
@@ -586,7 +585,6 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
                 const f32x2 nrh2 = splat2(-r_hi), nrl2 = splat2(-p.pairs.r_lo[pr]);
                 f32x2 a0 = t0[s], a1 = t1[s], a2 = t2[s], a3 = t3[s], a4 = t4[s];
                 float k = pivot[s];
-                bool hv = have[s];
 #pragma unroll
                 for (int it = 0; it < TILE / 64; ++it) {
                     const int q = 64 * it;
@@ -596,7 +594,7 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
                     float g0, g1;
                     unpack2(wg, g0, g1);
                     const f32x2 vm = pack2(mul_sat(g0, 1.0e30f), mul_sat(g1, 1.0e30f));           // 1 valid, 0 masked
-                    f32x2 wt = mul2(wg, vm);                                                      // Gaussian part of the weight
+                    f32x2 wt = wg;                                                                // Gaussian part of the weight; x vm below
                     f32x2 inv = 0ull, ell2;
                     if constexpr (RELATIVE) {
                         float es0, es1;
@@ -622,7 +620,7 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
                                 // = rs / (1 + x), x = 1e-6 rs <= 1e-3: 1 - x + x^2 is exact to 1e-9
                                 const f32x2 x = mul2(rs, splat2(1e-6f));
                                 const f32x2 pq = sub2(fma2(x, x, splat2(1.0f)), x);
-                                wt = fma2(mul2(rs, pq), vm, wt);
+                                wt = fma2(rs, pq, wt);
                             }
                         } else {
                             const f32x2 rsb = mul2(lds2(fj + 2 * TILE + q), splat2(r_hi));
@@ -632,19 +630,21 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
                             if (unc) {
                                 float u0, u1;
                                 unpack2(add2(err, splat2(1e-6f)), u0, u1);
-                                wt = fma2(pack2(rcp_approx(u0), rcp_approx(u1)), vm, wt);
+                                wt = add2(pack2(rcp_approx(u0), rcp_approx(u1)), wt);
                             }
                         }
                     }
+                    wt = mul2(wt, vm);                                // masked pixels: finite (sanitised terms) times 0
                     if constexpr (FULL) {
-                        if (!hv) {                                    // the pivot: the first valid loss this lane sees
-                            float l0, l1, m0, m1;
-                            unpack2(ell2, l0, l1);
+                        {                                             // the pivot: the first valid loss this lane sees; < 0: none yet
+                            float l0, l1, m0, m1;                     // (losses are >= 0; while there is none every weight was 0,
+                            unpack2(ell2, l0, l1);                    //  so the value subtracted so far does not matter)
                             unpack2(vm, m0, m1);
-                            k = (m0 != 0.0f) ? l0 : ((m1 != 0.0f) ? l1 : k);
-                            hv = (m0 != 0.0f) || (m1 != 0.0f);
+                            const bool none = k < 0.0f;
+                            k = (none && m1 != 0.0f) ? l1 : k;
+                            k = (none && m0 != 0.0f) ? l0 : k;
                         }
-                        const f32x2 dl = mul2(vm, sub2(ell2, splat2(k)));
+                        const f32x2 dl = sub2(ell2, splat2(k));       // wt carries the mask
                         const f32x2 wdl = mul2(wt, dl);
                         a0 = add2(a0, wt);
                         a1 = add2(a1, wdl);
@@ -662,7 +662,6 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
                     if constexpr (ERR) t3[s] = a3;
                     t4[s] = a4;
                     pivot[s] = k;
-                    have[s] = hv;
                 }
             }
         }
@@ -673,6 +672,8 @@ __global__ void __launch_bounds__(STATS_MAXT(SLOTS), STATS_MINB(SLOTS)) pair_sta
     // one buffer (very long stacks, where a second buffer would cost a resident block) it is A, barrier, B, barrier.
     const uint32_t nb = static_cast<uint32_t>(p.stats_buffers);
     const uint32_t buf_floats = static_cast<uint32_t>(N) * kFrameFloats;
+    // (Tried: three buffers handed over through mbarriers instead of the block barrier — a warp then only waits for one a
+    // whole pair phase behind.  Same sums, same time on c3 (1.69 ms): the barrier stalls ncu shows are not what bounds it.)
     prefetch();
     __syncthreads();                    // the table is staged
     uint32_t k_it = 0;
