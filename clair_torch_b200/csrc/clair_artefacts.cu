@@ -55,8 +55,14 @@ __global__ void __launch_bounds__(256) dark_mix_rows_kernel(const float *__restr
         row_group_blur<VEC>(rg, col, g, chained_left, chained_right, x, blur);
         if (!active) continue;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k)
-            dark_mix_value<HAS_STD>(x[k], blur[k], HAS_STD ? sv.v[k] : 0.0f, dk.v[k], HAS_STD ? ds.v[k] : 0.0f, g, xo.v[k], so.v[k]);
+        for (int k = 0; k < VEC; k += 2) {      // pixel pairs on packed fp32x2
+            f32x2 xm, sm = 0ull;
+            dark_mix_value2<HAS_STD>(pack2(x[k], x[k + 1]), pack2(blur[k], blur[k + 1]),
+                                     HAS_STD ? pack2(sv.v[k], sv.v[k + 1]) : 0ull, pack2(dk.v[k], dk.v[k + 1]),
+                                     HAS_STD ? pack2(ds.v[k], ds.v[k + 1]) : 0ull, g, xm, sm);
+            unpack2(xm, xo.v[k], xo.v[k + 1]);
+            if constexpr (HAS_STD) unpack2(sm, so.v[k], so.v[k + 1]);
+        }
         store_stream<VEC>(val_out + o, xo);
         if constexpr (HAS_STD) store_stream<VEC>(std_out + o, so);
     }

@@ -722,7 +722,6 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrPara
     const uint32_t tab_bias = curve_row_bias(s_tab);
     const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
     const float *val = static_cast<const float *>(p.val);
-
     for (uint32_t item = first_item; item - lane < n_items; item += item_stride, cur.advance()) {
         const bool active = item < n_items;
         const uint32_t row = active ? item / groups_per_row : 0u;
@@ -771,8 +770,13 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrPara
                     row_group_blur<VEC>(rg[j], col, p.dg, chained_left, chained_right, x, blur);
                     const float it = p.scale.inv_t[n0 + j];
                     float xm[VEC], sm[VEC];
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) dark_mix_value<true>(x[k], blur[k], sv[j].v[k], dk[j].v[k], ds[j].v[k], p.dg, xm[k], sm[k]);
+                    {
+                        f32x2 xm2, sm2;
+                        dark_mix_value2<true>(pack2(x[0], x[1]), pack2(blur[0], blur[1]), pack2(sv[j].v[0], sv[j].v[1]),
+                                              pack2(dk[j].v[0], dk[j].v[1]), pack2(ds[j].v[0], ds[j].v[1]), p.dg, xm2, sm2);
+                        unpack2(xm2, xm[0], xm[1]);
+                        unpack2(sm2, sm[0], sm[1]);
+                    }
                     if constexpr (PACKED) {
                         const HdrTerms2 t = hdr_terms2(xm[0], xm[1], sm[0], sm[1], it, has_model, gaussian, bias[0], bias[1], lm1, true);
                         wsum2 = add2(wsum2, t.w);

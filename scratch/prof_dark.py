@@ -1,4 +1,6 @@
+import os, sys
 import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import clair_torch_b200 as ct
 from clair_torch_b200 import kernels
 dev = torch.device("cuda", 0)
