@@ -320,7 +320,9 @@ extern "C" int clair_dark_field_mix(const float *val_dev, const float *std_dev, 
     if (vec > 1 && plane / vec < (1ll << 31)) {
         DarkGeometry g{height, width, threshold, alpha, -alpha * 1.4426950408889634f};
         const int64_t want = (plane / vec + 255) / 256;
-        const unsigned gx = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(want, resident_blocks_per_channel(8, static_cast<int>(slabs)))));
+        // 16 x the resident blocks: a grid of exactly the resident blocks ran 130 us at c1 size, this one 120 us (the blocks that
+        // happen to get the slower memory partitions no longer hold the whole launch back)
+        const unsigned gx = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(want, resident_blocks_per_channel(8 * (g_tuning.aux_waves > 0 ? g_tuning.aux_waves : 16), static_cast<int>(slabs)))));
         dim3 grid(gx, static_cast<unsigned>(slabs));
         const bool has_std = std_out_dev != nullptr;
         if (vec == 4) {
@@ -358,7 +360,7 @@ extern "C" int clair_flat_field_correct(void *value_dev, int value_f64, float *s
         if (q && reinterpret_cast<uintptr_t>(q) % 16 != 0) vec4 = false;
     const int vec = vec4 ? 4 : 1;
     const int64_t items = plane / vec;
-    const unsigned rblocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((items + 511) / 512, resident_blocks_per_channel(8, n_channels))));
+    const unsigned rblocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>((items + 511) / 512, resident_blocks_per_channel(8 * (g_tuning.aux_waves > 0 ? g_tuning.aux_waves : 1), n_channels))));
     dim3 rgrid(rblocks, n_channels), agrid(static_cast<unsigned>((items + 255) / 256), n_channels, n_images);
 #define FLAT_LAUNCH(V, VEC)                                                                                                    \
     do {                                                                                                                       \

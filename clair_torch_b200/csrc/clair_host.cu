@@ -90,6 +90,10 @@ extern "C" int clair_set_tuning(const char *key, int value) {
     else if (k == "grad_warps") g_tuning.grad_warps = value;
     else if (k == "grad_copies") g_tuning.grad_copies = value;
     else if (k == "hdr_tma") g_tuning.hdr_tma = value;
+    else if (k == "fwd_blocks") g_tuning.fwd_blocks = value;
+    else if (k == "aux_waves") g_tuning.aux_waves = value;
+    else if (k == "stats_waves") g_tuning.stats_waves = value;
+    else if (k == "grad_waves") g_tuning.grad_waves = value;
     else if (k == "stats_warps") g_tuning.stats_warps = value;
     else if (k == "stats_buffers") g_tuning.stats_buffers = value;
     else if (k == "stats_slots") g_tuning.stats_slots = value;

@@ -48,8 +48,11 @@ struct Tuning {
     int hdr_waves = 0;          // resident waves per persistent grid
     int hdr_fixed_max = 0;      // largest N that takes the register kernel (fp32 stacks)
     int hdr_force_dynamic = 0;  // use the N-dynamic float64-sum kernel even for N <= 8
+    int fwd_blocks = 0;         // forward / linearise: 1024-pixel tiles per block (-1 = one tile per block, no loop bound sharing)
+    int aux_waves = 0;          // dark mix / flat reduce / frame statistics / code expansion: grid = resident blocks x this
     int hdr_tma = 0;            // camera-layout 9..16-frame kernels: -1 = per-thread loads instead of the bulk-copy staging
     int hdr_prefetch = 0;       // camera-layout register kernels: prefetch the next trip's codes (1 = into L1, 2 = into L2, -1 = off)
+    int stats_waves = 0, grad_waves = 0;   // pair kernels: grid = resident blocks x this
     int stats_blocks_per_sm = 0;
     int stats_warps = 0;        // block shape of the statistics kernel (both must be set)
     int stats_slots = 0;

@@ -1677,6 +1677,11 @@ static int pair_stats_impl(const float *val_dev, const float *std_dev, int n_fra
             int per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
             per_sm = g_tuning.stats_blocks_per_sm > 0 ? g_tuning.stats_blocks_per_sm : std::max(per_sm, 1);
+            // Several pairs per tile: 4 x the resident blocks (c3 1.656 -> 1.55 ms, c2 0.271 -> 0.261 ms: blocks that start late
+            // or sit on a slower memory partition no longer hold the launch back); a single exposure pair is all staging, where
+            // the per-block table staging and final atomics weigh more (c5/8: 0.194 ms at 1 x, 0.222 ms at 4 x).
+            const int waves = g_tuning.stats_waves > 0 ? g_tuning.stats_waves : (count >= 4 ? 4 : 1);
+            if (n_tiles >= 8 * waves * resident_blocks_per_channel(per_sm, n_channels)) per_sm *= waves;
             int64_t gx = std::min<int64_t>(n_tiles, std::max<int64_t>(1, resident_blocks_per_channel(per_sm, n_channels)));
             // a grid stride that is a multiple of C pixels keeps every staging item on the same table rows in all its tiles
             if (gx > n_channels) gx -= gx % n_channels;
@@ -1806,6 +1811,10 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
             int per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
             per_sm = g_tuning.grad_blocks_per_sm > 0 ? g_tuning.grad_blocks_per_sm : std::max(per_sm, 1);
+        // (the single-pass kernel is fastest on exactly the resident blocks: c5 2.47 ms, 3.1 ms at 2 x)
+            // one or two pairs (little work per trip): 3 x the resident blocks (c5 2.59 -> 2.30 ms, an eighth of it 0.41 -> 0.31 ms);
+            // many pairs are fastest on exactly the resident blocks (c2 0.340 ms, 0.361 ms at 3 x)
+            per_sm *= g_tuning.grad_waves > 0 ? g_tuning.grad_waves : (count <= 2 ? 3 : 1);
             const int64_t gx = std::min<int64_t>((n_groups + warps - 1) / warps,
                                                  std::max<int64_t>(1, resident_blocks_per_channel(per_sm, n_channels)));
             kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), warps * 32, smem, s>>>(p);
@@ -1870,6 +1879,7 @@ extern "C" int clair_pair_fused(const float *val_dev, int n_frames, int n_channe
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
         per_sm = g_tuning.grad_blocks_per_sm > 0 ? g_tuning.grad_blocks_per_sm : std::max(per_sm, 1);
+        // (the single-pass kernel is fastest on exactly the resident blocks: c5 2.47 ms, 3.1 ms at 2 x)
         const int64_t gx = std::min<int64_t>((n_groups + warps - 1) / warps, std::max<int64_t>(1, resident_blocks_per_channel(per_sm, n_channels)));
         kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), warps * 32, smem, s>>>(p);
         return 0;

@@ -34,50 +34,67 @@ __global__ void __launch_bounds__(kBlock) icrf_forward_kernel(const ForwardParam
     stage_curve_pairs(s_tab, p.theta, C, L);
     __syncthreads();
 
-    const int64_t item = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x;
-    const int64_t pix = item * VEC;
-    if (pix >= p.plane) return;
     const int slab = blockIdx.y;                    // n * C + c
     const int c = slab % C;
-    const int64_t off = static_cast<int64_t>(slab) * p.stride + pix;
     const float lm1 = static_cast<float>(L - 1);
+    const int64_t slab_off = static_cast<int64_t>(slab) * p.stride;
+    const int64_t n_items = (p.plane + VEC - 1) / VEC;
+    const int64_t item_stride = static_cast<int64_t>(gridDim.x) * kBlock;
+    const bool has_std = MODE == 2 && p.std != nullptr;
 
-    const Pack<VEC> xv = load_stream<VEC>(p.x + off);
-    Pack<VEC> sv;
-    if constexpr (MODE == 2) {
-        if (p.std != nullptr) sv = load_stream<VEC>(p.std + off);
-    }
-    Pack<VEC> yv, dv, gv;
-    int u = static_cast<int>((pix + p.rows.base(c)) % C);
+    auto finish = [&](int64_t pix, const Pack<VEC> &xv, const Pack<VEC> &sv) {
+        const int64_t off = slab_off + pix;
+        Pack<VEC> yv, dv, gv;
+        int u = static_cast<int>((pix + p.rows.base(c)) % C);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-        if constexpr (MODE == 1) {
-            yv.v[k] = s_tab[c * L + icrf_lookup_index(xv.v[k], lm1)].x;
-        } else {
-            const IcrfTap t = icrf_linear(xv.v[k], s_tab + u * L, lm1);
-            yv.v[k] = t.f;
-            dv.v[k] = t.fp;
-            if constexpr (MODE == 2) {
-                // sqrt((f' * s)^2), inference/linearization.py:106,132
-                const float g = (p.std != nullptr) ? __fmul_rn(t.fp, sv.v[k]) : 0.0f;
-                gv.v[k] = sqrtf(__fmul_rn(g, g));
+        for (int k = 0; k < VEC; ++k) {
+            if constexpr (MODE == 1) {
+                yv.v[k] = s_tab[c * L + icrf_lookup_index(xv.v[k], lm1)].x;
+            } else {
+                const IcrfTap t = icrf_linear(xv.v[k], s_tab + u * L, lm1);
+                yv.v[k] = t.f;
+                dv.v[k] = t.fp;
+                if constexpr (MODE == 2) {
+                    // sqrt((f' * s)^2), inference/linearization.py:106,132
+                    const float g = has_std ? __fmul_rn(t.fp, sv.v[k]) : 0.0f;
+                    gv.v[k] = sqrtf(__fmul_rn(g, g));
+                }
+                u = wrap_inc(u, C);
             }
-            u = wrap_inc(u, C);
         }
-    }
-    store_stream<VEC>(p.y + off, yv);
-    if constexpr (MODE == 0) {
-        if (p.dydx != nullptr) store_stream<VEC>(p.dydx + off, dv);
-    }
-    if constexpr (MODE == 2) store_stream<VEC>(p.sigma + off, gv);
-    if constexpr (MODE == 1) {
-        if (p.sigma != nullptr) {                   // linearise with a LOOKUP model and no std images: zeros (:97)
-            Pack<VEC> zero;
+        store_stream<VEC>(p.y + off, yv);
+        if constexpr (MODE == 0) {
+            if (p.dydx != nullptr) store_stream<VEC>(p.dydx + off, dv);
+        }
+        if constexpr (MODE == 2) store_stream<VEC>(p.sigma + off, gv);
+        if constexpr (MODE == 1) {
+            if (p.sigma != nullptr) {                   // linearise with a LOOKUP model and no std images: zeros (:97)
+                Pack<VEC> zero;
 #pragma unroll
-            for (int k = 0; k < VEC; ++k) zero.v[k] = 0.0f;
-            store_stream<VEC>(p.sigma + off, zero);
+                for (int k = 0; k < VEC; ++k) zero.v[k] = 0.0f;
+                store_stream<VEC>(p.sigma + off, zero);
+            }
         }
+    };
+    // Persistent blocks: the table is staged once per block, not once per 1024 pixels.
+    for (int64_t item = static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x; item < n_items; item += item_stride) {
+        const int64_t pix = item * VEC;
+        const Pack<VEC> xv = load_stream<VEC>(p.x + slab_off + pix);
+        Pack<VEC> sv;
+        if (has_std) sv = load_stream<VEC>(p.std + slab_off + pix);
+        finish(pix, xv, sv);
     }
+}
+
+// Blocks per (frame, channel) slab of the forward / linearise grid.  A block walks several 1024-pixel tiles (the 6 KB table
+// is staged once per block), but the grid stays many times larger than what is resident: measured on 24 MP frames, one
+// tile per block 0.210 ms (0.84 of the copy peak), exactly the resident blocks 0.225 ms, ~6 tiles per block 0.177 ms (0.99).
+static unsigned forward_grid_x(int64_t plane, int vec, int64_t slabs) {
+    const int64_t tiles = (plane / vec + kBlock - 1) / kBlock;
+    if (g_tuning.fwd_blocks < 0) return static_cast<unsigned>(tiles);
+    const int per_block = g_tuning.fwd_blocks > 0 ? g_tuning.fwd_blocks : (tiles * slabs >= 100000 ? 6 : 4);   // c1-sized stacks: 4 (0.94)
+    const int64_t resident = std::max<int64_t>(1, (static_cast<int64_t>(device_sm_count()) * 8 + slabs - 1) / slabs);
+    return static_cast<unsigned>(std::min(tiles, std::max(resident, (tiles + per_block - 1) / per_block)));
 }
 
 // Linearisation straight from the camera's integer codes (SURVEY.md 8(f) rank 2 for the lineariser): the reference's CPU
@@ -108,12 +125,13 @@ __global__ void __launch_bounds__(kBlock) linearize_codes_kernel(const Linearize
         for (int k = threadIdx.x; k < 256; k += blockDim.x) s_x[k] = __fdiv_rn(static_cast<float>(k), p.code_max);
     }
     __syncthreads();
-    const int64_t pix = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * 4;
-    if (pix >= p.plane) return;
     const int slab = blockIdx.y;                    // n * C + c
     const int c = slab % C;
-    const int64_t off = static_cast<int64_t>(slab) * p.plane + pix;
     const float lm1 = static_cast<float>(L - 1);
+    // a block walks several 1024-pixel tiles: the tables are staged once per block (forward_grid_x)
+    for (int64_t pix = (static_cast<int64_t>(blockIdx.x) * kBlock + threadIdx.x) * 4; pix < p.plane;
+         pix += static_cast<int64_t>(gridDim.x) * kBlock * 4) {
+    const int64_t off = static_cast<int64_t>(slab) * p.plane + pix;
     Pack<4> xv;
     if constexpr (BYTES == 1) {
         const uint32_t w = __ldcs(reinterpret_cast<const uint32_t *>(static_cast<const uint8_t *>(p.codes) + off));
@@ -148,6 +166,7 @@ __global__ void __launch_bounds__(kBlock) linearize_codes_kernel(const Linearize
     }
     store_stream<4>(p.lin + off, yv);
     store_stream<4>(p.sigma + off, gv);
+    }
 }
 
 // grid: (ceil(plane / kBlock), n_frames * C); one element per thread (CATMULL is off the hot path)
@@ -321,7 +340,7 @@ extern "C" int clair_icrf_forward(const float *x_dev, const float *theta_dev, fl
 #define LAUNCH_FWD(V, M)                                                                          \
     do {                                                                                          \
         if (int rc = ensure_smem(icrf_forward_kernel<V, M>, smem)) return rc;                     \
-        dim3 grid(static_cast<unsigned>((plane / V + kBlock - 1) / kBlock), static_cast<unsigned>(slabs)); \
+        dim3 grid(forward_grid_x(plane, V, slabs), static_cast<unsigned>(slabs));                 \
         icrf_forward_kernel<V, M><<<grid, kBlock, smem, s>>>(p);                                  \
     } while (0)
     const bool lookup = interp_mode == CLAIR_INTERP_LOOKUP;
@@ -368,7 +387,7 @@ int linearize_impl(const char *fn, const float *val_dev, const float *std_dev, c
 #define LAUNCH_LIN(V, M)                                                                          \
     do {                                                                                          \
         if (int rc = ensure_smem(icrf_forward_kernel<V, M>, smem)) return rc;                     \
-        dim3 grid(static_cast<unsigned>((plane / V + kBlock - 1) / kBlock), static_cast<unsigned>(slabs)); \
+        dim3 grid(forward_grid_x(plane, V, slabs), static_cast<unsigned>(slabs));                 \
         icrf_forward_kernel<V, M><<<grid, kBlock, smem, s>>>(p);                                  \
     } while (0)
     if (interp_mode == CLAIR_INTERP_LOOKUP) {
@@ -418,7 +437,7 @@ extern "C" int clair_linearize_codes(const void *codes_dev, int code_bytes, floa
     fill_rows(p.rows, curve_row_base_host, n_channels, plane);
     const size_t smem = sizeof(float2) * n_channels * lut_size + (code_bytes == 1 ? 256 * sizeof(float) : 0);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    dim3 grid(static_cast<unsigned>((plane / 4 + kBlock - 1) / kBlock), static_cast<unsigned>(slabs));
+    dim3 grid(forward_grid_x(plane, 4, slabs), static_cast<unsigned>(slabs));
     if (code_bytes == 1) {
         if (int rc = ensure_smem(linearize_codes_kernel<1>, smem)) return rc;
         linearize_codes_kernel<1><<<grid, kBlock, smem, s>>>(p);
@@ -473,7 +492,7 @@ extern "C" int clair_expand_codes(const void *codes_dev, int code_bytes, float c
         reinterpret_cast<uintptr_t>(val_dev) % 16 != 0 || reinterpret_cast<uintptr_t>(std_dev) % 16 != 0)
         return fail(CLAIR_E_ARG, "clair_expand_codes: the element count must be a multiple of 4 and the buffers aligned for 4-sample accesses");
     const int64_t quads = n_elements / 4;
-    const unsigned grid = static_cast<unsigned>(std::min<int64_t>((quads + kBlock - 1) / kBlock, static_cast<int64_t>(device_sm_count()) * 16));
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>((quads + kBlock - 1) / kBlock, static_cast<int64_t>(device_sm_count()) * 8 * (g_tuning.aux_waves > 0 ? g_tuning.aux_waves : 32)));   // c3: 724 us at 2 waves, 637 us at 32
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (code_bytes == 1) expand_codes_kernel<1><<<grid, kBlock, 0, s>>>(codes_dev, code_max, std_mode, std_value, quads, val_dev, std_dev);
     else expand_codes_kernel<2><<<grid, kBlock, 0, s>>>(codes_dev, code_max, std_mode, std_value, quads, val_dev, std_dev);
@@ -1089,7 +1108,7 @@ extern "C" int clair_frame_stats_update(const float *val_dev, const float *weigh
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
         const int64_t want = (plane / vec + kBlock - 1) / kBlock;
-        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want, resident_blocks_per_channel(std::max(per_sm, 1) * 2, n_channels)));
+        const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want, resident_blocks_per_channel(std::max(per_sm, 1) * (g_tuning.aux_waves > 0 ? g_tuning.aux_waves : 2), n_channels)));
         kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p);
         return 0;
     };
