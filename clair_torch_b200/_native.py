@@ -143,6 +143,11 @@ def load() -> ctypes.CDLL:
             fn.argtypes = argtypes
         if lib.clair_abi_version() != ABI_VERSION:
             raise NativeLibraryError(f"ABI mismatch: library {lib.clair_abi_version()}, binding {ABI_VERSION}")
+        # developer knobs for measurement scripts: CLAIR_TUNE="key=value,key=value" (clair_set_tuning; unknown keys raise)
+        for item in filter(None, os.environ.get("CLAIR_TUNE", "").split(",")):
+            key, _, value = item.partition("=")
+            if lib.clair_set_tuning(key.strip().encode(), int(value)) != 0:
+                raise NativeLibraryError(f"CLAIR_TUNE: {lib.clair_last_error().decode()}")
         _lib = lib
     return _lib
 

@@ -1064,9 +1064,12 @@ int launch_merge_kernel(K kernel, const MergeLaunch &m, bool fold = false) {
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, m.smem);
     // resident waves per persistent grid (measured): 2 for the register kernel up to 8 frames, 3 beyond and for the
-    // shared-memory-parked kernel
-    per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : ((m.parked || m.n_frames > kMaxFixedFrames) ? 3 : 2));
+    // shared-memory-parked kernel; 6 for planes of tens of megapixels (c4, values interleaved in one process: fp32 stack 878 ->
+    // 869 us, uint16 codes 0.818 -> 0.802 ms, camera layout 0.883 -> 0.869 ms; 1080p stacks lose with more than 2)
     const int grid_channels = fold ? 1 : m.n_channels;
+    per_sm = std::max(per_sm, 1);
+    const bool big = m.want_blocks >= 64 * resident_blocks_per_channel(per_sm, grid_channels);
+    per_sm *= g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : (big ? 6 : ((m.parked || m.n_frames > kMaxFixedFrames) ? 3 : 2));
     const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(m.want_blocks, resident_blocks_per_channel(per_sm, grid_channels)));
     kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(grid_channels)), kBlock, m.smem, m.stream>>>(m.p);
     return 0;
