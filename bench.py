@@ -233,7 +233,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "Mpixel*frames/s", "cores": ref.threads, "kind": ref.kind, "sample": sample},
             "e2e": {"value": value, "unit": "Mpixel*frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline_train_c2(budget_rows=120):
@@ -934,7 +934,31 @@ def hdr_merge_bench(cfg, key, dev, lib, rank, world, steps, warmup, e2e_steps, s
     }
 
 
+_RESULT_FD = None
+
+
+def keep_stdout_for_the_result():
+    """stdout carries ONE line, the JSON result: anything libraries print on file descriptor 1 meanwhile (NCCL's version banner
+    at communicator creation, for instance) goes to stderr instead."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    text = json.dumps(line) + "\n"
+    if _RESULT_FD is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, text.encode())
+
+
 def main():
+    keep_stdout_for_the_result()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     # default K: one rank's share of c4 is 8 stacks, so a job is a burst of a few milliseconds; 200 back-to-back merges
@@ -975,7 +999,7 @@ def main():
     if args.only_dp:
         dp = dp_training_metrics(dev, rank, world)
         if rank == 0:
-            print(json.dumps({"dp_train_c5": dp}))
+            emit({"dp_train_c5": dp})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -1032,7 +1056,7 @@ def main():
             "e2e_codes": res["e2e_codes"],
             "gpu_launches": res["launches"], "clocks": res["clocks"], "extra": extra,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
