@@ -380,3 +380,48 @@ def test_integer_code_batches_reject_what_they_cannot_take(ct):
     ds_f = ExposureStackDataset(list(good.to(torch.float32) / 255), StdSpec("multiplier", 0.05), [0.01, 0.02, 0.04])
     with pytest.raises(ValueError):
         ct.measure_linearity(DataLoader(ds_f, batch_size=3, collate_fn=custom_collate), DEV, True, True, None)
+
+
+def test_grid_sizes_do_not_change_results(ct):
+    """The launch grids are tuned per kernel (blocks that walk several tiles, grids of 1x .. 32x the resident blocks): results
+    must not depend on them.  Elementwise kernels bit for bit, the pair sums to the rounding of their fp32 partial sums."""
+    from clair_torch_b200 import kernels
+    from clair_torch_b200.datasets import StdSpec
+    lib = ct._native.load()
+
+    def with_knobs(fn, **knobs):
+        try:
+            for key, value in knobs.items():
+                ct._native.check(lib.clair_set_tuning(key.encode(), value), "tune")
+            return fn()
+        finally:
+            for key in knobs:
+                lib.clair_set_tuning(key.encode(), 0)
+
+    val, std, t = ct.synthetic.make_stack(6, 3, 310, 404, bits=16, seed=77, device=DEV)       # 125 240 pixels: tiles with a tail
+    theta = ct.synthetic.reference_curve(3).to(DEV)
+    base = kernels.linearize(val, std, theta)
+    for blocks in (-1, 1, 3, 50):
+        got = with_knobs(lambda: kernels.linearize(val, std, theta), fwd_blocks=blocks)
+        assert all(torch.equal(a, b) for a, b in zip(got, base))
+    codes = torch.round(val * 65535.0).to(torch.int32).to(torch.uint16)
+    base_codes = kernels.expand_codes(codes, StdSpec("multiplier", 0.05), 65535.0)
+    for waves in (1, 7):
+        got = with_knobs(lambda: kernels.expand_codes(codes, StdSpec("multiplier", 0.05), 65535.0), aux_waves=waves)
+        assert all(torch.equal(a, b) for a, b in zip(got, base_codes))
+    dark = torch.rand_like(val) * 0.1
+    dark_std = dark * 0.1 + 1e-3
+    base_dark = kernels.dark_field_mix(val, std, dark, dark_std)
+    for waves in (1, 3):
+        got = with_knobs(lambda: kernels.dark_field_mix(val, std, dark, dark_std), aux_waves=waves)
+        assert all(torch.equal(a, b) for a, b in zip(got, base_dark))
+    i, j, r = orc.exposure_pairs(t, 0.2)
+    base_sums = kernels.pair_stats(val, std, i, j, r, theta, 1 / 255, 254 / 255, True, True)
+    for waves in (1, 2, 8):
+        got = with_knobs(lambda: kernels.pair_stats(val, std, i, j, r, theta, 1 / 255, 254 / 255, True, True), stats_waves=waves)
+        assert max_rel(got.cpu().numpy(), base_sums.cpu().numpy(), 1e-300) < 5e-6      # fp32 partial sums per (lane, block)
+    base_merge = kernels.hdr_merge_update(kernels.HdrMergeState(), val, std, t, theta, True, True, radiance_dtype=torch.float32)
+    for waves in (1, 5):
+        got = with_knobs(lambda: kernels.hdr_merge_update(kernels.HdrMergeState(), val, std, t, theta, True, True,
+                                                          radiance_dtype=torch.float32), hdr_waves=waves)
+        assert all(torch.equal(a, b) for a, b in zip(got, base_merge))
