@@ -91,6 +91,8 @@ extern "C" int clair_set_tuning(const char *key, int value) {
     else if (k == "grad_copies") g_tuning.grad_copies = value;
     else if (k == "hdr_tma") g_tuning.hdr_tma = value;
     else if (k == "fwd_blocks") g_tuning.fwd_blocks = value;
+    else if (k == "dark_strip") g_tuning.dark_strip = value;
+    else if (k == "dark_rows") g_tuning.dark_rows = value;
     else if (k == "aux_waves") g_tuning.aux_waves = value;
     else if (k == "stats_waves") g_tuning.stats_waves = value;
     else if (k == "grad_waves") g_tuning.grad_waves = value;

@@ -50,6 +50,7 @@ struct Tuning {
     int hdr_force_dynamic = 0;  // use the N-dynamic float64-sum kernel even for N <= 8
     int fwd_blocks = 0;         // forward / linearise: 1024-pixel tiles per block (-1 = one tile per block, no loop bound sharing)
     int aux_waves = 0;          // dark mix / flat reduce / frame statistics / code expansion: grid = resident blocks x this
+    int dark_strip = 0, dark_rows = 0;   // fused dark merge: -1 = grid-stride form instead of the strip walk; rows per band
     int hdr_tma = 0;            // camera-layout 9..16-frame kernels: -1 = per-thread loads instead of the bulk-copy staging
     int hdr_prefetch = 0;       // camera-layout register kernels: prefetch the next trip's codes (1 = into L1, 2 = into L2, -1 = off)
     int stats_waves = 0, grad_waves = 0;   // pair kernels: grid = resident blocks x this

@@ -44,6 +44,7 @@ struct HdrParams {
     int hwc;                  // integer codes are (n_frames, H, W, 3) BGR-interleaved instead of planar
     int prefetch;             // camera-layout register kernels: 1 / 2 = prefetch the next trip's codes into L1 / L2, 0 = off
     const float *dark;        // fused dark-field mix (hdr_merge_dark_kernel): dark frames and their std, shaped like val
+    int dark_rows;            // hdr_merge_dark_strip_kernel: rows per band of a warp's strip walk
     const float *dark_std;
     DarkGeometry dg;
     CurveRows rows;
@@ -694,6 +695,63 @@ __global__ void __launch_bounds__(kBlock, fixed_min_blocks(SRC, VEC, NF, SINGLE)
     }
 }
 
+// Output stage of the dark-field kernels for the pixel pair a thread owns (packed sums, (R_n, Q_n) of all frames in registers)
+template <int NF, bool SINGLE>
+__device__ __forceinline__ void dark_finish_pair(const HdrParams &p, int64_t off, f32x2 wsum2, f32x2 wv2, const f32x2 (&R2)[NF],
+                                                 const f32x2 (&Q2)[NF]) {
+    constexpr int VEC = 2;
+    if constexpr (SINGLE) {
+        // the single-batch epilogue of hdr_merge_fixed_kernel on the pixel pair (same operations, same bits)
+        Pack<VEC> rad, sg;
+        const f32x2 wbe = add2(wsum2, splat2(1e-6f));                     // statistics.py:76 (fp32 add)
+        float b0, b1, ws0, ws1;
+        unpack2(wbe, b0, b1);
+        unpack2(wsum2, ws0, ws1);
+        f32x2 inv = pack2(rcp_approx(b0), rcp_approx(b1));
+        inv = fma2(fma2(sub2(0ull, wbe), inv, splat2(1.0f)), inv, inv);      // one Newton step: <= 1 ulp
+        const f32x2 mean_b = mul2(wv2, inv);
+        const float nan = __int_as_float(0x7fc00000);                        // an all-zero-weight pixel: 0/0 as in the reference
+        const f32x2 frac = pack2(ws0 != 0.0f ? 1.0f : nan, ws1 != 0.0f ? 1.0f : nan);
+        unpack2(mul2(frac, mean_b), rad.v[0], rad.v[1]);
+        const f32x2 rho = sub2(0ull, mean_b);
+        f32x2 acc = 0ull;
+#pragma unroll
+        for (int n = 0; n < NF; ++n) {
+            const f32x2 g = fma2(rho, Q2[n], R2[n]);
+            acc = fma2(g, g, acc);
+        }
+        float a0, a1;
+        unpack2(acc, a0, a1);
+        unpack2(mul2(mul2(frac, inv), pack2(sqrt_approx(a0), sqrt_approx(a1))), sg.v[0], sg.v[1]);
+        if (p.radiance_f64) {
+            double r64[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) r64[k] = static_cast<double>(rad.v[k]);
+            store_stream_f64<VEC>(static_cast<double *>(p.radiance) + off, r64);
+        } else {
+            store_stream<VEC>(static_cast<float *>(p.radiance) + off, rad);
+        }
+        store_stream<VEC>(p.sigma + off, sg);
+    } else {
+        float wsum[VEC], wv[VEC];
+        unpack2(wsum2, wsum[0], wsum[1]);
+        unpack2(wv2, wv[0], wv[1]);
+        hdr_finish<VEC, true, SINGLE, false>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int n = 0; n < NF; ++n) {
+                float r0, r1, q0, q1;
+                unpack2(R2[n], r0, r1);
+                unpack2(Q2[n], q0, q1);
+                const float r = (k & 1) ? r1 : r0, q = (k & 1) ? q1 : q0;
+                const float g = fmaf(alpha, r, __fmul_rn(gamma, q));
+                acc = fmaf(g, g, acc);
+            }
+            return acc;
+        });
+    }
+}
+
 // ---- the fixed-N kernel with the dark-field mix fused into its load ----------------------
 // x' = m B(x) + (1 - m) x and s_eff (clair_dark.cuh) are formed in registers from the raw frame, its std and the dark
 // frame + std, so the mixed stack never exists in memory: 4 input stacks are read once instead of the pre-pass
@@ -798,55 +856,7 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrPara
         }
         if (!active) continue;
         if constexpr (PACKED) {
-            if constexpr (SINGLE) {
-                // the single-batch epilogue of hdr_merge_fixed_kernel on the pixel pair (same operations, same bits)
-                Pack<VEC> rad, sg;
-                const f32x2 wbe = add2(wsum2, splat2(1e-6f));                     // statistics.py:76 (fp32 add)
-                float b0, b1, ws0, ws1;
-                unpack2(wbe, b0, b1);
-                unpack2(wsum2, ws0, ws1);
-                f32x2 inv = pack2(rcp_approx(b0), rcp_approx(b1));
-                inv = fma2(fma2(sub2(0ull, wbe), inv, splat2(1.0f)), inv, inv);      // one Newton step: <= 1 ulp
-                const f32x2 mean_b = mul2(wv2, inv);
-                const float nan = __int_as_float(0x7fc00000);                        // an all-zero-weight pixel: 0/0 as in the reference
-                const f32x2 frac = pack2(ws0 != 0.0f ? 1.0f : nan, ws1 != 0.0f ? 1.0f : nan);
-                unpack2(mul2(frac, mean_b), rad.v[0], rad.v[1]);
-                const f32x2 rho = sub2(0ull, mean_b);
-                f32x2 acc = 0ull;
-#pragma unroll
-                for (int n = 0; n < NF; ++n) {
-                    const f32x2 g = fma2(rho, Q2[n], R2[n]);
-                    acc = fma2(g, g, acc);
-                }
-                float a0, a1;
-                unpack2(acc, a0, a1);
-                unpack2(mul2(mul2(frac, inv), pack2(sqrt_approx(a0), sqrt_approx(a1))), sg.v[0], sg.v[1]);
-                if (p.radiance_f64) {
-                    double r64[VEC];
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) r64[k] = static_cast<double>(rad.v[k]);
-                    store_stream_f64<VEC>(static_cast<double *>(p.radiance) + off, r64);
-                } else {
-                    store_stream<VEC>(static_cast<float *>(p.radiance) + off, rad);
-                }
-                store_stream<VEC>(p.sigma + off, sg);
-            } else {
-                unpack2(wsum2, wsum[0], wsum[1]);
-                unpack2(wv2, wv[0], wv[1]);
-                hdr_finish<VEC, true, SINGLE, false>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
-                    float acc = 0.0f;
-#pragma unroll
-                    for (int n = 0; n < NF; ++n) {
-                        float r0, r1, q0, q1;
-                        unpack2(R2[n], r0, r1);
-                        unpack2(Q2[n], q0, q1);
-                        const float r = (k & 1) ? r1 : r0, q = (k & 1) ? q1 : q0;
-                        const float g = fmaf(alpha, r, __fmul_rn(gamma, q));
-                        acc = fmaf(g, g, acc);
-                    }
-                    return acc;
-                });
-            }
+            dark_finish_pair<NF, SINGLE>(p, off, wsum2, wv2, R2, Q2);
         } else {
             hdr_finish<VEC, true, SINGLE, true>(p, off, wsum, wv, [&](int k, float alpha, float gamma) {
                 float acc = 0.0f;
@@ -857,6 +867,126 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrPara
                 }
                 return acc;
             });
+        }
+    }
+}
+
+// ---- the same merge as a walk down column strips ----------------------------------------------------------------------
+// The form above reads three value rows per output row (6 N vector loads + 6 N predicated end-lane loads per pixel pair)
+// and alternates between waiting for a chunk of loads and computing on it: loads alone 100 us at c1 size, arithmetic alone
+// ~95 us, 142 us together; prefetching, an asynchronous ring and more resident blocks all measured the same.  Here a warp
+// owns a strip of 60 output pixels and walks down a band of rows with the previous two value rows of every frame in
+// registers, so each value row is loaded once (4 N loads per pixel pair and row); lanes 0 and 31 of the warp hold the
+// strip's halo pixel pairs and produce no output, so the neighbour column sums always come from the adjacent lanes and
+// there are no end-lane loads or selects; and the loads of row r + 1 are issued before the arithmetic of row r.
+// kStripPix = 60: 1920 = 32 strips exactly.  Measured (1080p RGB): 3 frames 85 -> 67 us, 4 frames 127 -> 88 us, 5 frames (c1) 143 ->
+// 116 us = 0.72 of the roofline of its four input stacks; 5 x 4K 593 -> 433 us.
+constexpr int kStripPix = 60;
+constexpr int kMaxStripFrames = 5;     // 128 registers at 5 frames; more frames spill the row windows
+
+template <int NF, bool SINGLE>
+__global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_strip_kernel(const HdrParams p) {
+    constexpr int VEC = 2;
+    static_assert(NF > 1 && NF <= kMaxStripFrames, "the strip walk is the packed multi-frame kernel for a few frames");
+    extern __shared__ float2 s_tab[];
+    const int C = p.n_channels, L = p.lut;
+    const bool has_model = p.theta != nullptr;
+    if (has_model) stage_curve_slopes(s_tab, p.theta, C, L);
+    __syncthreads();
+    const int c = blockIdx.y;
+    const int64_t frame_stride = static_cast<int64_t>(C) * p.stride;
+    const float lm1 = static_cast<float>(L - 1);
+    const bool gaussian = p.gaussian != 0;
+    const int W = p.dg.W, H = p.dg.H, R = p.dark_rows;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t strips = static_cast<uint32_t>((W + kStripPix - 1) / kStripPix), bands = static_cast<uint32_t>((H + R - 1) / R);
+    const uint32_t n_tasks = strips * bands;
+    const uint32_t tab_bias = curve_row_bias(s_tab);
+    const uint32_t row_bytes = static_cast<uint32_t>(L) * 8u;
+    const uint32_t uC = static_cast<uint32_t>(C);
+    const float *val_c = static_cast<const float *>(p.val) + static_cast<int64_t>(c) * p.stride;
+    const float *std_c = p.std + static_cast<int64_t>(c) * p.stride;
+    const float *dark_c = p.dark + static_cast<int64_t>(c) * p.stride;
+    const float *dstd_c = p.dark_std + static_cast<int64_t>(c) * p.stride;
+    constexpr float t0 = blur_tap(0), t1 = blur_tap(1);
+    auto ld = [](const float *q, bool on) { return on ? __ldcs(reinterpret_cast<const unsigned long long *>(q)) : 0ull; };
+
+    for (uint32_t task = blockIdx.x * (kBlock / 32) + warp; task < n_tasks; task += gridDim.x * (kBlock / 32)) {
+        const uint32_t band = task / strips, strip = task - band * strips;
+        const int col = static_cast<int>(strip) * kStripPix - 2 + 2 * static_cast<int>(lane);     // the lane's pixel pair (W is even)
+        const bool in_row = col >= 0 && col < W;
+        const bool owner = in_row && lane >= 1u && lane <= 30u;
+        const bool wrap_l = col == 0, wrap_r = col + 2 == W;          // x[-1] = x[1], x[W] = x[W-2]
+        const int r_first = static_cast<int>(band) * R, r_end = min(r_first + R, H);
+        const uint32_t at0 = static_cast<uint32_t>(in_row ? col : 0);
+        // the two value rows above the first output row (reflect padding) of every frame, and the first row's other inputs
+        f32x2 above[NF], here[NF], below[NF], sv[NF], dk[NF], ds[NF];
+        {
+            const uint32_t ra = static_cast<uint32_t>(r_first == 0 ? 1 : r_first - 1) * W + at0, rh = static_cast<uint32_t>(r_first) * W + at0;
+            const uint32_t rb = static_cast<uint32_t>(r_first == H - 1 ? H - 2 : r_first + 1) * W + at0;
+#pragma unroll
+            for (int n = 0; n < NF; ++n) {
+                const int64_t fo = static_cast<int64_t>(n) * frame_stride;
+                above[n] = ld(val_c + fo + ra, in_row);
+                here[n] = ld(val_c + fo + rh, in_row);
+                below[n] = ld(val_c + fo + rb, in_row);
+                sv[n] = ld(std_c + fo + rh, in_row);
+                dk[n] = ld(dark_c + fo + rh, in_row);
+                ds[n] = ld(dstd_c + fo + rh, in_row);
+            }
+        }
+        uint32_t u_row = (static_cast<uint32_t>(r_first) * W + at0 + static_cast<uint32_t>(p.rows.base(c))) % uC;   // table row of the pair's first pixel
+        const uint32_t du_row = static_cast<uint32_t>(W) % uC;
+        for (int r = r_first; r < r_end; ++r) {
+            // next row's inputs go out before this row's arithmetic (nothing is loaded past the band's last row)
+            const bool more = in_row && r + 1 < r_end;
+            f32x2 nbelow[NF], nsv[NF], ndk[NF], nds[NF];
+            {
+                const uint32_t rn = static_cast<uint32_t>(r + 1) * W + at0;
+                const uint32_t rb = static_cast<uint32_t>(r + 2 >= H ? (r + 2 == H ? H - 2 : H - 1) : r + 2) * W + at0;
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    const int64_t fo = static_cast<int64_t>(n) * frame_stride;
+                    nbelow[n] = ld(val_c + fo + rb, more);
+                    nsv[n] = ld(std_c + fo + rn, more);
+                    ndk[n] = ld(dark_c + fo + rn, more);
+                    nds[n] = ld(dstd_c + fo + rn, more);
+                }
+            }
+            uint32_t bias[VEC];
+            bias[0] = tab_bias + u_row * row_bytes;
+            bias[1] = tab_bias + ((u_row + 1u == uC) ? 0u : u_row + 1u) * row_bytes;
+            f32x2 wsum2 = 0ull, wv2 = 0ull, R2[NF], Q2[NF];
+#pragma unroll
+            for (int n = 0; n < NF; ++n) {
+                // separable blur (clair_dark.cuh): column sums of the lane's two pixels, the neighbours' from the adjacent lanes
+                const f32x2 v2 = fma2(splat2(t0), add2(above[n], below[n]), mul2(splat2(t1), here[n]));
+                float v_lo, v_hi;
+                unpack2(v2, v_lo, v_hi);
+                float left = __shfl_up_sync(0xffffffffu, v_hi, 1), right = __shfl_down_sync(0xffffffffu, v_lo, 1);
+                left = wrap_l ? v_hi : left;
+                right = wrap_r ? v_lo : right;
+                const f32x2 blur2 = fma2(splat2(t0), add2(pack2(left, v_lo), pack2(v_hi, right)), mul2(splat2(t1), v2));
+                f32x2 xm2, sm2;
+                dark_mix_value2<true>(here[n], blur2, sv[n], dk[n], ds[n], p.dg, xm2, sm2);
+                float xm[VEC], sm[VEC];
+                unpack2(xm2, xm[0], xm[1]);
+                unpack2(sm2, sm[0], sm[1]);
+                const HdrTerms2 t = hdr_terms2(xm[0], xm[1], sm[0], sm[1], p.scale.inv_t[n], has_model, gaussian, bias[0], bias[1], lm1, true);
+                wsum2 = add2(wsum2, t.w);
+                wv2 = fma2(t.w, t.v, wv2);
+                R2[n] = t.R;
+                Q2[n] = t.Q;
+            }
+            if (owner)
+                dark_finish_pair<NF, SINGLE>(p, static_cast<int64_t>(c) * p.stride + static_cast<int64_t>(r) * W + col, wsum2, wv2, R2, Q2);
+#pragma unroll
+            for (int n = 0; n < NF; ++n) {
+                above[n] = here[n]; here[n] = below[n]; below[n] = nbelow[n];
+                sv[n] = nsv[n]; dk[n] = ndk[n]; ds[n] = nds[n];
+            }
+            u_row += du_row;
+            u_row = (u_row >= uC) ? u_row - uC : u_row;
         }
     }
 }

@@ -675,11 +675,32 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         p.dg = DarkGeometry{dark.height, dark.width, dark.threshold, dark.alpha, -dark.alpha * 1.4426950408889634f};
         const size_t smem = theta_dev ? sizeof(float2) * n_channels * lut_size : 0;
         const bool single = is_first && is_final;
-        const int64_t want_blocks = (plane / 2 + kBlock - 1) / kBlock;
+        // several frames: a warp walks down a strip of 60 pixels, band by band (hdr_merge_dark_strip_kernel; dark_strip = -1: the
+        // grid-stride form with chunked loads)
+        // (2..5 frames; from 6 frames on the walk's register windows spill: 6 x 1080p 185 us against 159 us)
+        const bool strip = n_frames > 1 && n_frames <= kMaxStripFrames && g_tuning.dark_strip >= 0;
         auto launch_dark = [&](auto kernel) -> int {
             if (int rc = ensure_smem(kernel, smem)) return rc;
             int per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, smem);
+            int64_t want_blocks = (plane / 2 + kBlock - 1) / kBlock;
+            if (strip) {
+                // Rows per band: a warp's task is one (strip, band); the launch takes ceil(tasks / resident warps) rounds of
+                // R + 1 row steps (the band's first step loads three value rows), so R is chosen to fill the last round
+                // (measured at c1 size: 45 rows = 2304 tasks on 2368 warps 116 us; 16 rows = 2.76 rounds 145 us; 12 rows 126 us)
+                const int64_t strips = (dark.width + kStripPix - 1) / kStripPix;
+                const int64_t slots = std::max<int64_t>(1, resident_blocks_per_channel(std::max(per_sm, 1), n_channels)) * (kBlock / 32);
+                int best_rows = 8;
+                int64_t best_cost = -1;
+                for (int rows = 6; rows <= 128; ++rows) {
+                    const int64_t tasks = strips * ((dark.height + rows - 1) / rows);
+                    const int64_t cost = ((tasks + slots - 1) / slots) * (rows + 1);
+                    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_rows = rows; }
+                }
+                p.dark_rows = g_tuning.dark_rows > 0 ? g_tuning.dark_rows : best_rows;
+                const int64_t tasks = strips * ((dark.height + p.dark_rows - 1) / p.dark_rows);
+                want_blocks = (tasks + kBlock / 32 - 1) / (kBlock / 32);
+            }
             per_sm = std::max(per_sm, 1) * (g_tuning.hdr_waves > 0 ? g_tuning.hdr_waves : 2);
             const int64_t gx = std::max<int64_t>(1, std::min<int64_t>(want_blocks, resident_blocks_per_channel(per_sm, n_channels)));
             kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), kBlock, smem, s>>>(p);
@@ -687,16 +708,20 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         };
         int rc = 0;
 #define DARK_NF(NF) rc = single ? launch_dark(hdr_merge_dark_kernel<NF, true>) : launch_dark(hdr_merge_dark_kernel<NF, false>)
+#define DARK_STRIP(NF) \
+    if (strip) rc = single ? launch_dark(hdr_merge_dark_strip_kernel<NF, true>) : launch_dark(hdr_merge_dark_strip_kernel<NF, false>); \
+    else DARK_NF(NF)
         switch (n_frames) {
             case 1: DARK_NF(1); break;
-            case 2: DARK_NF(2); break;
-            case 3: DARK_NF(3); break;
-            case 4: DARK_NF(4); break;
-            case 5: DARK_NF(5); break;
+            case 2: DARK_STRIP(2); break;
+            case 3: DARK_STRIP(3); break;
+            case 4: DARK_STRIP(4); break;
+            case 5: DARK_STRIP(5); break;
             case 6: DARK_NF(6); break;
             case 7: DARK_NF(7); break;
             default: DARK_NF(8); break;
         }
+#undef DARK_STRIP
 #undef DARK_NF
         if (rc) return rc;
         return launched("hdr_merge_dark_kernel");

@@ -57,7 +57,7 @@ CLAIR_API const char *clair_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 CLAIR_API uint64_t clair_launch_count(void);
 
-/* developer knob for kernel tuning experiments (keys: hdr_vec, hdr_waves, hdr_force_dynamic, hdr_fixed_max, hdr_prefetch, hdr_tma, fwd_blocks, aux_waves, stats_waves, grad_waves,
+/* developer knob for kernel tuning experiments (keys: hdr_vec, hdr_waves, hdr_force_dynamic, hdr_fixed_max, hdr_prefetch, hdr_tma, fwd_blocks, dark_strip, dark_rows, aux_waves, stats_waves, grad_waves,
  * stats_blocks_per_sm, stats_warps, stats_slots, stats_buffers, grad_blocks_per_sm, grad_pix, grad_warps, grad_copies); 0 restores the
  * library default.  Not part of the reference boundary. */
 CLAIR_API int clair_set_tuning(const char *key, int value);

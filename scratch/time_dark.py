@@ -9,7 +9,7 @@ lib = ct._native.load()
 for item in filter(None, os.environ.get("CLAIR_TUNE", "").split(",")):
     k, _, v = item.partition("=")
     ct._native.check(lib.clair_set_tuning(k.encode(), int(v)), "tune")
-N, C, H, W = 5, 3, 1080, 1920
+N, C, H, W = (int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "5x3x1080x1920").split("x"))
 sets = []
 for k in range(3):
     val, std, t = ct.synthetic.make_stack(N, C, H, W, bits=8, seed=10 + k, device=dev)
@@ -32,4 +32,4 @@ def prepass(k):
     v, s, d, ds = sets[k % 3]
     kernels.dark_field_mix(v, s, d, ds)
 for r in range(2):
-    print(f"fused dark merge {timed(fused)*1e3:.1f} us   dark pre-pass {timed(prepass)*1e3:.1f} us", flush=True)
+    print(f"{N}x{C}x{H}x{W}: fused dark merge {timed(fused)*1e3:.1f} us   dark pre-pass {timed(prepass)*1e3:.1f} us", flush=True)
