@@ -989,6 +989,9 @@ __device__ __forceinline__ float rcp_1ulp(float x) {     // MUFU.RCP + one Newto
 // accumulators and no mode dispatch: 94 -> 40 registers, and the four running-state loads are issued with the frame
 // loads instead of after them.  Quotients go through a 1-ulp reciprocal (the IEEE divisions were ~60 of the epilogue's
 // instructions per pixel).
+#ifndef STATS_CHUNK
+#define STATS_CHUNK 6
+#endif
 template <int VEC, bool WEIGHTED, bool MODES>
 __global__ void __launch_bounds__(kBlock, WEIGHTED ? 2 : 4) frame_stats_kernel(const FrameStatsParams p) {
     extern __shared__ float2 s_tab[];
@@ -1010,6 +1013,8 @@ __global__ void __launch_bounds__(kBlock, WEIGHTED ? 2 : 4) frame_stats_kernel(c
     const int N = p.n_frames;
     const bool first = p.is_first != 0;
     const float n_f = static_cast<float>(N);
+    // frames whose loads are in flight together: unweighted batches of up to 6 frames (a video burst, c1's 5) in ONE chunk
+    constexpr int kChunk = WEIGHTED ? kFrameChunk : STATS_CHUNK;
 
     for (uint32_t item = first_item; item < n_items; item += item_stride, cur.advance()) {
         const uint32_t pix = item * VEC;
@@ -1029,10 +1034,10 @@ __global__ void __launch_bounds__(kBlock, WEIGHTED ? 2 : 4) frame_stats_kernel(c
         float w0[VEC], w2[VEC], s1[VEC], s2[VEC], pivot[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) { w0[k] = 0.0f; w2[k] = 0.0f; s1[k] = 0.0f; s2[k] = 0.0f; pivot[k] = 0.0f; }
-        for (int n0 = 0; n0 < N; n0 += kFrameChunk) {
-            Pack<VEC> xv[kFrameChunk], wv[kFrameChunk];
+        for (int n0 = 0; n0 < N; n0 += kChunk) {
+            Pack<VEC> xv[kChunk], wv[kChunk];
 #pragma unroll
-            for (int j = 0; j < kFrameChunk; ++j) {
+            for (int j = 0; j < kChunk; ++j) {
                 if (n0 + j < N) {
                     const int64_t o = off + static_cast<int64_t>(n0 + j) * frame_stride;
                     xv[j] = load_stream<VEC>(p.val + o);
@@ -1040,7 +1045,7 @@ __global__ void __launch_bounds__(kBlock, WEIGHTED ? 2 : 4) frame_stats_kernel(c
                 }
             }
 #pragma unroll
-            for (int j = 0; j < kFrameChunk; ++j) {
+            for (int j = 0; j < kChunk; ++j) {
                 if (n0 + j < N) {
 #pragma unroll
                     for (int k = 0; k < VEC; ++k) {
