@@ -880,14 +880,17 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_kernel(const HdrPara
 // strip's halo pixel pairs and produce no output, so the neighbour column sums always come from the adjacent lanes and
 // there are no end-lane loads or selects; and the loads of row r + 1 are issued before the arithmetic of row r.
 // kStripPix = 60: 1920 = 32 strips exactly.  Measured (1080p RGB): 3 frames 85 -> 67 us, 4 frames 127 -> 88 us, 5 frames (c1) 143 ->
-// 116 us = 0.72 of the roofline of its four input stacks; 5 x 4K 593 -> 433 us.
+// 116 us = 0.72 of the roofline of its four input stacks; 5 x 4K 593 -> 433 us; 6 / 7 / 8 frames (no prefetch set) 159 -> 135,
+// 194 -> 156, 211 -> 176 us.
 constexpr int kStripPix = 60;
-constexpr int kMaxStripFrames = 5;     // 128 registers at 5 frames; more frames spill the row windows
+constexpr int kMaxStripFrames = 5;     // most frames whose NEXT row is prefetched into registers (128 registers at 5 frames)
 
-template <int NF, bool SINGLE>
+// PIPE: next row's inputs in a second register set (2..5 frames); without it (6..8 frames) a row's own inputs are loaded at its
+// start, all frames at once, and only the two-row value window persists
+template <int NF, bool SINGLE, bool PIPE = (NF <= kMaxStripFrames)>
 __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_strip_kernel(const HdrParams p) {
     constexpr int VEC = 2;
-    static_assert(NF > 1 && NF <= kMaxStripFrames, "the strip walk is the packed multi-frame kernel for a few frames");
+    static_assert(NF > 1, "the strip walk is the packed multi-frame kernel");
     extern __shared__ float2 s_tab[];
     const int C = p.n_channels, L = p.lut;
     const bool has_model = p.theta != nullptr;
@@ -929,10 +932,12 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_strip_kernel(const H
                 const int64_t fo = static_cast<int64_t>(n) * frame_stride;
                 above[n] = ld(val_c + fo + ra, in_row);
                 here[n] = ld(val_c + fo + rh, in_row);
-                below[n] = ld(val_c + fo + rb, in_row);
-                sv[n] = ld(std_c + fo + rh, in_row);
-                dk[n] = ld(dark_c + fo + rh, in_row);
-                ds[n] = ld(dstd_c + fo + rh, in_row);
+                if constexpr (PIPE) {
+                    below[n] = ld(val_c + fo + rb, in_row);
+                    sv[n] = ld(std_c + fo + rh, in_row);
+                    dk[n] = ld(dark_c + fo + rh, in_row);
+                    ds[n] = ld(dstd_c + fo + rh, in_row);
+                }
             }
         }
         uint32_t u_row = (static_cast<uint32_t>(r_first) * W + at0 + static_cast<uint32_t>(p.rows.base(c))) % uC;   // table row of the pair's first pixel
@@ -940,8 +945,8 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_strip_kernel(const H
         for (int r = r_first; r < r_end; ++r) {
             // next row's inputs go out before this row's arithmetic (nothing is loaded past the band's last row)
             const bool more = in_row && r + 1 < r_end;
-            f32x2 nbelow[NF], nsv[NF], ndk[NF], nds[NF];
-            {
+            f32x2 nbelow[PIPE ? NF : 1], nsv[PIPE ? NF : 1], ndk[PIPE ? NF : 1], nds[PIPE ? NF : 1];
+            if constexpr (PIPE) {
                 const uint32_t rn = static_cast<uint32_t>(r + 1) * W + at0;
                 const uint32_t rb = static_cast<uint32_t>(r + 2 >= H ? (r + 2 == H ? H - 2 : H - 1) : r + 2) * W + at0;
 #pragma unroll
@@ -951,6 +956,17 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_strip_kernel(const H
                     nsv[n] = ld(std_c + fo + rn, more);
                     ndk[n] = ld(dark_c + fo + rn, more);
                     nds[n] = ld(dstd_c + fo + rn, more);
+                }
+            } else {
+                const uint32_t rh = static_cast<uint32_t>(r) * W + at0;
+                const uint32_t rb = static_cast<uint32_t>(r + 1 == H ? H - 2 : r + 1) * W + at0;
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    const int64_t fo = static_cast<int64_t>(n) * frame_stride;
+                    below[n] = ld(val_c + fo + rb, in_row);
+                    sv[n] = ld(std_c + fo + rh, in_row);
+                    dk[n] = ld(dark_c + fo + rh, in_row);
+                    ds[n] = ld(dstd_c + fo + rh, in_row);
                 }
             }
             uint32_t bias[VEC];
@@ -982,8 +998,8 @@ __global__ void __launch_bounds__(kBlock, 2) hdr_merge_dark_strip_kernel(const H
                 dark_finish_pair<NF, SINGLE>(p, static_cast<int64_t>(c) * p.stride + static_cast<int64_t>(r) * W + col, wsum2, wv2, R2, Q2);
 #pragma unroll
             for (int n = 0; n < NF; ++n) {
-                above[n] = here[n]; here[n] = below[n]; below[n] = nbelow[n];
-                sv[n] = nsv[n]; dk[n] = ndk[n]; ds[n] = nds[n];
+                above[n] = here[n]; here[n] = below[n];
+                if constexpr (PIPE) { below[n] = nbelow[n]; sv[n] = nsv[n]; dk[n] = ndk[n]; ds[n] = nds[n]; }
             }
             u_row += du_row;
             u_row = (u_row >= uC) ? u_row - uC : u_row;

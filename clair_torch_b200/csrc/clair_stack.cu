@@ -677,8 +677,8 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
         const bool single = is_first && is_final;
         // several frames: a warp walks down a strip of 60 pixels, band by band (hdr_merge_dark_strip_kernel; dark_strip = -1: the
         // grid-stride form with chunked loads)
-        // (2..5 frames; from 6 frames on the walk's register windows spill: 6 x 1080p 185 us against 159 us)
-        const bool strip = n_frames > 1 && n_frames <= kMaxStripFrames && g_tuning.dark_strip >= 0;
+        // (2..5 frames with the next row's inputs in a second register set; 6..8 frames without it — there the windows would spill)
+        const bool strip = n_frames > 1 && g_tuning.dark_strip >= 0;
         auto launch_dark = [&](auto kernel) -> int {
             if (int rc = ensure_smem(kernel, smem)) return rc;
             int per_sm = 1;
@@ -717,9 +717,9 @@ int hdr_merge_impl(const char *fn, const void *val_dev, int src, float code_max,
             case 3: DARK_STRIP(3); break;
             case 4: DARK_STRIP(4); break;
             case 5: DARK_STRIP(5); break;
-            case 6: DARK_NF(6); break;
-            case 7: DARK_NF(7); break;
-            default: DARK_NF(8); break;
+            case 6: DARK_STRIP(6); break;
+            case 7: DARK_STRIP(7); break;
+            default: DARK_STRIP(8); break;
         }
 #undef DARK_STRIP
 #undef DARK_NF
