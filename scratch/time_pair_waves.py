@@ -16,7 +16,7 @@ def timed(fn, reps=10):
     return a.elapsed_time(b) / reps
 shapes = {"c2": (10, 1080, 1920, 8, 2345, 0.25), "c3": (16, 2160, 3840, 16, 3456, 0.2), "c5": (2, 8192, 12288, 16, 5678, 0.25),
           "c5/8": (2, 1024, 12288, 16, 5678, 0.25)}
-knobs = (1, 2, 3, 4, 6, 8)
+knobs = (1, 2, 3, 4, 6, 8)[:int(os.environ.get('N_KNOBS', '6'))]
 for name in sys.argv[1:] or list(shapes):
     n, h, w, bits, seed, thr = shapes[name]
     val, std, t = ct.synthetic.make_stack(n, 3, h, w, bits=bits, seed=seed, device=dev)
@@ -24,8 +24,8 @@ for name in sys.argv[1:] or list(shapes):
     sums = kernels.pair_stats(val, std, i, j, r, theta, 1 / 255, 254 / 255, True, False, means_only=True)
     _, _, up, mg = kernels.pair_upstream(sums)
     res = {}
-    for rnd in range(3):
-        for k in knobs:
+    for rnd in range(6):
+        for k in knobs[rnd % len(knobs):] + knobs[:rnd % len(knobs)]:      # order rotated: the power state drifts within a round
             ct._native.check(lib.clair_set_tuning(b"stats_waves", k), "tune")
             ct._native.check(lib.clair_set_tuning(b"grad_waves", k), "tune")
             full = timed(lambda: kernels.pair_stats(val, std, i, j, r, theta, 1 / 255, 254 / 255, True, True))
@@ -34,7 +34,7 @@ for name in sys.argv[1:] or list(shapes):
             fused = timed(lambda: kernels.pair_fused(val, i, j, r, theta, 1 / 255, 254 / 255, True), 20) if len(i) == 1 else float("nan")
             res.setdefault(k, []).append((full, means, grad, fused))
     for k in knobs:
-        med = [sorted(v[q] for v in res[k])[1] for q in range(4)]
+        med = [sorted(v[q] for v in res[k])[len(res[k]) // 2] for q in range(4)]
         print(f"{name:5s} waves={k}: stats {med[0]:.3f}  means {med[1]:.3f}  grad {med[2]:.3f}  fused {med[3]:.3f} ms", flush=True)
     del val, std
     torch.cuda.empty_cache()
