@@ -1810,11 +1810,14 @@ extern "C" int clair_pair_grad(const float *val_dev, const float *std_dev, int n
             if (int rc = set_smem(kernel, smem)) return rc;
             int per_sm = 1;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
-            per_sm = g_tuning.grad_blocks_per_sm > 0 ? g_tuning.grad_blocks_per_sm : std::max(per_sm, 1);
-        // (the single-pass kernel is fastest on exactly the resident blocks: c5 2.47 ms, 3.1 ms at 2 x)
-            // one or two pairs (little work per trip): 3 x the resident blocks (c5 2.59 -> 2.30 ms, an eighth of it 0.41 -> 0.31 ms);
-            // many pairs are fastest on exactly the resident blocks (c2 0.340 ms, 0.361 ms at 3 x)
-            per_sm *= g_tuning.grad_waves > 0 ? g_tuning.grad_waves : (count <= 2 ? 3 : 1);
+            // The kernel is bound by L2 reductions and runs best at 6 blocks of 4 warps per SM, not at the 8 that fit (two boxes,
+        // blocks per SM 4 / 5 / 6 / 7 / 8 / 12: c5 2.95 / 2.62 / 2.41 / 2.65 / 2.76 / 3.09 ms; half / a quarter of c5 1.50 -> 1.21,
+        // 0.71 -> 0.62 ms; 8K 0.91 -> 0.79 ms; an eighth of c5 is flat from 6 to 8), and on exactly that many blocks (2 x: 3.1 ms).
+        per_sm = g_tuning.grad_blocks_per_sm > 0 ? g_tuning.grad_blocks_per_sm : std::min(std::max(per_sm, 1), 6);
+            // one or two pairs (little work per trip): 4 x the resident blocks (c5 over three boxes: 2.39 / 2.59 / 2.73 ms at 1 x,
+            // 2.37 / 2.26 / 2.32 ms at 4 x — the L2-reduction-bound kernel is erratic at 1 x .. 3 x; an eighth of c5 0.41 -> 0.32 ms);
+            // many pairs are fastest on exactly the resident blocks (c2 0.340 ms, 0.349 ms at 4 x)
+            per_sm *= g_tuning.grad_waves > 0 ? g_tuning.grad_waves : (count <= 2 ? 4 : 1);
             const int64_t gx = std::min<int64_t>((n_groups + warps - 1) / warps,
                                                  std::max<int64_t>(1, resident_blocks_per_channel(per_sm, n_channels)));
             kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), warps * 32, smem, s>>>(p);
@@ -1878,8 +1881,10 @@ extern "C" int clair_pair_fused(const float *val_dev, int n_frames, int n_channe
         if (int rc = set_smem(kernel, smem)) return rc;
         int per_sm = 1;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem);
-        per_sm = g_tuning.grad_blocks_per_sm > 0 ? g_tuning.grad_blocks_per_sm : std::max(per_sm, 1);
-        // (the single-pass kernel is fastest on exactly the resident blocks: c5 2.47 ms, 3.1 ms at 2 x)
+        // The kernel is bound by L2 reductions and runs best at 6 blocks of 4 warps per SM, not at the 8 that fit (two boxes,
+        // blocks per SM 4 / 5 / 6 / 7 / 8 / 12: c5 2.95 / 2.62 / 2.41 / 2.65 / 2.76 / 3.09 ms; half / a quarter of c5 1.50 -> 1.21,
+        // 0.71 -> 0.62 ms; 8K 0.91 -> 0.79 ms; an eighth of c5 is flat from 6 to 8), and on exactly that many blocks (2 x: 3.1 ms).
+        per_sm = g_tuning.grad_blocks_per_sm > 0 ? g_tuning.grad_blocks_per_sm : std::min(std::max(per_sm, 1), 6);
         const int64_t gx = std::min<int64_t>((n_groups + warps - 1) / warps, std::max<int64_t>(1, resident_blocks_per_channel(per_sm, n_channels)));
         kernel<<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(n_channels)), warps * 32, smem, s>>>(p);
         return 0;

@@ -15,7 +15,8 @@ def timed(fn, reps=10):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
 shapes = {"c2": (10, 1080, 1920, 8, 2345, 0.25), "c3": (16, 2160, 3840, 16, 3456, 0.2), "c5": (2, 8192, 12288, 16, 5678, 0.25),
-          "c5/8": (2, 1024, 12288, 16, 5678, 0.25)}
+          "c5/8": (2, 1024, 12288, 16, 5678, 0.25), "c5/2": (2, 4096, 12288, 16, 5678, 0.25), "c5/4": (2, 2048, 12288, 16, 5678, 0.25),
+          "8k": (2, 4320, 7680, 16, 99, 0.25), "4k8": (2, 2160, 3840, 8, 98, 0.25)}
 knobs = (1, 2, 3, 4, 6, 8)[:int(os.environ.get('N_KNOBS', '6'))]
 for name in sys.argv[1:] or list(shapes):
     n, h, w, bits, seed, thr = shapes[name]
