@@ -222,3 +222,47 @@ def test_lookup_and_forward_full_frame(ct):
     yl = kernels.icrf_forward(val, theta.to(DEV), ct._native.INTERP_LOOKUP)
     fl, _ = corc.icrf_lookup(val.cpu().numpy(), theta.numpy())
     assert np.array_equal(yl.cpu().numpy(), fl)
+
+
+def test_dark_corrected_c1_full_size(ct):
+    """Config 1 with a dark field.  The mix itself (pre-pass kernel) against the numpy oracle at full size; the merge that
+    mixes in its load (column-strip walk, rows per band chosen for the launch) against pre-pass + merge, which evaluates the
+    same fp32 expressions (an fp64 mix would put a few of the 31 M mixed values on the other side of a table sample, where
+    the slope f' — and with it sigma — jumps); bit for bit against itself at other band heights (the arithmetic per pixel
+    does not depend on the band); and against the grid-stride form of the same kernel.  Also three frames and seven frames
+    (no next-row register set) at odd sizes."""
+    from clair_torch_b200 import kernels
+    lib = ct._native.load()
+
+    def with_knobs(fn, **knobs):
+        try:
+            for key, value in knobs.items():
+                ct._native.check(lib.clair_set_tuning(key.encode(), value), "tune")
+            return fn()
+        finally:
+            for key in knobs:
+                lib.clair_set_tuning(key.encode(), 0)
+
+    for n, h, w in ((5, 1080, 1920), (3, 431, 614), (7, 257, 362)):
+        val, std, t = ct.synthetic.make_stack(n, 3, h, w, bits=16, seed=1234 + n, device=DEV)
+        gen = torch.Generator(device=DEV).manual_seed(n)
+        dark = torch.rand(val.shape, device=DEV, generator=gen) * 0.02
+        hot = torch.rand(val.shape, device=DEV, generator=gen) < 0.08
+        dark = torch.where(hot, 0.03 + 0.4 * torch.rand(val.shape, device=DEV, generator=gen), dark)
+        dark_std = 0.1 * dark + 1e-3
+        theta = ct.synthetic.reference_curve(3).to(DEV)
+        mixed, seff = kernels.dark_field_mix(val, std, dark, dark_std)
+        o_mixed, o_seff = orc.dark_field_mix(val.cpu().numpy(), std.cpu().numpy(), dark.cpu().numpy(), dark_std.cpu().numpy())
+        assert max_rel(mixed.cpu().numpy(), o_mixed, 1e-12) < 2e-6 and max_rel(seff.cpu().numpy(), o_seff, 1e-12) < TOL   # (B(x) - x cancels)
+        run = lambda: kernels.hdr_merge_update(kernels.HdrMergeState(), val, std, t, theta, True, True, radiance_dtype=torch.float32,
+                                               dark=(dark, dark_std))
+        rad, sig = run()
+        p_rad, p_sig = _merge(ct, mixed, seff, t, theta)
+        e_rad, e_sig = max_rel(rad.cpu().numpy(), p_rad.cpu().numpy()), max_rel(sig.cpu().numpy(), p_sig.cpu().numpy())
+        assert e_rad < 1e-6 and e_sig < 5e-6, (n, h, w, e_rad, e_sig)
+        for rows in (6, 17, 128):
+            r2, s2 = with_knobs(run, dark_rows=rows)
+            assert torch.equal(r2, rad) and torch.equal(s2, sig)
+        r3, s3 = with_knobs(run, dark_strip=-1)
+        e_rad, e_sig = max_rel(r3.cpu().numpy(), rad.cpu().numpy()), max_rel(s3.cpu().numpy(), sig.cpu().numpy())
+        assert e_rad < 1e-6 and e_sig < 5e-6, ("grid-stride form", n, h, w, e_rad, e_sig)
