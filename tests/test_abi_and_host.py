@@ -59,9 +59,13 @@ def test_argument_validation_without_gpu(native):
     with pytest.raises(ValueError):
         native.check(rc, "clair_icrf_forward")
     assert lib.clair_set_tuning(b"no_such_knob", 1) == -1
-    for key in (b"hdr_vec", b"hdr_waves", b"hdr_force_dynamic", b"hdr_fixed_max", b"hdr_prefetch", b"stats_blocks_per_sm", b"stats_warps",
-                b"stats_slots", b"grad_blocks_per_sm", b"grad_pix", b"grad_warps", b"grad_copies"):     # every key the header lists
-        assert lib.clair_set_tuning(key, 0) == 0, key
+    import re
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "clair_b200.h")).read()
+    listed = re.search(r"developer knob for kernel tuning experiments \(keys: ([^)]*)\)", header, re.S)
+    keys = [k.strip(" */\n") for k in listed.group(1).replace("\n", " ").split(",")]
+    assert {"hdr_waves", "stats_waves", "grad_waves", "aux_waves", "fwd_blocks", "dark_strip", "dark_rows"} <= set(keys)
+    for key in keys:                                                 # every key the header lists
+        assert lib.clair_set_tuning(key.encode(), 0) == 0, key
 
 
 def test_descriptor_entry_points_validate_without_gpu(native):
