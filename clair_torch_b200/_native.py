@@ -15,7 +15,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CLAIR_B200_LIB") or os.path.join(_PKG_DIR, "lib", "libclair_b200.so")   # env: kernel experiments
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_FRAMES = 64
 MAX_CHANNELS = 8
 MAX_LUT = 1024
@@ -93,6 +93,7 @@ _PROTOTYPES = {
                                    _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "clair_expand_codes": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_float, _c.c_int, _c.c_float, _c.c_int64, _c.c_void_p, _c.c_void_p,
                                       _c.c_void_p]),
+    "clair_copy_band_h2d": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_void_p]),
     "clair_pair_fused_doubles": (_c.c_size_t, [_c.c_int, _c.c_int]),
     "clair_pair_fused": (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                     _c.c_void_p, _c.c_int, _c.c_int, _c.c_void_p, _c.c_float, _c.c_float, _c.c_int, _c.c_void_p,

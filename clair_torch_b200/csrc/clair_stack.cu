@@ -479,6 +479,18 @@ __global__ void __launch_bounds__(kBlock) expand_codes_kernel(const void *__rest
 }
 }  // namespace clair
 
+extern "C" int clair_copy_band_h2d(void *dst_dev, const void *src_host, int64_t n_slabs, int64_t slab_stride_bytes,
+                                   int64_t band_offset_bytes, int64_t band_bytes, void *stream) {
+    if (!dst_dev || !src_host) return fail(CLAIR_E_ARG, "clair_copy_band_h2d: null buffer");
+    if (n_slabs <= 0 || band_bytes <= 0 || band_offset_bytes < 0 || band_offset_bytes + band_bytes > slab_stride_bytes)
+        return fail(CLAIR_E_ARG, "clair_copy_band_h2d: the band must lie inside a slab");
+    const cudaError_t e = cudaMemcpy2DAsync(dst_dev, static_cast<size_t>(band_bytes), static_cast<const char *>(src_host) + band_offset_bytes,
+                                            static_cast<size_t>(slab_stride_bytes), static_cast<size_t>(band_bytes),
+                                            static_cast<size_t>(n_slabs), cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "cudaMemcpy2DAsync(band)");
+    return 0;
+}
+
 extern "C" int clair_expand_codes(const void *codes_dev, int code_bytes, float code_max, int std_mode, float std_value,
                                   int64_t n_elements, float *val_dev, float *std_dev, void *stream) {
     NvtxRange nvtx_range_("clair_expand_codes");

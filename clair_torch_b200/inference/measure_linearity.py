@@ -49,11 +49,71 @@ def measure_linearity(dataloader: DataLoader, device, use_uncertainty_weighting:
     dev = as_device(device)
     table, interp_mode = model_table(icrf_model, dev)          # any InterpMode: the kernels evaluate all three
     for _, val_batch, std_batch, meta_batch in dataloader:
-        images, stds = stage_batch(val_batch, std_batch, dev, code_max=code_max, expand_codes=True)
         exposures = meta_batch["exposure_time"]
         i_idx, j_idx, ratio_pairs = get_valid_exposure_pairs(exposures, RATIO_THRESHOLD)
-        sums = kernels.pair_stats(images, stds, i_idx, j_idx, ratio_pairs, table, VALID_LO, VALID_HI,
-                                  use_relative_linearity_loss, use_uncertainty_weighting, interp_mode=interp_mode)
-        mean, std, errmean = spatial_statistics(sums, stds is not None)
+        bands = _code_bands(val_batch, std_batch)
+        if bands:
+            sums, with_errors = _banded_code_statistics(val_batch, std_batch, bands, dev, code_max, i_idx, j_idx, ratio_pairs, table,
+                                                        use_relative_linearity_loss, use_uncertainty_weighting, interp_mode)
+        else:
+            images, stds = stage_batch(val_batch, std_batch, dev, code_max=code_max, expand_codes=True)
+            sums = kernels.pair_stats(images, stds, i_idx, j_idx, ratio_pairs, table, VALID_LO, VALID_HI,
+                                      use_relative_linearity_loss, use_uncertainty_weighting, interp_mode=interp_mode)
+            with_errors = stds is not None
+        mean, std, errmean = spatial_statistics(sums, with_errors)
         return ratio_pairs.to(dev), mean, std, errmean
     raise ValueError("the dataloader yielded no batches")
+
+
+_BAND_MIN_BYTES = 64 << 20      # below this the copy is too short to be worth cutting up
+
+
+def _code_bands(val_batch, std_batch) -> int:
+    """Number of row bands a page-locked uint8 / uint16 code batch (std: a StdSpec or none) is cut into so that its copy to the
+    device overlaps the expansion + statistics of the bands already there; 0 = take the batch whole."""
+    if not (torch.is_tensor(val_batch) and val_batch.dtype in (torch.uint8, torch.uint16) and val_batch.dim() == 4
+            and not val_batch.is_cuda and val_batch.is_pinned() and val_batch.is_contiguous()):
+        return 0
+    if torch.is_tensor(std_batch) or val_batch.numel() * val_batch.element_size() < _BAND_MIN_BYTES:
+        return 0
+    h, w = val_batch.shape[-2:]
+    for bands in (8, 6, 5, 4, 3, 2):
+        if h % bands == 0 and ((h // bands) * w) % 4 == 0:
+            return bands
+    return 0
+
+
+def _banded_code_statistics(codes, std_spec, bands, dev, code_max, i_idx, j_idx, ratio_pairs, table, relative, unc_weighting, interp_mode):
+    """measure_linearity.py:41-72 for a page-locked code batch, pipelined: while band b is expanded (CastTo + Normalize + std
+    synthesis) and its pair sums are accumulated, band b+1 crosses PCIe on a second stream (one strided copy per band,
+    clair_copy_band_h2d; the stream is synchronised with the copies before the batch is let go).  The statistics kernel accumulates into
+    the same (P, C, 5) sums with the band's table-row base, so the result is the whole-image one up to summation order."""
+    n, c, h, w = codes.shape
+    rows = h // bands
+    main = torch.cuda.current_stream(dev)
+    copier = torch.cuda.Stream(dev)
+    staging = [torch.empty((n, c, rows, w), dtype=codes.dtype, device=dev) for _ in range(2)]
+    landed = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    sums = torch.zeros((len(i_idx), c, 5), dtype=torch.float64, device=dev)
+    copier.wait_stream(main)
+    with_errors = False
+    for b in range(bands):
+        k, r0 = b % 2, b * rows
+        with torch.cuda.stream(copier):
+            if b >= 2:
+                copier.wait_event(consumed[k])
+            kernels.copy_band_to_device(staging[k], codes, r0, copier)
+            landed[k].record(copier)
+        main.wait_event(landed[k])
+        images, stds = kernels.expand_codes(staging[k], std_spec, code_max, dev)
+        with_errors = stds is not None
+        kernels.pair_stats(images, stds, i_idx, j_idx, ratio_pairs, table, VALID_LO, VALID_HI, relative, unc_weighting,
+                           row_base=kernels.shard_row_base(c, h, w, r0), out=sums, interp_mode=interp_mode)
+        consumed[k].record(main)
+    for buf in staging:
+        buf.record_stream(copier)
+    # the copies read the pinned batch through a raw pointer: hold it until the last one has landed (the caller's loop variable
+    # is the only other reference; the sums are read back by the caller right after anyway)
+    landed[(bands - 1) % 2].synchronize()
+    return sums, with_errors

@@ -207,6 +207,23 @@ def _linearize_codes(lib, val, std, theta, row_base, device, pinned_out, interp_
     return lin, sigma
 
 
+def copy_band_to_device(dst: torch.Tensor, src_host: torch.Tensor, first_row: int, stream: torch.cuda.Stream) -> None:
+    """Rows [first_row, first_row + dst.shape[-2]) of every (frame, channel) slab of the page-locked (N, C, H, W) host stack into
+    the dense device buffer `dst` (N, C, rows, W), as one strided copy on `stream` (clair_copy_band_h2d).  The caller keeps
+    `src_host` alive until the stream has passed the copy."""
+    lib = _native.load()
+    n, c, h, w = src_host.shape
+    rows = dst.shape[-2]
+    if not (src_host.is_pinned() and src_host.is_contiguous() and dst.is_cuda and dst.is_contiguous() and dst.dtype == src_host.dtype
+            and tuple(dst.shape) == (n, c, rows, w) and 0 <= first_row and first_row + rows <= h):
+        raise ValueError("copy_band_to_device: a contiguous page-locked (N, C, H, W) source and a dense (N, C, rows, W) device band")
+    size = src_host.element_size()
+    with torch.cuda.device(dst.device):
+        rc = lib.clair_copy_band_h2d(_ptr(dst), _ptr(src_host), n * c, h * w * size, first_row * w * size, rows * w * size,
+                                     ctypes.c_void_p(stream.cuda_stream))
+    _native.check(rc, "clair_copy_band_h2d")
+
+
 def expand_codes(codes: torch.Tensor, std=None, code_max=None, device=None):
     """(fp32 value stack, fp32 std stack | None) from uint8 / uint16 camera codes: CastTo(float32) + Normalize(max_val=code_max)
     and, for a `datasets.StdSpec`, the synthesised std, evaluated on the device (clair_expand_codes; bit-identical to the

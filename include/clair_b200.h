@@ -37,7 +37,7 @@ extern "C" {
 #define CLAIR_API
 #endif
 
-#define CLAIR_ABI_VERSION 3
+#define CLAIR_ABI_VERSION 4
 #define CLAIR_MAX_FRAMES 64     /* exposure frames per batch (exposure times travel as kernel arguments) */
 #define CLAIR_MAX_CHANNELS 8
 #define CLAIR_MAX_LUT 1024      /* ICRF samples per channel (reference default 256) */
@@ -124,6 +124,17 @@ CLAIR_API int clair_linearize_codes(const void *codes_dev, int code_bytes, float
  */
 CLAIR_API int clair_expand_codes(const void *codes_dev, int code_bytes, float code_max, int std_mode, float std_value,
                        int64_t n_elements, float *val_dev, float *std_dev, void *stream);
+
+/*
+ * One band of every (frame, channel) slab of a page-locked HOST stack to a dense device buffer, as ONE strided copy
+ * (cudaMemcpy2DAsync): the collated batch's .to(device) (inference/measure_linearity.py:41-43) cut into row bands, so that
+ * the copy of band b+1 overlaps clair_expand_codes + clair_pair_stats on band b (clair_torch_b200.measure_linearity does
+ * that for page-locked code batches).  Byte counts, so any sample type.
+ *   dst_dev            n_slabs x band_bytes, dense
+ *   src_host           n_slabs slabs of slab_stride_bytes each; the band starts band_offset_bytes into every slab
+ */
+CLAIR_API int clair_copy_band_h2d(void *dst_dev, const void *src_host, int64_t n_slabs, int64_t slab_stride_bytes,
+                                  int64_t band_offset_bytes, int64_t band_bytes, void *stream);
 
 /*
  * clair_linearize for images that live in page-locked HOST memory and whose results are wanted there too (the

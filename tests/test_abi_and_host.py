@@ -58,6 +58,7 @@ def test_argument_validation_without_gpu(native):
     assert rc == -2                                                  # more than CLAIR_MAX_CHANNELS
     with pytest.raises(ValueError):
         native.check(rc, "clair_icrf_forward")
+    assert lib.clair_copy_band_h2d(None, addr, 1, 64, 0, 64, None) == -1 and lib.clair_copy_band_h2d(addr, addr, 1, 64, 32, 64, None) == -1
     assert lib.clair_set_tuning(b"no_such_knob", 1) == -1
     import re
     header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "clair_b200.h")).read()

@@ -1029,6 +1029,29 @@ def test_pair_drivers_from_integer_codes_are_bit_identical(ct, bits):
     assert max_rel(losses[0], losses[1], 1e-6) < 1e-5
 
 
+def test_measure_linearity_pipelines_large_pinned_code_batches(ct):
+    """A page-locked code batch of more than 64 MB is cut into row bands whose copies overlap the expansion and the statistics of
+    the bands already on the device: same result as the whole batch (summation order aside), for a band count that divides
+    the height and with the fallback when none does."""
+    from clair_torch_b200.datasets import StdSpec
+    import importlib
+    ml = importlib.import_module("clair_torch_b200.inference.measure_linearity")     # (the package re-exports the function)
+    model = _model(ct, ct.synthetic.reference_curve(3).numpy())
+    for h, w, expect in ((1024, 1408, 8), (1021, 1416, 0)):
+        val, _, t = ct.synthetic.make_stack(8, 3, h, w, bits=16, seed=h, std_multiplier=None)
+        codes = torch.round(val * 65535.0).to(torch.int32).to(torch.uint16)
+        del val
+        spec = StdSpec("multiplier", 0.05)
+        exposures = {"exposure_time": torch.as_tensor(np.asarray(t, dtype=np.float64))}
+        assert ml._code_bands(codes.pin_memory(), spec) == expect and ml._code_bands(codes, spec) == 0
+        batch = lambda v: DataLoader([0], batch_size=1, collate_fn=lambda _: (torch.arange(8), v, spec, exposures))
+        got = ct.measure_linearity(batch(codes.pin_memory()), DEV, True, True, model)
+        want = ct.measure_linearity(batch(codes.to(DEV)), DEV, True, True, model)
+        assert torch.equal(got[0], want[0])
+        for a, b in zip(got[1:], want[1:]):
+            assert max_rel(a.cpu().numpy(), b.cpu().numpy()) < 2e-6
+
+
 # ---- streaming frame statistics (SURVEY.md 8(f) rank 3) -------------------------------------------------
 def test_wbomeanvar_golden(ct):
     from clair_torch_b200.common.statistics import WBOMeanVar
